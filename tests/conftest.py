@@ -1,0 +1,95 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class Golden:
+    """One tests/golden/*.npz fixture; ``g.inp(key)`` / ``g.out(key)`` give torch CPU tensors."""
+
+    def __init__(self, name):
+        self.name = name
+        self._z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+    def keys(self):
+        return list(self._z.keys())
+
+    def raw(self, key):
+        return torch.from_numpy(np.ascontiguousarray(self._z[key]))
+
+    def inp(self, key):
+        return self.raw("in." + key)
+
+    def out(self, key):
+        return self.raw("out." + key)
+
+    def group(self, prefix):
+        p = prefix + "."
+        return {k[len(p):]: self.raw(k) for k in self._z.keys() if k.startswith(p)}
+
+
+@pytest.fixture(scope="session")
+def golden():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = Golden(name)
+        return cache[name]
+
+    return get
+
+
+STEP_CASES = ["step_aligned", "step_random", "step_T10", "step_eval_reset", "step_no_early_term"]
+
+
+def assert_close(actual, expected, rtol=1e-5, atol=1e-6, what=""):
+    """|a-e| <= atol + rtol*|e| elementwise, with a readable report of the worst entry."""
+    a = torch.as_tensor(actual).detach().cpu().double()
+    e = torch.as_tensor(expected).detach().cpu().double()
+    assert a.shape == e.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(e.shape)}"
+    nan_a, nan_e = torch.isnan(a), torch.isnan(e)
+    assert torch.equal(nan_a, nan_e), f"{what}: NaN pattern differs ({int(nan_a.sum())} vs {int(nan_e.sum())})"
+    a = torch.where(nan_a, torch.zeros_like(a), a)
+    e = torch.where(nan_e, torch.zeros_like(e), e)
+    err = (a - e).abs()
+    tol = atol + rtol * e.abs()
+    bad = err > tol
+    if bad.any():
+        worst = torch.argmax(err - tol)
+        idx = np.unravel_index(int(worst), a.shape) if a.dim() else ()
+        raise AssertionError(
+            f"{what}: {int(bad.sum())}/{a.numel()} outside rtol={rtol} atol={atol}; worst at {idx}: "
+            f"got {a.flatten()[worst].item():.9g} want {e.flatten()[worst].item():.9g} "
+            f"(abs err {err.flatten()[worst].item():.3g})"
+        )
+
+
+def assert_equal_exact(actual, expected, what=""):
+    a = torch.as_tensor(actual).detach().cpu()
+    e = torch.as_tensor(expected).detach().cpu()
+    assert a.shape == e.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(e.shape)}"
+    if not torch.equal(a.to(e.dtype), e):
+        diff = (a.to(torch.int64) != e.to(torch.int64)).nonzero().flatten()[:8].tolist()
+        raise AssertionError(f"{what}: {int((a.to(torch.int64) != e.to(torch.int64)).sum())} mismatches, first at {diff}")

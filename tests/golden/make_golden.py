@@ -1,0 +1,310 @@
+"""Generate the golden fixtures in this directory by running the REFERENCE's own functions.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every fixture is an ``.npz`` holding seeded inputs (``in.*``) and the outputs
+(``out.*``) of the unmodified reference functions on CPU fp32:
+``MotionLibBase.get_motion_state`` / ``_calc_frame_blend`` (PHC/motion_lib.py:549,655),
+``compute_humanoid_observations_smpl_max`` / ``compute_imitation_observations_v6`` /
+``compute_imitation_reward`` / ``compute_humanoid_im_reset`` (PHC/envs/common.py:23,107,
+271,326), ``torch_utils.slerp`` (:110) and ``RunningNorm.update``
+(PHC/policies/running_norm.py:23), orchestrated as ``HumanoidPHC.step`` does
+(PHC/envs/humanoid_phc.py:138-149).  The reference has no tests or vectors of its own
+(SURVEY §4), so these are the pin for ``oracle/phc_oracle.py`` and for the CUDA path.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from humanoid_b200 import synth  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+ref_tu, ref_common, ref_ml = ref_loader.load()
+
+RWD = dict(
+    k_pos=100.0, k_rot=10.0, k_vel=0.1, k_ang_vel=0.1, w_pos=0.5, w_rot=0.3, w_vel=0.1, w_ang_vel=0.1,
+    imitation_reward_dim=4, full_body_reward=True, use_power_reward=True,
+)  # fmt: skip
+DT = synth.SIM_DT
+EVAL_BODY_IDS = [i for i in range(24) if i not in (4, 8, 18, 23)]  # body_sets.py:57 (no hands/toes)
+
+MOTION_KEYS = (
+    "root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "motion_aa",
+    "rg_pos", "rb_rot", "body_vel", "body_ang_vel", "motion_bodies", "motion_limb_weights",
+)  # fmt: skip
+
+
+def npify(d, prefix):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, torch.Tensor):
+            out[f"{prefix}.{k}"] = v.detach().cpu().numpy()
+        else:
+            out[f"{prefix}.{k}"] = np.asarray(v)
+    return out
+
+
+def ref_query(lib_data, ids, times, offset):
+    lib = ref_loader.make_reference_lib(lib_data)
+    return lib.get_motion_state(ids, times, offset)
+
+
+def reference_step(lib, state, clock, term_dist, time_steps=1, reset_body_ids=None, use_mean=False, early=True):
+    """The post-physics half of HumanoidPHC.step with the reference's functions."""
+    J = 24
+    pos, rot, vel, ang = synth.body_views(state, J)
+    progress = clock.progress_buf.clone()
+    progress += 1  # humanoid_phc.py:138
+    out = {}
+
+    t = progress * DT + clock.motion_start_times + clock.motion_start_times_offset  # :1236
+    ref = lib.get_motion_state(clock.sampled_motion_ids, t, clock.global_offset)
+    motion_len = lib._motion_lengths[clock.sampled_motion_ids]
+    nf = lib._motion_num_frames[clock.sampled_motion_ids]
+    mdt = lib._motion_dt[clock.sampled_motion_ids]
+    i0, i1, bl = lib._calc_frame_blend(t, motion_len, nf, mdt)
+    out.update({"t0": t, "t0.frame_idx0": i0, "t0.frame_idx1": i1, "t0.blend": bl})
+    for k in MOTION_KEYS:
+        out[f"t0.{k}"] = ref[k]
+
+    reward, raw = ref_common.compute_imitation_reward(
+        pos[:, 0], rot[:, 0], pos, rot, vel, ang,
+        ref["rg_pos"], ref["rb_rot"], ref["body_vel"], ref["body_ang_vel"], RWD,
+    )  # fmt: skip
+    out["reward"], out["reward_raw"] = reward, raw
+
+    rb = torch.arange(J) if reset_body_ids is None else torch.tensor(reset_body_ids)
+    pass_time = t >= motion_len  # :1317 (ids == arange there; length[id] in general)
+    reset, term = ref_common.compute_humanoid_im_reset(
+        torch.ones(state.shape[0], dtype=torch.bool), progress,
+        torch.zeros(state.shape[0], J, 3), torch.zeros(4, dtype=torch.long),
+        pos[:, rb].clone(), ref["rg_pos"][:, rb].clone(), pass_time, early, term_dist[rb], use_mean,
+    )  # fmt: skip
+    out["reset"], out["terminated"], out["pass_time"] = reset, term, pass_time
+
+    self_obs = ref_common.compute_humanoid_observations_smpl_max(
+        pos, rot, vel, ang, None, None, True, True, True, False, False
+    )
+    out["self_obs"] = self_obs
+
+    refs = []
+    for k in range(1, time_steps + 1):
+        tk = (progress + k) * DT + clock.motion_start_times + clock.motion_start_times_offset  # :1063-1067
+        r = lib.get_motion_state(clock.sampled_motion_ids, tk, clock.global_offset)
+        refs.append(r)
+        if k == 1:
+            i0, i1, bl = lib._calc_frame_blend(tk, motion_len, nf, mdt)
+            out.update({"t1": tk, "t1.frame_idx0": i0, "t1.frame_idx1": i1, "t1.blend": bl})
+            for key in MOTION_KEYS:
+                out[f"t1.{key}"] = r[key]
+
+    def stack(key):
+        return torch.stack([r[key] for r in refs], 1).reshape((-1,) + refs[0][key].shape[1:])
+
+    task = ref_common.compute_imitation_observations_v6(
+        pos[:, 0], rot[:, 0], pos, rot, vel, ang,
+        stack("rg_pos"), stack("rb_rot"), stack("body_vel"), stack("body_ang_vel"), time_steps, True,
+    )  # fmt: skip
+    out["task_obs"] = task
+    out["obs"] = torch.cat([self_obs, task], dim=-1)  # :949
+    out["progress_after"] = progress
+    return out
+
+
+def save(name, arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(arrays)} arrays")
+
+
+def case_step(name, N, M, seed, time_steps=1, reset_body_ids=None, use_mean=False, early=True, term=0.25, **kw):
+    lib_data, clock, state = synth.make_case(N, M, ref_query, seed=seed, device="cpu", **kw)
+    lib = ref_loader.make_reference_lib(lib_data)
+    term_dist = torch.full((24,), term, dtype=torch.float32)
+    out = reference_step(lib, state, clock, term_dist, time_steps, reset_body_ids, use_mean, early)
+    arrays = {}
+    arrays.update(npify(lib_data.as_dict(), "in.lib"))
+    arrays.update(npify(clock.__dict__, "in.clock"))
+    arrays["in.state"] = state.numpy()
+    arrays["in.term_dist"] = term_dist.numpy()
+    arrays["in.time_steps"] = np.asarray(time_steps)
+    arrays["in.use_mean"] = np.asarray(use_mean)
+    arrays["in.early"] = np.asarray(early)
+    arrays["in.reset_body_ids"] = np.asarray(list(range(24)) if reset_body_ids is None else reset_body_ids)
+    arrays.update(npify(out, "out"))
+    save(name, arrays)
+
+
+def case_frame_blend():
+    """Adversarial times for the integer path: exact frame boundaries and +-1 ulp around
+    them, negatives, beyond the clip, zero; 30/60/120 fps; 2-frame and long clips."""
+    rows = []
+    for fps in (30.0, 60.0, 120.0):
+        dt = 1.0 / fps
+        for nf in (2, 3, 17, 60, 300, 7000):
+            length = dt * (nf - 1)
+            ks = sorted(set([0, 1, 2, nf // 2, nf - 2, nf - 1, nf, nf + 5]))
+            for k in ks:
+                base = np.float32(k * (1 / 30)) if fps == 30.0 else np.float32(k * dt)
+                for t in (base, np.nextafter(base, np.float32(np.inf)), np.nextafter(base, np.float32(-np.inf))):
+                    rows.append((float(t), length, nf, dt))
+            for t in (-1.0, -1e-8, 0.0, length, length * 1.0000001, length * 2, 1e-9, 0.5 * dt, 1.5 * dt):
+                rows.append((t, length, nf, dt))
+    g = torch.Generator().manual_seed(5)
+    for _ in range(4000):
+        fps = (30.0, 60.0, 120.0)[int(torch.randint(0, 3, (1,), generator=g))]
+        nf = int(torch.randint(2, 400, (1,), generator=g))
+        dt = 1.0 / fps
+        length = dt * (nf - 1)
+        # progress*dt + start, the env's op order, on frame-aligned starts
+        k = int(torch.randint(0, nf, (1,), generator=g))
+        p = int(torch.randint(0, 300, (1,), generator=g))
+        t = float((torch.tensor([p], dtype=torch.int16) * DT + torch.tensor([k * (1 / 30)], dtype=torch.float32))[0])
+        rows.append((t, length, nf, dt))
+    time = torch.tensor([r[0] for r in rows], dtype=torch.float32)
+    length = torch.tensor([r[1] for r in rows], dtype=torch.float32)
+    nf = torch.tensor([r[2] for r in rows], dtype=torch.int64)
+    dt = torch.tensor([r[3] for r in rows], dtype=torch.float32)
+    lib = object.__new__(ref_ml.MotionLibBase)
+    i0, i1, bl = lib._calc_frame_blend(time, length, nf, dt)
+    save(
+        "frame_blend",
+        {
+            "in.time": time.numpy(), "in.len": length.numpy(), "in.num_frames": nf.numpy(), "in.dt": dt.numpy(),
+            "out.frame_idx0": i0.numpy(), "out.frame_idx1": i1.numpy(), "out.blend": bl.numpy(),
+        },
+    )  # fmt: skip
+
+
+def case_slerp():
+    g = torch.Generator().manual_seed(9)
+    n = 4096
+    q0 = torch.randn(n, 4, generator=g)
+    q0 = q0 / q0.norm(dim=-1, keepdim=True)
+    # small relative rotations of graded size, so every branch is hit
+    ang = torch.exp(torch.rand(n, 1, generator=g) * 16 - 16)  # e^-16 .. 1 rad
+    axis = torch.randn(n, 3, generator=g)
+    axis = axis / axis.norm(dim=-1, keepdim=True)
+    dq = torch.cat([axis * torch.sin(ang / 2), torch.cos(ang / 2)], -1)
+    q1 = ref_tu.quat_mul(q0, dq)
+    q1[::7] = -q1[::7]  # dot < 0
+    q1[::11] = q0[::11]  # identical -> |cos| >= 1 or sin ~ 0
+    q1[5::97] = q0[5::97] * 1.001  # non-unit, cos > 1 -> acos NaN masked by last select
+    rnd = torch.randn(n // 4, 4, generator=g)
+    q1[: n // 4] = rnd / rnd.norm(dim=-1, keepdim=True)  # large angles
+    t = torch.rand(n, 1, generator=g)
+    t[::13] = 0.0
+    t[1::13] = 1.0
+    out = ref_tu.slerp(q0, q1, t)
+    em = ref_tu.quat_to_exp_map(out / out.norm(dim=-1, keepdim=True).clamp_min(1e-9))
+    save("slerp", {"in.q0": q0.numpy(), "in.q1": q1.numpy(), "in.t": t.numpy(), "out.q": out.numpy(),
+                   "in.qn": (out / out.norm(dim=-1, keepdim=True).clamp_min(1e-9)).numpy(), "out.exp_map": em.numpy()})  # fmt: skip
+
+
+def case_flags():
+    """Flag variants of the standalone functions that the env's default path never takes."""
+    lib_data, clock, state = synth.make_case(40, 5, ref_query, seed=99, device="cpu", min_frames=12, max_frames=30)
+    lib = ref_loader.make_reference_lib(lib_data)
+    pos, rot, vel, ang = synth.body_views(state, 24)
+    g = torch.Generator().manual_seed(3)
+    smpl = torch.randn(40, 11, generator=g)
+    limb = torch.randn(40, 10, generator=g)
+    arrays = {"in.state": state.numpy(), "in.smpl": smpl.numpy(), "in.limb": limb.numpy()}
+    variants = {
+        "default": (True, True, True, False, False),
+        "not_upright": (True, True, False, False, False),
+        "global_root": (False, True, True, False, False),
+        "no_height": (True, False, True, False, False),
+        "with_params": (True, True, True, True, True),
+        "all_off": (False, False, False, True, False),
+    }
+    for name, fl in variants.items():
+        o = ref_common.compute_humanoid_observations_smpl_max(pos, rot, vel, ang, smpl, limb, *fl)
+        arrays[f"out.self.{name}"] = o.numpy()
+        arrays[f"in.self.{name}"] = np.asarray(fl)
+    t = synth.reward_time(clock, extra_steps=1)
+    ref = lib.get_motion_state(clock.sampled_motion_ids, t, clock.global_offset)
+    for k in ("rg_pos", "rb_rot", "body_vel", "body_ang_vel"):
+        arrays[f"in.ref.{k}"] = ref[k].numpy()
+    # v6, not upright; and a 12-body tracking subset
+    o = ref_common.compute_imitation_observations_v6(
+        pos[:, 0], rot[:, 0], pos, rot, vel, ang, ref["rg_pos"], ref["rb_rot"], ref["body_vel"], ref["body_ang_vel"], 1, False
+    )  # fmt: skip
+    arrays["out.v6.not_upright"] = o.numpy()
+    sub = torch.arange(0, 24, 2)
+    arrays["in.subset"] = sub.numpy()
+    o = ref_common.compute_imitation_observations_v6(
+        pos[:, 0], rot[:, 0], pos[:, sub], rot[:, sub], vel[:, sub], ang[:, sub],
+        ref["rg_pos"][:, sub], ref["rb_rot"][:, sub], ref["body_vel"][:, sub], ref["body_ang_vel"][:, sub], 1, True,
+    )  # fmt: skip
+    arrays["out.v6.subset12"] = o.numpy()
+    r, raw = ref_common.compute_imitation_reward(
+        pos[:, 0], rot[:, 0], pos[:, sub], rot[:, sub], vel[:, sub], ang[:, sub],
+        ref["rg_pos"][:, sub], ref["rb_rot"][:, sub], ref["body_vel"][:, sub], ref["body_ang_vel"][:, sub], RWD,
+    )  # fmt: skip
+    arrays["out.reward.subset12"], arrays["out.reward_raw.subset12"] = r.numpy(), raw.numpy()
+    # query without offset
+    ref2 = lib.get_motion_state(clock.sampled_motion_ids, t, None)
+    arrays["out.rg_pos.no_offset"] = ref2["rg_pos"].numpy()
+    arrays.update(npify(lib_data.as_dict(), "in.lib"))
+    arrays.update(npify(clock.__dict__, "in.clock"))
+    arrays["in.t"] = t.numpy()
+    save("flags", arrays)
+
+
+def case_running_norm():
+    # the policies package __init__ pulls in pufferlib (absent); load the one file directly
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "ref_running_norm", os.path.join(ref_loader.REFERENCE_ROOT, "puffer_phc/policies/running_norm.py")
+    )
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    RunningNorm = mod.RunningNorm
+
+    g = torch.Generator().manual_seed(21)
+    rn = RunningNorm(934)
+    x1 = torch.randn(192, 934, generator=g) * 3 + 1.5
+    x2 = torch.randn(160, 934, generator=g) * 0.2 - 4.0
+    arrays = {"in.x1": x1.numpy(), "in.x2": x2.numpy()}
+    rn.update(x1)
+    arrays["out.mean1"], arrays["out.var1"], arrays["out.count1"] = (
+        rn.running_mean.numpy().copy(), rn.running_var.numpy().copy(), rn.count.numpy().copy())  # fmt: skip
+    rn.update(x2)
+    arrays["out.mean2"], arrays["out.var2"], arrays["out.count2"] = (
+        rn.running_mean.numpy().copy(), rn.running_var.numpy().copy(), rn.count.numpy().copy())  # fmt: skip
+    arrays["out.fwd"] = rn(x2[:32]).numpy()
+    save("running_norm", arrays)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    # the reference regime: ids == arange, 30 fps clips, frame-aligned starts
+    case_step("step_aligned", N=32, M=32, seed=11, min_frames=8, max_frames=16, max_progress=10)
+    # config-4 style: random ids over a shared library, mixed fps, unaligned times, i.i.d. rotations
+    case_step("step_random", N=64, M=7, seed=12, min_frames=10, max_frames=40, fps_choices=(30, 60, 120),
+              ids="random", aligned=False, rot_regime="random", max_progress=6)  # fmt: skip
+    # config-5 style: 10 future frames
+    case_step("step_T10", N=24, M=6, seed=13, time_steps=10, min_frames=20, max_frames=40, max_progress=20)
+    # eval-mode reset: mean over the 20 EVAL_BODIES (humanoid_phc.py:1431-1437); the threshold is
+    # 0.15 m here instead of 0.5 m so that the synthetic noise produces both outcomes
+    case_step("step_eval_reset", N=48, M=6, seed=14, min_frames=10, max_frames=30, reset_body_ids=EVAL_BODY_IDS,
+              use_mean=True, term=0.15, max_progress=6)  # fmt: skip
+    case_step("step_no_early_term", N=16, M=4, seed=15, min_frames=6, max_frames=12, early=False, max_progress=14)
+    case_frame_blend()
+    case_slerp()
+    case_flags()
+    case_running_norm()

@@ -1,0 +1,130 @@
+"""CPU: the oracle restatement against the fixtures produced by the reference itself."""
+
+import pytest
+import torch
+
+from conftest import STEP_CASES, assert_close, assert_equal_exact
+from humanoid_b200 import synth
+from oracle import phc_oracle as O
+
+# same torch build => bit-exact; a tiny tolerance keeps a different host ISA from breaking the pin
+TIGHT = dict(rtol=1e-6, atol=1e-7)
+
+MOTION_KEYS = (
+    "root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "motion_aa",
+    "rg_pos", "rb_rot", "body_vel", "body_ang_vel", "motion_bodies", "motion_limb_weights",
+)  # fmt: skip
+
+
+def _lib(g):
+    return O.OracleMotionLib(g.group("in.lib"))
+
+
+def test_frame_blend_bit_exact(golden):
+    g = golden("frame_blend")
+    i0, i1, bl = O.frame_blend(g.inp("time"), g.inp("len"), g.inp("num_frames"), g.inp("dt"))
+    assert_equal_exact(i0, g.out("frame_idx0"), "frame_idx0")
+    assert_equal_exact(i1, g.out("frame_idx1"), "frame_idx1")
+    assert torch.equal(bl, g.out("blend"))
+
+
+def test_slerp_and_exp_map(golden):
+    g = golden("slerp")
+    q = O.slerp(g.inp("q0"), g.inp("q1"), g.inp("t"))
+    assert_close(q, g.out("q"), what="slerp", **TIGHT)
+    assert_close(O.exp_map(g.inp("qn")), g.out("exp_map"), what="exp_map", **TIGHT)
+
+
+@pytest.mark.parametrize("case", STEP_CASES)
+def test_step_against_reference_fixture(golden, case):
+    g = golden(case)
+    lib = _lib(g)
+    c = g.group("in.clock")
+    T = int(g.inp("time_steps"))
+    progress = c["progress_buf"].clone()
+    obs, reward, raw, reset, term = O.step(
+        lib, g.inp("state"), progress, c["motion_start_times"], c["motion_start_times_offset"],
+        c["global_offset"], c["sampled_motion_ids"], g.inp("term_dist"), synth.SIM_DT,
+        reset_body_ids=g.inp("reset_body_ids"), use_mean=bool(g.inp("use_mean")),
+        enable_early_termination=bool(g.inp("early")), time_steps=T,
+    )  # fmt: skip
+    assert_equal_exact(progress, g.out("progress_after"), "progress")
+    assert_equal_exact(reset, g.out("reset"), "reset")
+    assert_equal_exact(term, g.out("terminated"), "terminated")
+    assert_close(obs, g.out("obs"), what="obs", **TIGHT)
+    assert_close(reward, g.out("reward"), what="reward", **TIGHT)
+    assert_close(raw, g.out("reward_raw"), what="reward_raw", **TIGHT)
+    # the fixture must actually exercise both outcomes somewhere in the suite
+    assert obs.shape[1] == 358 + 576 * T
+
+
+@pytest.mark.parametrize("case", STEP_CASES)
+@pytest.mark.parametrize("which", ["t0", "t1"])
+def test_motion_state_against_reference_fixture(golden, case, which):
+    g = golden(case)
+    lib = _lib(g)
+    c = g.group("in.clock")
+    res = lib.get_motion_state(c["sampled_motion_ids"], g.out(which), c["global_offset"])
+    assert_equal_exact(res["frame_idx0"], g.out(f"{which}.frame_idx0"), "frame_idx0")
+    assert_equal_exact(res["frame_idx1"], g.out(f"{which}.frame_idx1"), "frame_idx1")
+    for k in MOTION_KEYS:
+        assert_close(res[k], g.out(f"{which}.{k}"), what=k, **TIGHT)
+
+
+def test_flag_variants(golden):
+    g = golden("flags")
+    pos, rot, vel, ang = synth.body_views(g.inp("state"))
+    for name in ("default", "not_upright", "global_root", "no_height", "with_params", "all_off"):
+        fl = [bool(x) for x in g.inp(f"self.{name}")]
+        o = O.self_obs_smpl_max(pos, rot, vel, ang, g.inp("smpl"), g.inp("limb"), *fl)
+        assert_close(o, g.out(f"self.{name}"), what=f"self obs {name}", **TIGHT)
+    ref = g.group("in.ref")
+    o = O.imitation_obs_v6(pos[:, 0], rot[:, 0], pos, rot, vel, ang,
+                           ref["rg_pos"], ref["rb_rot"], ref["body_vel"], ref["body_ang_vel"], 1, False)  # fmt: skip
+    assert_close(o, g.out("v6.not_upright"), what="v6 not upright", **TIGHT)
+    s = g.inp("subset")
+    o = O.imitation_obs_v6(pos[:, 0], rot[:, 0], pos[:, s], rot[:, s], vel[:, s], ang[:, s], ref["rg_pos"][:, s],
+                           ref["rb_rot"][:, s], ref["body_vel"][:, s], ref["body_ang_vel"][:, s], 1, True)  # fmt: skip
+    assert_close(o, g.out("v6.subset12"), what="v6 subset", **TIGHT)
+    r, raw = O.imitation_reward(pos[:, 0], rot[:, 0], pos[:, s], rot[:, s], vel[:, s], ang[:, s], ref["rg_pos"][:, s],
+                                ref["rb_rot"][:, s], ref["body_vel"][:, s], ref["body_ang_vel"][:, s],
+                                O.DEFAULT_RWD_SPECS)  # fmt: skip
+    assert_close(r, g.out("reward.subset12"), what="reward subset", **TIGHT)
+    assert_close(raw, g.out("reward_raw.subset12"), what="reward_raw subset", **TIGHT)
+    lib = _lib(g)
+    res = lib.get_motion_state(g.inp("clock.sampled_motion_ids"), g.inp("t"), None)
+    assert_close(res["rg_pos"], g.out("rg_pos.no_offset"), what="no offset", **TIGHT)
+
+
+def test_v7_is_the_documented_v6_column_subset(golden):
+    g = golden("step_T10")
+    T = int(g.inp("time_steps"))
+    cols = O.v7_columns(24, T)
+    assert cols.numel() == T * 24 * 9
+    v6 = g.out("task_obs")
+    blk = v6.view(v6.shape[0], T, 576)
+    want = torch.cat([blk[..., 0:72], blk[..., 216:288], blk[..., 360:432]], dim=-1).reshape(v6.shape[0], -1)
+    assert torch.equal(v6[:, cols], want)
+
+
+def test_running_norm(golden):
+    g = golden("running_norm")
+    m, v, c = torch.zeros(1, 934), torch.ones(1, 934), torch.ones(1)
+    m, v, c = O.running_norm_update(m, v, c, g.inp("x1"))
+    assert_close(m, g.out("mean1"), what="mean1", **TIGHT)
+    assert_close(v, g.out("var1"), what="var1", **TIGHT)
+    m, v, c = O.running_norm_update(m, v, c, g.inp("x2"))
+    assert_close(m, g.out("mean2"), what="mean2", **TIGHT)
+    assert_close(v, g.out("var2"), what="var2", **TIGHT)
+    assert float(c) == float(g.out("count2"))
+    assert_close(O.running_norm_forward(m, v, g.inp("x2")[:32]), g.out("fwd"), what="fwd", **TIGHT)
+
+
+def test_fixtures_exercise_both_flag_values(golden):
+    seen_reset, seen_term, seen_pass = set(), set(), set()
+    for case in STEP_CASES:
+        g = golden(case)
+        seen_reset |= set(g.out("reset").tolist())
+        seen_term |= set(g.out("terminated").tolist())
+        seen_pass |= set(g.out("pass_time").tolist())
+    assert seen_reset == {True, False} and seen_term == {True, False} and seen_pass == {True, False}

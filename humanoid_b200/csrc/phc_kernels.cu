@@ -1,0 +1,987 @@
+// libphc_b200.so — hand-written sm_100a kernels of the PHC step path behind the C ABI in
+// include/phc_b200.h.  No tensor cores (nothing here is a dense contraction): the path is
+// gather + stream + per-body quaternion math, bounded by HBM bandwidth and fp32 issue.
+//
+// Thread mapping everywhere: one thread per (env, body); 24 consecutive threads own one
+// env, so an 8-env block is 192 threads = 6 full warps with no idle lanes.  Per-env
+// reductions (reward means, termination any/mean) go through shared memory in ATen's CPU
+// summation order, so the result does not depend on how envs fall on warps.
+//
+// Compiled with -fmad=false (see phc_math.cuh).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include <cuda_runtime.h>
+
+#include "../../include/phc_b200.h"
+#include "phc_math.cuh"
+
+namespace phc {
+
+constexpr int J24 = PHC_NUM_BODIES;
+constexpr int SELF_DIM = PHC_SELF_OBS_DIM;
+constexpr int TASK_DIM = PHC_TASK_OBS_DIM;
+
+static thread_local int g_last_cuda_error = 0;
+
+static inline int cuda_fail(cudaError_t e) {
+  g_last_cuda_error = (int)e;
+  return PHC_ERR_CUDA;
+}
+#define PHC_CUDA(call)                              \
+  do {                                              \
+    cudaError_t e__ = (call);                       \
+    if (e__ != cudaSuccess) return cuda_fail(e__);  \
+  } while (0)
+
+static inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PHC_OK : cuda_fail(e);
+}
+
+struct LibDev {
+  const float *gts, *grs, *lrs, *gvs, *gavs, *dvs, *aa;
+  const float *len, *mdt, *bodies, *limb;
+  const int64_t *nf, *starts;
+  int64_t F, M;
+};
+
+// ---------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ Vec3 ld3(const float* p) { return {p[0], p[1], p[2]}; }
+__device__ __forceinline__ Quat ld4(const float* p) { return {p[0], p[1], p[2], p[3]}; }
+__device__ __forceinline__ Quat ld4v(const float* p) {  // 16-byte aligned
+  float4 v = *reinterpret_cast<const float4*>(p);
+  return {v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ void st3(float* p, Vec3 v) {
+  p[0] = v.x;
+  p[1] = v.y;
+  p[2] = v.z;
+}
+__device__ __forceinline__ void st4(float* p, Quat q) {
+  p[0] = q.x;
+  p[1] = q.y;
+  p[2] = q.z;
+  p[3] = q.w;
+}
+__device__ __forceinline__ const float* view_at(const PhcView& v, int64_t env, int body) {
+  return v.ptr + env * v.stride_env + (int64_t)body * v.stride_body;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// per-(query) reference body state
+struct RefBody {
+  Vec3 pos;
+  Quat rot;
+  Vec3 vel;
+  Vec3 ang;
+};
+
+// ---------------------------------------------------------------------------------------
+// K0: _calc_frame_blend (motion_lib.py:655-665)
+// ---------------------------------------------------------------------------------------
+__global__ void frame_blend_kernel(const float* __restrict__ time, const float* __restrict__ len,
+                                   const int64_t* __restrict__ nf, const float* __restrict__ dt, int64_t n,
+                                   int64_t* __restrict__ i0, int64_t* __restrict__ i1, float* __restrict__ bl) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t a, b;
+  float w;
+  calc_frame_blend(time[i], len[i], nf[i], dt[i], a, b, w);
+  i0[i] = a;
+  i1[i] = b;
+  bl[i] = w;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: get_motion_state (motion_lib.py:549-626), one thread per (query, body)
+// ---------------------------------------------------------------------------------------
+constexpr int K1_QPB = 8;  // queries per block
+
+__global__ void __launch_bounds__(K1_QPB* J24)
+    motion_state_kernel(LibDev L, const int64_t* __restrict__ ids, const float* __restrict__ times,
+                        const float* __restrict__ offset, int64_t n, PhcMotionOut o) {
+  const int e = threadIdx.x / J24, b = threadIdx.x % J24;
+  const int64_t q = (int64_t)blockIdx.x * K1_QPB + e;
+  if (q >= n) return;
+  const int64_t id = ids[q];
+  int64_t i0, i1;
+  float bl;
+  calc_frame_blend(times[q], L.len[id], L.nf[id], L.mdt[id], i0, i1, bl);
+  const int64_t st = L.starts[id];
+  const int64_t f0 = i0 + st, f1 = i1 + st;
+  const float om = 1.0f - bl;
+
+  if (b == 0) {
+    if (o.frame_idx0) o.frame_idx0[q] = i0;
+    if (o.frame_idx1) o.frame_idx1[q] = i1;
+    if (o.blend) o.blend[q] = bl;
+  }
+  // positions (+ offset), velocities
+  if (o.rg_pos || (o.root_pos && b == 0)) {
+    Vec3 p = lerp3(om, bl, ld3(L.gts + (f0 * J24 + b) * 3), ld3(L.gts + (f1 * J24 + b) * 3));
+    if (offset) p = p + ld3(offset + q * 3);
+    if (o.rg_pos) st3(o.rg_pos + (q * J24 + b) * 3, p);
+    if (o.root_pos && b == 0) st3(o.root_pos + q * 3, p);
+  }
+  if (o.body_vel || (o.root_vel && b == 0)) {
+    Vec3 v = lerp3(om, bl, ld3(L.gvs + (f0 * J24 + b) * 3), ld3(L.gvs + (f1 * J24 + b) * 3));
+    if (o.body_vel) st3(o.body_vel + (q * J24 + b) * 3, v);
+    if (o.root_vel && b == 0) st3(o.root_vel + q * 3, v);
+  }
+  if (o.body_ang_vel || (o.root_ang_vel && b == 0)) {
+    Vec3 v = lerp3(om, bl, ld3(L.gavs + (f0 * J24 + b) * 3), ld3(L.gavs + (f1 * J24 + b) * 3));
+    if (o.body_ang_vel) st3(o.body_ang_vel + (q * J24 + b) * 3, v);
+    if (o.root_ang_vel && b == 0) st3(o.root_ang_vel + q * 3, v);
+  }
+  if (o.rb_rot || (o.root_rot && b == 0)) {
+    Quat r = quat_slerp(ld4v(L.grs + (f0 * J24 + b) * 4), ld4v(L.grs + (f1 * J24 + b) * 4), bl);
+    if (o.rb_rot) st4(o.rb_rot + (q * J24 + b) * 4, r);
+    if (o.root_rot && b == 0) st4(o.root_rot + q * 4, r);
+  }
+  if (o.dof_pos && b >= 1) {  // _local_rotation_to_dof_smpl, motion_lib.py:670-673
+    Quat r = quat_slerp(ld4v(L.lrs + (f0 * J24 + b) * 4), ld4v(L.lrs + (f1 * J24 + b) * 4), bl);
+    st3(o.dof_pos + q * 69 + (b - 1) * 3, quat_exp_map(r));
+  }
+  if (o.dof_vel && b < 23) {
+    Vec3 v = lerp3(om, bl, ld3(L.dvs + (f0 * 23 + b) * 3), ld3(L.dvs + (f1 * 23 + b) * 3));
+    st3(o.dof_vel + q * 69 + b * 3, v);
+  }
+  if (o.motion_aa) st3(o.motion_aa + q * 72 + b * 3, ld3(L.aa + f0 * 72 + b * 3));  // frame f0, un-blended
+  if (o.motion_bodies && b < 17) o.motion_bodies[q * 17 + b] = L.bodies[id * 17 + b];
+  if (o.motion_limb_weights && b < 10) o.motion_limb_weights[q * 10 + b] = L.limb[id * 10 + b];
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: compute_humanoid_observations_smpl_max (envs/common.py:23-103), thread per (env, body)
+// ---------------------------------------------------------------------------------------
+__global__ void self_obs_kernel(PhcBodyState s, int64_t n, uint32_t flags, float* __restrict__ out,
+                                int64_t out_stride, int epb) {
+  const int J = s.num_bodies;
+  const int e = threadIdx.x / J, b = threadIdx.x % J;
+  const int64_t env = (int64_t)blockIdx.x * epb + e;
+  if (e >= epb || env >= n) return;
+  const Vec3 root_pos = ld3(view_at(s.pos, env, 0));
+  Quat root_rot = ld4(view_at(s.rot, env, 0));
+  if (!(flags & PHC_OBS_UPRIGHT)) root_rot = remove_base_rot(root_rot);
+  const Heading hi = heading_quat_inv(root_rot);
+  const float hs = heading_scale(hi);
+  float* row = out + env * out_stride;
+  int col = 0;
+  if (flags & PHC_OBS_ROOT_HEIGHT) {
+    if (b == 0) row[0] = root_pos.z;
+    col = 1;
+  }
+  if (b >= 1) st3(row + col + (b - 1) * 3, heading_rotate(hi, hs, ld3(view_at(s.pos, env, b)) - root_pos));
+  col += (J - 1) * 3;
+  {
+    float t6[6];
+    if (b == 0 && !(flags & PHC_OBS_LOCAL_ROOT)) {
+      // "if not local_root_obs: root_rot_obs = quat_to_tan_norm(root_rot)" (common.py:76-78);
+      // root_rot there is the (possibly base-rot-removed) root rotation
+      quat_tan_norm(root_rot, t6);
+    } else {
+      quat_tan_norm(heading_mul_left(hi, ld4(view_at(s.rot, env, b))), t6);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) row[col + b * 6 + k] = t6[k];
+  }
+  col += J * 6;
+  st3(row + col + b * 3, heading_rotate(hi, hs, ld3(view_at(s.vel, env, b))));
+  col += J * 3;
+  st3(row + col + b * 3, heading_rotate(hi, hs, ld3(view_at(s.ang_vel, env, b))));
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: compute_imitation_observations_v6 (envs/common.py:106-176), thread per (env, t, body)
+// mode 7 = column subset [d_pos | d_vel | l_pos]
+// ---------------------------------------------------------------------------------------
+struct TaskObs {  // one body's 24 floats of a v6 block
+  Vec3 d_pos;
+  float d_rot[6];
+  Vec3 d_vel, d_ang, l_pos;
+  float l_rot[6];
+};
+
+__device__ __forceinline__ void task_obs_body(Heading hi, float hs, Vec3 root_pos, Vec3 pos, Quat rot, Vec3 vel,
+                                              Vec3 ang, const RefBody& r, bool full, TaskObs& o) {
+  o.d_pos = heading_rotate(hi, hs, r.pos - pos);
+  o.d_vel = heading_rotate(hi, hs, r.vel - vel);
+  o.l_pos = heading_rotate(hi, hs, r.pos - root_pos);
+  if (full) {
+    o.d_ang = heading_rotate(hi, hs, r.ang - ang);
+    Quat dg = quat_mul(r.rot, quat_conj(rot));
+    Quat dl = heading_mul_right(heading_mul_left(hi, dg), heading_conj(hi));
+    quat_tan_norm(dl, o.d_rot);
+    quat_tan_norm(heading_mul_left(hi, r.rot), o.l_rot);
+  }
+}
+
+__global__ void imitation_obs_kernel(const float* __restrict__ root_pos, int64_t rp_stride,
+                                     const float* __restrict__ root_rot, int64_t rr_stride, PhcBodyState s,
+                                     PhcBodyState ref, int64_t n, int T, int upright, int mode,
+                                     float* __restrict__ out, int64_t out_stride) {
+  const int J = s.num_bodies;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = n * T * J;
+  if (gid >= total) return;
+  const int b = (int)(gid % J);
+  const int64_t et = gid / J;  // env * T + t
+  const int t = (int)(et % T);
+  const int64_t env = et / T;
+  Quat rr = ld4(root_rot + env * rr_stride);
+  if (!upright) rr = remove_base_rot(rr);
+  const Heading hi = heading_quat_inv(rr);
+  const float hs = heading_scale(hi);
+  RefBody r;
+  r.pos = ld3(view_at(ref.pos, et, b));
+  r.rot = ld4(view_at(ref.rot, et, b));
+  r.vel = ld3(view_at(ref.vel, et, b));
+  r.ang = ld3(view_at(ref.ang_vel, et, b));
+  TaskObs o;
+  task_obs_body(hi, hs, ld3(root_pos + env * rp_stride), ld3(view_at(s.pos, env, b)), ld4(view_at(s.rot, env, b)),
+                ld3(view_at(s.vel, env, b)), ld3(view_at(s.ang_vel, env, b)), r, mode == 6, o);
+  if (mode == 6) {
+    float* row = out + env * out_stride + (int64_t)t * (24 * J);
+    st3(row + b * 3, o.d_pos);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) row[3 * J + b * 6 + k] = o.d_rot[k];
+    st3(row + 9 * J + b * 3, o.d_vel);
+    st3(row + 12 * J + b * 3, o.d_ang);
+    st3(row + 15 * J + b * 3, o.l_pos);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) row[18 * J + b * 6 + k] = o.l_rot[k];
+  } else {
+    float* row = out + env * out_stride + (int64_t)t * (9 * J);
+    st3(row + b * 3, o.d_pos);
+    st3(row + 3 * J + b * 3, o.d_vel);
+    st3(row + 6 * J + b * 3, o.l_pos);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// reward / reset per-body pieces shared by K4, K5 and the fused step
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void reward_partials(Vec3 pos, Quat rot, Vec3 vel, Vec3 ang, const RefBody& r,
+                                                float& sp, float& sr, float& sv, float& sa) {
+  sp = mean_sq3(r.pos - pos);  // (d**2).mean(-1), common.py:299
+  Quat dq = quat_mul(r.rot, quat_conj(rot));
+  float a = quat_angle(dq.w);
+  sr = a * a;
+  sv = mean_sq3(r.vel - vel);
+  sa = mean_sq3(r.ang - ang);
+}
+
+// one env's reward from the four per-body rows (ATen row-sum order), common.py:298-320
+__device__ __forceinline__ float reward_term(const float* row, int J, float k) {
+  float d = row_sum8(row, J) / (float)J;
+  return expf((-k) * d);
+}
+
+constexpr int GEN_MAX_J = 32;
+
+__global__ void reward_kernel(PhcBodyState s, PhcBodyState ref, int64_t n, PhcRewardSpec spec,
+                              float* __restrict__ reward, float* __restrict__ raw, int64_t raw_stride, int epb) {
+  extern __shared__ float sm[];  // [epb][4][J] partials, [epb][4] terms
+  const int J = s.num_bodies;
+  const int e = threadIdx.x / J, b = threadIdx.x % J;
+  const int64_t env = (int64_t)blockIdx.x * epb + e;
+  const bool valid = e < epb && env < n;
+  float* part = sm;
+  float* terms = sm + epb * 4 * J;
+  if (valid) {
+    RefBody r;
+    r.pos = ld3(view_at(ref.pos, env, b));
+    r.rot = ld4(view_at(ref.rot, env, b));
+    r.vel = ld3(view_at(ref.vel, env, b));
+    r.ang = ld3(view_at(ref.ang_vel, env, b));
+    float sp, sr, sv, sa;
+    reward_partials(ld3(view_at(s.pos, env, b)), ld4(view_at(s.rot, env, b)), ld3(view_at(s.vel, env, b)),
+                    ld3(view_at(s.ang_vel, env, b)), r, sp, sr, sv, sa);
+    part[(e * 4 + 0) * J + b] = sp;
+    part[(e * 4 + 1) * J + b] = sr;
+    part[(e * 4 + 2) * J + b] = sv;
+    part[(e * 4 + 3) * J + b] = sa;
+  }
+  __syncthreads();
+  if (valid && b < 4) {
+    const float k = b == 0 ? spec.k_pos : b == 1 ? spec.k_rot : b == 2 ? spec.k_vel : spec.k_ang_vel;
+    float t = reward_term(part + (e * 4 + b) * J, J, k);
+    terms[e * 4 + b] = t;
+    raw[env * raw_stride + b] = t;
+  }
+  __syncthreads();
+  if (valid && b == 0) {
+    const float* t = terms + e * 4;
+    reward[env] = spec.w_pos * t[0] + spec.w_rot * t[1] + spec.w_vel * t[2] + spec.w_ang_vel * t[3];
+  }
+}
+
+__global__ void reset_kernel(PhcView pos, PhcView ref, int R, const int16_t* __restrict__ progress,
+                             const uint8_t* __restrict__ pass_time, const float* __restrict__ term_dist, int early,
+                             int use_mean, int64_t n, uint8_t* __restrict__ reset, uint8_t* __restrict__ terminated,
+                             int epb) {
+  extern __shared__ float sm[];  // [epb][R] distances
+  const int e = threadIdx.x / R, b = threadIdx.x % R;
+  const int64_t env = (int64_t)blockIdx.x * epb + e;
+  const bool valid = e < epb && env < n;
+  if (valid) sm[e * R + b] = norm3(ld3(view_at(pos, env, b)) - ld3(view_at(ref, env, b)));
+  __syncthreads();
+  if (valid && b == 0) {
+    bool fallen = false;
+    if (early) {
+      const float* d = sm + e * R;
+      if (use_mean) {
+        fallen = (row_sum8(d, R) / (float)R) > term_dist[0];
+      } else {
+        for (int j = 0; j < R; ++j) fallen = fallen || (d[j] > term_dist[j]);
+      }
+      fallen = fallen && (progress[env] > 1);
+    }
+    terminated[env] = fallen ? 1 : 0;
+    reset[env] = pass_time[env] ? 1 : (fallen ? 1 : 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6: the fused step.  One block = EPB envs x 24 bodies.
+//   phase 0  sim tile -> smem (cp.async 16 B when the four views are one 16-B aligned AoS-13
+//            tensor; strided scalar loads otherwise); env leaders advance the clock and run
+//            the frame-blend for t, t+dt .. t+T*dt
+//   phase 1  frames(t) -> smem; per body: lerp/slerp -> reference state, reward partials,
+//            distance; smem reductions -> rew_buf / reward_raw / reset_buf / terminate_buf
+//   phase 2  for each future step: frames -> smem; reference state; v6 block; the obs row is
+//            staged in smem (aliasing the frame buffer) and streamed out with 8-byte stores
+// ---------------------------------------------------------------------------------------
+constexpr int ROW13 = J24 * 13;              // 312 floats of sim state per env
+constexpr int FRAME_FLOATS = J24 * 13;       // pos 72 | rot 96 | vel 72 | ang 72
+constexpr int FRAME_F4 = FRAME_FLOATS / 4;   // 78
+constexpr int STAGE_FLOATS = SELF_DIM + TASK_DIM;  // 934
+
+struct StepParams {
+  LibDev L;
+  PhcBodyState body;
+  int16_t* progress;
+  const float* start;
+  const float* start_off;
+  const float* goff;
+  const int64_t* ids;
+  const float* term_dist;
+  uint32_t reset_mask;
+  int use_mean, early, advance, T;
+  float dt;
+  PhcRewardSpec rwd;
+  float* obs;
+  int64_t obs_stride;
+  float* rew;
+  float* raw;
+  int64_t raw_stride;
+  uint8_t* reset;
+  uint8_t* term;
+  double* moments;
+  int64_t n;
+  int aos;        // sim state is one AoS-13 tensor, 16-B aligned rows
+  int obs_vec2;   // obs rows can be written with 8-byte stores
+};
+
+template <int EPB>
+struct StepSmem {
+  static constexpr int NT = EPB * J24;
+  static constexpr int BUF = EPB * (STAGE_FLOATS > 2 * FRAME_FLOATS ? STAGE_FLOATS : 2 * FRAME_FLOATS);
+  float sim[EPB * ROW13];
+  float buf[BUF];             // frames [EPB][2][312]  /  obs stage [EPB][934]
+  float part[5][EPB][J24];    // reward partials x4, distance
+  float terms[EPB][4];
+  float goff[EPB][4];
+  float hz[EPB], hw[EPB];
+  int64_t f0[PHC_MAX_TIME_STEPS + 1][EPB];
+  int64_t f1[PHC_MAX_TIME_STEPS + 1][EPB];
+  float bl[PHC_MAX_TIME_STEPS + 1][EPB];
+  int prog[EPB];
+  int pass[EPB];
+};
+
+template <int EPB>
+__device__ __forceinline__ void load_frames(const LibDev& L, StepSmem<EPB>& S, int q, int e, int b, bool valid) {
+  // 24 threads of env e bring its two frames (2 x 78 float4) into S.buf[e][fr][...]
+  if (valid) {
+    const int64_t fa = S.f0[q][e], fb = S.f1[q][e];
+    float* dst_e = S.buf + e * (2 * FRAME_FLOATS);
+#pragma unroll
+    for (int it = 0; it < (2 * FRAME_F4 + J24 - 1) / J24; ++it) {
+      const int i = b + it * J24;
+      if (i < 2 * FRAME_F4) {
+        const int fr = i >= FRAME_F4;
+        const int k = i - fr * FRAME_F4;
+        const int64_t f = fr ? fb : fa;
+        const float* src;
+        if (k < 18)
+          src = L.gts + f * 72 + k * 4;
+        else if (k < 42)
+          src = L.grs + f * 96 + (k - 18) * 4;
+        else if (k < 60)
+          src = L.gvs + f * 72 + (k - 42) * 4;
+        else
+          src = L.gavs + f * 72 + (k - 60) * 4;
+        cp_async16(dst_e + fr * FRAME_FLOATS + k * 4, src);
+      }
+    }
+  }
+  cp_async_commit();
+}
+
+template <int EPB>
+__device__ __forceinline__ RefBody blend_ref(const StepSmem<EPB>& S, int q, int e, int b) {
+  const float* f0 = S.buf + e * (2 * FRAME_FLOATS);
+  const float* f1 = f0 + FRAME_FLOATS;
+  const float bl = S.bl[q][e];
+  const float om = 1.0f - bl;
+  RefBody r;
+  r.pos = lerp3(om, bl, ld3(f0 + b * 3), ld3(f1 + b * 3));
+  r.pos.x += S.goff[e][0];
+  r.pos.y += S.goff[e][1];
+  r.pos.z += S.goff[e][2];
+  r.rot = quat_slerp(ld4v(f0 + 72 + b * 4), ld4v(f1 + 72 + b * 4), bl);
+  r.vel = lerp3(om, bl, ld3(f0 + 168 + b * 3), ld3(f1 + 168 + b * 3));
+  r.ang = lerp3(om, bl, ld3(f0 + 240 + b * 3), ld3(f1 + 240 + b * 3));
+  return r;
+}
+
+template <int EPB>
+__global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StepSmem<EPB>& S = *reinterpret_cast<StepSmem<EPB>*>(smem_raw);
+  constexpr int NT = EPB * J24;
+  const int tid = threadIdx.x;
+  const int e = tid / J24, b = tid % J24;
+  const int64_t env0 = (int64_t)blockIdx.x * EPB;
+  const int64_t env = env0 + e;
+  const bool valid = env < p.n;
+  const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
+  const int T = p.T;
+
+  // ---- phase 0: sim tile + clock ------------------------------------------------------
+  if (p.aos) {
+    const float* src = p.body.pos.ptr + env0 * p.body.pos.stride_env;
+    if (p.body.pos.stride_env == ROW13) {  // envs contiguous: one flat copy
+      for (int i = tid; i < nvalid * (ROW13 / 4); i += NT) cp_async16(S.sim + i * 4, src + i * 4);
+    } else {
+      for (int i = tid; i < nvalid * (ROW13 / 4); i += NT) {
+        const int ee = i / (ROW13 / 4), k = i % (ROW13 / 4);
+        cp_async16(S.sim + ee * ROW13 + k * 4, src + ee * p.body.pos.stride_env + k * 4);
+      }
+    }
+  } else if (valid) {
+    float* d = S.sim + e * ROW13 + b * 13;
+    const float* a = view_at(p.body.pos, env, b);
+    const float* r = view_at(p.body.rot, env, b);
+    const float* v = view_at(p.body.vel, env, b);
+    const float* w = view_at(p.body.ang_vel, env, b);
+    d[0] = a[0], d[1] = a[1], d[2] = a[2];
+    d[3] = r[0], d[4] = r[1], d[5] = r[2], d[6] = r[3];
+    d[7] = v[0], d[8] = v[1], d[9] = v[2];
+    d[10] = w[0], d[11] = w[1], d[12] = w[2];
+  }
+  cp_async_commit();
+
+  if (valid && b <= T) {
+    // lanes 0..T of the env each run the frame-blend of one query time:
+    // q = 0: t = progress*dt + start + offset (humanoid_phc.py:1236); q >= 1: (progress+q)*dt + ..
+    // (humanoid_phc.py:1063-1067); progress is already advanced (humanoid_phc.py:138)
+    int prog = (int)p.progress[env];
+    if (p.advance) prog = (int)(int16_t)(prog + 1);
+    const int16_t pq = (int16_t)(prog + b);
+    const float t = (float)pq * p.dt + p.start[env] + p.start_off[env];
+    const int64_t id = p.ids[env];
+    const float len = p.L.len[id];
+    int64_t i0, i1;
+    float bl;
+    calc_frame_blend(t, len, p.L.nf[id], p.L.mdt[id], i0, i1, bl);
+    const int64_t st = p.L.starts[id];
+    S.f0[b][e] = i0 + st;
+    S.f1[b][e] = i1 + st;
+    S.bl[b][e] = bl;
+    if (b == 0) {
+      S.prog[e] = prog;
+      S.pass[e] = t >= len;  // _compute_reset, humanoid_phc.py:1317
+      if (p.advance) p.progress[env] = (int16_t)prog;
+      S.goff[e][0] = p.goff ? p.goff[env * 3 + 0] : 0.0f;
+      S.goff[e][1] = p.goff ? p.goff[env * 3 + 1] : 0.0f;
+      S.goff[e][2] = p.goff ? p.goff[env * 3 + 2] : 0.0f;
+    }
+  }
+  __syncthreads();  // frame indices visible
+
+  // ---- phase 1: reference state at t; reward; reset -------------------------------------
+  load_frames<EPB>(p.L, S, 0, e, b, valid);
+  cp_async_wait_all();
+  __syncthreads();  // sim tile + frames(t) landed
+
+  Vec3 pos, vel, ang;
+  Quat rot;
+  {
+    const float* d = S.sim + e * ROW13 + b * 13;
+    pos = {d[0], d[1], d[2]};
+    rot = {d[3], d[4], d[5], d[6]};
+    vel = {d[7], d[8], d[9]};
+    ang = {d[10], d[11], d[12]};
+  }
+  if (valid) {
+    const RefBody r = blend_ref<EPB>(S, 0, e, b);
+    float sp, sr, sv, sa;
+    reward_partials(pos, rot, vel, ang, r, sp, sr, sv, sa);
+    S.part[0][e][b] = sp;
+    S.part[1][e][b] = sr;
+    S.part[2][e][b] = sv;
+    S.part[3][e][b] = sa;
+    S.part[4][e][b] = norm3(pos - r.pos);  // torch.norm(rigid_body_pos - ref_body_pos), common.py:343/348
+    if (b == 0) {
+      const Heading hi = heading_quat_inv(rot);  // upright: root_rot used as is (common.py:42-44)
+      S.hz[e] = hi.z;
+      S.hw[e] = hi.w;
+    }
+  }
+  __syncthreads();  // partials written; frames(t) no longer needed
+
+  if (T >= 1) load_frames<EPB>(p.L, S, 1, e, b, valid);  // overlap with the reductions below
+
+  if (valid && b < 4) {
+    const float k = b == 0 ? p.rwd.k_pos : b == 1 ? p.rwd.k_rot : b == 2 ? p.rwd.k_vel : p.rwd.k_ang_vel;
+    const float t = reward_term(&S.part[b][e][0], J24, k);
+    S.terms[e][b] = t;
+    p.raw[env * p.raw_stride + b] = t;
+  } else if (valid && b == 4) {
+    bool fallen = false;
+    if (p.early) {
+      const float* d = &S.part[4][e][0];
+      if (p.use_mean) {
+        float sel[J24];
+        int m = 0;
+#pragma unroll
+        for (int j = 0; j < J24; ++j)
+          if (p.reset_mask >> j & 1u) sel[m++] = d[j];
+        // threshold of the first selected body: termination_distance[reset_ids][0] (common.py:343)
+        int first = __ffs(p.reset_mask) - 1;
+        fallen = m > 0 && (row_sum8(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+      } else {
+#pragma unroll
+        for (int j = 0; j < J24; ++j)
+          if (p.reset_mask >> j & 1u) fallen = fallen || (d[j] > p.term_dist[j]);
+      }
+      fallen = fallen && (S.prog[e] > 1);  // common.py:353
+    }
+    p.term[env] = fallen ? 1 : 0;
+    p.reset[env] = S.pass[e] ? 1 : (fallen ? 1 : 0);  // common.py:362
+  }
+  __syncwarp();
+  if (valid && b == 0) {
+    const float* t = S.terms[e];
+    p.rew[env] = p.rwd.w_pos * t[0] + p.rwd.w_rot * t[1] + p.rwd.w_vel * t[2] + p.rwd.w_ang_vel * t[3];
+  }
+
+  // ---- phase 2: observations -------------------------------------------------------------
+  const Vec3 root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
+  const Heading hi = {S.hz[e], S.hw[e]};
+  const float hs = heading_scale(hi);
+  const int W = SELF_DIM + TASK_DIM * T;
+
+  for (int q = 1; q <= T; ++q) {
+    cp_async_wait_all();
+    __syncthreads();  // frames(q) landed
+    RefBody r;
+    if (valid) r = blend_ref<EPB>(S, q, e, b);
+    __syncthreads();  // frame buffer dead -> becomes the obs stage
+
+    float* row = S.buf + e * STAGE_FLOATS;
+    if (valid) {
+      if (q == 1) {  // self obs, common.py:23-103 (default flags: local root, height, upright)
+        if (b == 0)
+          row[0] = root_pos.z;
+        else
+          st3(row + 1 + (b - 1) * 3, heading_rotate(hi, hs, pos - root_pos));
+        quat_tan_norm(heading_mul_left(hi, rot), row + 70 + b * 6);
+        st3(row + 214 + b * 3, heading_rotate(hi, hs, vel));
+        st3(row + 286 + b * 3, heading_rotate(hi, hs, ang));
+      }
+      TaskObs o;
+      task_obs_body(hi, hs, root_pos, pos, rot, vel, ang, r, true, o);
+      float* tk = row + SELF_DIM;
+      st3(tk + b * 3, o.d_pos);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tk[72 + b * 6 + k] = o.d_rot[k];
+      st3(tk + 216 + b * 3, o.d_vel);
+      st3(tk + 288 + b * 3, o.d_ang);
+      st3(tk + 360 + b * 3, o.l_pos);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tk[432 + b * 6 + k] = o.l_rot[k];
+    }
+    __syncthreads();  // stage complete
+
+    // stream the staged columns out: q == 1 -> cols [0, 934), else [358 + 576(q-1), +576)
+    const int s_off = q == 1 ? 0 : SELF_DIM;
+    const int s_len = q == 1 ? STAGE_FLOATS : TASK_DIM;
+    const int64_t c_off = q == 1 ? 0 : SELF_DIM + (int64_t)TASK_DIM * (q - 1);
+    if (p.obs_vec2) {
+      if (T == 1 && p.obs_stride == STAGE_FLOATS) {  // rows of the block are one contiguous span
+        float2* dst = reinterpret_cast<float2*>(p.obs + env0 * STAGE_FLOATS);
+        const float2* src = reinterpret_cast<const float2*>(S.buf);
+        for (int i = tid; i < nvalid * (STAGE_FLOATS / 2); i += NT) dst[i] = src[i];
+      } else {
+        for (int ee = 0; ee < nvalid; ++ee) {
+          float2* dst = reinterpret_cast<float2*>(p.obs + (env0 + ee) * p.obs_stride + c_off);
+          const float2* src = reinterpret_cast<const float2*>(S.buf + ee * STAGE_FLOATS + s_off);
+          for (int i = tid; i < s_len / 2; i += NT) dst[i] = src[i];
+        }
+      }
+    } else {
+      for (int ee = 0; ee < nvalid; ++ee) {
+        float* dst = p.obs + (env0 + ee) * p.obs_stride + c_off;
+        const float* src = S.buf + ee * STAGE_FLOATS + s_off;
+        for (int i = tid; i < s_len; i += NT) dst[i] = src[i];
+      }
+    }
+
+    if (p.moments) {  // RunningNorm partials: per-column fp64 sum / sum of squares over the block's envs
+      for (int c = tid; c < s_len; c += NT) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int ee = 0; ee < nvalid; ++ee) {
+          const double x = (double)S.buf[ee * STAGE_FLOATS + s_off + c];
+          s1 += x;
+          s2 += x * x;
+        }
+        atomicAdd(p.moments + c_off + c, s1);
+        atomicAdd(p.moments + W + c_off + c, s2);
+      }
+    }
+
+    if (q < T) {
+      __syncthreads();  // stage drained before the next frames overwrite it
+      load_frames<EPB>(p.L, S, q + 1, e, b, valid);
+    }
+  }
+  cp_async_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------
+// RunningNorm kernels (policies/running_norm.py:15-34)
+// ---------------------------------------------------------------------------------------
+constexpr int MOM_ROWS_PER_BLOCK = 256;
+
+__global__ void obs_moments_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t stride,
+                                   double* __restrict__ sums) {
+  // grid (ceil(cols/128), ceil(rows/256)); thread = one column, coalesced across the warp
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * MOM_ROWS_PER_BLOCK;
+  if (c >= cols) return;
+  const int64_t r1 = r0 + MOM_ROWS_PER_BLOCK < rows ? r0 + MOM_ROWS_PER_BLOCK : rows;
+  double s1 = 0.0, s2 = 0.0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const double v = (double)x[r * stride + c];
+    s1 += v;
+    s2 += v * v;
+  }
+  atomicAdd(sums + c, s1);
+  atomicAdd(sums + cols + c, s2);
+}
+
+__global__ void running_norm_update_kernel(float* __restrict__ mean, float* __restrict__ var,
+                                           float* __restrict__ count, const double* __restrict__ sums,
+                                           const double* __restrict__ total_rows, int64_t cols) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double n = *total_rows;
+  const float cnt = *count;
+  if (c < cols && n > 0) {
+    const double m = sums[c] / n;
+    double v = sums[cols + c] / n - m * m;  // var(unbiased=False)
+    if (v < 0) v = 0;
+    const float w = 1.0f / cnt;  // weight = 1 / self.count
+    mean[c] = mean[c] * (1.0f - w) + (float)m * w;
+    var[c] = var[c] * (1.0f - w) + (float)v * w;
+  }
+  // count += 1 after every column has read it: done by a second tiny launch
+}
+
+__global__ void running_norm_count_kernel(float* count) { *count = *count + 1.0f; }
+
+__global__ void running_norm_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t stride,
+                                            const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                            float clip, float* __restrict__ out, int64_t out_stride) {
+  const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  const int64_t r = blockIdx.x;
+  if (c >= cols || r >= rows) return;
+  const float v = (x[r * stride + c] - mean[c]) / sqrtf(var[c] + eps);
+  out[r * out_stride + c] = fminf(fmaxf(v, -clip), clip);
+}
+
+}  // namespace phc
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace phc;
+
+struct PhcLib {
+  LibDev d;
+};
+
+extern "C" {
+
+const char* phc_strerror(int code) {
+  switch (code) {
+    case PHC_OK: return "ok";
+    case PHC_ERR_NULL: return "required pointer is NULL";
+    case PHC_ERR_SHAPE: return "size or count out of range";
+    case PHC_ERR_ALIGN: return "pointer or stride not aligned as required";
+    case PHC_ERR_UNSUPPORTED: return "not supported by this build";
+    case PHC_ERR_CUDA: return "CUDA runtime error";
+    case PHC_ERR_ALLOC: return "allocation failed";
+    default: return "unknown error";
+  }
+}
+
+int phc_abi_version(void) { return PHC_ABI_VERSION; }
+int phc_last_cuda_error(void) { return g_last_cuda_error; }
+
+int phc_lib_create(const PhcLibDesc* desc, PhcLib** out) {
+  if (!desc || !out) return PHC_ERR_NULL;
+  if (!desc->gts || !desc->grs || !desc->gvs || !desc->gavs || !desc->motion_lengths ||
+      !desc->motion_num_frames || !desc->motion_dt || !desc->length_starts)
+    return PHC_ERR_NULL;
+  if (desc->total_frames <= 0 || desc->num_motions <= 0) return PHC_ERR_SHAPE;
+  // frame rows are fetched with 16-byte copies: 288 / 384 B rows keep the alignment of the base
+  const uintptr_t a = (uintptr_t)desc->gts | (uintptr_t)desc->grs | (uintptr_t)desc->gvs | (uintptr_t)desc->gavs |
+                      (uintptr_t)desc->lrs;
+  if (a & 15) return PHC_ERR_ALIGN;
+  PhcLib* lib = new (std::nothrow) PhcLib;
+  if (!lib) return PHC_ERR_ALLOC;
+  lib->d = LibDev{desc->gts,           desc->grs,        desc->lrs,          desc->gvs,
+                  desc->gavs,          desc->dvs,        desc->motion_aa,    desc->motion_lengths,
+                  desc->motion_dt,     desc->motion_bodies, desc->motion_limb_weights,
+                  desc->motion_num_frames, desc->length_starts, desc->total_frames, desc->num_motions};
+  *out = lib;
+  return PHC_OK;
+}
+
+void phc_lib_destroy(PhcLib* lib) { delete lib; }
+
+int phc_calc_frame_blend(const float* time, const float* len, const int64_t* num_frames, const float* dt,
+                         int64_t n, int64_t* frame_idx0, int64_t* frame_idx1, float* blend, phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0) return PHC_ERR_SHAPE;
+  if (!time || !len || !num_frames || !dt || !frame_idx0 || !frame_idx1 || !blend) return PHC_ERR_NULL;
+  const int bs = 256;
+  frame_blend_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, stream>>>(time, len, num_frames, dt, n, frame_idx0,
+                                                                        frame_idx1, blend);
+  return launch_status();
+}
+
+int phc_motion_state(const PhcLib* lib, const int64_t* motion_ids, const float* motion_times,
+                     const float* offset_or_null, int64_t n, const PhcMotionOut* out, phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0) return PHC_ERR_SHAPE;
+  if (!lib || !motion_ids || !motion_times || !out) return PHC_ERR_NULL;
+  if (out->dof_pos && !lib->d.lrs) return PHC_ERR_NULL;
+  if (out->dof_vel && !lib->d.dvs) return PHC_ERR_NULL;
+  if (out->motion_aa && !lib->d.aa) return PHC_ERR_NULL;
+  if (out->motion_bodies && !lib->d.bodies) return PHC_ERR_NULL;
+  if (out->motion_limb_weights && !lib->d.limb) return PHC_ERR_NULL;
+  const unsigned grid = (unsigned)((n + K1_QPB - 1) / K1_QPB);
+  motion_state_kernel<<<grid, K1_QPB * J24, 0, stream>>>(lib->d, motion_ids, motion_times, offset_or_null, n, *out);
+  return launch_status();
+}
+
+static int check_body(const PhcBodyState* s) {
+  if (!s) return PHC_ERR_NULL;
+  if (!s->pos.ptr || !s->rot.ptr || !s->vel.ptr || !s->ang_vel.ptr) return PHC_ERR_NULL;
+  if (s->num_bodies < 1 || s->num_bodies > GEN_MAX_J) return PHC_ERR_SHAPE;
+  return PHC_OK;
+}
+
+int phc_self_obs_smpl_max(const PhcBodyState* body, int64_t n, uint32_t flags, float* out, int64_t out_stride,
+                          phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0) return PHC_ERR_SHAPE;
+  int rc = check_body(body);
+  if (rc) return rc;
+  if (!out) return PHC_ERR_NULL;
+  const int J = body->num_bodies;
+  const int width = ((flags & PHC_OBS_ROOT_HEIGHT) ? 1 : 0) + 15 * J - 3;
+  if (out_stride < width) return PHC_ERR_SHAPE;
+  const int epb = 192 / J > 0 ? 192 / J : 1;
+  self_obs_kernel<<<(unsigned)((n + epb - 1) / epb), epb * J, 0, stream>>>(*body, n, flags, out, out_stride, epb);
+  return launch_status();
+}
+
+int phc_imitation_obs(const float* root_pos, int64_t root_pos_stride, const float* root_rot, int64_t root_rot_stride,
+                      const PhcBodyState* body, const PhcBodyState* ref, int64_t n, int32_t time_steps,
+                      int32_t upright, int32_t mode, float* out, int64_t out_stride, phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0 || time_steps < 1) return PHC_ERR_SHAPE;
+  int rc = check_body(body);
+  if (rc) return rc;
+  rc = check_body(ref);
+  if (rc) return rc;
+  if (!root_pos || !root_rot || !out) return PHC_ERR_NULL;
+  if (ref->num_bodies != body->num_bodies) return PHC_ERR_SHAPE;
+  if (mode != 6 && mode != 7) return PHC_ERR_UNSUPPORTED;
+  const int J = body->num_bodies;
+  const int64_t width = (int64_t)(mode == 6 ? 24 : 9) * J * time_steps;
+  if (out_stride < width) return PHC_ERR_SHAPE;
+  const int64_t total = n * time_steps * J;
+  const int bs = 192;
+  imitation_obs_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, stream>>>(
+      root_pos, root_pos_stride, root_rot, root_rot_stride, *body, *ref, n, time_steps, upright, mode, out, out_stride);
+  return launch_status();
+}
+
+int phc_imitation_reward(const PhcBodyState* body, const PhcBodyState* ref, int64_t n, const PhcRewardSpec* spec,
+                         float* reward, float* reward_raw, int64_t reward_raw_stride, phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0) return PHC_ERR_SHAPE;
+  int rc = check_body(body);
+  if (rc) return rc;
+  rc = check_body(ref);
+  if (rc) return rc;
+  if (!spec || !reward || !reward_raw) return PHC_ERR_NULL;
+  if (ref->num_bodies != body->num_bodies || reward_raw_stride < 4) return PHC_ERR_SHAPE;
+  const int J = body->num_bodies;
+  const int epb = 192 / J > 0 ? 192 / J : 1;
+  const size_t sm = (size_t)epb * 4 * (J + 1) * sizeof(float);
+  reward_kernel<<<(unsigned)((n + epb - 1) / epb), epb * J, sm, stream>>>(*body, *ref, n, *spec, reward, reward_raw,
+                                                                         reward_raw_stride, epb);
+  return launch_status();
+}
+
+int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_pos, int32_t num_reset_bodies,
+                 const int16_t* progress_buf, const uint8_t* pass_time, const float* termination_distance,
+                 int32_t enable_early_termination, int32_t use_mean, int64_t n, uint8_t* reset, uint8_t* terminated,
+                 phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0 || num_reset_bodies < 1 || num_reset_bodies > GEN_MAX_J) return PHC_ERR_SHAPE;
+  if (!rigid_body_pos || !ref_body_pos || !rigid_body_pos->ptr || !ref_body_pos->ptr || !progress_buf || !pass_time ||
+      !termination_distance || !reset || !terminated)
+    return PHC_ERR_NULL;
+  const int R = num_reset_bodies;
+  const int epb = 192 / R > 0 ? 192 / R : 1;
+  reset_kernel<<<(unsigned)((n + epb - 1) / epb), epb * R, (size_t)epb * R * sizeof(float), stream>>>(
+      *rigid_body_pos, *ref_body_pos, R, progress_buf, pass_time, termination_distance, enable_early_termination,
+      use_mean, n, reset, terminated, epb);
+  return launch_status();
+}
+
+// ---- fused step --------------------------------------------------------------------------
+constexpr int STEP_EPB = 8;
+
+static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, StepParams& p) {
+  if (!lib || !a) return PHC_ERR_NULL;
+  int rc = check_body(&a->body);
+  if (rc) return rc;
+  if (a->body.num_bodies != J24) return PHC_ERR_UNSUPPORTED;
+  if (!a->progress_buf || !a->motion_start_times || !a->motion_start_times_offset || !a->sampled_motion_ids ||
+      !a->termination_distances || !a->obs_buf || !a->rew_buf || !a->reward_raw || !a->reset_buf || !a->terminate_buf)
+    return PHC_ERR_NULL;
+  if (a->time_steps < 1 || a->time_steps > PHC_MAX_TIME_STEPS) return PHC_ERR_SHAPE;
+  const int64_t W = SELF_DIM + (int64_t)TASK_DIM * a->time_steps;
+  if (a->obs_stride < W || a->reward_raw_stride < 4) return PHC_ERR_SHAPE;
+  p.L = lib->d;
+  p.body = a->body;
+  p.progress = a->progress_buf;
+  p.start = a->motion_start_times;
+  p.start_off = a->motion_start_times_offset;
+  p.goff = a->global_offset;
+  p.ids = a->sampled_motion_ids;
+  p.term_dist = a->termination_distances;
+  p.reset_mask = a->reset_body_mask & 0xFFFFFFu;
+  p.use_mean = a->use_mean;
+  p.early = a->enable_early_termination;
+  p.advance = a->advance_progress;
+  p.T = a->time_steps;
+  p.dt = a->dt;
+  p.rwd = a->rwd;
+  p.obs = a->obs_buf;
+  p.obs_stride = a->obs_stride;
+  p.rew = a->rew_buf;
+  p.raw = a->reward_raw;
+  p.raw_stride = a->reward_raw_stride;
+  p.reset = a->reset_buf;
+  p.term = a->terminate_buf;
+  p.moments = a->obs_moments;
+  p.n = n;
+  const PhcBodyState& s = a->body;
+  // fast path: the four views are slices of one AoS-13 tensor whose env rows are 16-B aligned
+  p.aos = s.rot.ptr == s.pos.ptr + 3 && s.vel.ptr == s.pos.ptr + 7 && s.ang_vel.ptr == s.pos.ptr + 10 &&
+          s.pos.stride_body == 13 && s.rot.stride_body == 13 && s.vel.stride_body == 13 &&
+          s.ang_vel.stride_body == 13 && s.rot.stride_env == s.pos.stride_env &&
+          s.vel.stride_env == s.pos.stride_env && s.ang_vel.stride_env == s.pos.stride_env &&
+          ((uintptr_t)s.pos.ptr & 15) == 0 && (s.pos.stride_env % 4) == 0 && s.pos.stride_env >= ROW13;
+  p.obs_vec2 = ((uintptr_t)a->obs_buf & 7) == 0 && (a->obs_stride % 2) == 0;
+  return PHC_OK;
+}
+
+int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0) return PHC_ERR_SHAPE;
+  StepParams p;
+  int rc = step_fill_params(lib, args, n, p);
+  if (rc) return rc;
+  using SM = StepSmem<STEP_EPB>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  PHC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return PHC_ERR_UNSUPPORTED;
+  if (!attr_set[dev]) {
+    PHC_CUDA(cudaFuncSetAttribute(step_kernel<STEP_EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+    attr_set[dev] = true;
+  }
+  const unsigned grid = (unsigned)((n + STEP_EPB - 1) / STEP_EPB);
+  step_kernel<STEP_EPB><<<grid, STEP_EPB * J24, sizeof(SM), stream>>>(p);
+  return launch_status();
+}
+
+// ---- RunningNorm ---------------------------------------------------------------------------
+int phc_obs_moments(const float* x, int64_t rows, int64_t cols, int64_t row_stride, double* sums,
+                    phc_stream_t stream) {
+  if (rows == 0 || cols == 0) return PHC_OK;
+  if (rows < 0 || cols < 0 || row_stride < cols) return PHC_ERR_SHAPE;
+  if (!x || !sums) return PHC_ERR_NULL;
+  dim3 grid((unsigned)((cols + 127) / 128), (unsigned)((rows + MOM_ROWS_PER_BLOCK - 1) / MOM_ROWS_PER_BLOCK));
+  obs_moments_kernel<<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, sums);
+  return launch_status();
+}
+
+int phc_running_norm_update(float* running_mean, float* running_var, float* count, const double* sums,
+                            const double* total_rows, int64_t cols, phc_stream_t stream) {
+  if (cols <= 0) return PHC_ERR_SHAPE;
+  if (!running_mean || !running_var || !count || !sums || !total_rows) return PHC_ERR_NULL;
+  running_norm_update_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, stream>>>(running_mean, running_var, count,
+                                                                                 sums, total_rows, cols);
+  int rc = launch_status();
+  if (rc) return rc;
+  running_norm_count_kernel<<<1, 1, 0, stream>>>(count);
+  return launch_status();
+}
+
+int phc_running_norm_forward(const float* x, int64_t rows, int64_t cols, int64_t row_stride,
+                             const float* running_mean, const float* running_var, float epsilon, float clip,
+                             float* out, int64_t out_stride, phc_stream_t stream) {
+  if (rows == 0 || cols == 0) return PHC_OK;
+  if (rows < 0 || cols < 0 || row_stride < cols || out_stride < cols || rows > 0x7fffffff) return PHC_ERR_SHAPE;
+  if (!x || !running_mean || !running_var || !out) return PHC_ERR_NULL;
+  dim3 grid((unsigned)rows, (unsigned)((cols + 127) / 128));
+  running_norm_forward_kernel<<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, running_mean, running_var, epsilon,
+                                                        clip, out, out_stride);
+  return launch_status();
+}
+
+}  // extern "C"

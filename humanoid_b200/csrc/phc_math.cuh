@@ -1,0 +1,215 @@
+// Device-side quaternion / frame-blend arithmetic of the PHC step path (sm_100a).
+//
+// Every function reproduces the fp32 operation ORDER of the reference primitive it cites
+// (paths relative to packages/puffer-phc/puffer_phc/), because two places on the path are
+// rounding-sensitive: the frame index is a truncation of a value that lands on integers
+// (motion_lib.py:661), and slerp's sqrt(1 - c*c) cancels catastrophically for consecutive
+// mocap frames (torch_utils.py:121).  This translation unit is compiled with -fmad=false so
+// a*b+c is two roundings, as in ATen's one-kernel-per-op evaluation; the two places where
+// ATen's CPU kernels do fuse (cross product, 3-vector norm) use __fmaf_rn explicitly.
+// Divisions and square roots are IEEE (-prec-div/-prec-sqrt default), no fast-math.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace phc {
+
+struct Vec3 {
+  float x, y, z;
+};
+struct Quat {
+  float x, y, z, w;
+};
+
+__device__ __forceinline__ Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ Vec3 operator+(Vec3 a, Vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+
+// torch.clip(x, 0, 1) on finite input; NaN maps to 0 (the reference would index out of range)
+__device__ __forceinline__ float clip01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+// MotionLibBase._calc_frame_blend, motion_lib.py:655-665.
+//   phase = clip(t / len, 0, 1)   (from the un-clamped time)
+//   t[t < 0] = 0
+//   idx0 = trunc(phase * f32(nf - 1)); idx1 = min(idx0 + 1, nf - 1)
+//   blend = clip((t - f32(idx0) * dt) / dt, 0, 1)
+__device__ __forceinline__ void calc_frame_blend(float t, float len, int64_t nf, float dt, int64_t& idx0,
+                                                 int64_t& idx1, float& blend) {
+  float phase = clip01(t / len);
+  if (t < 0.0f) t = 0.0f;
+  idx0 = (int64_t)(phase * (float)(nf - 1));
+  idx1 = idx0 + 1 < nf - 1 ? idx0 + 1 : nf - 1;
+  blend = clip01((t - (float)idx0 * dt) / dt);
+}
+
+// quat_mul, torch_utils.py:55-75 (8-multiply form, same grouping)
+__device__ __forceinline__ Quat quat_mul(Quat a, Quat b) {
+  float ww = (a.z + a.x) * (b.x + b.y);
+  float yy = (a.w - a.y) * (b.w + b.z);
+  float zz = (a.w + a.y) * (b.w - b.z);
+  float xx = ww + yy + zz;
+  float qq = 0.5f * (xx + (a.z - a.x) * (b.x - b.y));
+  Quat r;
+  r.w = qq - ww + (a.z - a.y) * (b.y - b.z);
+  r.x = qq - xx + (a.x + a.w) * (b.x + b.w);
+  r.y = qq - yy + (a.w - a.x) * (b.y + b.z);
+  r.z = qq - zz + (a.z + a.y) * (b.w - b.x);
+  return r;
+}
+
+__device__ __forceinline__ Quat quat_conj(Quat q) { return {-q.x, -q.y, -q.z, q.w}; }
+
+// A heading quaternion (0, 0, z, w): rotation about the up axis.  The x, y components of
+// calc_heading_quat(_inv) are exactly +-0 (torch_utils.py:354-358 with axis (0,0,1)), so
+// the products below drop the terms that add +-0; results equal quat_mul / my_quat_rotate
+// bit for bit except for the sign of an exact zero.
+struct Heading {
+  float z, w;
+};
+
+// quat_mul(h, q) with h = (0,0,z,w)
+__device__ __forceinline__ Quat heading_mul_left(Heading h, Quat b) {
+  float ww = h.z * (b.x + b.y);
+  float yy = h.w * (b.w + b.z);
+  float zz = h.w * (b.w - b.z);
+  float xx = ww + yy + zz;
+  float qq = 0.5f * (xx + h.z * (b.x - b.y));
+  Quat r;
+  r.w = qq - ww + h.z * (b.y - b.z);
+  r.x = qq - xx + h.w * (b.x + b.w);
+  r.y = qq - yy + h.w * (b.y + b.z);
+  r.z = qq - zz + h.z * (b.w - b.x);
+  return r;
+}
+
+// quat_mul(q, h) with h = (0,0,z,w)
+__device__ __forceinline__ Quat heading_mul_right(Quat a, Heading h) {
+  float yy = (a.w - a.y) * (h.w + h.z);
+  float zz = (a.w + a.y) * (h.w - h.z);
+  float xx = yy + zz;
+  float qq = 0.5f * xx;
+  Quat r;
+  r.w = qq + (a.z - a.y) * (-h.z);
+  r.x = qq - xx + (a.x + a.w) * h.w;
+  r.y = qq - yy + (a.w - a.x) * h.z;
+  r.z = qq - zz + (a.z + a.y) * h.w;
+  return r;
+}
+
+// my_quat_rotate, torch_utils.py:274-281:  (v*(2w^2-1) + cross(q,v)*w*2) + q*dot(q,v)*2
+// cross is ATen's fused form fma(a1,b2,-(a2*b1)); the dot is bmm's sequential sum.
+__device__ __forceinline__ Vec3 quat_rotate(Quat q, Vec3 v) {
+  float s = 2.0f * (q.w * q.w) - 1.0f;
+  float cx = __fmaf_rn(q.y, v.z, -(q.z * v.y));
+  float cy = __fmaf_rn(q.z, v.x, -(q.x * v.z));
+  float cz = __fmaf_rn(q.x, v.y, -(q.y * v.x));
+  float d = (q.x * v.x + q.y * v.y) + q.z * v.z;
+  Vec3 r;
+  r.x = (v.x * s + cx * q.w * 2.0f) + q.x * d * 2.0f;
+  r.y = (v.y * s + cy * q.w * 2.0f) + q.y * d * 2.0f;
+  r.z = (v.z * s + cz * q.w * 2.0f) + q.z * d * 2.0f;
+  return r;
+}
+
+// my_quat_rotate with q = (0,0,z,w); hs = 2w^2-1 precomputed by heading_scale()
+__device__ __forceinline__ float heading_scale(Heading h) { return 2.0f * (h.w * h.w) - 1.0f; }
+__device__ __forceinline__ Vec3 heading_rotate(Heading h, float hs, Vec3 v) {
+  Vec3 r;
+  r.x = v.x * hs + (-(h.z * v.y)) * h.w * 2.0f;
+  r.y = v.y * hs + (h.z * v.x) * h.w * 2.0f;
+  r.z = v.z * hs + h.z * (h.z * v.z) * 2.0f;
+  return r;
+}
+
+// quat_to_tan_norm, torch_utils.py:285-297: rotate (1,0,0) then (0,0,1); closed form of
+// my_quat_rotate on the unit axes (terms that are exactly zero dropped).
+__device__ __forceinline__ void quat_tan_norm(Quat q, float* out6) {
+  float s = 2.0f * (q.w * q.w) - 1.0f;
+  out6[0] = s + q.x * q.x * 2.0f;
+  out6[1] = q.z * q.w * 2.0f + q.y * q.x * 2.0f;
+  out6[2] = (-q.y) * q.w * 2.0f + q.z * q.x * 2.0f;
+  out6[3] = q.y * q.w * 2.0f + q.x * q.z * 2.0f;
+  out6[4] = (-q.x) * q.w * 2.0f + q.y * q.z * 2.0f;
+  out6[5] = s + q.z * q.z * 2.0f;
+}
+
+// remove_base_rot, envs/common.py:15-19: q (x) conj(0.5,0.5,0.5,0.5)
+__device__ __forceinline__ Quat remove_base_rot(Quat q) { return quat_mul(q, Quat{-0.5f, -0.5f, -0.5f, 0.5f}); }
+
+// calc_heading_quat_inv / calc_heading_quat, torch_utils.py:369-408.
+//   heading = atan2(rot.y, rot.x), rot = my_quat_rotate(q,(1,0,0))
+//   q_h = quat_unit((0,0,sin(+-heading/2), cos(heading/2)))   (norm: sequential, no FMA)
+// heading_quat == conj(heading_quat_inv) exactly, so one evaluation serves both.
+__device__ __forceinline__ Heading heading_quat_inv(Quat q) {
+  float s = 2.0f * (q.w * q.w) - 1.0f;
+  float rx = s + q.x * q.x * 2.0f;
+  float ry = q.z * q.w * 2.0f + q.y * q.x * 2.0f;
+  float half = (-atan2f(ry, rx)) / 2.0f;
+  float sn = sinf(half), cs = cosf(half);
+  float nrm = fmaxf(sqrtf(sn * sn + cs * cs), 1e-9f);
+  return {sn / nrm, cs / nrm};
+}
+__device__ __forceinline__ Heading heading_conj(Heading h) { return {-h.z, h.w}; }
+
+// angle of quat_to_angle_axis, torch_utils.py:86-106:
+//   sin_theta = sqrt(1 - w*w); angle = normalize_angle(2*acos(w)); 0 unless |sin_theta| > 1e-5
+__device__ __forceinline__ float quat_angle(float w, float* sin_theta_out = nullptr) {
+  float st = sqrtf(1.0f - w * w);
+  float a = 2.0f * acosf(w);
+  a = atan2f(sinf(a), cosf(a));
+  if (sin_theta_out) *sin_theta_out = st;
+  return (fabsf(st) > 1e-5f) ? a : 0.0f;  // NaN compares false -> 0, as torch.where does
+}
+
+// quat_to_exp_map, torch_utils.py:135-150
+__device__ __forceinline__ Vec3 quat_exp_map(Quat q) {
+  float st;
+  float a = quat_angle(q.w, &st);
+  if (fabsf(st) > 1e-5f) return {a * (q.x / st), a * (q.y / st), a * (q.z / st)};
+  return {a * 0.0f, a * 0.0f, a * 1.0f};
+}
+
+// slerp, torch_utils.py:110-131.  c = ((x0x1 + y0y1) + z0z1) + w0w1 (ATen sum order);
+// q1 flipped when c < 0; result not renormalised; the |sin| < 1e-3 average is applied
+// first and the |cos| >= 1 -> q0 select last (it wins, and masks acos' NaN for c > 1).
+__device__ __forceinline__ Quat quat_slerp(Quat q0, Quat q1, float t) {
+  float c = ((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w;
+  if (c < 0.0f) q1 = {-q1.x, -q1.y, -q1.z, -q1.w};
+  c = fabsf(c);
+  float th = acosf(c);
+  float s = sqrtf(1.0f - c * c);
+  float ra = sinf((1.0f - t) * th) / s;
+  float rb = sinf(t * th) / s;
+  Quat r = {ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
+  if (fabsf(s) < 0.001f)
+    r = {0.5f * q0.x + 0.5f * q1.x, 0.5f * q0.y + 0.5f * q1.y, 0.5f * q0.z + 0.5f * q1.z, 0.5f * q0.w + 0.5f * q1.w};
+  if (fabsf(c) >= 1.0f) r = q0;
+  return r;
+}
+
+// lerp of get_motion_state, motion_lib.py:597-603: (1 - b)*x0 + b*x1
+__device__ __forceinline__ float lerp1(float om, float b, float x0, float x1) { return om * x0 + b * x1; }
+__device__ __forceinline__ Vec3 lerp3(float om, float b, Vec3 x0, Vec3 x1) {
+  return {om * x0.x + b * x1.x, om * x0.y + b * x1.y, om * x0.z + b * x1.z};
+}
+
+// torch.norm(v, dim=-1) over 3 on ATen CPU: sqrt(fma(z,z,fma(y,y,x*x)))
+__device__ __forceinline__ float norm3(Vec3 v) { return sqrtf(__fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, v.x * v.x))); }
+
+// (d**2).mean(dim=-1) over 3: ((x^2 + y^2) + z^2) / 3
+__device__ __forceinline__ float mean_sq3(Vec3 d) { return ((d.x * d.x + d.y * d.y) + d.z * d.z) / 3.0f; }
+
+// ATen CPU sum over a contiguous row of n <= 32 floats: 8 lane accumulators filled
+// round-robin, then combined left to right (measured; exact for n = 24).
+__device__ __forceinline__ float row_sum8(const float* v, int n) {
+  float acc[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) acc[l] = 0.0f;
+  for (int j = 0; j < n; ++j) acc[j & 7] += v[j];  // 0 + x is exact
+  float s = acc[0];
+#pragma unroll
+  for (int l = 1; l < 8; ++l) s = s + acc[l];
+  return s;
+}
+
+}  // namespace phc

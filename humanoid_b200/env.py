@@ -1,0 +1,290 @@
+"""HumanoidPHC-shaped shim around the fused step kernel.
+
+Mirrors the buffers and method names of the reference task env
+(PHC/envs/humanoid_phc.py) for the part of ``step()`` that runs after the physics step
+(:138-152).  Isaac Gym / PhysX is out of scope, so the rigid-body state is a plain tensor
+``_rigid_body_state_reshaped [N, bodies_per_env, 13]`` that the owner fills (synthetic data
+in tests and the bench; PhysX's buffer through gymtorch in the reference, :542-549).
+
+Two ways to run the post-physics half:
+
+* ``step()`` / ``post_physics_step()`` — one fused kernel launch (``phc_step_fused``): clock
+  advance, motion query at t, reward, reset, motion query at t+dt.., self + task obs written
+  as one ``obs_buf`` row.  No host sync, graph-capturable.
+* ``_compute_reward`` / ``_compute_reset`` / ``_compute_observations`` — the reference's
+  own decomposition, each calling the per-function drop-ins of ``humanoid_b200.common`` and
+  ``MotionLib.get_motion_state`` (used for per-op parity and for ``env_ids`` subsets).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _cabi
+from .common import (
+    compute_humanoid_im_reset,
+    compute_humanoid_observations_smpl_max,
+    compute_imitation_observations_v6,
+    compute_imitation_reward,
+)
+from .motion_lib import MotionLib
+
+BODY_NAMES = (
+    "Pelvis", "L_Hip", "L_Knee", "L_Ankle", "L_Toe", "R_Hip", "R_Knee", "R_Ankle", "R_Toe", "Torso", "Spine",
+    "Chest", "Neck", "Head", "L_Thorax", "L_Shoulder", "L_Elbow", "L_Wrist", "L_Hand", "R_Thorax", "R_Shoulder",
+    "R_Elbow", "R_Wrist", "R_Hand",
+)  # PHC/body_sets.py:11-36  # fmt: skip
+REMOVE_NAMES = ("L_Hand", "R_Hand", "L_Toe", "R_Toe")  # body_sets.py:42
+EVAL_BODIES = tuple(n for n in BODY_NAMES if n not in REMOVE_NAMES)  # body_sets.py:57
+
+DEFAULT_REWARD = dict(  # asdict(RewardConfig), PHC/config.py:38-50
+    k_pos=100.0, k_rot=10.0, k_vel=0.1, k_ang_vel=0.1, w_pos=0.5, w_rot=0.3, w_vel=0.1, w_ang_vel=0.1,
+    imitation_reward_dim=4, full_body_reward=True, use_power_reward=True,
+)  # fmt: skip
+
+
+def build_body_ids_tensor(body_names: Sequence[str], subset: Sequence[str], device) -> torch.Tensor:
+    """PHC/body_sets.py:143-158."""
+    return torch.tensor([body_names.index(n) for n in subset], dtype=torch.long, device=device)
+
+
+class HumanoidPHC:
+    def __init__(
+        self,
+        motion_lib: MotionLib,
+        num_envs: int,
+        device="cuda",
+        bodies_per_env: int = 24,
+        time_steps: int = 1,
+        termination_distance: float = 0.25,  # config.py:100
+        enable_early_termination: bool = True,  # config.py:99
+        dt: float = 2 * (1.0 / 60.0),  # isaacgym_env.py:39-41
+        rwd_specs: Optional[Dict[str, float]] = None,
+        obs_moments: bool = False,
+    ):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _cabi.PhcError("HumanoidPHC needs a CUDA device (there is no CPU path)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.num_envs = num_envs
+        self.num_bodies = 24
+        self.dt = dt
+        self.time_steps = int(time_steps)
+        self._motion_lib = motion_lib
+        self.enable_early_termination = enable_early_termination
+        self.flag_im_eval = False
+        self._rwd_specs = dict(rwd_specs or DEFAULT_REWARD)
+
+        N = num_envs
+        # sim tensors (stand-in for the gymtorch-wrapped PhysX buffer, humanoid_phc.py:542-549)
+        self._rigid_body_state_reshaped = torch.zeros((N, bodies_per_env, 13), dtype=torch.float32, device=dev)
+        self._bind_body_views()
+
+        # env buffers (humanoid_phc.py:556-597)
+        self.num_obs = _cabi.SELF_OBS_DIM + _cabi.TASK_OBS_DIM * self.time_steps  # :461-467
+        self.obs_buf = torch.zeros((N, self.num_obs), dtype=torch.float32, device=dev)
+        self.rew_buf = torch.zeros(N, dtype=torch.float32, device=dev)  # (:560 calls the torch module; fixed)
+        self.reward_raw = torch.zeros((N, 5), dtype=torch.float32, device=dev)  # 4 + power slot (:562-569)
+        self.progress_buf = torch.zeros(N, dtype=torch.short, device=dev)
+        self.reset_buf = torch.ones(N, dtype=torch.bool, device=dev)
+        self._terminate_buf = torch.ones(N, dtype=torch.bool, device=dev)
+        self.extras = {}
+        self._global_offset = torch.zeros((N, 3), dtype=torch.float32, device=dev)
+        self._motion_start_times = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._motion_start_times_offset = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._sampled_motion_ids = torch.arange(N, device=dev) % motion_lib.num_motions()
+        self.all_env_ids = torch.arange(N, device=dev)
+
+        # _config_env (humanoid_phc.py:239-250)
+        self._termination_distances = torch.full((24,), termination_distance, dtype=torch.float32, device=dev)
+        self._termination_distances_backup = self._termination_distances.clone()
+        self._track_bodies_id = build_body_ids_tensor(BODY_NAMES, BODY_NAMES, dev)
+        self._reset_bodies_id = build_body_ids_tensor(BODY_NAMES, BODY_NAMES, dev)
+        self._reset_bodies_id_backup = self._reset_bodies_id.clone()
+        self._eval_track_bodies_id = build_body_ids_tensor(BODY_NAMES, EVAL_BODIES, dev)
+
+        self.obs_moments = (
+            torch.zeros(2 * self.num_obs, dtype=torch.float64, device=dev) if obs_moments else None
+        )
+        self.obs_moment_rows = 0
+        self._step_args = None
+
+    # ------------------------------------------------------------------------------------
+    def _bind_body_views(self):
+        s = self._rigid_body_state_reshaped
+        J = self.num_bodies
+        self._rigid_body_pos = s[..., :J, 0:3]
+        self._rigid_body_rot = s[..., :J, 3:7]
+        self._rigid_body_vel = s[..., :J, 7:10]
+        self._rigid_body_ang_vel = s[..., :J, 10:13]
+        self._step_args = None
+
+    def set_sim_state(self, state: torch.Tensor, copy: bool = True):
+        """Stand-in for ``_refresh_sim_tensors`` (:782): adopt or copy an AoS [N,B,13] state."""
+        if copy:
+            self._rigid_body_state_reshaped.copy_(state)
+        else:
+            _cabi.require_cuda(state, "state", torch.float32)
+            self._rigid_body_state_reshaped = state
+            self._bind_body_views()
+
+    def set_clock(self, clock):
+        """Load a ``synth.Clock`` into the env's motion-clock buffers."""
+        self.progress_buf.copy_(clock.progress_buf)
+        self._motion_start_times.copy_(clock.motion_start_times)
+        self._motion_start_times_offset.copy_(clock.motion_start_times_offset)
+        self._global_offset.copy_(clock.global_offset)
+        self._sampled_motion_ids.copy_(clock.sampled_motion_ids)
+
+    @property
+    def rwd_specs(self) -> Dict[str, float]:
+        return self._rwd_specs
+
+    def set_termination_distances(self, termination_distances):  # :1338-1339
+        self._termination_distances[:] = termination_distances
+
+    def toggle_eval_mode(self):  # :1426-1440 (motion-lib swap is out of scope)
+        self.flag_im_eval = True
+        self.set_termination_distances(0.5)
+        if len(self._reset_bodies_id) > 15:
+            self._reset_bodies_id = self._eval_track_bodies_id
+        self._step_args = None
+
+    def untoggle_eval_mode(self):
+        self.flag_im_eval = False
+        self._termination_distances[:] = self._termination_distances_backup
+        self._reset_bodies_id = self._reset_bodies_id_backup
+        self._step_args = None
+
+    # ------------------------------------------------------------------------------------
+    # fused path
+    # ------------------------------------------------------------------------------------
+    def _build_step_args(self, advance: bool):
+        body, keep = _cabi.body_state(
+            self._rigid_body_pos, self._rigid_body_rot, self._rigid_body_vel, self._rigid_body_ang_vel
+        )
+        mask = 0
+        for b in self._reset_bodies_id.tolist():
+            mask |= 1 << int(b)
+        a = _cabi.PhcStepArgs()
+        a.body = body
+        a.progress_buf = self.progress_buf.data_ptr()
+        a.motion_start_times = self._motion_start_times.data_ptr()
+        a.motion_start_times_offset = self._motion_start_times_offset.data_ptr()
+        a.global_offset = self._global_offset.data_ptr()
+        a.sampled_motion_ids = self._sampled_motion_ids.data_ptr()
+        a.termination_distances = self._termination_distances.data_ptr()
+        a.reset_body_mask = mask
+        a.use_mean = 1 if self.flag_im_eval else 0
+        a.enable_early_termination = 1 if self.enable_early_termination else 0
+        a.advance_progress = 1 if advance else 0
+        a.time_steps = self.time_steps
+        a.dt = self.dt
+        a.rwd = _cabi.reward_spec(self._rwd_specs)
+        a.obs_buf = self.obs_buf.data_ptr()
+        a.obs_stride = self.obs_buf.stride(0)
+        a.rew_buf = self.rew_buf.data_ptr()
+        a.reward_raw = self.reward_raw.data_ptr()
+        a.reward_raw_stride = self.reward_raw.stride(0)
+        # torch.bool is one byte holding 0/1 — the kernel writes uint8 0/1 straight into it
+        a.reset_buf = self.reset_buf.data_ptr()
+        a.terminate_buf = self._terminate_buf.data_ptr()
+        a.obs_moments = self.obs_moments.data_ptr() if self.obs_moments is not None else None
+        self._step_args = (a, advance, keep)
+        return a
+
+    def post_physics_step(self, advance_progress: bool = True):
+        """progress += 1; reward; reset; observations (humanoid_phc.py:138-149) — one launch."""
+        if self._step_args is None or self._step_args[1] != advance_progress:
+            self._build_step_args(advance_progress)
+        a = self._step_args[0]
+        _cabi.check(
+            _cabi.load().phc_step_fused(
+                self._motion_lib.handle, C.byref(a), self.num_envs, _cabi.stream_ptr(self.device)
+            ),
+            "phc_step_fused",
+        )
+        if self.obs_moments is not None:
+            self.obs_moment_rows += self.num_envs
+
+    def step(self, actions=None):
+        """The reference's ``step`` minus PD targets and PhysX (both out of scope): the caller
+        has already written the post-physics rigid-body state."""
+        self.post_physics_step(True)
+        self.extras["terminate"] = self._terminate_buf
+        self.extras["reward_raw"] = self.reward_raw
+        return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # ------------------------------------------------------------------------------------
+    # the reference's decomposition, on the per-function kernels
+    # ------------------------------------------------------------------------------------
+    def _motion_times(self, env_ids=None, plus: int = 0):
+        p = self.progress_buf if env_ids is None else self.progress_buf[env_ids]
+        s = self._motion_start_times if env_ids is None else self._motion_start_times[env_ids]
+        o = self._motion_start_times_offset if env_ids is None else self._motion_start_times_offset[env_ids]
+        return (p + plus) * self.dt + s + o if plus else p * self.dt + s + o
+
+    def _compute_reward(self):  # :1230-1271
+        t = self._motion_times()
+        ref = self._motion_lib.get_motion_state(self._sampled_motion_ids, t, self._global_offset)
+        pos, rot, vel, ang = self._rigid_body_pos, self._rigid_body_rot, self._rigid_body_vel, self._rigid_body_ang_vel
+        self.rew_buf[:], self.reward_raw[:, :4] = compute_imitation_reward(
+            pos[..., 0, :], rot[..., 0, :], pos, rot, vel, ang,
+            ref["rg_pos"], ref["rb_rot"], ref["body_vel"], ref["body_ang_vel"], self.rwd_specs,
+        )  # fmt: skip
+
+    def _compute_reset(self):  # :1313-1335
+        t = self._motion_times()
+        pass_time = t >= self._motion_lib._motion_lengths[self._sampled_motion_ids]
+        ref = self._motion_lib.get_motion_state(self._sampled_motion_ids, t, self._global_offset)
+        ids = self._reset_bodies_id
+        self.reset_buf[:], self._terminate_buf[:] = compute_humanoid_im_reset(
+            self.reset_buf, self.progress_buf, None, None,
+            self._rigid_body_pos[..., ids, :].clone(), ref["rg_pos"][..., ids, :].clone(), pass_time,
+            self.enable_early_termination, self._termination_distances[..., ids], self.flag_im_eval,
+        )  # fmt: skip
+
+    def _compute_humanoid_obs(self, env_ids=None):  # :963-998
+        sel = (lambda x: x) if env_ids is None else (lambda x: x[env_ids])
+        return compute_humanoid_observations_smpl_max(
+            sel(self._rigid_body_pos), sel(self._rigid_body_rot), sel(self._rigid_body_vel),
+            sel(self._rigid_body_ang_vel), None, None, True, True, True, False, False,
+        )  # fmt: skip
+
+    def _compute_task_obs(self, env_ids=None):  # :1050-1123
+        sel = (lambda x: x) if env_ids is None else (lambda x: x[env_ids])
+        pos, rot = sel(self._rigid_body_pos), sel(self._rigid_body_rot)
+        vel, ang = sel(self._rigid_body_vel), sel(self._rigid_body_ang_vel)
+        ids, off = sel(self._sampled_motion_ids), sel(self._global_offset)
+        refs = [self._motion_lib.get_motion_state(ids, self._motion_times(env_ids, k), off)
+                for k in range(1, self.time_steps + 1)]  # fmt: skip
+
+        def stack(key):
+            if len(refs) == 1:
+                return refs[0][key]
+            return torch.stack([r[key] for r in refs], dim=1).flatten(0, 1)
+
+        return compute_imitation_observations_v6(
+            pos[..., 0, :], rot[..., 0, :], pos, rot, vel, ang,
+            stack("rg_pos"), stack("rb_rot"), stack("body_vel"), stack("body_ang_vel"), self.time_steps, True,
+        )  # fmt: skip
+
+    def _compute_observations(self, env_ids=None):  # :937-961
+        obs = torch.cat([self._compute_humanoid_obs(env_ids), self._compute_task_obs(env_ids)], dim=-1)
+        if env_ids is None:
+            self.obs_buf[:] = obs
+        else:
+            self.obs_buf[env_ids] = obs
+        return obs
+
+    def post_physics_step_unfused(self):
+        """Same result as ``post_physics_step`` through the per-function kernels."""
+        self.progress_buf += 1
+        self._compute_reward()
+        self._compute_reset()
+        self._compute_observations()

@@ -1,0 +1,85 @@
+"""Observation normaliser with multi-GPU statistics (PHC/policies/running_norm.py).
+
+``update(x)`` reproduces ``RunningNorm.update`` (:23-34): batch mean, biased variance,
+blend with weight 1/count, count += 1.  The batch statistics come from per-column fp64
+sum / sum-of-squares partials produced on the device (``phc_obs_moments`` over a rollout
+buffer, or accumulated by the fused step's epilogue); when ``torch.distributed`` is
+initialised the partials and the row count are summed with ONE all-reduce (NCCL over
+NVLink on GPUs) — the only collective anywhere on the path — so every rank ends with the
+statistics of the concatenated batch.  Buffers keep the reference's names, shapes and
+dtypes so a ``state_dict`` stays interchangeable.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _cabi
+
+
+class RunningNorm(nn.Module):
+    def __init__(self, shape: int, epsilon: float = 1e-5, clip: float = 10.0, device="cuda"):
+        super().__init__()
+        self.register_buffer("running_mean", torch.zeros((1, shape), dtype=torch.float32, device=device))
+        self.register_buffer("running_var", torch.ones((1, shape), dtype=torch.float32, device=device))
+        self.register_buffer("count", torch.ones(1, dtype=torch.float32, device=device))
+        self.epsilon = epsilon
+        self.clip = clip
+        self.shape = shape
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:  # :15-20
+        _cabi.require_cuda(x, "x", torch.float32)
+        x2 = x.reshape(-1, self.shape)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        out = torch.empty_like(x2, memory_format=torch.contiguous_format)
+        _cabi.check(
+            _cabi.load().phc_running_norm_forward(
+                x2.data_ptr(), x2.shape[0], self.shape, x2.stride(0), self.running_mean.data_ptr(),
+                self.running_var.data_ptr(), self.epsilon, self.clip, out.data_ptr(), out.stride(0),
+                _cabi.stream_ptr(x.device),
+            ),
+            "phc_running_norm_forward",
+        )  # fmt: skip
+        return out.view(x.shape)
+
+    @torch.no_grad()
+    def moments(self, x: torch.Tensor, sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Accumulate the per-column fp64 [sum | sum of squares] of x [rows, shape] into ``sums``."""
+        _cabi.require_cuda(x, "x", torch.float32)
+        assert x.dim() == 2 and x.shape[1] == self.shape, "x must be 2D [rows, shape]"
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        if sums is None:
+            sums = torch.zeros(2 * self.shape, dtype=torch.float64, device=x.device)
+        _cabi.check(
+            _cabi.load().phc_obs_moments(
+                x.data_ptr(), x.shape[0], self.shape, x.stride(0), sums.data_ptr(), _cabi.stream_ptr(x.device)
+            ),
+            "phc_obs_moments",
+        )
+        return sums
+
+    @torch.no_grad()
+    def update_from_moments(self, sums: torch.Tensor, rows: int, group=None):
+        """Blend statistics given local partials; all-reduces them first when distributed."""
+        payload = torch.cat([sums, torch.tensor([float(rows)], dtype=torch.float64, device=sums.device)])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
+        n = 2 * self.shape
+        _cabi.check(
+            _cabi.load().phc_running_norm_update(
+                self.running_mean.data_ptr(), self.running_var.data_ptr(), self.count.data_ptr(),
+                payload.data_ptr(), payload[n:].data_ptr(), self.shape, _cabi.stream_ptr(sums.device),
+            ),
+            "phc_running_norm_update",
+        )  # fmt: skip
+
+    @torch.no_grad()
+    def update(self, x: torch.Tensor, group=None):  # :23-34
+        x = x.float()
+        self.update_from_moments(self.moments(x), x.shape[0], group)

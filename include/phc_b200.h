@@ -1,0 +1,261 @@
+/*
+ * phc_b200.h — C ABI of the B200-native PHC step path (libphc_b200.so).
+ *
+ * The reference (howird/humanoid, packages/puffer-phc) has no FFI for this path: the
+ * boundary is a set of plain Python call signatures.  Each entry point
+ * below is the native function the Python drop-in of one of those signatures binds with
+ * ctypes; the reference interface it replaces is cited as file:line relative to
+ * packages/puffer-phc/puffer_phc/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host; fp32 unless typed;
+ *     quaternions are xyzw;
+ *   - nothing is allocated, retained or freed on behalf of the caller except the opaque
+ *     handles (PhcLib borrows the motion tensors; the caller keeps them alive);
+ *   - all functions return 0 on success and a negative PHC_ERR_* code otherwise, never
+ *     throw, never synchronise (except the *_host_* pipeline, which returns when the host
+ *     buffers are filled) and launch on the stream passed last, so they can be captured
+ *     in a CUDA graph;
+ *   - views of rigid-body state carry element strides so that the reference's stride-13
+ *     AoS views (envs/humanoid_phc.py:542-549) and contiguous tensors both work; the last
+ *     dimension (3 or 4 floats) must be contiguous.
+ */
+#ifndef PHC_B200_H_
+#define PHC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHC_ABI_VERSION 1
+#define PHC_NUM_BODIES 24      /* SMPL humanoid, body_sets.py:11-36 */
+#define PHC_SELF_OBS_DIM 358   /* envs/humanoid_phc.py:461 */
+#define PHC_TASK_OBS_DIM 576   /* per future step, envs/humanoid_phc.py:464 */
+#define PHC_MAX_TIME_STEPS 16
+
+typedef struct CUstream_st* phc_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define PHC_API __attribute__((visibility("default")))
+#else
+#define PHC_API
+#endif
+
+enum {
+  PHC_OK = 0,
+  PHC_ERR_NULL = -1,        /* required pointer is NULL */
+  PHC_ERR_SHAPE = -2,       /* size / count out of range */
+  PHC_ERR_ALIGN = -3,       /* pointer or stride not aligned as required */
+  PHC_ERR_UNSUPPORTED = -4, /* valid in the reference, not implemented here */
+  PHC_ERR_CUDA = -5,        /* CUDA runtime error (phc_last_cuda_error() has the code) */
+  PHC_ERR_ALLOC = -6
+};
+
+PHC_API const char* phc_strerror(int code);
+PHC_API int phc_abi_version(void);
+PHC_API int phc_last_cuda_error(void); /* cudaError_t of the last PHC_ERR_CUDA on this thread */
+
+/* ------------------------------------------------------------------------------------
+ * Motion library — the tensor set MotionLibBase.load_motions leaves on the device
+ * (motion_lib.py:396-420).  F = total frames of all clips, M = clips.
+ * ---------------------------------------------------------------------------------- */
+typedef struct PhcLibDesc {
+  const float* gts;   /* [F,24,3] global translation            motion_lib.py:407 */
+  const float* grs;   /* [F,24,4] global rotation                motion_lib.py:408 */
+  const float* lrs;   /* [F,24,4] local rotation (may be NULL if dof_pos is never asked) */
+  const float* gvs;   /* [F,24,3] global linear velocity         motion_lib.py:413 */
+  const float* gavs;  /* [F,24,3] global angular velocity        motion_lib.py:412 */
+  const float* dvs;   /* [F,23,3] dof velocity (may be NULL)     motion_lib.py:414 */
+  const float* motion_aa;           /* [F,72] (may be NULL)      motion_lib.py:399 */
+  const float* motion_lengths;      /* [M] seconds               motion_lib.py:396 */
+  const int64_t* motion_num_frames; /* [M]                       motion_lib.py:402 */
+  const float* motion_dt;           /* [M]                       motion_lib.py:401 */
+  const int64_t* length_starts;     /* [M] first frame of clip   motion_lib.py:416-419 */
+  const float* motion_bodies;       /* [M,17] (may be NULL)      motion_lib.py:398 */
+  const float* motion_limb_weights; /* [M,10] (may be NULL)      motion_lib.py:403 */
+  int64_t total_frames;             /* F */
+  int64_t num_motions;              /* M */
+} PhcLibDesc;
+
+typedef struct PhcLib PhcLib;
+PHC_API int phc_lib_create(const PhcLibDesc* desc, PhcLib** out);
+PHC_API void phc_lib_destroy(PhcLib* lib);
+
+/* [n, J, C] fp32 view, innermost C contiguous; strides in elements. */
+typedef struct PhcView {
+  const float* ptr;
+  int64_t stride_env;
+  int64_t stride_body;
+} PhcView;
+
+/* The four views the env hands to the path (envs/humanoid_phc.py:546-549). */
+typedef struct PhcBodyState {
+  PhcView pos;     /* [n,J,3] */
+  PhcView rot;     /* [n,J,4] */
+  PhcView vel;     /* [n,J,3] */
+  PhcView ang_vel; /* [n,J,3] */
+  int32_t num_bodies; /* J */
+} PhcBodyState;
+
+/* MotionLibBase._calc_frame_blend(time, len, num_frames, dt)      motion_lib.py:655-665 */
+PHC_API int phc_calc_frame_blend(const float* time, const float* len, const int64_t* num_frames, const float* dt,
+                         int64_t n, int64_t* frame_idx0, int64_t* frame_idx1, float* blend,
+                         phc_stream_t stream);
+
+/* Outputs of get_motion_state; any pointer may be NULL (that output is skipped).  All are
+ * dense row-major with the shapes of the reference's dict (motion_lib.py:611-626). */
+typedef struct PhcMotionOut {
+  float* root_pos;            /* [n,3]    */
+  float* root_rot;            /* [n,4]    */
+  float* dof_pos;             /* [n,69]   */
+  float* root_vel;            /* [n,3]    */
+  float* root_ang_vel;        /* [n,3]    */
+  float* dof_vel;             /* [n,69]   */
+  float* motion_aa;           /* [n,72]   frame f0, not blended */
+  float* rg_pos;              /* [n,24,3] */
+  float* rb_rot;              /* [n,24,4] */
+  float* body_vel;            /* [n,24,3] */
+  float* body_ang_vel;        /* [n,24,3] */
+  float* motion_bodies;       /* [n,17]   */
+  float* motion_limb_weights; /* [n,10]   */
+  int64_t* frame_idx0;        /* [n] clip-local, extra (for parity tests) */
+  int64_t* frame_idx1;        /* [n] */
+  float* blend;               /* [n] */
+} PhcMotionOut;
+
+/* MotionLibBase.get_motion_state(motion_ids, motion_times, offset=None)  motion_lib.py:549-626 */
+PHC_API int phc_motion_state(const PhcLib* lib, const int64_t* motion_ids, const float* motion_times,
+                     const float* offset_or_null /* [n,3] */, int64_t n, const PhcMotionOut* out,
+                     phc_stream_t stream);
+
+/* compute_humanoid_observations_smpl_max(...)                        envs/common.py:23-103
+ * Writes [root_h? | local pos 3(J-1) | rot 6J | vel 3J | ang vel 3J] per row; the optional
+ * smpl / limb-weight columns are appended by the caller (they are copies of inputs). */
+#define PHC_OBS_LOCAL_ROOT 1u   /* local_root_obs   */
+#define PHC_OBS_ROOT_HEIGHT 2u  /* root_height_obs  */
+#define PHC_OBS_UPRIGHT 4u      /* upright          */
+PHC_API int phc_self_obs_smpl_max(const PhcBodyState* body, int64_t n, uint32_t flags, float* out,
+                          int64_t out_stride, phc_stream_t stream);
+
+/* compute_imitation_observations_v6(root_pos, root_rot, body_*, ref_body_*, time_steps,
+ * upright)                                                          envs/common.py:106-176
+ * ref is [n*T, J, .] (env-major, then t).  mode 6 -> 24*J floats per future step;
+ * mode 7 -> the position/velocity column subset [d_pos | d_vel | l_pos], 9*J per step
+ * (the reference has no v7). */
+PHC_API int phc_imitation_obs(const float* root_pos, int64_t root_pos_stride, const float* root_rot,
+                      int64_t root_rot_stride, const PhcBodyState* body, const PhcBodyState* ref,
+                      int64_t n, int32_t time_steps, int32_t upright, int32_t mode, float* out,
+                      int64_t out_stride, phc_stream_t stream);
+
+/* rwd_specs of compute_imitation_reward (config.py:38-46). */
+typedef struct PhcRewardSpec {
+  float k_pos, k_rot, k_vel, k_ang_vel;
+  float w_pos, w_rot, w_vel, w_ang_vel;
+} PhcRewardSpec;
+
+/* compute_imitation_reward(root_pos, root_rot, body_*, ref_body_*, rwd_specs)
+ *                                                                   envs/common.py:270-322 */
+PHC_API int phc_imitation_reward(const PhcBodyState* body, const PhcBodyState* ref, int64_t n,
+                         const PhcRewardSpec* spec, float* reward /* [n] */,
+                         float* reward_raw /* [n,4] */, int64_t reward_raw_stride,
+                         phc_stream_t stream);
+
+/* compute_humanoid_im_reset(reset_buf, progress_buf, contact_buf, contact_body_ids,
+ * rigid_body_pos, ref_body_pos, pass_time, enable_early_termination, termination_distance,
+ * use_mean)                                                         envs/common.py:325-364
+ * contact_buf / contact_body_ids are never read by the reference and are not taken. */
+PHC_API int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_pos, int32_t num_reset_bodies,
+                 const int16_t* progress_buf, const uint8_t* pass_time,
+                 const float* termination_distance /* [R] */, int32_t enable_early_termination,
+                 int32_t use_mean, int64_t n, uint8_t* reset, uint8_t* terminated,
+                 phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * The fused step: the post-physics half of HumanoidPHC.step   envs/humanoid_phc.py:138-149
+ *   progress_buf += 1 (:138); _compute_reward (:1230-1271); _compute_reset (:1313-1335);
+ *   _compute_observations (:937-961) = smpl_max self obs (:963-998) + v6 task obs at
+ *   t+dt .. t+T*dt (:1050-1123), written as one row of obs_buf.
+ * One kernel; no host reads; graph-capturable.
+ * ---------------------------------------------------------------------------------- */
+typedef struct PhcStepArgs {
+  PhcBodyState body;                     /* sim state views, J must be 24               */
+  int16_t* progress_buf;                 /* [n] in/out                  humanoid_phc.py:571 */
+  const float* motion_start_times;       /* [n]                         humanoid_phc.py:592 */
+  const float* motion_start_times_offset;/* [n]                         humanoid_phc.py:593 */
+  const float* global_offset;            /* [n,3] or NULL               humanoid_phc.py:591 */
+  const int64_t* sampled_motion_ids;     /* [n]                         humanoid_phc.py:597 */
+  const float* termination_distances;    /* [24]                        humanoid_phc.py:240 */
+  uint32_t reset_body_mask;              /* bit b = body b is in _reset_bodies_id       */
+  int32_t use_mean;                      /* flag_im_eval                humanoid_phc.py:1334 */
+  int32_t enable_early_termination;      /* config.py:99                                */
+  int32_t advance_progress;              /* 1: progress_buf += 1 first, as step() does  */
+  int32_t time_steps;                    /* future reference frames T (1 in the env)    */
+  float dt;                              /* isaac_base.dt = 2*(1/60)    isaacgym_env.py:41 */
+  PhcRewardSpec rwd;
+  float* obs_buf;                        /* [n, 358+576*T]              humanoid_phc.py:557 */
+  int64_t obs_stride;
+  float* rew_buf;                        /* [n]                         humanoid_phc.py:560 */
+  float* reward_raw;                     /* [n, >=4]                    humanoid_phc.py:562 */
+  int64_t reward_raw_stride;
+  uint8_t* reset_buf;                    /* [n] bool                    humanoid_phc.py:573 */
+  uint8_t* terminate_buf;                /* [n] bool                    humanoid_phc.py:575 */
+  double* obs_moments;                   /* NULL, or [2*(358+576*T)] fp64: per-column sum
+                                            and sum of squares accumulated (+=) for
+                                            RunningNorm.update           running_norm.py:23 */
+} PhcStepArgs;
+
+PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Host-buffer pipeline around the fused step (the end-to-end call): chunked
+ * H2D(sim state, clock) -> phc_step_fused -> D2H(obs, reward, flags) on internal streams.
+ * All pointers in PhcHostStepArgs are HOST pointers (pinned for full speed).
+ * ---------------------------------------------------------------------------------- */
+typedef struct PhcHostStep PhcHostStep;
+
+typedef struct PhcHostStepArgs {
+  const float* state;                    /* host [n, 24, 13] AoS sim state              */
+  int16_t* progress_buf;                 /* host [n] in/out                             */
+  const float* motion_start_times;       /* host [n]                                    */
+  const float* motion_start_times_offset;/* host [n]                                    */
+  const float* global_offset;            /* host [n,3]                                  */
+  const int64_t* sampled_motion_ids;     /* host [n]                                    */
+  float* obs_buf;                        /* host [n, 358+576*T]                         */
+  float* rew_buf;                        /* host [n]                                    */
+  float* reward_raw;                     /* host [n,4]                                  */
+  uint8_t* reset_buf;                    /* host [n]                                    */
+  uint8_t* terminate_buf;                /* host [n]                                    */
+} PhcHostStepArgs;
+
+PHC_API int phc_host_step_create(const PhcLib* lib, int64_t max_envs, int32_t time_steps, int32_t num_chunks,
+                         const float* termination_distances_host /* [24] */, uint32_t reset_body_mask,
+                         int32_t use_mean, int32_t enable_early_termination, float dt,
+                         const PhcRewardSpec* rwd, PhcHostStep** out);
+PHC_API int phc_host_step(PhcHostStep* ctx, const PhcHostStepArgs* args, int64_t n);
+PHC_API void phc_host_step_destroy(PhcHostStep* ctx);
+PHC_API int64_t phc_host_step_h2d_bytes(const PhcHostStep* ctx, int64_t n);
+PHC_API int64_t phc_host_step_d2h_bytes(const PhcHostStep* ctx, int64_t n);
+
+/* ------------------------------------------------------------------------------------
+ * RunningNorm statistics                                   policies/running_norm.py:23-34
+ * phc_obs_moments accumulates (+=) per-column fp64 sum and sum of squares of x[rows,cols]
+ * into sums[2*cols]; the caller all-reduces sums (and the row count) across GPUs, then
+ * phc_running_norm_update applies mean/var(unbiased=False) with the reference's 1/count
+ * blend to the fp32 running buffers in place.
+ * ---------------------------------------------------------------------------------- */
+PHC_API int phc_obs_moments(const float* x, int64_t rows, int64_t cols, int64_t row_stride, double* sums,
+                    phc_stream_t stream);
+PHC_API int phc_running_norm_update(float* running_mean, float* running_var, float* count, const double* sums,
+                            const double* total_rows /* device scalar */, int64_t cols,
+                            phc_stream_t stream);
+/* RunningNorm.forward                                      policies/running_norm.py:15-20 */
+PHC_API int phc_running_norm_forward(const float* x, int64_t rows, int64_t cols, int64_t row_stride,
+                             const float* running_mean, const float* running_var, float epsilon,
+                             float clip, float* out, int64_t out_stride, phc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHC_B200_H_ */

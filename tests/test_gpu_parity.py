@@ -1,0 +1,431 @@
+"""GPU: the CUDA path (through the C ABI) against the reference-generated fixtures and the oracle."""
+
+import pytest
+import torch
+
+from conftest import STEP_CASES, assert_close, assert_equal_exact
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from humanoid_b200 import (
+        MotionLib,
+        compute_humanoid_im_reset,
+        compute_humanoid_observations_smpl_max,
+        compute_imitation_observations_v6,
+        compute_imitation_observations_v7,
+        compute_imitation_reward,
+        synth,
+    )
+    from oracle import phc_oracle as O
+    from util_gpu import (DEV, DOF_TOL, OBS_TOL, clock_from_golden, env_from, lib_from_golden, make_case_cpu,
+                          oracle_step)  # fmt: skip
+
+MOTION_KEYS = (
+    "root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "motion_aa",
+    "rg_pos", "rb_rot", "body_vel", "body_ang_vel", "motion_bodies", "motion_limb_weights",
+)  # fmt: skip
+
+
+def cuda(x):
+    return x.to(DEV)
+
+
+# ---------------------------------------------------------------------------------------
+# integer path
+# ---------------------------------------------------------------------------------------
+def test_frame_blend_bit_exact(golden):
+    g = golden("frame_blend")
+    lib = MotionLib(synth.make_motion_lib(2, 4, 6), device=DEV)
+    i0, i1, bl = lib._calc_frame_blend(cuda(g.inp("time")), cuda(g.inp("len")), cuda(g.inp("num_frames")), cuda(g.inp("dt")))
+    assert_equal_exact(i0, g.out("frame_idx0"), "frame_idx0")
+    assert_equal_exact(i1, g.out("frame_idx1"), "frame_idx1")
+    assert torch.equal(bl.cpu(), g.out("blend")), "blend is IEEE +-*/ only: must be bit-exact"
+
+
+def test_frame_blend_env_clock_regime_bit_exact():
+    """progress*dt + k/30 lands on frame boundaries (SURVEY §7 hard part 1): 1M random draws."""
+    gen = torch.Generator().manual_seed(77)
+    n = 1 << 20
+    nf = torch.randint(2, 7000, (n,), generator=gen)
+    fps = torch.tensor([30.0, 60.0, 120.0], dtype=torch.float64)[torch.randint(0, 3, (n,), generator=gen)]
+    dt = (1.0 / fps).float()
+    ln = ((1.0 / fps) * (nf - 1)).float()
+    k = (torch.rand(n, generator=gen) * nf).long()
+    p = torch.randint(0, 400, (n,), generator=gen).to(torch.int16)
+    t = p * synth.SIM_DT + (k * (1 / 30)).float()
+    want = O.frame_blend(t, ln, nf, dt)
+    lib = MotionLib(synth.make_motion_lib(2, 4, 6), device=DEV)
+    got = lib._calc_frame_blend(cuda(t), cuda(ln), cuda(nf), cuda(dt))
+    assert_equal_exact(got[0], want[0], "frame_idx0")
+    assert_equal_exact(got[1], want[1], "frame_idx1")
+    assert torch.equal(got[2].cpu(), want[2])
+
+
+# ---------------------------------------------------------------------------------------
+# motion state
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", STEP_CASES)
+@pytest.mark.parametrize("which", ["t0", "t1"])
+def test_motion_state_vs_reference_fixture(golden, case, which):
+    g = golden(case)
+    lib = MotionLib(lib_from_golden(g), device=DEV)
+    c = clock_from_golden(g)
+    res = lib.get_motion_state(cuda(c.sampled_motion_ids), cuda(g.out(which)), cuda(c.global_offset), with_frame_info=True)
+    assert_equal_exact(res["frame_idx0"], g.out(f"{which}.frame_idx0"), "frame_idx0")
+    assert_equal_exact(res["frame_idx1"], g.out(f"{which}.frame_idx1"), "frame_idx1")
+    assert torch.equal(res["blend"].cpu(), g.out(f"{which}.blend"))
+    for k in MOTION_KEYS:
+        tol = DOF_TOL if k == "dof_pos" else OBS_TOL
+        assert_close(res[k], g.out(f"{which}.{k}"), what=f"{case}/{which}/{k}", **tol)
+    for k in ("motion_aa", "motion_bodies", "motion_limb_weights"):  # pure gathers
+        assert torch.equal(res[k].cpu(), g.out(f"{which}.{k}")), k
+
+
+def test_motion_state_no_offset_and_negative_times(golden):
+    g = golden("flags")
+    lib_data = lib_from_golden(g)
+    lib = MotionLib(lib_data, device=DEV)
+    ids, t = g.inp("clock.sampled_motion_ids"), g.inp("t")
+    res = lib.get_motion_state(cuda(ids), cuda(t), None)
+    assert_close(res["rg_pos"], g.out("rg_pos.no_offset"), what="no offset", **OBS_TOL)
+    t2 = t - 0.3
+    want = O.OracleMotionLib(lib_data).get_motion_state(ids, t2, None)
+    got = lib.get_motion_state(cuda(ids), cuda(t2), None, with_frame_info=True)
+    assert_equal_exact(got["frame_idx0"], want["frame_idx0"], "idx0 (t<0)")
+    assert_close(got["rb_rot"], want["rb_rot"], what="rb_rot (t<0)", **OBS_TOL)
+
+
+def test_slerp_branches_through_motion_state(golden):
+    """dot<0, |sin|<1e-3, |cos|>=1 (incl. non-unit inputs): one 2-frame clip per golden pair."""
+    g = golden("slerp")
+    q0, q1, t = g.inp("q0"), g.inp("q1"), g.inp("t").flatten()
+    n = q0.shape[0]
+    grs = torch.stack([q0, q1], dim=1).reshape(2 * n, 1, 4).expand(2 * n, 24, 4).contiguous()
+    dt = 1.0 / 30.0
+    data = synth.MotionData(
+        gts=torch.zeros(2 * n, 24, 3), grs=grs, lrs=grs.clone(), gvs=torch.zeros(2 * n, 24, 3),
+        gavs=torch.zeros(2 * n, 24, 3), dvs=torch.zeros(2 * n, 23, 3), motion_aa=torch.zeros(2 * n, 72),
+        motion_lengths=torch.full((n,), dt), motion_num_frames=torch.full((n,), 2, dtype=torch.int64),
+        motion_dt=torch.full((n,), dt), motion_fps=torch.full((n,), 30.0),
+        length_starts=torch.arange(n, dtype=torch.int64) * 2, motion_bodies=torch.zeros(n, 17),
+        motion_limb_weights=torch.zeros(n, 10),
+    )  # fmt: skip
+    lib = MotionLib(data, device=DEV)
+    ids = torch.arange(n)
+    times = (t * dt).float() * 0.999  # stay inside the clip so idx0 == 0
+    res = lib.get_motion_state(cuda(ids), cuda(times), None, with_frame_info=True)
+    assert int(res["frame_idx0"].max()) == 0
+    blend = res["blend"].cpu()
+    want = O.slerp(q0, q1, blend[:, None])
+    assert not torch.isnan(want).any()
+    assert_close(res["rb_rot"][:, 0], want, what="slerp", **OBS_TOL)
+    assert_close(res["rb_rot"][:, 23], want, what="slerp (last body)", **OBS_TOL)
+    want_dof = O.exp_map(O.slerp(q0, q1, blend[:, None]))
+    assert_close(res["dof_pos"][:, 0:3], want_dof, what="exp_map", rtol=2e-4, atol=5e-5)
+    # rows whose result is far from the identity are well conditioned: tight tolerance there
+    far = want[:, 3].abs() < 0.99
+    assert far.sum() > 100
+    assert_close(res["dof_pos"][:, 0:3][far], want_dof[far], what="exp_map (well conditioned)", **OBS_TOL)
+
+
+# ---------------------------------------------------------------------------------------
+# whole step: fused kernel and the per-function decomposition, vs the reference fixtures
+# ---------------------------------------------------------------------------------------
+def _run_env(g, fused):
+    T = int(g.inp("time_steps"))
+    env = env_from(lib_from_golden(g), clock_from_golden(g), g.inp("state"), time_steps=T,
+                   enable_early_termination=bool(g.inp("early")))  # fmt: skip
+    env.set_termination_distances(cuda(g.inp("term_dist")))
+    ids = g.inp("reset_body_ids")
+    if ids.numel() != 24:
+        env._reset_bodies_id = cuda(ids)
+        env._step_args = None
+    env.flag_im_eval = bool(g.inp("use_mean"))
+    if fused:
+        env.step()
+    else:
+        env.post_physics_step_unfused()
+    torch.cuda.synchronize()
+    return env
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "per_function"])
+@pytest.mark.parametrize("case", STEP_CASES)
+def test_step_vs_reference_fixture(golden, case, fused):
+    g = golden(case)
+    env = _run_env(g, fused)
+    assert_equal_exact(env.progress_buf, g.out("progress_after"), "progress_buf")
+    assert_equal_exact(env.reset_buf, g.out("reset"), "reset_buf")
+    assert_equal_exact(env._terminate_buf, g.out("terminated"), "_terminate_buf")
+    assert_close(env.obs_buf, g.out("obs"), what="obs_buf", **OBS_TOL)
+    assert_close(env.rew_buf, g.out("reward"), what="rew_buf", **OBS_TOL)
+    assert_close(env.reward_raw[:, :4], g.out("reward_raw"), what="reward_raw", **OBS_TOL)
+
+
+def test_flag_variants_vs_reference_fixture(golden):
+    g = golden("flags")
+    state = cuda(g.inp("state"))
+    pos, rot, vel, ang = synth.body_views(state)
+    smpl, limb = cuda(g.inp("smpl")), cuda(g.inp("limb"))
+    for name in ("default", "not_upright", "global_root", "no_height", "with_params", "all_off"):
+        fl = [bool(x) for x in g.inp(f"self.{name}")]
+        o = compute_humanoid_observations_smpl_max(pos, rot, vel, ang, smpl, limb, *fl)
+        assert_close(o, g.out(f"self.{name}"), what=f"self obs {name}", **OBS_TOL)
+    ref = {k: cuda(v) for k, v in g.group("in.ref").items()}
+    o = compute_imitation_observations_v6(pos[:, 0], rot[:, 0], pos, rot, vel, ang, ref["rg_pos"], ref["rb_rot"],
+                                          ref["body_vel"], ref["body_ang_vel"], 1, False)  # fmt: skip
+    assert_close(o, g.out("v6.not_upright"), what="v6 not upright", **OBS_TOL)
+    s = cuda(g.inp("subset"))
+    args = (pos[:, 0], rot[:, 0], pos[:, s], rot[:, s], vel[:, s], ang[:, s], ref["rg_pos"][:, s], ref["rb_rot"][:, s],
+            ref["body_vel"][:, s], ref["body_ang_vel"][:, s])  # fmt: skip
+    assert_close(compute_imitation_observations_v6(*args, 1, True), g.out("v6.subset12"), what="v6 subset", **OBS_TOL)
+    r, raw = compute_imitation_reward(*args, O.DEFAULT_RWD_SPECS)
+    assert_close(r, g.out("reward.subset12"), what="reward subset", **OBS_TOL)
+    assert_close(raw, g.out("reward_raw.subset12"), what="reward_raw subset", **OBS_TOL)
+
+
+def test_v7_is_the_v6_column_subset(golden):
+    g = golden("step_T10")
+    T = int(g.inp("time_steps"))
+    state = cuda(g.inp("state"))
+    pos, rot, vel, ang = synth.body_views(state)
+    lib_data, c = lib_from_golden(g), clock_from_golden(g)
+    ol = O.OracleMotionLib(lib_data)
+    p = c.progress_buf + 1
+    refs = [ol.get_motion_state(c.sampled_motion_ids, (p + k) * synth.SIM_DT + c.motion_start_times
+                                + c.motion_start_times_offset, c.global_offset) for k in range(1, T + 1)]  # fmt: skip
+    st = lambda key: cuda(torch.stack([r[key] for r in refs], 1).flatten(0, 1))  # noqa: E731
+    args = (pos[:, 0], rot[:, 0], pos, rot, vel, ang, st("rg_pos"), st("rb_rot"), st("body_vel"), st("body_ang_vel"), T, True)
+    v6 = compute_imitation_observations_v6(*args)
+    v7 = compute_imitation_observations_v7(*args)
+    assert_close(v6, g.out("task_obs"), what="v6 T=10", **OBS_TOL)
+    assert torch.equal(v7, v6[:, cuda(O.v7_columns(24, T))])
+
+
+# ---------------------------------------------------------------------------------------
+# larger seeded workloads vs the oracle (BASELINE configs 1, 2, 4, 5 at oracle-friendly sizes)
+# ---------------------------------------------------------------------------------------
+CASES = {
+    "config1_N256_M16": dict(num_envs=256, num_motions=16, seed=101, max_progress=30),
+    "config2_N4096_ids_arange": dict(num_envs=4096, num_motions=4096, seed=102, max_frames=120, max_progress=40),
+    "config4_random_ids_mixed_fps": dict(num_envs=2048, num_motions=96, seed=103, ids="random", aligned=False,
+                                         fps_choices=(30, 60, 120), min_frames=60, max_frames=900, max_progress=40),
+    "random_rotations": dict(num_envs=1024, num_motions=64, seed=104, rot_regime="random", max_progress=40),
+    "ragged_N1001": dict(num_envs=1001, num_motions=37, seed=105, max_progress=40),
+    "tiny_N1": dict(num_envs=1, num_motions=1, seed=106, max_progress=5),
+}  # fmt: skip
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fused_step_vs_oracle(name):
+    lib_data, clock, state = make_case_cpu(**CASES[name])
+    obs, rew, raw, reset, term, prog = oracle_step(lib_data, clock, state)
+    env = env_from(lib_data, clock, state)
+    env.step()
+    assert_equal_exact(env.progress_buf, prog, "progress")
+    assert_equal_exact(env.reset_buf, reset, f"{name}: reset")
+    assert_equal_exact(env._terminate_buf, term, f"{name}: terminated")
+    assert_close(env.obs_buf, obs, what=f"{name}: obs", **OBS_TOL)
+    assert_close(env.rew_buf, rew, what=f"{name}: reward", **OBS_TOL)
+    assert_close(env.reward_raw[:, :4], raw, what=f"{name}: reward_raw", **OBS_TOL)
+    if state.shape[0] >= 256:
+        assert 0.02 < term.float().mean() < 0.98, "workload should mix terminated / alive envs"
+
+
+def test_fused_step_T10_vs_oracle():
+    lib_data, clock, state = make_case_cpu(num_envs=512, num_motions=64, seed=107, max_progress=40)
+    obs, rew, raw, reset, term, prog = oracle_step(lib_data, clock, state, time_steps=10)
+    env = env_from(lib_data, clock, state, time_steps=10)
+    env.step()
+    assert env.obs_buf.shape == (512, 358 + 5760)
+    assert_close(env.obs_buf, obs, what="obs T=10", **OBS_TOL)
+    assert_equal_exact(env.reset_buf, reset, "reset")
+    assert_close(env.rew_buf, rew, what="reward", **OBS_TOL)
+
+
+def test_eval_mode_reset_vs_oracle():
+    lib_data, clock, state = make_case_cpu(num_envs=2048, num_motions=32, seed=108, max_progress=40)
+    eval_ids = torch.tensor([i for i in range(24) if i not in (4, 8, 18, 23)])
+    o = oracle_step(lib_data, clock, state, term=0.12, reset_body_ids=eval_ids, use_mean=True)
+    env = env_from(lib_data, clock, state)
+    env.toggle_eval_mode()
+    env.set_termination_distances(0.12)
+    env.step()
+    mism = (env._terminate_buf.cpu() != o[4]).sum().item()
+    # the mean over 20 bodies is summed in a different association than ATen's: a flag
+    # may differ only when the mean is within 1 ulp of the threshold
+    assert mism <= 1, f"{mism} eval-mode termination flags differ"
+    assert 0.05 < o[4].float().mean() < 0.95
+
+
+# ---------------------------------------------------------------------------------------
+# size-independent properties at BASELINE sizes (no oracle needed)
+# ---------------------------------------------------------------------------------------
+def _gpu_case(N, M, seed, **kw):
+    def query(lib_data, ids, times, offset):
+        return MotionLib(lib_data, device=DEV).get_motion_state(ids, times, offset)
+
+    return synth.make_case(N, M, query, seed=seed, device=DEV, **kw)
+
+
+@pytest.mark.parametrize("N,M", [(4096, 4096), (65536, 8192)])
+def test_fused_equals_per_function_kernels_bitwise(N, M):
+    lib_data, clock, state = _gpu_case(N, M, 201, max_frames=90, max_progress=40)
+    lib = MotionLib(lib_data, device=DEV)
+    from humanoid_b200 import HumanoidPHC
+
+    a = HumanoidPHC(lib, N, device=DEV)
+    b = HumanoidPHC(lib, N, device=DEV)
+    for env in (a, b):
+        env.set_sim_state(state)
+        env.set_clock(clock)
+    a.step()
+    b.post_physics_step_unfused()
+    assert torch.equal(a.obs_buf, b.obs_buf)
+    assert torch.equal(a.rew_buf, b.rew_buf)
+    assert torch.equal(a.reward_raw[:, :4], b.reward_raw[:, :4])
+    assert torch.equal(a.reset_buf, b.reset_buf) and torch.equal(a._terminate_buf, b._terminate_buf)
+    assert torch.equal(a.progress_buf, b.progress_buf)
+    assert 0.02 < a._terminate_buf.float().mean() < 0.98
+
+
+def test_env_partition_invariance_bitwise():
+    """Multi-GPU contract: envs [lo,hi) computed alone == the same rows of the whole batch."""
+    N = 16384
+    lib_data, clock, state = _gpu_case(N, 2048, 202, max_frames=90, max_progress=40)
+    lib = MotionLib(lib_data, device=DEV)
+    from humanoid_b200 import HumanoidPHC
+
+    whole = HumanoidPHC(lib, N, device=DEV)
+    whole.set_sim_state(state)
+    whole.set_clock(clock)
+    whole.step()
+    for lo, hi in ((0, 8192), (8192, 16384), (4099, 9001)):
+        part = HumanoidPHC(lib, hi - lo, device=DEV)
+        part.set_sim_state(state[lo:hi])
+        part.set_clock(synth.Clock(**{k: v[lo:hi] for k, v in clock.__dict__.items()}))
+        part.step()
+        assert torch.equal(part.obs_buf, whole.obs_buf[lo:hi])
+        assert torch.equal(part.rew_buf, whole.rew_buf[lo:hi])
+        assert torch.equal(part.reset_buf, whole.reset_buf[lo:hi])
+
+
+def test_strided_views_and_contiguous_inputs_agree():
+    lib_data, clock, state = _gpu_case(1536, 64, 203, max_progress=20)
+    wide = torch.zeros(1536, 27, 13, device=DEV)  # extra actors per env, as bodies_per_env > num_bodies
+    wide[:, :24] = state
+    pos, rot, vel, ang = synth.body_views(wide)
+    a = compute_humanoid_observations_smpl_max(pos, rot, vel, ang, None, None, True, True, True, False, False)
+    b = compute_humanoid_observations_smpl_max(pos.contiguous(), rot.contiguous(), vel.contiguous(), ang.contiguous(),
+                                               None, None, True, True, True, False, False)  # fmt: skip
+    assert torch.equal(a, b)
+    lib = MotionLib(lib_data, device=DEV)
+    from humanoid_b200 import HumanoidPHC
+
+    e1 = HumanoidPHC(lib, 1536, device=DEV)
+    e1.set_sim_state(state)
+    e1.set_clock(clock)
+    e1.step()
+    e2 = HumanoidPHC(lib, 1536, device=DEV, bodies_per_env=27)  # env stride 351: not 16-B aligned -> strided path
+    e2.set_sim_state(wide)
+    e2.set_clock(clock)
+    e2.step()
+    assert torch.equal(e1.obs_buf, e2.obs_buf) and torch.equal(e1.rew_buf, e2.rew_buf)
+
+
+def test_subset_env_ids_observations():
+    lib_data, clock, state = _gpu_case(512, 32, 204, max_progress=20)
+    lib = MotionLib(lib_data, device=DEV)
+    from humanoid_b200 import HumanoidPHC
+
+    env = HumanoidPHC(lib, 512, device=DEV)
+    env.set_sim_state(state)
+    env.set_clock(clock)
+    full = env._compute_observations().clone()
+    env.obs_buf.zero_()
+    ids = torch.tensor([3, 17, 200, 511], device=DEV)
+    sub = env._compute_observations(ids)
+    assert torch.equal(sub, full[ids]) and torch.equal(env.obs_buf[ids], full[ids])
+    assert float(env.obs_buf[0].abs().sum()) == 0.0
+
+
+def test_multi_step_trajectory_vs_oracle():
+    """Five consecutive steps with the clock advancing in-kernel."""
+    lib_data, clock, state = make_case_cpu(num_envs=300, num_motions=300, seed=109, min_frames=20, max_frames=40)
+    env = env_from(lib_data, clock, state)
+    ol = O.OracleMotionLib(lib_data)
+    prog = clock.progress_buf.clone()
+    for it in range(5):
+        want = O.step(ol, state, prog, clock.motion_start_times, clock.motion_start_times_offset, clock.global_offset,
+                      clock.sampled_motion_ids, torch.full((24,), 0.25), synth.SIM_DT)  # fmt: skip
+        env.step()
+        assert_equal_exact(env.progress_buf, prog, f"progress @{it}")
+        assert_equal_exact(env.reset_buf, want[3], f"reset @{it}")
+        assert_equal_exact(env._terminate_buf, want[4], f"terminated @{it}")
+        assert_close(env.obs_buf, want[0], what=f"obs @{it}", **OBS_TOL)
+        assert_close(env.rew_buf, want[1], what=f"reward @{it}", **OBS_TOL)
+
+
+def test_step_is_cuda_graph_capturable():
+    lib_data, clock, state = _gpu_case(2048, 128, 205, max_progress=10)
+    lib = MotionLib(lib_data, device=DEV)
+    from humanoid_b200 import HumanoidPHC
+
+    ref_env = HumanoidPHC(lib, 2048, device=DEV)
+    ref_env.set_sim_state(state)
+    ref_env.set_clock(clock)
+    for _ in range(3):
+        ref_env.step()
+    env = HumanoidPHC(lib, 2048, device=DEV)
+    env.set_sim_state(state)
+    env.set_clock(clock)
+    env.step()  # warm up (sets the smem attribute) outside capture
+    env.set_clock(clock)
+    graph = torch.cuda.CUDAGraph()
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(graph, stream=stream):
+            env.step()
+    torch.cuda.synchronize()
+    env.set_clock(clock)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(env.progress_buf, ref_env.progress_buf)
+    assert torch.equal(env.obs_buf, ref_env.obs_buf) and torch.equal(env.rew_buf, ref_env.rew_buf)
+
+
+def test_standalone_reset_and_reward_vs_oracle():
+    lib_data, clock, state = make_case_cpu(num_envs=777, num_motions=50, seed=110, max_progress=30)
+    ol = O.OracleMotionLib(lib_data)
+    t = synth.reward_time(clock, extra_steps=1)
+    ref = ol.get_motion_state(clock.sampled_motion_ids, t, clock.global_offset)
+    pos, rot, vel, ang = synth.body_views(state)
+    prog = (clock.progress_buf + 1).to(torch.int16)
+    pass_time = t >= lib_data.motion_lengths[clock.sampled_motion_ids]
+    term = torch.full((24,), 0.25)
+    want = O.im_reset(torch.ones(777, dtype=torch.bool), prog, None, None, pos.clone(), ref["rg_pos"], pass_time, True, term, False)
+    sc = cuda(state)
+    p, r, v, a = synth.body_views(sc)
+    got = compute_humanoid_im_reset(torch.ones(777, dtype=torch.bool, device=DEV), cuda(prog), None, None, p,
+                                    cuda(ref["rg_pos"]), cuda(pass_time), True, cuda(term), False)  # fmt: skip
+    assert got[0].dtype == torch.bool
+    assert_equal_exact(got[0], want[0], "reset")
+    assert_equal_exact(got[1], want[1], "terminated")
+    wr = O.imitation_reward(pos[:, 0], rot[:, 0], pos, rot, vel, ang, ref["rg_pos"], ref["rb_rot"], ref["body_vel"],
+                            ref["body_ang_vel"], O.DEFAULT_RWD_SPECS)  # fmt: skip
+    gr = compute_imitation_reward(p[:, 0], r[:, 0], p, r, v, a, cuda(ref["rg_pos"]), cuda(ref["rb_rot"]),
+                                  cuda(ref["body_vel"]), cuda(ref["body_ang_vel"]), O.DEFAULT_RWD_SPECS)  # fmt: skip
+    assert_close(gr[0], wr[0], what="reward", **OBS_TOL)
+    assert_close(gr[1], wr[1], what="reward_raw", **OBS_TOL)
+
+
+def test_empty_batch_is_a_no_op():
+    lib = MotionLib(synth.make_motion_lib(3, 5, 9), device=DEV)
+    res = lib.get_motion_state(torch.zeros(0, dtype=torch.int64, device=DEV), torch.zeros(0, device=DEV), None)
+    assert res["rg_pos"].shape == (0, 24, 3)
+    z = torch.zeros(0, 24, 13, device=DEV)
+    o = compute_humanoid_observations_smpl_max(*synth.body_views(z), None, None, True, True, True, False, False)
+    assert o.shape == (0, 358)

@@ -259,7 +259,7 @@ def run_gpu(args):
             envs[i % R].post_physics_step(True)
 
     # warm-up (also sets the kernel's smem attribute outside capture)
-    run_steps(W)
+    run_steps(max(W, R))  # every ring slot at least once
     torch.cuda.synchronize()
     stream = torch.cuda.Stream()
     graph = torch.cuda.CUDAGraph()

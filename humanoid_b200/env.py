@@ -115,6 +115,21 @@ class HumanoidPHC:
         self._step_args = None
 
     # ------------------------------------------------------------------------------------
+    @property
+    def _reset_bodies_id(self) -> torch.Tensor:
+        return self.__reset_bodies_id
+
+    @_reset_bodies_id.setter
+    def _reset_bodies_id(self, ids: torch.Tensor):
+        """Assigning the index tensor (as toggle_eval_mode does, :1437) also refreshes the body
+        bit mask the fused kernel takes; done here, once, so step() itself never reads the device."""
+        self.__reset_bodies_id = ids
+        mask = 0
+        for b in ids.tolist():
+            mask |= 1 << int(b)
+        self._reset_mask = mask
+        self._step_args = None
+
     def _bind_body_views(self):
         s = self._rigid_body_state_reshaped
         J = self.num_bodies
@@ -168,9 +183,7 @@ class HumanoidPHC:
         body, keep = _cabi.body_state(
             self._rigid_body_pos, self._rigid_body_rot, self._rigid_body_vel, self._rigid_body_ang_vel
         )
-        mask = 0
-        for b in self._reset_bodies_id.tolist():
-            mask |= 1 << int(b)
+        mask = self._reset_mask
         a = _cabi.PhcStepArgs()
         a.body = body
         a.progress_buf = self.progress_buf.data_ptr()

@@ -22,6 +22,9 @@ SELF_OBS_DIM = 358
 TASK_OBS_DIM = 576
 MAX_TIME_STEPS = 16
 
+OPT_FORCE_GENERIC_STEP = 1
+OPT_STEP_EPB = 2
+
 OBS_LOCAL_ROOT = 1
 OBS_ROOT_HEIGHT = 2
 OBS_UPRIGHT = 4
@@ -138,6 +141,7 @@ SIGNATURES = {
          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),  # fmt: skip
     "phc_step_fused": (C.c_int, [C.c_void_p, C.POINTER(PhcStepArgs), C.c_int64, C.c_void_p]),
+    "phc_set_option": (C.c_int, [C.c_int, C.c_int]),
     "phc_host_step_create": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_float,

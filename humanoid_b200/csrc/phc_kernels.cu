@@ -80,6 +80,50 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PHC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PHC_DONE;\n"
+      "bra PHC_WAIT;\n"
+      "PHC_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared, 16-B aligned, size multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                         unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // per-(query) reference body state
 struct RefBody {
   Vec3 pos;
@@ -674,6 +718,256 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
 }
 
 // ---------------------------------------------------------------------------------------
+// K6-fast: the fused step for T == 1 on the AoS sim tensor with a dense obs_buf — the
+// configuration the env runs (humanoid_phc.py:1100) and the benchmark measures.
+//
+//   * all bulk data movement is TMA: warp 0 runs the clock + frame-blend for (env, t) and
+//     (env, t+dt) on 2*EPB lanes, then each lane issues cp.async.bulk copies of its env's sim
+//     row (1248 B) and of the frame rows it needs (gts 288 | grs 384 | gvs 288 | gavs 288 B per
+//     frame) straight into shared memory, completing on one mbarrier.  Frames shared between
+//     t and t+dt (the usual case: idx1(t) == idx0(t+dt)) are fetched once.
+//   * 24 threads per env do the per-body math out of shared memory; reward means and the
+//     termination test are reduced by warp 0 in ATen's summation order.
+//   * the 934-float obs rows of the block are assembled in shared memory (aliasing the frame
+//     buffer) and leave with ONE cp.async.bulk shared->global store.
+// ---------------------------------------------------------------------------------------
+template <int EPB>
+struct FastSmem {
+  float sim[EPB * ROW13];
+  float frames[EPB * 4 * FRAME_FLOATS];  // [env][slot 0..3][312]; later the obs stage [env][934]
+  float part[5][EPB][J24];
+  unsigned long long bar;
+  float bl[2][EPB];
+  int slot[2][2][EPB];
+  float goff[EPB][4];
+  float hz[EPB], hw[EPB];
+  int prog[EPB], pass[EPB], fallen[EPB];
+};
+
+__device__ __forceinline__ void bulk_load_frame(const LibDev& L, float* dst, int64_t f, unsigned long long* bar) {
+  bulk_g2s(dst, L.gts + f * 72, 288, bar);
+  bulk_g2s(dst + 72, L.grs + f * 96, 384, bar);
+  bulk_g2s(dst + 168, L.gvs + f * 72, 288, bar);
+  bulk_g2s(dst + 240, L.gavs + f * 72, 288, bar);
+}
+
+__device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, float bl, const float* goff, int b) {
+  const float om = 1.0f - bl;
+  RefBody r;
+  r.pos = lerp3(om, bl, ld3(f0 + b * 3), ld3(f1 + b * 3));
+  r.pos.x += goff[0];
+  r.pos.y += goff[1];
+  r.pos.z += goff[2];
+  r.rot = quat_slerp(ld4v(f0 + 72 + b * 4), ld4v(f1 + 72 + b * 4), bl);
+  r.vel = lerp3(om, bl, ld3(f0 + 168 + b * 3), ld3(f1 + 168 + b * 3));
+  r.ang = lerp3(om, bl, ld3(f0 + 240 + b * 3), ld3(f1 + 240 + b * 3));
+  return r;
+}
+
+template <int EPB, int MINB>
+__global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastSmem<EPB>& S = *reinterpret_cast<FastSmem<EPB>*>(smem_raw);
+  constexpr int NT = EPB * J24;
+  static_assert(2 * EPB <= 32, "phase 0 runs on one warp");
+  static_assert(4 * EPB <= 32, "reductions run on one warp");
+  const int tid = threadIdx.x;
+  const int64_t env0 = (int64_t)blockIdx.x * EPB;
+  const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
+
+  // ---- phase 0 (warp 0): clock, frame-blend, TMA loads ------------------------------------
+  if (tid < 32) {
+    if (tid == 0) mbar_init(&S.bar, 1);
+    __syncwarp();
+    const int le = tid >> 1, q = tid & 1;
+    const bool act = le < nvalid;
+    int64_t f0 = -1, f1 = -1;
+    if (act) {
+      const int64_t env = env0 + le;
+      int prog = (int)p.progress[env];
+      if (p.advance) prog = (int)(int16_t)(prog + 1);
+      // q = 0: t = progress*dt + start + offset (humanoid_phc.py:1236); q = 1: (progress+1)*dt + ..
+      // (humanoid_phc.py:1063-1067), progress already advanced (humanoid_phc.py:138)
+      const float t = (float)(int16_t)(prog + q) * p.dt + p.start[env] + p.start_off[env];
+      const int64_t id = p.ids[env];
+      const float len = p.L.len[id];
+      int64_t i0, i1;
+      float bl;
+      calc_frame_blend(t, len, p.L.nf[id], p.L.mdt[id], i0, i1, bl);
+      const int64_t st = p.L.starts[id];
+      f0 = i0 + st;
+      f1 = i1 + st;
+      S.bl[q][le] = bl;
+      if (q == 0) {
+        S.prog[le] = prog;
+        S.pass[le] = t >= len;  // _compute_reset, humanoid_phc.py:1317
+        S.fallen[le] = 0;
+        if (p.advance) p.progress[env] = (int16_t)prog;
+        S.goff[le][0] = p.goff ? p.goff[env * 3 + 0] : 0.0f;
+        S.goff[le][1] = p.goff ? p.goff[env * 3 + 1] : 0.0f;
+        S.goff[le][2] = p.goff ? p.goff[env * 3 + 2] : 0.0f;
+      }
+    }
+    // the t+dt lane learns the frames of the t lane and reuses their slots where equal
+    const int64_t p0 = __shfl_up_sync(0xffffffffu, f0, 1), p1 = __shfl_up_sync(0xffffffffu, f1, 1);
+    if (act) {
+      float* fr = S.frames + le * (4 * FRAME_FLOATS);
+      int s0, s1;
+      uint32_t bytes = 0;
+      if (q == 0) {
+        s0 = 0;
+        s1 = (f1 == f0) ? 0 : 1;
+        bytes = (1 + (s1 == 1) + 1) * (uint32_t)(FRAME_FLOATS * 4);  // frame(s) + the env's sim row
+      } else {
+        const int ps1 = (p1 == p0) ? 0 : 1;
+        s0 = (f0 == p0) ? 0 : (f0 == p1) ? ps1 : 2;
+        s1 = (f1 == f0) ? s0 : (f1 == p0) ? 0 : (f1 == p1) ? ps1 : 3;
+        bytes = ((s0 == 2) + (s1 == 3)) * (uint32_t)(FRAME_FLOATS * 4);
+      }
+      S.slot[q][0][le] = s0;
+      S.slot[q][1][le] = s1;
+      if (bytes) mbar_expect_tx(&S.bar, bytes);
+      if (q == 0) {
+        bulk_g2s(S.sim + le * ROW13, p.body.pos.ptr + (env0 + le) * p.body.pos.stride_env, ROW13 * 4, &S.bar);
+        bulk_load_frame(p.L, fr, f0, &S.bar);
+        if (s1 == 1) bulk_load_frame(p.L, fr + FRAME_FLOATS, f1, &S.bar);
+      } else {
+        if (s0 == 2) bulk_load_frame(p.L, fr + 2 * FRAME_FLOATS, f0, &S.bar);
+        if (s1 == 3) bulk_load_frame(p.L, fr + 3 * FRAME_FLOATS, f1, &S.bar);
+      }
+    }
+    __syncwarp();
+    if (tid == 0) mbar_arrive(&S.bar);
+  }
+  __syncthreads();  // #1: slots / blends / barrier init visible
+  mbar_wait(&S.bar, 0);
+
+  // ---- phase 1: per-body reference states, reward partials, distance ------------------------
+  const int e = tid / J24, b = tid % J24;
+  const bool valid = e < nvalid;
+  Vec3 pos, vel, ang;
+  Quat rot;
+  RefBody r1;
+  if (valid) {
+    const float* d = S.sim + e * ROW13 + b * 13;
+    pos = {d[0], d[1], d[2]};
+    rot = {d[3], d[4], d[5], d[6]};
+    vel = {d[7], d[8], d[9]};
+    ang = {d[10], d[11], d[12]};
+    const float* fr = S.frames + e * (4 * FRAME_FLOATS);
+    {
+      const RefBody r0 = blend_ref2(fr + S.slot[0][0][e] * FRAME_FLOATS, fr + S.slot[0][1][e] * FRAME_FLOATS,
+                                    S.bl[0][e], S.goff[e], b);
+      float sp, sr, sv, sa;
+      reward_partials(pos, rot, vel, ang, r0, sp, sr, sv, sa);
+      S.part[0][e][b] = sp;
+      S.part[1][e][b] = sr;
+      S.part[2][e][b] = sv;
+      S.part[3][e][b] = sa;
+      const float dist = norm3(pos - r0.pos);  // torch.norm(rigid_body_pos - ref_body_pos), common.py:343/348
+      S.part[4][e][b] = dist;
+      if (!p.use_mean && (p.reset_mask >> b & 1u) && dist > p.term_dist[b]) S.fallen[e] = 1;  // any(), benign race
+    }
+    r1 = blend_ref2(fr + S.slot[1][0][e] * FRAME_FLOATS, fr + S.slot[1][1][e] * FRAME_FLOATS, S.bl[1][e], S.goff[e], b);
+    if (b == 0) {
+      const Heading h0 = heading_quat_inv(rot);  // upright: root_rot used as is (common.py:42-44)
+      S.hz[e] = h0.z;
+      S.hw[e] = h0.w;
+    }
+  }
+  __syncthreads();  // #2: partials / heading visible; frame buffer dead -> becomes the obs stage
+
+  // ---- reductions and scalar outputs (warp 0) -------------------------------------------------
+  if (tid < 32) {
+    const int le = tid >> 2, k = tid & 3;
+    const bool act = le < nvalid && tid < 4 * EPB;
+    float term_k = 0.0f;
+    if (act) {
+      const float kk = k == 0 ? p.rwd.k_pos : k == 1 ? p.rwd.k_rot : k == 2 ? p.rwd.k_vel : p.rwd.k_ang_vel;
+      term_k = expf((-kk) * (row_sum24(&S.part[k][le][0]) / 24.0f));  // common.py:298-320
+      p.raw[(env0 + le) * p.raw_stride + k] = term_k;
+    }
+    const int base = tid & ~3;
+    const float t0 = __shfl_sync(0xffffffffu, term_k, base), t1 = __shfl_sync(0xffffffffu, term_k, base + 1);
+    const float t2 = __shfl_sync(0xffffffffu, term_k, base + 2), t3 = __shfl_sync(0xffffffffu, term_k, base + 3);
+    if (act && k == 0)
+      p.rew[env0 + le] = p.rwd.w_pos * t0 + p.rwd.w_rot * t1 + p.rwd.w_vel * t2 + p.rwd.w_ang_vel * t3;
+    if (act && k == 1) {
+      bool fallen = false;
+      if (p.early) {
+        if (p.use_mean) {  // eval mode: mean distance of the selected bodies vs the first one's threshold
+          float sel[J24];
+          int m = 0;
+#pragma unroll
+          for (int j = 0; j < J24; ++j)
+            if (p.reset_mask >> j & 1u) sel[m++] = S.part[4][le][j];
+          const int first = __ffs(p.reset_mask) - 1;
+          fallen = m > 0 && (row_sum8(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+        } else {
+          fallen = S.fallen[le] != 0;
+        }
+        fallen = fallen && (S.prog[le] > 1);  // common.py:353
+      }
+      p.term[env0 + le] = fallen ? 1 : 0;
+      p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
+    }
+  }
+
+  // ---- phase 2: observations into the stage ---------------------------------------------------
+  if (valid) {
+    const Vec3 root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
+    const Heading hi = {S.hz[e], S.hw[e]};
+    const float hs = heading_scale(hi);
+    float* row = S.frames + e * STAGE_FLOATS;
+    // self obs, common.py:23-103 (default flags: local root, height, upright)
+    if (b == 0)
+      row[0] = root_pos.z;
+    else
+      st3(row + 1 + (b - 1) * 3, heading_rotate(hi, hs, pos - root_pos));
+    quat_tan_norm(heading_mul_left(hi, rot), row + 70 + b * 6);
+    st3(row + 214 + b * 3, heading_rotate(hi, hs, vel));
+    st3(row + 286 + b * 3, heading_rotate(hi, hs, ang));
+    // task obs v6, common.py:106-176
+    TaskObs o;
+    task_obs_body(hi, hs, root_pos, pos, rot, vel, ang, r1, true, o);
+    float* tk = row + SELF_DIM;
+    st3(tk + b * 3, o.d_pos);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tk[72 + b * 6 + k] = o.d_rot[k];
+    st3(tk + 216 + b * 3, o.d_vel);
+    st3(tk + 288 + b * 3, o.d_ang);
+    st3(tk + 360 + b * 3, o.l_pos);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tk[432 + b * 6 + k] = o.l_rot[k];
+  }
+  fence_proxy_async();  // stage writes -> visible to the bulk-store engine
+  __syncthreads();      // #3: stage complete
+
+  const uint32_t out_bytes = (uint32_t)nvalid * (STAGE_FLOATS * 4);
+  const bool bulk_ok = (out_bytes & 15u) == 0;
+  if (bulk_ok) {
+    if (tid == NT - 1) bulk_s2g(p.obs + env0 * STAGE_FLOATS, S.frames, out_bytes);
+  } else {  // odd tail block: 8-byte stores
+    float2* dst = reinterpret_cast<float2*>(p.obs + env0 * STAGE_FLOATS);
+    const float2* src = reinterpret_cast<const float2*>(S.frames);
+    for (int i = tid; i < nvalid * (STAGE_FLOATS / 2); i += NT) dst[i] = src[i];
+  }
+  if (p.moments) {  // RunningNorm partials: per-column fp64 sum / sum of squares over the block's envs
+    for (int c = tid; c < STAGE_FLOATS; c += NT) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int ee = 0; ee < nvalid; ++ee) {
+        const double x = (double)S.frames[ee * STAGE_FLOATS + c];
+        s1 += x;
+        s2 += x * x;
+      }
+      atomicAdd(p.moments + c, s1);
+      atomicAdd(p.moments + STAGE_FLOATS + c, s2);
+    }
+  }
+  if (bulk_ok && tid == NT - 1) bulk_wait_read();  // shared memory must outlive the store's reads
+}
+
+// ---------------------------------------------------------------------------------------
 // RunningNorm kernels (policies/running_norm.py:15-34)
 // ---------------------------------------------------------------------------------------
 constexpr int MOM_ROWS_PER_BLOCK = 256;
@@ -730,6 +1024,18 @@ __global__ void running_norm_forward_kernel(const float* __restrict__ x, int64_t
 // C ABI
 // =========================================================================================
 using namespace phc;
+
+template <typename Kern>
+static int launch_step(Kern kern, size_t smem, int epb, const StepParams& p, cudaStream_t stream, bool* attr_set) {
+  if (!*attr_set) {
+    PHC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *attr_set = true;
+  }
+  const unsigned grid = (unsigned)((p.n + epb - 1) / epb);
+  kern<<<grid, epb * J24, smem, stream>>>(p);
+  return launch_status();
+}
+
 
 struct PhcLib {
   LibDev d;
@@ -929,24 +1235,55 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   return PHC_OK;
 }
 
+static int g_force_generic = -1;  // PHC_OPT_FORCE_GENERIC_STEP / env PHC_STEP_GENERIC=1
+static int g_fast_epb = -1;       // PHC_OPT_STEP_EPB / env PHC_STEP_EPB=4|8
+
+static void init_options() {
+  if (g_force_generic < 0) {
+    const char* v = getenv("PHC_STEP_GENERIC");
+    g_force_generic = (v && v[0] == '1') ? 1 : 0;
+  }
+  if (g_fast_epb < 0) {
+    const char* w = getenv("PHC_STEP_EPB");
+    g_fast_epb = (w && w[0] == '8') ? 8 : 4;
+  }
+}
+
+int phc_set_option(int key, int value) {
+  init_options();
+  switch (key) {
+    case PHC_OPT_FORCE_GENERIC_STEP:
+      g_force_generic = value ? 1 : 0;
+      return PHC_OK;
+    case PHC_OPT_STEP_EPB:
+      if (value != 4 && value != 8) return PHC_ERR_SHAPE;
+      g_fast_epb = value;
+      return PHC_OK;
+    default:
+      return PHC_ERR_UNSUPPORTED;
+  }
+}
+
 int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream) {
   if (n == 0) return PHC_OK;
   if (n < 0) return PHC_ERR_SHAPE;
   StepParams p;
   int rc = step_fill_params(lib, args, n, p);
   if (rc) return rc;
-  using SM = StepSmem<STEP_EPB>;
-  static bool attr_set[64] = {};
   int dev = 0;
   PHC_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return PHC_ERR_UNSUPPORTED;
-  if (!attr_set[dev]) {
-    PHC_CUDA(cudaFuncSetAttribute(step_kernel<STEP_EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
-    attr_set[dev] = true;
+  init_options();
+  // fast path: T == 1, AoS sim tensor (16-B aligned rows), dense 16-B aligned obs_buf
+  const bool fast = !g_force_generic && p.T == 1 && p.aos && p.obs_stride == STAGE_FLOATS &&
+                    ((uintptr_t)p.obs & 15) == 0;
+  static bool attr_fast4[64] = {}, attr_fast8[64] = {}, attr_gen[64] = {};
+  if (fast) {
+    if (g_fast_epb == 8)
+      return launch_step(step_fast_kernel<8, 4>, sizeof(FastSmem<8>), 8, p, stream, &attr_fast8[dev]);
+    return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev]);
   }
-  const unsigned grid = (unsigned)((n + STEP_EPB - 1) / STEP_EPB);
-  step_kernel<STEP_EPB><<<grid, STEP_EPB * J24, sizeof(SM), stream>>>(p);
-  return launch_status();
+  return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev]);
 }
 
 // ---- RunningNorm ---------------------------------------------------------------------------

@@ -199,13 +199,29 @@ __device__ __forceinline__ float norm3(Vec3 v) { return sqrtf(__fmaf_rn(v.z, v.z
 // (d**2).mean(dim=-1) over 3: ((x^2 + y^2) + z^2) / 3
 __device__ __forceinline__ float mean_sq3(Vec3 d) { return ((d.x * d.x + d.y * d.y) + d.z * d.z) / 3.0f; }
 
-// ATen CPU sum over a contiguous row of n <= 32 floats: 8 lane accumulators filled
-// round-robin, then combined left to right (measured; exact for n = 24).
+// ATen CPU sum over a contiguous row of floats (vectorised inner reduction, measured on torch
+// 2.11): 8 lane accumulators filled round-robin (lane l gets v[l], v[l+8], ..), then combined
+// left to right.  Exact for n = 24; for n <= 7 it degenerates to the sequential sum ATen uses.
+// The lane loop is fully unrolled so the accumulators stay in registers.
 __device__ __forceinline__ float row_sum8(const float* v, int n) {
   float acc[8];
 #pragma unroll
   for (int l = 0; l < 8; ++l) acc[l] = 0.0f;
-  for (int j = 0; j < n; ++j) acc[j & 7] += v[j];  // 0 + x is exact
+  for (int base = 0; base < n; base += 8) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l)
+      if (base + l < n) acc[l] += v[base + l];  // 0 + x is exact
+  }
+  float s = acc[0];
+#pragma unroll
+  for (int l = 1; l < 8; ++l) s = s + acc[l];
+  return s;
+}
+
+__device__ __forceinline__ float row_sum24(const float* v) {
+  float acc[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) acc[l] = (v[l] + v[l + 8]) + v[l + 16];
   float s = acc[0];
 #pragma unroll
   for (int l = 1; l < 8; ++l) s = s + acc[l];

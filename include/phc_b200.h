@@ -208,6 +208,14 @@ typedef struct PhcStepArgs {
 
 PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream);
 
+/* Process-wide tuning / test switches of phc_step_fused (not part of the reference surface).
+ * phc_step_fused picks the TMA fast kernel when time_steps == 1, the four body views are one
+ * 16-B aligned AoS-13 tensor and obs_buf is dense and 16-B aligned; otherwise, or when
+ * PHC_OPT_FORCE_GENERIC_STEP is set, the generic kernel (any T, any strides). */
+#define PHC_OPT_FORCE_GENERIC_STEP 1 /* value 0/1 */
+#define PHC_OPT_STEP_EPB 2           /* envs per block of the fast kernel: 4 (default) or 8 */
+PHC_API int phc_set_option(int key, int value);
+
 /* ------------------------------------------------------------------------------------
  * Host-buffer pipeline around the fused step (the end-to-end call): chunked
  * H2D(sim state, clock) -> phc_step_fused -> D2H(obs, reward, flags) on internal streams.

@@ -429,3 +429,100 @@ def test_empty_batch_is_a_no_op():
     z = torch.zeros(0, 24, 13, device=DEV)
     o = compute_humanoid_observations_smpl_max(*synth.body_views(z), None, None, True, True, True, False, False)
     assert o.shape == (0, 358)
+
+
+@pytest.mark.parametrize("N", [4096, 4099, 7])
+def test_fast_kernel_equals_generic_kernel_bitwise(N):
+    """T=1 dispatches to the TMA kernel (4 or 8 envs per block); the generic kernel is the same math."""
+    from humanoid_b200 import HumanoidPHC, _cabi
+
+    lib_data, clock, state = _gpu_case(N, max(N // 4, 3), 206, max_frames=90, max_progress=40)
+    lib = MotionLib(lib_data, device=DEV)
+    capi = _cabi.load()
+    outs = []
+    try:
+        for generic, epb in ((1, 4), (0, 4), (0, 8)):
+            assert capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, generic) == 0
+            assert capi.phc_set_option(_cabi.OPT_STEP_EPB, epb) == 0
+            env = HumanoidPHC(lib, N, device=DEV, obs_moments=True)
+            env.set_sim_state(state)
+            env.set_clock(clock)
+            env.step()
+            torch.cuda.synchronize()
+            outs.append(env)
+    finally:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+        capi.phc_set_option(_cabi.OPT_STEP_EPB, 4)
+    g = outs[0]
+    for f in outs[1:]:
+        assert torch.equal(f.obs_buf, g.obs_buf)
+        assert torch.equal(f.rew_buf, g.rew_buf) and torch.equal(f.reward_raw, g.reward_raw)
+        assert torch.equal(f.reset_buf, g.reset_buf) and torch.equal(f._terminate_buf, g._terminate_buf)
+        assert torch.equal(f.progress_buf, g.progress_buf)
+        torch.testing.assert_close(f.obs_moments, g.obs_moments, rtol=1e-12, atol=1e-9)
+
+
+def test_fused_moments_epilogue_matches_column_moments():
+    from humanoid_b200 import HumanoidPHC, RunningNorm
+
+    lib_data, clock, state = _gpu_case(3000, 100, 207, max_progress=40)
+    env = HumanoidPHC(MotionLib(lib_data, device=DEV), 3000, device=DEV, obs_moments=True)
+    env.set_sim_state(state)
+    env.set_clock(clock)
+    env.step()
+    rn = RunningNorm(934, device=DEV)
+    sums = rn.moments(env.obs_buf)
+    torch.testing.assert_close(env.obs_moments, sums, rtol=1e-12, atol=1e-9)
+    x = env.obs_buf.double()
+    torch.testing.assert_close(sums[:934], x.sum(0), rtol=1e-12, atol=1e-9)
+    torch.testing.assert_close(sums[934:], (x * x).sum(0), rtol=1e-12, atol=1e-9)
+
+
+def test_running_norm_vs_reference_fixture(golden):
+    from humanoid_b200 import RunningNorm
+
+    g = golden("running_norm")
+    rn = RunningNorm(934, device=DEV)
+    rn.update(cuda(g.inp("x1")))
+    assert_close(rn.running_mean, g.out("mean1"), what="mean1", rtol=1e-5, atol=1e-6)
+    assert_close(rn.running_var, g.out("var1"), what="var1", rtol=1e-5, atol=1e-6)
+    rn.update(cuda(g.inp("x2")))
+    assert_close(rn.running_mean, g.out("mean2"), what="mean2", rtol=1e-5, atol=1e-6)
+    assert_close(rn.running_var, g.out("var2"), what="var2", rtol=1e-5, atol=1e-6)
+    assert float(rn.count) == float(g.out("count2"))
+    assert_close(rn(cuda(g.inp("x2")[:32])), g.out("fwd"), what="forward", rtol=1e-5, atol=1e-5)
+
+
+def test_host_pipeline_matches_device_path():
+    import ctypes as C
+
+    from humanoid_b200 import HumanoidPHC, _cabi
+
+    N = 5000
+    lib_data, clock, state = _gpu_case(N, 64, 208, max_progress=40)
+    lib = MotionLib(lib_data, device=DEV)
+    env = HumanoidPHC(lib, N, device=DEV)
+    env.set_sim_state(state)
+    env.set_clock(clock)
+    env.step()
+    capi = _cabi.load()
+    ctx = C.c_void_p()
+    term = (C.c_float * 24)(*([0.25] * 24))
+    spec = _cabi.reward_spec(env.rwd_specs)
+    _cabi.check(capi.phc_host_step_create(lib.handle, N, 1, 3, term, 0xFFFFFF, 0, 1, synth.SIM_DT, C.byref(spec),
+                                          C.byref(ctx)), "create")  # fmt: skip
+    h = dict(
+        state=state.cpu().contiguous(), prog=clock.progress_buf.cpu().clone(), start=clock.motion_start_times.cpu(),
+        off=clock.motion_start_times_offset.cpu(), goff=clock.global_offset.cpu().contiguous(),
+        ids=clock.sampled_motion_ids.cpu(), obs=torch.empty(N, 934), rew=torch.empty(N), raw=torch.empty(N, 4),
+        reset=torch.empty(N, dtype=torch.uint8), term=torch.empty(N, dtype=torch.uint8),
+    )  # fmt: skip
+    args = _cabi.PhcHostStepArgs(*[h[k].data_ptr() for k in ("state", "prog", "start", "off", "goff", "ids", "obs",
+                                                             "rew", "raw", "reset", "term")])  # fmt: skip
+    _cabi.check(capi.phc_host_step(ctx, C.byref(args), N), "host step")
+    assert capi.phc_host_step_h2d_bytes(ctx, N) == N * (1248 + 2 + 4 + 4 + 12 + 8)
+    capi.phc_host_step_destroy(ctx)
+    assert torch.equal(h["obs"], env.obs_buf.cpu()) and torch.equal(h["rew"], env.rew_buf.cpu())
+    assert torch.equal(h["raw"], env.reward_raw[:, :4].cpu())
+    assert torch.equal(h["reset"].bool(), env.reset_buf.cpu()) and torch.equal(h["term"].bool(), env._terminate_buf.cpu())
+    assert torch.equal(h["prog"], env.progress_buf.cpu())

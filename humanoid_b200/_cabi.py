@@ -113,6 +113,7 @@ SIGNATURES = {
     "phc_last_cuda_error": (C.c_int, []),
     "phc_lib_create": (C.c_int, [C.POINTER(PhcLibDesc), C.POINTER(C.c_void_p)]),
     "phc_lib_destroy": (None, [C.c_void_p]),
+    "phc_lib_pack": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phc_calc_frame_blend": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],

@@ -47,6 +47,7 @@ struct LibDev {
   const float *len, *mdt, *bodies, *limb;
   const int64_t *nf, *starts;
   int64_t F, M;
+  const float* packed;  // [F][312] = per frame [gts 72 | grs 96 | gvs 72 | gavs 72], owned by PhcLib
 };
 
 // ---------------------------------------------------------------------------------------
@@ -146,6 +147,30 @@ __global__ void frame_blend_kernel(const float* __restrict__ time, const float* 
   i0[i] = a;
   i1[i] = b;
   bl[i] = w;
+}
+
+// ---------------------------------------------------------------------------------------
+// Frame packing (one-off, at phc_lib_create): the step kernels read, per frame, the body
+// positions, rotations and both velocities — four rows that the reference keeps in four tensors
+// (motion_lib.py:407-414).  Interleaving them into one 1248-B row per frame turns four
+// gathers into one contiguous 39-sector read and one TMA bulk copy.
+// ---------------------------------------------------------------------------------------
+__global__ void pack_frames_kernel(LibDev L, float* __restrict__ packed) {
+  const int64_t total4 = L.F * 78;  // float4 units
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / 78;
+    const int k = (int)(i - f * 78);
+    const float* src;
+    if (k < 18)
+      src = L.gts + f * 72 + k * 4;
+    else if (k < 42)
+      src = L.grs + f * 96 + (k - 18) * 4;
+    else if (k < 60)
+      src = L.gvs + f * 72 + (k - 42) * 4;
+    else
+      src = L.gavs + f * 72 + (k - 60) * 4;
+    reinterpret_cast<float4*>(packed)[i] = *reinterpret_cast<const float4*>(src);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -723,8 +748,8 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
 //
 //   * all bulk data movement is TMA: warp 0 runs the clock + frame-blend for (env, t) and
 //     (env, t+dt) on 2*EPB lanes, then each lane issues cp.async.bulk copies of its env's sim
-//     row (1248 B) and of the frame rows it needs (gts 288 | grs 384 | gvs 288 | gavs 288 B per
-//     frame) straight into shared memory, completing on one mbarrier.  Frames shared between
+//     row (1248 B) and of the packed frame rows it needs (1248 B each, see pack_frames_kernel)
+//     straight into shared memory, completing on one mbarrier.  Frames shared between
 //     t and t+dt (the usual case: idx1(t) == idx0(t+dt)) are fetched once.
 //   * 24 threads per env do the per-body math out of shared memory; reward means and the
 //     termination test are reduced by warp 0 in ATen's summation order.
@@ -745,10 +770,7 @@ struct FastSmem {
 };
 
 __device__ __forceinline__ void bulk_load_frame(const LibDev& L, float* dst, int64_t f, unsigned long long* bar) {
-  bulk_g2s(dst, L.gts + f * 72, 288, bar);
-  bulk_g2s(dst + 72, L.grs + f * 96, 384, bar);
-  bulk_g2s(dst + 168, L.gvs + f * 72, 288, bar);
-  bulk_g2s(dst + 240, L.gavs + f * 72, 288, bar);
+  bulk_g2s(dst, L.packed + f * FRAME_FLOATS, FRAME_FLOATS * 4, bar);
 }
 
 __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, float bl, const float* goff, int b) {
@@ -869,49 +891,14 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       if (!p.use_mean && (p.reset_mask >> b & 1u) && dist > p.term_dist[b]) S.fallen[e] = 1;  // any(), benign race
     }
     r1 = blend_ref2(fr + S.slot[1][0][e] * FRAME_FLOATS, fr + S.slot[1][1][e] * FRAME_FLOATS, S.bl[1][e], S.goff[e], b);
-    if (b == 0) {
-      const Heading h0 = heading_quat_inv(rot);  // upright: root_rot used as is (common.py:42-44)
-      S.hz[e] = h0.z;
-      S.hw[e] = h0.w;
-    }
+  }
+  if (tid < nvalid) {  // one lane per env, all in warp 0: a single divergent region per block
+    const float* d = S.sim + tid * ROW13;
+    const Heading h0 = heading_quat_inv(Quat{d[3], d[4], d[5], d[6]});  // upright: root_rot as is (common.py:42-44)
+    S.hz[tid] = h0.z;
+    S.hw[tid] = h0.w;
   }
   __syncthreads();  // #2: partials / heading visible; frame buffer dead -> becomes the obs stage
-
-  // ---- reductions and scalar outputs (warp 0) -------------------------------------------------
-  if (tid < 32) {
-    const int le = tid >> 2, k = tid & 3;
-    const bool act = le < nvalid && tid < 4 * EPB;
-    float term_k = 0.0f;
-    if (act) {
-      const float kk = k == 0 ? p.rwd.k_pos : k == 1 ? p.rwd.k_rot : k == 2 ? p.rwd.k_vel : p.rwd.k_ang_vel;
-      term_k = expf((-kk) * (row_sum24(&S.part[k][le][0]) / 24.0f));  // common.py:298-320
-      p.raw[(env0 + le) * p.raw_stride + k] = term_k;
-    }
-    const int base = tid & ~3;
-    const float t0 = __shfl_sync(0xffffffffu, term_k, base), t1 = __shfl_sync(0xffffffffu, term_k, base + 1);
-    const float t2 = __shfl_sync(0xffffffffu, term_k, base + 2), t3 = __shfl_sync(0xffffffffu, term_k, base + 3);
-    if (act && k == 0)
-      p.rew[env0 + le] = p.rwd.w_pos * t0 + p.rwd.w_rot * t1 + p.rwd.w_vel * t2 + p.rwd.w_ang_vel * t3;
-    if (act && k == 1) {
-      bool fallen = false;
-      if (p.early) {
-        if (p.use_mean) {  // eval mode: mean distance of the selected bodies vs the first one's threshold
-          float sel[J24];
-          int m = 0;
-#pragma unroll
-          for (int j = 0; j < J24; ++j)
-            if (p.reset_mask >> j & 1u) sel[m++] = S.part[4][le][j];
-          const int first = __ffs(p.reset_mask) - 1;
-          fallen = m > 0 && (row_sum8(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
-        } else {
-          fallen = S.fallen[le] != 0;
-        }
-        fallen = fallen && (S.prog[le] > 1);  // common.py:353
-      }
-      p.term[env0 + le] = fallen ? 1 : 0;
-      p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
-    }
-  }
 
   // ---- phase 2: observations into the stage ---------------------------------------------------
   if (valid) {
@@ -964,6 +951,42 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       atomicAdd(p.moments + STAGE_FLOATS + c, s2);
     }
   }
+  // ---- reductions and scalar outputs (warp 0), off the critical path: nothing waits for them -------------------------------------------------
+  if (tid < 32) {
+    const int le = tid >> 2, k = tid & 3;
+    const bool act = le < nvalid && tid < 4 * EPB;
+    float term_k = 0.0f;
+    if (act) {
+      const float kk = k == 0 ? p.rwd.k_pos : k == 1 ? p.rwd.k_rot : k == 2 ? p.rwd.k_vel : p.rwd.k_ang_vel;
+      term_k = expf((-kk) * (row_sum24(&S.part[k][le][0]) / 24.0f));  // common.py:298-320
+      p.raw[(env0 + le) * p.raw_stride + k] = term_k;
+    }
+    const int base = tid & ~3;
+    const float t0 = __shfl_sync(0xffffffffu, term_k, base), t1 = __shfl_sync(0xffffffffu, term_k, base + 1);
+    const float t2 = __shfl_sync(0xffffffffu, term_k, base + 2), t3 = __shfl_sync(0xffffffffu, term_k, base + 3);
+    if (act && k == 0)
+      p.rew[env0 + le] = p.rwd.w_pos * t0 + p.rwd.w_rot * t1 + p.rwd.w_vel * t2 + p.rwd.w_ang_vel * t3;
+    if (act && k == 1) {
+      bool fallen = false;
+      if (p.early) {
+        if (p.use_mean) {  // eval mode: mean distance of the selected bodies vs the first one's threshold
+          float sel[J24];
+          int m = 0;
+#pragma unroll
+          for (int j = 0; j < J24; ++j)
+            if (p.reset_mask >> j & 1u) sel[m++] = S.part[4][le][j];
+          const int first = __ffs(p.reset_mask) - 1;
+          fallen = m > 0 && (row_sum8(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+        } else {
+          fallen = S.fallen[le] != 0;
+        }
+        fallen = fallen && (S.prog[le] > 1);  // common.py:353
+      }
+      p.term[env0 + le] = fallen ? 1 : 0;
+      p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
+    }
+  }
+
   if (bulk_ok && tid == NT - 1) bulk_wait_read();  // shared memory must outlive the store's reads
 }
 
@@ -1039,6 +1062,7 @@ static int launch_step(Kern kern, size_t smem, int epb, const StepParams& p, cud
 
 struct PhcLib {
   LibDev d;
+  float* packed_owned = nullptr;
 };
 
 extern "C" {
@@ -1074,12 +1098,35 @@ int phc_lib_create(const PhcLibDesc* desc, PhcLib** out) {
   lib->d = LibDev{desc->gts,           desc->grs,        desc->lrs,          desc->gvs,
                   desc->gavs,          desc->dvs,        desc->motion_aa,    desc->motion_lengths,
                   desc->motion_dt,     desc->motion_bodies, desc->motion_limb_weights,
-                  desc->motion_num_frames, desc->length_starts, desc->total_frames, desc->num_motions};
+                  desc->motion_num_frames, desc->length_starts, desc->total_frames, desc->num_motions, nullptr};
   *out = lib;
   return PHC_OK;
 }
 
-void phc_lib_destroy(PhcLib* lib) { delete lib; }
+int phc_lib_pack(PhcLib* lib, phc_stream_t stream) {
+  if (!lib) return PHC_ERR_NULL;
+  if (!lib->packed_owned) {
+    cudaError_t e = cudaMalloc((void**)&lib->packed_owned, (size_t)lib->d.F * FRAME_FLOATS * sizeof(float));
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      g_last_cuda_error = (int)e;
+      return PHC_ERR_ALLOC;
+    }
+  }
+  const int64_t total4 = lib->d.F * 78;
+  const unsigned grid = (unsigned)((total4 + 255) / 256 < 148 * 16 ? (total4 + 255) / 256 : 148 * 16);
+  pack_frames_kernel<<<grid, 256, 0, stream>>>(lib->d, lib->packed_owned);
+  int rc = launch_status();
+  if (rc) return rc;
+  lib->d.packed = lib->packed_owned;
+  return PHC_OK;
+}
+
+void phc_lib_destroy(PhcLib* lib) {
+  if (!lib) return;
+  if (lib->packed_owned) cudaFree(lib->packed_owned);
+  delete lib;
+}
 
 int phc_calc_frame_blend(const float* time, const float* len, const int64_t* num_frames, const float* dt,
                          int64_t n, int64_t* frame_idx0, int64_t* frame_idx1, float* blend, phc_stream_t stream) {
@@ -1275,7 +1322,7 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
   if (dev < 0 || dev >= 64) return PHC_ERR_UNSUPPORTED;
   init_options();
   // fast path: T == 1, AoS sim tensor (16-B aligned rows), dense 16-B aligned obs_buf
-  const bool fast = !g_force_generic && p.T == 1 && p.aos && p.obs_stride == STAGE_FLOATS &&
+  const bool fast = !g_force_generic && p.T == 1 && p.aos && p.L.packed && p.obs_stride == STAGE_FLOATS &&
                     ((uintptr_t)p.obs & 15) == 0;
   static bool attr_fast4[64] = {}, attr_fast8[64] = {}, attr_gen[64] = {};
   if (fast) {

@@ -62,6 +62,12 @@ class MotionLib:
         handle = C.c_void_p()
         _cabi.check(lib.phc_lib_create(C.byref(desc), C.byref(handle)), "phc_lib_create")
         self._handle = handle
+        self.repack()
+
+    def repack(self):
+        """Build (or rebuild, after the frame tensors were rewritten in place) the packed
+        [F, 312] frame table the fused step's TMA path reads."""
+        _cabi.check(_cabi.load().phc_lib_pack(self._handle, _cabi.stream_ptr(self._device)), "phc_lib_pack")
 
     def __del__(self):
         h = getattr(self, "_handle", None)

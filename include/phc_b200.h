@@ -82,6 +82,12 @@ typedef struct PhcLibDesc {
 typedef struct PhcLib PhcLib;
 PHC_API int phc_lib_create(const PhcLibDesc* desc, PhcLib** out);
 PHC_API void phc_lib_destroy(PhcLib* lib);
+/* (Re)build the library's packed frame table on `stream`: one 1248-B row per frame,
+ * [gts 72 | grs 96 | gvs 72 | gavs 72] floats, owned by the handle (1248 B x F of HBM).  The
+ * fused step's TMA fast path reads it; without it phc_step_fused uses the generic kernel on
+ * the four reference tensors.  Call once after phc_lib_create and again if the caller rewrites
+ * the frame tensors in place. */
+PHC_API int phc_lib_pack(PhcLib* lib, phc_stream_t stream);
 
 /* [n, J, C] fp32 view, innermost C contiguous; strides in elements. */
 typedef struct PhcView {

@@ -24,6 +24,7 @@ MAX_TIME_STEPS = 16
 
 OPT_FORCE_GENERIC_STEP = 1
 OPT_STEP_EPB = 2
+OPT_STEP_PDL = 3
 
 OBS_LOCAL_ROOT = 1
 OBS_ROOT_HEIGHT = 2
@@ -143,6 +144,7 @@ SIGNATURES = {
     ),  # fmt: skip
     "phc_step_fused": (C.c_int, [C.c_void_p, C.POINTER(PhcStepArgs), C.c_int64, C.c_void_p]),
     "phc_set_option": (C.c_int, [C.c_int, C.c_int]),
+    "phc_set_trace_buffer": (C.c_int, [C.c_void_p, C.c_int64]),
     "phc_host_step_create": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_float,

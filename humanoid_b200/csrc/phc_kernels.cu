@@ -125,6 +125,17 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define PHC_STAMP(slot)                                                                      \
+  do {                                                                                       \
+    if (p.trace && (threadIdx.x & 31) == 0)                                                  \
+      p.trace[((size_t)blockIdx.x * 3 + (threadIdx.x >> 5)) * 8 + (slot)] = globaltimer_ns(); \
+  } while (0)
+
 // per-(query) reference body state
 struct RefBody {
   Vec3 pos;
@@ -346,7 +357,7 @@ __device__ __forceinline__ void reward_partials(Vec3 pos, Quat rot, Vec3 vel, Ve
                                                 float& sp, float& sr, float& sv, float& sa) {
   sp = mean_sq3(r.pos - pos);  // (d**2).mean(-1), common.py:299
   Quat dq = quat_mul(r.rot, quat_conj(rot));
-  float a = quat_angle(dq.w);
+  const float a = quat_angle(dq.w);
   sr = a * a;
   sv = mean_sq3(r.vel - vel);
   sa = mean_sq3(r.ang - ang);
@@ -460,6 +471,7 @@ struct StepParams {
   uint8_t* term;
   double* moments;
   int64_t n;
+  unsigned long long* trace;  // NULL, or [grid][8] globaltimer stamps (phc_set_trace_buffer)
   int aos;        // sim state is one AoS-13 tensor, 16-B aligned rows
   int obs_vec2;   // obs rows can be written with 8-byte stores
 };
@@ -796,27 +808,59 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   const int tid = threadIdx.x;
   const int64_t env0 = (int64_t)blockIdx.x * EPB;
   const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
+  PHC_STAMP(0);
 
   // ---- phase 0 (warp 0): clock, frame-blend, TMA loads ------------------------------------
+  // The kernel is launched with programmatic stream serialization: everything before
+  // griddepcontrol.wait overlaps the tail of whatever kernel precedes it in the stream.  That
+  // part only SPECULATES — it reads the env's motion id and gathers the clip metadata for it;
+  // after the wait the id is re-read (with the rest of the clock) and the gather is redone in the
+  // rare case it changed, so no caller contract is needed.  All reads of sim state / progress
+  // and all writes happen after the wait.
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (tid < 32) {
     if (tid == 0) mbar_init(&S.bar, 1);
-    __syncwarp();
     const int le = tid >> 1, q = tid & 1;
     const bool act = le < nvalid;
+    const int64_t env = env0 + (act ? le : 0);
+    int64_t sid = 0, nf = 2, st = 0;
+    float len = 1.0f, mdt = 1.0f;
+    if (act) {
+      sid = p.ids[env];
+      const int64_t c = sid < 0 ? 0 : (sid >= p.L.M ? p.L.M - 1 : sid);  // stale garbage must not fault
+      len = p.L.len[c];
+      nf = p.L.nf[c];
+      mdt = p.L.mdt[c];
+      st = p.L.starts[c];
+    }
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    __syncwarp();
     int64_t f0 = -1, f1 = -1;
     if (act) {
-      const int64_t env = env0 + le;
-      int prog = (int)p.progress[env];
+      // one round of independent loads
+      const int16_t prog_in = p.progress[env];
+      const int64_t id = p.ids[env];
+      const float start = p.start[env], soff = p.start_off[env];
+      float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+      if (q == 0 && p.goff) {
+        g0 = p.goff[env * 3 + 0];
+        g1 = p.goff[env * 3 + 1];
+        g2 = p.goff[env * 3 + 2];
+      }
+      if (id != sid) {  // the speculation missed (env was re-assigned a clip): gather again
+        len = p.L.len[id];
+        nf = p.L.nf[id];
+        mdt = p.L.mdt[id];
+        st = p.L.starts[id];
+      }
+      int prog = (int)prog_in;
       if (p.advance) prog = (int)(int16_t)(prog + 1);
       // q = 0: t = progress*dt + start + offset (humanoid_phc.py:1236); q = 1: (progress+1)*dt + ..
       // (humanoid_phc.py:1063-1067), progress already advanced (humanoid_phc.py:138)
-      const float t = (float)(int16_t)(prog + q) * p.dt + p.start[env] + p.start_off[env];
-      const int64_t id = p.ids[env];
-      const float len = p.L.len[id];
+      const float t = (float)(int16_t)(prog + q) * p.dt + start + soff;
       int64_t i0, i1;
       float bl;
-      calc_frame_blend(t, len, p.L.nf[id], p.L.mdt[id], i0, i1, bl);
-      const int64_t st = p.L.starts[id];
+      calc_frame_blend(t, len, nf, mdt, i0, i1, bl);
       f0 = i0 + st;
       f1 = i1 + st;
       S.bl[q][le] = bl;
@@ -825,9 +869,9 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
         S.pass[le] = t >= len;  // _compute_reset, humanoid_phc.py:1317
         S.fallen[le] = 0;
         if (p.advance) p.progress[env] = (int16_t)prog;
-        S.goff[le][0] = p.goff ? p.goff[env * 3 + 0] : 0.0f;
-        S.goff[le][1] = p.goff ? p.goff[env * 3 + 1] : 0.0f;
-        S.goff[le][2] = p.goff ? p.goff[env * 3 + 2] : 0.0f;
+        S.goff[le][0] = g0;
+        S.goff[le][1] = g1;
+        S.goff[le][2] = g2;
       }
     }
     // the t+dt lane learns the frames of the t lane and reuses their slots where equal
@@ -860,9 +904,15 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     }
     __syncwarp();
     if (tid == 0) mbar_arrive(&S.bar);
+    PHC_STAMP(1);
+  }
+  else {
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
   }
   __syncthreads();  // #1: slots / blends / barrier init visible
+  PHC_STAMP(2);
   mbar_wait(&S.bar, 0);
+  PHC_STAMP(3);
 
   // ---- phase 1: per-body reference states, reward partials, distance ------------------------
   const int e = tid / J24, b = tid % J24;
@@ -898,6 +948,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     S.hz[tid] = h0.z;
     S.hw[tid] = h0.w;
   }
+  PHC_STAMP(4);
   __syncthreads();  // #2: partials / heading visible; frame buffer dead -> becomes the obs stage
 
   // ---- phase 2: observations into the stage ---------------------------------------------------
@@ -928,7 +979,9 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     for (int k = 0; k < 6; ++k) tk[432 + b * 6 + k] = o.l_rot[k];
   }
   fence_proxy_async();  // stage writes -> visible to the bulk-store engine
+  PHC_STAMP(5);
   __syncthreads();      // #3: stage complete
+  PHC_STAMP(6);
 
   const uint32_t out_bytes = (uint32_t)nvalid * (STAGE_FLOATS * 4);
   const bool bulk_ok = (out_bytes & 15u) == 0;
@@ -988,6 +1041,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   }
 
   if (bulk_ok && tid == NT - 1) bulk_wait_read();  // shared memory must outlive the store's reads
+  PHC_STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1049,16 +1103,25 @@ __global__ void running_norm_forward_kernel(const float* __restrict__ x, int64_t
 using namespace phc;
 
 template <typename Kern>
-static int launch_step(Kern kern, size_t smem, int epb, const StepParams& p, cudaStream_t stream, bool* attr_set) {
+static int launch_step(Kern kern, size_t smem, int epb, const StepParams& p, cudaStream_t stream, bool* attr_set,
+                       bool pdl) {
   if (!*attr_set) {
     PHC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     *attr_set = true;
   }
-  const unsigned grid = (unsigned)((p.n + epb - 1) / epb);
-  kern<<<grid, epb * J24, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((p.n + epb - 1) / epb));
+  cfg.blockDim = dim3((unsigned)(epb * J24));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  PHC_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   return launch_status();
 }
-
 
 struct PhcLib {
   LibDev d;
@@ -1236,6 +1299,9 @@ int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_pos, int
 // ---- fused step --------------------------------------------------------------------------
 constexpr int STEP_EPB = 8;
 
+static unsigned long long* g_trace = nullptr;  // phc_set_trace_buffer (profiling only)
+static int64_t g_trace_capacity = 0;
+
 static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, StepParams& p) {
   if (!lib || !a) return PHC_ERR_NULL;
   int rc = check_body(&a->body);
@@ -1270,6 +1336,7 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.reset = a->reset_buf;
   p.term = a->terminate_buf;
   p.moments = a->obs_moments;
+  p.trace = g_trace_capacity >= (n + 3) / 4 * 3 ? g_trace : nullptr;
   p.n = n;
   const PhcBodyState& s = a->body;
   // fast path: the four views are slices of one AoS-13 tensor whose env rows are 16-B aligned
@@ -1284,6 +1351,7 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
 
 static int g_force_generic = -1;  // PHC_OPT_FORCE_GENERIC_STEP / env PHC_STEP_GENERIC=1
 static int g_fast_epb = -1;       // PHC_OPT_STEP_EPB / env PHC_STEP_EPB=4|8
+static int g_pdl = -1;            // PHC_OPT_STEP_PDL / env PHC_STEP_PDL=0|1 (default 1)
 
 static void init_options() {
   if (g_force_generic < 0) {
@@ -1294,6 +1362,16 @@ static void init_options() {
     const char* w = getenv("PHC_STEP_EPB");
     g_fast_epb = (w && w[0] == '8') ? 8 : 4;
   }
+  if (g_pdl < 0) {
+    const char* w = getenv("PHC_STEP_PDL");
+    g_pdl = (w && w[0] == '0') ? 0 : 1;
+  }
+}
+
+int phc_set_trace_buffer(uint64_t* device_buf, int64_t capacity_warps) {
+  g_trace = (unsigned long long*)device_buf;
+  g_trace_capacity = device_buf ? capacity_warps : 0;
+  return PHC_OK;
 }
 
 int phc_set_option(int key, int value) {
@@ -1305,6 +1383,9 @@ int phc_set_option(int key, int value) {
     case PHC_OPT_STEP_EPB:
       if (value != 4 && value != 8) return PHC_ERR_SHAPE;
       g_fast_epb = value;
+      return PHC_OK;
+    case PHC_OPT_STEP_PDL:
+      g_pdl = value ? 1 : 0;
       return PHC_OK;
     default:
       return PHC_ERR_UNSUPPORTED;
@@ -1327,10 +1408,10 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
   static bool attr_fast4[64] = {}, attr_fast8[64] = {}, attr_gen[64] = {};
   if (fast) {
     if (g_fast_epb == 8)
-      return launch_step(step_fast_kernel<8, 4>, sizeof(FastSmem<8>), 8, p, stream, &attr_fast8[dev]);
-    return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev]);
+      return launch_step(step_fast_kernel<8, 4>, sizeof(FastSmem<8>), 8, p, stream, &attr_fast8[dev], g_pdl != 0);
+    return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev], g_pdl != 0);
   }
-  return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev]);
+  return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev], false);
 }
 
 // ---- RunningNorm ---------------------------------------------------------------------------

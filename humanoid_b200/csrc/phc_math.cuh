@@ -7,7 +7,11 @@
 // mocap frames (torch_utils.py:121).  This translation unit is compiled with -fmad=false so
 // a*b+c is two roundings, as in ATen's one-kernel-per-op evaluation; the two places where
 // ATen's CPU kernels do fuse (cross product, 3-vector norm) use __fmaf_rn explicitly.
-// Divisions and square roots are IEEE (-prec-div/-prec-sqrt default), no fast-math.
+// The integer path (calc_frame_blend) and everything a termination flag depends on use IEEE
+// division / square root (-prec-div/-prec-sqrt default, no fast-math).  The float-only outputs
+// use branch-free "faithful" (<= 1-2 ulp) replacements where the reference's value is itself a
+// rounded transcendental: see sin_q1 / sqrt_faithful / div_faithful / wrap_angle below and
+// DESIGN.md "arithmetic" for the measured effect (1e-7 relative, against the 1e-5 tolerance).
 #pragma once
 
 #include <cstdint>
@@ -27,6 +31,46 @@ __device__ __forceinline__ Vec3 operator+(Vec3 a, Vec3 b) { return {a.x + b.x, a
 
 // torch.clip(x, 0, 1) on finite input; NaN maps to 0 (the reference would index out of range)
 __device__ __forceinline__ float clip01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+// ---- branch-free faithful primitives (float outputs only) -----------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// a / b given r ~ 1/b: one Newton correction of the quotient, <= 1 ulp, no special-case path
+__device__ __forceinline__ float div_faithful(float a, float b, float r) {
+  const float q = a * r;
+  return __fmaf_rn(__fmaf_rn(-b, q, a), r, q);
+}
+// sqrt(x) for normal x > 0 (NaN for x <= 0, which every caller masks afterwards)
+__device__ __forceinline__ float sqrt_faithful(float x) {
+  const float r = rsqrt_approx(x);
+  const float s = x * r;
+  return __fmaf_rn(__fmaf_rn(-s, s, x), 0.5f * r, s);
+}
+// sin(x) on [0, pi/2] (slerp's arguments are t*theta with theta = acos(|c|) <= pi/2): odd minimax
+// polynomial x + x^3 q(x^2), <= 1.7 ulp, 87 % correctly rounded (profiles/sin_poly_fit.py); no range
+// reduction and no Payne-Hanek slow path, unlike sinf.
+__device__ __forceinline__ float sin_q1(float x) {
+  const float u = x * x;
+  float q = 2.6018724383902736e-06f;
+  q = __fmaf_rn(q, u, -0.00019807404896710068f);
+  q = __fmaf_rn(q, u, 0.008333024568855762f);
+  q = __fmaf_rn(q, u, -0.16666656732559204f);
+  return __fmaf_rn(x * u, q, x);
+}
+// normalize_angle(a) = atan2(sin a, cos a) (torch_utils.py:50-51) for a in [0, 2 pi]: the wrap to
+// (-pi, pi] it computes, without the three transcendentals.  ATen's own evaluation is within
+// 2.4e-7 absolute of this (measured over 6M angles), i.e. at the level of its rounding noise.
+__device__ __forceinline__ float wrap_angle_0_2pi(float a) {
+  return a > 3.14159274101257324f ? a - 6.28318548202514648f : a;
+}
 
 // MotionLibBase._calc_frame_blend, motion_lib.py:655-665.
 //   phase = clip(t / len, 0, 1)   (from the un-clamped time)
@@ -152,21 +196,21 @@ __device__ __forceinline__ Heading heading_quat_inv(Quat q) {
 __device__ __forceinline__ Heading heading_conj(Heading h) { return {-h.z, h.w}; }
 
 // angle of quat_to_angle_axis, torch_utils.py:86-106:
-//   sin_theta = sqrt(1 - w*w); angle = normalize_angle(2*acos(w)); 0 unless |sin_theta| > 1e-5
-__device__ __forceinline__ float quat_angle(float w, float* sin_theta_out = nullptr) {
-  float st = sqrtf(1.0f - w * w);
-  float a = 2.0f * acosf(w);
-  a = atan2f(sinf(a), cosf(a));
-  if (sin_theta_out) *sin_theta_out = st;
-  return (fabsf(st) > 1e-5f) ? a : 0.0f;  // NaN compares false -> 0, as torch.where does
+//   sin_theta = sqrt(1 - w*w); angle = normalize_angle(2*acos(w)); 0 unless |sin_theta| > 1e-5.
+// The mask is evaluated on 1 - w*w directly (sqrt is monotonic; |w| > 1 gives a negative or NaN
+// argument and the comparison is false, as abs(NaN) > 1e-5 is in the reference).
+__device__ __forceinline__ float quat_angle(float w) {
+  const float x = 1.0f - w * w;
+  const float a = wrap_angle_0_2pi(2.0f * acosf(w));
+  return (x > 1.0000000e-10f) ? a : 0.0f;
 }
 
-// quat_to_exp_map, torch_utils.py:135-150
+// quat_to_exp_map, torch_utils.py:135-150 (only get_motion_state's dof_pos needs the axis)
 __device__ __forceinline__ Vec3 quat_exp_map(Quat q) {
-  float st;
-  float a = quat_angle(q.w, &st);
+  const float st = sqrtf(1.0f - q.w * q.w);
+  const float a = wrap_angle_0_2pi(2.0f * acosf(q.w));
   if (fabsf(st) > 1e-5f) return {a * (q.x / st), a * (q.y / st), a * (q.z / st)};
-  return {a * 0.0f, a * 0.0f, a * 1.0f};
+  return {0.0f, 0.0f, 0.0f};
 }
 
 // slerp, torch_utils.py:110-131.  c = ((x0x1 + y0y1) + z0z1) + w0w1 (ATen sum order);
@@ -174,17 +218,21 @@ __device__ __forceinline__ Vec3 quat_exp_map(Quat q) {
 // first and the |cos| >= 1 -> q0 select last (it wins, and masks acos' NaN for c > 1).
 __device__ __forceinline__ Quat quat_slerp(Quat q0, Quat q1, float t) {
   float c = ((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w;
-  if (c < 0.0f) q1 = {-q1.x, -q1.y, -q1.z, -q1.w};
+  const float sg = c < 0.0f ? -1.0f : 1.0f;  // q1[neg] = -q1[neg]: an exact sign flip
+  q1 = {q1.x * sg, q1.y * sg, q1.z * sg, q1.w * sg};
   c = fabsf(c);
-  float th = acosf(c);
-  float s = sqrtf(1.0f - c * c);
-  float ra = sinf((1.0f - t) * th) / s;
-  float rb = sinf(t * th) / s;
+  const float th = acosf(c);
+  const float s = sqrt_faithful(1.0f - c * c);  // 1 - c*c: two roundings, never an FMA
+  const float rs = rcp_approx(s);
+  const float ra = div_faithful(sin_q1((1.0f - t) * th), s, rs);
+  const float rb = div_faithful(sin_q1(t * th), s, rs);
   Quat r = {ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
-  if (fabsf(s) < 0.001f)
-    r = {0.5f * q0.x + 0.5f * q1.x, 0.5f * q0.y + 0.5f * q1.y, 0.5f * q0.z + 0.5f * q1.z, 0.5f * q0.w + 0.5f * q1.w};
-  if (fabsf(c) >= 1.0f) r = q0;
-  return r;
+  const bool avg = fabsf(s) < 0.001f;  // false for NaN, as in the reference
+  r.x = avg ? 0.5f * q0.x + 0.5f * q1.x : r.x;
+  r.y = avg ? 0.5f * q0.y + 0.5f * q1.y : r.y;
+  r.z = avg ? 0.5f * q0.z + 0.5f * q1.z : r.z;
+  r.w = avg ? 0.5f * q0.w + 0.5f * q1.w : r.w;
+  return (c >= 1.0f) ? q0 : r;
 }
 
 // lerp of get_motion_state, motion_lib.py:597-603: (1 - b)*x0 + b*x1
@@ -196,8 +244,11 @@ __device__ __forceinline__ Vec3 lerp3(float om, float b, Vec3 x0, Vec3 x1) {
 // torch.norm(v, dim=-1) over 3 on ATen CPU: sqrt(fma(z,z,fma(y,y,x*x)))
 __device__ __forceinline__ float norm3(Vec3 v) { return sqrtf(__fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, v.x * v.x))); }
 
-// (d**2).mean(dim=-1) over 3: ((x^2 + y^2) + z^2) / 3
-__device__ __forceinline__ float mean_sq3(Vec3 d) { return ((d.x * d.x + d.y * d.y) + d.z * d.z) / 3.0f; }
+// (d**2).mean(dim=-1) over 3: ((x^2 + y^2) + z^2) / 3, the division as a multiply by fl(1/3)
+// (<= 1 ulp from the quotient; feeds only the reward's exponent)
+__device__ __forceinline__ float mean_sq3(Vec3 d) {
+  return ((d.x * d.x + d.y * d.y) + d.z * d.z) * 0.333333343267440796f;
+}
 
 // ATen CPU sum over a contiguous row of floats (vectorised inner reduction, measured on torch
 // 2.11): 8 lane accumulators filled round-robin (lane l gets v[l], v[l+8], ..), then combined

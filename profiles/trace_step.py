@@ -1,0 +1,57 @@
+"""Phase timeline of the fast step kernel from per-warp %globaltimer stamps (phc_set_trace_buffer).
+
+    python profiles/trace_step.py [num_envs]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from humanoid_b200 import HumanoidPHC, MotionLib, _cabi, synth  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+dev = torch.device("cuda", 0)
+lib_data = synth.make_motion_lib(N, 60, 300, (30,), seed=1234, device=dev)
+lib = MotionLib(lib_data, device=dev)
+clock = synth.make_clock(lib_data, N, seed=1235, max_progress=30)
+envs = []
+for r in range(17):
+    ref = lib.get_motion_state(clock.sampled_motion_ids, synth.reward_time(clock, extra_steps=r + 1), clock.global_offset)
+    env = HumanoidPHC(lib, N, device=dev)
+    env.set_sim_state(synth.make_sim_state(ref, seed=1236 + r), copy=False)
+    env.set_clock(clock)
+    envs.append(env)
+for i in range(20):
+    envs[i % 17].post_physics_step(True)
+torch.cuda.synchronize()
+nw = (N + 3) // 4 * 3
+K = 4
+bufs = [torch.zeros(nw * 8, dtype=torch.int64, device=dev) for _ in range(K)]
+capi = _cabi.load()
+for e in envs:
+    e._step_args = None
+    e.post_physics_step(True)
+torch.cuda.synchronize()
+for k in range(K):  # K kernels back to back, each stamping into its own buffer
+    capi.phc_set_trace_buffer(bufs[k].data_ptr(), nw)
+    envs[3 + k].post_physics_step(True)
+torch.cuda.synchronize()
+capi.phc_set_trace_buffer(None, 0)
+T = [b.cpu().numpy().reshape(-1, 3, 8).astype(np.float64) for b in bufs]
+names = ["entry", "tma issued", "past bar1", "data landed", "phase1 done", "stage written", "past bar3", "exit"]
+t00 = T[0][:, :, 0].min()
+prev_end = None
+for k, t in enumerate(T):
+    t = (t - t00) / 1e3
+    w0 = t[:, 0, :]
+    first, last = t[:, :, 0].min(), t[:, :, 7].max()
+    line = f"kernel {k}: first entry {first:7.2f}  last exit {last:7.2f}  span {last - first:5.2f} us"
+    if prev_end is not None:
+        line += f"  | starts {first - prev_end:+.2f} us vs previous kernel's last exit; period {last - prev_last:5.2f} us"
+    print(line)
+    for j, nm in enumerate(names):
+        col = w0[:, j] - (prev_end if prev_end is not None else first)
+        print(f"    warp0 {nm:14s} (rel. prev exit): min {col.min():6.2f}  median {np.median(col):6.2f}  max {col.max():6.2f}")
+    prev_end, prev_last = last, last

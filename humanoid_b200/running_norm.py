@@ -15,10 +15,10 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.distributed as dist
 from torch import nn
 
 from . import _cabi
+from .parallel import reduce_moments
 
 
 class RunningNorm(nn.Module):
@@ -67,9 +67,7 @@ class RunningNorm(nn.Module):
     @torch.no_grad()
     def update_from_moments(self, sums: torch.Tensor, rows: int, group=None):
         """Blend statistics given local partials; all-reduces them first when distributed."""
-        payload = torch.cat([sums, torch.tensor([float(rows)], dtype=torch.float64, device=sums.device)])
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(payload, op=dist.ReduceOp.SUM, group=group)
+        payload = reduce_moments(sums, rows, group)
         n = 2 * self.shape
         _cabi.check(
             _cabi.load().phc_running_norm_update(

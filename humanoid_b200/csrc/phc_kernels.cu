@@ -803,7 +803,6 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem<EPB>& S = *reinterpret_cast<FastSmem<EPB>*>(smem_raw);
   constexpr int NT = EPB * J24;
-  static_assert(2 * EPB <= 32, "phase 0 runs on one warp");
   static_assert(4 * EPB <= 32, "reductions run on one warp");
   const int tid = threadIdx.x;
   const int64_t env0 = (int64_t)blockIdx.x * EPB;
@@ -813,93 +812,138 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   // ---- phase 0 (warp 0): clock, frame-blend, TMA loads ------------------------------------
   // The kernel is launched with programmatic stream serialization: everything before
   // griddepcontrol.wait overlaps the tail of whatever kernel precedes it in the stream.  That
-  // part only SPECULATES — it reads the env's motion id and gathers the clip metadata for it;
-  // after the wait the id is re-read (with the rest of the clock) and the gather is redone in the
-  // rare case it changed, so no caller contract is needed.  All reads of sim state / progress
-  // and all writes happen after the wait.
+  // part only SPECULATES: 3 lanes per env read the clock as it is now and run the frame blend
+  // for progress+1, +2, +3 (this step's two query times, whether or not the previous step's
+  // increment has landed yet), and prefetch the sim row and the frame span into L2.  After the
+  // wait the clock is re-read in one round of loads; if motion id, start time and offset are
+  // unchanged and progress moved by 0 or 1 the precomputed blends are picked by shuffle,
+  // otherwise the env's leader lane recomputes them.  No caller contract is needed: all
+  // dependent reads (sim state, progress) and all writes happen after the wait.
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (tid < 32) {
+    static_assert(EPB == 4, "phase 0 maps 8 lanes to each of 4 envs");
     if (tid == 0) mbar_init(&S.bar, 1);
-    const int le = tid >> 1, q = tid & 1;
+    const int le = tid >> 3, j = tid & 7;
     const bool act = le < nvalid;
     const int64_t env = env0 + (act ? le : 0);
-    int64_t sid = 0, nf = 2, st = 0;
-    float len = 1.0f, mdt = 1.0f;
-    if (act) {
+    const int adv = p.advance ? 1 : 0;
+    // -- speculation
+    int64_t sid = -1, st = 0;
+    int nf = 2, sprog = 0;
+    float len = 1.0f, mdt = 1.0f, sstart = 0.0f, ssoff = 0.0f;
+    int c_f0 = 0, c_f1 = 0;  // clip-local candidate frames for progress + adv + j
+    float c_bl = 0.0f, c_t = 0.0f;
+    if (act && j < 3) {
       sid = p.ids[env];
+      sprog = (int)p.progress[env];
+      sstart = p.start[env];
+      ssoff = p.start_off[env];
       const int64_t c = sid < 0 ? 0 : (sid >= p.L.M ? p.L.M - 1 : sid);  // stale garbage must not fault
       len = p.L.len[c];
-      nf = p.L.nf[c];
+      nf = (int)p.L.nf[c];
       mdt = p.L.mdt[c];
       st = p.L.starts[c];
+      c_t = (float)(int16_t)(sprog + adv + j) * p.dt + sstart + ssoff;
+      calc_frame_blend32(c_t, len, nf, mdt, c_f0, c_f1, c_bl);
+      if (j == 0) {  // warm L2: sim row (coherent there, whoever writes it next) and frames j = 0..2
+        const float* srow = p.body.pos.ptr + env * p.body.pos.stride_env;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(srow), "r"(ROW13 * 4) : "memory");
+        const float* frow = p.L.packed + (st + c_f0) * FRAME_FLOATS;
+        int nfr = nf - c_f0 < 4 ? nf - c_f0 : 4;
+        if (nfr > 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(frow), "r"(nfr * FRAME_FLOATS * 4)
+                       : "memory");
+      }
     }
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    PHC_STAMP(2);
     __syncwarp();
-    int64_t f0 = -1, f1 = -1;
-    if (act) {
-      // one round of independent loads
-      const int16_t prog_in = p.progress[env];
-      const int64_t id = p.ids[env];
-      const float start = p.start[env], soff = p.start_off[env];
-      float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
-      if (q == 0 && p.goff) {
+    // -- one round of dependent loads, then validate
+    int prog_in = 0;
+    bool ok = false;
+    float start = 0.0f, soff = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+    int64_t id = 0;
+    if (act && j == 0) {
+      prog_in = (int)p.progress[env];
+      id = p.ids[env];
+      start = p.start[env];
+      soff = p.start_off[env];
+      if (p.goff) {
         g0 = p.goff[env * 3 + 0];
         g1 = p.goff[env * 3 + 1];
         g2 = p.goff[env * 3 + 2];
       }
-      if (id != sid) {  // the speculation missed (env was re-assigned a clip): gather again
+      const int d = prog_in - sprog;
+      ok = id == sid && __float_as_uint(start) == __float_as_uint(sstart) &&
+           __float_as_uint(soff) == __float_as_uint(ssoff) && (d == 0 || d == 1);
+    }
+    const int d = act ? (prog_in - sprog) & 1 : 0;  // only meaningful on leaders with ok
+    const int src0 = (tid & ~7) + d, src1 = src0 + 1;
+    int a_f0 = __shfl_sync(0xffffffffu, c_f0, src0), a_f1 = __shfl_sync(0xffffffffu, c_f1, src0);
+    int b_f0 = __shfl_sync(0xffffffffu, c_f0, src1), b_f1 = __shfl_sync(0xffffffffu, c_f1, src1);
+    float a_bl = __shfl_sync(0xffffffffu, c_bl, src0), b_bl = __shfl_sync(0xffffffffu, c_bl, src1);
+    float a_t = __shfl_sync(0xffffffffu, c_t, src0);
+    if (act && j == 0) {
+      int prog = prog_in;
+      if (p.advance) prog = (int)(int16_t)(prog + 1);
+      if (!ok) {  // the speculation missed (reset / re-assigned clip / foreign writer): do it now
         len = p.L.len[id];
-        nf = p.L.nf[id];
+        nf = (int)p.L.nf[id];
         mdt = p.L.mdt[id];
         st = p.L.starts[id];
+        // q = 0: t = progress*dt + start + offset (humanoid_phc.py:1236); q = 1: (progress+1)*dt + ..
+        // (humanoid_phc.py:1063-1067), progress already advanced (humanoid_phc.py:138)
+        a_t = (float)(int16_t)prog * p.dt + start + soff;
+        calc_frame_blend32(a_t, len, nf, mdt, a_f0, a_f1, a_bl);
+        const float t1 = (float)(int16_t)(prog + 1) * p.dt + start + soff;
+        calc_frame_blend32(t1, len, nf, mdt, b_f0, b_f1, b_bl);
       }
-      int prog = (int)prog_in;
-      if (p.advance) prog = (int)(int16_t)(prog + 1);
-      // q = 0: t = progress*dt + start + offset (humanoid_phc.py:1236); q = 1: (progress+1)*dt + ..
-      // (humanoid_phc.py:1063-1067), progress already advanced (humanoid_phc.py:138)
-      const float t = (float)(int16_t)(prog + q) * p.dt + start + soff;
-      int64_t i0, i1;
-      float bl;
-      calc_frame_blend(t, len, nf, mdt, i0, i1, bl);
-      f0 = i0 + st;
-      f1 = i1 + st;
-      S.bl[q][le] = bl;
-      if (q == 0) {
-        S.prog[le] = prog;
-        S.pass[le] = t >= len;  // _compute_reset, humanoid_phc.py:1317
-        S.fallen[le] = 0;
-        if (p.advance) p.progress[env] = (int16_t)prog;
-        S.goff[le][0] = g0;
-        S.goff[le][1] = g1;
-        S.goff[le][2] = g2;
-      }
-    }
-    // the t+dt lane learns the frames of the t lane and reuses their slots where equal
-    const int64_t p0 = __shfl_up_sync(0xffffffffu, f0, 1), p1 = __shfl_up_sync(0xffffffffu, f1, 1);
-    if (act) {
+      S.bl[0][le] = a_bl;
+      S.bl[1][le] = b_bl;
+      S.prog[le] = prog;
+      S.pass[le] = a_t >= len;  // _compute_reset, humanoid_phc.py:1317
+      S.fallen[le] = 0;
+      if (p.advance) p.progress[env] = (int16_t)prog;
+      S.goff[le][0] = g0;
+      S.goff[le][1] = g1;
+      S.goff[le][2] = g2;
+      // frames of one clip are consecutive rows of the packed table: when the (up to four)
+      // frames span <= 4 rows they arrive with ONE copy and slot = frame - first
       float* fr = S.frames + le * (4 * FRAME_FLOATS);
-      int s0, s1;
-      uint32_t bytes = 0;
-      if (q == 0) {
-        s0 = 0;
-        s1 = (f1 == f0) ? 0 : 1;
-        bytes = (1 + (s1 == 1) + 1) * (uint32_t)(FRAME_FLOATS * 4);  // frame(s) + the env's sim row
-      } else {
-        const int ps1 = (p1 == p0) ? 0 : 1;
-        s0 = (f0 == p0) ? 0 : (f0 == p1) ? ps1 : 2;
-        s1 = (f1 == f0) ? s0 : (f1 == p0) ? 0 : (f1 == p1) ? ps1 : 3;
-        bytes = ((s0 == 2) + (s1 == 3)) * (uint32_t)(FRAME_FLOATS * 4);
+      const float* tab = p.L.packed + st * FRAME_FLOATS;
+      const int lo = a_f0 < b_f0 ? a_f0 : b_f0;
+      int hi = a_f1 > b_f1 ? a_f1 : b_f1;
+      hi = hi > a_f0 ? hi : a_f0;
+      hi = hi > b_f0 ? hi : b_f0;
+      const bool one = hi - lo <= 3 && a_f1 >= lo && a_f0 >= lo;
+      const bool block_sim = p.body.pos.stride_env == ROW13;  // whole block's sim rows are one span
+      uint32_t bytes = (block_sim ? (le == 0 ? (uint32_t)nvalid : 0u) : 1u) * (uint32_t)(ROW13 * 4);
+      if (one) {
+        S.slot[0][0][le] = a_f0 - lo;
+        S.slot[0][1][le] = a_f1 - lo;
+        S.slot[1][0][le] = b_f0 - lo;
+        S.slot[1][1][le] = b_f1 - lo;
+        bytes += (uint32_t)(hi - lo + 1) * (uint32_t)(FRAME_FLOATS * 4);
+      } else {  // two spans of one or two rows each (idx1 is idx0 or idx0 + 1)
+        S.slot[0][0][le] = 0;
+        S.slot[0][1][le] = a_f1 - a_f0;
+        S.slot[1][0][le] = 2;
+        S.slot[1][1][le] = 2 + (b_f1 - b_f0);
+        bytes += (uint32_t)((a_f1 - a_f0 + 1) + (b_f1 - b_f0 + 1)) * (uint32_t)(FRAME_FLOATS * 4);
       }
-      S.slot[q][0][le] = s0;
-      S.slot[q][1][le] = s1;
-      if (bytes) mbar_expect_tx(&S.bar, bytes);
-      if (q == 0) {
-        bulk_g2s(S.sim + le * ROW13, p.body.pos.ptr + (env0 + le) * p.body.pos.stride_env, ROW13 * 4, &S.bar);
-        bulk_load_frame(p.L, fr, f0, &S.bar);
-        if (s1 == 1) bulk_load_frame(p.L, fr + FRAME_FLOATS, f1, &S.bar);
+      mbar_expect_tx(&S.bar, bytes);
+      if (block_sim) {
+        if (le == 0)
+          bulk_g2s(S.sim, p.body.pos.ptr + env0 * ROW13, (uint32_t)nvalid * (ROW13 * 4), &S.bar);
       } else {
-        if (s0 == 2) bulk_load_frame(p.L, fr + 2 * FRAME_FLOATS, f0, &S.bar);
-        if (s1 == 3) bulk_load_frame(p.L, fr + 3 * FRAME_FLOATS, f1, &S.bar);
+        bulk_g2s(S.sim + le * ROW13, p.body.pos.ptr + env * p.body.pos.stride_env, ROW13 * 4, &S.bar);
+      }
+      if (one) {
+        bulk_g2s(fr, tab + (int64_t)lo * FRAME_FLOATS, (uint32_t)(hi - lo + 1) * (FRAME_FLOATS * 4), &S.bar);
+      } else {
+        bulk_g2s(fr, tab + (int64_t)a_f0 * FRAME_FLOATS, (uint32_t)(a_f1 - a_f0 + 1) * (FRAME_FLOATS * 4), &S.bar);
+        bulk_g2s(fr + 2 * FRAME_FLOATS, tab + (int64_t)b_f0 * FRAME_FLOATS,
+                 (uint32_t)(b_f1 - b_f0 + 1) * (FRAME_FLOATS * 4), &S.bar);
       }
     }
     __syncwarp();
@@ -910,7 +954,6 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
   }
   __syncthreads();  // #1: slots / blends / barrier init visible
-  PHC_STAMP(2);
   mbar_wait(&S.bar, 0);
   PHC_STAMP(3);
 
@@ -1381,7 +1424,7 @@ int phc_set_option(int key, int value) {
       g_force_generic = value ? 1 : 0;
       return PHC_OK;
     case PHC_OPT_STEP_EPB:
-      if (value != 4 && value != 8) return PHC_ERR_SHAPE;
+      if (value != 4) return PHC_ERR_SHAPE;
       g_fast_epb = value;
       return PHC_OK;
     case PHC_OPT_STEP_PDL:
@@ -1405,10 +1448,8 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
   // fast path: T == 1, AoS sim tensor (16-B aligned rows), dense 16-B aligned obs_buf
   const bool fast = !g_force_generic && p.T == 1 && p.aos && p.L.packed && p.obs_stride == STAGE_FLOATS &&
                     ((uintptr_t)p.obs & 15) == 0;
-  static bool attr_fast4[64] = {}, attr_fast8[64] = {}, attr_gen[64] = {};
+  static bool attr_fast4[64] = {}, attr_gen[64] = {};
   if (fast) {
-    if (g_fast_epb == 8)
-      return launch_step(step_fast_kernel<8, 4>, sizeof(FastSmem<8>), 8, p, stream, &attr_fast8[dev], g_pdl != 0);
     return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev], g_pdl != 0);
   }
   return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev], false);

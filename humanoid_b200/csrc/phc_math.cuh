@@ -86,6 +86,17 @@ __device__ __forceinline__ void calc_frame_blend(float t, float len, int64_t nf,
   blend = clip01((t - (float)idx0 * dt) / dt);
 }
 
+// The same with 32-bit frame counts (any clip below 2^31 frames): identical results — int32 and
+// int64 convert to the same float, and the truncation is of a value in [0, nf-1].
+__device__ __forceinline__ void calc_frame_blend32(float t, float len, int nf, float dt, int& idx0, int& idx1,
+                                                   float& blend) {
+  float phase = clip01(t / len);
+  if (t < 0.0f) t = 0.0f;
+  idx0 = (int)(phase * (float)(nf - 1));
+  idx1 = idx0 + 1 < nf - 1 ? idx0 + 1 : nf - 1;
+  blend = clip01((t - (float)idx0 * dt) / dt);
+}
+
 // quat_mul, torch_utils.py:55-75 (8-multiply form, same grouping)
 __device__ __forceinline__ Quat quat_mul(Quat a, Quat b) {
   float ww = (a.z + a.x) * (b.x + b.y);

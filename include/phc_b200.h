@@ -219,13 +219,13 @@ PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n
  * 16-B aligned AoS-13 tensor and obs_buf is dense and 16-B aligned; otherwise, or when
  * PHC_OPT_FORCE_GENERIC_STEP is set, the generic kernel (any T, any strides). */
 #define PHC_OPT_FORCE_GENERIC_STEP 1 /* value 0/1 */
-#define PHC_OPT_STEP_EPB 2           /* envs per block of the fast kernel: 4 (default) or 8 */
+#define PHC_OPT_STEP_EPB 2           /* envs per block of the fast kernel: 4 (the only value built) */
 #define PHC_OPT_STEP_PDL 3           /* 1 (default): launch the fast kernel with programmatic stream
                                         serialization so its prologue overlaps the previous kernel's tail */
 PHC_API int phc_set_option(int key, int value);
 /* Profiling aid: when a device buffer of capacity_warps x 8 uint64 is set, every warp of the
  * fast step kernel (EPB 4: 3 warps per block) stamps %globaltimer (ns) at its phase boundaries:
- * 0 entry, 1 TMA issued (warp 0), 2 past barrier 1, 3 data landed, 4 phase 1 done,
+ * 0 entry, 1 TMA issued (warp 0), 2 dependency wait returned (warp 0), 3 data landed, 4 phase 1 done,
  * 5 stage written, 6 past barrier 3, 7 exit.  NULL switches it off. */
 PHC_API int phc_set_trace_buffer(uint64_t* device_buf, int64_t capacity_warps);
 

@@ -40,7 +40,7 @@ for k in range(K):  # K kernels back to back, each stamping into its own buffer
 torch.cuda.synchronize()
 capi.phc_set_trace_buffer(None, 0)
 T = [b.cpu().numpy().reshape(-1, 3, 8).astype(np.float64) for b in bufs]
-names = ["entry", "tma issued", "past bar1", "data landed", "phase1 done", "stage written", "past bar3", "exit"]
+names = ["entry", "tma issued", "dep wait done", "data landed", "phase1 done", "stage written", "past bar3", "exit"]
 t00 = T[0][:, :, 0].min()
 prev_end = None
 for k, t in enumerate(T):

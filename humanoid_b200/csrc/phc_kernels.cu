@@ -70,6 +70,11 @@ __device__ __forceinline__ void st4(float* p, Quat q) {
   p[2] = q.z;
   p[3] = q.w;
 }
+__device__ __forceinline__ void st6_shared(float* p, const float* v) {  // p is 8-byte aligned
+  reinterpret_cast<float2*>(p)[0] = make_float2(v[0], v[1]);
+  reinterpret_cast<float2*>(p)[1] = make_float2(v[2], v[3]);
+  reinterpret_cast<float2*>(p)[2] = make_float2(v[4], v[5]);
+}
 __device__ __forceinline__ const float* view_at(const PhcView& v, int64_t env, int body) {
   return v.ptr + env * v.stride_env + (int64_t)body * v.stride_body;
 }
@@ -256,14 +261,14 @@ __global__ void self_obs_kernel(PhcBodyState s, int64_t n, uint32_t flags, float
   Quat root_rot = ld4(view_at(s.rot, env, 0));
   if (!(flags & PHC_OBS_UPRIGHT)) root_rot = remove_base_rot(root_rot);
   const Heading hi = heading_quat_inv(root_rot);
-  const float hs = heading_scale(hi);
+  const HeadingRot hr = heading_rot(hi);
   float* row = out + env * out_stride;
   int col = 0;
   if (flags & PHC_OBS_ROOT_HEIGHT) {
     if (b == 0) row[0] = root_pos.z;
     col = 1;
   }
-  if (b >= 1) st3(row + col + (b - 1) * 3, heading_rotate(hi, hs, ld3(view_at(s.pos, env, b)) - root_pos));
+  if (b >= 1) st3(row + col + (b - 1) * 3, heading_rotate(hr, ld3(view_at(s.pos, env, b)) - root_pos));
   col += (J - 1) * 3;
   {
     float t6[6];
@@ -278,9 +283,9 @@ __global__ void self_obs_kernel(PhcBodyState s, int64_t n, uint32_t flags, float
     for (int k = 0; k < 6; ++k) row[col + b * 6 + k] = t6[k];
   }
   col += J * 6;
-  st3(row + col + b * 3, heading_rotate(hi, hs, ld3(view_at(s.vel, env, b))));
+  st3(row + col + b * 3, heading_rotate(hr, ld3(view_at(s.vel, env, b))));
   col += J * 3;
-  st3(row + col + b * 3, heading_rotate(hi, hs, ld3(view_at(s.ang_vel, env, b))));
+  st3(row + col + b * 3, heading_rotate(hr, ld3(view_at(s.ang_vel, env, b))));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -294,13 +299,13 @@ struct TaskObs {  // one body's 24 floats of a v6 block
   float l_rot[6];
 };
 
-__device__ __forceinline__ void task_obs_body(Heading hi, float hs, Vec3 root_pos, Vec3 pos, Quat rot, Vec3 vel,
+__device__ __forceinline__ void task_obs_body(Heading hi, const HeadingRot& hr, Vec3 root_pos, Vec3 pos, Quat rot, Vec3 vel,
                                               Vec3 ang, const RefBody& r, bool full, TaskObs& o) {
-  o.d_pos = heading_rotate(hi, hs, r.pos - pos);
-  o.d_vel = heading_rotate(hi, hs, r.vel - vel);
-  o.l_pos = heading_rotate(hi, hs, r.pos - root_pos);
+  o.d_pos = heading_rotate(hr, r.pos - pos);
+  o.d_vel = heading_rotate(hr, r.vel - vel);
+  o.l_pos = heading_rotate(hr, r.pos - root_pos);
   if (full) {
-    o.d_ang = heading_rotate(hi, hs, r.ang - ang);
+    o.d_ang = heading_rotate(hr, r.ang - ang);
     Quat dg = quat_mul(r.rot, quat_conj(rot));
     Quat dl = heading_mul_right(heading_mul_left(hi, dg), heading_conj(hi));
     quat_tan_norm(dl, o.d_rot);
@@ -323,14 +328,14 @@ __global__ void imitation_obs_kernel(const float* __restrict__ root_pos, int64_t
   Quat rr = ld4(root_rot + env * rr_stride);
   if (!upright) rr = remove_base_rot(rr);
   const Heading hi = heading_quat_inv(rr);
-  const float hs = heading_scale(hi);
+  const HeadingRot hr = heading_rot(hi);
   RefBody r;
   r.pos = ld3(view_at(ref.pos, et, b));
   r.rot = ld4(view_at(ref.rot, et, b));
   r.vel = ld3(view_at(ref.vel, et, b));
   r.ang = ld3(view_at(ref.ang_vel, et, b));
   TaskObs o;
-  task_obs_body(hi, hs, ld3(root_pos + env * rp_stride), ld3(view_at(s.pos, env, b)), ld4(view_at(s.rot, env, b)),
+  task_obs_body(hi, hr, ld3(root_pos + env * rp_stride), ld3(view_at(s.pos, env, b)), ld4(view_at(s.rot, env, b)),
                 ld3(view_at(s.vel, env, b)), ld3(view_at(s.ang_vel, env, b)), r, mode == 6, o);
   if (mode == 6) {
     float* row = out + env * out_stride + (int64_t)t * (24 * J);
@@ -356,8 +361,7 @@ __global__ void imitation_obs_kernel(const float* __restrict__ root_pos, int64_t
 __device__ __forceinline__ void reward_partials(Vec3 pos, Quat rot, Vec3 vel, Vec3 ang, const RefBody& r,
                                                 float& sp, float& sr, float& sv, float& sa) {
   sp = mean_sq3(r.pos - pos);  // (d**2).mean(-1), common.py:299
-  Quat dq = quat_mul(r.rot, quat_conj(rot));
-  const float a = quat_angle(dq.w);
+  const float a = quat_angle(quat_mul_conj_w(r.rot, rot));
   sr = a * a;
   sv = mean_sq3(r.vel - vel);
   sa = mean_sq3(r.ang - ang);
@@ -674,7 +678,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
   // ---- phase 2: observations -------------------------------------------------------------
   const Vec3 root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
   const Heading hi = {S.hz[e], S.hw[e]};
-  const float hs = heading_scale(hi);
+  const HeadingRot hr = heading_rot(hi);
   const int W = SELF_DIM + TASK_DIM * T;
 
   for (int q = 1; q <= T; ++q) {
@@ -690,13 +694,13 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
         if (b == 0)
           row[0] = root_pos.z;
         else
-          st3(row + 1 + (b - 1) * 3, heading_rotate(hi, hs, pos - root_pos));
+          st3(row + 1 + (b - 1) * 3, heading_rotate(hr, pos - root_pos));
         quat_tan_norm(heading_mul_left(hi, rot), row + 70 + b * 6);
-        st3(row + 214 + b * 3, heading_rotate(hi, hs, vel));
-        st3(row + 286 + b * 3, heading_rotate(hi, hs, ang));
+        st3(row + 214 + b * 3, heading_rotate(hr, vel));
+        st3(row + 286 + b * 3, heading_rotate(hr, ang));
       }
       TaskObs o;
-      task_obs_body(hi, hs, root_pos, pos, rot, vel, ang, r, true, o);
+      task_obs_body(hi, hr, root_pos, pos, rot, vel, ang, r, true, o);
       float* tk = row + SELF_DIM;
       st3(tk + b * 3, o.d_pos);
 #pragma unroll
@@ -863,15 +867,20 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     bool ok = false;
     float start = 0.0f, soff = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
     int64_t id = 0;
-    if (act && j == 0) {
-      prog_in = (int)p.progress[env];
-      id = p.ids[env];
-      start = p.start[env];
-      soff = p.start_off[env];
+    Quat rootq = {0.0f, 0.0f, 0.0f, 1.0f};
+    if (act && j == 1) {  // root rotation = floats 3..6 of the env's sim row
+      const float* rq = p.body.pos.ptr + env * p.body.pos.stride_env + 3;
+      rootq = {__ldcg(rq), __ldcg(rq + 1), __ldcg(rq + 2), __ldcg(rq + 3)};
+    }
+    if (act && j == 0) {  // .cg: these addresses were read before the wait; never trust L1 for them
+      prog_in = (int)__ldcg(p.progress + env);
+      id = __ldcg(p.ids + env);
+      start = __ldcg(p.start + env);
+      soff = __ldcg(p.start_off + env);
       if (p.goff) {
-        g0 = p.goff[env * 3 + 0];
-        g1 = p.goff[env * 3 + 1];
-        g2 = p.goff[env * 3 + 2];
+        g0 = __ldcg(p.goff + env * 3 + 0);
+        g1 = __ldcg(p.goff + env * 3 + 1);
+        g2 = __ldcg(p.goff + env * 3 + 2);
       }
       const int d = prog_in - sprog;
       ok = id == sid && __float_as_uint(start) == __float_as_uint(sstart) &&
@@ -949,6 +958,13 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     __syncwarp();
     if (tid == 0) mbar_arrive(&S.bar);
     PHC_STAMP(1);
+    // while the copies fly: the env's heading quaternion from the root rotation (lane j == 1 read
+    // it with the clock), so nobody computes it on the block's critical path later
+    if (act && j == 1) {
+      const Heading h0 = heading_quat_inv(rootq);  // upright: root_rot as is (common.py:42-44)
+      S.hz[le] = h0.z;
+      S.hw[le] = h0.w;
+    }
   }
   else {
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
@@ -985,12 +1001,6 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     }
     r1 = blend_ref2(fr + S.slot[1][0][e] * FRAME_FLOATS, fr + S.slot[1][1][e] * FRAME_FLOATS, S.bl[1][e], S.goff[e], b);
   }
-  if (tid < nvalid) {  // one lane per env, all in warp 0: a single divergent region per block
-    const float* d = S.sim + tid * ROW13;
-    const Heading h0 = heading_quat_inv(Quat{d[3], d[4], d[5], d[6]});  // upright: root_rot as is (common.py:42-44)
-    S.hz[tid] = h0.z;
-    S.hw[tid] = h0.w;
-  }
   PHC_STAMP(4);
   __syncthreads();  // #2: partials / heading visible; frame buffer dead -> becomes the obs stage
 
@@ -998,28 +1008,28 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   if (valid) {
     const Vec3 root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
     const Heading hi = {S.hz[e], S.hw[e]};
-    const float hs = heading_scale(hi);
+    const HeadingRot hr = heading_rot(hi);
     float* row = S.frames + e * STAGE_FLOATS;
     // self obs, common.py:23-103 (default flags: local root, height, upright)
     if (b == 0)
       row[0] = root_pos.z;
     else
-      st3(row + 1 + (b - 1) * 3, heading_rotate(hi, hs, pos - root_pos));
-    quat_tan_norm(heading_mul_left(hi, rot), row + 70 + b * 6);
-    st3(row + 214 + b * 3, heading_rotate(hi, hs, vel));
-    st3(row + 286 + b * 3, heading_rotate(hi, hs, ang));
+      st3(row + 1 + (b - 1) * 3, heading_rotate(hr, pos - root_pos));
+    float t6[6];
+    quat_tan_norm(heading_mul_left(hi, rot), t6);
+    st6_shared(row + 70 + b * 6, t6);
+    st3(row + 214 + b * 3, heading_rotate(hr, vel));
+    st3(row + 286 + b * 3, heading_rotate(hr, ang));
     // task obs v6, common.py:106-176
     TaskObs o;
-    task_obs_body(hi, hs, root_pos, pos, rot, vel, ang, r1, true, o);
+    task_obs_body(hi, hr, root_pos, pos, rot, vel, ang, r1, true, o);
     float* tk = row + SELF_DIM;
     st3(tk + b * 3, o.d_pos);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) tk[72 + b * 6 + k] = o.d_rot[k];
+    st6_shared(tk + 72 + b * 6, o.d_rot);
     st3(tk + 216 + b * 3, o.d_vel);
     st3(tk + 288 + b * 3, o.d_ang);
     st3(tk + 360 + b * 3, o.l_pos);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) tk[432 + b * 6 + k] = o.l_rot[k];
+    st6_shared(tk + 432 + b * 6, o.l_rot);
   }
   fence_proxy_async();  // stage writes -> visible to the bulk-store engine
   PHC_STAMP(5);

@@ -97,95 +97,81 @@ __device__ __forceinline__ void calc_frame_blend32(float t, float len, int nf, f
   blend = clip01((t - (float)idx0 * dt) / dt);
 }
 
-// quat_mul, torch_utils.py:55-75 (8-multiply form, same grouping)
+// quat_mul, torch_utils.py:55-75.  The reference uses an 8-multiply form whose absolute error is
+// ~1e-7 for unit quaternions; the Hamilton product accumulated with FMAs has the same error level
+// in 16 instructions instead of 26, so it is used for every product on the path (the operands are
+// slerp outputs that already differ from the reference's by their sin/acos rounding).
 __device__ __forceinline__ Quat quat_mul(Quat a, Quat b) {
-  float ww = (a.z + a.x) * (b.x + b.y);
-  float yy = (a.w - a.y) * (b.w + b.z);
-  float zz = (a.w + a.y) * (b.w - b.z);
-  float xx = ww + yy + zz;
-  float qq = 0.5f * (xx + (a.z - a.x) * (b.x - b.y));
   Quat r;
-  r.w = qq - ww + (a.z - a.y) * (b.y - b.z);
-  r.x = qq - xx + (a.x + a.w) * (b.x + b.w);
-  r.y = qq - yy + (a.w - a.x) * (b.y + b.z);
-  r.z = qq - zz + (a.z + a.y) * (b.w - b.x);
+  r.x = __fmaf_rn(a.w, b.x, __fmaf_rn(a.x, b.w, __fmaf_rn(a.y, b.z, -(a.z * b.y))));
+  r.y = __fmaf_rn(a.w, b.y, __fmaf_rn(a.y, b.w, __fmaf_rn(a.z, b.x, -(a.x * b.z))));
+  r.z = __fmaf_rn(a.w, b.z, __fmaf_rn(a.z, b.w, __fmaf_rn(a.x, b.y, -(a.y * b.x))));
+  r.w = __fmaf_rn(a.w, b.w, -__fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)));
   return r;
 }
 
 __device__ __forceinline__ Quat quat_conj(Quat q) { return {-q.x, -q.y, -q.z, q.w}; }
 
+// w of quat_mul(a, conj(b)) — all the reward needs of the rotation difference (common.py:304-306)
+__device__ __forceinline__ float quat_mul_conj_w(Quat a, Quat b) {
+  return __fmaf_rn(a.w, b.w, __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)));
+}
+
 // A heading quaternion (0, 0, z, w): rotation about the up axis.  The x, y components of
-// calc_heading_quat(_inv) are exactly +-0 (torch_utils.py:354-358 with axis (0,0,1)), so
-// the products below drop the terms that add +-0; results equal quat_mul / my_quat_rotate
-// bit for bit except for the sign of an exact zero.
+// calc_heading_quat(_inv) are exactly +-0 (torch_utils.py:354-358 with axis (0,0,1)), so the
+// products below only keep the terms that survive.
 struct Heading {
   float z, w;
 };
 
 // quat_mul(h, q) with h = (0,0,z,w)
 __device__ __forceinline__ Quat heading_mul_left(Heading h, Quat b) {
-  float ww = h.z * (b.x + b.y);
-  float yy = h.w * (b.w + b.z);
-  float zz = h.w * (b.w - b.z);
-  float xx = ww + yy + zz;
-  float qq = 0.5f * (xx + h.z * (b.x - b.y));
   Quat r;
-  r.w = qq - ww + h.z * (b.y - b.z);
-  r.x = qq - xx + h.w * (b.x + b.w);
-  r.y = qq - yy + h.w * (b.y + b.z);
-  r.z = qq - zz + h.z * (b.w - b.x);
+  r.x = __fmaf_rn(h.w, b.x, -(h.z * b.y));
+  r.y = __fmaf_rn(h.w, b.y, h.z * b.x);
+  r.z = __fmaf_rn(h.w, b.z, h.z * b.w);
+  r.w = __fmaf_rn(h.w, b.w, -(h.z * b.z));
   return r;
 }
 
 // quat_mul(q, h) with h = (0,0,z,w)
 __device__ __forceinline__ Quat heading_mul_right(Quat a, Heading h) {
-  float yy = (a.w - a.y) * (h.w + h.z);
-  float zz = (a.w + a.y) * (h.w - h.z);
-  float xx = yy + zz;
-  float qq = 0.5f * xx;
   Quat r;
-  r.w = qq + (a.z - a.y) * (-h.z);
-  r.x = qq - xx + (a.x + a.w) * h.w;
-  r.y = qq - yy + (a.w - a.x) * h.z;
-  r.z = qq - zz + (a.z + a.y) * h.w;
+  r.x = __fmaf_rn(a.x, h.w, a.y * h.z);
+  r.y = __fmaf_rn(a.y, h.w, -(a.x * h.z));
+  r.z = __fmaf_rn(a.z, h.w, a.w * h.z);
+  r.w = __fmaf_rn(a.w, h.w, -(a.z * h.z));
   return r;
 }
 
-// my_quat_rotate, torch_utils.py:274-281:  (v*(2w^2-1) + cross(q,v)*w*2) + q*dot(q,v)*2
-// cross is ATen's fused form fma(a1,b2,-(a2*b1)); the dot is bmm's sequential sum.
-__device__ __forceinline__ Vec3 quat_rotate(Quat q, Vec3 v) {
-  float s = 2.0f * (q.w * q.w) - 1.0f;
-  float cx = __fmaf_rn(q.y, v.z, -(q.z * v.y));
-  float cy = __fmaf_rn(q.z, v.x, -(q.x * v.z));
-  float cz = __fmaf_rn(q.x, v.y, -(q.y * v.x));
-  float d = (q.x * v.x + q.y * v.y) + q.z * v.z;
-  Vec3 r;
-  r.x = (v.x * s + cx * q.w * 2.0f) + q.x * d * 2.0f;
-  r.y = (v.y * s + cy * q.w * 2.0f) + q.y * d * 2.0f;
-  r.z = (v.z * s + cz * q.w * 2.0f) + q.z * d * 2.0f;
-  return r;
+// my_quat_rotate, torch_utils.py:274-281, with q = (0,0,z,w):
+//   x' = x(2w^2-1) - 2zw y,   y' = y(2w^2-1) + 2zw x,   z' = z((2w^2-1) + 2z^2)
+// The three coefficients are formed once per thread.
+struct HeadingRot {
+  float a, b, d;
+};
+__device__ __forceinline__ HeadingRot heading_rot(Heading h) {
+  HeadingRot c;
+  c.a = __fmaf_rn(2.0f * h.w, h.w, -1.0f);
+  c.b = 2.0f * h.z * h.w;
+  c.d = __fmaf_rn(2.0f * h.z, h.z, c.a);
+  return c;
+}
+__device__ __forceinline__ Vec3 heading_rotate(const HeadingRot& c, Vec3 v) {
+  return {__fmaf_rn(v.x, c.a, -(v.y * c.b)), __fmaf_rn(v.y, c.a, v.x * c.b), v.z * c.d};
 }
 
-// my_quat_rotate with q = (0,0,z,w); hs = 2w^2-1 precomputed by heading_scale()
-__device__ __forceinline__ float heading_scale(Heading h) { return 2.0f * (h.w * h.w) - 1.0f; }
-__device__ __forceinline__ Vec3 heading_rotate(Heading h, float hs, Vec3 v) {
-  Vec3 r;
-  r.x = v.x * hs + (-(h.z * v.y)) * h.w * 2.0f;
-  r.y = v.y * hs + (h.z * v.x) * h.w * 2.0f;
-  r.z = v.z * hs + h.z * (h.z * v.z) * 2.0f;
-  return r;
-}
-
-// quat_to_tan_norm, torch_utils.py:285-297: rotate (1,0,0) then (0,0,1); closed form of
-// my_quat_rotate on the unit axes (terms that are exactly zero dropped).
+// quat_to_tan_norm, torch_utils.py:285-297: my_quat_rotate of (1,0,0) and of (0,0,1):
+//   tan  = (2w^2-1 + 2x^2,  2zw + 2xy,  -2yw + 2xz),   norm = (2yw + 2xz,  -2xw + 2yz,  2w^2-1 + 2z^2)
 __device__ __forceinline__ void quat_tan_norm(Quat q, float* out6) {
-  float s = 2.0f * (q.w * q.w) - 1.0f;
-  out6[0] = s + q.x * q.x * 2.0f;
-  out6[1] = q.z * q.w * 2.0f + q.y * q.x * 2.0f;
-  out6[2] = (-q.y) * q.w * 2.0f + q.z * q.x * 2.0f;
-  out6[3] = q.y * q.w * 2.0f + q.x * q.z * 2.0f;
-  out6[4] = (-q.x) * q.w * 2.0f + q.y * q.z * 2.0f;
-  out6[5] = s + q.z * q.z * 2.0f;
+  const float x2 = q.x + q.x, y2 = q.y + q.y, z2 = q.z + q.z;
+  const float s = __fmaf_rn(q.w + q.w, q.w, -1.0f);
+  out6[0] = __fmaf_rn(x2, q.x, s);
+  out6[1] = __fmaf_rn(z2, q.w, y2 * q.x);
+  out6[2] = __fmaf_rn(z2, q.x, -(y2 * q.w));
+  out6[3] = __fmaf_rn(y2, q.w, x2 * q.z);
+  out6[4] = __fmaf_rn(y2, q.z, -(x2 * q.w));
+  out6[5] = __fmaf_rn(z2, q.z, s);
 }
 
 // remove_base_rot, envs/common.py:15-19: q (x) conj(0.5,0.5,0.5,0.5)
@@ -229,21 +215,21 @@ __device__ __forceinline__ Vec3 quat_exp_map(Quat q) {
 // first and the |cos| >= 1 -> q0 select last (it wins, and masks acos' NaN for c > 1).
 __device__ __forceinline__ Quat quat_slerp(Quat q0, Quat q1, float t) {
   float c = ((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w;
-  const float sg = c < 0.0f ? -1.0f : 1.0f;  // q1[neg] = -q1[neg]: an exact sign flip
-  q1 = {q1.x * sg, q1.y * sg, q1.z * sg, q1.w * sg};
+  const float sg = c < 0.0f ? -1.0f : 1.0f;  // q1[neg] = -q1[neg]: folded into q1's coefficient
   c = fabsf(c);
   const float th = acosf(c);
   const float s = sqrt_faithful(1.0f - c * c);  // 1 - c*c: two roundings, never an FMA
   const float rs = rcp_approx(s);
-  const float ra = div_faithful(sin_q1((1.0f - t) * th), s, rs);
-  const float rb = div_faithful(sin_q1(t * th), s, rs);
-  Quat r = {ra * q0.x + rb * q1.x, ra * q0.y + rb * q1.y, ra * q0.z + rb * q1.z, ra * q0.w + rb * q1.w};
+  float ra = div_faithful(sin_q1((1.0f - t) * th), s, rs);
+  float rb = div_faithful(sin_q1(t * th), s, rs);
   const bool avg = fabsf(s) < 0.001f;  // false for NaN, as in the reference
-  r.x = avg ? 0.5f * q0.x + 0.5f * q1.x : r.x;
-  r.y = avg ? 0.5f * q0.y + 0.5f * q1.y : r.y;
-  r.z = avg ? 0.5f * q0.z + 0.5f * q1.z : r.z;
-  r.w = avg ? 0.5f * q0.w + 0.5f * q1.w : r.w;
-  return (c >= 1.0f) ? q0 : r;
+  ra = avg ? 0.5f : ra;                // 0.5 q0 + 0.5 q1
+  rb = avg ? 0.5f : rb;
+  const bool same = c >= 1.0f;         // -> q0; applied last, masks the NaNs of acos(c > 1)
+  ra = same ? 1.0f : ra;
+  rb = (same ? 0.0f : rb) * sg;
+  return {__fmaf_rn(rb, q1.x, ra * q0.x), __fmaf_rn(rb, q1.y, ra * q0.y), __fmaf_rn(rb, q1.z, ra * q0.z),
+          __fmaf_rn(rb, q1.w, ra * q0.w)};
 }
 
 // lerp of get_motion_state, motion_lib.py:597-603: (1 - b)*x0 + b*x1
@@ -258,7 +244,7 @@ __device__ __forceinline__ float norm3(Vec3 v) { return sqrtf(__fmaf_rn(v.z, v.z
 // (d**2).mean(dim=-1) over 3: ((x^2 + y^2) + z^2) / 3, the division as a multiply by fl(1/3)
 // (<= 1 ulp from the quotient; feeds only the reward's exponent)
 __device__ __forceinline__ float mean_sq3(Vec3 d) {
-  return ((d.x * d.x + d.y * d.y) + d.z * d.z) * 0.333333343267440796f;
+  return __fmaf_rn(d.z, d.z, __fmaf_rn(d.y, d.y, d.x * d.x)) * 0.333333343267440796f;
 }
 
 // ATen CPU sum over a contiguous row of floats (vectorised inner reduction, measured on torch

@@ -25,6 +25,7 @@ MAX_TIME_STEPS = 16
 OPT_FORCE_GENERIC_STEP = 1
 OPT_STEP_EPB = 2
 OPT_STEP_PDL = 3
+OPT_TEST_SPEC_FAULT = 4
 
 OBS_LOCAL_ROOT = 1
 OBS_ROOT_HEIGHT = 2

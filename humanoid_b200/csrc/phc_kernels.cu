@@ -475,6 +475,8 @@ struct StepParams {
   uint8_t* term;
   double* moments;
   int64_t n;
+  int first_wave_blocks;      // blocks that can be resident at once (speculate before the dependency wait)
+  int spec_fault;             // test hook: perturb the speculated clock (PHC_OPT_TEST_SPEC_FAULT)
   unsigned long long* trace;  // NULL, or [grid][8] globaltimer stamps (phc_set_trace_buffer)
   int aos;        // sim state is one AoS-13 tensor, 16-B aligned rows
   int obs_vec2;   // obs rows can be written with 8-byte stores
@@ -783,6 +785,7 @@ struct FastSmem {
   float goff[EPB][4];
   float hz[EPB], hw[EPB];
   int prog[EPB], pass[EPB], fallen[EPB];
+  int parity;  // phase of `bar` the consumers wait for
 };
 
 __device__ __forceinline__ void bulk_load_frame(const LibDev& L, float* dst, int64_t f, unsigned long long* bar) {
@@ -813,35 +816,48 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
   PHC_STAMP(0);
 
-  // ---- phase 0 (warp 0): clock, frame-blend, TMA loads ------------------------------------
+  // ---- phase 0: clock, frame-blend, TMA loads ---------------------------------------------------
   // The kernel is launched with programmatic stream serialization: everything before
   // griddepcontrol.wait overlaps the tail of whatever kernel precedes it in the stream.  That
-  // part only SPECULATES: 3 lanes per env read the clock as it is now and run the frame blend
-  // for progress+1, +2, +3 (this step's two query times, whether or not the previous step's
-  // increment has landed yet), and prefetch the sim row and the frame span into L2.  After the
-  // wait the clock is re-read in one round of loads; if motion id, start time and offset are
-  // unchanged and progress moved by 0 or 1 the precomputed blends are picked by shuffle,
-  // otherwise the env's leader lane recomputes them.  No caller contract is needed: all
-  // dependent reads (sim state, progress) and all writes happen after the wait.
+  // part only SPECULATES, and only on immutable data: 3 lanes per env read the clock as it is
+  // now and run the frame blend for progress+1, +2, +3 (this step's two query times, whether or
+  // not the previous step's increment has landed yet); when the frames of all three fit the env's
+  // four slots they are copied into shared memory right away (frame rows never change).  After
+  // the wait the sim rows are fetched at once and the clock is re-read in one round of loads; if
+  // motion id, start time and offset are unchanged and progress moved by 0 or 1 the pre-loaded
+  // frames and precomputed blends are simply selected, otherwise the env's leader lane redoes
+  // its blends and copies.  No caller contract is needed: every dependent read (sim state,
+  // progress) and every write happens after the wait.
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  // blocks beyond the first wave start after the dependency is long resolved: nothing to overlap
+  const bool speculate = blockIdx.x < (unsigned)p.first_wave_blocks;
   if (tid < 32) {
     static_assert(EPB == 4, "phase 0 maps 8 lanes to each of 4 envs");
     if (tid == 0) mbar_init(&S.bar, 1);
+    __syncwarp();
     const int le = tid >> 3, j = tid & 7;
     const bool act = le < nvalid;
+    const bool lead = act && j == 0;
     const int64_t env = env0 + (act ? le : 0);
     const int adv = p.advance ? 1 : 0;
-    // -- speculation
+    float* fr = S.frames + le * (4 * FRAME_FLOATS);
+    // -- speculation (lanes j < 3 of each env)
     int64_t sid = -1, st = 0;
     int nf = 2, sprog = 0;
     float len = 1.0f, mdt = 1.0f, sstart = 0.0f, ssoff = 0.0f;
     int c_f0 = 0, c_f1 = 0;  // clip-local candidate frames for progress + adv + j
     float c_bl = 0.0f, c_t = 0.0f;
-    if (act && j < 3) {
+    if (speculate && act && j < 3) {
       sid = p.ids[env];
       sprog = (int)p.progress[env];
       sstart = p.start[env];
       ssoff = p.start_off[env];
+      if (p.spec_fault) {  // test hook: pretend the clock was different when speculated
+        if (p.spec_fault & 1) sprog -= 1;               // previous step's increment not landed yet
+        if (p.spec_fault & 2) sstart += 1.0f / 30.0f;   // env was reset in between
+        if (p.spec_fault & 4) sprog -= 2;               // progress moved by more than one
+        if (p.spec_fault & 8) sid += 1;                 // env was re-assigned a clip
+      }
       const int64_t c = sid < 0 ? 0 : (sid >= p.L.M ? p.L.M - 1 : sid);  // stale garbage must not fault
       len = p.L.len[c];
       nf = (int)p.L.nf[c];
@@ -849,30 +865,38 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       st = p.L.starts[c];
       c_t = (float)(int16_t)(sprog + adv + j) * p.dt + sstart + ssoff;
       calc_frame_blend32(c_t, len, nf, mdt, c_f0, c_f1, c_bl);
-      if (j == 0) {  // warm L2: sim row (coherent there, whoever writes it next) and frames j = 0..2
-        const float* srow = p.body.pos.ptr + env * p.body.pos.stride_env;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(srow), "r"(ROW13 * 4) : "memory");
-        const float* frow = p.L.packed + (st + c_f0) * FRAME_FLOATS;
-        int nfr = nf - c_f0 < 4 ? nf - c_f0 : 4;
-        if (nfr > 0)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(frow), "r"(nfr * FRAME_FLOATS * 4)
-                       : "memory");
-      }
+    }
+    // Slots hold 4 frames.  Candidates 0..1 serve "progress unchanged since speculation" (the
+    // usual case: the previous step wrote progress long before this block started), 1..2 serve
+    // "moved by one"; take all three when they fit, else the first two.
+    const int hi1 = __shfl_sync(0xffffffffu, c_f1, (tid & ~7) + 1);
+    const int hi2 = __shfl_sync(0xffffffffu, c_f1, (tid & ~7) + 2);
+    const int s_lo = c_f0;  // on the leader: candidate 0's first frame
+    const bool all3 = hi2 - s_lo <= 3 && hi2 >= hi1;
+    const int s_hi = all3 ? hi2 : hi1;
+    const bool spec = speculate && lead && s_hi - s_lo <= 3 && s_hi >= s_lo;
+    if (spec) {  // frames of all three candidates -> slots 0..(hi-lo)
+      const uint32_t bytes = (uint32_t)(s_hi - s_lo + 1) * (uint32_t)(FRAME_FLOATS * 4);
+      mbar_expect_tx(&S.bar, bytes);
+      bulk_g2s(fr, p.L.packed + (st + s_lo) * FRAME_FLOATS, bytes, &S.bar);
+    }
+    const bool block_sim = p.body.pos.stride_env == ROW13;  // the block's sim rows are one span
+    if (speculate && lead && (block_sim ? le == 0 : true)) {
+      // warm L2 with the sim rows: L2 is the point of coherence, so whoever writes them before the
+      // dependency resolves updates the same lines
+      const uint32_t bytes = (block_sim ? (uint32_t)nvalid : 1u) * (uint32_t)(ROW13 * 4);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p.body.pos.ptr + env * p.body.pos.stride_env),
+                   "r"(bytes)
+                   : "memory");
     }
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     PHC_STAMP(2);
-    __syncwarp();
-    // -- one round of dependent loads, then validate
+    // -- dependent data: one round of clock loads, the sim rows' copy issued under them
     int prog_in = 0;
     bool ok = false;
     float start = 0.0f, soff = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
     int64_t id = 0;
-    Quat rootq = {0.0f, 0.0f, 0.0f, 1.0f};
-    if (act && j == 1) {  // root rotation = floats 3..6 of the env's sim row
-      const float* rq = p.body.pos.ptr + env * p.body.pos.stride_env + 3;
-      rootq = {__ldcg(rq), __ldcg(rq + 1), __ldcg(rq + 2), __ldcg(rq + 3)};
-    }
-    if (act && j == 0) {  // .cg: these addresses were read before the wait; never trust L1 for them
+    if (lead) {  // .cg: these addresses may have been read before the wait; never trust L1 for them
       prog_in = (int)__ldcg(p.progress + env);
       id = __ldcg(p.ids + env);
       start = __ldcg(p.start + env);
@@ -882,20 +906,33 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
         g1 = __ldcg(p.goff + env * 3 + 1);
         g2 = __ldcg(p.goff + env * 3 + 2);
       }
-      const int d = prog_in - sprog;
-      ok = id == sid && __float_as_uint(start) == __float_as_uint(sstart) &&
-           __float_as_uint(soff) == __float_as_uint(ssoff) && (d == 0 || d == 1);
+      if (block_sim ? le == 0 : true) {  // sim rows: issued while the clock loads are in flight
+        const uint32_t bytes = (block_sim ? (uint32_t)nvalid : 1u) * (uint32_t)(ROW13 * 4);
+        mbar_expect_tx(&S.bar, bytes);
+        bulk_g2s(S.sim + le * ROW13, p.body.pos.ptr + env * p.body.pos.stride_env, bytes, &S.bar);
+      }
+      const int dd = prog_in - sprog;
+      ok = speculate && id == sid && __float_as_uint(start) == __float_as_uint(sstart) &&
+           __float_as_uint(soff) == __float_as_uint(ssoff) && (dd == 0 || (dd == 1 && all3));
     }
-    const int d = act ? (prog_in - sprog) & 1 : 0;  // only meaningful on leaders with ok
+    const int d = (prog_in - sprog) & 1;  // meaningful on leaders with ok
     const int src0 = (tid & ~7) + d, src1 = src0 + 1;
     int a_f0 = __shfl_sync(0xffffffffu, c_f0, src0), a_f1 = __shfl_sync(0xffffffffu, c_f1, src0);
     int b_f0 = __shfl_sync(0xffffffffu, c_f0, src1), b_f1 = __shfl_sync(0xffffffffu, c_f1, src1);
     float a_bl = __shfl_sync(0xffffffffu, c_bl, src0), b_bl = __shfl_sync(0xffffffffu, c_bl, src1);
     float a_t = __shfl_sync(0xffffffffu, c_t, src0);
-    if (act && j == 0) {
+    // a leader whose pre-loaded frames cannot be used has to wait for them to land before it
+    // overwrites the slots: rare, handled with a second phase of the same mbarrier
+    const bool redo = lead && spec && !ok;
+    const unsigned any_redo = __ballot_sync(0xffffffffu, redo);
+    if (any_redo) {
+      if (tid == 0) mbar_arrive(&S.bar);
+      mbar_wait(&S.bar, 0);
+    }
+    if (lead) {
       int prog = prog_in;
       if (p.advance) prog = (int)(int16_t)(prog + 1);
-      if (!ok) {  // the speculation missed (reset / re-assigned clip / foreign writer): do it now
+      if (!ok) {  // no (usable) speculation: first-wave miss, or a later-wave block
         len = p.L.len[id];
         nf = (int)p.L.nf[id];
         mdt = p.L.mdt[id];
@@ -916,61 +953,60 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       S.goff[le][0] = g0;
       S.goff[le][1] = g1;
       S.goff[le][2] = g2;
-      // frames of one clip are consecutive rows of the packed table: when the (up to four)
-      // frames span <= 4 rows they arrive with ONE copy and slot = frame - first
-      float* fr = S.frames + le * (4 * FRAME_FLOATS);
-      const float* tab = p.L.packed + st * FRAME_FLOATS;
-      const int lo = a_f0 < b_f0 ? a_f0 : b_f0;
-      int hi = a_f1 > b_f1 ? a_f1 : b_f1;
-      hi = hi > a_f0 ? hi : a_f0;
-      hi = hi > b_f0 ? hi : b_f0;
-      const bool one = hi - lo <= 3 && a_f1 >= lo && a_f0 >= lo;
-      const bool block_sim = p.body.pos.stride_env == ROW13;  // whole block's sim rows are one span
-      uint32_t bytes = (block_sim ? (le == 0 ? (uint32_t)nvalid : 0u) : 1u) * (uint32_t)(ROW13 * 4);
-      if (one) {
-        S.slot[0][0][le] = a_f0 - lo;
-        S.slot[0][1][le] = a_f1 - lo;
-        S.slot[1][0][le] = b_f0 - lo;
-        S.slot[1][1][le] = b_f1 - lo;
-        bytes += (uint32_t)(hi - lo + 1) * (uint32_t)(FRAME_FLOATS * 4);
-      } else {  // two spans of one or two rows each (idx1 is idx0 or idx0 + 1)
-        S.slot[0][0][le] = 0;
-        S.slot[0][1][le] = a_f1 - a_f0;
-        S.slot[1][0][le] = 2;
-        S.slot[1][1][le] = 2 + (b_f1 - b_f0);
-        bytes += (uint32_t)((a_f1 - a_f0 + 1) + (b_f1 - b_f0 + 1)) * (uint32_t)(FRAME_FLOATS * 4);
-      }
-      mbar_expect_tx(&S.bar, bytes);
-      if (block_sim) {
-        if (le == 0)
-          bulk_g2s(S.sim, p.body.pos.ptr + env0 * ROW13, (uint32_t)nvalid * (ROW13 * 4), &S.bar);
+      if (ok && spec) {  // frames are already (arriving) in the slots
+        S.slot[0][0][le] = a_f0 - s_lo;
+        S.slot[0][1][le] = a_f1 - s_lo;
+        S.slot[1][0][le] = b_f0 - s_lo;
+        S.slot[1][1][le] = b_f1 - s_lo;
       } else {
-        bulk_g2s(S.sim + le * ROW13, p.body.pos.ptr + env * p.body.pos.stride_env, ROW13 * 4, &S.bar);
-      }
-      if (one) {
-        bulk_g2s(fr, tab + (int64_t)lo * FRAME_FLOATS, (uint32_t)(hi - lo + 1) * (FRAME_FLOATS * 4), &S.bar);
-      } else {
-        bulk_g2s(fr, tab + (int64_t)a_f0 * FRAME_FLOATS, (uint32_t)(a_f1 - a_f0 + 1) * (FRAME_FLOATS * 4), &S.bar);
-        bulk_g2s(fr + 2 * FRAME_FLOATS, tab + (int64_t)b_f0 * FRAME_FLOATS,
-                 (uint32_t)(b_f1 - b_f0 + 1) * (FRAME_FLOATS * 4), &S.bar);
+        // frames of one clip are consecutive rows of the packed table: when the (up to four)
+        // frames span <= 4 rows they arrive with ONE copy and slot = frame - first
+        const float* tab = p.L.packed + st * FRAME_FLOATS;
+        const int lo = a_f0 < b_f0 ? a_f0 : b_f0;
+        int hi = a_f1 > b_f1 ? a_f1 : b_f1;
+        hi = hi > a_f0 ? hi : a_f0;
+        hi = hi > b_f0 ? hi : b_f0;
+        if (hi - lo <= 3) {
+          S.slot[0][0][le] = a_f0 - lo;
+          S.slot[0][1][le] = a_f1 - lo;
+          S.slot[1][0][le] = b_f0 - lo;
+          S.slot[1][1][le] = b_f1 - lo;
+          const uint32_t bytes = (uint32_t)(hi - lo + 1) * (uint32_t)(FRAME_FLOATS * 4);
+          mbar_expect_tx(&S.bar, bytes);
+          bulk_g2s(fr, tab + (int64_t)lo * FRAME_FLOATS, bytes, &S.bar);
+        } else {  // two spans of one or two rows each (idx1 is idx0 or idx0 + 1)
+          S.slot[0][0][le] = 0;
+          S.slot[0][1][le] = a_f1 - a_f0;
+          S.slot[1][0][le] = 2;
+          S.slot[1][1][le] = 2 + (b_f1 - b_f0);
+          const uint32_t ba = (uint32_t)(a_f1 - a_f0 + 1) * (uint32_t)(FRAME_FLOATS * 4);
+          const uint32_t bb = (uint32_t)(b_f1 - b_f0 + 1) * (uint32_t)(FRAME_FLOATS * 4);
+          mbar_expect_tx(&S.bar, ba + bb);
+          bulk_g2s(fr, tab + (int64_t)a_f0 * FRAME_FLOATS, ba, &S.bar);
+          bulk_g2s(fr + 2 * FRAME_FLOATS, tab + (int64_t)b_f0 * FRAME_FLOATS, bb, &S.bar);
+        }
       }
     }
     __syncwarp();
-    if (tid == 0) mbar_arrive(&S.bar);
+    if (tid == 0) {
+      S.parity = any_redo ? 1 : 0;
+      mbar_arrive(&S.bar);
+    }
     PHC_STAMP(1);
-    // while the copies fly: the env's heading quaternion from the root rotation (lane j == 1 read
-    // it with the clock), so nobody computes it on the block's critical path later
-    if (act && j == 1) {
-      const Heading h0 = heading_quat_inv(rootq);  // upright: root_rot as is (common.py:42-44)
-      S.hz[le] = h0.z;
+  } else {
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    // warp 1, one lane per env: the heading quaternion straight from the root rotation in global
+    // memory (floats 3..6 of the env's sim row), while warp 0 validates the clock
+    if (tid >= 32 && tid < 32 + nvalid) {
+      const int le = tid - 32;
+      const float* rq = p.body.pos.ptr + (env0 + le) * p.body.pos.stride_env + 3;
+      const Heading h0 = heading_quat_inv(Quat{__ldcg(rq), __ldcg(rq + 1), __ldcg(rq + 2), __ldcg(rq + 3)});
+      S.hz[le] = h0.z;  // upright: root_rot used as is (common.py:42-44)
       S.hw[le] = h0.w;
     }
   }
-  else {
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
-  }
-  __syncthreads();  // #1: slots / blends / barrier init visible
-  mbar_wait(&S.bar, 0);
+  __syncthreads();  // #1: slots / blends / heading / barrier state visible
+  mbar_wait(&S.bar, (uint32_t)S.parity);
   PHC_STAMP(3);
 
   // ---- phase 1: per-body reference states, reward partials, distance ------------------------
@@ -1352,8 +1388,10 @@ int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_pos, int
 // ---- fused step --------------------------------------------------------------------------
 constexpr int STEP_EPB = 8;
 
+static int g_spec_fault = 0;  // PHC_OPT_TEST_SPEC_FAULT
 static unsigned long long* g_trace = nullptr;  // phc_set_trace_buffer (profiling only)
 static int64_t g_trace_capacity = 0;
+static int64_t g_trace_launch = 0;
 
 static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, StepParams& p) {
   if (!lib || !a) return PHC_ERR_NULL;
@@ -1389,7 +1427,17 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.reset = a->reset_buf;
   p.term = a->terminate_buf;
   p.moments = a->obs_moments;
-  p.trace = g_trace_capacity >= (n + 3) / 4 * 3 ? g_trace : nullptr;
+  p.first_wave_blocks = 0;
+  p.spec_fault = g_spec_fault;
+  {  // profiling only: consecutive launches stamp consecutive slices of the trace buffer
+    const int64_t nw = (n + 3) / 4 * 3;
+    if (g_trace && (g_trace_launch + 1) * nw <= g_trace_capacity) {
+      p.trace = g_trace + g_trace_launch * nw * 8;
+      ++g_trace_launch;
+    } else {
+      p.trace = nullptr;
+    }
+  }
   p.n = n;
   const PhcBodyState& s = a->body;
   // fast path: the four views are slices of one AoS-13 tensor whose env rows are 16-B aligned
@@ -1424,6 +1472,7 @@ static void init_options() {
 int phc_set_trace_buffer(uint64_t* device_buf, int64_t capacity_warps) {
   g_trace = (unsigned long long*)device_buf;
   g_trace_capacity = device_buf ? capacity_warps : 0;
+  g_trace_launch = 0;
   return PHC_OK;
 }
 
@@ -1439,6 +1488,9 @@ int phc_set_option(int key, int value) {
       return PHC_OK;
     case PHC_OPT_STEP_PDL:
       g_pdl = value ? 1 : 0;
+      return PHC_OK;
+    case PHC_OPT_TEST_SPEC_FAULT:
+      g_spec_fault = value;
       return PHC_OK;
     default:
       return PHC_ERR_UNSUPPORTED;
@@ -1459,7 +1511,18 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
   const bool fast = !g_force_generic && p.T == 1 && p.aos && p.L.packed && p.obs_stride == STAGE_FLOATS &&
                     ((uintptr_t)p.obs & 15) == 0;
   static bool attr_fast4[64] = {}, attr_gen[64] = {};
+  static int first_wave[64] = {};
   if (fast) {
+    if (!first_wave[dev]) {
+      int sms = 0, per_sm = 0;
+      PHC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      PHC_CUDA(cudaFuncSetAttribute(step_fast_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(FastSmem<4>)));
+      PHC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_fast_kernel<4, 8>, 4 * J24,
+                                                             sizeof(FastSmem<4>)));
+      first_wave[dev] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    p.first_wave_blocks = g_pdl ? first_wave[dev] : 0;
     return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev], g_pdl != 0);
   }
   return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev], false);

@@ -222,11 +222,15 @@ PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n
 #define PHC_OPT_STEP_EPB 2           /* envs per block of the fast kernel: 4 (the only value built) */
 #define PHC_OPT_STEP_PDL 3           /* 1 (default): launch the fast kernel with programmatic stream
                                         serialization so its prologue overlaps the previous kernel's tail */
+#define PHC_OPT_TEST_SPEC_FAULT 4     /* test hook, bit mask: perturb the clock the fast kernel speculated on
+                                        (1 progress-1, 2 start time, 4 progress-2, 8 motion id) so the
+                                        validation / redo paths run; results must not change */
 PHC_API int phc_set_option(int key, int value);
 /* Profiling aid: when a device buffer of capacity_warps x 8 uint64 is set, every warp of the
  * fast step kernel (EPB 4: 3 warps per block) stamps %globaltimer (ns) at its phase boundaries:
  * 0 entry, 1 TMA issued (warp 0), 2 dependency wait returned (warp 0), 3 data landed, 4 phase 1 done,
- * 5 stage written, 6 past barrier 3, 7 exit.  NULL switches it off. */
+ * 5 stage written, 6 past barrier 3, 7 exit.  Consecutive launches use consecutive slices of
+ * the buffer until it is full.  NULL switches it off. */
 PHC_API int phc_set_trace_buffer(uint64_t* device_buf, int64_t capacity_warps);
 
 /* ------------------------------------------------------------------------------------

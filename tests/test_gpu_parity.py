@@ -526,3 +526,68 @@ def test_host_pipeline_matches_device_path():
     assert torch.equal(h["raw"], env.reward_raw[:, :4].cpu())
     assert torch.equal(h["reset"].bool(), env.reset_buf.cpu()) and torch.equal(h["term"].bool(), env._terminate_buf.cpu())
     assert torch.equal(h["prog"], env.progress_buf.cpu())
+
+
+@pytest.mark.parametrize("regime", ["aligned30", "mixed_fps_unaligned"])
+def test_speculation_miss_paths_do_not_change_results(regime):
+    """The fast kernel speculates on the clock before its stream dependency resolves.  Perturbing
+    what it speculated on (progress behind by 1 or 2, start time, motion id) must leave every
+    output bit-identical: the validation selects other candidates or redoes blends and copies."""
+    from humanoid_b200 import HumanoidPHC, _cabi
+
+    kw = dict(max_frames=90, max_progress=40)
+    if regime != "aligned30":
+        kw.update(ids="random", aligned=False, fps_choices=(30, 60, 120), min_frames=60, max_frames=400)
+    N = 3001
+    lib_data, clock, state = _gpu_case(N, 257, 209, **kw)
+    lib = MotionLib(lib_data, device=DEV)
+    capi = _cabi.load()
+    outs = []
+    try:
+        for fault in (0, 1, 2, 4, 8, 3):
+            assert capi.phc_set_option(_cabi.OPT_TEST_SPEC_FAULT, fault) == 0
+            env = HumanoidPHC(lib, N, device=DEV)
+            env.set_sim_state(state)
+            env.set_clock(clock)
+            for _ in range(3):
+                env.step()
+            torch.cuda.synchronize()
+            outs.append(env)
+    finally:
+        capi.phc_set_option(_cabi.OPT_TEST_SPEC_FAULT, 0)
+    g = outs[0]
+    for f in outs[1:]:
+        assert torch.equal(f.obs_buf, g.obs_buf)
+        assert torch.equal(f.rew_buf, g.rew_buf) and torch.equal(f.reward_raw, g.reward_raw)
+        assert torch.equal(f.reset_buf, g.reset_buf) and torch.equal(f._terminate_buf, g._terminate_buf)
+        assert torch.equal(f.progress_buf, g.progress_buf)
+
+
+def test_env_reset_between_steps_is_seen_by_the_next_step():
+    """Clock arrays rewritten on the device between two steps (what a reset does) with no host sync."""
+    lib_data, clock, state = make_case_cpu(num_envs=640, num_motions=40, seed=111, max_progress=30)
+    env = env_from(lib_data, clock, state)
+    ol = O.OracleMotionLib(lib_data)
+    prog = clock.progress_buf.clone()
+    term = torch.full((24,), 0.25)
+    args = lambda c, p: (ol, state, p, c.motion_start_times, c.motion_start_times_offset, c.global_offset,  # noqa: E731
+                         c.sampled_motion_ids, term, synth.SIM_DT)
+    O.step(*args(clock, prog))
+    env.step()
+    # "reset" every third env: new clip, new start time, progress 0 — device-side writes, same stream
+    sel = torch.arange(0, 640, 3)
+    c2 = clock.clone()
+    c2.sampled_motion_ids[sel] = (clock.sampled_motion_ids[sel] + 7) % 40
+    c2.motion_start_times[sel] = (torch.arange(sel.numel()) % 5).float() * (1 / 30)
+    prog[sel] = 0
+    sel_d = sel.to(DEV)
+    env._sampled_motion_ids[sel_d] = c2.sampled_motion_ids[sel].to(DEV)
+    env._motion_start_times[sel_d] = c2.motion_start_times[sel].to(DEV)
+    env.progress_buf[sel_d] = 0
+    want = O.step(*args(c2, prog))
+    env.step()
+    assert_equal_exact(env.progress_buf, prog, "progress")
+    assert_equal_exact(env.reset_buf, want[3], "reset")
+    assert_equal_exact(env._terminate_buf, want[4], "terminated")
+    assert_close(env.obs_buf, want[0], what="obs after reset", **OBS_TOL)
+    assert_close(env.rew_buf, want[1], what="reward after reset", **OBS_TOL)

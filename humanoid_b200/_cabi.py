@@ -94,6 +94,7 @@ class PhcStepArgs(C.Structure):
         ("reward_raw_stride", C.c_int64),
         ("reset_buf", C.c_void_p),
         ("terminate_buf", C.c_void_p),
+        ("flags", C.c_uint32),
         ("obs_moments", C.c_void_p),
     ]
 

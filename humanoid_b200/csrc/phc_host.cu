@@ -1,11 +1,25 @@
-// Host-buffer pipeline around phc_step_fused (the end-to-end call of include/phc_b200.h).
+// Host-buffer entry point around phc_step_fused (the end-to-end call of include/phc_b200.h).
 //
-// The env batch is cut into chunks; chunk c runs H2D(sim state + clock) -> fused step ->
-// D2H(obs, reward, flags) on stream c % 3, so the host->device copy of one chunk, the kernel
-// of another and the device->host copy of a third overlap (PCIe is full duplex; the B200 has
-// separate copy engines per direction).  The call returns when every output is in host memory.
+// Direct path (all caller buffers pinned, hence mapped into the device address space by UVA): the
+// sim state of each chunk is copied in by the host->device copy engine, and the chunk's fused
+// kernel writes obs rows, rewards and flags straight into the caller's host buffers with its
+// bulk stores (no device->host DMA descriptors, no device staging of outputs), so the two
+// directions of the link overlap.  Used whenever cudaPointerGetAttributes says every buffer is
+// device-accessible.
+//
+// Staged path (any pageable buffer): chunked copy pipeline, below.
+//
+// The env batch is cut into chunks; chunk c runs
+//     H2D(sim state) + H2D(packed clock)  ->  fused step  ->  D2H(obs) + D2H(packed scalars)
+// on stream c % 3, so the host->device copy of one chunk, the kernel of another and the
+// device->host copy of a third overlap (PCIe is full duplex; the B200 has copy engines per
+// direction).  The five small clock arrays and the five small outputs of a chunk travel as ONE
+// transfer each through pinned staging buffers owned by the context (a DMA descriptor costs a
+// few microseconds regardless of size; 22 of them per chunk were half of the step time).  The
+// call returns when every output is in the caller's host memory.
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 
 #include <cuda_runtime.h>
@@ -16,19 +30,16 @@ namespace {
 
 constexpr int kStreams = 3;
 constexpr int kStateFloats = PHC_NUM_BODIES * 13;
+// packed clock, per env: ids i64 | goff 3 f32 | start f32 | soff f32 | progress i16  (SoA per chunk)
+constexpr size_t kClockBytes = 8 + 12 + 4 + 4 + 2;
+// packed scalars out, per env: rew f32 | raw 4 f32 | progress i16 | reset u8 | term u8
+constexpr size_t kOutBytes = 4 + 16 + 2 + 1 + 1;
 
-struct DevBuf {
-  float* state = nullptr;
-  int16_t* progress = nullptr;
-  float* start = nullptr;
-  float* start_off = nullptr;
-  float* goff = nullptr;
-  int64_t* ids = nullptr;
-  float* obs = nullptr;
-  float* rew = nullptr;
-  float* raw = nullptr;
-  uint8_t* reset = nullptr;
-  uint8_t* term = nullptr;
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Chunk {
+  int64_t lo = 0, m = 0;
+  size_t clock_off = 0, out_off = 0;  // byte offsets into the packed staging buffers
 };
 
 }  // namespace
@@ -44,9 +55,18 @@ struct PhcHostStep {
   int32_t use_mean = 0, early = 1;
   float dt = 0.f;
   PhcRewardSpec rwd{};
-  DevBuf d;
+  float* d_state = nullptr;
+  float* d_obs = nullptr;
+  unsigned char* d_clock = nullptr;  // packed clock, device
+  unsigned char* d_out = nullptr;    // packed scalar outputs, device
+  unsigned char* h_clock = nullptr;  // pinned staging
+  unsigned char* h_out = nullptr;    // pinned staging
+  size_t pack_capacity = 0;
   cudaStream_t streams[kStreams] = {};
   int last_cuda = 0;
+  // direct path: verdict cached per set of caller pointers
+  const void* seen[11] = {};
+  int seen_direct = -1;
 };
 
 #define HOST_CUDA(ctx, call)            \
@@ -62,18 +82,13 @@ extern "C" {
 
 void phc_host_step_destroy(PhcHostStep* c) {
   if (!c) return;
-  cudaFree(c->d.state);
-  cudaFree(c->d.progress);
-  cudaFree(c->d.start);
-  cudaFree(c->d.start_off);
-  cudaFree(c->d.goff);
-  cudaFree(c->d.ids);
-  cudaFree(c->d.obs);
-  cudaFree(c->d.rew);
-  cudaFree(c->d.raw);
-  cudaFree(c->d.reset);
-  cudaFree(c->d.term);
+  cudaFree(c->d_state);
+  cudaFree(c->d_obs);
+  cudaFree(c->d_clock);
+  cudaFree(c->d_out);
   cudaFree(c->term_dist);
+  if (c->h_clock) cudaFreeHost(c->h_clock);
+  if (c->h_out) cudaFreeHost(c->h_out);
   for (auto& s : c->streams)
     if (s) cudaStreamDestroy(s);
   delete c;
@@ -98,25 +113,23 @@ int phc_host_step_create(const PhcLib* lib, int64_t max_envs, int32_t time_steps
   c->dt = dt;
   c->rwd = *rwd;
   const size_t n = (size_t)max_envs;
+  // every chunk's packed region is padded so each sub-array starts 16-B aligned
+  c->pack_capacity = n * 32 + (size_t)num_chunks * 6 * 64 + 4096;
   cudaError_t e = cudaSuccess;
-  auto alloc = [&](void** p, size_t bytes) {
+  auto dmalloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
   };
-  alloc((void**)&c->d.state, n * kStateFloats * sizeof(float));
-  alloc((void**)&c->d.progress, n * sizeof(int16_t));
-  alloc((void**)&c->d.start, n * sizeof(float));
-  alloc((void**)&c->d.start_off, n * sizeof(float));
-  alloc((void**)&c->d.goff, n * 3 * sizeof(float));
-  alloc((void**)&c->d.ids, n * sizeof(int64_t));
-  alloc((void**)&c->d.obs, n * c->obs_dim * sizeof(float));
-  alloc((void**)&c->d.rew, n * sizeof(float));
-  alloc((void**)&c->d.raw, n * 4 * sizeof(float));
-  alloc((void**)&c->d.reset, n);
-  alloc((void**)&c->d.term, n);
-  alloc((void**)&c->term_dist, PHC_NUM_BODIES * sizeof(float));
+  dmalloc((void**)&c->d_state, n * kStateFloats * sizeof(float));
+  dmalloc((void**)&c->d_obs, n * c->obs_dim * sizeof(float));
+  dmalloc((void**)&c->d_clock, c->pack_capacity);
+  dmalloc((void**)&c->d_out, c->pack_capacity);
+  dmalloc((void**)&c->term_dist, PHC_NUM_BODIES * sizeof(float));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_clock, c->pack_capacity);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_out, c->pack_capacity);
   if (e == cudaSuccess)
     e = cudaMemcpy(c->term_dist, termination_distances_host, PHC_NUM_BODIES * sizeof(float), cudaMemcpyHostToDevice);
-  for (int i = 0; i < kStreams && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+  for (int i = 0; i < kStreams && e == cudaSuccess; ++i)
+    e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     phc_host_step_destroy(c);
     return e == cudaErrorMemoryAllocation ? PHC_ERR_ALLOC : PHC_ERR_CUDA;
@@ -127,11 +140,10 @@ int phc_host_step_create(const PhcLib* lib, int64_t max_envs, int32_t time_steps
 
 int64_t phc_host_step_h2d_bytes(const PhcHostStep* c, int64_t n) {
   (void)c;
-  return n * (int64_t)(kStateFloats * sizeof(float) + sizeof(int16_t) + 2 * sizeof(float) + 3 * sizeof(float) +
-                       sizeof(int64_t));
+  return n * (int64_t)(kStateFloats * sizeof(float) + kClockBytes);
 }
 int64_t phc_host_step_d2h_bytes(const PhcHostStep* c, int64_t n) {
-  return n * (int64_t)(c->obs_dim * sizeof(float) + sizeof(float) + 4 * sizeof(float) + 2 + sizeof(int16_t));
+  return n * (int64_t)(c->obs_dim * sizeof(float) + kOutBytes);
 }
 
 int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
@@ -142,35 +154,155 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
       !a->global_offset || !a->sampled_motion_ids || !a->obs_buf || !a->rew_buf || !a->reward_raw || !a->reset_buf ||
       !a->terminate_buf)
     return PHC_ERR_NULL;
-  // chunk boundaries on multiples of 8 envs (one kernel block) so obs rows stay 16-B friendly
-  int64_t per = (n + c->chunks - 1) / c->chunks;
-  per = (per + 7) / 8 * 8;
-  int ci = 0;
-  for (int64_t lo = 0; lo < n; lo += per, ++ci) {
-    const int64_t m = (n - lo) < per ? (n - lo) : per;
+  {  // ---- direct path: every buffer is mapped host (or device) memory ----------------------
+    const void* ptrs[11] = {a->state, a->progress_buf, a->motion_start_times, a->motion_start_times_offset,
+                            a->global_offset, a->sampled_motion_ids, a->obs_buf, a->rew_buf, a->reward_raw,
+                            a->reset_buf, a->terminate_buf};
+    if (c->seen_direct < 0 || memcmp(ptrs, c->seen, sizeof(ptrs)) != 0) {
+      int direct = getenv("PHC_HOST_STAGED") ? 0 : 1;
+      for (int i = 0; i < 11 && direct; ++i) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess) {
+          (void)cudaGetLastError();
+          direct = 0;
+        } else if (at.type == cudaMemoryTypeUnregistered || at.devicePointer != ptrs[i]) {
+          direct = 0;  // pageable, or mapped at a different device address
+        }
+      }
+      memcpy(c->seen, ptrs, sizeof(ptrs));
+      c->seen_direct = direct;
+    }
+    if (c->seen_direct == 1) {
+      // Hybrid: sim state rides the host->device copy engine in a few chunks (SM-issued reads of
+      // system memory run at ~80 % of DMA rate and, measured, do not overlap SM-issued writes),
+      // while each chunk's kernel reads the tiny clock arrays and WRITES every output straight
+      // into the mapped host buffers.  The copy engine pulling chunk c+1 and the kernel pushing
+      // chunk c's obs rows use opposite directions of the link.
+      const int C = c->chunks < 1 ? 1 : c->chunks;
+      int64_t per = (n + C - 1) / C;
+      per = (per + 7) / 8 * 8;
+      int ci = 0;
+      for (int64_t lo = 0; lo < n; lo += per, ++ci) {
+        const int64_t m = (n - lo) < per ? (n - lo) : per;
+        cudaStream_t s = c->streams[ci % kStreams];
+        float* st = c->d_state + lo * kStateFloats;
+        HOST_CUDA(c, cudaMemcpyAsync(st, a->state + lo * kStateFloats, (size_t)m * kStateFloats * sizeof(float),
+                                     cudaMemcpyHostToDevice, s));
+        PhcStepArgs k{};
+        k.body.pos = PhcView{st, kStateFloats, 13};
+        k.body.rot = PhcView{st + 3, kStateFloats, 13};
+        k.body.vel = PhcView{st + 7, kStateFloats, 13};
+        k.body.ang_vel = PhcView{st + 10, kStateFloats, 13};
+        k.body.num_bodies = PHC_NUM_BODIES;
+        k.progress_buf = a->progress_buf + lo;
+        k.motion_start_times = a->motion_start_times + lo;
+        k.motion_start_times_offset = a->motion_start_times_offset + lo;
+        k.global_offset = a->global_offset + lo * 3;
+        k.sampled_motion_ids = a->sampled_motion_ids + lo;
+        k.termination_distances = c->term_dist;
+        k.reset_body_mask = c->reset_mask;
+        k.use_mean = c->use_mean;
+        k.enable_early_termination = c->early;
+        k.advance_progress = 1;
+        k.time_steps = c->T;
+        k.dt = c->dt;
+        k.rwd = c->rwd;
+        k.obs_buf = a->obs_buf + lo * c->obs_dim;
+        k.obs_stride = c->obs_dim;
+        k.rew_buf = a->rew_buf + lo;
+        k.reward_raw = a->reward_raw + lo * 4;
+        k.reward_raw_stride = 4;
+        k.reset_buf = a->reset_buf + lo;
+        k.terminate_buf = a->terminate_buf + lo;
+        k.flags = PHC_STEP_MAPPED_HOST_IO;
+        k.obs_moments = nullptr;
+        int rc = phc_step_fused(c->lib, &k, m, s);
+        if (rc) return rc;
+      }
+      for (int i = 0; i < kStreams && i < ci; ++i) HOST_CUDA(c, cudaStreamSynchronize(c->streams[i]));
+      return PHC_OK;
+    }
+  }
+  // ---- staged path ---------------------------------------------------------------------------
+  // Chunk sizes double (n/2^(C-1), n/2^(C-1), n/2^(C-2), .., n/2): the device->host direction
+  // carries 3x the bytes and is the bottleneck, so the first chunk is small to start it early
+  // while the later, larger chunks keep the per-transfer overhead low.  Boundaries fall on
+  // multiples of 8 envs so every chunk's obs rows start 16-B aligned.
+  int64_t bounds[1026];
+  int nchunks = 0;
+  {
+    const int C = c->chunks;
+    int64_t lo = 0;
+    bounds[0] = 0;
+    for (int i = 0; i < C && lo < n; ++i) {
+      const int shift = (i == 0) ? C - 1 : C - i;
+      int64_t sz = shift < 62 ? (n >> shift) : 0;
+      sz = (sz + 7) / 8 * 8;
+      if (sz < 8) sz = 8;
+      int64_t hi = (i == C - 1) ? n : (lo + sz < n ? lo + sz : n);
+      bounds[++nchunks] = hi;
+      lo = hi;
+    }
+    bounds[nchunks] = n;
+  }
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+
+  // sub-array offsets inside a chunk's packed regions (each 16-B aligned)
+  struct Layout {
+    size_t ids, goff, start, soff, prog, clock_bytes;
+    size_t rew, raw, oprog, reset, term, out_bytes;
+  };
+  auto layout = [](int64_t m) {
+    Layout L;
+    size_t o = 0;
+    L.ids = o, o = align_up(o + (size_t)m * 8, 16);
+    L.goff = o, o = align_up(o + (size_t)m * 12, 16);
+    L.start = o, o = align_up(o + (size_t)m * 4, 16);
+    L.soff = o, o = align_up(o + (size_t)m * 4, 16);
+    L.prog = o, o = align_up(o + (size_t)m * 2, 16);
+    L.clock_bytes = o;
+    o = 0;
+    L.rew = o, o = align_up(o + (size_t)m * 4, 16);
+    L.raw = o, o = align_up(o + (size_t)m * 16, 16);
+    L.oprog = o, o = align_up(o + (size_t)m * 2, 16);
+    L.reset = o, o = align_up(o + (size_t)m, 16);
+    L.term = o, o = align_up(o + (size_t)m, 16);
+    L.out_bytes = o;
+    return L;
+  };
+
+  size_t coff = 0, ooff = 0;
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const int64_t lo = bounds[ci], m = bounds[ci + 1] - bounds[ci];
+    if (m <= 0) continue;
+    const Layout L = layout(m);
+    if (coff + L.clock_bytes > c->pack_capacity || ooff + L.out_bytes > c->pack_capacity) return PHC_ERR_SHAPE;
     cudaStream_t s = c->streams[ci % kStreams];
-    const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
-    HOST_CUDA(c, cudaMemcpyAsync(c->d.state + lo * kStateFloats, a->state + lo * kStateFloats,
+    // pack the chunk's clock on the host (tens of KB), then ONE transfer
+    unsigned char* hc = c->h_clock + coff;
+    memcpy(hc + L.ids, a->sampled_motion_ids + lo, (size_t)m * 8);
+    memcpy(hc + L.goff, a->global_offset + lo * 3, (size_t)m * 12);
+    memcpy(hc + L.start, a->motion_start_times + lo, (size_t)m * 4);
+    memcpy(hc + L.soff, a->motion_start_times_offset + lo, (size_t)m * 4);
+    memcpy(hc + L.prog, a->progress_buf + lo, (size_t)m * 2);
+    unsigned char* dc = c->d_clock + coff;
+    unsigned char* dout = c->d_out + ooff;
+    HOST_CUDA(c, cudaMemcpyAsync(c->d_state + lo * kStateFloats, a->state + lo * kStateFloats,
                                  (size_t)m * kStateFloats * sizeof(float), H2D, s));
-    HOST_CUDA(c, cudaMemcpyAsync(c->d.progress + lo, a->progress_buf + lo, (size_t)m * sizeof(int16_t), H2D, s));
-    HOST_CUDA(c, cudaMemcpyAsync(c->d.start + lo, a->motion_start_times + lo, (size_t)m * sizeof(float), H2D, s));
-    HOST_CUDA(c, cudaMemcpyAsync(c->d.start_off + lo, a->motion_start_times_offset + lo, (size_t)m * sizeof(float),
-                                 H2D, s));
-    HOST_CUDA(c, cudaMemcpyAsync(c->d.goff + lo * 3, a->global_offset + lo * 3, (size_t)m * 3 * sizeof(float), H2D, s));
-    HOST_CUDA(c, cudaMemcpyAsync(c->d.ids + lo, a->sampled_motion_ids + lo, (size_t)m * sizeof(int64_t), H2D, s));
+    HOST_CUDA(c, cudaMemcpyAsync(dc, hc, L.clock_bytes, H2D, s));
 
     PhcStepArgs k{};
-    float* st = c->d.state + lo * kStateFloats;
+    float* st = c->d_state + lo * kStateFloats;
     k.body.pos = PhcView{st, kStateFloats, 13};
     k.body.rot = PhcView{st + 3, kStateFloats, 13};
     k.body.vel = PhcView{st + 7, kStateFloats, 13};
     k.body.ang_vel = PhcView{st + 10, kStateFloats, 13};
     k.body.num_bodies = PHC_NUM_BODIES;
-    k.progress_buf = c->d.progress + lo;
-    k.motion_start_times = c->d.start + lo;
-    k.motion_start_times_offset = c->d.start_off + lo;
-    k.global_offset = c->d.goff + lo * 3;
-    k.sampled_motion_ids = c->d.ids + lo;
+    k.progress_buf = (int16_t*)(dc + L.prog);
+    k.motion_start_times = (const float*)(dc + L.start);
+    k.motion_start_times_offset = (const float*)(dc + L.soff);
+    k.global_offset = (const float*)(dc + L.goff);
+    k.sampled_motion_ids = (const int64_t*)(dc + L.ids);
     k.termination_distances = c->term_dist;
     k.reset_body_mask = c->reset_mask;
     k.use_mean = c->use_mean;
@@ -179,26 +311,39 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
     k.time_steps = c->T;
     k.dt = c->dt;
     k.rwd = c->rwd;
-    k.obs_buf = c->d.obs + lo * c->obs_dim;
+    k.obs_buf = c->d_obs + lo * c->obs_dim;
     k.obs_stride = c->obs_dim;
-    k.rew_buf = c->d.rew + lo;
-    k.reward_raw = c->d.raw + lo * 4;
+    k.rew_buf = (float*)(dout + L.rew);
+    k.reward_raw = (float*)(dout + L.raw);
     k.reward_raw_stride = 4;
-    k.reset_buf = c->d.reset + lo;
-    k.terminate_buf = c->d.term + lo;
+    k.reset_buf = dout + L.reset;
+    k.terminate_buf = dout + L.term;
     k.obs_moments = nullptr;
     int rc = phc_step_fused(c->lib, &k, m, s);
     if (rc) return rc;
-
-    HOST_CUDA(c, cudaMemcpyAsync(a->obs_buf + lo * c->obs_dim, c->d.obs + lo * c->obs_dim,
+    // the advanced progress rides back with the scalar outputs
+    HOST_CUDA(c, cudaMemcpyAsync(dout + L.oprog, dc + L.prog, (size_t)m * 2, cudaMemcpyDeviceToDevice, s));
+    HOST_CUDA(c, cudaMemcpyAsync(a->obs_buf + lo * c->obs_dim, c->d_obs + lo * c->obs_dim,
                                  (size_t)m * c->obs_dim * sizeof(float), D2H, s));
-    HOST_CUDA(c, cudaMemcpyAsync(a->rew_buf + lo, c->d.rew + lo, (size_t)m * sizeof(float), D2H, s));
-    HOST_CUDA(c, cudaMemcpyAsync(a->reward_raw + lo * 4, c->d.raw + lo * 4, (size_t)m * 4 * sizeof(float), D2H, s));
-    HOST_CUDA(c, cudaMemcpyAsync(a->reset_buf + lo, c->d.reset + lo, (size_t)m, D2H, s));
-    HOST_CUDA(c, cudaMemcpyAsync(a->terminate_buf + lo, c->d.term + lo, (size_t)m, D2H, s));
-    HOST_CUDA(c, cudaMemcpyAsync(a->progress_buf + lo, c->d.progress + lo, (size_t)m * sizeof(int16_t), D2H, s));
+    HOST_CUDA(c, cudaMemcpyAsync(c->h_out + ooff, dout, L.out_bytes, D2H, s));
+    coff += L.clock_bytes;
+    ooff += L.out_bytes;
   }
   for (int i = 0; i < kStreams; ++i) HOST_CUDA(c, cudaStreamSynchronize(c->streams[i]));
+  // unpack the scalar outputs
+  ooff = 0;
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const int64_t lo = bounds[ci], m = bounds[ci + 1] - bounds[ci];
+    if (m <= 0) continue;
+    const Layout L = layout(m);
+    const unsigned char* ho = c->h_out + ooff;
+    memcpy(a->rew_buf + lo, ho + L.rew, (size_t)m * 4);
+    memcpy(a->reward_raw + lo * 4, ho + L.raw, (size_t)m * 16);
+    memcpy(a->progress_buf + lo, ho + L.oprog, (size_t)m * 2);
+    memcpy(a->reset_buf + lo, ho + L.reset, (size_t)m);
+    memcpy(a->terminate_buf + lo, ho + L.term, (size_t)m);
+    ooff += L.out_bytes;
+  }
   return PHC_OK;
 }
 

@@ -1522,7 +1522,7 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
                                                              sizeof(FastSmem<4>)));
       first_wave[dev] = sms * (per_sm > 0 ? per_sm : 1);
     }
-    p.first_wave_blocks = g_pdl ? first_wave[dev] : 0;
+    p.first_wave_blocks = (g_pdl && !(args->flags & PHC_STEP_MAPPED_HOST_IO)) ? first_wave[dev] : 0;
     return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev], g_pdl != 0);
   }
   return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev], false);

@@ -185,6 +185,8 @@ PHC_API int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_
  *   t+dt .. t+T*dt (:1050-1123), written as one row of obs_buf.
  * One kernel; no host reads; graph-capturable.
  * ---------------------------------------------------------------------------------- */
+#define PHC_STEP_MAPPED_HOST_IO 1u /* sim state / clock / outputs are pinned host memory mapped into the
+                                      device address space: no L2 prefetch, no pre-dependency speculation */
 typedef struct PhcStepArgs {
   PhcBodyState body;                     /* sim state views, J must be 24               */
   int16_t* progress_buf;                 /* [n] in/out                  humanoid_phc.py:571 */
@@ -207,6 +209,7 @@ typedef struct PhcStepArgs {
   int64_t reward_raw_stride;
   uint8_t* reset_buf;                    /* [n] bool                    humanoid_phc.py:573 */
   uint8_t* terminate_buf;                /* [n] bool                    humanoid_phc.py:575 */
+  uint32_t flags;                        /* PHC_STEP_* bits, 0 by default                */
   double* obs_moments;                   /* NULL, or [2*(358+576*T)] fp64: per-column sum
                                             and sum of squares accumulated (+=) for
                                             RunningNorm.update           running_norm.py:23 */

@@ -493,7 +493,10 @@ def test_running_norm_vs_reference_fixture(golden):
     assert_close(rn(cuda(g.inp("x2")[:32])), g.out("fwd"), what="forward", rtol=1e-5, atol=1e-5)
 
 
-def test_host_pipeline_matches_device_path():
+@pytest.mark.parametrize("pinned", [True, False], ids=["pinned_direct", "pageable_staged"])
+def test_host_pipeline_matches_device_path(pinned):
+    """phc_host_step on host buffers == the device path, bit for bit.  Pinned buffers take the
+    direct path (the kernel works on the mapped host memory), pageable ones the staged copies."""
     import ctypes as C
 
     from humanoid_b200 import HumanoidPHC, _cabi
@@ -511,11 +514,13 @@ def test_host_pipeline_matches_device_path():
     spec = _cabi.reward_spec(env.rwd_specs)
     _cabi.check(capi.phc_host_step_create(lib.handle, N, 1, 3, term, 0xFFFFFF, 0, 1, synth.SIM_DT, C.byref(spec),
                                           C.byref(ctx)), "create")  # fmt: skip
+    mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
     h = dict(
-        state=state.cpu().contiguous(), prog=clock.progress_buf.cpu().clone(), start=clock.motion_start_times.cpu(),
-        off=clock.motion_start_times_offset.cpu(), goff=clock.global_offset.cpu().contiguous(),
-        ids=clock.sampled_motion_ids.cpu(), obs=torch.empty(N, 934), rew=torch.empty(N), raw=torch.empty(N, 4),
-        reset=torch.empty(N, dtype=torch.uint8), term=torch.empty(N, dtype=torch.uint8),
+        state=mk(state.cpu().contiguous()), prog=mk(clock.progress_buf.cpu().clone()),
+        start=mk(clock.motion_start_times.cpu()), off=mk(clock.motion_start_times_offset.cpu()),
+        goff=mk(clock.global_offset.cpu().contiguous()), ids=mk(clock.sampled_motion_ids.cpu()),
+        obs=mk(torch.empty(N, 934)), rew=mk(torch.empty(N)), raw=mk(torch.empty(N, 4)),
+        reset=mk(torch.empty(N, dtype=torch.uint8)), term=mk(torch.empty(N, dtype=torch.uint8)),
     )  # fmt: skip
     args = _cabi.PhcHostStepArgs(*[h[k].data_ptr() for k in ("state", "prog", "start", "off", "goff", "ids", "obs",
                                                              "rew", "raw", "reset", "term")])  # fmt: skip

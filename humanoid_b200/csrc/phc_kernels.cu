@@ -1136,23 +1136,54 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
 // ---------------------------------------------------------------------------------------
 // RunningNorm kernels (policies/running_norm.py:15-34)
 // ---------------------------------------------------------------------------------------
-constexpr int MOM_ROWS_PER_BLOCK = 256;
+constexpr int MOM_ROWS_PER_BLOCK = 32;
 
+// grid (ceil(cols / (128*VEC)), ceil(rows / 32)); a thread owns VEC adjacent columns (coalesced
+// across the warp) and walks 32 rows with 8 independent loads in flight; fp64 partials are merged
+// with one atomicAdd per column per block.
+template <int VEC>
 __global__ void obs_moments_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t stride,
                                    double* __restrict__ sums) {
-  // grid (ceil(cols/128), ceil(rows/256)); thread = one column, coalesced across the warp
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   const int64_t r0 = (int64_t)blockIdx.y * MOM_ROWS_PER_BLOCK;
   if (c >= cols) return;
   const int64_t r1 = r0 + MOM_ROWS_PER_BLOCK < rows ? r0 + MOM_ROWS_PER_BLOCK : rows;
-  double s1 = 0.0, s2 = 0.0;
-  for (int64_t r = r0; r < r1; ++r) {
-    const double v = (double)x[r * stride + c];
-    s1 += v;
-    s2 += v * v;
+  double s1[VEC], s2[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) s1[v] = s2[v] = 0.0;
+  for (int64_t r = r0; r < r1; r += 8) {
+    float vals[8][VEC];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (r + u < r1) {
+        const float* p = x + (r + u) * stride + c;
+        if (VEC == 2) {
+          const float2 t = *reinterpret_cast<const float2*>(p);
+          vals[u][0] = t.x;
+          vals[u][VEC - 1] = t.y;
+        } else {
+          vals[u][0] = *p;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) vals[u][v] = 0.0f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const double d = (double)vals[u][v];
+        s1[v] += d;
+        s2[v] += d * d;
+      }
   }
-  atomicAdd(sums + c, s1);
-  atomicAdd(sums + cols + c, s2);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+    if (c + v < cols) {
+      atomicAdd(sums + c + v, s1[v]);
+      atomicAdd(sums + cols + c + v, s2[v]);
+    }
 }
 
 __global__ void running_norm_update_kernel(float* __restrict__ mean, float* __restrict__ var,
@@ -1534,8 +1565,16 @@ int phc_obs_moments(const float* x, int64_t rows, int64_t cols, int64_t row_stri
   if (rows == 0 || cols == 0) return PHC_OK;
   if (rows < 0 || cols < 0 || row_stride < cols) return PHC_ERR_SHAPE;
   if (!x || !sums) return PHC_ERR_NULL;
-  dim3 grid((unsigned)((cols + 127) / 128), (unsigned)((rows + MOM_ROWS_PER_BLOCK - 1) / MOM_ROWS_PER_BLOCK));
-  obs_moments_kernel<<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, sums);
+  const unsigned gy = (unsigned)((rows + MOM_ROWS_PER_BLOCK - 1) / MOM_ROWS_PER_BLOCK);
+  if (gy > 65535u) return PHC_ERR_SHAPE;
+  const bool vec2 = (cols % 2 == 0) && (row_stride % 2 == 0) && (((uintptr_t)x & 7) == 0);
+  if (vec2) {
+    dim3 grid((unsigned)((cols / 2 + 127) / 128), gy);
+    obs_moments_kernel<2><<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, sums);
+  } else {
+    dim3 grid((unsigned)((cols + 127) / 128), gy);
+    obs_moments_kernel<1><<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, sums);
+  }
   return launch_status();
 }
 

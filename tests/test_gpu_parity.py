@@ -596,3 +596,65 @@ def test_env_reset_between_steps_is_seen_by_the_next_step():
     assert_equal_exact(env._terminate_buf, want[4], "terminated")
     assert_close(env.obs_buf, want[0], what="obs after reset", **OBS_TOL)
     assert_close(env.rew_buf, want[1], what="reward after reset", **OBS_TOL)
+
+
+def test_amass_scale_library_random_queries():
+    """BASELINE config 4 at scale: ~0.6 M frames, mixed fps, long clips, random ids and unaligned
+    times.  Size-independent checks: fused == per-function kernels bitwise, frame indices in range,
+    and a 512-env sample against the oracle (which only gathers the frames it needs)."""
+    from humanoid_b200 import HumanoidPHC
+
+    M, N = 1500, 32768
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    nf = torch.randint(60, 760, (M,), generator=gen, device=DEV)
+    nf[:8] = 7000  # a few very long clips
+    lib_data = synth.make_motion_lib(M, fps_choices=(30, 60, 120), seed=301, device=DEV, frames_per_motion=nf)
+    assert lib_data.total_frames > 600_000
+    lib = MotionLib(lib_data, device=DEV)
+    clock = synth.make_clock(lib_data, N, seed=302, ids="random", aligned=False, max_progress=60)
+    t = synth.reward_time(clock, extra_steps=1)
+    ref = lib.get_motion_state(clock.sampled_motion_ids, t, clock.global_offset, with_frame_info=True)
+    assert int(ref["frame_idx0"].min()) >= 0
+    assert bool((ref["frame_idx1"] < lib_data.motion_num_frames[clock.sampled_motion_ids]).all())
+    assert bool((ref["frame_idx1"] - ref["frame_idx0"]).clamp(0, 1).eq(ref["frame_idx1"] - ref["frame_idx0"]).all())
+    state = synth.make_sim_state(ref, seed=303)
+    a, b = HumanoidPHC(lib, N, device=DEV), HumanoidPHC(lib, N, device=DEV)
+    for env in (a, b):
+        env.set_sim_state(state)
+        env.set_clock(clock)
+    a.step()
+    b.post_physics_step_unfused()
+    assert torch.equal(a.obs_buf, b.obs_buf) and torch.equal(a.rew_buf, b.rew_buf)
+    assert torch.equal(a.reset_buf, b.reset_buf) and torch.equal(a._terminate_buf, b._terminate_buf)
+    # oracle on a sample of envs: CPU copies of only the four frame tensors the step reads
+    sel = torch.randperm(N, generator=torch.Generator().manual_seed(1))[:512]
+    cpu = {k: (v.cpu() if k in ("gts", "grs", "gvs", "gavs") or v.dim() < 2 or v.shape[0] == M else v[:1].cpu())
+           for k, v in lib_data.as_dict().items()}  # fmt: skip
+    ol = O.OracleMotionLib(cpu)
+    ol.lrs, ol.dvs, ol._motion_aa = cpu["grs"], cpu["gvs"][:, :23], torch.zeros(lib_data.total_frames, 1)
+    c = synth.Clock(**{k: v.cpu()[sel] for k, v in clock.__dict__.items()})
+    prog = c.progress_buf.clone()
+    want = O.step(ol, state.cpu()[sel], prog, c.motion_start_times, c.motion_start_times_offset, c.global_offset,
+                  c.sampled_motion_ids, torch.full((24,), 0.25), synth.SIM_DT)  # fmt: skip
+    sel_d = sel.to(DEV)
+    assert_equal_exact(a.reset_buf[sel_d], want[3], "reset")
+    assert_equal_exact(a._terminate_buf[sel_d], want[4], "terminated")
+    assert_close(a.obs_buf[sel_d], want[0], what="obs (AMASS-scale sample)", **OBS_TOL)
+    assert_close(a.rew_buf[sel_d], want[1], what="reward (AMASS-scale sample)", **OBS_TOL)
+
+
+def test_config5_T10_fused_equals_per_function_at_16384():
+    from humanoid_b200 import HumanoidPHC
+
+    N = 16384
+    lib_data, clock, state = _gpu_case(N, 1024, 304, max_frames=120, max_progress=40)
+    lib = MotionLib(lib_data, device=DEV)
+    a, b = HumanoidPHC(lib, N, device=DEV, time_steps=10), HumanoidPHC(lib, N, device=DEV, time_steps=10)
+    for env in (a, b):
+        env.set_sim_state(state)
+        env.set_clock(clock)
+    a.step()
+    b.post_physics_step_unfused()
+    assert a.obs_buf.shape == (N, 358 + 5760)
+    assert torch.equal(a.obs_buf, b.obs_buf) and torch.equal(a.rew_buf, b.rew_buf)
+    assert torch.equal(a.reset_buf, b.reset_buf) and torch.equal(a._terminate_buf, b._terminate_buf)

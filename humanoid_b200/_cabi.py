@@ -95,6 +95,13 @@ class PhcStepArgs(C.Structure):
         ("reset_buf", C.c_void_p),
         ("terminate_buf", C.c_void_p),
         ("flags", C.c_uint32),
+        ("dof_force", C.c_void_p),
+        ("dof_force_stride", C.c_int64),
+        ("dof_vel", C.c_void_p),
+        ("dof_vel_stride", C.c_int64),
+        ("dof_vel_elem_stride", C.c_int64),
+        ("rew_power_coef", C.c_float),
+        ("power_col", C.c_int32),
         ("obs_moments", C.c_void_p),
     ]
 

@@ -474,6 +474,12 @@ struct StepParams {
   uint8_t* reset;
   uint8_t* term;
   double* moments;
+  const float* dof_force;  // power reward inputs (NULL = off)
+  int64_t dof_force_stride;
+  const float* dof_vel;
+  int64_t dof_vel_stride, dof_vel_estride;
+  float power_coef;
+  int power_col;
   int64_t n;
   int first_wave_blocks;      // blocks that can be resident at once (speculate before the dependency wait)
   int spec_fault;             // test hook: perturb the speculated clock (PHC_OPT_TEST_SPEC_FAULT)
@@ -482,13 +488,28 @@ struct StepParams {
   int obs_vec2;   // obs rows can be written with 8-byte stores
 };
 
+// per-body share of power = sum_dof |dof_force * dof_vel| (humanoid_phc.py:1298): body b >= 1 owns
+// the 3 dofs of joint b - 1
+__device__ __forceinline__ float power_partial(const StepParams& p, int64_t env, int b) {
+  if (b == 0) return 0.0f;
+  const float* f = p.dof_force + env * p.dof_force_stride + (b - 1) * 3;
+  const float* v = p.dof_vel + env * p.dof_vel_stride + (int64_t)(b - 1) * 3 * p.dof_vel_estride;
+  return (fabsf(__ldcg(f) * __ldcg(v)) + fabsf(__ldcg(f + 1) * __ldcg(v + p.dof_vel_estride))) +
+         fabsf(__ldcg(f + 2) * __ldcg(v + 2 * p.dof_vel_estride));
+}
+// r = -coef * power, zeroed while progress <= 3 (humanoid_phc.py:1300-1302)
+__device__ __forceinline__ float power_reward(const StepParams& p, const float* row24, int prog) {
+  const float r = (-p.power_coef) * row_sum24(row24);
+  return prog <= 3 ? 0.0f : r;
+}
+
 template <int EPB>
 struct StepSmem {
   static constexpr int NT = EPB * J24;
   static constexpr int BUF = EPB * (STAGE_FLOATS > 2 * FRAME_FLOATS ? STAGE_FLOATS : 2 * FRAME_FLOATS);
   float sim[EPB * ROW13];
   float buf[BUF];             // frames [EPB][2][312]  /  obs stage [EPB][934]
-  float part[5][EPB][J24];    // reward partials x4, distance
+  float part[6][EPB][J24];    // reward partials x4, distance, power
   float terms[EPB][4];
   float goff[EPB][4];
   float hz[EPB], hw[EPB];
@@ -633,6 +654,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
     S.part[2][e][b] = sv;
     S.part[3][e][b] = sa;
     S.part[4][e][b] = norm3(pos - r.pos);  // torch.norm(rigid_body_pos - ref_body_pos), common.py:343/348
+    if (p.dof_force) S.part[5][e][b] = power_partial(p, env, b);
     if (b == 0) {
       const Heading hi = heading_quat_inv(rot);  // upright: root_rot used as is (common.py:42-44)
       S.hz[e] = hi.z;
@@ -674,7 +696,13 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
   __syncwarp();
   if (valid && b == 0) {
     const float* t = S.terms[e];
-    p.rew[env] = p.rwd.w_pos * t[0] + p.rwd.w_rot * t[1] + p.rwd.w_vel * t[2] + p.rwd.w_ang_vel * t[3];
+    float r = p.rwd.w_pos * t[0] + p.rwd.w_rot * t[1] + p.rwd.w_vel * t[2] + p.rwd.w_ang_vel * t[3];
+    if (p.dof_force) {
+      const float pr = power_reward(p, &S.part[5][e][0], S.prog[e]);
+      r += pr;  // rew_buf[:] += power_reward (humanoid_phc.py:1304)
+      p.raw[env * p.raw_stride + p.power_col] = pr;
+    }
+    p.rew[env] = r;
   }
 
   // ---- phase 2: observations -------------------------------------------------------------
@@ -778,7 +806,7 @@ template <int EPB>
 struct FastSmem {
   float sim[EPB * ROW13];
   float frames[EPB * 4 * FRAME_FLOATS];  // [env][slot 0..3][312]; later the obs stage [env][934]
-  float part[5][EPB][J24];
+  float part[6][EPB][J24];  // reward partials x4, distance, power
   unsigned long long bar;
   float bl[2][EPB];
   int slot[2][2][EPB];
@@ -1034,6 +1062,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       const float dist = norm3(pos - r0.pos);  // torch.norm(rigid_body_pos - ref_body_pos), common.py:343/348
       S.part[4][e][b] = dist;
       if (!p.use_mean && (p.reset_mask >> b & 1u) && dist > p.term_dist[b]) S.fallen[e] = 1;  // any(), benign race
+      if (p.dof_force) S.part[5][e][b] = power_partial(p, env0 + e, b);
     }
     r1 = blend_ref2(fr + S.slot[1][0][e] * FRAME_FLOATS, fr + S.slot[1][1][e] * FRAME_FLOATS, S.bl[1][e], S.goff[e], b);
   }
@@ -1106,8 +1135,15 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     const int base = tid & ~3;
     const float t0 = __shfl_sync(0xffffffffu, term_k, base), t1 = __shfl_sync(0xffffffffu, term_k, base + 1);
     const float t2 = __shfl_sync(0xffffffffu, term_k, base + 2), t3 = __shfl_sync(0xffffffffu, term_k, base + 3);
-    if (act && k == 0)
-      p.rew[env0 + le] = p.rwd.w_pos * t0 + p.rwd.w_rot * t1 + p.rwd.w_vel * t2 + p.rwd.w_ang_vel * t3;
+    if (act && k == 0) {
+      float r = p.rwd.w_pos * t0 + p.rwd.w_rot * t1 + p.rwd.w_vel * t2 + p.rwd.w_ang_vel * t3;
+      if (p.dof_force) {
+        const float pr = power_reward(p, &S.part[5][le][0], S.prog[le]);
+        r += pr;  // rew_buf[:] += power_reward (humanoid_phc.py:1304)
+        p.raw[(env0 + le) * p.raw_stride + p.power_col] = pr;
+      }
+      p.rew[env0 + le] = r;
+    }
     if (act && k == 1) {
       bool fallen = false;
       if (p.early) {
@@ -1458,6 +1494,19 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.reset = a->reset_buf;
   p.term = a->terminate_buf;
   p.moments = a->obs_moments;
+  p.dof_force = a->dof_force;
+  p.dof_force_stride = a->dof_force_stride;
+  p.dof_vel = a->dof_vel;
+  p.dof_vel_stride = a->dof_vel_stride;
+  p.dof_vel_estride = a->dof_vel_elem_stride;
+  p.power_coef = a->rew_power_coef;
+  p.power_col = a->power_col;
+  if (a->dof_force) {
+    if (!a->dof_vel) return PHC_ERR_NULL;
+    if (a->power_col < 4 || a->power_col >= a->reward_raw_stride || a->dof_force_stride < 69 ||
+        a->dof_vel_elem_stride < 1)
+      return PHC_ERR_SHAPE;
+  }
   p.first_wave_blocks = 0;
   p.spec_fault = g_spec_fault;
   {  // profiling only: consecutive launches stamp consecutive slices of the trace buffer

@@ -64,6 +64,8 @@ class HumanoidPHC:
         dt: float = 2 * (1.0 / 60.0),  # isaacgym_env.py:39-41
         rwd_specs: Optional[Dict[str, float]] = None,
         obs_moments: bool = False,
+        use_power_reward: bool = False,  # config.py:50 (True in the reference; needs dof_force / dof_vel)
+        rew_power_coef: float = 0.0005,  # config.py:112
     ):
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -79,11 +81,20 @@ class HumanoidPHC:
         self.enable_early_termination = enable_early_termination
         self.flag_im_eval = False
         self._rwd_specs = dict(rwd_specs or DEFAULT_REWARD)
+        self.use_power_reward = bool(use_power_reward)
+        self.rew_power_coef = float(rew_power_coef)
+        self.num_dof = 69
 
         N = num_envs
         # sim tensors (stand-in for the gymtorch-wrapped PhysX buffer, humanoid_phc.py:542-549)
         self._rigid_body_state_reshaped = torch.zeros((N, bodies_per_env, 13), dtype=torch.float32, device=dev)
         self._bind_body_views()
+
+        # dof state / force tensors (humanoid_phc.py:504-506, 533-536): (pos, vel) interleaved per dof
+        self._dof_state = torch.zeros((N * self.num_dof, 2), dtype=torch.float32, device=dev)
+        self._dof_pos = self._dof_state.view(N, self.num_dof, 2)[..., : self.num_dof, 0]
+        self._dof_vel = self._dof_state.view(N, self.num_dof, 2)[..., : self.num_dof, 1]
+        self.dof_force_tensor = torch.zeros((N, self.num_dof), dtype=torch.float32, device=dev)
 
         # env buffers (humanoid_phc.py:556-597)
         self.num_obs = _cabi.SELF_OBS_DIM + _cabi.TASK_OBS_DIM * self.time_steps  # :461-467
@@ -208,6 +219,14 @@ class HumanoidPHC:
         a.reset_buf = self.reset_buf.data_ptr()
         a.terminate_buf = self._terminate_buf.data_ptr()
         a.obs_moments = self.obs_moments.data_ptr() if self.obs_moments is not None else None
+        if self.use_power_reward:  # humanoid_phc.py:1297-1305
+            a.dof_force = self.dof_force_tensor.data_ptr()
+            a.dof_force_stride = self.dof_force_tensor.stride(0)
+            a.dof_vel = self._dof_vel.data_ptr()
+            a.dof_vel_stride = self._dof_vel.stride(0)
+            a.dof_vel_elem_stride = self._dof_vel.stride(1)
+            a.rew_power_coef = self.rew_power_coef
+            a.power_col = self.reward_raw.shape[1] - 1
         self._step_args = (a, advance, keep)
         return a
 
@@ -250,6 +269,12 @@ class HumanoidPHC:
             pos[..., 0, :], rot[..., 0, :], pos, rot, vel, ang,
             ref["rg_pos"], ref["rb_rot"], ref["body_vel"], ref["body_ang_vel"], self.rwd_specs,
         )  # fmt: skip
+        if self.use_power_reward:  # :1297-1305 — plain torch ops; the fused step does this in-kernel
+            power = torch.abs(torch.multiply(self.dof_force_tensor, self._dof_vel)).sum(dim=-1)
+            power_reward = -self.rew_power_coef * power
+            power_reward[self.progress_buf <= 3] = 0
+            self.rew_buf[:] += power_reward
+            self.reward_raw[:, -1] = power_reward
 
     def _compute_reset(self):  # :1313-1335
         t = self._motion_times()

@@ -210,6 +210,16 @@ typedef struct PhcStepArgs {
   uint8_t* reset_buf;                    /* [n] bool                    humanoid_phc.py:573 */
   uint8_t* terminate_buf;                /* [n] bool                    humanoid_phc.py:575 */
   uint32_t flags;                        /* PHC_STEP_* bits, 0 by default                */
+  /* power reward (humanoid_phc.py:1297-1305), off when dof_force is NULL:
+   *   power = sum_dof |dof_force * dof_vel|; r = -rew_power_coef * power, 0 while progress <= 3;
+   *   rew_buf += r; reward_raw[:, power_col] = r                                           */
+  const float* dof_force;                /* NULL or [n, 69]             humanoid_phc.py:506  */
+  int64_t dof_force_stride;
+  const float* dof_vel;                  /* [n, 69] view of the dof state humanoid_phc.py:536 */
+  int64_t dof_vel_stride;                /* row stride in elements                           */
+  int64_t dof_vel_elem_stride;           /* 2 for the reference's (pos, vel) interleaved state */
+  float rew_power_coef;                  /* config.py rew_power_coef                          */
+  int32_t power_col;                     /* column of reward_raw that receives r (4)          */
   double* obs_moments;                   /* NULL, or [2*(358+576*T)] fp64: per-column sum
                                             and sum of squares accumulated (+=) for
                                             RunningNorm.update           running_norm.py:23 */

@@ -439,6 +439,9 @@ def step(
     rwd_specs: Optional[Dict[str, float]] = None,
     time_steps: int = 1,
     num_bodies: int = 24,
+    dof_force: Optional[Tensor] = None,
+    dof_vel: Optional[Tensor] = None,
+    rew_power_coef: float = 0.0005,
 ):
     """post-physics half of HumanoidPHC.step (humanoid_phc.py:138-149):
     progress += 1; _compute_reward (:1230-1271); _compute_reset (:1313-1335);
@@ -466,6 +469,14 @@ def step(
         pos[:, 0], rot[:, 0], pos, rot, vel, ang,
         ref["rg_pos"], ref["rb_rot"], ref["body_vel"], ref["body_ang_vel"], rwd_specs,
     )  # fmt: skip
+
+    power_reward = None
+    if dof_force is not None:  # use_power_reward (:1297-1305)
+        power = torch.abs(torch.multiply(dof_force, dof_vel)).sum(dim=-1)
+        power_reward = -rew_power_coef * power
+        power_reward[progress_buf <= 3] = 0
+        reward = reward + power_reward
+        raw = torch.cat([raw, power_reward[:, None]], dim=-1)  # reward_raw[:, -1] = power_reward
 
     # reset (:1313-1335); quirk: the reference compares against the un-indexed lengths,
     # valid because ids == arange(N); length[id] is the same thing there.

@@ -658,3 +658,29 @@ def test_config5_T10_fused_equals_per_function_at_16384():
     assert a.obs_buf.shape == (N, 358 + 5760)
     assert torch.equal(a.obs_buf, b.obs_buf) and torch.equal(a.rew_buf, b.rew_buf)
     assert torch.equal(a.reset_buf, b.reset_buf) and torch.equal(a._terminate_buf, b._terminate_buf)
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "per_function"])
+def test_power_reward_vs_oracle(fused):
+    """use_power_reward (humanoid_phc.py:1297-1305): -coef * sum |dof_force * dof_vel|, zero while
+    progress <= 3, added to rew_buf and stored in reward_raw[:, -1]; dof_vel is the stride-2 view."""
+    lib_data, clock, state = make_case_cpu(num_envs=1500, num_motions=48, seed=112, max_progress=12)
+    gen = torch.Generator().manual_seed(4)
+    force = torch.randn(1500, 69, generator=gen) * 40
+    dvel = torch.randn(1500, 69, generator=gen) * 3
+    prog = clock.progress_buf.clone()
+    want = O.step(O.OracleMotionLib(lib_data), state, prog, clock.motion_start_times, clock.motion_start_times_offset,
+                  clock.global_offset, clock.sampled_motion_ids, torch.full((24,), 0.25), synth.SIM_DT,
+                  dof_force=force, dof_vel=dvel, rew_power_coef=0.0005)  # fmt: skip
+    env = env_from(lib_data, clock, state, use_power_reward=True)
+    env.dof_force_tensor.copy_(force)
+    env._dof_vel.copy_(dvel)
+    assert env._dof_vel.stride(1) == 2
+    if fused:
+        env.step()
+    else:
+        env.post_physics_step_unfused()
+    assert (prog <= 3).any() and (prog > 3).any()
+    assert_close(env.rew_buf, want[1], what="reward incl. power", **OBS_TOL)
+    assert_close(env.reward_raw, want[2], what="reward_raw incl. power column", **OBS_TOL)
+    assert float(env.reward_raw[:, 4].cpu()[prog <= 3].abs().max()) == 0.0

@@ -27,6 +27,9 @@ OPT_STEP_EPB = 2
 OPT_STEP_PDL = 3
 OPT_TEST_SPEC_FAULT = 4
 
+STATE_INIT_START = 0
+STATE_INIT_RANDOM = 1
+
 OBS_LOCAL_ROOT = 1
 OBS_ROOT_HEIGHT = 2
 OBS_UPRIGHT = 4
@@ -106,6 +109,33 @@ class PhcStepArgs(C.Structure):
     ]
 
 
+class PhcResetArgs(C.Structure):
+    _fields_ = [
+        ("body", PhcBodyState),
+        ("humanoid_root_states", C.c_void_p),
+        ("root_stride", C.c_int64),
+        ("dof_pos", C.c_void_p),
+        ("dof_vel", C.c_void_p),
+        ("dof_stride", C.c_int64),
+        ("dof_elem_stride", C.c_int64),
+        ("progress_buf", C.c_void_p),
+        ("reset_buf", C.c_void_p),
+        ("terminate_buf", C.c_void_p),
+        ("motion_start_times", C.c_void_p),
+        ("motion_start_times_offset", C.c_void_p),
+        ("global_offset", C.c_void_p),
+        ("sampled_motion_ids", C.c_void_p),
+        ("env_mask", C.c_void_p),
+        ("phase", C.c_void_p),
+        ("state_init", C.c_int32),
+        ("flag_test", C.c_int32),
+        ("time_steps", C.c_int32),
+        ("dt", C.c_float),
+        ("obs_buf", C.c_void_p),
+        ("obs_stride", C.c_int64),
+    ]
+
+
 class PhcHostStepArgs(C.Structure):
     _fields_ = [
         (k, C.c_void_p)
@@ -152,6 +182,7 @@ SIGNATURES = {
          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),  # fmt: skip
     "phc_step_fused": (C.c_int, [C.c_void_p, C.POINTER(PhcStepArgs), C.c_int64, C.c_void_p]),
+    "phc_reset_envs": (C.c_int, [C.c_void_p, C.POINTER(PhcResetArgs), C.c_int64, C.c_void_p]),
     "phc_set_option": (C.c_int, [C.c_int, C.c_int]),
     "phc_set_trace_buffer": (C.c_int, [C.c_void_p, C.c_int64]),
     "phc_host_step_create": (

@@ -439,6 +439,108 @@ __global__ void reset_kernel(PhcView pos, PhcView ref, int R, const int16_t* __r
 }
 
 // ---------------------------------------------------------------------------------------
+// K7: reference-state-init reset of the envs selected by a mask (humanoid_phc.py:665-778).
+// One thread per (env, body).  _sample_ref_state -> get_motion_state (full: local rotations ->
+// dof_pos, dof velocities) -> _set_env_state scatter -> clock / buffer resets.  The observation
+// of the reset envs is a masked obs-only pass of the step kernel, launched right after.
+// ---------------------------------------------------------------------------------------
+struct ResetParams {
+  LibDev L;
+  PhcBodyState body;  // written
+  float* root;
+  int64_t root_stride;
+  float* dof_pos;
+  float* dof_vel;
+  int64_t dof_stride, dof_estride;
+  int16_t* progress;
+  uint8_t* reset;
+  uint8_t* term;
+  float* start;
+  float* start_off;
+  float* goff;
+  const int64_t* ids;
+  const uint8_t* mask;
+  const float* phase;
+  int state_init, flag_test;
+  int64_t n;
+};
+
+constexpr int K7_EPB = 8;
+
+__global__ void __launch_bounds__(K7_EPB* J24) reset_scatter_kernel(const ResetParams p) {
+  __shared__ float s_goff[K7_EPB][3];
+  const int e = threadIdx.x / J24, b = threadIdx.x % J24;
+  const int64_t env = (int64_t)blockIdx.x * K7_EPB + e;
+  const bool act = env < p.n && p.mask[env];
+  if (act && b < 3) s_goff[e][b] = p.goff ? p.goff[env * 3 + b] : 0.0f;  // the OLD offset poses the env (:860)
+  __syncthreads();
+  if (!act) return;
+  const int64_t id = p.ids[env];
+  const float len = p.L.len[id];
+  // MotionLibBase.sample_time_interval (motion_lib.py:526-535):
+  //   ((phase * motion_len) / curr_fps).long() * curr_fps with curr_fps = 1/30
+  float t = 0.0f;
+  if (p.state_init == PHC_STATE_INIT_RANDOM && !p.flag_test) {
+    const float c30 = (float)(1.0 / 30.0);
+    const long long k = (long long)((p.phase[env] * len) / c30);
+    t = (float)k * c30;
+  }
+  int64_t i0, i1;
+  float bl;
+  calc_frame_blend(t, len, p.L.nf[id], p.L.mdt[id], i0, i1, bl);
+  const int64_t st = p.L.starts[id];
+  const int64_t f0 = i0 + st, f1 = i1 + st;
+  const float om = 1.0f - bl;
+  // get_motion_state (motion_lib.py:549-626)
+  Vec3 pos = lerp3(om, bl, ld3(p.L.gts + (f0 * J24 + b) * 3), ld3(p.L.gts + (f1 * J24 + b) * 3));
+  pos.x += s_goff[e][0];
+  pos.y += s_goff[e][1];
+  pos.z += s_goff[e][2];
+  const Quat rot = quat_slerp(ld4v(p.L.grs + (f0 * J24 + b) * 4), ld4v(p.L.grs + (f1 * J24 + b) * 4), bl);
+  const Vec3 vel = lerp3(om, bl, ld3(p.L.gvs + (f0 * J24 + b) * 3), ld3(p.L.gvs + (f1 * J24 + b) * 3));
+  const Vec3 ang = lerp3(om, bl, ld3(p.L.gavs + (f0 * J24 + b) * 3), ld3(p.L.gavs + (f1 * J24 + b) * 3));
+  // _set_env_state (humanoid_phc.py:901-931)
+  st3(const_cast<float*>(view_at(p.body.pos, env, b)), pos);
+  st4(const_cast<float*>(view_at(p.body.rot, env, b)), rot);
+  st3(const_cast<float*>(view_at(p.body.vel, env, b)), vel);
+  st3(const_cast<float*>(view_at(p.body.ang_vel, env, b)), ang);
+  if (b == 0 && p.root) {
+    float* r = p.root + env * p.root_stride;
+    st3(r, pos);
+    st4(r + 3, rot);
+    st3(r + 7, vel);
+    st3(r + 10, ang);
+  }
+  if (p.dof_pos && b >= 1) {  // _local_rotation_to_dof_smpl (motion_lib.py:670-673)
+    const Quat lr = quat_slerp(ld4v(p.L.lrs + (f0 * J24 + b) * 4), ld4v(p.L.lrs + (f1 * J24 + b) * 4), bl);
+    const Vec3 em = quat_exp_map(lr);
+    float* d = p.dof_pos + env * p.dof_stride + (int64_t)(b - 1) * 3 * p.dof_estride;
+    d[0] = em.x;
+    d[p.dof_estride] = em.y;
+    d[2 * p.dof_estride] = em.z;
+  }
+  if (p.dof_vel && b < 23) {
+    const Vec3 dv = lerp3(om, bl, ld3(p.L.dvs + (f0 * 23 + b) * 3), ld3(p.L.dvs + (f1 * 23 + b) * 3));
+    float* d = p.dof_vel + env * p.dof_stride + (int64_t)b * 3 * p.dof_estride;
+    d[0] = dv.x;
+    d[p.dof_estride] = dv.y;
+    d[2 * p.dof_estride] = dv.z;
+  }
+  if (b == 0) {  // _reset_ref_state_init (:724-731) and _reset_env_tensors (:775-778)
+    if (p.goff) {
+      p.goff[env * 3 + 0] = 0.0f;
+      p.goff[env * 3 + 1] = 0.0f;
+      p.goff[env * 3 + 2] = 0.0f;
+    }
+    p.start[env] = t;
+    p.start_off[env] = 0.0f;
+    p.progress[env] = 0;
+    p.reset[env] = 0;
+    p.term[env] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // K6: the fused step.  One block = EPB envs x 24 bodies.
 //   phase 0  sim tile -> smem (cp.async 16 B when the four views are one 16-B aligned AoS-13
 //            tensor; strided scalar loads otherwise); env leaders advance the clock and run
@@ -484,6 +586,8 @@ struct StepParams {
   int first_wave_blocks;      // blocks that can be resident at once (speculate before the dependency wait)
   int spec_fault;             // test hook: perturb the speculated clock (PHC_OPT_TEST_SPEC_FAULT)
   unsigned long long* trace;  // NULL, or [grid][8] globaltimer stamps (phc_set_trace_buffer)
+  const uint8_t* env_mask;  // NULL, or [n]: only envs with a non-zero byte are processed (generic kernel)
+  int obs_only;             // 1: observations only — no reward / reset outputs, clock untouched
   int aos;        // sim state is one AoS-13 tensor, 16-B aligned rows
   int obs_vec2;   // obs rows can be written with 8-byte stores
 };
@@ -518,6 +622,7 @@ struct StepSmem {
   float bl[PHC_MAX_TIME_STEPS + 1][EPB];
   int prog[EPB];
   int pass[EPB];
+  int act[EPB];  // env is in range and selected by env_mask
 };
 
 template <int EPB>
@@ -575,9 +680,10 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
   const int e = tid / J24, b = tid % J24;
   const int64_t env0 = (int64_t)blockIdx.x * EPB;
   const int64_t env = env0 + e;
-  const bool valid = env < p.n;
+  const bool valid = env < p.n && (!p.env_mask || p.env_mask[env]);
   const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
   const int T = p.T;
+  if (b == 0) S.act[e] = valid;  // read after the first barrier
 
   // ---- phase 0: sim tile + clock ------------------------------------------------------
   if (p.aos) {
@@ -623,7 +729,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
     if (b == 0) {
       S.prog[e] = prog;
       S.pass[e] = t >= len;  // _compute_reset, humanoid_phc.py:1317
-      if (p.advance) p.progress[env] = (int16_t)prog;
+      if (p.advance && !p.obs_only) p.progress[env] = (int16_t)prog;
       S.goff[e][0] = p.goff ? p.goff[env * 3 + 0] : 0.0f;
       S.goff[e][1] = p.goff ? p.goff[env * 3 + 1] : 0.0f;
       S.goff[e][2] = p.goff ? p.goff[env * 3 + 2] : 0.0f;
@@ -665,12 +771,13 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
 
   if (T >= 1) load_frames<EPB>(p.L, S, 1, e, b, valid);  // overlap with the reductions below
 
-  if (valid && b < 4) {
+  const bool outs = valid && !p.obs_only;  // obs-only passes leave reward / flags untouched
+  if (outs && b < 4) {
     const float k = b == 0 ? p.rwd.k_pos : b == 1 ? p.rwd.k_rot : b == 2 ? p.rwd.k_vel : p.rwd.k_ang_vel;
     const float t = reward_term(&S.part[b][e][0], J24, k);
     S.terms[e][b] = t;
     p.raw[env * p.raw_stride + b] = t;
-  } else if (valid && b == 4) {
+  } else if (outs && b == 4) {
     bool fallen = false;
     if (p.early) {
       const float* d = &S.part[4][e][0];
@@ -694,7 +801,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
     p.reset[env] = S.pass[e] ? 1 : (fallen ? 1 : 0);  // common.py:362
   }
   __syncwarp();
-  if (valid && b == 0) {
+  if (outs && b == 0) {
     const float* t = S.terms[e];
     float r = p.rwd.w_pos * t[0] + p.rwd.w_rot * t[1] + p.rwd.w_vel * t[2] + p.rwd.w_ang_vel * t[3];
     if (p.dof_force) {
@@ -748,12 +855,13 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
     const int s_len = q == 1 ? STAGE_FLOATS : TASK_DIM;
     const int64_t c_off = q == 1 ? 0 : SELF_DIM + (int64_t)TASK_DIM * (q - 1);
     if (p.obs_vec2) {
-      if (T == 1 && p.obs_stride == STAGE_FLOATS) {  // rows of the block are one contiguous span
+      if (T == 1 && p.obs_stride == STAGE_FLOATS && !p.env_mask) {  // rows of the block are one contiguous span
         float2* dst = reinterpret_cast<float2*>(p.obs + env0 * STAGE_FLOATS);
         const float2* src = reinterpret_cast<const float2*>(S.buf);
         for (int i = tid; i < nvalid * (STAGE_FLOATS / 2); i += NT) dst[i] = src[i];
       } else {
         for (int ee = 0; ee < nvalid; ++ee) {
+          if (!S.act[ee]) continue;
           float2* dst = reinterpret_cast<float2*>(p.obs + (env0 + ee) * p.obs_stride + c_off);
           const float2* src = reinterpret_cast<const float2*>(S.buf + ee * STAGE_FLOATS + s_off);
           for (int i = tid; i < s_len / 2; i += NT) dst[i] = src[i];
@@ -761,6 +869,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
       }
     } else {
       for (int ee = 0; ee < nvalid; ++ee) {
+        if (!S.act[ee]) continue;
         float* dst = p.obs + (env0 + ee) * p.obs_stride + c_off;
         const float* src = S.buf + ee * STAGE_FLOATS + s_off;
         for (int i = tid; i < s_len; i += NT) dst[i] = src[i];
@@ -771,6 +880,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
       for (int c = tid; c < s_len; c += NT) {
         double s1 = 0.0, s2 = 0.0;
         for (int ee = 0; ee < nvalid; ++ee) {
+          if (!S.act[ee]) continue;
           const double x = (double)S.buf[ee * STAGE_FLOATS + s_off + c];
           s1 += x;
           s2 += x * x;
@@ -1509,6 +1619,8 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   }
   p.first_wave_blocks = 0;
   p.spec_fault = g_spec_fault;
+  p.env_mask = nullptr;
+  p.obs_only = 0;
   {  // profiling only: consecutive launches stamp consecutive slices of the trace buffer
     const int64_t nw = (n + 3) / 4 * 3;
     if (g_trace && (g_trace_launch + 1) * nw <= g_trace_capacity) {
@@ -1547,6 +1659,82 @@ static void init_options() {
     const char* w = getenv("PHC_STEP_PDL");
     g_pdl = (w && w[0] == '0') ? 0 : 1;
   }
+}
+
+int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* a, int64_t n, phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0) return PHC_ERR_SHAPE;
+  if (!lib || !a) return PHC_ERR_NULL;
+  int rc = check_body(&a->body);
+  if (rc) return rc;
+  if (a->body.num_bodies != J24) return PHC_ERR_UNSUPPORTED;
+  if (!a->progress_buf || !a->reset_buf || !a->terminate_buf || !a->motion_start_times ||
+      !a->motion_start_times_offset || !a->sampled_motion_ids || !a->env_mask || !a->obs_buf)
+    return PHC_ERR_NULL;
+  if (a->state_init == PHC_STATE_INIT_RANDOM && !a->flag_test && !a->phase) return PHC_ERR_NULL;
+  if (a->state_init != PHC_STATE_INIT_RANDOM && a->state_init != PHC_STATE_INIT_START) return PHC_ERR_UNSUPPORTED;
+  if ((a->dof_pos && !lib->d.lrs) || (a->dof_vel && !lib->d.dvs)) return PHC_ERR_NULL;
+  if ((const void*)a->env_mask == (const void*)a->reset_buf) return PHC_ERR_UNSUPPORTED;
+  if (a->time_steps < 1 || a->time_steps > PHC_MAX_TIME_STEPS) return PHC_ERR_SHAPE;
+  const int64_t W = SELF_DIM + (int64_t)TASK_DIM * a->time_steps;
+  if (a->obs_stride < W || ((a->dof_pos || a->dof_vel) && a->dof_elem_stride < 1)) return PHC_ERR_SHAPE;
+
+  ResetParams r{};
+  r.L = lib->d;
+  r.body = a->body;
+  r.root = a->humanoid_root_states;
+  r.root_stride = a->root_stride;
+  r.dof_pos = a->dof_pos;
+  r.dof_vel = a->dof_vel;
+  r.dof_stride = a->dof_stride;
+  r.dof_estride = a->dof_elem_stride;
+  r.progress = a->progress_buf;
+  r.reset = a->reset_buf;
+  r.term = a->terminate_buf;
+  r.start = a->motion_start_times;
+  r.start_off = a->motion_start_times_offset;
+  r.goff = a->global_offset;
+  r.ids = a->sampled_motion_ids;
+  r.mask = a->env_mask;
+  r.phase = a->phase;
+  r.state_init = a->state_init;
+  r.flag_test = a->flag_test;
+  r.n = n;
+  reset_scatter_kernel<<<(unsigned)((n + K7_EPB - 1) / K7_EPB), K7_EPB * J24, 0, stream>>>(r);
+  rc = launch_status();
+  if (rc) return rc;
+
+  // _compute_observations(env_ids): masked obs-only pass of the generic step kernel on the new state
+  PhcStepArgs s{};
+  s.body = a->body;
+  s.progress_buf = a->progress_buf;
+  s.motion_start_times = a->motion_start_times;
+  s.motion_start_times_offset = a->motion_start_times_offset;
+  s.global_offset = a->global_offset;
+  s.sampled_motion_ids = a->sampled_motion_ids;
+  s.time_steps = a->time_steps;
+  s.dt = a->dt;
+  s.obs_buf = a->obs_buf;
+  s.obs_stride = a->obs_stride;
+  StepParams p;
+  // reward / flag outputs are not written in obs-only mode; give the validator harmless non-NULLs
+  s.termination_distances = a->motion_start_times;
+  s.rew_buf = a->motion_start_times;
+  s.reward_raw = a->motion_start_times;
+  s.reward_raw_stride = 4;
+  s.reset_buf = a->reset_buf;
+  s.terminate_buf = a->terminate_buf;
+  rc = step_fill_params(lib, &s, n, p);
+  if (rc) return rc;
+  p.env_mask = a->env_mask;
+  p.obs_only = 1;
+  p.advance = 0;
+  p.trace = nullptr;
+  int dev = 0;
+  PHC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return PHC_ERR_UNSUPPORTED;
+  static bool attr_gen_reset[64] = {};
+  return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen_reset[dev], false);
 }
 
 int phc_set_trace_buffer(uint64_t* device_buf, int64_t capacity_warps) {

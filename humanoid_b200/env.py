@@ -119,6 +119,11 @@ class HumanoidPHC:
         self._reset_bodies_id_backup = self._reset_bodies_id.clone()
         self._eval_track_bodies_id = build_body_ids_tensor(BODY_NAMES, EVAL_BODIES, dev)
 
+        # root state of the humanoid actor (humanoid_phc.py:518-523)
+        self._humanoid_root_states = torch.zeros((N, 13), dtype=torch.float32, device=dev)
+        self.state_init_random = True  # StateInit.Random (config.py:110); False = StateInit.Start
+        self.flag_test = False
+
         self.obs_moments = (
             torch.zeros(2 * self.num_obs, dtype=torch.float64, device=dev) if obs_moments else None
         )
@@ -251,6 +256,68 @@ class HumanoidPHC:
         self.extras["terminate"] = self._terminate_buf
         self.extras["reward_raw"] = self.reward_raw
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # ------------------------------------------------------------------------------------
+    # reset (humanoid_phc.py:90-103, 665-778) — on the device, no host sync
+    # ------------------------------------------------------------------------------------
+    def _reset_masked(self, mask: torch.Tensor, phase_by_env: torch.Tensor):
+        body, keep = _cabi.body_state(
+            self._rigid_body_pos, self._rigid_body_rot, self._rigid_body_vel, self._rigid_body_ang_vel
+        )
+        a = _cabi.PhcResetArgs()
+        a.body = body
+        a.humanoid_root_states = self._humanoid_root_states.data_ptr()
+        a.root_stride = self._humanoid_root_states.stride(0)
+        a.dof_pos = self._dof_pos.data_ptr()
+        a.dof_vel = self._dof_vel.data_ptr()
+        a.dof_stride = self._dof_pos.stride(0)
+        a.dof_elem_stride = self._dof_pos.stride(1)
+        a.progress_buf = self.progress_buf.data_ptr()
+        a.reset_buf = self.reset_buf.data_ptr()
+        a.terminate_buf = self._terminate_buf.data_ptr()
+        a.motion_start_times = self._motion_start_times.data_ptr()
+        a.motion_start_times_offset = self._motion_start_times_offset.data_ptr()
+        a.global_offset = self._global_offset.data_ptr()
+        a.sampled_motion_ids = self._sampled_motion_ids.data_ptr()
+        a.env_mask = mask.data_ptr()
+        a.phase = phase_by_env.data_ptr()
+        a.state_init = _cabi.STATE_INIT_RANDOM if self.state_init_random else _cabi.STATE_INIT_START
+        a.flag_test = 1 if self.flag_test else 0
+        a.time_steps = self.time_steps
+        a.dt = self.dt
+        a.obs_buf = self.obs_buf.data_ptr()
+        a.obs_stride = self.obs_buf.stride(0)
+        _cabi.check(
+            _cabi.load().phc_reset_envs(self._motion_lib.handle, C.byref(a), self.num_envs, _cabi.stream_ptr(self.device)),
+            "phc_reset_envs",
+        )
+
+    def reset(self, env_ids=None, phase: Optional[torch.Tensor] = None):
+        """``HumanoidPHC.reset(env_ids)`` (:90-103) with reference-state init: sample a start time
+        per env (``sample_time_interval``), pose the env from the motion library, reset its clock
+        and buffers, recompute its observation.  ``phase`` are the uniform numbers the reference
+        draws with ``torch.rand(len(env_ids))``; drawn here when omitted.  The second, PhysX-settling
+        pass of ``safe_reset`` (:97-101) is out of scope."""
+        if env_ids is None:
+            env_ids = self.all_env_ids
+        env_ids = env_ids.to(self.device)
+        if phase is None:
+            phase = torch.rand(env_ids.shape, device=self.device)
+        mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        mask[env_ids] = True
+        by_env = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+        by_env[env_ids] = phase.to(self.device, torch.float32)
+        self._reset_masked(mask, by_env)
+        return self.obs_buf
+
+    def reset_done(self, phase_by_env: Optional[torch.Tensor] = None):
+        """Reset every env whose ``reset_buf`` is set, entirely on the device: replaces the
+        ``nonzero(reset_buf)`` + ``env.reset(reset_indices)`` of clean_pufferl/env.py:133-135 and its
+        host sync.  ``phase_by_env [N]`` supplies one uniform number per env (used where flagged)."""
+        if phase_by_env is None:
+            phase_by_env = torch.rand(self.num_envs, device=self.device)
+        self._reset_masked(self.reset_buf.clone(), phase_by_env.to(self.device, torch.float32).contiguous())
+        return self.obs_buf
 
     # ------------------------------------------------------------------------------------
     # the reference's decomposition, on the per-function kernels

@@ -227,6 +227,45 @@ typedef struct PhcStepArgs {
 
 PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Reference-state-init reset of a subset of envs, on the device, with no host sync:
+ *   HumanoidPHC._reset_envs (envs/humanoid_phc.py:665-676) =
+ *     _sample_ref_state (:845-875; MotionLibBase.sample_time_interval motion_lib.py:526-535)
+ *     -> get_motion_state -> _set_env_state (:901-931) -> clock updates of
+ *     _reset_ref_state_init (:724-731) -> buffer zeroing of _reset_env_tensors (:775-778)
+ *     -> _compute_observations(env_ids) (:937-961).
+ * The PhysX setters (:748-765) are out of scope.  Envs are selected by a byte mask (e.g. a copy
+ * of reset_buf), so the `nonzero()` of clean_pufferl/env.py:133 is not needed.  Random numbers
+ * come from the caller (`phase`, what torch.rand gives in sample_time_interval), indexed by env.
+ * ---------------------------------------------------------------------------------- */
+#define PHC_STATE_INIT_START 0  /* motion time 0                       state_init.py */
+#define PHC_STATE_INIT_RANDOM 1 /* sample_time_interval(phase)                       */
+typedef struct PhcResetArgs {
+  PhcBodyState body;                      /* sim state views, written for the selected envs (J = 24) */
+  float* humanoid_root_states;            /* NULL or [n,13]: pos3|rot4|vel3|ang vel3  humanoid_phc.py:518 */
+  int64_t root_stride;
+  float* dof_pos;                         /* NULL or [n,69] view          humanoid_phc.py:535 */
+  float* dof_vel;                         /* NULL or [n,69] view          humanoid_phc.py:536 */
+  int64_t dof_stride;                     /* row stride in elements (both views)             */
+  int64_t dof_elem_stride;                /* 2 for the interleaved (pos, vel) dof state       */
+  int16_t* progress_buf;                  /* [n] -> 0                                         */
+  uint8_t* reset_buf;                     /* [n] -> 0                                         */
+  uint8_t* terminate_buf;                 /* [n] -> 0                                         */
+  float* motion_start_times;              /* [n] -> sampled motion time                       */
+  float* motion_start_times_offset;       /* [n] -> 0                                         */
+  float* global_offset;                   /* [n,3] read (old value offsets the pose), then -> 0 */
+  const int64_t* sampled_motion_ids;      /* [n]                                              */
+  const uint8_t* env_mask;                /* [n] 1 = reset this env; must not alias reset_buf  */
+  const float* phase;                     /* [n] uniform [0,1), used when state_init == RANDOM */
+  int32_t state_init;                     /* PHC_STATE_INIT_*                                 */
+  int32_t flag_test;                      /* motion_times[:] = 0         humanoid_phc.py:856  */
+  int32_t time_steps;                     /* T of the observation                             */
+  float dt;
+  float* obs_buf;                         /* [n, 358+576*T]: rows of the selected envs rewritten */
+  int64_t obs_stride;
+} PhcResetArgs;
+PHC_API int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* args, int64_t n, phc_stream_t stream);
+
 /* Process-wide tuning / test switches of phc_step_fused (not part of the reference surface).
  * phc_step_fused picks the TMA fast kernel when time_steps == 1, the four body views are one
  * 16-B aligned AoS-13 tensor and obs_buf is dense and 16-B aligned; otherwise, or when

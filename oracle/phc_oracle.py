@@ -506,6 +506,93 @@ def step(
 
 
 # ----------------------------------------------------------------------------------
+# reset — envs/humanoid_phc.py:665-778, motion_lib.py:526-535
+# ----------------------------------------------------------------------------------
+
+
+def sample_time_interval(motion_lengths: Tensor, motion_ids: Tensor, phase: Tensor) -> Tensor:
+    """MotionLibBase.sample_time_interval, motion_lib.py:526-535, with the uniform numbers
+    ``torch.rand`` would draw passed in as ``phase`` (truncate_time=None)."""
+    motion_len = motion_lengths[motion_ids]
+    curr_fps = 1 / 30
+    return ((phase * motion_len) / curr_fps).long() * curr_fps
+
+
+def reset_envs(
+    lib: OracleMotionLib,
+    env_ids: Tensor,
+    phase: Tensor,  # [len(env_ids)]
+    state: Tensor,  # [N, B, 13] AoS sim state — written in place
+    root_states: Tensor,  # [N, 13]
+    dof_pos: Tensor,  # [N, 69]
+    dof_vel: Tensor,  # [N, 69]
+    progress_buf: Tensor,
+    reset_buf: Tensor,
+    terminate_buf: Tensor,
+    motion_start_times: Tensor,
+    motion_start_times_offset: Tensor,
+    global_offset: Tensor,
+    sampled_motion_ids: Tensor,
+    obs_buf: Tensor,
+    dt: float,
+    random_init: bool = True,
+    flag_test: bool = False,
+    time_steps: int = 1,
+    num_bodies: int = 24,
+):
+    """HumanoidPHC._reset_envs(env_ids) for StateInit.Random / Start, minus the PhysX setters
+    (humanoid_phc.py:665-676): _sample_ref_state (:845-875) -> _set_env_state (:901-931) ->
+    clock updates (:724-731) -> buffer zeroing (:775-778) -> _compute_observations(env_ids)
+    (:937-961).  All tensors are updated in place; returns the obs rows of env_ids."""
+    J = num_bodies
+    ids = sampled_motion_ids[env_ids]
+    if random_init:
+        motion_times = sample_time_interval(lib._motion_lengths, ids, phase)
+    else:
+        motion_times = torch.zeros(env_ids.shape[0])
+    if flag_test:
+        motion_times[:] = 0
+    res = lib.get_motion_state(ids, motion_times, global_offset[env_ids])  # the old offset (:860)
+    # _set_env_state
+    root_states[env_ids, 0:3] = res["root_pos"]
+    root_states[env_ids, 3:7] = res["root_rot"]
+    root_states[env_ids, 7:10] = res["root_vel"]
+    root_states[env_ids, 10:13] = res["root_ang_vel"]
+    dof_pos[env_ids] = res["dof_pos"]
+    dof_vel[env_ids] = res["dof_vel"]
+    state[env_ids, :J, 0:3] = res["rg_pos"]
+    state[env_ids, :J, 3:7] = res["rb_rot"]
+    state[env_ids, :J, 7:10] = res["body_vel"]
+    state[env_ids, :J, 10:13] = res["body_ang_vel"]
+    # _reset_ref_state_init
+    global_offset[env_ids] = 0
+    motion_start_times[env_ids] = motion_times
+    motion_start_times_offset[env_ids] = 0
+    # _reset_env_tensors
+    progress_buf[env_ids] = 0
+    reset_buf[env_ids] = 0
+    terminate_buf[env_ids] = 0
+    # _compute_observations(env_ids)
+    pos, rot = state[env_ids, :J, 0:3], state[env_ids, :J, 3:7]
+    vel, ang = state[env_ids, :J, 7:10], state[env_ids, :J, 10:13]
+    self_obs = self_obs_smpl_max(pos, rot, vel, ang, None, None, True, True, True, False, False)
+    refs = []
+    for k in range(1, time_steps + 1):
+        tk = (progress_buf[env_ids] + k) * dt + motion_start_times[env_ids] + motion_start_times_offset[env_ids]
+        refs.append(lib.get_motion_state(ids, tk, global_offset[env_ids]))
+    n = env_ids.shape[0]
+
+    def stack(key):
+        return torch.stack([r[key] for r in refs], dim=1).reshape((n * time_steps,) + refs[0][key].shape[1:])
+
+    task = imitation_obs_v6(pos[:, 0], rot[:, 0], pos, rot, vel, ang, stack("rg_pos"), stack("rb_rot"),
+                            stack("body_vel"), stack("body_ang_vel"), time_steps, True)  # fmt: skip
+    obs = torch.cat([self_obs, task], dim=-1)
+    obs_buf[env_ids] = obs
+    return obs
+
+
+# ----------------------------------------------------------------------------------
 # observation normaliser — policies/running_norm.py
 # ----------------------------------------------------------------------------------
 

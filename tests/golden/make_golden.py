@@ -263,6 +263,21 @@ def case_flags():
     save("flags", arrays)
 
 
+def case_sample_time():
+    """MotionLibBase.sample_time_interval (motion_lib.py:526-535) under a fixed torch seed; the
+    fixture stores the uniform numbers the same seed produces, so the drop-in takes them as input."""
+    lib_data = synth.make_motion_lib(300, 20, 400, fps_choices=(30, 60, 120), seed=77)
+    lib = ref_loader.make_reference_lib(lib_data)
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, 300, (5000,), generator=g)
+    torch.manual_seed(4242)
+    t = lib.sample_time_interval(ids)
+    torch.manual_seed(4242)
+    phase = torch.rand(ids.shape)
+    save("sample_time", {"in.motion_lengths": lib_data.motion_lengths.numpy(), "in.ids": ids.numpy(),
+                         "in.phase": phase.numpy(), "out.motion_time": t.numpy()})  # fmt: skip
+
+
 def case_running_norm():
     # the policies package __init__ pulls in pufferlib (absent); load the one file directly
     import importlib.util
@@ -308,3 +323,4 @@ if __name__ == "__main__":
     case_slerp()
     case_flags()
     case_running_norm()
+    case_sample_time()

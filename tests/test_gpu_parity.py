@@ -684,3 +684,113 @@ def test_power_reward_vs_oracle(fused):
     assert_close(env.rew_buf, want[1], what="reward incl. power", **OBS_TOL)
     assert_close(env.reward_raw, want[2], what="reward_raw incl. power column", **OBS_TOL)
     assert float(env.reward_raw[:, 4].cpu()[prog <= 3].abs().max()) == 0.0
+
+
+def _oracle_env_state(N, clock, state):
+    return dict(
+        state=state.clone(), root=torch.zeros(N, 13), dof_pos=torch.zeros(N, 69), dof_vel=torch.zeros(N, 69),
+        prog=clock.progress_buf.clone(), reset=torch.ones(N, dtype=torch.bool), term=torch.ones(N, dtype=torch.bool),
+        start=clock.motion_start_times.clone(), soff=clock.motion_start_times_offset.clone(),
+        goff=clock.global_offset.clone(), ids=clock.sampled_motion_ids.clone(), obs=torch.zeros(N, 934),
+    )  # fmt: skip
+
+
+def _oracle_reset(ol, s, env_ids, phase, **kw):
+    return O.reset_envs(ol, env_ids, phase, s["state"], s["root"], s["dof_pos"], s["dof_vel"], s["prog"], s["reset"],
+                        s["term"], s["start"], s["soff"], s["goff"], s["ids"], s["obs"], synth.SIM_DT, **kw)  # fmt: skip
+
+
+def _oracle_obs_on(ol, state_cpu, s, env_ids):
+    """Observation of env_ids computed by the oracle from a GIVEN sim state (the one the device
+    wrote), so that the comparison does not go through each side's own 1e-7-different root rotation
+    (the heading is ill-conditioned when the root's x axis is near vertical)."""
+    J = 24
+    pos, rot = state_cpu[env_ids, :J, 0:3], state_cpu[env_ids, :J, 3:7]
+    vel, ang = state_cpu[env_ids, :J, 7:10], state_cpu[env_ids, :J, 10:13]
+    so = O.self_obs_smpl_max(pos, rot, vel, ang, None, None, True, True, True, False, False)
+    t1 = (s["prog"][env_ids] + 1) * synth.SIM_DT + s["start"][env_ids] + s["soff"][env_ids]
+    r = ol.get_motion_state(s["ids"][env_ids], t1, s["goff"][env_ids])
+    to = O.imitation_obs_v6(pos[:, 0], rot[:, 0], pos, rot, vel, ang, r["rg_pos"], r["rb_rot"], r["body_vel"],
+                            r["body_ang_vel"], 1, True)  # fmt: skip
+    return torch.cat([so, to], dim=-1)
+
+
+def test_sample_time_interval_vs_reference_fixture(golden):
+    """The start times a reset writes are the reference's sample_time_interval for the same phase."""
+    from humanoid_b200 import HumanoidPHC
+
+    g = golden("sample_time")
+    lens, ids, phase = g.inp("motion_lengths"), g.inp("ids"), g.inp("phase")
+    n, M = ids.numel(), lens.numel()
+    nf = ((lens * 30).round().long() + 1).clamp_min(2)
+    lib_data = synth.make_motion_lib(M, seed=5, frames_per_motion=nf)
+    lib_data.motion_lengths = lens.clone()  # the lengths the fixture was made with
+    env = HumanoidPHC(MotionLib(lib_data, device=DEV), n, device=DEV)
+    env._sampled_motion_ids.copy_(ids)
+    env.reset(torch.arange(n), phase=cuda(phase))
+    assert torch.equal(env._motion_start_times.cpu(), g.out("motion_time"))
+    assert int(env.progress_buf.abs().sum()) == 0 and not bool(env.reset_buf.any())
+
+
+@pytest.mark.parametrize("random_init", [True, False], ids=["StateInit.Random", "StateInit.Start"])
+def test_reset_subset_vs_oracle(random_init):
+    lib_data, clock, state = make_case_cpu(num_envs=900, num_motions=60, seed=113, max_progress=30,
+                                           fps_choices=(30, 60), min_frames=40, max_frames=200)  # fmt: skip
+    env = env_from(lib_data, clock, state)
+    env.state_init_random = random_init
+    ol = O.OracleMotionLib(lib_data)
+    s = _oracle_env_state(900, clock, state)
+    gen = torch.Generator().manual_seed(9)
+    env_ids = torch.randperm(900, generator=gen)[:333]
+    phase = torch.rand(333, generator=gen)
+    before = env._rigid_body_state_reshaped.clone()
+    _oracle_reset(ol, s, env_ids, phase, random_init=random_init)
+    env.reset(cuda(env_ids), phase=cuda(phase))
+    keep = torch.ones(900, dtype=torch.bool)
+    keep[env_ids] = False
+    # untouched envs are bit-identical; reset envs match the oracle
+    assert torch.equal(env._rigid_body_state_reshaped.cpu()[keep], before.cpu()[keep])
+    assert torch.equal(env._motion_start_times.cpu(), s["start"])
+    assert torch.equal(env._motion_start_times_offset.cpu(), s["soff"]) and torch.equal(env._global_offset.cpu(), s["goff"])
+    assert_equal_exact(env.progress_buf, s["prog"], "progress")
+    assert_equal_exact(env.reset_buf, s["reset"], "reset_buf")
+    assert_equal_exact(env._terminate_buf, s["term"], "terminate_buf")
+    assert_close(env._rigid_body_state_reshaped, s["state"], what="rigid body state", **OBS_TOL)
+    assert_close(env._humanoid_root_states[cuda(env_ids)], s["root"][env_ids], what="root states", **OBS_TOL)
+    assert_close(env._dof_pos[cuda(env_ids)], s["dof_pos"][env_ids], what="dof_pos", **DOF_TOL)
+    assert_close(env._dof_vel[cuda(env_ids)], s["dof_vel"][env_ids], what="dof_vel", **OBS_TOL)
+    want_obs = _oracle_obs_on(ol, env._rigid_body_state_reshaped.cpu(), s, env_ids)
+    assert_close(env.obs_buf[cuda(env_ids)], want_obs, what="obs of reset envs", **OBS_TOL)
+    assert float(env.obs_buf.cpu()[keep].abs().sum()) == 0.0  # rows of other envs untouched
+
+
+def test_rollout_with_device_side_resets_vs_oracle():
+    """step -> reset the envs flagged by reset_buf (no host sync) -> step ..., six times."""
+    N = 512
+    lib_data, clock, state = make_case_cpu(num_envs=N, num_motions=N, seed=114, min_frames=12, max_frames=40, max_progress=8)
+    env = env_from(lib_data, clock, state)
+    ol = O.OracleMotionLib(lib_data)
+    s = _oracle_env_state(N, clock, state)
+    term = torch.full((24,), 0.25)
+    gen = torch.Generator().manual_seed(10)
+    for it in range(6):
+        want = O.step(ol, s["state"], s["prog"], s["start"], s["soff"], s["goff"], s["ids"], term, synth.SIM_DT)
+        s["reset"], s["term"] = want[3].clone(), want[4].clone()
+        env.step()
+        assert_equal_exact(env.reset_buf, want[3], f"reset @{it}")
+        assert_close(env.obs_buf, want[0], what=f"obs @{it}", **OBS_TOL)
+        assert_close(env.rew_buf, want[1], what=f"reward @{it}", **OBS_TOL)
+        phase = torch.rand(N, generator=gen)
+        ids = torch.nonzero(s["reset"]).squeeze(-1)  # the oracle side may sync; the device side does not
+        assert 0 < ids.numel() < N
+        s["obs"] = want[0].clone()
+        _oracle_reset(ol, s, ids, phase[ids])
+        env.reset_done(cuda(phase))
+        assert_equal_exact(env.progress_buf, s["prog"], f"progress after reset @{it}")
+        assert torch.equal(env._motion_start_times.cpu(), s["start"])
+        # the "physics" of this test: the state the reset wrote is what the next step sees
+        assert_close(env._rigid_body_state_reshaped, s["state"], what=f"state after reset @{it}", **OBS_TOL)
+        want_obs = want[0].clone()
+        want_obs[ids] = _oracle_obs_on(ol, env._rigid_body_state_reshaped.cpu(), s, ids)
+        assert_close(env.obs_buf, want_obs, what=f"obs after reset @{it}", **OBS_TOL)
+        s["state"] = env._rigid_body_state_reshaped.cpu().clone()  # keep both sides on identical inputs

@@ -128,3 +128,11 @@ def test_fixtures_exercise_both_flag_values(golden):
         seen_term |= set(g.out("terminated").tolist())
         seen_pass |= set(g.out("pass_time").tolist())
     assert seen_reset == {True, False} and seen_term == {True, False} and seen_pass == {True, False}
+
+
+def test_sample_time_interval_bit_exact(golden):
+    g = golden("sample_time")
+    t = O.sample_time_interval(g.inp("motion_lengths"), g.inp("ids"), g.inp("phase"))
+    assert torch.equal(t, g.out("motion_time"))
+    k = t * 30
+    assert float((k - k.round()).abs().max()) < 1e-3  # multiples of 1/30 s

@@ -46,7 +46,10 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
 
-def workload_name(n):
+def workload_name(n, workload="config2", clips=0, frames=0):
+    if workload == "config4":
+        return (f"PHC SMPL 24-body step compute, num_envs={n} per GPU, AMASS-scale synthetic library ({clips} clips, "
+                f"{frames} frames, mixed 30/60/120 fps), random motion ids and unaligned times per step")
     return (f"PHC SMPL 24-body step compute (motion query + smpl_max obs + imitation obs v6 + reward + reset), "
             f"num_envs={n} per GPU, one 60-300 frame 30 fps synthetic clip per env, synthetic sim state")  # fmt: skip
 
@@ -225,23 +228,37 @@ def run_gpu(args):
     seed = 1234 + 1000 * rank  # each rank owns its own envs and their clips
 
     # -------- workload (device-generated; the reference pose comes from the product's own query kernel)
-    lib_data = synth.make_motion_lib(N, 60, 300, (30,), seed=seed, device=dev)
-    lib = MotionLib(lib_data, device=dev)
-    clock = synth.make_clock(lib_data, N, seed=seed + 1, ids="mod", aligned=True, max_progress=30)
     obs_dim = 358 + 576 * T
     set_bytes = N * (24 * 13 + obs_dim) * 4
     R = max(4, -(-args.ring_mb * (1 << 20) // set_bytes))  # ring of R buffer sets > L2
     envs = []
+    config4 = args.workload == "config4"
+    if config4:
+        # BASELINE configs[3]: AMASS-scale library (~10k clips, ~4M frames, mixed fps, a few very long
+        # clips) replicated per GPU; every ring slot has its OWN clock with random motion ids and
+        # unaligned start times, so consecutive steps gather unrelated frames (defeats L2).
+        M = args.clips
+        g = torch.Generator(device=dev).manual_seed(seed + 7)
+        nf = torch.randint(100, 701, (M,), generator=g, device=dev)
+        nf[: max(1, M // 500)] = 7000
+        lib_data = synth.make_motion_lib(M, fps_choices=(30, 60, 120), seed=seed, device=dev, frames_per_motion=nf)
+    else:
+        lib_data = synth.make_motion_lib(N, 60, 300, (30,), seed=seed, device=dev)
+    lib = MotionLib(lib_data, device=dev)
+    clock = None
     first = None
     for r in range(R):
-        t = synth.reward_time(clock, extra_steps=r + 1)
+        if config4 or clock is None:
+            clock = synth.make_clock(lib_data, N, seed=seed + 1 + 31 * r, ids="random" if config4 else "mod",
+                                     aligned=not config4, max_progress=30)  # fmt: skip
+        t = synth.reward_time(clock, extra_steps=1 if config4 else r + 1)
         ref = lib.get_motion_state(clock.sampled_motion_ids, t, clock.global_offset)
         state = synth.make_sim_state(ref, seed=seed + 2 + r)
         env = HumanoidPHC(lib, N, device=dev, time_steps=T)
         env.set_sim_state(state, copy=False)
-        if first is None:
-            first = env
+        if first is None or config4:
             env.set_clock(clock)
+            first = first or env
         else:  # all ring slots share one motion clock
             env.progress_buf = first.progress_buf
             env._motion_start_times = first._motion_start_times
@@ -249,12 +266,17 @@ def run_gpu(args):
             env._global_offset = first._global_offset
             env._sampled_motion_ids = first._sampled_motion_ids
         envs.append(env)
-    progress0 = clock.progress_buf.clone()
+    progress0 = envs[0].progress_buf.clone()
+    prog0_all = [e.progress_buf.clone() for e in envs] if config4 else None
     torch.cuda.synchronize()
 
     def run_steps(k):
         for i in range(k):
-            if i % R == 0:
+            if config4:
+                if i >= R and i % R == 0:  # every lap: each slot's clock back to its start
+                    for e, p0 in zip(envs, prog0_all):
+                        e.progress_buf.copy_(p0)
+            elif i % R == 0:
                 first.progress_buf.copy_(progress0)  # re-seed the clock at every lap of the ring
             envs[i % R].post_physics_step(True)
 
@@ -308,6 +330,10 @@ def run_gpu(args):
     def pinned(t):
         return t.detach().cpu().contiguous().pin_memory()
 
+    e0 = envs[0]  # the host-buffer leg and the CPU baseline run ring slot 0's inputs
+    clock = synth.Clock(progress_buf=progress0, motion_start_times=e0._motion_start_times,
+                        motion_start_times_offset=e0._motion_start_times_offset, global_offset=e0._global_offset,
+                        sampled_motion_ids=e0._sampled_motion_ids)  # fmt: skip
     h_state = pinned(envs[0]._rigid_body_state_reshaped)
     h_prog0 = pinned(progress0)
     h_prog = h_prog0.clone().pin_memory()
@@ -380,14 +406,17 @@ def run_gpu(args):
 
     peak, peak_src = load_peak()
     bytes_step = BYTES_PER_ENV_STEP if T == 1 else BYTES_PER_ENV_STEP_T(T)
+    if config4 and T == 1:
+        bytes_step = 10052  # 4 distinct frames
     achieved = bytes_step * N / (ms_per_step * 1e-3) / 1e9  # per GPU
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": workload_name(N), "num_envs_per_gpu": N, "num_envs_total": N * world, "time_steps": T,
-            "motion_clips_per_gpu": N, "motion_frames_per_gpu": lib_data.total_frames,
+            "workload": workload_name(N, args.workload, lib_data.num_motions, lib_data.total_frames),
+            "num_envs_per_gpu": N, "num_envs_total": N * world, "time_steps": T,
+            "motion_clips_per_gpu": lib_data.num_motions, "motion_frames_per_gpu": lib_data.total_frames,
             "l2": f"inputs larger than L2: every step uses the next of {R} sim-state/obs buffer sets "
                   f"({R * set_bytes / 2**20:.0f} MiB ring), clock re-seeded each lap",
             "cuda_graph": f"{K} step kernels in one graph", "terminated_frac": round(frac_term, 4),
@@ -432,6 +461,10 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--num-envs", type=int, default=NUM_ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--time-steps", type=int, default=1, help="future reference frames T (config 5: 10)")
+    ap.add_argument("--workload", choices=["config2", "config4"], default="config2",
+                    help="config2: one clip per env, aligned (default, BASELINE configs[1]); config4: AMASS-scale "
+                         "library, random ids / unaligned times per step (BASELINE configs[3])")
+    ap.add_argument("--clips", type=int, default=10000, help="clips of the config4 library")
     ap.add_argument("--ring-mb", type=int, default=320, help="min size of the sim-state/obs buffer ring (> L2)")
     ap.add_argument("--repeats", type=int, default=5, help="timed graph replays; the median is reported")
     ap.add_argument("--e2e-steps", type=int, default=64)

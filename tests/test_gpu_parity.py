@@ -794,3 +794,35 @@ def test_rollout_with_device_side_resets_vs_oracle():
         want_obs[ids] = _oracle_obs_on(ol, env._rigid_body_state_reshaped.cpu(), s, ids)
         assert_close(env.obs_buf, want_obs, what=f"obs after reset @{it}", **OBS_TOL)
         s["state"] = env._rigid_body_state_reshaped.cpu().clone()  # keep both sides on identical inputs
+
+
+@pytest.mark.parametrize("N,T", [(1027, 10), (64, 16), (515, 2)])
+def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T):
+    """T > 1 dispatches to the pipelined TMA kernel; the generic kernel is the same math.  Also a
+    regression test: the clock must be advanced only after every query lane has read it."""
+    from humanoid_b200 import HumanoidPHC, _cabi
+
+    lib_data, clock, state = _gpu_case(N, 64, 210, max_frames=60, max_progress=40)
+    lib = MotionLib(lib_data, device=DEV)
+    capi = _cabi.load()
+    outs = []
+    try:
+        for generic in (1, 0):
+            assert capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, generic) == 0
+            env = HumanoidPHC(lib, N, device=DEV, time_steps=T, obs_moments=True, use_power_reward=True)
+            env.set_sim_state(state)
+            env.set_clock(clock)
+            env.dof_force_tensor.normal_(generator=torch.Generator(device=DEV).manual_seed(1))
+            env._dof_vel.copy_(torch.randn(N, 69, generator=torch.Generator(device=DEV).manual_seed(2), device=DEV))
+            for _ in range(2):
+                env.step()
+            torch.cuda.synchronize()
+            outs.append(env)
+    finally:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+    g, f = outs
+    assert torch.equal(f.obs_buf, g.obs_buf)
+    assert torch.equal(f.rew_buf, g.rew_buf) and torch.equal(f.reward_raw, g.reward_raw)
+    assert torch.equal(f.reset_buf, g.reset_buf) and torch.equal(f._terminate_buf, g._terminate_buf)
+    assert torch.equal(f.progress_buf, g.progress_buf)
+    torch.testing.assert_close(f.obs_moments, g.obs_moments, rtol=1e-12, atol=1e-9)

@@ -8,6 +8,8 @@ the built shared object and a CUDA device.
 """
 
 from .common import (  # noqa: F401
+    build_amp_observations_smpl,
+    dof_subset_smpl,
     compute_humanoid_im_reset,
     compute_humanoid_observations_smpl_max,
     compute_imitation_observations_v6,
@@ -27,4 +29,6 @@ __all__ = [
     "compute_imitation_observations_v7",
     "compute_imitation_reward",
     "compute_humanoid_im_reset",
+    "build_amp_observations_smpl",
+    "dof_subset_smpl",
 ]

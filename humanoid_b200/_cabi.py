@@ -70,6 +70,22 @@ class PhcMotionOut(C.Structure):
     ]  # fmt: skip
 
 
+class PhcAmpArgs(C.Structure):
+    _fields_ = [
+        ("root_pos", C.c_void_p), ("root_pos_stride", C.c_int64),
+        ("root_rot", C.c_void_p), ("root_rot_stride", C.c_int64),
+        ("root_vel", C.c_void_p), ("root_vel_stride", C.c_int64),
+        ("root_ang_vel", C.c_void_p), ("root_ang_vel_stride", C.c_int64),
+        ("dof_pos", C.c_void_p), ("dof_pos_stride", C.c_int64), ("dof_pos_elem_stride", C.c_int64),
+        ("dof_vel", C.c_void_p), ("dof_vel_stride", C.c_int64), ("dof_vel_elem_stride", C.c_int64),
+        ("key_body_pos", PhcView),
+        ("num_key_bodies", C.c_int32),
+        ("dof_subset", C.c_void_p),
+        ("num_sel", C.c_int32),
+        ("flags", C.c_uint32),
+    ]  # fmt: skip
+
+
 class PhcRewardSpec(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("k_pos", "k_rot", "k_vel", "k_ang_vel", "w_pos", "w_rot", "w_vel", "w_ang_vel")]
 
@@ -171,6 +187,7 @@ SIGNATURES = {
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(PhcBodyState), C.POINTER(PhcBodyState), C.c_int64,
          C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p],
     ),  # fmt: skip
+    "phc_amp_obs": (C.c_int, [C.POINTER(PhcAmpArgs), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "phc_imitation_reward": (
         C.c_int,
         [C.POINTER(PhcBodyState), C.POINTER(PhcBodyState), C.c_int64, C.POINTER(PhcRewardSpec), C.c_void_p,

@@ -97,6 +97,62 @@ def compute_imitation_observations_v7(
                           ref_body_pos, ref_body_rot, ref_body_vel, ref_body_ang_vel, time_steps, upright)  # fmt: skip
 
 
+def dof_subset_smpl(device=None) -> torch.Tensor:
+    """The 57-dof subset the AMP observation uses: all joints but toes and hands
+    (humanoid_phc.py:186-194 with body_sets.py:42)."""
+    removed = (3, 7, 17, 22)  # L_Toe, R_Toe, L_Hand, R_Hand in DOF_NAMES
+    idx = [3 * j + k for j in range(23) if j not in removed for k in range(3)]
+    return torch.tensor(idx, dtype=torch.long, device=device)
+
+
+def build_amp_observations_smpl(
+    root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos, shape_params, limb_weight_params,
+    dof_subset, local_root_obs, root_height_obs, has_dof_subset, has_shape_obs_disc, has_limb_weight_obs, upright,
+):  # fmt: skip
+    """Drop-in for envs/common.py:192-267 (one kernel launch)."""
+    for t, nm in ((root_pos, "root_pos"), (root_rot, "root_rot"), (root_vel, "root_vel"),
+                  (root_ang_vel, "root_ang_vel"), (dof_pos, "dof_pos"), (dof_vel, "dof_vel")):  # fmt: skip
+        _cabi.require_cuda(t, nm, torch.float32)
+    B, D = dof_pos.shape
+    dev = root_pos.device
+
+    def rows(t):
+        return t if t.stride(-1) == 1 else t.contiguous()
+
+    root_pos, root_rot, root_vel, root_ang_vel = rows(root_pos), rows(root_rot), rows(root_vel), rows(root_ang_vel)
+    vk, key_body_pos = _cabi.view3(key_body_pos, "key_body_pos")
+    K = key_body_pos.shape[1]
+    sub = None
+    num_sel = D
+    if has_dof_subset:
+        _cabi.require_cuda(dof_subset, "dof_subset", torch.int64)
+        sub = dof_subset.contiguous()
+        num_sel = sub.numel()
+    a = _cabi.PhcAmpArgs(
+        root_pos.data_ptr(), root_pos.stride(0), root_rot.data_ptr(), root_rot.stride(0),
+        root_vel.data_ptr(), root_vel.stride(0), root_ang_vel.data_ptr(), root_ang_vel.stride(0),
+        dof_pos.data_ptr(), dof_pos.stride(0), dof_pos.stride(1), dof_vel.data_ptr(), dof_vel.stride(0), dof_vel.stride(1),
+        vk, K, _cabi.ptr(sub), num_sel,
+        (_cabi.OBS_LOCAL_ROOT if local_root_obs else 0) | (_cabi.OBS_ROOT_HEIGHT if root_height_obs else 0)
+        | (_cabi.OBS_UPRIGHT if upright else 0),
+    )  # fmt: skip
+    width = (1 if root_height_obs else 0) + 12 + 3 * num_sel + 3 * K
+    extra = []
+    if has_shape_obs_disc:
+        extra.append(shape_params)
+    if has_limb_weight_obs:
+        extra.append(limb_weight_params)
+    out = torch.empty((B, width + sum(int(x.shape[-1]) for x in extra)), dtype=torch.float32, device=dev)
+    _cabi.check(
+        _cabi.load().phc_amp_obs(C.byref(a), B, out.data_ptr(), out.stride(0), _cabi.stream_ptr(dev)), "phc_amp_obs"
+    )
+    col = width
+    for x in extra:  # appended verbatim (common.py:261-264)
+        out[:, col : col + x.shape[-1]] = x
+        col += x.shape[-1]
+    return out
+
+
 def compute_imitation_reward(
     root_pos, root_rot, body_pos, body_rot, body_vel, body_ang_vel,
     ref_body_pos, ref_body_rot, ref_body_vel, ref_body_ang_vel, rwd_specs: Dict[str, float],

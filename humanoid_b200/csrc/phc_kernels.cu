@@ -356,6 +356,55 @@ __global__ void imitation_obs_kernel(const float* __restrict__ root_pos, int64_t
 }
 
 // ---------------------------------------------------------------------------------------
+// K8: build_amp_observations_smpl (envs/common.py:192-267), 32 threads per env: thread j < nj owns
+// joint j of the dof subset (exp map -> quaternion -> tan/norm, and its dof velocities), thread 0
+// also the root terms, threads < K the key-body positions.
+// ---------------------------------------------------------------------------------------
+__global__ void amp_obs_kernel(PhcAmpArgs a, int64_t n, float* __restrict__ out, int64_t out_stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= n) return;
+  const int nj = a.num_sel / 3, K = a.num_key_bodies;
+  const Vec3 root_pos = ld3(a.root_pos + env * a.root_pos_stride);
+  Quat root_rot = ld4(a.root_rot + env * a.root_rot_stride);
+  if (!(a.flags & PHC_OBS_UPRIGHT)) root_rot = remove_base_rot(root_rot);
+  const Heading hi = heading_quat_inv(root_rot);
+  const HeadingRot hr = heading_rot(hi);
+  float* row = out + env * out_stride;
+  int col = 0;
+  if (a.flags & PHC_OBS_ROOT_HEIGHT) {
+    if (lane == 0) row[0] = root_pos.z;
+    col = 1;
+  }
+  if (lane == 0) {
+    float t6[6];
+    quat_tan_norm((a.flags & PHC_OBS_LOCAL_ROOT) ? heading_mul_left(hi, root_rot) : root_rot, t6);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) row[col + k] = t6[k];
+    st3(row + col + 6, heading_rotate(hr, ld3(a.root_vel + env * a.root_vel_stride)));
+    st3(row + col + 9, heading_rotate(hr, ld3(a.root_ang_vel + env * a.root_ang_vel_stride)));
+  }
+  col += 12;
+  for (int j = lane; j < nj; j += 32) {  // dof_to_obs_smpl (:179-189) + the selected dof velocities
+    float e3[3], v3[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int64_t d = a.dof_subset ? a.dof_subset[3 * j + k] : 3 * j + k;
+      e3[k] = a.dof_pos[env * a.dof_pos_stride + d * a.dof_pos_elem_stride];
+      v3[k] = a.dof_vel[env * a.dof_vel_stride + d * a.dof_vel_elem_stride];
+    }
+    float t6[6];
+    quat_tan_norm(exp_map_to_quat(Vec3{e3[0], e3[1], e3[2]}), t6);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) row[col + 6 * j + k] = t6[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) row[col + 6 * nj + 3 * j + k] = v3[k];
+  }
+  col += 9 * nj;
+  if (lane < K) st3(row + col + 3 * lane, heading_rotate(hr, ld3(view_at(a.key_body_pos, env, lane)) - root_pos));
+}
+
+// ---------------------------------------------------------------------------------------
 // reward / reset per-body pieces shared by K4, K5 and the fused step
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void reward_partials(Vec3 pos, Quat rot, Vec3 vel, Vec3 ang, const RefBody& r,
@@ -1774,6 +1823,21 @@ int phc_imitation_obs(const float* root_pos, int64_t root_pos_stride, const floa
   const int bs = 192;
   imitation_obs_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, stream>>>(
       root_pos, root_pos_stride, root_rot, root_rot_stride, *body, *ref, n, time_steps, upright, mode, out, out_stride);
+  return launch_status();
+}
+
+int phc_amp_obs(const PhcAmpArgs* a, int64_t n, float* out, int64_t out_stride, phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0) return PHC_ERR_SHAPE;
+  if (!a || !out || !a->root_pos || !a->root_rot || !a->root_vel || !a->root_ang_vel || !a->dof_pos || !a->dof_vel ||
+      !a->key_body_pos.ptr)
+    return PHC_ERR_NULL;
+  if (a->num_sel < 0 || a->num_sel % 3 != 0 || a->num_sel > 96 || a->num_key_bodies < 0 || a->num_key_bodies > 8)
+    return PHC_ERR_SHAPE;
+  const int width = ((a->flags & PHC_OBS_ROOT_HEIGHT) ? 1 : 0) + 12 + 3 * a->num_sel + 3 * a->num_key_bodies;
+  if (out_stride < width) return PHC_ERR_SHAPE;
+  const int epb = 4;
+  amp_obs_kernel<<<(unsigned)((n + epb - 1) / epb), epb * 32, 0, stream>>>(*a, n, out, out_stride);
   return launch_status();
 }
 

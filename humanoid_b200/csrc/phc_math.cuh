@@ -210,6 +210,27 @@ __device__ __forceinline__ Vec3 quat_exp_map(Quat q) {
   return {0.0f, 0.0f, 0.0f};
 }
 
+// torch.norm(v, dim=-1) over 3 on ATen CPU: sqrt(fma(z,z,fma(y,y,x*x)))
+__device__ __forceinline__ float norm3(Vec3 v) { return sqrtf(__fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, v.x * v.x))); }
+
+// exp_map_to_quat, torch_utils.py:334-366: angle = |e| wrapped to (-pi, pi] by atan2(sin, cos), axis
+// e/|e| (z axis when |angle| <= 1e-5), then quat_from_angle_axis incl. its two normalisations
+__device__ __forceinline__ Quat exp_map_to_quat(Vec3 e) {
+  float ang = norm3(e);
+  Vec3 ax = {e.x / ang, e.y / ang, e.z / ang};
+  ang = atan2f(sinf(ang), cosf(ang));
+  if (!(fabsf(ang) > 1e-5f)) {
+    ang = 0.0f;
+    ax = {0.0f, 0.0f, 1.0f};
+  }
+  const float an = fmaxf(norm3(ax), 1e-9f);
+  const float half = ang / 2.0f;
+  const float sn = sinf(half), cs = cosf(half);
+  Quat q = {ax.x / an * sn, ax.y / an * sn, ax.z / an * sn, cs};
+  const float qn = fmaxf(sqrtf(((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w), 1e-9f);
+  return {q.x / qn, q.y / qn, q.z / qn, q.w / qn};
+}
+
 // slerp, torch_utils.py:110-131.  c = ((x0x1 + y0y1) + z0z1) + w0w1 (ATen sum order);
 // q1 flipped when c < 0; result not renormalised; the |sin| < 1e-3 average is applied
 // first and the |cos| >= 1 -> q0 select last (it wins, and masks acos' NaN for c > 1).
@@ -237,9 +258,6 @@ __device__ __forceinline__ float lerp1(float om, float b, float x0, float x1) { 
 __device__ __forceinline__ Vec3 lerp3(float om, float b, Vec3 x0, Vec3 x1) {
   return {om * x0.x + b * x1.x, om * x0.y + b * x1.y, om * x0.z + b * x1.z};
 }
-
-// torch.norm(v, dim=-1) over 3 on ATen CPU: sqrt(fma(z,z,fma(y,y,x*x)))
-__device__ __forceinline__ float norm3(Vec3 v) { return sqrtf(__fmaf_rn(v.z, v.z, __fmaf_rn(v.y, v.y, v.x * v.x))); }
 
 // (d**2).mean(dim=-1) over 3: ((x^2 + y^2) + z^2) / 3, the division as a multiply by fl(1/3)
 // (<= 1 ulp from the quotient; feeds only the reward's exponent)

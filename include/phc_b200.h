@@ -155,6 +155,28 @@ PHC_API int phc_imitation_obs(const float* root_pos, int64_t root_pos_stride, co
                       int64_t n, int32_t time_steps, int32_t upright, int32_t mode, float* out,
                       int64_t out_stride, phc_stream_t stream);
 
+/* build_amp_observations_smpl(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel,
+ * key_body_pos, shape_params, limb_weight_params, dof_subset, local_root_obs, root_height_obs,
+ * has_dof_subset, has_shape_obs_disc, has_limb_weight_obs, upright)      envs/common.py:192-267
+ * (dof_to_obs_smpl :179-189, exp_map_to_quat torch_utils.py:334-366).  Writes
+ * [root_h? | root rot 6 | root vel 3 | root ang vel 3 | dof obs 6*nj | dof vel 3*nj | key pos 3*K]
+ * per row; shape / limb-weight columns are appended by the caller (copies of inputs).
+ * dof_subset: NULL (all dofs) or num_sel int64 dof indices (a multiple of 3). */
+typedef struct PhcAmpArgs {
+  const float* root_pos;     int64_t root_pos_stride;      /* [n,3] */
+  const float* root_rot;     int64_t root_rot_stride;      /* [n,4] */
+  const float* root_vel;     int64_t root_vel_stride;      /* [n,3] */
+  const float* root_ang_vel; int64_t root_ang_vel_stride;  /* [n,3] */
+  const float* dof_pos;      int64_t dof_pos_stride, dof_pos_elem_stride; /* [n,D] */
+  const float* dof_vel;      int64_t dof_vel_stride, dof_vel_elem_stride; /* [n,D] */
+  PhcView key_body_pos;      /* [n,K,3] */
+  int32_t num_key_bodies;    /* K <= 8 */
+  const int64_t* dof_subset; /* NULL or [num_sel] */
+  int32_t num_sel;           /* dofs used (D when dof_subset is NULL), multiple of 3, <= 96 */
+  uint32_t flags;            /* PHC_OBS_LOCAL_ROOT | PHC_OBS_ROOT_HEIGHT | PHC_OBS_UPRIGHT */
+} PhcAmpArgs;
+PHC_API int phc_amp_obs(const PhcAmpArgs* args, int64_t n, float* out, int64_t out_stride, phc_stream_t stream);
+
 /* rwd_specs of compute_imitation_reward (config.py:38-46). */
 typedef struct PhcRewardSpec {
   float k_pos, k_rot, k_vel, k_ang_vel;

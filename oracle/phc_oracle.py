@@ -351,6 +351,55 @@ def imitation_obs_v7(*args) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------
+# AMP observations — envs/common.py:179-267, torch_utils.py:334-366
+# ----------------------------------------------------------------------------------
+
+
+def exp_map_to_quat(em: Tensor) -> Tensor:
+    """exp_map_to_angle_axis + quat_from_angle_axis, torch_utils.py:334-366."""
+    ang = torch.norm(em, dim=-1)
+    axis = em / ang.unsqueeze(-1)
+    ang = torch.atan2(torch.sin(ang), torch.cos(ang))
+    ok = torch.abs(ang) > 1e-5
+    fallback = torch.zeros_like(em)
+    fallback[..., 2] = 1
+    ang = torch.where(ok, ang, torch.zeros_like(ang))
+    axis = torch.where(ok.unsqueeze(-1), axis, fallback)
+    half = (ang / 2).unsqueeze(-1)
+    unit_axis = axis / axis.norm(p=2, dim=-1).clamp(min=1e-9, max=None).unsqueeze(-1)
+    q = torch.cat((unit_axis * half.sin(), half.cos()), dim=-1)
+    return q / q.norm(p=2, dim=-1).unsqueeze(-1).clamp(min=1e-9)
+
+
+def amp_obs_smpl(
+    root_pos, root_rot, root_vel, root_ang_vel, dof_pos, dof_vel, key_body_pos, shape_params, limb_weight_params,
+    dof_subset, local_root_obs: bool, root_height_obs: bool, has_dof_subset: bool, has_shape_obs_disc: bool,
+    has_limb_weight_obs: bool, upright: bool,
+) -> Tensor:  # fmt: skip
+    """build_amp_observations_smpl, envs/common.py:192-267 (dof_to_obs_smpl :179-189)."""
+    B = root_pos.shape[0]
+    root_h = root_pos[:, 2:3]
+    if not upright:
+        root_rot = remove_base_rot(root_rot)
+    hinv = heading_quat_inv(root_rot)
+    root_rot_obs = tan_norm(quat_mul(hinv, root_rot) if local_root_obs else root_rot)
+    local_root_vel = rotate(hinv, root_vel)
+    local_root_ang_vel = rotate(hinv, root_ang_vel)
+    local_key = rotate(hinv[:, None, :], key_body_pos - root_pos[:, None, :]).reshape(B, -1)
+    if has_dof_subset:
+        dof_vel = dof_vel[:, dof_subset]
+        dof_pos = dof_pos[:, dof_subset]
+    dof_obs = tan_norm(exp_map_to_quat(dof_pos.reshape(-1, 3))).reshape(B, -1)
+    parts = [root_h] if root_height_obs else []
+    parts += [root_rot_obs, local_root_vel, local_root_ang_vel, dof_obs, dof_vel, local_key]
+    if has_shape_obs_disc:
+        parts.append(shape_params)
+    if has_limb_weight_obs:
+        parts.append(limb_weight_params)
+    return torch.cat(parts, dim=-1)
+
+
+# ----------------------------------------------------------------------------------
 # reward and reset — envs/common.py
 # ----------------------------------------------------------------------------------
 

@@ -278,6 +278,40 @@ def case_sample_time():
                          "in.phase": phase.numpy(), "out.motion_time": t.numpy()})  # fmt: skip
 
 
+def case_amp_obs():
+    """build_amp_observations_smpl (common.py:192-267) on seeded inputs: default flags with the
+    19-joint dof subset (humanoid_phc.py:186-194), and the flag variants."""
+    g = torch.Generator().manual_seed(17)
+    n = 96
+    root_pos = torch.randn(n, 3, generator=g)
+    q = torch.randn(n, 4, generator=g)
+    root_rot = q / q.norm(dim=-1, keepdim=True)
+    root_vel, root_ang = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+    dof_pos = torch.randn(n, 69, generator=g) * torch.exp(torch.rand(n, 1, generator=g) * 12 - 12)  # tiny .. ~1 rad
+    dof_pos[::9] = 0
+    dof_pos[5::31] *= 6.0  # some angles beyond pi
+    dof_vel = torch.randn(n, 69, generator=g)
+    key = torch.randn(n, 4, 3, generator=g)
+    shape, limb = torch.randn(n, 11, generator=g), torch.randn(n, 10, generator=g)
+    removed = (3, 7, 17, 22)  # L_Toe R_Toe L_Hand R_Hand in DOF_NAMES (body_sets.py:42, humanoid_phc.py:186-194)
+    subset = torch.tensor([3 * j + k for j in range(23) if j not in removed for k in range(3)])
+    arrays = {"in.root_pos": root_pos, "in.root_rot": root_rot, "in.root_vel": root_vel, "in.root_ang_vel": root_ang,
+              "in.dof_pos": dof_pos, "in.dof_vel": dof_vel, "in.key_body_pos": key, "in.shape": shape, "in.limb": limb,
+              "in.dof_subset": subset}  # fmt: skip
+    variants = {  # local_root_obs, root_height_obs, has_dof_subset, has_shape_obs_disc, has_limb_weight_obs, upright
+        "default": (True, True, True, False, False, True),
+        "all_dofs": (True, True, False, False, False, True),
+        "global_root_no_height": (False, False, True, False, False, True),
+        "not_upright_with_params": (True, True, True, True, True, False),
+    }
+    for name, fl in variants.items():
+        o = ref_common.build_amp_observations_smpl(root_pos, root_rot, root_vel, root_ang, dof_pos, dof_vel, key, shape,
+                                                   limb, subset, *fl)  # fmt: skip
+        arrays[f"out.{name}"] = o
+        arrays[f"in.flags.{name}"] = torch.tensor(fl)
+    save("amp_obs", {k: v.numpy() for k, v in arrays.items()})
+
+
 def case_running_norm():
     # the policies package __init__ pulls in pufferlib (absent); load the one file directly
     import importlib.util
@@ -324,3 +358,4 @@ if __name__ == "__main__":
     case_flags()
     case_running_norm()
     case_sample_time()
+    case_amp_obs()

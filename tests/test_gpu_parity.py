@@ -826,3 +826,22 @@ def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T):
     assert torch.equal(f.reset_buf, g.reset_buf) and torch.equal(f._terminate_buf, g._terminate_buf)
     assert torch.equal(f.progress_buf, g.progress_buf)
     torch.testing.assert_close(f.obs_moments, g.obs_moments, rtol=1e-12, atol=1e-9)
+
+
+def test_amp_observations_vs_reference_fixture(golden):
+    from humanoid_b200 import build_amp_observations_smpl, dof_subset_smpl
+
+    g = golden("amp_obs")
+    a = {k: cuda(g.inp(k)) for k in ("root_pos", "root_rot", "root_vel", "root_ang_vel", "dof_pos", "dof_vel",
+                                      "key_body_pos", "shape", "limb", "dof_subset")}  # fmt: skip
+    assert torch.equal(dof_subset_smpl(DEV), a["dof_subset"])
+    # the env hands the stride-2 view of the interleaved dof state (humanoid_phc.py:535-536)
+    n = a["dof_pos"].shape[0]
+    dof_state = torch.zeros(n, 69, 2, device=DEV)
+    dof_state[..., 0], dof_state[..., 1] = a["dof_pos"], a["dof_vel"]
+    for name in ("default", "all_dofs", "global_root_no_height", "not_upright_with_params"):
+        fl = [bool(x) for x in g.inp(f"flags.{name}")]
+        o = build_amp_observations_smpl(a["root_pos"], a["root_rot"], a["root_vel"], a["root_ang_vel"],
+                                        dof_state[..., 0], dof_state[..., 1], a["key_body_pos"], a["shape"], a["limb"],
+                                        a["dof_subset"], *fl)  # fmt: skip
+        assert_close(o, g.out(name), what=f"amp obs {name}", **OBS_TOL)

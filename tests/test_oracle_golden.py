@@ -136,3 +136,15 @@ def test_sample_time_interval_bit_exact(golden):
     assert torch.equal(t, g.out("motion_time"))
     k = t * 30
     assert float((k - k.round()).abs().max()) < 1e-3  # multiples of 1/30 s
+
+
+def test_amp_obs_variants(golden):
+    g = golden("amp_obs")
+    a = {k: g.inp(k) for k in ("root_pos", "root_rot", "root_vel", "root_ang_vel", "dof_pos", "dof_vel",
+                                "key_body_pos", "shape", "limb", "dof_subset")}  # fmt: skip
+    for name in ("default", "all_dofs", "global_root_no_height", "not_upright_with_params"):
+        fl = [bool(x) for x in g.inp(f"flags.{name}")]
+        o = O.amp_obs_smpl(a["root_pos"], a["root_rot"], a["root_vel"], a["root_ang_vel"], a["dof_pos"], a["dof_vel"],
+                           a["key_body_pos"], a["shape"], a["limb"], a["dof_subset"], *fl)  # fmt: skip
+        assert_close(o, g.out(name), what=f"amp obs {name}", **TIGHT)
+    assert g.out("default").shape[1] == 196

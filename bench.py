@@ -468,7 +468,7 @@ def main():
     ap.add_argument("--ring-mb", type=int, default=320, help="min size of the sim-state/obs buffer ring (> L2)")
     ap.add_argument("--repeats", type=int, default=5, help="timed graph replays; the median is reported")
     ap.add_argument("--e2e-steps", type=int, default=64)
-    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--e2e-chunks", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -154,76 +154,6 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
       !a->global_offset || !a->sampled_motion_ids || !a->obs_buf || !a->rew_buf || !a->reward_raw || !a->reset_buf ||
       !a->terminate_buf)
     return PHC_ERR_NULL;
-  {  // ---- direct path: every buffer is mapped host (or device) memory ----------------------
-    const void* ptrs[11] = {a->state, a->progress_buf, a->motion_start_times, a->motion_start_times_offset,
-                            a->global_offset, a->sampled_motion_ids, a->obs_buf, a->rew_buf, a->reward_raw,
-                            a->reset_buf, a->terminate_buf};
-    if (c->seen_direct < 0 || memcmp(ptrs, c->seen, sizeof(ptrs)) != 0) {
-      int direct = getenv("PHC_HOST_STAGED") ? 0 : 1;
-      for (int i = 0; i < 11 && direct; ++i) {
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess) {
-          (void)cudaGetLastError();
-          direct = 0;
-        } else if (at.type == cudaMemoryTypeUnregistered || at.devicePointer != ptrs[i]) {
-          direct = 0;  // pageable, or mapped at a different device address
-        }
-      }
-      memcpy(c->seen, ptrs, sizeof(ptrs));
-      c->seen_direct = direct;
-    }
-    if (c->seen_direct == 1) {
-      // Hybrid: sim state rides the host->device copy engine in a few chunks (SM-issued reads of
-      // system memory run at ~80 % of DMA rate and, measured, do not overlap SM-issued writes),
-      // while each chunk's kernel reads the tiny clock arrays and WRITES every output straight
-      // into the mapped host buffers.  The copy engine pulling chunk c+1 and the kernel pushing
-      // chunk c's obs rows use opposite directions of the link.
-      const int C = c->chunks < 1 ? 1 : c->chunks;
-      int64_t per = (n + C - 1) / C;
-      per = (per + 7) / 8 * 8;
-      int ci = 0;
-      for (int64_t lo = 0; lo < n; lo += per, ++ci) {
-        const int64_t m = (n - lo) < per ? (n - lo) : per;
-        cudaStream_t s = c->streams[ci % kStreams];
-        float* st = c->d_state + lo * kStateFloats;
-        HOST_CUDA(c, cudaMemcpyAsync(st, a->state + lo * kStateFloats, (size_t)m * kStateFloats * sizeof(float),
-                                     cudaMemcpyHostToDevice, s));
-        PhcStepArgs k{};
-        k.body.pos = PhcView{st, kStateFloats, 13};
-        k.body.rot = PhcView{st + 3, kStateFloats, 13};
-        k.body.vel = PhcView{st + 7, kStateFloats, 13};
-        k.body.ang_vel = PhcView{st + 10, kStateFloats, 13};
-        k.body.num_bodies = PHC_NUM_BODIES;
-        k.progress_buf = a->progress_buf + lo;
-        k.motion_start_times = a->motion_start_times + lo;
-        k.motion_start_times_offset = a->motion_start_times_offset + lo;
-        k.global_offset = a->global_offset + lo * 3;
-        k.sampled_motion_ids = a->sampled_motion_ids + lo;
-        k.termination_distances = c->term_dist;
-        k.reset_body_mask = c->reset_mask;
-        k.use_mean = c->use_mean;
-        k.enable_early_termination = c->early;
-        k.advance_progress = 1;
-        k.time_steps = c->T;
-        k.dt = c->dt;
-        k.rwd = c->rwd;
-        k.obs_buf = a->obs_buf + lo * c->obs_dim;
-        k.obs_stride = c->obs_dim;
-        k.rew_buf = a->rew_buf + lo;
-        k.reward_raw = a->reward_raw + lo * 4;
-        k.reward_raw_stride = 4;
-        k.reset_buf = a->reset_buf + lo;
-        k.terminate_buf = a->terminate_buf + lo;
-        k.flags = PHC_STEP_MAPPED_HOST_IO;
-        k.obs_moments = nullptr;
-        int rc = phc_step_fused(c->lib, &k, m, s);
-        if (rc) return rc;
-      }
-      for (int i = 0; i < kStreams && i < ci; ++i) HOST_CUDA(c, cudaStreamSynchronize(c->streams[i]));
-      return PHC_OK;
-    }
-  }
-  // ---- staged path ---------------------------------------------------------------------------
   // Chunk sizes double (n/2^(C-1), n/2^(C-1), n/2^(C-2), .., n/2): the device->host direction
   // carries 3x the bytes and is the bottleneck, so the first chunk is small to start it early
   // while the later, larger chunks keep the per-transfer overhead low.  Boundaries fall on
@@ -245,8 +175,6 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
     }
     bounds[nchunks] = n;
   }
-  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
-
   // sub-array offsets inside a chunk's packed regions (each 16-B aligned)
   struct Layout {
     size_t ids, goff, start, soff, prog, clock_bytes;
@@ -270,6 +198,95 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
     L.out_bytes = o;
     return L;
   };
+
+  {  // ---- direct path: every buffer is mapped host (or device) memory ----------------------
+    const void* ptrs[11] = {a->state, a->progress_buf, a->motion_start_times, a->motion_start_times_offset,
+                            a->global_offset, a->sampled_motion_ids, a->obs_buf, a->rew_buf, a->reward_raw,
+                            a->reset_buf, a->terminate_buf};
+    if (c->seen_direct < 0 || memcmp(ptrs, c->seen, sizeof(ptrs)) != 0) {
+      int direct = getenv("PHC_HOST_STAGED") ? 0 : 1;
+      for (int i = 0; i < 11 && direct; ++i) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess) {
+          (void)cudaGetLastError();
+          direct = 0;
+        } else if (at.type == cudaMemoryTypeUnregistered || at.devicePointer != ptrs[i]) {
+          direct = 0;  // pageable, or mapped at a different device address
+        }
+      }
+      memcpy(c->seen, ptrs, sizeof(ptrs));
+      c->seen_direct = direct;
+    }
+    if (c->seen_direct == 1) {
+      // Hybrid: everything INBOUND rides the host->device copy engine in a few chunks — the sim
+      // rows directly from the caller's buffer, the five small clock arrays packed into one
+      // transfer (SM-issued reads of system memory are 32-B PCIe round trips: 6 per block, ~70 us
+      // per 4096-env step when the kernel read the clock in place) — while each chunk's kernel
+      // WRITES obs rows, rewards and flags straight into the mapped host buffers.  The copy
+      // engine pulling chunk c+1 and the kernel pushing chunk c's rows use opposite directions of
+      // the link.  The advanced progress returns with one 2-byte-per-env copy per chunk.
+      // equal chunks here: measured, a small first chunk does not help this path (the step is
+      // bound by the kernels' posted writes, ~300 us per 4096 envs, plus the first copy)
+      const int C = c->chunks < 1 ? 1 : c->chunks;
+      int64_t per = (n + C - 1) / C;
+      per = (per + 7) / 8 * 8;
+      size_t coff = 0;
+      int ci = 0;
+      for (int64_t lo = 0; lo < n; lo += per, ++ci) {
+        const int64_t m = (n - lo) < per ? (n - lo) : per;
+        const Layout L = layout(m);
+        if (coff + L.clock_bytes > c->pack_capacity) return PHC_ERR_SHAPE;
+        cudaStream_t s = c->streams[ci % kStreams];
+        float* st = c->d_state + lo * kStateFloats;
+        unsigned char* hc = c->h_clock + coff;
+        unsigned char* dc = c->d_clock + coff;
+        memcpy(hc + L.ids, a->sampled_motion_ids + lo, (size_t)m * 8);
+        memcpy(hc + L.goff, a->global_offset + lo * 3, (size_t)m * 12);
+        memcpy(hc + L.start, a->motion_start_times + lo, (size_t)m * 4);
+        memcpy(hc + L.soff, a->motion_start_times_offset + lo, (size_t)m * 4);
+        memcpy(hc + L.prog, a->progress_buf + lo, (size_t)m * 2);
+        HOST_CUDA(c, cudaMemcpyAsync(dc, hc, L.clock_bytes, cudaMemcpyHostToDevice, s));
+        HOST_CUDA(c, cudaMemcpyAsync(st, a->state + lo * kStateFloats, (size_t)m * kStateFloats * sizeof(float),
+                                     cudaMemcpyHostToDevice, s));
+        PhcStepArgs k{};
+        k.body.pos = PhcView{st, kStateFloats, 13};
+        k.body.rot = PhcView{st + 3, kStateFloats, 13};
+        k.body.vel = PhcView{st + 7, kStateFloats, 13};
+        k.body.ang_vel = PhcView{st + 10, kStateFloats, 13};
+        k.body.num_bodies = PHC_NUM_BODIES;
+        k.progress_buf = (int16_t*)(dc + L.prog);
+        k.motion_start_times = (const float*)(dc + L.start);
+        k.motion_start_times_offset = (const float*)(dc + L.soff);
+        k.global_offset = (const float*)(dc + L.goff);
+        k.sampled_motion_ids = (const int64_t*)(dc + L.ids);
+        k.termination_distances = c->term_dist;
+        k.reset_body_mask = c->reset_mask;
+        k.use_mean = c->use_mean;
+        k.enable_early_termination = c->early;
+        k.advance_progress = 1;
+        k.time_steps = c->T;
+        k.dt = c->dt;
+        k.rwd = c->rwd;
+        k.obs_buf = a->obs_buf + lo * c->obs_dim;
+        k.obs_stride = c->obs_dim;
+        k.rew_buf = a->rew_buf + lo;
+        k.reward_raw = a->reward_raw + lo * 4;
+        k.reward_raw_stride = 4;
+        k.reset_buf = a->reset_buf + lo;
+        k.terminate_buf = a->terminate_buf + lo;
+        k.flags = PHC_STEP_MAPPED_HOST_IO;
+        k.obs_moments = nullptr;
+        int rc = phc_step_fused(c->lib, &k, m, s);
+        if (rc) return rc;
+        HOST_CUDA(c, cudaMemcpyAsync(a->progress_buf + lo, dc + L.prog, (size_t)m * 2, cudaMemcpyDeviceToHost, s));
+        coff += L.clock_bytes;
+      }
+      for (int i = 0; i < kStreams; ++i) HOST_CUDA(c, cudaStreamSynchronize(c->streams[i]));
+      return PHC_OK;
+    }
+  }
+  // ---- staged path ---------------------------------------------------------------------------
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
 
   size_t coff = 0, ooff = 0;
   for (int ci = 0; ci < nchunks; ++ci) {

@@ -34,12 +34,6 @@ OBS_LOCAL_ROOT = 1
 OBS_ROOT_HEIGHT = 2
 OBS_UPRIGHT = 4
 
-c_f32p = C.POINTER(C.c_float)
-c_i64p = C.POINTER(C.c_int64)
-c_i16p = C.POINTER(C.c_int16)
-c_u8p = C.POINTER(C.c_uint8)
-c_f64p = C.POINTER(C.c_double)
-
 
 class PhcLibDesc(C.Structure):
     _fields_ = [

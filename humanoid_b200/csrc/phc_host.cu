@@ -37,11 +37,6 @@ constexpr size_t kOutBytes = 4 + 16 + 2 + 1 + 1;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct Chunk {
-  int64_t lo = 0, m = 0;
-  size_t clock_off = 0, out_off = 0;  // byte offsets into the packed staging buffers
-};
-
 }  // namespace
 
 struct PhcHostStep {

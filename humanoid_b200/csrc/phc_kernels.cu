@@ -952,13 +952,14 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
 // K6-fast: the fused step for T == 1 on the AoS sim tensor with a dense obs_buf — the
 // configuration the env runs (humanoid_phc.py:1100) and the benchmark measures.
 //
-//   * all bulk data movement is TMA: warp 0 runs the clock + frame-blend for (env, t) and
-//     (env, t+dt) on 2*EPB lanes, then each lane issues cp.async.bulk copies of its env's sim
-//     row (1248 B) and of the packed frame rows it needs (1248 B each, see pack_frames_kernel)
-//     straight into shared memory, completing on one mbarrier.  Frames shared between
-//     t and t+dt (the usual case: idx1(t) == idx0(t+dt)) are fetched once.
+//   * launched with programmatic stream serialization; before griddepcontrol.wait warp 0 only
+//     speculates on immutable data (frame blends for the candidate progress values, frames copied
+//     into shared memory by TMA); after the wait it re-reads the clock, validates, fetches the
+//     sim rows and selects (see "phase 0" in the kernel);
+//   * all bulk data movement is TMA (cp.async.bulk, SASS UBLKCP) completing on one mbarrier: one
+//     copy for the block's sim rows, one per env for its span of packed frame rows;
 //   * 24 threads per env do the per-body math out of shared memory; reward means and the
-//     termination test are reduced by warp 0 in ATen's summation order.
+//     termination test are reduced by warp 0 in ATen's summation order, after the store;
 //   * the 934-float obs rows of the block are assembled in shared memory (aliasing the frame
 //     buffer) and leave with ONE cp.async.bulk shared->global store.
 // ---------------------------------------------------------------------------------------
@@ -975,10 +976,6 @@ struct FastSmem {
   int prog[EPB], pass[EPB], fallen[EPB];
   int parity;  // phase of `bar` the consumers wait for
 };
-
-__device__ __forceinline__ void bulk_load_frame(const LibDev& L, float* dst, int64_t f, unsigned long long* bar) {
-  bulk_g2s(dst, L.packed + f * FRAME_FLOATS, FRAME_FLOATS * 4, bar);
-}
 
 __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, float bl, const float* goff, int b) {
   const float om = 1.0f - bl;

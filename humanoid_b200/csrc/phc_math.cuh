@@ -254,7 +254,6 @@ __device__ __forceinline__ Quat quat_slerp(Quat q0, Quat q1, float t) {
 }
 
 // lerp of get_motion_state, motion_lib.py:597-603: (1 - b)*x0 + b*x1
-__device__ __forceinline__ float lerp1(float om, float b, float x0, float x1) { return om * x0 + b * x1; }
 __device__ __forceinline__ Vec3 lerp3(float om, float b, Vec3 x0, Vec3 x1) {
   return {om * x0.x + b * x1.x, om * x0.y + b * x1.y, om * x0.z + b * x1.z};
 }

@@ -68,3 +68,19 @@ for k, t in enumerate(T):
             print(f"    warp0 {names[j]:14s} (rel. prev exit): min {col.min():6.2f}  median {np.median(col):6.2f}  "
                   f"p90 {np.percentile(col, 90):6.2f}  max {col.max():6.2f}")
     prev_end, prev_last = last, last
+
+# straggler analysis of the last kernel: who exits late, and why
+t = (T[-1] - t00) / 1e3
+w0 = t[:, 0, :]
+last_prev = ((T[-2] - t00) / 1e3)[:, :, 7].max()
+exit_rel = t[:, :, 7].max(axis=1) - last_prev
+post = w0[:, 1] - w0[:, 2]  # dependency resolved -> TMA issued (clock loads, validation, redo)
+land = w0[:, 3] - w0[:, 1]  # TMA issued -> data landed
+entry_rel = w0[:, 0] - last_prev
+print("\nlatest-exiting blocks of the last kernel (us relative to the previous kernel's last exit):")
+for i in np.argsort(-exit_rel)[:10]:
+    print(f"  block {i:5d}: entry {entry_rel[i]:6.2f}  wait->issued {post[i]:5.2f}  issued->landed {land[i]:5.2f}  "
+          f"phase1 {w0[i, 4] - w0[i, 3]:5.2f}  phase2 {w0[i, 5] - w0[i, 4]:5.2f}  exit {exit_rel[i]:5.2f}")
+for name, arr in (("wait->issued", post), ("issued->landed", land), ("exit", exit_rel)):
+    qs = np.percentile(arr, [50, 90, 99, 100])
+    print(f"  {name:15s}: p50 {qs[0]:5.2f}  p90 {qs[1]:5.2f}  p99 {qs[2]:5.2f}  max {qs[3]:5.2f}")

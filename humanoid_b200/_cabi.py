@@ -192,6 +192,11 @@ SIGNATURES = {
         [C.POINTER(PhcView), C.POINTER(PhcView), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     ),  # fmt: skip
+    "phc_action_to_pd_targets": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32,
+         C.c_int64, C.c_int32, C.c_void_p, C.c_void_p],
+    ),  # fmt: skip
     "phc_step_fused": (C.c_int, [C.c_void_p, C.POINTER(PhcStepArgs), C.c_int64, C.c_void_p]),
     "phc_reset_envs": (C.c_int, [C.c_void_p, C.POINTER(PhcResetArgs), C.c_int64, C.c_void_p]),
     "phc_set_option": (C.c_int, [C.c_int, C.c_int]),

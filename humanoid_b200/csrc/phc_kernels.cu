@@ -488,6 +488,31 @@ __global__ void reset_kernel(PhcView pos, PhcView ref, int R, const int16_t* __r
 }
 
 // ---------------------------------------------------------------------------------------
+// _action_to_pd_targets (humanoid_phc.py:1218-1228) + the freeze_hand / freeze_toe zeroing of
+// step() (:118-127); one thread per (env, dof)
+// ---------------------------------------------------------------------------------------
+__global__ void pd_targets_kernel(const float* __restrict__ action, const float* __restrict__ offset,
+                                  const float* __restrict__ scale, int res_action, const float* __restrict__ ref_dof_pos,
+                                  const float* __restrict__ dof_pos, int64_t dp_stride, int64_t dp_estride,
+                                  uint32_t zero_mask, int64_t n, int D, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * D) return;
+  const int64_t env = i / D;
+  const int d = (int)(i - env * D);
+  float pd;
+  if (res_action) {
+    pd = ref_dof_pos[i] + scale[d] * action[i];
+    const float q = dof_pos[env * dp_stride + d * dp_estride];
+    const float half_pi = 1.57079637050628662f;  // f32(np.pi / 2)
+    pd = fmaxf(fminf(pd, q + half_pi), q - half_pi);  // maximum(minimum(pd, upper), lower)
+  } else {
+    pd = offset[d] + scale[d] * action[i];
+  }
+  if (zero_mask >> (d / 3) & 1u) pd = 0.0f;
+  out[i] = pd;
+}
+
+// ---------------------------------------------------------------------------------------
 // K7: reference-state-init reset of the envs selected by a mask (humanoid_phc.py:665-778).
 // One thread per (env, body).  _sample_ref_state -> get_motion_state (full: local rotations ->
 // dof_pos, dof velocities) -> _set_env_state scatter -> clock / buffer resets.  The observation
@@ -1970,6 +1995,21 @@ static void init_options() {
     const char* w = getenv("PHC_STEP_PDL");
     g_pdl = (w && w[0] == '0') ? 0 : 1;
   }
+}
+
+int phc_action_to_pd_targets(const float* action, const float* pd_action_offset, const float* pd_action_scale,
+                             int32_t res_action, const float* ref_dof_pos, const float* dof_pos,
+                             int64_t dof_pos_stride, int64_t dof_pos_elem_stride, uint32_t zero_mask, int64_t n,
+                             int32_t num_dof, float* out, phc_stream_t stream) {
+  if (n == 0) return PHC_OK;
+  if (n < 0 || num_dof < 1 || num_dof > 96) return PHC_ERR_SHAPE;
+  if (!action || !pd_action_scale || !out) return PHC_ERR_NULL;
+  if (res_action ? (!ref_dof_pos || !dof_pos) : !pd_action_offset) return PHC_ERR_NULL;
+  const int64_t total = n * num_dof;
+  pd_targets_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(action, pd_action_offset, pd_action_scale,
+                                                                         res_action, ref_dof_pos, dof_pos, dof_pos_stride,
+                                                                         dof_pos_elem_stride, zero_mask, n, num_dof, out);
+  return launch_status();
 }
 
 int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* a, int64_t n, phc_stream_t stream) {

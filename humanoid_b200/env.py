@@ -95,6 +95,8 @@ class HumanoidPHC:
         self._dof_pos = self._dof_state.view(N, self.num_dof, 2)[..., : self.num_dof, 0]
         self._dof_vel = self._dof_state.view(N, self.num_dof, 2)[..., : self.num_dof, 1]
         self.dof_force_tensor = torch.zeros((N, self.num_dof), dtype=torch.float32, device=dev)
+        self._pd_action_offset = torch.zeros(self.num_dof, dtype=torch.float32, device=dev)  # :436-451
+        self._pd_action_scale = torch.ones(self.num_dof, dtype=torch.float32, device=dev)
 
         # env buffers (humanoid_phc.py:556-597)
         self.num_obs = _cabi.SELF_OBS_DIM + _cabi.TASK_OBS_DIM * self.time_steps  # :461-467
@@ -256,6 +258,36 @@ class HumanoidPHC:
         self.extras["terminate"] = self._terminate_buf
         self.extras["reward_raw"] = self.reward_raw
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # ------------------------------------------------------------------------------------
+    # pre-physics: actions -> PD targets (humanoid_phc.py:105-128, 1218-1228)
+    # ------------------------------------------------------------------------------------
+    def _action_to_pd_targets(self, action: torch.Tensor, res_action: bool = False, ref_dof_pos=None,
+                              freeze_hand: bool = False, freeze_toe: bool = False) -> torch.Tensor:  # fmt: skip
+        """``pd_action_offset + pd_action_scale * action`` (or the clamped residual form), with the
+        hand / toe joints zeroed as ``step()`` does when ``freeze_hand`` / ``freeze_toe`` are set.
+        ``self._pd_action_offset`` / ``_pd_action_scale`` are [69] tensors the owner fills
+        (built from the asset's joint limits in the reference, :385-451)."""
+        _cabi.require_cuda(action, "action", torch.float32)
+        action = action.contiguous()
+        n, D = action.shape
+        out = torch.empty_like(action)
+        dof_names = BODY_NAMES[1:]
+        mask = 0
+        if freeze_hand:
+            mask |= (1 << dof_names.index("L_Hand")) | (1 << dof_names.index("R_Hand"))
+        if freeze_toe:
+            mask |= (1 << dof_names.index("L_Toe")) | (1 << dof_names.index("R_Toe"))
+        ref = ref_dof_pos.contiguous() if res_action else None
+        _cabi.check(
+            _cabi.load().phc_action_to_pd_targets(
+                action.data_ptr(), self._pd_action_offset.data_ptr(), self._pd_action_scale.data_ptr(),
+                1 if res_action else 0, _cabi.ptr(ref), self._dof_pos.data_ptr(), self._dof_pos.stride(0),
+                self._dof_pos.stride(1), mask, n, D, out.data_ptr(), _cabi.stream_ptr(self.device),
+            ),
+            "phc_action_to_pd_targets",
+        )  # fmt: skip
+        return out
 
     # ------------------------------------------------------------------------------------
     # reset (humanoid_phc.py:90-103, 665-778) — on the device, no host sync

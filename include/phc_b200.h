@@ -307,6 +307,17 @@ PHC_API int phc_set_option(int key, int value);
  * the buffer until it is full.  NULL switches it off. */
 PHC_API int phc_set_trace_buffer(uint64_t* device_buf, int64_t capacity_warps);
 
+/* HumanoidPHC._action_to_pd_targets(action)                      envs/humanoid_phc.py:1218-1228
+ *   res_action == 0:  pd = pd_action_offset + pd_action_scale * action
+ *   res_action != 0:  pd = clamp(ref_dof_pos + pd_action_scale * action, dof_pos -+ pi/2)
+ * offset / scale are [D]; action, ref_dof_pos, out are dense [n, D]; dof_pos is the strided view
+ * of the dof state.  The freeze_hand / freeze_toe zeroing of step() (:118-127) is `zero_mask`:
+ * bit j set = the 3 dofs of joint j are written as 0. */
+PHC_API int phc_action_to_pd_targets(const float* action, const float* pd_action_offset, const float* pd_action_scale,
+                                     int32_t res_action, const float* ref_dof_pos, const float* dof_pos,
+                                     int64_t dof_pos_stride, int64_t dof_pos_elem_stride, uint32_t zero_mask,
+                                     int64_t n, int32_t num_dof, float* out, phc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Host-buffer pipeline around the fused step (the end-to-end call): chunked
  * H2D(sim state, clock) -> phc_step_fused -> D2H(obs, reward, flags) on internal streams.

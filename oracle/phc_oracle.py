@@ -555,6 +555,27 @@ def step(
 
 
 # ----------------------------------------------------------------------------------
+# actions -> PD targets — envs/humanoid_phc.py:105-128, 1218-1228
+# ----------------------------------------------------------------------------------
+
+
+def action_to_pd_targets(action, offset, scale, res_action=False, ref_dof_pos=None, dof_pos=None,
+                         zero_joints=()):  # fmt: skip
+    """_action_to_pd_targets (:1218-1228) followed by step()'s freeze_hand / freeze_toe zeroing
+    (:118-127); ``zero_joints`` are indices into DOF_NAMES."""
+    import numpy as np
+
+    if res_action:
+        pd = ref_dof_pos + scale * action
+        pd = torch.maximum(torch.minimum(pd, dof_pos + np.pi / 2), dof_pos - np.pi / 2)
+    else:
+        pd = offset + scale * action
+    for j in zero_joints:
+        pd[:, 3 * j : 3 * j + 3] = 0
+    return pd
+
+
+# ----------------------------------------------------------------------------------
 # reset — envs/humanoid_phc.py:665-778, motion_lib.py:526-535
 # ----------------------------------------------------------------------------------
 

@@ -845,3 +845,23 @@ def test_amp_observations_vs_reference_fixture(golden):
                                         dof_state[..., 0], dof_state[..., 1], a["key_body_pos"], a["shape"], a["limb"],
                                         a["dof_subset"], *fl)  # fmt: skip
         assert_close(o, g.out(name), what=f"amp obs {name}", **OBS_TOL)
+
+
+@pytest.mark.parametrize("res_action", [False, True])
+def test_action_to_pd_targets_bit_exact(res_action):
+    from humanoid_b200 import HumanoidPHC
+
+    lib = MotionLib(synth.make_motion_lib(4, 6, 9), device=DEV)
+    n = 777
+    env = HumanoidPHC(lib, n, device=DEV)
+    g = torch.Generator().manual_seed(6)
+    act = torch.randn(n, 69, generator=g).clamp(-1, 1)
+    off, sc = torch.randn(69, generator=g), torch.rand(69, generator=g) * 3
+    refp, dofp = torch.randn(n, 69, generator=g), torch.randn(n, 69, generator=g)
+    env._pd_action_offset.copy_(off)
+    env._pd_action_scale.copy_(sc)
+    env._dof_pos.copy_(dofp)
+    got = env._action_to_pd_targets(cuda(act), res_action=res_action, ref_dof_pos=cuda(refp), freeze_hand=True, freeze_toe=True)
+    want = O.action_to_pd_targets(act, off, sc, res_action, refp, dofp, zero_joints=(3, 7, 17, 22))
+    assert torch.equal(got.cpu(), want)  # one multiply, one add, min/max: no room for rounding differences
+    assert float(got[:, 9:12].abs().sum()) == 0.0 and float(got[:, 66:69].abs().sum()) == 0.0

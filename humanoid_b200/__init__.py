@@ -18,12 +18,14 @@ from .common import (  # noqa: F401
 )
 from .env import HumanoidPHC  # noqa: F401
 from .motion_lib import MotionLib  # noqa: F401
+from .puffer_env import PHCPufferEnv  # noqa: F401
 from .running_norm import RunningNorm  # noqa: F401
 
 __all__ = [
     "MotionLib",
     "HumanoidPHC",
     "RunningNorm",
+    "PHCPufferEnv",
     "compute_humanoid_observations_smpl_max",
     "compute_imitation_observations_v6",
     "compute_imitation_observations_v7",

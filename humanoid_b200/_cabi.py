@@ -146,6 +146,26 @@ class PhcResetArgs(C.Structure):
     ]
 
 
+class PhcEpisodeArgs(C.Structure):
+    _fields_ = [
+        ("reset", C.c_void_p),
+        ("terminate", C.c_void_p),
+        ("rewards", C.c_void_p),
+        ("reward_raw", C.c_void_p),
+        ("reward_raw_stride", C.c_int64),
+        ("reward_raw_cols", C.c_int32),
+        ("_pad0", C.c_int32),
+        ("terminals", C.c_void_p),
+        ("truncations", C.c_void_p),
+        ("masks", C.c_void_p),
+        ("episode_returns", C.c_void_p),
+        ("episode_lengths", C.c_void_p),
+        ("stats", C.c_void_p),
+        ("raw_rewards", C.c_void_p),
+        ("workspace", C.c_void_p),
+    ]
+
+
 class PhcHostStepArgs(C.Structure):
     _fields_ = [
         (k, C.c_void_p)
@@ -220,6 +240,7 @@ SIGNATURES = {
         [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p,
          C.c_int64, C.c_void_p],
     ),  # fmt: skip
+    "phc_episode_update": (C.c_int, [C.POINTER(PhcEpisodeArgs), C.c_int64, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -8,6 +8,7 @@
 // summation order, so the result does not depend on how envs fall on warps.
 //
 // Compiled with -fmad=false (see phc_math.cuh).
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -1682,6 +1683,95 @@ __global__ void running_norm_forward_kernel(const float* __restrict__ x, int64_t
   out[r * out_stride + c] = fminf(fmaxf(v, -clip), clip);
 }
 
+// -----------------------------------------------------------------------------------------
+// K10  episode bookkeeping of the pufferlib wrapper (clean_pufferl/env.py:121-159): one thread
+//      per env, ~15 B/env; finished-episode sums and the reward_raw column sums are reduced per
+//      block in fp64 and added to a small workspace, the last block folds them into the caller's
+//      accumulators and leaves the workspace zero for the next launch.
+// -----------------------------------------------------------------------------------------
+constexpr int EP_MAX_RAW = 8;
+static_assert(PHC_EPISODE_WORKSPACE_DOUBLES >= 13, "workspace layout");  // [0..3] stats, [4..11] reward_raw column sums, [12] block ticket
+struct EpisodeParams {
+  const uint8_t* reset;
+  const uint8_t* terminate;
+  const float* rewards;
+  const float* reward_raw;
+  int64_t raw_stride;
+  int raw_cols;
+  int64_t n;
+  uint8_t* terminals;
+  uint8_t* truncations;
+  uint8_t* masks;
+  float* episode_returns;
+  int32_t* episode_lengths;
+  double* stats;
+  float* raw_rewards;
+  double* ws;
+};
+
+__global__ void __launch_bounds__(256) episode_update_kernel(EpisodeParams p) {
+  double acc[4 + EP_MAX_RAW];
+#pragma unroll
+  for (int i = 0; i < 4 + EP_MAX_RAW; ++i) acc[i] = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += (int64_t)gridDim.x * blockDim.x) {
+    const bool rs = p.reset[e] != 0, tm = p.terminate[e] != 0;
+    const bool tr = rs && !tm;
+    p.terminals[e] = tm ? 1 : 0;
+    p.truncations[e] = tr ? 1 : 0;
+    p.masks[e] = tr ? 0 : 1;
+    float ret = p.episode_returns[e];
+    int32_t len = p.episode_lengths[e];
+    if (rs) {
+      acc[0] += 1.0;
+      acc[1] += (double)ret;
+      acc[2] += (double)len;
+      acc[3] += tr ? 1.0 : 0.0;
+      ret = 0.0f;
+      len = 0;
+    }
+    p.episode_returns[e] = ret + p.rewards[e];
+    p.episode_lengths[e] = len + 1;
+#pragma unroll
+    for (int c = 0; c < EP_MAX_RAW; ++c)
+      if (c < p.raw_cols) acc[4 + c] += (double)p.reward_raw[e * p.raw_stride + c];
+  }
+  __shared__ double part[8][4 + EP_MAX_RAW];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4 + EP_MAX_RAW; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) part[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 + p.raw_cols) {
+    const int i = threadIdx.x;
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[w][i];
+    if (v != 0.0) atomicAdd(&p.ws[i], v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(&p.ws[12]), 1ull);
+    last = (t == (unsigned long long)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 4) {
+    p.stats[threadIdx.x] += __ldcg(&p.ws[threadIdx.x]);
+    p.ws[threadIdx.x] = 0.0;
+  } else if (threadIdx.x < 4 + p.raw_cols) {
+    const int c = threadIdx.x - 4;
+    p.raw_rewards[c] += (float)(__ldcg(&p.ws[threadIdx.x]) / (double)p.n);
+    p.ws[threadIdx.x] = 0.0;
+  }
+  if (threadIdx.x == 32) *reinterpret_cast<unsigned long long*>(&p.ws[12]) = 0ull;
+}
+
 }  // namespace phc
 
 // =========================================================================================
@@ -2193,6 +2283,36 @@ int phc_running_norm_forward(const float* x, int64_t rows, int64_t cols, int64_t
   dim3 grid((unsigned)rows, (unsigned)((cols + 127) / 128));
   running_norm_forward_kernel<<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, running_mean, running_var, epsilon,
                                                         clip, out, out_stride);
+  return launch_status();
+}
+
+int phc_episode_update(const PhcEpisodeArgs* a, int64_t n, phc_stream_t stream) {
+  if (!a) return PHC_ERR_NULL;
+  if (n == 0) return PHC_OK;
+  if (n < 0 || a->reward_raw_cols < 0 || a->reward_raw_cols > EP_MAX_RAW) return PHC_ERR_SHAPE;
+  if (a->reward_raw_cols > 0 && (!a->reward_raw || !a->raw_rewards || a->reward_raw_stride < a->reward_raw_cols))
+    return a->reward_raw && a->raw_rewards ? PHC_ERR_SHAPE : PHC_ERR_NULL;
+  if (!a->reset || !a->terminate || !a->rewards || !a->terminals || !a->truncations || !a->masks ||
+      !a->episode_returns || !a->episode_lengths || !a->stats || !a->workspace)
+    return PHC_ERR_NULL;
+  EpisodeParams p;
+  p.reset = a->reset;
+  p.terminate = a->terminate;
+  p.rewards = a->rewards;
+  p.reward_raw = a->reward_raw;
+  p.raw_stride = a->reward_raw_stride;
+  p.raw_cols = a->reward_raw_cols;
+  p.n = n;
+  p.terminals = a->terminals;
+  p.truncations = a->truncations;
+  p.masks = a->masks;
+  p.episode_returns = a->episode_returns;
+  p.episode_lengths = a->episode_lengths;
+  p.stats = a->stats;
+  p.raw_rewards = a->raw_rewards;
+  p.ws = a->workspace;
+  const int64_t blocks = std::min<int64_t>((n + 255) / 256, 148 * 4);
+  episode_update_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
   return launch_status();
 }
 

@@ -365,6 +365,37 @@ PHC_API int phc_running_norm_forward(const float* x, int64_t rows, int64_t cols,
                              const float* running_mean, const float* running_var, float epsilon,
                              float clip, float* out, int64_t out_stride, phc_stream_t stream);
 
+/* Per-env episode bookkeeping of the pufferlib wrapper, PHCPufferEnv.step   clean_pufferl/env.py:121-159
+ *   raw_rewards += mean_env(reward_raw)                                           (:124)
+ *   terminals = terminate;  truncations = reset & ~terminate;  masks = ~truncations   (:130-154)
+ *   for reset envs: stats += {1, episode_return, episode_length, truncated};  return = length = 0  (:136-140)
+ *   then EVERY env: episode_return += reward;  episode_length += 1   (:158-159 — env.reset() has already
+ *   cleared reset_buf there, humanoid_phc.py:778, so the mask is all-true)
+ * `reset` is reset_buf as the step left it (before the reset), `terminate` is extras["terminate"].
+ * `stats` replaces the three Python lists mean_and_log (:191-204) averages, so no host sync is
+ * needed per step: {episodes finished, sum of returns, sum of lengths, truncations} in fp64.
+ * `workspace` is PHC_EPISODE_WORKSPACE_DOUBLES doubles, zeroed once by the caller; every launch
+ * leaves it zero.  Flags are bytes (torch.bool). */
+#define PHC_EPISODE_WORKSPACE_DOUBLES 16
+typedef struct PhcEpisodeArgs {
+  const uint8_t* reset;       /* [n] */
+  const uint8_t* terminate;   /* [n] */
+  const float* rewards;       /* [n] rew_buf */
+  const float* reward_raw;    /* [n, reward_raw_cols] rows `reward_raw_stride` floats apart, or NULL when cols == 0 */
+  int64_t reward_raw_stride;
+  int32_t reward_raw_cols;    /* <= 8 (the reference logs 5) */
+  int32_t _pad0;
+  uint8_t* terminals;         /* [n] out */
+  uint8_t* truncations;       /* [n] out */
+  uint8_t* masks;             /* [n] out */
+  float* episode_returns;     /* [n] in/out */
+  int32_t* episode_lengths;   /* [n] in/out */
+  double* stats;              /* [4] accumulated */
+  float* raw_rewards;         /* [reward_raw_cols] accumulated */
+  double* workspace;          /* [PHC_EPISODE_WORKSPACE_DOUBLES] */
+} PhcEpisodeArgs;
+PHC_API int phc_episode_update(const PhcEpisodeArgs* args, int64_t n, phc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

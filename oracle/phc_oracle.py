@@ -683,3 +683,38 @@ def running_norm_update(running_mean, running_var, count, x):
 def running_norm_forward(running_mean, running_var, x, epsilon=1e-5, clip=10.0):
     """RunningNorm.forward, policies/running_norm.py:15-20."""
     return torch.clamp((x - running_mean.expand_as(x)) / torch.sqrt(running_var.expand_as(x) + epsilon), -clip, clip)
+
+
+# ----------------------------------------------------------------------------------------
+# episode bookkeeping of the pufferlib wrapper — clean_pufferl/env.py
+# ----------------------------------------------------------------------------------------
+def episode_update(state: Dict[str, Tensor], reset: Tensor, terminate: Tensor, rewards: Tensor, reward_raw: Tensor):
+    """The per-env part of PHCPufferEnv.step, clean_pufferl/env.py:121-159, in place on ``state``.
+
+    ``state`` holds ``terminals, truncations, masks`` (bool [n]), ``episode_returns`` (f32 [n]),
+    ``episode_lengths`` (i32 [n]), ``raw_rewards`` (f32 [5]) and ``stats`` (f64 [4] = finished
+    episodes, sum of their returns, sum of their lengths, how many were truncations: the running
+    sums behind the three lists ``mean_and_log`` (:191-204) averages).  ``reset`` is ``reset_buf``
+    as ``HumanoidPHC.step`` left it, i.e. before ``env.reset(reset_indices)`` clears it (:133-135,
+    humanoid_phc.py:778); ``terminate`` is ``extras["terminate"]``.
+
+    Reference order, kept: finished episodes are logged and zeroed first (:137-140); then, because
+    ``env.reset`` has already cleared ``reset_buf``, ``~reset_buf`` is all-true at :158-159 and EVERY
+    env — the just-reset ones too — accumulates this step's reward and one step of length."""
+    reset = reset.bool()
+    terminate = terminate.bool()
+    state["raw_rewards"] += reward_raw.mean(dim=0)  # :124
+    state["terminals"][:] = terminate  # :130,145-146 (terminated envs are always reset envs)
+    trunc = reset & ~terminate  # :149-150
+    state["truncations"][:] = trunc
+    state["masks"][:] = ~trunc  # :132,154
+    st = state["stats"]
+    st[0] += reset.sum().double()
+    st[1] += state["episode_returns"][reset].double().sum()
+    st[2] += state["episode_lengths"][reset].double().sum()
+    st[3] += trunc.sum().double()
+    state["episode_returns"][reset] = 0  # :139-140
+    state["episode_lengths"][reset] = 0
+    state["episode_returns"] += rewards  # :158-159
+    state["episode_lengths"] += 1
+    return state

@@ -93,3 +93,36 @@ def assert_equal_exact(actual, expected, what=""):
     if not torch.equal(a.to(e.dtype), e):
         diff = (a.to(torch.int64) != e.to(torch.int64)).nonzero().flatten()[:8].tolist()
         raise AssertionError(f"{what}: {int((a.to(torch.int64) != e.to(torch.int64)).sum())} mismatches, first at {diff}")
+
+
+def replay_episode_golden(g, new_state, update, read=lambda t: t):
+    """Drive an episode-bookkeeping implementation through tests/golden/episode.npz (recorded from
+    the reference's PHCPufferEnv.step) and compare after every step.  ``new_state(n, cols)`` makes the
+    state dict of oracle.episode_update's layout, ``update(state, reset, terminate, rewards, raw)``
+    applies one step in place, ``read`` brings a state tensor to the CPU."""
+    rewards, raw = g.inp("rewards"), g.inp("reward_raw")
+    reset, terminate = g.inp("reset"), g.inp("terminate")
+    log = int(g.inp("log_interval"))
+    infos = {int(r[0]): r[1:] for r in g.out("infos").tolist()}
+    K, N = rewards.shape
+    st = new_state(N, raw.shape[-1])
+    count = 0
+    for k in range(K):
+        update(st, reset[k], terminate[k], rewards[k], raw[k])
+        for key in ("terminals", "truncations", "masks", "episode_lengths"):
+            assert_equal_exact(read(st[key]).to(g.out(key).dtype), g.out(key)[k], what=f"{key}[{k}]")
+        # one fp32 add per env per step in the reference's order: bit-exact
+        assert_equal_exact(read(st["episode_returns"]), g.out("episode_returns")[k], what=f"episode_returns[{k}]")
+        if (k + 1) % log == 0:  # clean_pufferl/env.py:162-176
+            s = read(st["stats"]).tolist()
+            want = infos[k]
+            got = [s[1] / s[0], s[2] / s[0], s[3] / s[0]] + (read(st["raw_rewards"]).double() / log).tolist()
+            assert_close(torch.tensor(got), torch.tensor(want), rtol=1e-6, atol=1e-7, what=f"info[{k}]")
+            count += int(s[0])
+            st["stats"].zero_()
+            st["raw_rewards"].zero_()
+        else:
+            assert_close(read(st["raw_rewards"]), g.out("raw_rewards")[k], rtol=1e-6, atol=1e-7, what=f"raw[{k}]")
+        partial = 0 if (k + 1) % log == 0 else int(read(st["stats"])[0])
+        assert count + partial == int(g.out("episode_count")[k]), f"episode_count[{k}]"
+    assert len(infos) == K // log

@@ -338,9 +338,105 @@ def case_running_norm():
     save("running_norm", arrays)
 
 
+def case_episode():
+    """PHCPufferEnv.step's per-env episode bookkeeping (clean_pufferl/env.py:109-183), run
+    unmodified on a scripted stand-in for HumanoidPHC (isaacgym / pufferlib are absent: both
+    imports are stubbed, the bookkeeping code itself is the reference's)."""
+    import importlib.util
+    import types
+
+    for name, attrs in (
+        ("puffer_phc.envs.humanoid_phc", {"HumanoidPHC": object}),
+        ("puffer_phc.envs.render_env", {"HumanoidRenderEnv": object}),
+        ("pufferlib", {"PufferEnv": type("PufferEnv", (), {})}),
+    ):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+    spec = importlib.util.spec_from_file_location(
+        "ref_puffer_env", os.path.join(ref_loader.REFERENCE_ROOT, "puffer_phc/clean_pufferl/env.py")
+    )
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    N, K, A, LOG = 96, 48, 5, 12
+    g = torch.Generator().manual_seed(31)
+    rewards = torch.rand(K, N, generator=g) * 1.2
+    reward_raw = torch.rand(K, N, 5, generator=g)
+    reset = torch.rand(K, N, generator=g) < 0.12
+    terminate = reset & (torch.rand(K, N, generator=g) < 0.6)
+    reset[7] = False  # a step without any reset takes the other branch
+    terminate[7] = False
+    actions = (torch.rand(K, N, A, generator=g) * 3 - 1.5).numpy()
+
+    class ScriptedEnv:
+        def __init__(self):
+            self.obs_buf = torch.zeros(N, 4)
+            self.rew_buf = torch.zeros(N)
+            self.reset_buf = torch.zeros(N, dtype=torch.bool)
+            self.extras = {}
+            self.k = 0
+
+        def step(self, actions):
+            self.rew_buf[:] = rewards[self.k]
+            self.reset_buf[:] = reset[self.k]
+            self.extras["terminate"] = terminate[self.k].clone()
+            self.extras["reward_raw"] = reward_raw[self.k]
+            self.k += 1
+
+        def reset(self, env_ids=None):  # humanoid_phc.py:778-779
+            if env_ids is not None:
+                self.reset_buf[env_ids] = 0
+
+    env = ScriptedEnv()
+    pe = object.__new__(mod.PHCPufferEnv)
+    pe.cfg = types.SimpleNamespace(clip_actions=True, use_amp_obs=False, log_interval=LOG, num_envs=N, device="cpu")
+    pe.env = env
+    bufs = mod.PufferEnvBuffers(env.obs_buf, env.rew_buf, env.reset_buf, N, (A,), "cpu")
+    for k in ("observations", "rewards", "terminals", "truncations", "masks", "actions"):
+        setattr(pe, k, getattr(bufs, k))
+    pe.episode_returns = torch.zeros(N, dtype=torch.float32)
+    pe.episode_lengths = torch.zeros(N, dtype=torch.int32)
+    pe.episode_count = 0
+    pe._infos = {"episode_return": [], "episode_length": [], "truncated_rate": []}
+    pe.raw_rewards = torch.zeros(5, dtype=torch.float32)
+    pe.tick = 0
+
+    out = {k: [] for k in ("rew", "terminals", "truncations", "masks", "episode_returns", "episode_lengths",
+                           "raw_rewards", "episode_count", "actions")}  # fmt: skip
+    infos = []
+    for k in range(K):
+        _, rew, term, trunc, info = pe.step(actions[k])
+        out["rew"].append(rew.numpy().copy())
+        out["terminals"].append(term.numpy().copy())
+        out["truncations"].append(trunc.numpy().copy())
+        out["masks"].append(pe.masks.numpy().copy())
+        out["episode_returns"].append(pe.episode_returns.numpy().copy())
+        out["episode_lengths"].append(pe.episode_lengths.numpy().copy())
+        out["raw_rewards"].append(pe.raw_rewards.numpy().copy())
+        out["episode_count"].append(pe.episode_count)
+        out["actions"].append(pe.actions.numpy().copy())
+        if info:
+            d = info[0]
+            infos.append([k, d["episode_return"], d["episode_length"], d["truncated_rate"], d["rew_body_pos"],
+                          d["rew_body_rot"], d["rew_lin_vel"], d["rew_ang_vel"], d["rew_power"]])  # fmt: skip
+    arrays = {"in.rewards": rewards.numpy(), "in.reward_raw": reward_raw.numpy(), "in.reset": reset.numpy(),
+              "in.terminate": terminate.numpy(), "in.actions": actions, "in.log_interval": np.int64(LOG)}  # fmt: skip
+    for k, v in out.items():
+        arrays[f"out.{k}"] = np.stack([np.asarray(x) for x in v])
+    arrays["out.infos"] = np.asarray(infos, dtype=np.float64)
+    save("episode", arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     torch.manual_seed(0)
+    if len(sys.argv) > 1:  # regenerate only the named fixtures, e.g. `make_golden.py episode`
+        for name in sys.argv[1:]:
+            globals()[f"case_{name}"]()
+        sys.exit(0)
     # the reference regime: ids == arange, 30 fps clips, frame-aligned starts
     case_step("step_aligned", N=32, M=32, seed=11, min_frames=8, max_frames=16, max_progress=10)
     # config-4 style: random ids over a shared library, mixed fps, unaligned times, i.i.d. rotations
@@ -359,3 +455,4 @@ if __name__ == "__main__":
     case_running_norm()
     case_sample_time()
     case_amp_obs()
+    case_episode()

@@ -865,3 +865,86 @@ def test_action_to_pd_targets_bit_exact(res_action):
     want = O.action_to_pd_targets(act, off, sc, res_action, refp, dofp, zero_joints=(3, 7, 17, 22))
     assert torch.equal(got.cpu(), want)  # one multiply, one add, min/max: no room for rounding differences
     assert float(got[:, 9:12].abs().sum()) == 0.0 and float(got[:, 66:69].abs().sum()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------
+# episode bookkeeping of the pufferlib wrapper (clean_pufferl/env.py:121-159)
+# ---------------------------------------------------------------------------------------
+def _episode_state(n, cols, device):
+    return dict(
+        terminals=torch.zeros(n, dtype=torch.bool, device=device), truncations=torch.zeros(n, dtype=torch.bool, device=device),
+        masks=torch.ones(n, dtype=torch.bool, device=device), episode_returns=torch.zeros(n, device=device),
+        episode_lengths=torch.zeros(n, dtype=torch.int32, device=device), raw_rewards=torch.zeros(cols, device=device),
+        stats=torch.zeros(4, dtype=torch.float64, device=device), workspace=torch.zeros(16, dtype=torch.float64, device=device),
+    )  # fmt: skip
+
+
+def _episode_update_cabi(st, reset, terminate, rewards, raw):
+    from humanoid_b200 import _cabi
+
+    reset, terminate, rewards, raw = cuda(reset), cuda(terminate), cuda(rewards), cuda(raw).contiguous()
+    a = _cabi.PhcEpisodeArgs()
+    a.reset, a.terminate, a.rewards = reset.data_ptr(), terminate.data_ptr(), rewards.data_ptr()
+    a.reward_raw, a.reward_raw_stride, a.reward_raw_cols = raw.data_ptr(), raw.stride(0), raw.shape[1]
+    a.terminals, a.truncations, a.masks = st["terminals"].data_ptr(), st["truncations"].data_ptr(), st["masks"].data_ptr()
+    a.episode_returns, a.episode_lengths = st["episode_returns"].data_ptr(), st["episode_lengths"].data_ptr()
+    a.stats, a.raw_rewards, a.workspace = st["stats"].data_ptr(), st["raw_rewards"].data_ptr(), st["workspace"].data_ptr()
+    _cabi.check(_cabi.load().phc_episode_update(a, reset.shape[0], _cabi.stream_ptr(DEV)), "phc_episode_update")
+    torch.cuda.synchronize()
+    assert not st["workspace"].any(), "workspace must be left zero"
+
+
+def test_episode_bookkeeping_vs_reference_recording(golden):
+    from conftest import replay_episode_golden
+
+    replay_episode_golden(golden("episode"), lambda n, c: _episode_state(n, c, DEV), _episode_update_cabi, read=lambda t: t.cpu())
+
+
+@pytest.mark.parametrize("N", [1, 257, 70001, 300000])
+def test_episode_bookkeeping_vs_oracle_many_blocks(N):
+    g = torch.Generator().manual_seed(N)
+    want = _episode_state(N, 5, "cpu")
+    want.pop("workspace")
+    got = _episode_state(N, 5, DEV)
+    for k in range(4):
+        rewards = torch.rand(N, generator=g)
+        raw = torch.rand(N, 5, generator=g)
+        reset = torch.rand(N, generator=g) < (0.3 if k else 0.0)
+        terminate = reset & (torch.rand(N, generator=g) < 0.5)
+        O.episode_update(want, reset, terminate, rewards, raw)
+        _episode_update_cabi(got, reset, terminate, rewards, raw)
+    for key in ("terminals", "truncations", "masks", "episode_lengths", "episode_returns"):
+        assert_equal_exact(got[key], want[key], key)
+    assert_close(got["raw_rewards"], want["raw_rewards"], rtol=1e-6, atol=1e-7, what="raw_rewards")
+    assert_equal_exact(got["stats"][[0, 2, 3]], want["stats"][[0, 2, 3]], "counts")
+    assert_close(got["stats"][1], want["stats"][1], rtol=1e-12, atol=0, what="sum of returns")
+
+
+def test_puffer_env_step_matches_oracle():
+    """PHCPufferEnv.step = fused step + bookkeeping kernel + device-side reset of the flagged envs."""
+    from humanoid_b200 import PHCPufferEnv
+
+    N = 1500
+    lib_data, clock, state = make_case_cpu(num_envs=N, num_motions=40, seed=131, max_progress=30)
+    env = env_from(lib_data, clock, state)
+    pe = PHCPufferEnv(env, num_actions=69, log_interval=3)
+    want = _episode_state(N, 5, "cpu")
+    want.pop("workspace")
+    g = torch.Generator().manual_seed(5)
+    for k in range(3):
+        actions = torch.rand(N, 69, generator=g) * 4 - 2
+        phase = torch.rand(N, generator=g)
+        obs, rew, term, trunc, info = pe.step(actions.numpy(), phase_by_env=cuda(phase))
+        # the oracle bookkeeping on the flags / rewards the step produced (their parity is tested above)
+        assert torch.equal(pe.actions.cpu(), actions.clamp(-1, 1))
+        reset_k, rew_k = (term | trunc).cpu(), rew.cpu()
+        O.episode_update(want, reset_k, term.cpu(), rew_k, env.reward_raw.cpu())
+        assert_equal_exact(pe.episode_lengths, want["episode_lengths"], f"lengths[{k}]")
+        assert_equal_exact(pe.episode_returns, want["episode_returns"], f"returns[{k}]")
+        assert_equal_exact(pe.masks, want["masks"], f"masks[{k}]")
+        assert not env.reset_buf.any() and (env.progress_buf[reset_k.to(DEV)] == 0).all()
+    assert len(info) == 1 and set(info[0]) >= {"episode_return", "episode_length", "truncated_rate", "rew_body_pos"}
+    s = want["stats"].tolist()
+    assert s[0] > 0 and pe.episode_count == int(s[0])
+    assert abs(info[0]["episode_return"] - s[1] / s[0]) <= 1e-9 * abs(s[1] / s[0])
+    assert abs(info[0]["rew_body_pos"] - float(want["raw_rewards"][0]) / 3) < 1e-6

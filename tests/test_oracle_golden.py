@@ -120,6 +120,21 @@ def test_running_norm(golden):
     assert_close(O.running_norm_forward(m, v, g.inp("x2")[:32]), g.out("fwd"), what="fwd", **TIGHT)
 
 
+def test_episode_bookkeeping(golden):
+    """oracle.episode_update against the recorded run of the reference's PHCPufferEnv.step."""
+    from conftest import replay_episode_golden
+
+    def new_state(n, cols):
+        return dict(
+            terminals=torch.zeros(n, dtype=torch.bool), truncations=torch.zeros(n, dtype=torch.bool),
+            masks=torch.ones(n, dtype=torch.bool), episode_returns=torch.zeros(n),
+            episode_lengths=torch.zeros(n, dtype=torch.int32), raw_rewards=torch.zeros(cols),
+            stats=torch.zeros(4, dtype=torch.float64),
+        )  # fmt: skip
+
+    replay_episode_golden(golden("episode"), new_state, O.episode_update)
+
+
 def test_fixtures_exercise_both_flag_values(golden):
     seen_reset, seen_term, seen_pass = set(), set(), set()
     for case in STEP_CASES:

@@ -1,7 +1,10 @@
 """Small driver for ncu: builds the configs[1] workload (4096 envs, one clip per env) and
 launches the fused step kernel a few dozen times outside any CUDA graph.
 
-    python profiles/prof_step.py [num_envs] [time_steps] [launches]
+    python profiles/prof_step.py [num_envs] [time_steps] [launches] [config4]
+
+With a 4th argument ``config4`` the workload is BASELINE configs[3] instead: a 10k-clip mixed-fps
+library, random motion ids and unaligned times, a different clock for every ring slot.
 """
 
 import os
@@ -16,14 +19,23 @@ from humanoid_b200 import HumanoidPHC, MotionLib, synth  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+C4 = len(sys.argv) > 4 and sys.argv[4] == "config4"
 dev = torch.device("cuda", 0)
-lib_data = synth.make_motion_lib(N, 60, 300, (30,), seed=1234, device=dev)
+if C4:
+    g = torch.Generator(device=dev).manual_seed(1241)
+    nf = torch.randint(100, 701, (10000,), generator=g, device=dev)
+    nf[:20] = 7000
+    lib_data = synth.make_motion_lib(10000, fps_choices=(30, 60, 120), seed=1234, device=dev, frames_per_motion=nf)
+else:
+    lib_data = synth.make_motion_lib(N, 60, 300, (30,), seed=1234, device=dev)
 lib = MotionLib(lib_data, device=dev)
 clock = synth.make_clock(lib_data, N, seed=1235, max_progress=30)
 R = 17
 envs = []
 for r in range(R):
-    ref = lib.get_motion_state(clock.sampled_motion_ids, synth.reward_time(clock, extra_steps=r + 1), clock.global_offset)
+    if C4:
+        clock = synth.make_clock(lib_data, N, seed=1235 + 31 * r, ids="random", aligned=False, max_progress=30)
+    ref = lib.get_motion_state(clock.sampled_motion_ids, synth.reward_time(clock, extra_steps=1 if C4 else r + 1), clock.global_offset)
     env = HumanoidPHC(lib, N, device=dev, time_steps=T)
     env.set_sim_state(synth.make_sim_state(ref, seed=1236 + r), copy=False)
     env.set_clock(clock)
@@ -36,4 +48,4 @@ for i in range(L):
     envs[i % R].post_physics_step(True)
 e1.record()
 torch.cuda.synchronize()
-print(f"N={N} T={T}: {1e3 * e0.elapsed_time(e1) / (L - L // 2):.2f} us per launch (back-to-back, no graph)")
+print(f"N={N} T={T}{' config4' if C4 else ''}: {1e3 * e0.elapsed_time(e1) / (L - L // 2):.2f} us per launch (back-to-back, no graph)")

@@ -116,6 +116,12 @@ class PhcStepArgs(C.Structure):
         ("rew_power_coef", C.c_float),
         ("power_col", C.c_int32),
         ("obs_moments", C.c_void_p),
+        ("obs_norm", C.c_void_p),
+        ("obs_norm_stride", C.c_int64),
+        ("norm_mean", C.c_void_p),
+        ("norm_var", C.c_void_p),
+        ("norm_epsilon", C.c_float),
+        ("norm_clip", C.c_float),
     ]
 
 

@@ -651,6 +651,11 @@ struct StepParams {
   uint8_t* reset;
   uint8_t* term;
   double* moments;
+  float* obs_norm;  // NULL, or the normalised copy of the obs rows (RunningNorm.forward)
+  int64_t obs_norm_stride;
+  const float* norm_mean;
+  const float* norm_var;
+  float norm_eps, norm_clip;
   const float* dof_force;  // power reward inputs (NULL = off)
   int64_t dof_force_stride;
   const float* dof_vel;
@@ -666,6 +671,17 @@ struct StepParams {
   int aos;        // sim state is one AoS-13 tensor, 16-B aligned rows
   int obs_vec2;   // obs rows can be written with 8-byte stores
 };
+
+// RunningNorm.forward of one value (policies/running_norm.py:15-20): clamp((x - mean) / sqrt(var + eps)).
+// `sd` = sqrt(var + eps) and `r` ~ 1/sd are per column; the quotient is within 1 ulp of IEEE division.
+__device__ __forceinline__ void norm_column(const StepParams& p, int64_t col, float& mean, float& sd, float& r) {
+  mean = p.norm_mean[col];
+  sd = sqrt_faithful(p.norm_var[col] + p.norm_eps);
+  r = rcp_approx(sd);
+}
+__device__ __forceinline__ float norm_value(float x, float mean, float sd, float r, float clip) {
+  return fminf(fmaxf(div_faithful(x - mean, sd, r), -clip), clip);
+}
 
 // per-body share of power = sum_dof |dof_force * dof_vel| (humanoid_phc.py:1298): body b >= 1 owns
 // the 3 dofs of joint b - 1
@@ -963,6 +979,17 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
         }
         atomicAdd(p.moments + c_off + c, s1);
         atomicAdd(p.moments + W + c_off + c, s2);
+      }
+    }
+    if (p.obs_norm) {  // RunningNorm.forward of the same staged columns
+      for (int c = tid; c < s_len; c += NT) {
+        float m, sd, r;
+        norm_column(p, c_off + c, m, sd, r);
+        for (int ee = 0; ee < nvalid; ++ee) {
+          if (!S.act[ee]) continue;
+          p.obs_norm[(env0 + ee) * p.obs_norm_stride + c_off + c] =
+              norm_value(S.buf[ee * STAGE_FLOATS + s_off + c], m, sd, r, p.norm_clip);
+        }
       }
     }
 
@@ -1348,6 +1375,23 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     }
   }
 
+  if (p.obs_norm) {
+    // RunningNorm.forward fused into the epilogue: the staged rows are read a second time (while the
+    // bulk store drains them) and leave normalised with coalesced 8-byte stores; mean / var are 7.5 KB
+    // that every block reads from L2
+    float2* dst = reinterpret_cast<float2*>(p.obs_norm + env0 * STAGE_FLOATS);
+    const float2* src = reinterpret_cast<const float2*>(S.frames);
+    for (int c2 = tid; c2 < STAGE_FLOATS / 2; c2 += NT) {
+      float m0, sd0, r0, m1, sd1, r1;
+      norm_column(p, 2 * c2, m0, sd0, r0);
+      norm_column(p, 2 * c2 + 1, m1, sd1, r1);
+      for (int ee = 0; ee < nvalid; ++ee) {
+        const float2 x = src[ee * (STAGE_FLOATS / 2) + c2];
+        dst[ee * (STAGE_FLOATS / 2) + c2] =
+            make_float2(norm_value(x.x, m0, sd0, r0, p.norm_clip), norm_value(x.y, m1, sd1, r1, p.norm_clip));
+      }
+    }
+  }
   if (bulk_ok && tid == NT - 1) bulk_wait_read();  // shared memory must outlive the store's reads
   PHC_STAMP(7);
 }
@@ -1676,11 +1720,16 @@ __global__ void running_norm_count_kernel(float* count) { *count = *count + 1.0f
 __global__ void running_norm_forward_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t stride,
                                             const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                             float clip, float* __restrict__ out, int64_t out_stride) {
+  // one thread per column, RN_ROWS rows per block: sqrt / reciprocal once per column, coalesced rows
+  constexpr int RN_ROWS = 16;
   const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
-  const int64_t r = blockIdx.x;
-  if (c >= cols || r >= rows) return;
-  const float v = (x[r * stride + c] - mean[c]) / sqrtf(var[c] + eps);
-  out[r * out_stride + c] = fminf(fmaxf(v, -clip), clip);
+  if (c >= cols) return;
+  const float m = mean[c];
+  const float sd = sqrtf(var[c] + eps);
+  const int64_t r0 = (int64_t)blockIdx.x * RN_ROWS;
+#pragma unroll 4
+  for (int64_t r = r0; r < r0 + RN_ROWS && r < rows; ++r)
+    out[r * out_stride + c] = fminf(fmaxf((x[r * stride + c] - m) / sd, -clip), clip);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -2030,6 +2079,16 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.reset = a->reset_buf;
   p.term = a->terminate_buf;
   p.moments = a->obs_moments;
+  p.obs_norm = a->obs_norm;
+  p.obs_norm_stride = a->obs_norm_stride;
+  p.norm_mean = a->norm_mean;
+  p.norm_var = a->norm_var;
+  p.norm_eps = a->norm_epsilon;
+  p.norm_clip = a->norm_clip;
+  if (a->obs_norm) {
+    if (!a->norm_mean || !a->norm_var) return PHC_ERR_NULL;
+    if (a->obs_norm_stride < SELF_DIM + (int64_t)TASK_DIM * a->time_steps || !(a->norm_clip > 0.0f)) return PHC_ERR_SHAPE;
+  }
   p.dof_force = a->dof_force;
   p.dof_force_stride = a->dof_force_stride;
   p.dof_vel = a->dof_vel;
@@ -2218,7 +2277,8 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
   init_options();
   // fast path: T == 1, AoS sim tensor (16-B aligned rows), dense 16-B aligned obs_buf
   const bool fast = !g_force_generic && p.T == 1 && p.aos && p.L.packed && p.obs_stride == STAGE_FLOATS &&
-                    ((uintptr_t)p.obs & 15) == 0;
+                    ((uintptr_t)p.obs & 15) == 0 &&
+                    (!p.obs_norm || (p.obs_norm_stride == STAGE_FLOATS && ((uintptr_t)p.obs_norm & 15) == 0));
   static bool attr_fast4[64] = {}, attr_gen[64] = {};
   static int first_wave[64] = {};
   if (fast) {
@@ -2235,7 +2295,7 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
     return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev], g_pdl != 0);
   }
   // T > 1 on the AoS tensor + packed table: the pipelined TMA kernel
-  const bool multi = !g_force_generic && p.T > 1 && p.aos && p.L.packed && p.obs_vec2 &&
+  const bool multi = !g_force_generic && p.T > 1 && p.aos && p.L.packed && p.obs_vec2 && !p.obs_norm &&
                      !(args->flags & PHC_STEP_MAPPED_HOST_IO);
   static bool attr_multi[64] = {};
   if (multi)
@@ -2280,7 +2340,7 @@ int phc_running_norm_forward(const float* x, int64_t rows, int64_t cols, int64_t
   if (rows == 0 || cols == 0) return PHC_OK;
   if (rows < 0 || cols < 0 || row_stride < cols || out_stride < cols || rows > 0x7fffffff) return PHC_ERR_SHAPE;
   if (!x || !running_mean || !running_var || !out) return PHC_ERR_NULL;
-  dim3 grid((unsigned)rows, (unsigned)((cols + 127) / 128));
+  dim3 grid((unsigned)((rows + 15) / 16), (unsigned)((cols + 127) / 128));
   running_norm_forward_kernel<<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, running_mean, running_var, epsilon,
                                                         clip, out, out_stride);
   return launch_status();

@@ -130,6 +130,8 @@ class HumanoidPHC:
             torch.zeros(2 * self.num_obs, dtype=torch.float64, device=dev) if obs_moments else None
         )
         self.obs_moment_rows = 0
+        self.obs_normalizer = None  # set_obs_normalizer(): RunningNorm.forward fused into the step's epilogue
+        self.obs_norm_buf = None
         self._step_args = None
 
     # ------------------------------------------------------------------------------------
@@ -226,6 +228,14 @@ class HumanoidPHC:
         a.reset_buf = self.reset_buf.data_ptr()
         a.terminate_buf = self._terminate_buf.data_ptr()
         a.obs_moments = self.obs_moments.data_ptr() if self.obs_moments is not None else None
+        if self.obs_normalizer is not None:  # policies/running_norm.py:15-20, fused
+            rn = self.obs_normalizer
+            a.obs_norm = self.obs_norm_buf.data_ptr()
+            a.obs_norm_stride = self.obs_norm_buf.stride(0)
+            a.norm_mean = rn.running_mean.data_ptr()
+            a.norm_var = rn.running_var.data_ptr()
+            a.norm_epsilon = rn.epsilon
+            a.norm_clip = rn.clip
         if self.use_power_reward:  # humanoid_phc.py:1297-1305
             a.dof_force = self.dof_force_tensor.data_ptr()
             a.dof_force_stride = self.dof_force_tensor.stride(0)
@@ -236,6 +246,20 @@ class HumanoidPHC:
             a.power_col = self.reward_raw.shape[1] - 1
         self._step_args = (a, advance, keep)
         return a
+
+    def set_obs_normalizer(self, normalizer):
+        """Fuse ``RunningNorm.forward`` (PHC/policies/running_norm.py:15-20) into the step: every step also
+        writes ``obs_norm_buf = clamp((obs_buf - running_mean) / sqrt(running_var + eps), -clip, clip)`` —
+        what the policy's first layer consumes — from the same shared-memory rows, while ``obs_buf`` keeps
+        the raw rows the experience buffer and ``RunningNorm.update`` need.  The normaliser's buffers are
+        read at launch time, so an ``update()`` between steps is seen by the next step.  ``None`` turns it off."""
+        if normalizer is not None:
+            if normalizer.shape != self.num_obs or normalizer.running_mean.device != self.device:
+                raise ValueError("normalizer must have shape num_obs and live on the env's device")
+            if self.obs_norm_buf is None:
+                self.obs_norm_buf = torch.zeros_like(self.obs_buf)
+        self.obs_normalizer = normalizer
+        self._step_args = None
 
     def post_physics_step(self, advance_progress: bool = True):
         """progress += 1; reward; reset; observations (humanoid_phc.py:138-149) — one launch."""

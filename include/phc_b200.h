@@ -245,6 +245,15 @@ typedef struct PhcStepArgs {
   double* obs_moments;                   /* NULL, or [2*(358+576*T)] fp64: per-column sum
                                             and sum of squares accumulated (+=) for
                                             RunningNorm.update           running_norm.py:23 */
+  /* RunningNorm.forward fused into the obs epilogue (policies/running_norm.py:15-20), off when
+   * obs_norm is NULL:  obs_norm = clamp((obs - mean) / sqrt(var + epsilon), -clip, clip), written
+   * IN ADDITION to obs_buf (the experience buffer keeps the raw rows, RunningNorm.update needs them) */
+  float* obs_norm;                       /* NULL or [n, 358+576*T]                           */
+  int64_t obs_norm_stride;
+  const float* norm_mean;                /* [358+576*T] running_mean                         */
+  const float* norm_var;                 /* [358+576*T] running_var                          */
+  float norm_epsilon;                    /* 1e-5 in the reference                            */
+  float norm_clip;                       /* 10.0 in the reference                            */
 } PhcStepArgs;
 
 PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream);

@@ -948,3 +948,44 @@ def test_puffer_env_step_matches_oracle():
     assert s[0] > 0 and pe.episode_count == int(s[0])
     assert abs(info[0]["episode_return"] - s[1] / s[0]) <= 1e-9 * abs(s[1] / s[0])
     assert abs(info[0]["rew_body_pos"] - float(want["raw_rewards"][0]) / 3) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------
+# RunningNorm.forward fused into the step's obs epilogue (policies/running_norm.py:15-20)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,T,generic", [(4099, 1, False), (1000, 1, True), (600, 3, False)],
+                         ids=["fast_T1", "generic_T1", "generic_T3"])  # fmt: skip
+def test_fused_obs_normalisation_vs_oracle(N, T, generic):
+    from humanoid_b200 import HumanoidPHC, RunningNorm, _cabi
+
+    lib_data, clock, state = _gpu_case(N, 64, 209, max_progress=40)
+    env = HumanoidPHC(MotionLib(lib_data, device=DEV), N, device=DEV, time_steps=T)
+    env.set_sim_state(state)
+    env.set_clock(clock)
+    rn = RunningNorm(env.num_obs, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    rn.running_mean.copy_(torch.randn(1, env.num_obs, generator=g) * 0.3)
+    rn.running_var.copy_(torch.rand(1, env.num_obs, generator=g) * 2 + 1e-3)
+    rn.running_var[0, :5] = 0.0  # a column that never varied: only epsilon under the root
+    env.set_obs_normalizer(rn)
+    capi = _cabi.load()
+    try:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if generic else 0)
+        env.step()
+    finally:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+    plain = HumanoidPHC(env._motion_lib, N, device=DEV, time_steps=T)
+    plain.set_sim_state(state)
+    plain.set_clock(clock)
+    plain.step()
+    assert torch.equal(env.obs_buf, plain.obs_buf), "the raw rows must not change"
+    assert torch.equal(env.rew_buf, plain.rew_buf) and torch.equal(env.reset_buf, plain.reset_buf)
+    want = O.running_norm_forward(rn.running_mean.cpu(), rn.running_var.cpu(), env.obs_buf.cpu(), rn.epsilon, rn.clip)
+    assert_close(env.obs_norm_buf, want, rtol=1e-5, atol=1e-6, what="fused normalised obs")
+    assert_close(env.obs_norm_buf, rn(env.obs_buf), rtol=2e-7, atol=1e-7, what="fused vs standalone forward kernel")
+    assert float(env.obs_norm_buf.abs().max()) == rn.clip  # the clamp is exercised
+    # an update between steps is picked up by the next launch (buffers are read at launch time)
+    rn.running_mean.add_(0.5)
+    env.step()
+    want = O.running_norm_forward(rn.running_mean.cpu(), rn.running_var.cpu(), env.obs_buf.cpu(), rn.epsilon, rn.clip)
+    assert_close(env.obs_norm_buf, want, rtol=1e-5, atol=1e-6, what="fused normalised obs, second step")

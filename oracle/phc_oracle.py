@@ -718,3 +718,113 @@ def episode_update(state: Dict[str, Tensor], reset: Tensor, terminate: Tensor, r
     state["episode_returns"] += rewards  # :158-159
     state["episode_lengths"] += 1
     return state
+
+
+# ----------------------------------------------------------------------------------------
+# AMP observation buffers of the env — envs/humanoid_phc.py:791-843, 1125-1212, 1341-1361
+# ----------------------------------------------------------------------------------------
+def amp_obs_from_state(state: Tensor, dof_pos: Tensor, dof_vel: Tensor, key_body_ids: Tensor, dof_subset: Tensor):
+    """_compute_amp_observations -> _compute_amp_observations_from_state (:1125-1212) with the config's
+    constant flags (local_root_obs, amp_root_height_obs, has_dof_subset, upright = True; shape / limb
+    weight columns off).  ``state`` is the [n, B, 13] AoS rigid-body state; root = body 0."""
+    return amp_obs_smpl(
+        state[:, 0, 0:3], state[:, 0, 3:7], state[:, 0, 7:10], state[:, 0, 10:13], dof_pos, dof_vel,
+        state[:, key_body_ids, 0:3], None, None, dof_subset, True, True, True, False, False, True,
+    )  # fmt: skip
+
+
+def update_hist_amp_obs(amp_obs_buf: Tensor, env_ids: Optional[Tensor] = None):
+    """_update_hist_amp_obs (:1341-1350): slots 1.. take what slots 0..S-2 held."""
+    if env_ids is None:
+        amp_obs_buf[:, 1:] = amp_obs_buf[:, :-1].clone()
+    else:
+        amp_obs_buf[env_ids, 1:] = amp_obs_buf[env_ids, :-1].clone()
+
+
+def init_amp_obs_ref(lib: OracleMotionLib, amp_obs_buf: Tensor, amp_obs_demo_buf: Tensor, env_ids: Tensor,
+                     motion_ids: Tensor, motion_times: Tensor, dt: float, key_body_ids: Tensor, dof_subset: Tensor):  # fmt: skip
+    """_init_amp_obs_ref (:805-819) with _get_amp_obs (:821-838): history slot k+1 of the reset envs is the
+    AMP observation of the reference motion at ``motion_time - dt*(k+1)`` (no global offset), then the
+    envs' whole rows are copied to the demo buffer."""
+    S = amp_obs_buf.shape[1]
+    ids = torch.tile(motion_ids.unsqueeze(-1), [1, S - 1]).view(-1)
+    steps = -dt * (torch.arange(0, S - 1) + 1)
+    times = (motion_times.unsqueeze(-1) + steps).view(-1)
+    res = lib.get_motion_state(ids, times, None)
+    obs = amp_obs_smpl(
+        res["root_pos"], res["root_rot"], res["root_vel"], res["root_ang_vel"], res["dof_pos"], res["dof_vel"],
+        res["rg_pos"][:, key_body_ids], None, None, dof_subset, True, True, True, False, False, True,
+    )  # fmt: skip
+    amp_obs_buf[env_ids, 1:] = obs.view(env_ids.shape[0], S - 1, -1)
+    amp_obs_demo_buf[env_ids] = amp_obs_buf[env_ids]
+
+
+class OracleEnv:
+    """HumanoidPHC.step / reset (envs/humanoid_phc.py:90-172) with PhysX replaced by whatever the caller
+    writes into ``state`` / ``dof_state`` / ``dof_force`` between the pre- and the post-physics half.
+    Default config: power reward on, hands and toes frozen, reference-state init, T = 1."""
+
+    def __init__(self, lib: OracleMotionLib, num_envs: int, progress_buf, motion_start_times,
+                 motion_start_times_offset, global_offset, sampled_motion_ids, pd_action_offset, pd_action_scale,
+                 dof_subset, key_body_ids, num_amp_obs_steps: int = 10, use_amp_obs: bool = True,
+                 dt: float = 2 * (1.0 / 60.0), termination_distance: float = 0.25, rew_power_coef: float = 0.0005,
+                 zero_joints=(17, 22, 3, 7)):  # fmt: skip
+        N = num_envs
+        self.lib, self.N, self.dt = lib, N, dt
+        self.progress_buf = progress_buf.clone()
+        self._motion_start_times = motion_start_times.clone()
+        self._motion_start_times_offset = motion_start_times_offset.clone()
+        self._global_offset = global_offset.clone()
+        self._sampled_motion_ids = sampled_motion_ids.clone()
+        self._pd_action_offset, self._pd_action_scale = pd_action_offset, pd_action_scale
+        self.dof_subset, self._key_body_ids = dof_subset, key_body_ids
+        self.use_amp_obs = use_amp_obs
+        self.rew_power_coef = rew_power_coef
+        self.zero_joints = zero_joints  # L_Hand, R_Hand, L_Toe, R_Toe in DOF_NAMES (:118-127)
+        self._termination_distances = torch.full((24,), termination_distance)
+        self.state = torch.zeros(N, 24, 13)
+        self.root_states = torch.zeros(N, 13)
+        self.dof_state = torch.zeros(N, 69, 2)
+        self.dof_force = torch.zeros(N, 69)
+        self.obs_buf = torch.zeros(N, 934)
+        self.rew_buf = torch.zeros(N)
+        self.reward_raw = torch.zeros(N, 5)
+        self.reset_buf = torch.ones(N, dtype=torch.bool)
+        self._terminate_buf = torch.ones(N, dtype=torch.bool)
+        P = 13 + 23 * 6 + 69 + 3 * len(key_body_ids) - 9 * ((69 - len(dof_subset)) // 3)  # :470-476
+        self._amp_obs_buf = torch.zeros(N, num_amp_obs_steps, P)
+        self._amp_obs_demo_buf = torch.zeros_like(self._amp_obs_buf)
+
+    def step(self, actions: Tensor, physics):
+        pd_target = action_to_pd_targets(actions, self._pd_action_offset, self._pd_action_scale,
+                                         zero_joints=self.zero_joints)  # fmt: skip
+        physics(self)
+        obs, rew, raw, reset, term = step(
+            self.lib, self.state, self.progress_buf, self._motion_start_times, self._motion_start_times_offset,
+            self._global_offset, self._sampled_motion_ids, self._termination_distances, self.dt,
+            reset_buf=self.reset_buf, dof_force=self.dof_force, dof_vel=self.dof_state[..., 1],
+            rew_power_coef=self.rew_power_coef,
+        )  # fmt: skip
+        self.obs_buf[:], self.rew_buf[:], self.reward_raw[:] = obs, rew, raw
+        self.reset_buf[:], self._terminate_buf[:] = reset, term
+        if self.use_amp_obs:  # :153-157
+            update_hist_amp_obs(self._amp_obs_buf)
+            self._amp_obs_buf[:, 0] = amp_obs_from_state(self.state, self.dof_state[..., 0], self.dof_state[..., 1],
+                                                         self._key_body_ids, self.dof_subset)  # fmt: skip
+        return pd_target
+
+    def reset(self, env_ids: Tensor, phase: Tensor):
+        if len(env_ids) == 0:
+            return
+        reset_envs(
+            self.lib, env_ids, phase, self.state, self.root_states, self.dof_state[..., 0], self.dof_state[..., 1],
+            self.progress_buf, self.reset_buf, self._terminate_buf, self._motion_start_times,
+            self._motion_start_times_offset, self._global_offset, self._sampled_motion_ids, self.obs_buf, self.dt,
+        )  # fmt: skip
+        if self.use_amp_obs:  # _init_amp_obs (:791-799)
+            self._amp_obs_buf[env_ids, 0] = amp_obs_from_state(
+                self.state[env_ids], self.dof_state[env_ids, :, 0], self.dof_state[env_ids, :, 1],
+                self._key_body_ids, self.dof_subset)  # fmt: skip
+            init_amp_obs_ref(self.lib, self._amp_obs_buf, self._amp_obs_demo_buf, env_ids,
+                             self._sampled_motion_ids[env_ids], self._motion_start_times[env_ids], self.dt,
+                             self._key_body_ids, self.dof_subset)  # fmt: skip

@@ -126,3 +126,43 @@ def replay_episode_golden(g, new_state, update, read=lambda t: t):
         partial = 0 if (k + 1) % log == 0 else int(read(st["stats"])[0])
         assert count + partial == int(g.out("episode_count")[k]), f"episode_count[{k}]"
     assert len(infos) == K // log
+
+
+def replay_env_rollout(g, env, read=lambda t: t, tol=None, dof_tol=None):
+    """Drive ``env`` (oracle.OracleEnv or the CUDA shim behind the same five calls) through
+    tests/golden/env_rollout.npz — a recording of the reference's own HumanoidPHC.step / reset — and
+    compare every buffer after every call.  ``env`` needs: step(actions, physics) -> pd_target,
+    reset(env_ids, phase), write_sim(state, dof_state, dof_force) and the reference's buffer names."""
+    tol = tol or dict(rtol=1e-6, atol=1e-6)
+    dof_tol = dof_tol or tol
+    K = len([k for k in g.keys() if k.startswith("in.actions.")])
+    for k in range(K):
+        def physics(e, k=k):
+            e.write_sim(g.inp(f"state.{k}"), g.inp(f"dof_state.{k}"), g.inp(f"dof_force.{k}"))
+
+        pd = env.step(g.inp(f"actions.{k}"), physics)
+        assert_equal_exact(read(pd), g.out(f"pd_target.{k}"), f"pd_target[{k}]")
+        o = lambda n, k=k: g.out(f"step.{k}.{n}")  # noqa: E731
+        assert_equal_exact(read(env.progress_buf), o("progress"), f"progress[{k}]")
+        assert_equal_exact(read(env.reset_buf), o("reset"), f"reset[{k}]")
+        assert_equal_exact(read(env._terminate_buf), o("terminate"), f"terminate[{k}]")
+        assert_close(read(env.obs_buf), o("obs"), what=f"obs[{k}]", **tol)
+        assert_close(read(env.rew_buf), o("rew"), what=f"rew[{k}]", **tol)
+        assert_close(read(env.reward_raw), o("reward_raw"), what=f"reward_raw[{k}]", **tol)
+        assert_close(read(env._amp_obs_buf).flatten(1), o("amp_obs"), what=f"amp_obs[{k}]", **tol)
+        env.reset(g.inp(f"reset_indices.{k}"), g.inp(f"phase.{k}"))
+        o = lambda n, k=k: g.out(f"reset.{k}.{n}")  # noqa: E731
+        for name, attr in (("progress", "progress_buf"), ("reset", "reset_buf"), ("terminate", "_terminate_buf"),
+                           ("motion_start_times", "_motion_start_times"), ("global_offset", "_global_offset"),
+                           ("motion_start_times_offset", "_motion_start_times_offset")):  # fmt: skip
+            assert_equal_exact(read(getattr(env, attr)), o(name), f"{name} after reset[{k}]")
+        rows = g.inp(f"reset_indices.{k}")
+        sim, root, dof = env.read_sim()
+        assert_close(read(sim), o("rigid_body_state"), what=f"rigid_body_state after reset[{k}]", **tol)
+        assert_close(read(root)[rows], o("root_states")[rows], what=f"root_states after reset[{k}]", **tol)
+        assert_close(read(dof)[rows], o("dof_state")[rows], what=f"dof_state after reset[{k}]", **dof_tol)
+        assert_close(read(env.obs_buf), o("obs"), what=f"obs after reset[{k}]", **tol)
+        assert_close(read(env._amp_obs_buf).flatten(1), o("amp_obs"), what=f"amp_obs after reset[{k}]", **dof_tol)
+        assert_close(read(env._amp_obs_demo_buf).flatten(1), o("amp_obs_demo"), what=f"amp_obs_demo after reset[{k}]",
+                     **dof_tol)  # fmt: skip
+    return K

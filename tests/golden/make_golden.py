@@ -430,6 +430,188 @@ def case_episode():
     save("episode", arrays)
 
 
+def load_reference_env_module():
+    """puffer_phc.envs.humanoid_phc with its simulator imports stubbed (isaacgym, gymtorch, gym are not
+    installed and PhysX is out of scope): the class body — step(), reset() and every _compute_* /
+    _reset_* / AMP method — is the reference's own code."""
+    import types
+
+    for name in ("isaacgym", "isaacgym.gymapi", "isaacgym.gymtorch", "gymtorch", "gym", "gym.spaces"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["isaacgym"].gymapi = sys.modules["isaacgym.gymapi"]
+    sys.modules["isaacgym"].gymtorch = sys.modules["isaacgym.gymtorch"]
+    sys.modules["gym"].spaces = sys.modules["gym.spaces"]
+    for m in ("gymtorch", "isaacgym.gymtorch"):
+        sys.modules[m].unwrap_tensor = lambda t: t
+    import puffer_phc.envs.humanoid_phc as H
+
+    return H
+
+
+def case_env_rollout():
+    """The unmodified reference ``HumanoidPHC.step(actions)`` and ``HumanoidPHC.reset(env_ids)``
+    (envs/humanoid_phc.py:90-172) driven for a few steps as clean_pufferl/env.py:109-140 drives them, on
+    an instance built without ``__init__`` (which needs Isaac Gym and asset files).  PhysX is a scripted
+    stand-in: ``fetch_results`` writes the next rigid-body / dof state (reference pose at the coming
+    reward time + noise) into the same AoS tensors the reference wraps.  Default EnvConfig except
+    use_amp_obs=True and num_amp_obs_steps=4 (10 in the config; smaller fixture)."""
+    import types
+
+    H = load_reference_env_module()
+    from puffer_phc.config import EnvConfig
+
+    N, K, S = 24, 5, 4
+    lib_data, clock, _ = synth.make_case(N, N, ref_query, seed=41, device="cpu", min_frames=16, max_frames=26,
+                                         max_progress=6)  # fmt: skip
+    lib = ref_loader.make_reference_lib(lib_data)
+    cfg = EnvConfig()
+    cfg.num_envs, cfg.device_type, cfg.use_amp_obs, cfg.num_amp_obs_steps = N, "cpu", True, S
+    assert cfg.device == "cpu" and cfg.robot.freeze_hand and cfg.robot.freeze_toe and cfg.reward.use_power_reward
+
+    env = object.__new__(H.HumanoidPHC)
+    env.cfg = cfg
+    env.isaac_base = types.SimpleNamespace(dt=DT, control_freq_inv=2)
+    env.sim = None
+    env.viewer = None
+    env.num_dof, env.num_bodies = 69, 24
+    env.num_obs = 934
+    env._dof_obs_size = 23 * 6
+    disc = [np.arange(i * 3, (i + 1) * 3) for i, n in enumerate(H.DOF_NAMES) if n not in H.REMOVE_NAMES]  # :186-194
+    env.dof_subset = torch.from_numpy(np.concatenate(disc))
+    env._num_amp_obs_per_step = 13 + env._dof_obs_size + env.num_dof + 3 * len(H.KEY_BODIES)  # :470-476
+    env._num_amp_obs_per_step -= (6 + 3) * int((env.num_dof - len(env.dof_subset)) / 3)
+    env.num_amp_obs = S * env._num_amp_obs_per_step
+    env.humanoid_shapes = torch.zeros(N, 17 + 6)
+    env.humanoid_limb_and_weights = torch.zeros(N, 10)
+    env._humanoid_actor_ids = torch.arange(N, dtype=torch.int32)
+    env.all_env_ids = torch.arange(N)
+    env._key_body_ids = H.build_body_ids_tensor(H.BODY_NAMES, H.KEY_BODIES, "cpu")
+    env._contact_body_ids = H.build_body_ids_tensor(H.BODY_NAMES, H.CONTACT_BODIES, "cpu")
+    env._track_bodies_id = H.build_body_ids_tensor(H.BODY_NAMES, H.TRACK_BODIES, "cpu")
+    env._reset_bodies_id = H.build_body_ids_tensor(H.BODY_NAMES, H.RESET_BODIES, "cpu")
+    env._termination_distances = torch.full((24,), cfg.termination_distance)
+    env.flag_im_eval = env.flag_test = False
+    env._motion_lib = lib
+    # simulator tensors, laid out as gymtorch hands them over (:499-553)
+    env._root_states = torch.zeros(N, 13)
+    env._humanoid_root_states = env._root_states.view(N, 1, 13)[:, 0]
+    env._dof_state = torch.zeros(N * 69, 2)
+    env._dof_pos = env._dof_state.view(N, 69, 2)[..., 0]
+    env._dof_vel = env._dof_state.view(N, 69, 2)[..., 1]
+    env._rigid_body_state = torch.zeros(N * 24, 13)
+    rb = env._rigid_body_state.view(N, 24, 13)
+    env._rigid_body_pos, env._rigid_body_rot = rb[..., 0:3], rb[..., 3:7]
+    env._rigid_body_vel, env._rigid_body_ang_vel = rb[..., 7:10], rb[..., 10:13]
+    env.dof_force_tensor = torch.zeros(N, 69)
+    env._contact_forces = torch.zeros(N, 24, 3)
+    g = torch.Generator().manual_seed(43)
+    env._pd_action_offset = torch.randn(69, generator=g) * 0.2
+    env._pd_action_scale = torch.rand(69, generator=g) + 0.5
+    # env buffers (:556-611), rew_buf as intended there (the torch(...) call at :560 is a typo)
+    env.obs_buf = torch.zeros(N, 934)
+    env.rew_buf = torch.zeros(N)
+    env.reward_raw = torch.zeros(N, 5)
+    env.progress_buf = clock.progress_buf.clone()
+    env.reset_buf = torch.ones(N, dtype=torch.bool)
+    env._terminate_buf = torch.ones(N, dtype=torch.bool)
+    env.extras = {}
+    env._reset_default_env_ids, env._reset_ref_env_ids = [], []
+    env._global_offset = clock.global_offset.clone()
+    env._motion_start_times = clock.motion_start_times.clone()
+    env._motion_start_times_offset = clock.motion_start_times_offset.clone()
+    env._sampled_motion_ids = clock.sampled_motion_ids.clone()
+    env.ref_motion_cache = {}
+    env._amp_obs_buf = torch.zeros(N, S, env._num_amp_obs_per_step)
+    env._curr_amp_obs_buf = env._amp_obs_buf[:, 0]
+
+    class RaisesOnOverlap(torch.Tensor):
+        """_update_hist_amp_obs (:1341-1347) assigns buf[:, 0:S-1] to the overlapping view buf[:, 1:] inside a
+        try and falls back to .clone() on the RuntimeError the reference's pinned torch 2.3.1 raises there
+        (the message is quoted in its comment).  torch 2.11 does not raise and copies front to back, which
+        smears slot 0 over the whole history; restore the pinned behaviour so the fallback runs."""
+
+        def __setitem__(self, idx, value):
+            if isinstance(value, torch.Tensor) and value.untyped_storage().data_ptr() == self.untyped_storage().data_ptr():
+                raise RuntimeError("unsupported operation: some elements of the input tensor and the written-to "
+                                   "tensor refer to a single memory location. Please clone() the tensor before "
+                                   "performing the operation.")  # fmt: skip
+            super().__setitem__(idx, value)
+
+    env._hist_amp_obs_buf = env._amp_obs_buf[:, 1:].as_subclass(RaisesOnOverlap)
+    env._amp_obs_demo_buf = torch.zeros_like(env._amp_obs_buf)
+    assert torch.equal(env._sampled_motion_ids, torch.arange(N)), "the reference regime: clip i <-> env i"
+
+    rec = {"pd_target": [], "state": [], "dof_state": [], "dof_force": []}
+
+    class ScriptedGym:
+        """Every Isaac Gym call is a no-op except the two that matter to the path."""
+
+        def __getattr__(self, name):
+            return lambda *a, **k: None
+
+        def set_dof_position_target_tensor(self, sim, t):
+            rec["pd_target"].append(t.clone())
+
+        def fetch_results(self, sim, wait):
+            # "physics": the pose the reward of THIS step will be compared with, plus noise
+            t = (env.progress_buf + 1) * DT + env._motion_start_times + env._motion_start_times_offset
+            ref = lib.get_motion_state(env._sampled_motion_ids, t, env._global_offset)
+            k = len(rec["state"])
+            state = synth.make_sim_state(ref, seed=500 + k)
+            env._rigid_body_state.view(N, 24, 13)[:] = state
+            env._root_states[:] = state[:, 0]
+            gk = torch.Generator().manual_seed(600 + k)
+            env._dof_state.view(N, 69, 2)[:] = torch.randn(N, 69, 2, generator=gk)
+            env.dof_force_tensor[:] = torch.randn(N, 69, generator=gk) * 30
+            rec["state"].append(state.clone())
+            rec["dof_state"].append(env._dof_state.view(N, 69, 2).clone())
+            rec["dof_force"].append(env.dof_force_tensor.clone())
+
+    env.gym = ScriptedGym()
+
+    arrays = {}
+    arrays.update(npify(lib_data.as_dict(), "in.lib"))
+    arrays.update(npify(clock.__dict__, "in.clock"))
+    arrays["in.pd_action_offset"], arrays["in.pd_action_scale"] = env._pd_action_offset.numpy(), env._pd_action_scale.numpy()
+    arrays["in.dof_subset"] = env.dof_subset.numpy()
+    arrays["in.key_body_ids"] = env._key_body_ids.numpy()
+    arrays["in.num_amp_obs_steps"] = np.int64(S)
+    arrays["in.rew_power_coef"] = np.float32(cfg.rew_power_coef)
+    arrays["in.termination_distance"] = np.float32(cfg.termination_distance)
+    ga = torch.Generator().manual_seed(44)
+    for k in range(K):
+        actions = torch.rand(N, 69, generator=ga) * 2 - 1
+        arrays[f"in.actions.{k}"] = actions.numpy()
+        obs, rew, reset, extras = env.step(actions)
+        out = {
+            "obs": env.obs_buf, "rew": env.rew_buf, "reward_raw": env.reward_raw, "reset": env.reset_buf,
+            "terminate": extras["terminate"], "progress": env.progress_buf, "amp_obs": env.amp_obs,
+        }  # fmt: skip
+        arrays.update({f"out.step.{k}.{n}": v.detach().numpy().copy() for n, v in out.items()})
+        # clean_pufferl/env.py:133-135
+        reset_indices = torch.nonzero(env.reset_buf).squeeze(-1)
+        arrays[f"in.reset_indices.{k}"] = reset_indices.numpy()
+        torch.manual_seed(700 + k)
+        arrays[f"in.phase.{k}"] = torch.rand(reset_indices.shape).numpy()  # what sample_time_interval will draw
+        torch.manual_seed(700 + k)
+        if len(reset_indices) > 0:
+            env.reset(reset_indices)
+        out = {
+            "rigid_body_state": env._rigid_body_state.view(N, 24, 13), "root_states": env._humanoid_root_states,
+            "dof_state": env._dof_state.view(N, 69, 2), "obs": env.obs_buf, "progress": env.progress_buf,
+            "reset": env.reset_buf, "terminate": env._terminate_buf, "motion_start_times": env._motion_start_times,
+            "motion_start_times_offset": env._motion_start_times_offset, "global_offset": env._global_offset,
+            "amp_obs": env.amp_obs, "amp_obs_demo": env.fetch_amp_obs_demo(),
+        }  # fmt: skip
+        arrays.update({f"out.reset.{k}.{n}": v.detach().numpy().copy() for n, v in out.items()})
+    for n in ("pd_target", "state", "dof_state", "dof_force"):
+        assert len(rec[n]) == K, (n, len(rec[n]))
+        for k in range(K):
+            arrays[("out" if n == "pd_target" else "in") + f".{n}.{k}"] = rec[n][k].numpy()
+    save("env_rollout", arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     torch.manual_seed(0)
@@ -456,3 +638,4 @@ if __name__ == "__main__":
     case_sample_time()
     case_amp_obs()
     case_episode()
+    case_env_rollout()

@@ -135,6 +135,17 @@ def test_episode_bookkeeping(golden):
     replay_episode_golden(golden("episode"), new_state, O.episode_update)
 
 
+def test_env_rollout_vs_reference_step_and_reset(golden):
+    """oracle.OracleEnv against a recording of the reference's own HumanoidPHC.step / reset methods."""
+    from conftest import replay_env_rollout
+    from util_cpu import oracle_env_from_golden
+
+    g = golden("env_rollout")
+    env = oracle_env_from_golden(g)
+    assert replay_env_rollout(g, env) == 5
+    assert sum(int(g.out(f"step.{k}.terminate").sum()) for k in range(5)) > 0
+
+
 def test_fixtures_exercise_both_flag_values(golden):
     seen_reset, seen_term, seen_pass = set(), set(), set()
     for case in STEP_CASES:

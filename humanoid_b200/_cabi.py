@@ -172,6 +172,27 @@ class PhcEpisodeArgs(C.Structure):
     ]
 
 
+class PhcAmpEnvArgs(C.Structure):
+    _fields_ = [
+        ("body", PhcBodyState),
+        ("dof_pos", C.c_void_p),
+        ("dof_vel", C.c_void_p),
+        ("dof_stride", C.c_int64),
+        ("dof_elem_stride", C.c_int64),
+        ("key_body_ids", C.c_int32 * 8),
+        ("num_key_bodies", C.c_int32),
+        ("num_sel", C.c_int32),
+        ("dof_subset", C.c_void_p),
+        ("flags", C.c_uint32),
+        ("num_steps", C.c_int32),
+        ("obs_per_step", C.c_int32),
+        ("_pad0", C.c_int32),
+        ("amp_obs_buf", C.c_void_p),
+        ("amp_obs_demo_buf", C.c_void_p),
+        ("env_mask", C.c_void_p),
+    ]
+
+
 class PhcHostStepArgs(C.Structure):
     _fields_ = [
         (k, C.c_void_p)
@@ -247,6 +268,11 @@ SIGNATURES = {
          C.c_int64, C.c_void_p],
     ),  # fmt: skip
     "phc_episode_update": (C.c_int, [C.POINTER(PhcEpisodeArgs), C.c_int64, C.c_void_p]),
+    "phc_amp_step": (C.c_int, [C.POINTER(PhcAmpEnvArgs), C.c_int64, C.c_int32, C.c_void_p]),
+    "phc_amp_init_ref": (
+        C.c_int,
+        [C.c_void_p, C.POINTER(PhcAmpEnvArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p],
+    ),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -361,39 +361,37 @@ __global__ void imitation_obs_kernel(const float* __restrict__ root_pos, int64_t
 // joint j of the dof subset (exp map -> quaternion -> tan/norm, and its dof velocities), thread 0
 // also the root terms, threads < K the key-body positions.
 // ---------------------------------------------------------------------------------------
-__global__ void amp_obs_kernel(PhcAmpArgs a, int64_t n, float* __restrict__ out, int64_t out_stride) {
-  const int lane = threadIdx.x & 31;
-  const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (env >= n) return;
-  const int nj = a.num_sel / 3, K = a.num_key_bodies;
-  const Vec3 root_pos = ld3(a.root_pos + env * a.root_pos_stride);
-  Quat root_rot = ld4(a.root_rot + env * a.root_rot_stride);
-  if (!(a.flags & PHC_OBS_UPRIGHT)) root_rot = remove_base_rot(root_rot);
+// One AMP observation row by one warp.  `Src` supplies the inputs: the root state (every lane),
+// dof3(d, pos, vel) = position / velocity of three dof indices, key_pos(i) = position of key body i.
+template <class Src>
+__device__ __forceinline__ void amp_obs_row(const Src& src, int K, const int64_t* __restrict__ dof_subset, int num_sel,
+                                            uint32_t flags, int lane, float* __restrict__ row) {
+  const int nj = num_sel / 3;
+  const Vec3 root_pos = src.root_pos();
+  Quat root_rot = src.root_rot();
+  if (!(flags & PHC_OBS_UPRIGHT)) root_rot = remove_base_rot(root_rot);
   const Heading hi = heading_quat_inv(root_rot);
   const HeadingRot hr = heading_rot(hi);
-  float* row = out + env * out_stride;
   int col = 0;
-  if (a.flags & PHC_OBS_ROOT_HEIGHT) {
+  if (flags & PHC_OBS_ROOT_HEIGHT) {
     if (lane == 0) row[0] = root_pos.z;
     col = 1;
   }
   if (lane == 0) {
     float t6[6];
-    quat_tan_norm((a.flags & PHC_OBS_LOCAL_ROOT) ? heading_mul_left(hi, root_rot) : root_rot, t6);
+    quat_tan_norm((flags & PHC_OBS_LOCAL_ROOT) ? heading_mul_left(hi, root_rot) : root_rot, t6);
 #pragma unroll
     for (int k = 0; k < 6; ++k) row[col + k] = t6[k];
-    st3(row + col + 6, heading_rotate(hr, ld3(a.root_vel + env * a.root_vel_stride)));
-    st3(row + col + 9, heading_rotate(hr, ld3(a.root_ang_vel + env * a.root_ang_vel_stride)));
+    st3(row + col + 6, heading_rotate(hr, src.root_vel()));
+    st3(row + col + 9, heading_rotate(hr, src.root_ang_vel()));
   }
   col += 12;
   for (int j = lane; j < nj; j += 32) {  // dof_to_obs_smpl (:179-189) + the selected dof velocities
+    int64_t d[3];
     float e3[3], v3[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int64_t d = a.dof_subset ? a.dof_subset[3 * j + k] : 3 * j + k;
-      e3[k] = a.dof_pos[env * a.dof_pos_stride + d * a.dof_pos_elem_stride];
-      v3[k] = a.dof_vel[env * a.dof_vel_stride + d * a.dof_vel_elem_stride];
-    }
+    for (int k = 0; k < 3; ++k) d[k] = dof_subset ? dof_subset[3 * j + k] : 3 * j + k;
+    src.dof3(d, e3, v3);
     float t6[6];
     quat_tan_norm(exp_map_to_quat(Vec3{e3[0], e3[1], e3[2]}), t6);
 #pragma unroll
@@ -402,7 +400,150 @@ __global__ void amp_obs_kernel(PhcAmpArgs a, int64_t n, float* __restrict__ out,
     for (int k = 0; k < 3; ++k) row[col + 6 * nj + 3 * j + k] = v3[k];
   }
   col += 9 * nj;
-  if (lane < K) st3(row + col + 3 * lane, heading_rotate(hr, ld3(view_at(a.key_body_pos, env, lane)) - root_pos));
+  if (lane < K) st3(row + col + 3 * lane, heading_rotate(hr, src.key_pos(lane) - root_pos));
+}
+
+struct AmpSrcArrays {  // build_amp_observations_smpl's argument list, row `env`
+  const PhcAmpArgs& a;
+  int64_t env;
+  __device__ Vec3 root_pos() const { return ld3(a.root_pos + env * a.root_pos_stride); }
+  __device__ Quat root_rot() const { return ld4(a.root_rot + env * a.root_rot_stride); }
+  __device__ Vec3 root_vel() const { return ld3(a.root_vel + env * a.root_vel_stride); }
+  __device__ Vec3 root_ang_vel() const { return ld3(a.root_ang_vel + env * a.root_ang_vel_stride); }
+  __device__ void dof3(const int64_t* d, float* e3, float* v3) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      e3[k] = a.dof_pos[env * a.dof_pos_stride + d[k] * a.dof_pos_elem_stride];
+      v3[k] = a.dof_vel[env * a.dof_vel_stride + d[k] * a.dof_vel_elem_stride];
+    }
+  }
+  __device__ Vec3 key_pos(int i) const { return ld3(view_at(a.key_body_pos, env, i)); }
+};
+
+__global__ void amp_obs_kernel(PhcAmpArgs a, int64_t n, float* __restrict__ out, int64_t out_stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= n) return;
+  amp_obs_row(AmpSrcArrays{a, env}, a.num_key_bodies, a.dof_subset, a.num_sel, a.flags, lane, out + env * out_stride);
+}
+
+// ---------------------------------------------------------------------------------------
+// K11 / K12: the env's AMP observation buffers (envs/humanoid_phc.py:791-843, 1125-1176, 1341-1350).
+//   amp_step_kernel      one warp per env: history roll (slot k+1 <- slot k) + slot 0 from the sim state
+//   amp_init_ref_kernel  one warp per (env, slot) of the selected envs: slot k >= 1 from the motion library
+//                        at motion_time - k*dt, then the env's row copied to the demo buffer
+// ---------------------------------------------------------------------------------------
+constexpr int AMP_MAX_STEPS = 16;
+struct AmpEnvParams {
+  PhcBodyState body;
+  const float* dof_pos;
+  const float* dof_vel;
+  int64_t dof_stride, dof_estride;
+  int key_ids[8];
+  int K;
+  const int64_t* dof_subset;
+  int num_sel;
+  uint32_t flags;
+  float* buf;
+  float* demo;
+  int S, P;
+  const uint8_t* mask;
+  int roll;
+  int64_t n;
+};
+
+struct AmpSrcSim {  // _compute_amp_observations (:1125-1176): root = body 0 of the sim state
+  const AmpEnvParams& p;
+  int64_t env;
+  __device__ Vec3 root_pos() const { return ld3(view_at(p.body.pos, env, 0)); }
+  __device__ Quat root_rot() const { return ld4(view_at(p.body.rot, env, 0)); }
+  __device__ Vec3 root_vel() const { return ld3(view_at(p.body.vel, env, 0)); }
+  __device__ Vec3 root_ang_vel() const { return ld3(view_at(p.body.ang_vel, env, 0)); }
+  __device__ void dof3(const int64_t* d, float* e3, float* v3) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      e3[k] = p.dof_pos[env * p.dof_stride + d[k] * p.dof_estride];
+      v3[k] = p.dof_vel[env * p.dof_stride + d[k] * p.dof_estride];
+    }
+  }
+  __device__ Vec3 key_pos(int i) const { return ld3(view_at(p.body.pos, env, p.key_ids[i])); }
+};
+
+struct AmpSrcLib {  // _get_amp_obs (:821-838): get_motion_state at (id, t) without a global offset
+  const LibDev& L;
+  const int* key_ids;
+  int64_t f0, f1;
+  float bl;
+  __device__ Vec3 lerp_body(const float* tab, int per_frame, int b) const {
+    return lerp3(1.0f - bl, bl, ld3(tab + (f0 * per_frame + b) * 3), ld3(tab + (f1 * per_frame + b) * 3));
+  }
+  __device__ Vec3 root_pos() const { return lerp_body(L.gts, J24, 0); }
+  __device__ Quat root_rot() const { return quat_slerp(ld4v(L.grs + f0 * J24 * 4), ld4v(L.grs + f1 * J24 * 4), bl); }
+  __device__ Vec3 root_vel() const { return lerp_body(L.gvs, J24, 0); }
+  __device__ Vec3 root_ang_vel() const { return lerp_body(L.gavs, J24, 0); }
+  __device__ void dof3(const int64_t* d, float* e3, float* v3) const {
+    int last = -1;
+    Vec3 em{}, dv{};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {  // dof 3j+c belongs to body j+1 (motion_lib.py:670-673), dof velocity row j
+      const int j = (int)(d[k] / 3), c = (int)(d[k] % 3);
+      if (j != last) {
+        em = quat_exp_map(quat_slerp(ld4v(L.lrs + (f0 * J24 + j + 1) * 4), ld4v(L.lrs + (f1 * J24 + j + 1) * 4), bl));
+        dv = lerp_body(L.dvs, 23, j);
+        last = j;
+      }
+      e3[k] = c == 0 ? em.x : c == 1 ? em.y : em.z;
+      v3[k] = c == 0 ? dv.x : c == 1 ? dv.y : dv.z;
+    }
+  }
+  __device__ Vec3 key_pos(int i) const { return lerp_body(L.gts, J24, key_ids[i]); }
+};
+
+__global__ void amp_step_kernel(AmpEnvParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (env >= p.n || (p.mask && !p.mask[env])) return;
+  float* rows = p.buf + env * (int64_t)p.S * p.P;
+  if (p.roll) {
+    // _update_hist_amp_obs (:1341-1350).  A lane owns column i of every slot, so its loads of the old
+    // slots precede its stores in program order; only slot 0 is rewritten by other lanes afterwards.
+    for (int i = lane; i < p.P; i += 32) {
+      float v[AMP_MAX_STEPS - 1];
+#pragma unroll
+      for (int k = 0; k < AMP_MAX_STEPS - 1; ++k)
+        if (k < p.S - 1) v[k] = rows[k * p.P + i];
+#pragma unroll
+      for (int k = 0; k < AMP_MAX_STEPS - 1; ++k)
+        if (k < p.S - 1) rows[(k + 1) * p.P + i] = v[k];
+    }
+    __syncwarp();
+  }
+  amp_obs_row(AmpSrcSim{p, env}, p.K, p.dof_subset, p.num_sel, p.flags, lane, rows);
+}
+
+__global__ void amp_init_ref_kernel(AmpEnvParams p, LibDev L, const int64_t* __restrict__ motion_ids,
+                                    const float* __restrict__ motion_times, float dt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t env = w / p.S;
+  const int k = (int)(w % p.S);
+  if (env >= p.n || (p.mask && !p.mask[env])) return;
+  float* row = p.buf + (env * p.S + k) * (int64_t)p.P;
+  if (k > 0) {
+    const int64_t id = motion_ids[env];
+    // motion_times + (-dt * (arange(S-1) + 1)), both fp32 (:809-810)
+    const float t = motion_times[env] + (-dt) * (float)k;
+    int64_t i0, i1;
+    float bl;
+    calc_frame_blend(t, L.len[id], L.nf[id], L.mdt[id], i0, i1, bl);
+    const int64_t st = L.starts[id];
+    amp_obs_row(AmpSrcLib{L, p.key_ids, i0 + st, i1 + st, bl}, p.K, p.dof_subset, p.num_sel, p.flags, lane, row);
+    __syncwarp();
+  }
+  if (p.demo) {  // _amp_obs_demo_buf[env_ids] = _amp_obs_buf[env_ids] (:819)
+    float* drow = p.demo + (env * p.S + k) * (int64_t)p.P;
+    for (int i = lane; i < p.P; i += 32) drow[i] = row[i];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2373,6 +2514,67 @@ int phc_episode_update(const PhcEpisodeArgs* a, int64_t n, phc_stream_t stream) 
   p.ws = a->workspace;
   const int64_t blocks = std::min<int64_t>((n + 255) / 256, 148 * 4);
   episode_update_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  return launch_status();
+}
+
+static int amp_env_fill(const PhcAmpEnvArgs* a, int64_t n, AmpEnvParams& p) {
+  if (!a) return PHC_ERR_NULL;
+  if (n < 0) return PHC_ERR_SHAPE;
+  if (!a->amp_obs_buf || !a->body.pos.ptr || !a->body.rot.ptr || !a->body.vel.ptr || !a->body.ang_vel.ptr)
+    return PHC_ERR_NULL;
+  if (a->num_sel < 0 || a->num_sel % 3 != 0 || a->num_sel > 96 || a->num_key_bodies < 0 || a->num_key_bodies > 8 ||
+      a->num_steps < 1 || a->num_steps > AMP_MAX_STEPS)
+    return PHC_ERR_SHAPE;
+  const int width = ((a->flags & PHC_OBS_ROOT_HEIGHT) ? 1 : 0) + 12 + 3 * a->num_sel + 3 * a->num_key_bodies;
+  if (a->obs_per_step != width) return PHC_ERR_SHAPE;
+  for (int i = 0; i < a->num_key_bodies; ++i)
+    if (a->key_body_ids[i] < 0 || a->key_body_ids[i] >= a->body.num_bodies) return PHC_ERR_SHAPE;
+  p.body = a->body;
+  p.dof_pos = a->dof_pos;
+  p.dof_vel = a->dof_vel;
+  p.dof_stride = a->dof_stride;
+  p.dof_estride = a->dof_elem_stride;
+  for (int i = 0; i < 8; ++i) p.key_ids[i] = a->key_body_ids[i];
+  p.K = a->num_key_bodies;
+  p.dof_subset = a->dof_subset;
+  p.num_sel = a->num_sel;
+  p.flags = a->flags;
+  p.buf = a->amp_obs_buf;
+  p.demo = a->amp_obs_demo_buf;
+  p.S = a->num_steps;
+  p.P = a->obs_per_step;
+  p.mask = a->env_mask;
+  p.roll = 0;
+  p.n = n;
+  return PHC_OK;
+}
+
+int phc_amp_step(const PhcAmpEnvArgs* a, int64_t n, int32_t roll_history, phc_stream_t stream) {
+  AmpEnvParams p;
+  const int rc = amp_env_fill(a, n, p);
+  if (rc) return rc;
+  if (n == 0) return PHC_OK;
+  if (!a->dof_pos || !a->dof_vel) return PHC_ERR_NULL;
+  if (a->dof_elem_stride < 1) return PHC_ERR_SHAPE;
+  p.roll = roll_history ? 1 : 0;
+  const int epb = 4;
+  amp_step_kernel<<<(unsigned)((n + epb - 1) / epb), epb * 32, 0, stream>>>(p);
+  return launch_status();
+}
+
+int phc_amp_init_ref(const PhcLib* lib, const PhcAmpEnvArgs* a, const int64_t* motion_ids, const float* motion_times,
+                     float dt, int64_t n, phc_stream_t stream) {
+  AmpEnvParams p;
+  const int rc = amp_env_fill(a, n, p);
+  if (rc) return rc;
+  if (n == 0) return PHC_OK;
+  if (!lib || !motion_ids || !motion_times) return PHC_ERR_NULL;
+  if (!lib->d.lrs || !lib->d.dvs) return PHC_ERR_NULL;  // dof_pos / dof_vel need the local rotations and dof velocities
+  for (int i = 0; i < a->num_key_bodies; ++i)
+    if (a->key_body_ids[i] >= J24) return PHC_ERR_SHAPE;
+  const int wpb = 4;
+  const int64_t warps = n * p.S;
+  amp_init_ref_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p, lib->d, motion_ids, motion_times, dt);
   return launch_status();
 }
 

@@ -39,6 +39,7 @@ BODY_NAMES = (
 )  # PHC/body_sets.py:11-36  # fmt: skip
 REMOVE_NAMES = ("L_Hand", "R_Hand", "L_Toe", "R_Toe")  # body_sets.py:42
 EVAL_BODIES = tuple(n for n in BODY_NAMES if n not in REMOVE_NAMES)  # body_sets.py:57
+KEY_BODIES = ("R_Ankle", "L_Ankle", "R_Wrist", "L_Wrist")  # body_sets.py:45
 
 DEFAULT_REWARD = dict(  # asdict(RewardConfig), PHC/config.py:38-50
     k_pos=100.0, k_rot=10.0, k_vel=0.1, k_ang_vel=0.1, w_pos=0.5, w_rot=0.3, w_vel=0.1, w_ang_vel=0.1,
@@ -66,6 +67,8 @@ class HumanoidPHC:
         obs_moments: bool = False,
         use_power_reward: bool = False,  # config.py:50 (True in the reference; needs dof_force / dof_vel)
         rew_power_coef: float = 0.0005,  # config.py:112
+        use_amp_obs: bool = False,  # config.py:98
+        num_amp_obs_steps: int = 10,  # config.py:141
     ):
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -125,6 +128,29 @@ class HumanoidPHC:
         self._humanoid_root_states = torch.zeros((N, 13), dtype=torch.float32, device=dev)
         self.state_init_random = True  # StateInit.Random (config.py:110); False = StateInit.Start
         self.flag_test = False
+
+        # AMP observation buffers (humanoid_phc.py:186-194, 245, 469-478, 596-611)
+        self.use_amp_obs = bool(use_amp_obs)
+        self.num_amp_obs_steps = int(num_amp_obs_steps)
+        dof_names = BODY_NAMES[1:]
+        self.dof_subset = torch.tensor(
+            [3 * i + k for i, n in enumerate(dof_names) if n not in REMOVE_NAMES for k in range(3)],
+            dtype=torch.int64, device=dev,
+        )  # fmt: skip
+        self._key_body_ids = build_body_ids_tensor(BODY_NAMES, KEY_BODIES, dev)
+        self._key_body_ids_host = [BODY_NAMES.index(n) for n in KEY_BODIES]
+        self._num_amp_obs_per_step = (
+            13 + len(dof_names) * 6 + self.num_dof + 3 * len(KEY_BODIES)
+            - (6 + 3) * ((self.num_dof - len(self.dof_subset)) // 3)
+        )  # fmt: skip
+        self.num_amp_obs = self.num_amp_obs_steps * self._num_amp_obs_per_step
+        if self.use_amp_obs:
+            self._amp_obs_buf = torch.zeros(
+                (N, self.num_amp_obs_steps, self._num_amp_obs_per_step), dtype=torch.float32, device=dev
+            )
+            self._curr_amp_obs_buf = self._amp_obs_buf[:, 0]
+            self._hist_amp_obs_buf = self._amp_obs_buf[:, 1:]
+            self._amp_obs_demo_buf = torch.zeros_like(self._amp_obs_buf)
 
         self.obs_moments = (
             torch.zeros(2 * self.num_obs, dtype=torch.float64, device=dev) if obs_moments else None
@@ -281,7 +307,71 @@ class HumanoidPHC:
         self.post_physics_step(True)
         self.extras["terminate"] = self._terminate_buf
         self.extras["reward_raw"] = self.reward_raw
+        if self.use_amp_obs:  # :153-157
+            self._amp_step(roll=True)
+            self.extras["amp_obs"] = self.amp_obs
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # ------------------------------------------------------------------------------------
+    # AMP observation buffers (humanoid_phc.py:791-843, 1125-1176, 1341-1361)
+    # ------------------------------------------------------------------------------------
+    @property
+    def amp_obs(self):  # :1356-1358
+        return self._amp_obs_buf.view(-1, self.num_amp_obs) if self.use_amp_obs else None
+
+    def fetch_amp_obs_demo(self):  # :1360-1361
+        return self._amp_obs_demo_buf.view(-1, self.num_amp_obs) if self.use_amp_obs else None
+
+    def _amp_args(self, mask: Optional[torch.Tensor]):
+        body, keep = _cabi.body_state(
+            self._rigid_body_pos, self._rigid_body_rot, self._rigid_body_vel, self._rigid_body_ang_vel
+        )
+        a = _cabi.PhcAmpEnvArgs()
+        a.body = body
+        a.dof_pos, a.dof_vel = self._dof_pos.data_ptr(), self._dof_vel.data_ptr()
+        a.dof_stride, a.dof_elem_stride = self._dof_pos.stride(0), self._dof_pos.stride(1)
+        for i, b in enumerate(self._key_body_ids_host):
+            a.key_body_ids[i] = int(b)
+        a.num_key_bodies = len(self._key_body_ids_host)
+        a.num_sel = int(self.dof_subset.shape[0])
+        a.dof_subset = self.dof_subset.data_ptr()
+        a.flags = _cabi.OBS_LOCAL_ROOT | _cabi.OBS_ROOT_HEIGHT | _cabi.OBS_UPRIGHT  # the config's constants (:1206-1211)
+        a.num_steps, a.obs_per_step = self.num_amp_obs_steps, self._num_amp_obs_per_step
+        a.amp_obs_buf = self._amp_obs_buf.data_ptr()
+        a.amp_obs_demo_buf = self._amp_obs_demo_buf.data_ptr()
+        a.env_mask = _cabi.ptr(mask)
+        return a, keep
+
+    def _amp_step(self, roll: bool, mask: Optional[torch.Tensor] = None):
+        """``_update_hist_amp_obs()`` (when ``roll``) + ``_compute_amp_observations()``; one launch."""
+        a, keep = self._amp_args(mask)
+        _cabi.check(
+            _cabi.load().phc_amp_step(C.byref(a), self.num_envs, 1 if roll else 0, _cabi.stream_ptr(self.device)),
+            "phc_amp_step",
+        )
+
+    def _update_hist_amp_obs(self, env_ids=None):  # :1341-1350 (only reached through _amp_step here)
+        raise NotImplementedError("fused with _compute_amp_observations: use _amp_step(roll=True)")
+
+    def _compute_amp_observations(self, env_ids=None):  # :1125-1176
+        mask = None
+        if env_ids is not None:
+            mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+            mask[env_ids] = True
+        self._amp_step(roll=False, mask=mask)
+
+    def _init_amp_obs_masked(self, mask: torch.Tensor):
+        """``_init_amp_obs(env_ids)`` (:791-799) for the envs of a byte mask, right after their reset:
+        slot 0 from the freshly set sim state, the history from the motion library, the demo rows."""
+        self._amp_step(roll=False, mask=mask)
+        a, keep = self._amp_args(mask)
+        _cabi.check(
+            _cabi.load().phc_amp_init_ref(
+                self._motion_lib.handle, C.byref(a), self._sampled_motion_ids.data_ptr(),
+                self._motion_start_times.data_ptr(), self.dt, self.num_envs, _cabi.stream_ptr(self.device),
+            ),
+            "phc_amp_init_ref",
+        )  # fmt: skip
 
     # ------------------------------------------------------------------------------------
     # pre-physics: actions -> PD targets (humanoid_phc.py:105-128, 1218-1228)
@@ -347,6 +437,8 @@ class HumanoidPHC:
             _cabi.load().phc_reset_envs(self._motion_lib.handle, C.byref(a), self.num_envs, _cabi.stream_ptr(self.device)),
             "phc_reset_envs",
         )
+        if self.use_amp_obs:  # _reset_envs (:675-676)
+            self._init_amp_obs_masked(mask)
 
     def reset(self, env_ids=None, phase: Optional[torch.Tensor] = None):
         """``HumanoidPHC.reset(env_ids)`` (:90-103) with reference-state init: sample a start time

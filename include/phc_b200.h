@@ -405,6 +405,41 @@ typedef struct PhcEpisodeArgs {
 } PhcEpisodeArgs;
 PHC_API int phc_episode_update(const PhcEpisodeArgs* args, int64_t n, phc_stream_t stream);
 
+/* The env's AMP observation buffers                          envs/humanoid_phc.py:596-611
+ *   _amp_obs_buf [n, S, P]: slot 0 = _curr_amp_obs_buf, slots 1.. = _hist_amp_obs_buf; P as phc_amp_obs
+ *   writes it.  Dense.  `env_mask` (NULL = all envs) selects envs by a byte mask, as phc_reset_envs does.
+ *
+ * phc_amp_step: per-step update (:153-156) — with roll_history the history roll of
+ *   _update_hist_amp_obs (:1341-1350: slot k+1 <- slot k, i.e. the .clone() branch the reference takes on
+ *   its pinned torch), then _compute_amp_observations (:1125-1176) writes slot 0 from the sim state:
+ *   root = body 0, key bodies by id, dof_pos / dof_vel the strided dof-state views.  With
+ *   roll_history == 0 and a mask it is _compute_amp_observations(env_ids) of a reset (:792).
+ * phc_amp_init_ref: _init_amp_obs_ref (:805-819) for the selected envs — slot k >= 1 is the AMP
+ *   observation of clip motion_ids[env] at motion_times[env] - k*dt (_get_amp_obs :821-838, no global
+ *   offset), then the env's whole row is copied to amp_obs_demo_buf (may be NULL).  motion_ids /
+ *   motion_times are indexed by env (after a reset: _sampled_motion_ids / _motion_start_times). */
+typedef struct PhcAmpEnvArgs {
+  PhcBodyState body;           /* sim state views (phc_amp_step); num_bodies also bounds key_body_ids */
+  const float* dof_pos;        /* [n,69] view (phc_amp_step)       humanoid_phc.py:535 */
+  const float* dof_vel;        /* [n,69] view                      humanoid_phc.py:536 */
+  int64_t dof_stride;          /* row stride in elements (both views) */
+  int64_t dof_elem_stride;     /* 2 for the interleaved (pos, vel) dof state */
+  int32_t key_body_ids[8];     /* _key_body_ids                    humanoid_phc.py:245 */
+  int32_t num_key_bodies;
+  int32_t num_sel;             /* dofs used (69 when dof_subset is NULL), a multiple of 3 */
+  const int64_t* dof_subset;   /* NULL or [num_sel]                humanoid_phc.py:186-194 */
+  uint32_t flags;              /* PHC_OBS_LOCAL_ROOT | PHC_OBS_ROOT_HEIGHT | PHC_OBS_UPRIGHT */
+  int32_t num_steps;           /* S = num_amp_obs_steps <= 16      config.py:141 */
+  int32_t obs_per_step;        /* P */
+  int32_t _pad0;
+  float* amp_obs_buf;          /* [n, S, P] */
+  float* amp_obs_demo_buf;     /* [n, S, P] or NULL (phc_amp_init_ref) */
+  const uint8_t* env_mask;     /* NULL or [n] */
+} PhcAmpEnvArgs;
+PHC_API int phc_amp_step(const PhcAmpEnvArgs* args, int64_t n, int32_t roll_history, phc_stream_t stream);
+PHC_API int phc_amp_init_ref(const PhcLib* lib, const PhcAmpEnvArgs* args, const int64_t* motion_ids,
+                             const float* motion_times, float dt, int64_t n, phc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

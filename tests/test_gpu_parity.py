@@ -989,3 +989,56 @@ def test_fused_obs_normalisation_vs_oracle(N, T, generic):
     env.step()
     want = O.running_norm_forward(rn.running_mean.cpu(), rn.running_var.cpu(), env.obs_buf.cpu(), rn.epsilon, rn.clip)
     assert_close(env.obs_norm_buf, want, rtol=1e-5, atol=1e-6, what="fused normalised obs, second step")
+
+
+# ---------------------------------------------------------------------------------------
+# the whole env against a recording of the reference's own HumanoidPHC.step / reset
+# ---------------------------------------------------------------------------------------
+class _ShimUnderReplay:
+    """Adapts the CUDA shim to conftest.replay_env_rollout (default config of the reference: power reward,
+    frozen hands / toes, reference-state init, AMP observations on)."""
+
+    def __init__(self, g):
+        from humanoid_b200 import HumanoidPHC
+
+        clock = clock_from_golden(g)
+        N = clock.progress_buf.shape[0]
+        self.env = env = HumanoidPHC(
+            MotionLib(lib_from_golden(g), device=DEV), N, device=DEV, use_power_reward=True,
+            rew_power_coef=float(g.inp("rew_power_coef")), termination_distance=float(g.inp("termination_distance")),
+            use_amp_obs=True, num_amp_obs_steps=int(g.inp("num_amp_obs_steps")),
+        )  # fmt: skip
+        env.set_clock(clock.to(DEV))
+        env._pd_action_offset.copy_(g.inp("pd_action_offset"))
+        env._pd_action_scale.copy_(g.inp("pd_action_scale"))
+        assert torch.equal(env.dof_subset.cpu(), g.inp("dof_subset")) and torch.equal(env._key_body_ids.cpu(), g.inp("key_body_ids"))
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def write_sim(self, state, dof_state, dof_force):
+        env = self.env
+        env._rigid_body_state_reshaped.copy_(state)
+        env._humanoid_root_states.copy_(state[:, 0])
+        env._dof_state.view(-1, 69, 2).copy_(dof_state)
+        env.dof_force_tensor.copy_(dof_force)
+
+    def read_sim(self):
+        return self.env._rigid_body_state_reshaped, self.env._humanoid_root_states, self.env._dof_state.view(-1, 69, 2)
+
+    def step(self, actions, physics):
+        pd = self.env._action_to_pd_targets(cuda(actions), freeze_hand=True, freeze_toe=True)
+        physics(self)
+        self.env.step(cuda(actions))
+        return pd
+
+    def reset(self, env_ids, phase):
+        if len(env_ids):
+            self.env.reset(cuda(env_ids), cuda(phase))
+
+
+def test_env_rollout_vs_reference_step_and_reset(golden):
+    from conftest import replay_env_rollout
+
+    g = golden("env_rollout")
+    replay_env_rollout(g, _ShimUnderReplay(g), read=lambda t: t.cpu(), tol=OBS_TOL, dof_tol=DOF_TOL)

@@ -122,6 +122,7 @@ class PhcStepArgs(C.Structure):
         ("norm_var", C.c_void_p),
         ("norm_epsilon", C.c_float),
         ("norm_clip", C.c_float),
+        ("mpjpe", C.c_void_p),
     ]
 
 

@@ -792,6 +792,7 @@ struct StepParams {
   uint8_t* reset;
   uint8_t* term;
   double* moments;
+  float* mpjpe;     // NULL, or [n]: mean over the 24 bodies of |body_pos - ref_body_pos| (extras["mpjpe"])
   float* obs_norm;  // NULL, or the normalised copy of the obs rows (RunningNorm.forward)
   int64_t obs_norm_stride;
   const float* norm_mean;
@@ -1032,6 +1033,8 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
     }
     p.term[env] = fallen ? 1 : 0;
     p.reset[env] = S.pass[e] ? 1 : (fallen ? 1 : 0);  // common.py:362
+  } else if (outs && b == 5 && p.mpjpe) {
+    p.mpjpe[env] = row_sum24(&S.part[4][e][0]) / 24.0f;  // humanoid_phc.py:167
   }
   __syncwarp();
   if (outs && b == 0) {
@@ -1514,6 +1517,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       p.term[env0 + le] = fallen ? 1 : 0;
       p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
     }
+    if (act && k == 2 && p.mpjpe) p.mpjpe[env0 + le] = row_sum24(&S.part[4][le][0]) / 24.0f;  // humanoid_phc.py:167
   }
 
   if (p.obs_norm) {
@@ -1783,6 +1787,7 @@ __global__ void __launch_bounds__(MULTI_EPB* J24, 5) step_multi_kernel(const Ste
       p.term[env0 + le] = fallen ? 1 : 0;
       p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
     }
+    if (act && k == 2 && p.mpjpe) p.mpjpe[env0 + le] = row_sum24(&S.part[4][le][0]) / 24.0f;  // humanoid_phc.py:167
   }
 }
 
@@ -2220,6 +2225,7 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.reset = a->reset_buf;
   p.term = a->terminate_buf;
   p.moments = a->obs_moments;
+  p.mpjpe = a->mpjpe;
   p.obs_norm = a->obs_norm;
   p.obs_norm_stride = a->obs_norm_stride;
   p.norm_mean = a->norm_mean;

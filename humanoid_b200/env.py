@@ -158,6 +158,7 @@ class HumanoidPHC:
         self.obs_moment_rows = 0
         self.obs_normalizer = None  # set_obs_normalizer(): RunningNorm.forward fused into the step's epilogue
         self.obs_norm_buf = None
+        self._mpjpe = None
         self._step_args = None
 
     # ------------------------------------------------------------------------------------
@@ -210,6 +211,7 @@ class HumanoidPHC:
         self._termination_distances[:] = termination_distances
 
     def toggle_eval_mode(self):  # :1426-1440 (motion-lib swap is out of scope)
+        self.flag_test = True
         self.flag_im_eval = True
         self.set_termination_distances(0.5)
         if len(self._reset_bodies_id) > 15:
@@ -217,6 +219,7 @@ class HumanoidPHC:
         self._step_args = None
 
     def untoggle_eval_mode(self):
+        self.flag_test = False
         self.flag_im_eval = False
         self._termination_distances[:] = self._termination_distances_backup
         self._reset_bodies_id = self._reset_bodies_id_backup
@@ -254,6 +257,10 @@ class HumanoidPHC:
         a.reset_buf = self.reset_buf.data_ptr()
         a.terminate_buf = self._terminate_buf.data_ptr()
         a.obs_moments = self.obs_moments.data_ptr() if self.obs_moments is not None else None
+        if self.flag_im_eval:  # extras["mpjpe"] (:159-167), from the distances the reset test computes anyway
+            if self._mpjpe is None:
+                self._mpjpe = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+            a.mpjpe = self._mpjpe.data_ptr()
         if self.obs_normalizer is not None:  # policies/running_norm.py:15-20, fused
             rn = self.obs_normalizer
             a.obs_norm = self.obs_norm_buf.data_ptr()
@@ -310,6 +317,8 @@ class HumanoidPHC:
         if self.use_amp_obs:  # :153-157
             self._amp_step(roll=True)
             self.extras["amp_obs"] = self.amp_obs
+        if self.flag_im_eval:  # :159-167 (body_pos / body_pos_gt are host copies the caller can take itself)
+            self.extras["mpjpe"] = self._mpjpe
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     # ------------------------------------------------------------------------------------

@@ -254,6 +254,9 @@ typedef struct PhcStepArgs {
   const float* norm_var;                 /* [358+576*T] running_var                          */
   float norm_epsilon;                    /* 1e-5 in the reference                            */
   float norm_clip;                       /* 10.0 in the reference                            */
+  float* mpjpe;                          /* NULL or [n]: extras["mpjpe"] of eval mode, the mean over all
+                                            24 bodies of |rigid_body_pos - ref rg_pos| at the reward
+                                            time                              humanoid_phc.py:159-167 */
 } PhcStepArgs;
 
 PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream);

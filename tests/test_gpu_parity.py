@@ -257,6 +257,11 @@ def test_eval_mode_reset_vs_oracle():
     # may differ only when the mean is within 1 ulp of the threshold
     assert mism <= 1, f"{mism} eval-mode termination flags differ"
     assert 0.05 < o[4].float().mean() < 0.95
+    # extras["mpjpe"] (humanoid_phc.py:159-167): mean over all 24 bodies at the reward time
+    t = synth.reward_time(clock, extra_steps=1)
+    ref = O.OracleMotionLib(lib_data).get_motion_state(clock.sampled_motion_ids, t, clock.global_offset)
+    want = (state[:, :, 0:3] - ref["rg_pos"]).norm(dim=-1).mean(dim=-1)
+    assert_close(env.extras["mpjpe"], want, what="mpjpe", **OBS_TOL)
 
 
 # ---------------------------------------------------------------------------------------

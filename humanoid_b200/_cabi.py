@@ -204,6 +204,21 @@ class PhcHostStepArgs(C.Structure):
     ]  # fmt: skip
 
 
+BUILD_FILTER_RADIUS = 8
+
+
+class PhcBuildArgs(C.Structure):
+    _fields_ = [
+        ("pose_quat_global", C.c_void_p), ("root_trans", C.c_void_p), ("pose_aa", C.c_void_p),
+        ("local_translation", C.c_void_p), ("num_frames", C.c_void_p), ("length_starts", C.c_void_p),
+        ("fps", C.c_void_p), ("heading_zw", C.c_void_p),
+        ("parent_indices_host", C.POINTER(C.c_int32)), ("filter_weights_host", C.POINTER(C.c_double)),
+        ("total_frames", C.c_int64), ("num_motions", C.c_int64),
+        ("gts", C.c_void_p), ("grs", C.c_void_p), ("lrs", C.c_void_p), ("gvs", C.c_void_p), ("gavs", C.c_void_p),
+        ("dvs", C.c_void_p), ("motion_aa", C.c_void_p), ("scratch", C.c_void_p),
+    ]  # fmt: skip
+
+
 # name -> (restype, argtypes); every symbol include/phc_b200.h declares
 SIGNATURES = {
     "phc_strerror": (C.c_char_p, [C.c_int]),
@@ -274,6 +289,7 @@ SIGNATURES = {
         C.c_int,
         [C.c_void_p, C.POINTER(PhcAmpEnvArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p],
     ),
+    "phc_motion_build": (C.c_int, [C.POINTER(PhcBuildArgs), C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

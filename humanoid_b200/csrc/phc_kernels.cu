@@ -38,6 +38,8 @@ static inline int cuda_fail(cudaError_t e) {
     if (e__ != cudaSuccess) return cuda_fail(e__);  \
   } while (0)
 
+int record_cuda_error(int cuda_error) { return cuda_fail((cudaError_t)cuda_error); }  // for the other TUs
+
 static inline int launch_status() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? PHC_OK : cuda_fail(e);

@@ -443,6 +443,46 @@ PHC_API int phc_amp_step(const PhcAmpEnvArgs* args, int64_t n, int32_t roll_hist
 PHC_API int phc_amp_init_ref(const PhcLib* lib, const PhcAmpEnvArgs* args, const int64_t* motion_ids,
                              const float* motion_times, float dt, int64_t n, phc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Motion-library build: the per-clip work of MotionLibSMPL.load_motions (motion_lib.py:257-428,
+ * worker load_motion_with_skeleton :748-824) for all clips at once, on the device.  Inputs are the
+ * pkl entries of scripts/phc_convert_amass_data.py:186-194 concatenated on the frame axis (after
+ * the caller's max_length crop, :773-778) as fp64, exactly the dtypes the reference computes in:
+ *   heading (optional, :789-799)  -> rotates the global rotations, the root translation and
+ *                                    pose_aa[:, :3];
+ *   SkeletonState.from_rotation_and_root_translation(is_local=False) (:806) -> lrs (fp64 product
+ *   rounded to fp32, poselib_skeleton.py:575-594) and, by fp32 forward kinematics (:519-539), gts;
+ *   SkeletonMotion.from_skeleton_state (:810, poselib_skeleton.py:1167-1251) -> gvs (np.gradient +
+ *   gaussian_filter1d sigma 2 "nearest") and gavs; compute_motion_dof_vels_jit (:120-142) -> dvs.
+ * grvs / gravs are gvs[:,0] / gavs[:,0].  fix_trans_height (:696-745) needs the SMPL mesh model and
+ * is not implemented: this is the mesh_parsers == None path (:692-694, :801).  Clips need >= 2
+ * frames (np.gradient raises below that); shorter clips get zero velocities.
+ * ---------------------------------------------------------------------------------- */
+#define PHC_BUILD_FILTER_RADIUS 8 /* int(4.0 * sigma + 0.5), sigma = 2: scipy.ndimage.gaussian_filter1d */
+typedef struct PhcBuildArgs {
+  const double* pose_quat_global;     /* [F,24,4] xyzw, 32-B aligned      motion_lib.py:784 */
+  const double* root_trans;           /* [F,3] root_trans_offset          motion_lib.py:781 */
+  const double* pose_aa;              /* [F,72] or NULL                   motion_lib.py:783 */
+  const float* local_translation;     /* [M,24,3] skeleton_trees[m].local_translation (fp32, poselib_skeleton.py:318) */
+  const int64_t* num_frames;          /* [M] */
+  const int64_t* length_starts;       /* [M] exclusive prefix sum of num_frames */
+  const double* fps;                  /* [M] curr_file.get("fps", 30)     motion_lib.py:810 */
+  const double* heading_zw;           /* NULL or [M,2]: (sin, cos) of half the heading angle pi*(2u-1) */
+  const int32_t* parent_indices_host; /* HOST [24], -1 for the root, parents precede children */
+  const double* filter_weights_host;  /* HOST [17] gaussian taps, scipy's _gaussian_kernel1d(2, 0, 8) */
+  int64_t total_frames;               /* F */
+  int64_t num_motions;                /* M */
+  float* gts;                         /* [F,24,3] out */
+  float* grs;                         /* [F,24,4] out, 16-B aligned */
+  float* lrs;                         /* [F,24,4] out, 16-B aligned */
+  float* gvs;                         /* [F,24,3] out */
+  float* gavs;                        /* [F,24,3] out */
+  float* dvs;                         /* [F,23,3] out */
+  float* motion_aa;                   /* [F,72] out, NULL iff pose_aa is NULL */
+  double* scratch;                    /* [F,24,3] fp64 work space (raw angular velocities) */
+} PhcBuildArgs;
+PHC_API int phc_motion_build(const PhcBuildArgs* args, phc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

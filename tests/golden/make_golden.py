@@ -612,6 +612,103 @@ def case_env_rollout():
     save("env_rollout", arrays)
 
 
+def synth_build_clips(tree_parents, seed=5, shapes=((20, 30), (45, 30), (3, 30), (33, 60), (12, 30), (2, 30))):
+    """Synthetic stand-ins for the AMASS pkl entries (scripts/phc_convert_amass_data.py:186-194):
+    per clip ``root_trans_offset`` (torch f64), ``pose_aa`` (numpy f64 [B,72]), ``pose_quat_global``
+    (numpy f64 [B,24,4], a smooth rotation per joint composed down the SMPL tree), ``fps``."""
+    from scipy.spatial.transform import Rotation as R
+
+    rng = np.random.default_rng(seed)
+    clips = {}
+    for i, (B, fps) in enumerate(shapes):
+        base = R.random(24, random_state=100 + i)
+        w = rng.normal(size=(24, 3)) * 0.8
+        quat = np.zeros((B, 24, 4))
+        for f in range(B):
+            g = [None] * 24
+            for j in range(24):
+                loc = R.from_rotvec(w[j] * f / fps) * base[j]
+                g[j] = loc if tree_parents[j] < 0 else g[tree_parents[j]] * loc
+                quat[f, j] = g[j].as_quat()
+        if i == 4:  # quaternions that went through fp32 storage: unit only to 1e-8
+            quat = quat.astype(np.float32).astype(np.float64)
+        trans = np.cumsum(rng.normal(size=(B, 3)) * 0.02, 0) + np.array([0.3 * i, -0.2 * i, 0.9])
+        pose_aa = rng.normal(size=(B, 72)) * 0.7
+        pose_aa[:: 5, :3] *= 1e-4  # small-angle branch of from_rotvec / as_rotvec
+        clip = {"root_trans_offset": torch.from_numpy(trans), "pose_aa": pose_aa, "pose_quat_global": quat,
+                "beta": np.zeros(16), "gender": "neutral"}  # fmt: skip
+        if fps != 30:
+            clip["fps"] = fps  # the loader defaults to 30 (motion_lib.py:806)
+        clips[f"clip{i}"] = clip
+    return clips
+
+
+def case_motion_build():
+    """The reference's own ``MotionLibSMPL.load_motions`` (PHC/motion_lib.py:257-428, worker
+    ``load_motion_with_skeleton`` :748-824: forward kinematics and velocity estimation through
+    ``SkeletonState`` / ``SkeletonMotion`` of PHC/poselib_skeleton.py, ``compute_motion_dof_vels_jit`` :120)
+    on synthetic clips and the SMPL skeleton tree of the reference's MJCF asset.  ``__init__`` needs an AMASS
+    pkl + SMPL model files, so the object is made with ``object.__new__`` and the attributes ``load_data`` /
+    ``setup_constants`` would set; ``mesh_parsers`` is None as when the SMPL models are not found (:692-694).
+    Two variants: deterministic (no heading randomisation) and the training default (random heading per
+    clip, :789-799) under a fixed numpy seed; the fixture stores the uniform numbers that seed produces."""
+    import types
+
+    from puffer_phc.poselib_skeleton import SkeletonTree
+
+    tree = SkeletonTree.from_mjcf(os.path.join(ref_loader.REFERENCE_ROOT, "puffer_phc/assets/smpl_humanoid.xml"))
+    parents = tree.parent_indices.numpy()
+    g = torch.Generator().manual_seed(9)
+    # a second body shape: the env holds one tree per humanoid (humanoid_phc.py:208-209, :360)
+    tree2 = SkeletonTree(tree.node_names, tree.parent_indices,
+                         tree.local_translation * (1.0 + 0.1 * torch.rand(24, 3, generator=g)))  # fmt: skip
+    clips = synth_build_clips(parents)
+    M = len(clips)
+    trees = [tree if i % 2 == 0 else tree2 for i in range(M)]
+    gender_betas = [torch.cat([torch.zeros(1), torch.randn(16, generator=g)]) for _ in range(M)]
+    limb_weights = [np.random.default_rng(i).normal(size=10) for i in range(M)]
+
+    arrays = {
+        "in.parent_indices": parents.astype(np.int32),
+        "in.local_translation": np.stack([t.local_translation.numpy() for t in trees]),
+        "in.pose_quat_global": np.concatenate([c["pose_quat_global"] for c in clips.values()]),
+        "in.root_trans_offset": np.concatenate([c["root_trans_offset"].numpy() for c in clips.values()]),
+        "in.pose_aa": np.concatenate([c["pose_aa"] for c in clips.values()]).copy(),
+        "in.num_frames": np.asarray([c["pose_aa"].shape[0] for c in clips.values()], dtype=np.int64),
+        "in.fps": np.asarray([c.get("fps", 30) for c in clips.values()], dtype=np.int64),
+        "in.gender_betas": torch.stack(gender_betas).numpy(),
+        "in.limb_weights": np.stack(limb_weights),
+    }
+
+    def run(deterministic, seed):
+        import copy
+
+        data = copy.deepcopy(clips)  # the loader rotates pose_aa[:, :3] of its input in place (:794)
+        lib = object.__new__(ref_ml.MotionLibSMPL)
+        lib.m_cfg = types.SimpleNamespace(max_length=-1, fix_height=ref_ml.FixHeightMode.no_fix,
+                                          is_deterministic=deterministic, im_eval=False, num_thread=1)  # fmt: skip
+        lib._device, lib.mesh_parsers, lib.num_thread = "cpu", None, 1
+        lib._motion_data_list = np.array(list(data.values()))
+        lib._motion_data_keys = np.array(list(data.keys()))
+        lib._num_unique_motions = M
+        lib._sampling_prob = torch.ones(M) / M
+        np.random.seed(seed)
+        lib.load_motions(trees, gender_betas, limb_weights, random_sample=False)
+        out = {k: getattr(lib, k) for k in (
+            "gts", "grs", "lrs", "gvs", "gavs", "dvs", "grvs", "gravs", "_motion_aa", "_motion_lengths",
+            "_motion_num_frames", "_motion_dt", "_motion_fps", "length_starts", "_motion_bodies",
+            "_motion_limb_weights")}  # fmt: skip
+        return {k.lstrip("_"): v.numpy() for k, v in out.items()}
+
+    for k, v in run(True, 0).items():
+        arrays[f"out.deterministic.{k}"] = v
+    for k, v in run(False, 31).items():
+        arrays[f"out.random_heading.{k}"] = v
+    np.random.seed(31)
+    arrays["in.heading_u"] = np.asarray([np.random.random() for _ in range(M)])
+    save("motion_build", arrays)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     torch.manual_seed(0)
@@ -638,4 +735,5 @@ if __name__ == "__main__":
     case_sample_time()
     case_amp_obs()
     case_episode()
+    case_motion_build()
     case_env_rollout()

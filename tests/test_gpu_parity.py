@@ -1047,3 +1047,120 @@ def test_env_rollout_vs_reference_step_and_reset(golden):
 
     g = golden("env_rollout")
     replay_env_rollout(g, _ShimUnderReplay(g), read=lambda t: t.cpu(), tol=OBS_TOL, dof_tol=DOF_TOL)
+
+
+# ---------------------------------------------------------------------------------------
+# motion-library build (phc_motion_build) against the reference's own load_motions
+# ---------------------------------------------------------------------------------------
+def _clips_from_golden(g):
+    import numpy as np
+
+    nf = g.inp("num_frames").tolist()
+    starts = np.concatenate([[0], np.cumsum(nf)])
+    clips = {}
+    for m in range(len(nf)):
+        sl = slice(int(starts[m]), int(starts[m + 1]))
+        clip = {"root_trans_offset": g.inp("root_trans_offset")[sl], "pose_aa": g.inp("pose_aa")[sl].numpy(),
+                "pose_quat_global": g.inp("pose_quat_global")[sl].numpy(), "beta": np.zeros(16)}  # fmt: skip
+        if int(g.inp("fps")[m]) != 30:
+            clip["fps"] = int(g.inp("fps")[m])
+        clips[f"clip{m}"] = clip
+    return clips
+
+
+def _trees_from_golden(g):
+    from humanoid_b200.motion_build import SkeletonTree
+
+    names = [f"b{j}" for j in range(24)]
+    return [SkeletonTree(names, g.inp("parent_indices"), lt) for lt in g.inp("local_translation")]
+
+
+BUILD_EXACT = ("grs", "lrs", "gts", "gvs", "_motion_aa", "_motion_lengths", "_motion_num_frames", "_motion_dt",
+               "_motion_fps", "length_starts", "_motion_bodies", "_motion_limb_weights")  # fmt: skip
+
+
+@pytest.mark.parametrize("variant", ["deterministic", "random_heading"])
+def test_motion_build_vs_reference_load_motions(golden, variant):
+    import numpy as np
+
+    from humanoid_b200.motion_build import MotionLibSMPL
+
+    g = golden("motion_build")
+    lib = MotionLibSMPL(_clips_from_golden(g), device=DEV, is_deterministic=variant == "deterministic")
+    np.random.seed(31)  # the seed make_golden.py ran the reference's loader under
+    lib.load_motions(_trees_from_golden(g), list(g.inp("gender_betas")), g.inp("limb_weights").numpy(), random_sample=False)
+    for k in BUILD_EXACT + ("gavs", "dvs", "grvs", "gravs"):
+        got, want = getattr(lib, k).cpu(), g.out(f"{variant}.{k.lstrip('_')}")
+        assert got.dtype == want.dtype and got.shape == want.shape, k
+        if want.dtype == torch.int64:
+            assert_equal_exact(got, want, k)
+        elif k in BUILD_EXACT and variant == "deterministic":
+            # same roundings in the same order as the reference's mixed fp64/fp32 pipeline: no libm call on
+            # these outputs, so they are reproduced to the bit
+            assert torch.equal(got, want), f"{k}: {(got != want).sum()} of {got.numel()} differ, max {float((got - want).abs().max())}"
+        else:  # sin/cos/acos/atan2 of libdevice vs libm / SLEEF on the way
+            assert_close(got, want, what=f"{variant}.{k}", **OBS_TOL)
+    # the built library answers queries like one assembled from the reference's tensors
+    ids = torch.arange(lib.num_motions(), device=DEV).repeat(3)
+    t = torch.rand(ids.shape[0], device=DEV) * lib._motion_lengths[ids]
+    ref = MotionLib({k.lstrip("_"): g.out(f"{variant}.{k.lstrip('_')}") for k in BUILD_EXACT + ("gavs", "dvs")}, device=DEV)
+    a, b = lib.get_motion_state(ids, t), ref.get_motion_state(ids, t)
+    for k in MOTION_KEYS:
+        assert_close(a[k].cpu(), b[k].cpu(), what=f"query {k}", **(DOF_TOL if k == "dof_pos" else OBS_TOL))
+
+
+def test_motion_build_many_clips_vs_oracle():
+    """A few hundred ragged clips in one launch; spot clips (first, last, shortest, longest) against the oracle."""
+    import numpy as np
+    from scipy.spatial.transform import Rotation as R
+
+    from humanoid_b200.motion_build import build_motion_tensors
+    from oracle import build_oracle as B
+
+    rng = np.random.default_rng(3)
+    g_parents = [-1, 0, 1, 2, 3, 0, 5, 6, 7, 0, 9, 10, 11, 12, 11, 14, 15, 16, 17, 11, 19, 20, 21, 22]
+    M = 300
+    nf = rng.integers(2, 120, size=M)
+    nf[7], nf[11] = 2, 300
+    fps = rng.choice([30, 60, 120], size=M)
+    F = int(nf.sum())
+    quat = R.random(F * 24, random_state=5).as_quat().reshape(F, 24, 4)
+    # smooth in time within a clip: blend towards the previous frame and renormalise
+    for f in range(1, F):
+        quat[f] = 0.2 * quat[f] + 0.8 * quat[f - 1] * np.sign((quat[f] * quat[f - 1]).sum(-1, keepdims=True))
+        quat[f] /= np.linalg.norm(quat[f], axis=-1, keepdims=True)
+    trans = np.cumsum(rng.normal(size=(F, 3)) * 0.02, 0)
+    aa = rng.normal(size=(F, 72))
+    lt = (rng.normal(size=(M, 24, 3)) * 0.2).astype(np.float32)
+    u = rng.random(M)
+    for heading in (None, u):
+        out = build_motion_tensors(quat, trans, aa, nf, fps, g_parents, lt, heading_u=heading, device=DEV)
+        torch.cuda.synchronize()
+        starts = np.concatenate([[0], np.cumsum(nf)])
+        for m in (0, 7, 11, M - 1):
+            sl = slice(int(starts[m]), int(starts[m + 1]))
+            want = B.build_motion_library(quat[sl], trans[sl], aa[sl], [nf[m]], [fps[m]], g_parents, lt[m : m + 1],
+                                          np.zeros((1, 17)), np.zeros((1, 10)),
+                                          heading_u=None if heading is None else [u[m]])  # fmt: skip
+            for k in ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "motion_aa"):
+                # random i.i.d.-ish rotations: angular velocities reach ~100 rad/s, so a relative bound
+                assert_close(out[k][sl].cpu(), want[k], what=f"clip {m} {k}", rtol=2e-5, atol=2e-5)
+
+
+def test_motion_build_rejects_bad_arguments():
+    import numpy as np
+
+    from humanoid_b200 import _cabi
+    from humanoid_b200.motion_build import build_motion_tensors
+
+    q = np.zeros((4, 24, 4))
+    q[..., 3] = 1
+    par = [-1] + list(range(23))
+    with pytest.raises(_cabi.PhcError):  # a parent that follows its child
+        build_motion_tensors(q, np.zeros((4, 3)), None, [4], [30], [-1, 2, 1] + list(range(2, 23)), np.zeros((1, 24, 3)), device=DEV)
+    with pytest.raises(_cabi.PhcError):  # frame count mismatch
+        build_motion_tensors(q, np.zeros((4, 3)), None, [5], [30], par, np.zeros((1, 24, 3)), device=DEV)
+    with pytest.raises(_cabi.PhcError):
+        build_motion_tensors(q, np.zeros((4, 3)), None, [4], [30], par, np.zeros((1, 24, 3)), device="cpu")
+    out = build_motion_tensors(q, np.zeros((4, 3)), None, [4], [30], par, np.zeros((1, 24, 3)), device=DEV)
+    assert float(out["gvs"].abs().max()) == 0 and float(out["motion_aa"].abs().max()) == 0

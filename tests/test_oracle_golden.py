@@ -174,3 +174,55 @@ def test_amp_obs_variants(golden):
                            a["key_body_pos"], a["shape"], a["limb"], a["dof_subset"], *fl)  # fmt: skip
         assert_close(o, g.out(name), what=f"amp obs {name}", **TIGHT)
     assert g.out("default").shape[1] == 196
+
+
+# ---------------------------------------------------------------------------------------
+# motion-library build (the load side): oracle/build_oracle.py against the reference's own load_motions
+# ---------------------------------------------------------------------------------------
+BUILD_KEYS = ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "grvs", "gravs", "motion_aa", "motion_lengths",
+              "motion_num_frames", "motion_dt", "motion_fps", "length_starts", "motion_bodies", "motion_limb_weights")  # fmt: skip
+
+
+def oracle_build_from_golden(g, variant):
+    from oracle import build_oracle as B
+
+    return B.build_motion_library(
+        g.inp("pose_quat_global").numpy(), g.inp("root_trans_offset").numpy(), g.inp("pose_aa").numpy(),
+        g.inp("num_frames").tolist(), g.inp("fps").tolist(), g.inp("parent_indices").tolist(),
+        g.inp("local_translation").numpy(), g.inp("gender_betas").numpy(), g.inp("limb_weights").numpy(),
+        heading_u=g.inp("heading_u").tolist() if variant == "random_heading" else None,
+    )  # fmt: skip
+
+
+@pytest.mark.parametrize("variant", ["deterministic", "random_heading"])
+def test_motion_build_against_reference_load_motions(golden, variant):
+    g = golden("motion_build")
+    torch.set_num_threads(1)
+    out = oracle_build_from_golden(g, variant)
+    for k in BUILD_KEYS:
+        want = g.out(f"{variant}.{k}")
+        assert out[k].dtype == want.dtype and out[k].shape == want.shape, k
+        if want.dtype == torch.int64:
+            assert_equal_exact(out[k], want, k)
+        else:
+            assert_close(out[k], want, what=f"{variant}.{k}", **TIGHT)
+    # the fixture covers: a 2-frame clip, a 3-frame clip (shorter than the filter), a 60 fps clip
+    assert g.inp("num_frames").min() == 2 and set(g.inp("fps").tolist()) == {30, 60}
+
+
+def test_motion_build_host_constants_match_scipy(golden):
+    """The two host-side constants the CUDA build takes: scipy's gaussian taps and the heading quaternion."""
+    from scipy.ndimage import _filters
+    from scipy.spatial.transform import Rotation as sRot
+
+    from humanoid_b200 import motion_build as MB
+
+    import numpy as np
+
+    assert np.array_equal(MB.gaussian_taps(), _filters._gaussian_kernel1d(2.0, 0, 8))
+    u = golden("motion_build").inp("heading_u").numpy()
+    zw = MB.heading_half_angle(u)
+    for i, ui in enumerate(u):
+        q = sRot.from_euler("xyz", [0.0, 0.0, np.pi * (2 * ui - 1.0)]).as_quat()
+        assert q[0] == 0 and q[1] == 0
+        assert np.allclose(zw[i], q[2:], rtol=0, atol=2e-16)

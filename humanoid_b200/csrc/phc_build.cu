@@ -98,7 +98,8 @@ struct BuildParams {
   const double* heading; // [M,2] (z, w) or null
   int64_t F, M;
   float *gts, *grs, *lrs, *gvs, *gavs, *dvs, *motion_aa;
-  double* av_raw;  // [F,24,3] scratch
+  double* av_raw;  // [F,24,3] scratch: unfiltered angular velocity
+  float* vel_raw;  // [F,24,3] scratch: np.gradient(gts) / dt
   double w[2 * R + 1];
   int8_t parent[J];
   int8_t depth[J];
@@ -237,8 +238,18 @@ __global__ void __launch_bounds__(256) build_pose_kernel(const BuildParams p) {
   }
 }
 
+// np.gradient over the clip's frame axis, uniform spacing 1, edge_order 1; then / time_delta, all in fp32
+__device__ __forceinline__ float gradient_at(const float* __restrict__ col, int64_t i, int64_t nf, float dtf) {
+  float g;
+  if (i == 0) g = col[72] - col[0];
+  else if (i == nf - 1) g = col[i * 72] - col[(i - 1) * 72];
+  else g = (col[(i + 1) * 72] - col[(i - 1) * 72]) / 2.0f;
+  return g / dtf;
+}
+
 // ---------------------------------------------------------------------------------------------
-// Kernel B — one thread per (frame, joint): raw angular velocity (fp64 scratch) and dof velocity.
+// Kernel B — one thread per (frame, joint): unfiltered linear (fp32) and angular (fp64) velocity into the
+//            scratch, and the dof velocity.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_diff_kernel(const BuildParams p) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,6 +278,15 @@ __global__ void __launch_bounds__(256) build_diff_kernel(const BuildParams p) {
   o[1] = av.y;
   o[2] = av.z;
 
+  if (nf >= 2) {  // _compute_velocity, poselib_skeleton.py:1231-1236, before the filter
+    const float dtf = (float)td;
+    const float* col = p.gts + (f - k) * 72 + j * 3;
+    float* v = p.vel_raw + idx * 3;
+    v[0] = gradient_at(col, k, nf, dtf);
+    v[1] = gradient_at(col + 1, k, nf, dtf);
+    v[2] = gradient_at(col + 2, k, nf, dtf);
+  }
+
   if (j == 0) return;
   // compute_motion_dof_vels_jit, motion_lib.py:120-142: frames (k, k+1); the last frame repeats
   float* dv = p.dvs + (f * (J - 1) + (j - 1)) * 3;
@@ -292,18 +312,10 @@ __global__ void __launch_bounds__(256) build_diff_kernel(const BuildParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Kernel C — one thread per (frame, joint*3+c): gaussian_filter1d(sigma 2, mode nearest) of
-// np.gradient(gts)/dt -> gvs and of the raw angular velocity -> gavs.
+// Kernel C — one thread per (frame, joint*3+c): gaussian_filter1d(sigma 2, mode "nearest") of the two
+//            unfiltered velocities -> gvs, gavs.  scipy's correlate1d accumulates in fp64: centre tap
+//            first, then the symmetric pairs from the outside in.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gradient_at(const float* __restrict__ col, int64_t i, int64_t nf, float dtf) {
-  // np.gradient, uniform spacing 1, edge_order 1; then / time_delta, all in fp32
-  float g;
-  if (i == 0) g = col[72] - col[0];
-  else if (i == nf - 1) g = col[i * 72] - col[(i - 1) * 72];
-  else g = (col[(i + 1) * 72] - col[(i - 1) * 72]) / 2.0f;
-  return g / dtf;
-}
-
 __global__ void __launch_bounds__(256) build_filter_kernel(const BuildParams p) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.F * 72) return;
@@ -318,16 +330,15 @@ __global__ void __launch_bounds__(256) build_filter_kernel(const BuildParams p) 
     p.gavs[idx] = 0.0f;
     return;
   }
-  const float dtf = (float)(1.0 / __ldg(p.fps + m));
-  const float* pos = p.gts + s0 * 72 + e;
+  const float* vel = p.vel_raw + s0 * 72 + e;
   const double* av = p.av_raw + s0 * 72 + e;
   auto clampi = [nf](int64_t i) { return i < 0 ? (int64_t)0 : (i > nf - 1 ? nf - 1 : i); };
-  double acc_v = (double)gradient_at(pos, k, nf, dtf) * p.w[R];
+  double acc_v = (double)vel[k * 72] * p.w[R];
   double acc_a = av[k * 72] * p.w[R];
 #pragma unroll
   for (int jj = -R; jj < 0; ++jj) {
     const int64_t lo = clampi(k + jj), hi = clampi(k - jj);
-    acc_v += ((double)gradient_at(pos, lo, nf, dtf) + (double)gradient_at(pos, hi, nf, dtf)) * p.w[R + jj];
+    acc_v += ((double)vel[lo * 72] + (double)vel[hi * 72]) * p.w[R + jj];
     acc_a += (av[lo * 72] + av[hi * 72]) * p.w[R + jj];
   }
   p.gvs[idx] = (float)acc_v;
@@ -367,6 +378,7 @@ extern "C" int phc_motion_build(const PhcBuildArgs* a, phc_stream_t stream) {
   p.dvs = a->dvs;
   p.motion_aa = a->motion_aa;
   p.av_raw = a->scratch;
+  p.vel_raw = reinterpret_cast<float*>(a->scratch + a->total_frames * J * 3);
   for (int i = 0; i < 2 * R + 1; ++i) p.w[i] = a->filter_weights_host[i];
   p.max_depth = 0;
   for (int j = 0; j < J; ++j) {  // topological order: a parent precedes its children (SkeletonTree.from_mjcf)

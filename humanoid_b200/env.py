@@ -476,6 +476,30 @@ class HumanoidPHC:
         self._reset_masked(self.reset_buf.clone(), phase_by_env.to(self.device, torch.float32).contiguous())
         return self.obs_buf
 
+    def set_humanoid_assets(self, skeleton_trees, humanoid_shapes, humanoid_limb_and_weights):
+        """What ``_load_motion`` / ``resample_motions`` hand the loader (humanoid_phc.py:360, 418-419, 640-647):
+        one skeleton tree, one [17] gender+beta row and one [10] limb-weight row per env."""
+        self.skeleton_trees = list(skeleton_trees)
+        self.humanoid_shapes = humanoid_shapes
+        self.humanoid_limb_and_weights = humanoid_limb_and_weights
+
+    def resample_motions(self, seq_motions: bool = False, phase: Optional[torch.Tensor] = None):
+        """``resample_motions`` (:1363-1379), training branch: rebuild the library on the device from a fresh
+        sample of clips (``MotionLibSMPL.load_motions``), re-anchor the xy global offset so every env's
+        reference root passes through where its humanoid stands now, then reset every env."""
+        if self.flag_test:
+            raise _cabi.PhcError("forward_motion_samples (evaluation sweep, :1391-1402) is not part of the shim")
+        self._motion_lib.load_motions(
+            skeleton_trees=self.skeleton_trees,
+            limb_weights=self.humanoid_limb_and_weights.cpu(),
+            gender_betas=self.humanoid_shapes.cpu(),
+            random_sample=(not self.flag_test) and (not seq_motions),
+        )
+        time = self.progress_buf * self.dt + self._motion_start_times + self._motion_start_times_offset
+        root_res = self._motion_lib.get_root_pos_smpl(self._sampled_motion_ids, time)
+        self._global_offset[:, :2] = self._humanoid_root_states[:, :2] - root_res["root_pos"][:, :2]
+        return self.reset(phase=phase)
+
     # ------------------------------------------------------------------------------------
     # the reference's decomposition, on the per-function kernels
     # ------------------------------------------------------------------------------------

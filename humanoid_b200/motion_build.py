@@ -61,13 +61,15 @@ def _as_np64(x) -> np.ndarray:
 
 def build_motion_tensors(
     pose_quat_global, root_trans, pose_aa, num_frames, fps, parent_indices, local_translation,
-    heading_u=None, device="cuda",
+    heading_u=None, device="cuda", pin: bool = False,
 ) -> Dict[str, torch.Tensor]:  # fmt: skip
     """Clips concatenated on the frame axis -> the device tensors of motion_lib.py:396-403.
 
     ``pose_quat_global [F,24,4]``, ``root_trans [F,3]``, ``pose_aa [F,72]`` (or None) are fp64 as in the pkl
     (scripts/phc_convert_amass_data.py:186-194); ``local_translation [M,24,3]`` fp32 is one skeleton per clip;
-    ``heading_u [M]`` are the uniform numbers of the random heading, None for the deterministic path."""
+    ``heading_u [M]`` are the uniform numbers of the random heading, None for the deterministic path.
+    ``pin`` stages the inputs through freshly pinned memory first; for a one-shot upload the pageable copy is
+    faster (allocating 1 GB of pinned memory costs more than it saves, ``profiles/r1_motion_build.md``)."""
     dev = torch.device(device)
     if dev.type != "cuda":
         raise _cabi.PhcError("the motion-library build runs on the device: pass device='cuda' (there is no CPU path)")
@@ -83,9 +85,9 @@ def build_motion_tensors(
     if M and int(nf.min()) < 1:
         raise _cabi.PhcError("every clip needs at least one frame")
 
-    def up(a, dtype):  # pinned staging -> one async copy each
+    def up(a, dtype):  # one copy each
         t = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
-        return t.pin_memory().to(dev, non_blocking=True) if t.numel() else t.to(dev)
+        return t.pin_memory().to(dev, non_blocking=True) if pin and t.numel() else t.to(dev)
 
     d_quat, d_trans = up(quat, torch.float64), up(trans, torch.float64)
     d_aa = None
@@ -104,7 +106,7 @@ def build_motion_tensors(
     J = _cabi.NUM_BODIES
     out = {"gts": f32(F, J, 3), "grs": f32(F, J, 4), "lrs": f32(F, J, 4), "gvs": f32(F, J, 3), "gavs": f32(F, J, 3),
            "dvs": f32(F, J - 1, 3), "motion_aa": f32(F, J * 3)}  # fmt: skip
-    scratch = torch.empty((F, J, 3), dtype=torch.float64, device=dev)
+    scratch = torch.empty(F * 108, dtype=torch.float64, device=dev)  # PhcBuildArgs.scratch
     parents = (C.c_int32 * J)(*[int(p) for p in np.asarray(parent_indices).tolist()])
     taps = (C.c_double * (2 * _cabi.BUILD_FILTER_RADIUS + 1))(*gaussian_taps().tolist())
     if d_aa is None:
@@ -126,7 +128,7 @@ class MotionLibSMPL(MotionLib):
     """``MotionLibSMPL(motion_data, device, ...)`` then ``load_motions(skeleton_trees, gender_betas,
     limb_weights, ...)`` as in the reference (motion_lib.py:676-694, :257); queries are inherited."""
 
-    def __init__(self, motion_data: Dict[str, dict], device="cuda", max_length: int = -1,
+    def __init__(self, motion_data, device="cuda", max_length: int = -1,
                  is_deterministic: bool = False, im_eval: bool = False):  # fmt: skip
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -134,7 +136,11 @@ class MotionLibSMPL(MotionLib):
         self._device = dev
         self._handle = None
         self.max_length, self.is_deterministic, self.im_eval = int(max_length), bool(is_deterministic), bool(im_eval)
-        # load_data, motion_lib.py:227-243
+        # load_data, motion_lib.py:227-243: a joblib pkl of {clip name: entry} (scripts/phc_convert_amass_data.py:186-194)
+        if isinstance(motion_data, (str, bytes)) or hasattr(motion_data, "__fspath__"):
+            import joblib
+
+            motion_data = joblib.load(motion_data)
         self._motion_data_keys = np.array(list(motion_data.keys()))
         self._motion_data_list = list(motion_data.values())
         self._num_unique_motions = len(self._motion_data_list)
@@ -204,7 +210,8 @@ class MotionLibSMPL(MotionLib):
             motion_dt=torch.tensor((1.0 / fps64).tolist(), dtype=torch.float32),
             motion_fps=torch.tensor(fps64.tolist(), dtype=torch.float32),
             motion_bodies=torch.stack(bodies),
-            motion_limb_weights=torch.tensor(np.array(limb_weights), dtype=torch.float32),
+            motion_limb_weights=(limb_weights.detach().clone() if isinstance(limb_weights, torch.Tensor)
+                                 else torch.tensor(np.array(limb_weights))).to(torch.float32),
         )
         if self._handle:
             self.__del__()

@@ -95,6 +95,12 @@ class MotionLib:
     def handle(self) -> C.c_void_p:
         return self._handle
 
+    # -- get_root_pos_smpl (motion_lib.py:628-653) -------------------------------------------
+    def get_root_pos_smpl(self, motion_ids, motion_times):
+        """Blended root position without the global offset: the same ``(1-b)*p0 + b*p1`` on body 0 that
+        ``get_motion_state`` returns as ``root_pos`` (called once per motion resample, humanoid_phc.py:1377)."""
+        return {"root_pos": self.get_motion_state(motion_ids, motion_times)["root_pos"]}
+
     # -- _calc_frame_blend (motion_lib.py:655-665) -----------------------------------------
     def _calc_frame_blend(self, time, len, num_frames, dt):  # noqa: A002 - the reference's names
         for t, nm, dty in ((time, "time", torch.float32), (len, "len", torch.float32),

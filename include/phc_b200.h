@@ -479,7 +479,8 @@ typedef struct PhcBuildArgs {
   float* gavs;                        /* [F,24,3] out */
   float* dvs;                         /* [F,23,3] out */
   float* motion_aa;                   /* [F,72] out, NULL iff pose_aa is NULL */
-  double* scratch;                    /* [F,24,3] fp64 work space (raw angular velocities) */
+  double* scratch;                    /* F*108 doubles of work space: [F,24,3] fp64 unfiltered angular velocity, then
+                                         [F,24,3] fp32 unfiltered linear velocity */
 } PhcBuildArgs;
 PHC_API int phc_motion_build(const PhcBuildArgs* args, phc_stream_t stream);
 

@@ -828,3 +828,13 @@ class OracleEnv:
             init_amp_obs_ref(self.lib, self._amp_obs_buf, self._amp_obs_demo_buf, env_ids,
                              self._sampled_motion_ids[env_ids], self._motion_start_times[env_ids], self.dt,
                              self._key_body_ids, self.dof_subset)  # fmt: skip
+
+    def resample_motions(self, new_lib: OracleMotionLib, phase: Tensor):
+        """resample_motions, humanoid_phc.py:1363-1379 (training branch).  ``new_lib`` is what ``load_motions``
+        built (oracle/build_oracle.py); get_root_pos_smpl (motion_lib.py:628-653) is the root row of the same
+        position blend ``get_motion_state`` does, without the offset."""
+        self.lib = new_lib
+        time = self.progress_buf * self.dt + self._motion_start_times + self._motion_start_times_offset
+        root_pos = new_lib.get_motion_state(self._sampled_motion_ids, time)["root_pos"]
+        self._global_offset[:, :2] = self.root_states[:, :2] - root_pos[:, :2]
+        self.reset(torch.arange(self.N), phase)

@@ -1164,3 +1164,69 @@ def test_motion_build_rejects_bad_arguments():
         build_motion_tensors(q, np.zeros((4, 3)), None, [4], [30], par, np.zeros((1, 24, 3)), device="cpu")
     out = build_motion_tensors(q, np.zeros((4, 3)), None, [4], [30], par, np.zeros((1, 24, 3)), device=DEV)
     assert float(out["gvs"].abs().max()) == 0 and float(out["motion_aa"].abs().max()) == 0
+
+
+def test_resample_motions_rebuilds_the_library_and_resets_vs_oracle(golden):
+    """HumanoidPHC.resample_motions (:1363-1379): load_motions on the device, xy re-anchoring of the global
+    offset, reset of every env — against the oracle env on the oracle-built library, with a step either side."""
+    import numpy as np
+
+    from humanoid_b200 import HumanoidPHC
+    from humanoid_b200.motion_build import MotionLibSMPL
+    from oracle import build_oracle as B
+
+    g = golden("motion_build")
+    clips, trees = _clips_from_golden(g), _trees_from_golden(g)
+    M = len(clips)
+    N = 2 * M  # env e holds clip (e + start_idx) % M and env e's skeleton
+    trees = [trees[e % M] for e in range(N)]
+    shapes, limbs = g.inp("gender_betas").repeat(2, 1), g.inp("limb_weights").repeat(2, 1).float()
+    starts = np.concatenate([[0], np.cumsum(g.inp("num_frames").tolist())])
+
+    def oracle_lib(order):
+        sl = [slice(int(starts[m]), int(starts[m + 1])) for m in order]
+        cat = lambda k: np.concatenate([g.inp(k).numpy()[s] for s in sl])  # noqa: E731
+        return O.OracleMotionLib(B.build_motion_library(
+            cat("pose_quat_global"), cat("root_trans_offset"), cat("pose_aa"), [int(g.inp("num_frames")[m]) for m in order],
+            [int(g.inp("fps")[m]) for m in order], g.inp("parent_indices").tolist(),
+            np.stack([t.local_translation.numpy() for t in trees]), shapes.numpy(), limbs.numpy()))  # fmt: skip
+
+    lib = MotionLibSMPL(clips, device=DEV, is_deterministic=True)
+    lib.load_motions(trees, list(shapes), limbs.numpy(), start_idx=0)
+    env = HumanoidPHC(lib, N, device=DEV, use_amp_obs=True)
+    env.set_humanoid_assets(trees, shapes, limbs)
+    order0 = [e % M for e in range(N)]
+    zeros = torch.zeros(N)
+    ref = O.OracleEnv(oracle_lib(order0), N, torch.zeros(N, dtype=torch.short), zeros, zeros, torch.zeros(N, 3),
+                      torch.arange(N), torch.zeros(69), torch.ones(69), env.dof_subset.cpu(), env._key_body_ids.cpu(),
+                      rew_power_coef=0.0)  # fmt: skip
+    gen = torch.Generator().manual_seed(4)
+    phase = torch.rand(N, generator=gen)
+    env.reset(phase=cuda(phase))
+    ref.reset(torch.arange(N), phase)
+
+    def physics(e):  # a drifted copy of the posed state stands in for PhysX
+        e.state[:] = e.state + 0.01
+        e.root_states[:] = e.state[:, 0]
+
+    def step_both():
+        ref.step(torch.zeros(N, 69), physics)
+        env._rigid_body_state_reshaped.copy_(ref.state)
+        env._humanoid_root_states.copy_(ref.root_states)
+        env._dof_state.view(N, 69, 2).copy_(ref.dof_state)
+        env.step()
+        assert_equal_exact(env.reset_buf.cpu(), ref.reset_buf, "reset_buf")
+        assert_close(env.obs_buf.cpu(), ref.obs_buf, what="obs", **OBS_TOL)
+
+    step_both()
+    # the loader's start_idx is host state of the caller in the reference too (forward_motion_samples :1391-1402);
+    # resample with the sequential branch so both sides load the same clips
+    phase2 = torch.rand(N, generator=gen)
+    env.resample_motions(seq_motions=True, phase=cuda(phase2))
+    ref.resample_motions(oracle_lib(order0), phase2)
+    assert_close(env._global_offset.cpu(), ref._global_offset, what="global offset", rtol=1e-6, atol=1e-6)
+    assert_close(env._motion_start_times.cpu(), ref._motion_start_times, what="start times", rtol=0, atol=0)
+    assert_close(env._rigid_body_state_reshaped.cpu(), ref.state, what="posed state", **OBS_TOL)
+    assert_close(env.obs_buf.cpu(), ref.obs_buf, what="obs after resample", **OBS_TOL)
+    assert_close(env.amp_obs.cpu().view(N, -1), ref._amp_obs_buf.view(N, -1), what="amp obs", **DOF_TOL)
+    step_both()

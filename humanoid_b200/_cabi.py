@@ -22,6 +22,9 @@ SELF_OBS_DIM = 358
 TASK_OBS_DIM = 576
 MAX_TIME_STEPS = 16
 
+STEP_MAPPED_HOST_IO = 1
+STEP_OBS_NORM_BF16 = 2
+
 OPT_FORCE_GENERIC_STEP = 1
 OPT_STEP_EPB = 2
 OPT_STEP_PDL = 3

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/phc_b200.h"
@@ -800,6 +801,7 @@ struct StepParams {
   const float* norm_mean;
   const float* norm_var;
   float norm_eps, norm_clip;
+  int norm_bf16;  // obs_norm holds bfloat16 rows (PHC_STEP_OBS_NORM_BF16)
   const float* dof_force;  // power reward inputs (NULL = off)
   int64_t dof_force_stride;
   const float* dof_vel;
@@ -1133,8 +1135,10 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
         norm_column(p, c_off + c, m, sd, r);
         for (int ee = 0; ee < nvalid; ++ee) {
           if (!S.act[ee]) continue;
-          p.obs_norm[(env0 + ee) * p.obs_norm_stride + c_off + c] =
-              norm_value(S.buf[ee * STAGE_FLOATS + s_off + c], m, sd, r, p.norm_clip);
+          const float v = norm_value(S.buf[ee * STAGE_FLOATS + s_off + c], m, sd, r, p.norm_clip);
+          const int64_t at = (env0 + ee) * p.obs_norm_stride + c_off + c;
+          if (p.norm_bf16) reinterpret_cast<__nv_bfloat16*>(p.obs_norm)[at] = __float2bfloat16_rn(v);
+          else p.obs_norm[at] = v;
         }
       }
     }
@@ -1527,6 +1531,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     // bulk store drains them) and leave normalised with coalesced 8-byte stores; mean / var are 7.5 KB
     // that every block reads from L2
     float2* dst = reinterpret_cast<float2*>(p.obs_norm + env0 * STAGE_FLOATS);
+    __nv_bfloat162* dst16 = reinterpret_cast<__nv_bfloat162*>(p.obs_norm) + env0 * (STAGE_FLOATS / 2);
     const float2* src = reinterpret_cast<const float2*>(S.frames);
     for (int c2 = tid; c2 < STAGE_FLOATS / 2; c2 += NT) {
       float m0, sd0, r0, m1, sd1, r1;
@@ -1534,8 +1539,9 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       norm_column(p, 2 * c2 + 1, m1, sd1, r1);
       for (int ee = 0; ee < nvalid; ++ee) {
         const float2 x = src[ee * (STAGE_FLOATS / 2) + c2];
-        dst[ee * (STAGE_FLOATS / 2) + c2] =
-            make_float2(norm_value(x.x, m0, sd0, r0, p.norm_clip), norm_value(x.y, m1, sd1, r1, p.norm_clip));
+        const float y0 = norm_value(x.x, m0, sd0, r0, p.norm_clip), y1 = norm_value(x.y, m1, sd1, r1, p.norm_clip);
+        if (p.norm_bf16) dst16[ee * (STAGE_FLOATS / 2) + c2] = __floats2bfloat162_rn(y0, y1);  // half the bytes
+        else dst[ee * (STAGE_FLOATS / 2) + c2] = make_float2(y0, y1);
       }
     }
   }
@@ -2234,6 +2240,7 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.norm_var = a->norm_var;
   p.norm_eps = a->norm_epsilon;
   p.norm_clip = a->norm_clip;
+  p.norm_bf16 = (a->flags & PHC_STEP_OBS_NORM_BF16) ? 1 : 0;
   if (a->obs_norm) {
     if (!a->norm_mean || !a->norm_var) return PHC_ERR_NULL;
     if (a->obs_norm_stride < SELF_DIM + (int64_t)TASK_DIM * a->time_steps || !(a->norm_clip > 0.0f)) return PHC_ERR_SHAPE;
@@ -2427,7 +2434,7 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
   // fast path: T == 1, AoS sim tensor (16-B aligned rows), dense 16-B aligned obs_buf
   const bool fast = !g_force_generic && p.T == 1 && p.aos && p.L.packed && p.obs_stride == STAGE_FLOATS &&
                     ((uintptr_t)p.obs & 15) == 0 &&
-                    (!p.obs_norm || (p.obs_norm_stride == STAGE_FLOATS && ((uintptr_t)p.obs_norm & 15) == 0));
+                    (!p.obs_norm || (p.obs_norm_stride == STAGE_FLOATS && ((uintptr_t)p.obs_norm & (p.norm_bf16 ? 3 : 15)) == 0));
   static bool attr_fast4[64] = {}, attr_gen[64] = {};
   static int first_wave[64] = {};
   if (fast) {

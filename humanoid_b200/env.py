@@ -269,6 +269,8 @@ class HumanoidPHC:
             a.norm_var = rn.running_var.data_ptr()
             a.norm_epsilon = rn.epsilon
             a.norm_clip = rn.clip
+            if self.obs_norm_buf.dtype == torch.bfloat16:
+                a.flags |= _cabi.STEP_OBS_NORM_BF16
         if self.use_power_reward:  # humanoid_phc.py:1297-1305
             a.dof_force = self.dof_force_tensor.data_ptr()
             a.dof_force_stride = self.dof_force_tensor.stride(0)
@@ -280,17 +282,21 @@ class HumanoidPHC:
         self._step_args = (a, advance, keep)
         return a
 
-    def set_obs_normalizer(self, normalizer):
+    def set_obs_normalizer(self, normalizer, dtype=torch.float32):
         """Fuse ``RunningNorm.forward`` (PHC/policies/running_norm.py:15-20) into the step: every step also
         writes ``obs_norm_buf = clamp((obs_buf - running_mean) / sqrt(running_var + eps), -clip, clip)`` —
         what the policy's first layer consumes — from the same shared-memory rows, while ``obs_buf`` keeps
         the raw rows the experience buffer and ``RunningNorm.update`` need.  The normaliser's buffers are
-        read at launch time, so an ``update()`` between steps is seen by the next step.  ``None`` turns it off."""
+        read at launch time, so an ``update()`` between steps is seen by the next step.  ``None`` turns it off.
+        ``dtype=torch.bfloat16`` emits the normalised rows as bf16 (each fp32 result rounded to nearest-even):
+        the policy's input under autocast, at half the bytes."""
         if normalizer is not None:
             if normalizer.shape != self.num_obs or normalizer.running_mean.device != self.device:
                 raise ValueError("normalizer must have shape num_obs and live on the env's device")
-            if self.obs_norm_buf is None:
-                self.obs_norm_buf = torch.zeros_like(self.obs_buf)
+            if dtype not in (torch.float32, torch.bfloat16):
+                raise ValueError("obs_norm_buf is float32 or bfloat16")
+            if self.obs_norm_buf is None or self.obs_norm_buf.dtype != dtype:
+                self.obs_norm_buf = torch.zeros_like(self.obs_buf, dtype=dtype)
         self.obs_normalizer = normalizer
         self._step_args = None
 

@@ -209,6 +209,8 @@ PHC_API int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_
  * ---------------------------------------------------------------------------------- */
 #define PHC_STEP_MAPPED_HOST_IO 1u /* sim state / clock / outputs are pinned host memory mapped into the
                                       device address space: no L2 prefetch, no pre-dependency speculation */
+#define PHC_STEP_OBS_NORM_BF16 2u  /* obs_norm points to bfloat16 rows (the policy's input dtype under autocast): each
+                                      normalised fp32 value is rounded to nearest-even; obs_norm_stride counts bf16 elements */
 typedef struct PhcStepArgs {
   PhcBodyState body;                     /* sim state views, J must be 24               */
   int16_t* progress_buf;                 /* [n] in/out                  humanoid_phc.py:571 */
@@ -248,7 +250,7 @@ typedef struct PhcStepArgs {
   /* RunningNorm.forward fused into the obs epilogue (policies/running_norm.py:15-20), off when
    * obs_norm is NULL:  obs_norm = clamp((obs - mean) / sqrt(var + epsilon), -clip, clip), written
    * IN ADDITION to obs_buf (the experience buffer keeps the raw rows, RunningNorm.update needs them) */
-  float* obs_norm;                       /* NULL or [n, 358+576*T]                           */
+  float* obs_norm;                       /* NULL or [n, 358+576*T] fp32 (bf16 with PHC_STEP_OBS_NORM_BF16) */
   int64_t obs_norm_stride;
   const float* norm_mean;                /* [358+576*T] running_mean                         */
   const float* norm_var;                 /* [358+576*T] running_var                          */

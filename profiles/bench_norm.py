@@ -29,7 +29,7 @@ def make(fused):
         if r:
             env.progress_buf = envs[0].progress_buf
         if fused:
-            env.set_obs_normalizer(rn)
+            env.set_obs_normalizer(rn, dtype=fused)
         envs.append(env)
     return envs
 
@@ -70,9 +70,11 @@ def timed(envs, after):
 outs = [torch.empty(N, 934, device=dev) for _ in range(R)]
 plain = timed(make(False), lambda e: None)
 sep = timed(make(False), lambda e: rn(e.obs_buf))
-fused = timed(make(True), lambda e: None)
+fused = timed(make(torch.float32), lambda e: None)
+fused16 = timed(make(torch.bfloat16), lambda e: None)
 print(f"# RunningNorm.forward at N = {N} (us per step, {K}-step CUDA graph, best of 5)\n")
 print("| variant | us / step |\n|---|---|")
 print(f"| step only (raw obs) | {plain:.2f} |")
 print(f"| step + standalone phc_running_norm_forward (allocates its output) | {sep:.2f} |")
-print(f"| step with the fused epilogue (raw + normalised rows) | {fused:.2f} |")
+print(f"| step with the fused epilogue (raw + normalised fp32 rows) | {fused:.2f} |")
+print(f"| step with the fused epilogue, normalised rows as bf16 (PHC_STEP_OBS_NORM_BF16) | {fused16:.2f} |")

@@ -996,6 +996,39 @@ def test_fused_obs_normalisation_vs_oracle(N, T, generic):
     assert_close(env.obs_norm_buf, want, rtol=1e-5, atol=1e-6, what="fused normalised obs, second step")
 
 
+@pytest.mark.parametrize("N,T,generic", [(4099, 1, False), (777, 1, True), (300, 3, False)],
+                         ids=["fast_T1", "generic_T1", "generic_T3"])  # fmt: skip
+def test_fused_obs_normalisation_bf16_rows(N, T, generic):
+    """PHC_STEP_OBS_NORM_BF16: the bf16 rows are the fp32 rows of the same kernel rounded to nearest-even."""
+    from humanoid_b200 import HumanoidPHC, RunningNorm, _cabi
+
+    lib_data, clock, state = _gpu_case(N, 64, 209, max_progress=40)
+    lib = MotionLib(lib_data, device=DEV)
+    rn = RunningNorm(358 + 576 * T, device=DEV)
+    g = torch.Generator().manual_seed(5)
+    rn.running_mean.copy_(torch.randn(1, rn.shape, generator=g) * 0.3)
+    rn.running_var.copy_(torch.rand(1, rn.shape, generator=g) * 2 + 1e-3)
+    envs = {}
+    capi = _cabi.load()
+    for dtype in (torch.float32, torch.bfloat16):
+        env = HumanoidPHC(lib, N, device=DEV, time_steps=T)
+        env.set_sim_state(state)
+        env.set_clock(clock)
+        env.set_obs_normalizer(rn, dtype=dtype)
+        try:
+            capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if generic else 0)
+            env.step()
+        finally:
+            capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+        envs[dtype] = env
+    f32, b16 = envs[torch.float32], envs[torch.bfloat16]
+    assert b16.obs_norm_buf.dtype == torch.bfloat16 and b16.obs_norm_buf.shape == f32.obs_norm_buf.shape
+    assert torch.equal(b16.obs_buf, f32.obs_buf) and torch.equal(b16.rew_buf, f32.rew_buf)
+    assert torch.equal(b16.obs_norm_buf, f32.obs_norm_buf.to(torch.bfloat16)), "bf16 rows = RN-even rounding of the fp32 rows"
+    want = O.running_norm_forward(rn.running_mean.cpu(), rn.running_var.cpu(), f32.obs_buf.cpu(), rn.epsilon, rn.clip)
+    assert_close(b16.obs_norm_buf.float(), want, rtol=2**-8, atol=1e-6, what="bf16 normalised obs vs oracle (half a bf16 ulp)")
+
+
 # ---------------------------------------------------------------------------------------
 # the whole env against a recording of the reference's own HumanoidPHC.step / reset
 # ---------------------------------------------------------------------------------------

@@ -11,7 +11,10 @@ The host side keeps what is host logic in the reference: which clips are sampled
 ``max_length`` crop (:773-778), the random heading draw (:789-791, one ``np.random.random()`` per
 clip, in clip order, so a seeded run draws the same headings) and the per-clip metadata (:361-392).
 ``fix_trans_height`` (:696-745) needs the SMPL mesh model files and is not implemented — this is the
-``mesh_parsers is None`` path (:692-694, :801).  There is no CPU path.
+``mesh_parsers is None`` path (:692-694, :801).  Two quirks of the reference's single-process loader
+(``num_thread == 1``) are kept rather than fixed: ``_motion_aa`` is the files' UNCROPPED ``pose_aa`` (:377), so
+with a ``max_length`` crop it has more rows than ``gts``; and the random heading is written in place into the
+caller's ``pose_aa`` window (:783, :794), so it accumulates over resamples.  There is no CPU path.
 """
 
 from __future__ import annotations
@@ -51,6 +54,27 @@ def heading_half_angle(u: np.ndarray) -> np.ndarray:
     ``sRot.from_euler("xyz", [0, 0, angle])``."""
     half = np.pi * (2 * np.asarray(u, dtype=np.float64) - 1.0) / 2
     return np.stack([np.sin(half), np.cos(half)], axis=-1)
+
+
+def heading_on_rotvec(v: np.ndarray, z: float, w: float) -> np.ndarray:
+    """``(heading * Rotation.from_rotvec(v)).as_rotvec()`` for the heading quaternion (0, 0, z, w), in scipy's
+    formulas (Taylor branches below 1e-3 rad), fp64, vectorised over rows: the root entry of ``pose_aa``
+    under the random heading (motion_lib.py:794)."""
+    v = np.asarray(v, dtype=np.float64)
+    ang = np.sqrt((v * v).sum(-1))
+    small = ang <= 1e-3
+    a2 = ang * ang
+    safe = np.where(small, 1.0, ang)
+    sc = np.where(small, 0.5 - a2 / 48.0 + a2 * a2 / 3840.0, np.sin(safe / 2) / safe)
+    x, y, zq, wq = sc * v[..., 0], sc * v[..., 1], sc * v[..., 2], np.cos(ang / 2)
+    x, y, zq, wq = w * x - z * y, w * y + z * x, w * zq + z * wq, w * wq - z * zq
+    sign = np.where(wq < 0, -1.0, 1.0)
+    x, y, zq, wq = sign * x, sign * y, sign * zq, sign * wq
+    a = 2 * np.arctan2(np.sqrt(x * x + y * y + zq * zq), wq)
+    small = a <= 1e-3
+    a2 = a * a
+    s2 = np.where(small, 2 + a2 / 12 + 7 * a2 * a2 / 2880, a / np.sin(np.where(small, 1.0, a) / 2))
+    return np.stack([s2 * x, s2 * y, s2 * zq], axis=-1)
 
 
 def _as_np64(x) -> np.ndarray:
@@ -163,6 +187,7 @@ class MotionLibSMPL(MotionLib):
 
         quats, transs, aas, nfs, fpss, bodies, heading_u, files = [], [], [], [], [], [], [], []
         randomise = not (self.is_deterministic or self.im_eval)
+        J = _cabi.NUM_BODIES
         for f, idx in enumerate(sample_idxes.tolist()):
             clip = self._motion_data_list[idx]
             seq_len = clip["root_trans_offset"].shape[0]
@@ -171,39 +196,35 @@ class MotionLibSMPL(MotionLib):
             else:
                 start = 0 if self.is_deterministic else random.randint(0, seq_len - self.max_length)
                 end = start + self.max_length
+            nf = end - start
             if randomise:
                 heading_u.append(np.random.random())  # :790
+                # Reference quirk kept (:783, :794): the heading is written IN PLACE into the window of the clip's
+                # own pose_aa (to_torch of a numpy slice shares memory), so it persists in the caller's data.
+                aa = clip["pose_aa"]
+                window = (aa.numpy() if isinstance(aa, torch.Tensor) else aa)[start:end]
+                z, w = heading_half_angle(heading_u[-1])
+                window[:, :3] = heading_on_rotvec(window[:, :3], z, w)
             transs.append(_as_np64(clip["root_trans_offset"])[start:end])
             quats.append(_as_np64(clip["pose_quat_global"])[start:end])
-            nf = end - start
-            if "beta" in clip:  # :376-381
-                aas.append(_as_np64(clip["pose_aa"])[start:end].reshape(nf, -1))
+            if "beta" in clip:  # :376-381 — the FILE's pose_aa, uncropped: with a crop _motion_aa has more rows than gts
+                aas.append(clip)  # read after the loop: a clip sampled twice carries both headings, as in the reference
                 bodies.append(torch.as_tensor(gender_betas[f], dtype=torch.float32))
             else:
-                aas.append(None)
+                aas.append(nf)
                 bodies.append(torch.zeros(17))
             nfs.append(nf)
             fpss.append(clip.get("fps", 30))
             files.append(clip)
 
-        J = _cabi.NUM_BODIES
-        have_aa = [a is not None for a in aas]
-        pose_aa = None
-        if any(have_aa):
-            # a clip without "beta" stores zeros and ignores the heading (motion_lib.py:380); an exact-zero
-            # rotation vector composed with the heading would not stay zero, so such clips are patched below
-            pose_aa = np.concatenate([a if a is not None else np.zeros((k, J * 3)) for a, k in zip(aas, nfs)])
         built = build_motion_tensors(
             np.concatenate(quats) if quats else np.zeros((0, J, 4)), np.concatenate(transs) if transs else np.zeros((0, 3)),
-            pose_aa, nfs, fpss, np.asarray(skeleton_trees[0].parent_indices),
+            None, nfs, fpss, np.asarray(skeleton_trees[0].parent_indices),
             np.stack([np.asarray(t.local_translation, dtype=np.float32) for t in skeleton_trees]),
             heading_u=np.asarray(heading_u) if randomise else None, device=self._device,
         )  # fmt: skip
-        if pose_aa is not None and not all(have_aa):
-            starts = np.concatenate([[0], np.cumsum(nfs)])
-            for m, ok in enumerate(have_aa):
-                if not ok:
-                    built["motion_aa"][starts[m]:starts[m + 1]].zero_()
+        aas = [np.zeros((a, J * 3)) if isinstance(a, int) else _as_np64(a["pose_aa"]).reshape(-1, J * 3) for a in aas]
+        built["motion_aa"] = torch.from_numpy(np.concatenate(aas).astype(np.float32)).to(self._device)  # :391
         fps64 = np.asarray(fpss, dtype=np.float64)
         built.update(
             motion_lengths=torch.tensor((1.0 / fps64 * (np.asarray(nfs) - 1)).tolist(), dtype=torch.float32),  # :372

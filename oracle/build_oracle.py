@@ -124,38 +124,51 @@ def dof_vels(local_rot: Tensor, fps: int) -> Tensor:
 
 def random_heading(pose_aa: np.ndarray, pose_quat_global: np.ndarray, trans: Tensor, u: float):
     """The heading randomisation of load_motion_with_skeleton, motion_lib.py:789-799, with the uniform
-    number ``u`` supplied (the reference draws ``np.random.random()``)."""
+    number ``u`` supplied (the reference draws ``np.random.random()``).  ``pose_aa`` is modified IN PLACE
+    like the reference's (``to_torch`` of a numpy slice shares the file's memory, :783/:794)."""
     B, J, N = pose_quat_global.shape
     random_rot = np.zeros(3)
     random_rot[2] = np.pi * (2 * u - 1.0)
     h = sRot.from_euler("xyz", random_rot)
-    pose_aa = pose_aa.copy()
     pose_aa[:, :3] = (h * sRot.from_rotvec(pose_aa[:, :3])).as_rotvec()
     pose_quat_global = (h * sRot.from_quat(pose_quat_global.reshape(-1, 4))).as_quat().reshape(B, J, N)
     trans = torch.matmul(trans, torch.from_numpy(h.as_matrix().T))
-    return pose_aa, pose_quat_global, trans
+    return pose_quat_global, trans
 
 
 def build_motion_library(
     pose_quat_global: np.ndarray, root_trans: np.ndarray, pose_aa: np.ndarray, num_frames: Sequence[int],
     fps: Sequence[int], parents: Sequence[int], local_translation: np.ndarray, gender_betas: np.ndarray,
-    limb_weights: np.ndarray, heading_u: Optional[Sequence[float]] = None,
+    limb_weights: np.ndarray, heading_u: Optional[Sequence[float]] = None, max_length: int = -1,
+    crop_start: Optional[Sequence[int]] = None,
 ) -> Dict[str, Tensor]:  # fmt: skip
-    """Clips are concatenated on the frame axis; ``local_translation`` is [M,24,3] fp32 (one tree per
-    clip).  Returns the reference's attribute set (motion_lib.py:390-414) without the leading underscore."""
+    """The files' clips are concatenated on the frame axis (``num_frames`` = the files' lengths);
+    ``local_translation`` is [M,24,3] fp32 (one tree per clip).  ``max_length`` / ``crop_start`` are the
+    window of :773-778 (the reference draws the start with ``random.randint``).  Returns the reference's
+    attribute set (motion_lib.py:390-414) without the leading underscore.
+
+    Reference quirk kept: ``_motion_aa`` is built from the FILE's ``pose_aa`` (:377), i.e. the uncropped
+    clip — with the rows of the window heading-rotated in place (:783, :794) — so with a crop it has more
+    rows than ``gts`` and is not frame-aligned with it."""
     parents = [int(p) for p in parents]
     cols = {k: [] for k in ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "motion_aa")}
-    lengths, dts, fpss = [], [], []
-    start = 0
-    for m, nf in enumerate(num_frames):
-        nf, f = int(nf), int(fps[m])
-        sl = slice(start, start + nf)
-        start += nf
+    lengths, dts, fpss, nfs = [], [], [], []
+    file_start = 0
+    for m, seq_len in enumerate(num_frames):
+        seq_len, f = int(seq_len), int(fps[m])
+        if max_length == -1 or seq_len < max_length:
+            start, end = 0, seq_len
+        else:
+            start = int(crop_start[m])
+            end = start + max_length
+        file_aa = np.array(pose_aa[file_start : file_start + seq_len], dtype=np.float64)  # this clip's "file"
+        sl = slice(file_start + start, file_start + end)
+        file_start += seq_len
+        nf = end - start
         q = np.asarray(pose_quat_global[sl], dtype=np.float64)
         t = torch.from_numpy(np.asarray(root_trans[sl], dtype=np.float64))
-        aa = np.asarray(pose_aa[sl], dtype=np.float64)
         if heading_u is not None:
-            aa, q, t = random_heading(aa, q, t, float(heading_u[m]))
+            q, t = random_heading(file_aa[start:end], q, t, float(heading_u[m]))
         q = torch.from_numpy(q)
         lr = local_rotation(q, parents)
         gt = forward_kinematics(lr, t, torch.from_numpy(np.asarray(local_translation[m], dtype=np.float32)), parents)
@@ -165,14 +178,15 @@ def build_motion_library(
         cols["gvs"].append(compute_velocity(gt, 1 / f).float())
         cols["gavs"].append(compute_angular_velocity(q, 1 / f).float())
         cols["dvs"].append(dof_vels(lr, f))
-        cols["motion_aa"].append(torch.from_numpy(aa).float())  # :377, :391
+        cols["motion_aa"].append(torch.from_numpy(file_aa).float())  # :377, :391
         fpss.append(f)
         dts.append(1.0 / f)
         lengths.append(1.0 / f * (nf - 1))  # :372
+        nfs.append(nf)
     out = {k: torch.cat(v, dim=0) for k, v in cols.items()}
     out["grvs"] = out["gvs"][:, 0]
     out["gravs"] = out["gavs"][:, 0]
-    nfr = torch.tensor([int(n) for n in num_frames])
+    nfr = torch.tensor(nfs)
     shifted = nfr.roll(1)
     shifted[0] = 0
     out["length_starts"] = shifted.cumsum(0)  # :405-408

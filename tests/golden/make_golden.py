@@ -680,12 +680,13 @@ def case_motion_build():
         "in.limb_weights": np.stack(limb_weights),
     }
 
-    def run(deterministic, seed):
+    def run(deterministic, seed, max_length=-1, pyseed=0):
         import copy
+        import random
 
         data = copy.deepcopy(clips)  # the loader rotates pose_aa[:, :3] of its input in place (:794)
         lib = object.__new__(ref_ml.MotionLibSMPL)
-        lib.m_cfg = types.SimpleNamespace(max_length=-1, fix_height=ref_ml.FixHeightMode.no_fix,
+        lib.m_cfg = types.SimpleNamespace(max_length=max_length, fix_height=ref_ml.FixHeightMode.no_fix,
                                           is_deterministic=deterministic, im_eval=False, num_thread=1)  # fmt: skip
         lib._device, lib.mesh_parsers, lib.num_thread = "cpu", None, 1
         lib._motion_data_list = np.array(list(data.values()))
@@ -693,6 +694,7 @@ def case_motion_build():
         lib._num_unique_motions = M
         lib._sampling_prob = torch.ones(M) / M
         np.random.seed(seed)
+        random.seed(pyseed)  # the crop start of clips longer than max_length (:776)
         lib.load_motions(trees, gender_betas, limb_weights, random_sample=False)
         out = {k: getattr(lib, k) for k in (
             "gts", "grs", "lrs", "gvs", "gavs", "dvs", "grvs", "gravs", "_motion_aa", "_motion_lengths",
@@ -706,6 +708,17 @@ def case_motion_build():
         arrays[f"out.random_heading.{k}"] = v
     np.random.seed(31)
     arrays["in.heading_u"] = np.asarray([np.random.random() for _ in range(M)])
+    # third variant: max_length crop at a random start (python's `random`) + random heading, the training default
+    # with cfg.max_length set; the draws the loader makes, in its order, are recorded for the oracle
+    import random
+
+    CROP = 16
+    for k, v in run(False, 31, max_length=CROP, pyseed=7).items():
+        arrays[f"out.cropped.{k}"] = v
+    random.seed(7)
+    lens = arrays["in.num_frames"].tolist()
+    arrays["in.crop_start"] = np.asarray([0 if n < CROP else random.randint(0, n - CROP) for n in lens], dtype=np.int64)
+    arrays["in.crop_max_length"] = np.asarray(CROP, dtype=np.int64)
     save("motion_build", arrays)
 
 

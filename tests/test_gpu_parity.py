@@ -1093,7 +1093,7 @@ def _clips_from_golden(g):
     clips = {}
     for m in range(len(nf)):
         sl = slice(int(starts[m]), int(starts[m + 1]))
-        clip = {"root_trans_offset": g.inp("root_trans_offset")[sl], "pose_aa": g.inp("pose_aa")[sl].numpy(),
+        clip = {"root_trans_offset": g.inp("root_trans_offset")[sl], "pose_aa": g.inp("pose_aa")[sl].numpy().copy(),
                 "pose_quat_global": g.inp("pose_quat_global")[sl].numpy(), "beta": np.zeros(16)}  # fmt: skip
         if int(g.inp("fps")[m]) != 30:
             clip["fps"] = int(g.inp("fps")[m])
@@ -1112,15 +1112,19 @@ BUILD_EXACT = ("grs", "lrs", "gts", "gvs", "_motion_aa", "_motion_lengths", "_mo
                "_motion_fps", "length_starts", "_motion_bodies", "_motion_limb_weights")  # fmt: skip
 
 
-@pytest.mark.parametrize("variant", ["deterministic", "random_heading"])
+@pytest.mark.parametrize("variant", ["deterministic", "random_heading", "cropped"])
 def test_motion_build_vs_reference_load_motions(golden, variant):
+    import random
+
     import numpy as np
 
     from humanoid_b200.motion_build import MotionLibSMPL
 
     g = golden("motion_build")
-    lib = MotionLibSMPL(_clips_from_golden(g), device=DEV, is_deterministic=variant == "deterministic")
-    np.random.seed(31)  # the seed make_golden.py ran the reference's loader under
+    lib = MotionLibSMPL(_clips_from_golden(g), device=DEV, is_deterministic=variant == "deterministic",
+                        max_length=int(g.inp("crop_max_length")) if variant == "cropped" else -1)  # fmt: skip
+    np.random.seed(31)  # the seeds make_golden.py ran the reference's loader under: the host side must draw the
+    random.seed(7)      # crop starts and the headings in the reference's order to land on the same clips
     lib.load_motions(_trees_from_golden(g), list(g.inp("gender_betas")), g.inp("limb_weights").numpy(), random_sample=False)
     for k in BUILD_EXACT + ("gavs", "dvs", "grvs", "gravs"):
         got, want = getattr(lib, k).cpu(), g.out(f"{variant}.{k.lstrip('_')}")
@@ -1133,6 +1137,9 @@ def test_motion_build_vs_reference_load_motions(golden, variant):
             assert torch.equal(got, want), f"{k}: {(got != want).sum()} of {got.numel()} differ, max {float((got - want).abs().max())}"
         else:  # sin/cos/acos/atan2 of libdevice vs libm / SLEEF on the way
             assert_close(got, want, what=f"{variant}.{k}", **OBS_TOL)
+    if variant != "deterministic":  # the heading went into the caller's pose_aa in place (motion_lib.py:783, :794)
+        src = np.concatenate([c["pose_aa"] for c in lib._motion_data_list]).astype(np.float32)
+        assert np.array_equal(src, lib._motion_aa.cpu().numpy()) and not np.array_equal(src, g.inp("pose_aa").numpy().astype(np.float32))
     # the built library answers queries like one assembled from the reference's tensors
     ids = torch.arange(lib.num_motions(), device=DEV).repeat(3)
     t = torch.rand(ids.shape[0], device=DEV) * lib._motion_lengths[ids]

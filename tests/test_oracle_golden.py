@@ -186,15 +186,17 @@ BUILD_KEYS = ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "grvs", "gravs", "motio
 def oracle_build_from_golden(g, variant):
     from oracle import build_oracle as B
 
+    crop = variant == "cropped"  # load_motion_with_skeleton's max_length window (:773-778) at the recorded random starts
     return B.build_motion_library(
         g.inp("pose_quat_global").numpy(), g.inp("root_trans_offset").numpy(), g.inp("pose_aa").numpy(),
         g.inp("num_frames").tolist(), g.inp("fps").tolist(), g.inp("parent_indices").tolist(),
         g.inp("local_translation").numpy(), g.inp("gender_betas").numpy(), g.inp("limb_weights").numpy(),
-        heading_u=g.inp("heading_u").tolist() if variant == "random_heading" else None,
+        heading_u=None if variant == "deterministic" else g.inp("heading_u").tolist(),
+        max_length=int(g.inp("crop_max_length")) if crop else -1, crop_start=g.inp("crop_start").tolist() if crop else None,
     )  # fmt: skip
 
 
-@pytest.mark.parametrize("variant", ["deterministic", "random_heading"])
+@pytest.mark.parametrize("variant", ["deterministic", "random_heading", "cropped"])
 def test_motion_build_against_reference_load_motions(golden, variant):
     g = golden("motion_build")
     torch.set_num_threads(1)
@@ -206,8 +208,12 @@ def test_motion_build_against_reference_load_motions(golden, variant):
             assert_equal_exact(out[k], want, k)
         else:
             assert_close(out[k], want, what=f"{variant}.{k}", **TIGHT)
-    # the fixture covers: a 2-frame clip, a 3-frame clip (shorter than the filter), a 60 fps clip
+    # the fixture covers: a 2-frame clip, a 3-frame clip (shorter than the filter), a 60 fps clip, and crops that
+    # start inside a clip
     assert g.inp("num_frames").min() == 2 and set(g.inp("fps").tolist()) == {30, 60}
+    assert int(g.inp("crop_start").max()) > 0 and int(g.out("cropped.motion_num_frames").max()) == int(g.inp("crop_max_length"))
+    # reference quirk: _motion_aa keeps the files' full length (motion_lib.py:377), so it is longer than gts when cropped
+    assert g.out("cropped.motion_aa").shape[0] == int(g.inp("num_frames").sum()) > g.out("cropped.gts").shape[0]
 
 
 def test_motion_build_host_constants_match_scipy(golden):
@@ -226,3 +232,12 @@ def test_motion_build_host_constants_match_scipy(golden):
         q = sRot.from_euler("xyz", [0.0, 0.0, np.pi * (2 * ui - 1.0)]).as_quat()
         assert q[0] == 0 and q[1] == 0
         assert np.allclose(zw[i], q[2:], rtol=0, atol=2e-16)
+    # the root rotation vector under the heading (motion_lib.py:794), incl. both small-angle branches
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=(500, 3))
+    v[::5] *= 1e-4
+    v[::7] *= 3
+    for ui in (0.1, 0.5, 0.93, 1e-4, 0.5 + 1e-5):
+        h = sRot.from_euler("xyz", [0.0, 0.0, np.pi * (2 * ui - 1.0)])
+        want = (h * sRot.from_rotvec(v)).as_rotvec()
+        assert np.abs(MB.heading_on_rotvec(v, *MB.heading_half_angle(ui)) - want).max() < 4e-15

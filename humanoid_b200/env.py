@@ -210,20 +210,37 @@ class HumanoidPHC:
     def set_termination_distances(self, termination_distances):  # :1338-1339
         self._termination_distances[:] = termination_distances
 
-    def toggle_eval_mode(self):  # :1426-1440 (motion-lib swap is out of scope)
+    def set_motion_libs(self, train_lib, eval_lib):
+        """``_motion_train_lib`` / ``_motion_eval_lib`` of ``_load_motion`` (:612-663): two ``MotionLibSMPL`` over the
+        same clips, the second with ``im_eval=True`` (longest first, no heading, no crop)."""
+        self._motion_train_lib, self._motion_eval_lib = train_lib, eval_lib
+        self._motion_lib = train_lib
+
+    def toggle_eval_mode(self, phase: Optional[torch.Tensor] = None):  # :1426-1440
         self.flag_test = True
         self.flag_im_eval = True
         self.set_termination_distances(0.5)
+        self._step_args = None
+        if getattr(self, "_motion_eval_lib", None) is not None:
+            self._motion_lib = self._motion_eval_lib
+            self.begin_seq_motion_samples(phase=phase)
         if len(self._reset_bodies_id) > 15:
             self._reset_bodies_id = self._eval_track_bodies_id
-        self._step_args = None
+        return self._motion_lib.num_motions() if not hasattr(self._motion_lib, "_num_unique_motions") else self._motion_lib._num_unique_motions
 
-    def untoggle_eval_mode(self):
+    def untoggle_eval_mode(self, failed_keys=(), auto_pmcp: bool = False, auto_pmcp_soft: bool = True):  # :1441-1455
         self.flag_test = False
         self.flag_im_eval = False
         self._termination_distances[:] = self._termination_distances_backup
         self._reset_bodies_id = self._reset_bodies_id_backup
         self._step_args = None
+        if getattr(self, "_motion_train_lib", None) is not None:
+            self._motion_lib = self._motion_train_lib
+            if auto_pmcp:  # config.py:103-104
+                self._motion_lib.update_hard_sampling_weight(failed_keys)
+            elif auto_pmcp_soft:
+                self._motion_lib.update_soft_sampling_weight(failed_keys)
+            return self._motion_lib._termination_history.clone()
 
     # ------------------------------------------------------------------------------------
     # fused path
@@ -494,7 +511,7 @@ class HumanoidPHC:
         sample of clips (``MotionLibSMPL.load_motions``), re-anchor the xy global offset so every env's
         reference root passes through where its humanoid stands now, then reset every env."""
         if self.flag_test:
-            raise _cabi.PhcError("forward_motion_samples (evaluation sweep, :1391-1402) is not part of the shim")
+            return self.forward_motion_samples(phase=phase)
         self._motion_lib.load_motions(
             skeleton_trees=self.skeleton_trees,
             limb_weights=self.humanoid_limb_and_weights.cpu(),
@@ -505,6 +522,43 @@ class HumanoidPHC:
         root_res = self._motion_lib.get_root_pos_smpl(self._sampled_motion_ids, time)
         self._global_offset[:, :2] = self._humanoid_root_states[:, :2] - root_res["root_pos"][:, :2]
         return self.reset(phase=phase)
+
+    def _load_seq(self, phase):
+        self._motion_lib.load_motions(
+            skeleton_trees=self.skeleton_trees,
+            gender_betas=self.humanoid_shapes.cpu(),
+            limb_weights=self.humanoid_limb_and_weights.cpu(),
+            random_sample=False,
+            start_idx=self._motion_sample_start_idx,
+        )
+        return self.reset(phase=phase)
+
+    def begin_seq_motion_samples(self, phase: Optional[torch.Tensor] = None):  # :1381-1391, evaluation sweep
+        self._motion_sample_start_idx = 0
+        return self._load_seq(phase)
+
+    def forward_motion_samples(self, phase: Optional[torch.Tensor] = None):  # :1393-1402
+        self._motion_sample_start_idx += self.num_envs
+        return self._load_seq(phase)
+
+    @property
+    def num_unique_motions(self):  # :1404-1418
+        return self._motion_lib._num_unique_motions
+
+    @property
+    def current_motion_ids(self):
+        return self._motion_lib._curr_motion_ids
+
+    @property
+    def motion_sample_start_idx(self):
+        return self._motion_sample_start_idx
+
+    @property
+    def motion_data_keys(self):
+        return self._motion_lib._motion_data_keys
+
+    def get_motion_steps(self):  # :1420-1421
+        return self._motion_lib.get_motion_num_steps()
 
     # ------------------------------------------------------------------------------------
     # the reference's decomposition, on the per-function kernels

@@ -148,42 +148,91 @@ def build_motion_tensors(
     return out
 
 
-class MotionLibSMPL(MotionLib):
+class ClipSampler:
+    """Which clips a load draws: the host-side state and methods of ``MotionLibBase`` that involve no frame data
+    (``load_data`` :192-230, ``setup_constants`` :232-245, the PMCP sampling weights :454-500, ``sample_motions``
+    :510-513).  Pure host logic, no device needed."""
+
+    def _init_clips(self, motion_data, min_length: int = -1, im_eval: bool = False):
+        if isinstance(motion_data, (str, bytes)) or hasattr(motion_data, "__fspath__"):
+            import joblib  # a pkl of {clip name: entry}, scripts/phc_convert_amass_data.py:186-194
+
+            motion_data = joblib.load(motion_data)
+        if min_length != -1:  # :205-208
+            motion_data = {k: v for k, v in motion_data.items() if len(v["pose_quat_global"]) >= min_length}
+        elif im_eval:  # longest first (stable), :209-217
+            motion_data = dict(sorted(motion_data.items(), key=lambda e: len(e[1]["pose_quat_global"]), reverse=True))
+        self._motion_data_keys = np.array(list(motion_data.keys()))
+        self._motion_data_list = list(motion_data.values())
+        n = self._num_unique_motions = len(self._motion_data_list)
+        self._curr_motion_ids = None
+        self._termination_history = torch.zeros(n)
+        self._success_rate = torch.zeros(n)
+        self._sampling_history = torch.zeros(n)
+        self._sampling_prob = torch.ones(n) / max(n, 1)
+        self._sampling_batch_prob = None
+
+    def pick_clips(self, n: int, random_sample: bool, start_idx: int, sample_idxes, is_deterministic: bool):
+        """load_motions :300-321."""
+        if sample_idxes is None or len(sample_idxes) != n:
+            if not is_deterministic and random_sample:
+                sample_idxes = torch.multinomial(self._sampling_prob, num_samples=n, replacement=True)
+            else:
+                sample_idxes = torch.remainder(torch.arange(n) + start_idx, self._num_unique_motions)
+        sample_idxes = torch.as_tensor(sample_idxes).cpu()
+        self.curr_motion_keys = self._motion_data_keys[sample_idxes.numpy()]
+        picked = self._sampling_prob[sample_idxes]
+        self._sampling_batch_prob = picked / picked.sum()
+        return sample_idxes
+
+    def update_hard_sampling_weight(self, failed_keys):  # :454-470
+        if len(failed_keys) > 0:
+            all_keys = self._motion_data_keys.tolist()
+            indexes = [all_keys.index(k) for k in failed_keys]
+            self._sampling_prob[:] = 0
+            self._sampling_prob[indexes] = 1 / len(indexes)
+        else:
+            self._sampling_prob = torch.ones(self._num_unique_motions) / self._num_unique_motions
+
+    def update_soft_sampling_weight(self, failed_keys):  # :472-492
+        if len(failed_keys) > 0:
+            all_keys = self._motion_data_keys.tolist()
+            indexes = [all_keys.index(k) for k in failed_keys]
+            self._termination_history[indexes] += 1
+            self.update_sampling_prob(self._termination_history)
+        else:
+            self._sampling_prob = torch.ones(self._num_unique_motions) / self._num_unique_motions
+
+    def update_sampling_prob(self, termination_history):  # :494-500
+        if len(termination_history) == len(self._termination_history) and termination_history.sum() > 0:
+            self._sampling_prob[:] = termination_history / termination_history.sum()
+            self._termination_history = termination_history
+            return True
+        return False
+
+    def sample_motions(self, n):  # :510-513
+        return torch.multinomial(self._sampling_batch_prob, num_samples=n, replacement=True)
+
+
+class MotionLibSMPL(ClipSampler, MotionLib):
     """``MotionLibSMPL(motion_data, device, ...)`` then ``load_motions(skeleton_trees, gender_betas,
     limb_weights, ...)`` as in the reference (motion_lib.py:676-694, :257); queries are inherited."""
 
-    def __init__(self, motion_data, device="cuda", max_length: int = -1,
-                 is_deterministic: bool = False, im_eval: bool = False):  # fmt: skip
+    def __init__(self, motion_data, device="cuda", max_length: int = -1, is_deterministic: bool = False,
+                 im_eval: bool = False, min_length: int = -1, step_dt: float = 1 / 30):  # fmt: skip
         dev = torch.device(device)
         if dev.type != "cuda":
             raise _cabi.PhcError("MotionLib lives in HBM: pass device='cuda' (there is no CPU path)")
         self._device = dev
         self._handle = None
         self.max_length, self.is_deterministic, self.im_eval = int(max_length), bool(is_deterministic), bool(im_eval)
-        # load_data, motion_lib.py:227-243: a joblib pkl of {clip name: entry} (scripts/phc_convert_amass_data.py:186-194)
-        if isinstance(motion_data, (str, bytes)) or hasattr(motion_data, "__fspath__"):
-            import joblib
-
-            motion_data = joblib.load(motion_data)
-        self._motion_data_keys = np.array(list(motion_data.keys()))
-        self._motion_data_list = list(motion_data.values())
-        self._num_unique_motions = len(self._motion_data_list)
-        # setup_constants, :206-225
-        self._sampling_prob = torch.ones(self._num_unique_motions) / max(self._num_unique_motions, 1)
+        self._sim_fps = 1 / step_dt  # :183
+        self._init_clips(motion_data, min_length=min_length, im_eval=im_eval)
 
     def load_motions(self, skeleton_trees, gender_betas, limb_weights, random_sample=True, start_idx=0, max_len=-1,
                      sample_idxes=None) -> List[dict]:  # fmt: skip
-        n = len(skeleton_trees)
-        if sample_idxes is None or len(sample_idxes) != n:  # :300-310
-            if not self.is_deterministic and random_sample:
-                sample_idxes = torch.multinomial(self._sampling_prob, num_samples=n, replacement=True)
-            else:
-                sample_idxes = torch.remainder(torch.arange(n) + start_idx, self._num_unique_motions)
-        sample_idxes = torch.as_tensor(sample_idxes).cpu()
+        sample_idxes = self.pick_clips(len(skeleton_trees), random_sample, start_idx, sample_idxes, self.is_deterministic)
         self._curr_motion_ids = sample_idxes.to(self._device)
-        self.curr_motion_keys = self._motion_data_keys[sample_idxes.numpy()]
-        picked = self._sampling_prob[sample_idxes]
-        self._sampling_batch_prob = picked / picked.sum()
 
         quats, transs, aas, nfs, fpss, bodies, heading_u, files = [], [], [], [], [], [], [], []
         randomise = not (self.is_deterministic or self.im_eval)

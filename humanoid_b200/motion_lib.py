@@ -91,6 +91,33 @@ class MotionLib:
     def _get_num_bodies(self) -> int:
         return self.num_bodies
 
+    def get_motion_num_steps(self, motion_ids=None):  # motion_lib.py:543-547
+        sim_fps = getattr(self, "_sim_fps", 30.0)
+        nf = self._motion_num_frames if motion_ids is None else self._motion_num_frames[motion_ids]
+        fps = self._motion_fps if motion_ids is None else self._motion_fps[motion_ids]
+        return (nf * sim_fps / fps).ceil().int()
+
+    def sample_time(self, motion_ids, truncate_time=None, phase=None):  # motion_lib.py:515-524
+        if phase is None:
+            phase = torch.rand(motion_ids.shape, device=self._device)
+        motion_len = self._motion_lengths[motion_ids]
+        if truncate_time is not None:
+            assert truncate_time >= 0.0
+            motion_len = motion_len - truncate_time
+        return phase * motion_len
+
+    def sample_time_interval(self, motion_ids, truncate_time=None, phase=None):  # motion_lib.py:526-535
+        """Start times on the 30 Hz grid.  The env's reset draws these inside ``phc_reset_envs``; this is the
+        standalone method, a handful of elementwise torch ops on the device."""
+        if phase is None:
+            phase = torch.rand(motion_ids.shape, device=self._device)
+        motion_len = self._motion_lengths[motion_ids]
+        if truncate_time is not None:
+            assert truncate_time >= 0.0
+            motion_len = motion_len - truncate_time
+        curr_fps = 1 / 30
+        return ((phase * motion_len) / curr_fps).long() * curr_fps
+
     @property
     def handle(self) -> C.c_void_p:
         return self._handle

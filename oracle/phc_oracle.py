@@ -780,6 +780,7 @@ class OracleEnv:
         self.dof_subset, self._key_body_ids = dof_subset, key_body_ids
         self.use_amp_obs = use_amp_obs
         self.rew_power_coef = rew_power_coef
+        self.flag_test = False  # toggle_eval_mode (:1427): resets start at time 0 (:852-853)
         self.zero_joints = zero_joints  # L_Hand, R_Hand, L_Toe, R_Toe in DOF_NAMES (:118-127)
         self._termination_distances = torch.full((24,), termination_distance)
         self.state = torch.zeros(N, 24, 13)
@@ -820,6 +821,7 @@ class OracleEnv:
             self.lib, env_ids, phase, self.state, self.root_states, self.dof_state[..., 0], self.dof_state[..., 1],
             self.progress_buf, self.reset_buf, self._terminate_buf, self._motion_start_times,
             self._motion_start_times_offset, self._global_offset, self._sampled_motion_ids, self.obs_buf, self.dt,
+            flag_test=self.flag_test,
         )  # fmt: skip
         if self.use_amp_obs:  # _init_amp_obs (:791-799)
             self._amp_obs_buf[env_ids, 0] = amp_obs_from_state(

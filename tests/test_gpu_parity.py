@@ -1270,3 +1270,62 @@ def test_resample_motions_rebuilds_the_library_and_resets_vs_oracle(golden):
     assert_close(env.obs_buf.cpu(), ref.obs_buf, what="obs after resample", **OBS_TOL)
     assert_close(env.amp_obs.cpu().view(N, -1), ref._amp_obs_buf.view(N, -1), what="amp obs", **DOF_TOL)
     step_both()
+
+
+def test_eval_sweep_swaps_libraries_and_walks_the_clips(golden):
+    """toggle_eval_mode -> begin_seq_motion_samples -> forward_motion_samples -> untoggle_eval_mode
+    (humanoid_phc.py:1381-1455) with a train and an eval library (longest clip first) over the same clips."""
+    import numpy as np
+
+    from humanoid_b200 import HumanoidPHC
+    from humanoid_b200.motion_build import MotionLibSMPL
+    from oracle import build_oracle as B
+
+    g = golden("motion_build")
+    M, N = 6, 4
+    trees = _trees_from_golden(g)[:N]
+    shapes, limbs = g.inp("gender_betas")[:N], g.inp("limb_weights")[:N].float()
+    nf = g.inp("num_frames").tolist()
+    starts = np.concatenate([[0], np.cumsum(nf)])
+    eval_order = sorted(range(M), key=lambda m: -nf[m])  # stable: load_data's im_eval sort (motion_lib.py:209-217)
+
+    def oracle_lib(order):
+        sl = [slice(int(starts[m]), int(starts[m + 1])) for m in order]
+        cat = lambda k: np.concatenate([g.inp(k).numpy()[s] for s in sl])  # noqa: E731
+        return O.OracleMotionLib(B.build_motion_library(
+            cat("pose_quat_global"), cat("root_trans_offset"), cat("pose_aa"), [nf[m] for m in order],
+            [int(g.inp("fps")[m]) for m in order], g.inp("parent_indices").tolist(),
+            np.stack([t.local_translation.numpy() for t in trees]), shapes.numpy(), limbs.numpy()))  # fmt: skip
+
+    train = MotionLibSMPL(_clips_from_golden(g), device=DEV, is_deterministic=True)
+    evall = MotionLibSMPL(_clips_from_golden(g), device=DEV, im_eval=True)
+    train.load_motions(trees, list(shapes), limbs.numpy(), random_sample=False)
+    env = HumanoidPHC(train, N, device=DEV)
+    env.set_humanoid_assets(trees, shapes, limbs)
+    env.set_motion_libs(train, evall)
+    assert evall._motion_data_keys.tolist() == [f"clip{m}" for m in eval_order]
+
+    gen = torch.Generator().manual_seed(11)
+    for sweep, start in enumerate((0, N)):
+        phase = torch.rand(N, generator=gen)
+        if sweep == 0:
+            assert env.toggle_eval_mode(phase=cuda(phase)) == M and env._motion_lib is evall
+        else:
+            env.resample_motions(phase=cuda(phase))  # flag_test: forward_motion_samples (:1364-1365)
+        assert env.motion_sample_start_idx == start
+        order = [eval_order[(e + start) % M] for e in range(N)]
+        assert env.current_motion_ids.tolist() == [(e + start) % M for e in range(N)]
+        assert env.get_motion_steps().tolist() == [int(np.ceil(nf[m] * 30 / int(g.inp("fps")[m]))) for m in order]
+        zeros = torch.zeros(N)
+        ref = O.OracleEnv(oracle_lib(order), N, torch.zeros(N, dtype=torch.short), zeros, zeros, torch.zeros(N, 3),
+                          torch.arange(N), torch.zeros(69), torch.ones(69), env.dof_subset.cpu(), env._key_body_ids.cpu(),
+                          use_amp_obs=False)  # fmt: skip
+        ref.flag_test = True
+        ref.reset(torch.arange(N), phase)
+        assert_close(env._motion_start_times.cpu(), ref._motion_start_times, what="start times", rtol=0, atol=0)
+        assert_close(env._rigid_body_state_reshaped.cpu(), ref.state, what="posed state", **OBS_TOL)
+        assert_close(env.obs_buf.cpu(), ref.obs_buf, what="obs", **OBS_TOL)
+    hist = env.untoggle_eval_mode(failed_keys=["clip1", "clip4"])
+    assert env._motion_lib is train and not env.flag_test
+    assert hist.tolist() == [0, 1, 0, 0, 1, 0] and train._sampling_prob.tolist() == [0, 0.5, 0, 0, 0.5, 0]
+    assert float(env._termination_distances[0]) == 0.25

@@ -75,3 +75,69 @@ def test_motion_state_all_keys_bit_exact_vs_reference():
     got = O.OracleMotionLib(lib_data).get_motion_state(clock.sampled_motion_ids, t, clock.global_offset)
     for k, v in ref.items():
         assert torch.equal(got[k], v), k
+
+
+def test_clip_sampler_matches_reference_sampling_state(golden):
+    """Host logic of the loader (which clips, PMCP weights, batch sampling) against the reference's MotionLibSMPL
+    under the same torch seed: load_data ordering, load_motions :300-321, update_*_sampling_weight, sample_motions."""
+    import types
+
+    import numpy as np
+
+    from humanoid_b200.motion_build import ClipSampler
+
+    _, _, ref_ml = ref_loader.load()
+    from puffer_phc.poselib_skeleton import SkeletonTree
+
+    g = golden("motion_build")
+    nf = g.inp("num_frames").tolist()
+    starts = np.concatenate([[0], np.cumsum(nf)])
+    clips = {}
+    for m in range(len(nf)):
+        sl = slice(int(starts[m]), int(starts[m + 1]))
+        clips[f"clip{m}"] = {"root_trans_offset": g.inp("root_trans_offset")[sl].clone(), "pose_aa": g.inp("pose_aa")[sl].numpy().copy(),
+                             "pose_quat_global": g.inp("pose_quat_global")[sl].numpy().copy(), "beta": np.zeros(16), "fps": int(g.inp("fps")[m])}  # fmt: skip
+    names = [f"b{j}" for j in range(24)]
+    N = 10
+    trees = [SkeletonTree(names, g.inp("parent_indices").long(), g.inp("local_translation")[e % len(nf)]) for e in range(N)]
+    betas = [torch.zeros(17) for _ in range(N)]
+    limbs = [np.zeros(10) for _ in range(N)]
+
+    for im_eval in (False, True):
+        ref = object.__new__(ref_ml.MotionLibSMPL)
+        ref.m_cfg = types.SimpleNamespace(max_length=-1, fix_height=ref_ml.FixHeightMode.no_fix, is_deterministic=False,
+                                          im_eval=im_eval, num_thread=1)  # fmt: skip
+        ref._device, ref.mesh_parsers = "cpu", None
+        # load_data (:192-230) minus joblib.load of a file
+        order = sorted(clips.items(), key=lambda e: len(e[1]["pose_quat_global"]), reverse=True) if im_eval else clips.items()
+        ref._motion_data_list = np.array([v for _, v in order])
+        ref._motion_data_keys = np.array([k for k, _ in order])
+        ref._num_unique_motions = len(clips)
+        ref.setup_constants(fix_height=ref_ml.FixHeightMode.no_fix, num_thread=1)
+        mine = ClipSampler()
+        mine._init_clips(clips, im_eval=im_eval)
+        assert mine._motion_data_keys.tolist() == ref._motion_data_keys.tolist()
+
+        failed = ["clip3", "clip0"]
+        for step in range(3):
+            if step == 1:
+                ref.update_soft_sampling_weight(failed), mine.update_soft_sampling_weight(failed)
+            if step == 2:
+                ref.update_hard_sampling_weight(failed[:1]), mine.update_hard_sampling_weight(failed[:1])
+            assert torch.equal(mine._sampling_prob, ref._sampling_prob) and torch.equal(mine._termination_history, ref._termination_history)
+            torch.manual_seed(100 + step)
+            np.random.seed(0)
+            ref.load_motions(trees, betas, limbs, random_sample=True)
+            torch.manual_seed(100 + step)
+            ids = mine.pick_clips(N, True, 0, None, is_deterministic=False)
+            assert torch.equal(ids, ref._curr_motion_ids) and mine.curr_motion_keys.tolist() == ref.curr_motion_keys.tolist()
+            assert torch.equal(mine._sampling_batch_prob, ref._sampling_batch_prob)
+            torch.manual_seed(7)
+            a = ref.sample_motions(5)
+            torch.manual_seed(7)
+            assert torch.equal(mine.sample_motions(5), a)
+        # the sequential branch with a start index (evaluation sweep, humanoid_phc.py:1381-1402)
+        ref.load_motions(trees, betas, limbs, random_sample=False, start_idx=4)
+        assert torch.equal(mine.pick_clips(N, False, 4, None, is_deterministic=False), ref._curr_motion_ids)
+        ref.update_soft_sampling_weight([]), mine.update_soft_sampling_weight([])
+        assert torch.equal(mine._sampling_prob, ref._sampling_prob)

@@ -91,3 +91,31 @@ def test_slerp_properties(a, b, t, eps):
     if ref_loader.available():
         ref_tu, _, _ = ref_loader.load()
         assert torch.equal(ref_tu.slerp(q0[None], q1[None], tt[None])[0], out)
+
+
+def test_clip_sampler_host_logic():
+    """ClipSampler without the reference: ordering, filters, weights (runs on the GPU box too)."""
+    import numpy as np
+
+    from humanoid_b200.motion_build import ClipSampler
+
+    clips = {f"c{i}": {"pose_quat_global": np.zeros((n, 24, 4))} for i, n in enumerate([5, 9, 9, 2, 7])}
+    s = ClipSampler()
+    s._init_clips(clips, im_eval=True)
+    assert s._motion_data_keys.tolist() == ["c1", "c2", "c4", "c0", "c3"]  # longest first, stable
+    s._init_clips(clips, min_length=7)
+    assert s._motion_data_keys.tolist() == ["c1", "c2", "c4"]
+    s._init_clips(clips)
+    assert s._num_unique_motions == 5 and torch.allclose(s._sampling_prob, torch.full((5,), 0.2))
+    assert s.pick_clips(7, False, 3, None, is_deterministic=False).tolist() == [3, 4, 0, 1, 2, 3, 4]
+    assert s.pick_clips(3, True, 0, [4, 4, 1], is_deterministic=False).tolist() == [4, 4, 1]  # caller-supplied ids win
+    assert s.curr_motion_keys.tolist() == ["c4", "c4", "c1"] and abs(float(s._sampling_batch_prob.sum()) - 1) < 1e-6
+    s.update_hard_sampling_weight(["c2"])
+    assert s._sampling_prob.tolist() == [0, 0, 1, 0, 0]
+    assert set(s.pick_clips(16, True, 0, None, is_deterministic=False).tolist()) == {2}
+    assert s.pick_clips(2, True, 0, None, is_deterministic=True).tolist() == [0, 1]  # deterministic ignores the weights
+    s.update_soft_sampling_weight(["c0", "c3"])
+    assert s._sampling_prob.tolist() == [0.5, 0, 0, 0.5, 0] and s._termination_history.tolist() == [1, 0, 0, 1, 0]
+    assert not s.update_sampling_prob(torch.zeros(5)) and not s.update_sampling_prob(torch.ones(4))
+    s.update_hard_sampling_weight([])
+    assert torch.allclose(s._sampling_prob, torch.full((5,), 0.2))

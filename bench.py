@@ -379,8 +379,13 @@ def run_gpu(args):
     d2h = int(capi.phc_host_step_d2h_bytes(ctx, N))
     capi.phc_host_step_destroy(ctx)
 
-    # -------- RunningNorm: moments of a 32-step rollout + ONE all-reduce (+ blend), per rollout
+    # -------- RunningNorm: moments of a 32-step rollout + ONE exchange (+ blend), per rollout.
+    # The exchange + blend is one launch per rank over NVLink peer memory (phc_running_norm_update_peers);
+    # the NCCL all-reduce + update-kernel path is timed beside it.
     rn = RunningNorm(obs_dim, device=dev)
+    rn_nccl = RunningNorm(obs_dim, device=dev)
+    if world > 1:
+        rn.enable_peer_reduce(timeout_ms=20000)
     sums = torch.zeros(2 * obs_dim, dtype=torch.float64, device=dev)
     roll = min(32, R)
 
@@ -390,14 +395,25 @@ def run_gpu(args):
             rn.moments(envs[r].obs_buf, sums)
         rn.update_from_moments(sums, roll * N)
 
-    rms_once()
-    barrier()
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r0.record()
-    rms_once()
-    r1.record()
-    barrier()
-    rms_ms = r0.elapsed_time(r1)
+    def timed_ms(fn, reps=1):
+        fn()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(reps):
+            fn()
+        r1.record()
+        barrier()
+        t = torch.tensor([r0.elapsed_time(r1) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rms_ms = timed_ms(rms_once)
+    exch_fused_us = timed_ms(lambda: rn.update_from_moments(sums, roll * N), reps=50) * 1e3
+    exch_nccl_us = timed_ms(lambda: rn_nccl.update_from_moments(sums, roll * N), reps=50) * 1e3
+    if world > 1:
+        rn._peers.status()  # raises if any launch timed out waiting for a peer
 
     if rank != 0:
         if world > 1:
@@ -430,8 +446,11 @@ def run_gpu(args):
                      "traffic": load_traffic(T), "peak_source": peak_src, "bytes_per_env_step": bytes_step,
                      "kernel": "phc::step_fast_kernel<4,8>" if T == 1 else "phc::step_multi_kernel", "launch_ms": ms_per_step},
         "rms": {"what": f"RunningNorm.update over a {roll}-step rollout: fp64 column moments + "
-                        f"{'1 NCCL all-reduce of ' + str((2 * obs_dim + 1) * 8) + ' B' if world > 1 else 'no collective (1 GPU)'} + blend",
-                "ms_per_rollout": rms_ms},
+                        + (f"one fused launch per rank (all-reduce of {(2 * obs_dim + 1) * 8} B over NVLink peer memory + blend)"
+                           if world > 1 else "blend (1 GPU: no exchange)"),
+                "ms_per_rollout": rms_ms,
+                "exchange_and_blend_us": {"fused_peer_kernel" if world > 1 else "update_kernel": exch_fused_us,
+                                          "nccl_all_reduce_plus_update_kernel" if world > 1 else "update_kernel_again": exch_nccl_us}},
     }  # fmt: skip
 
     if world == 1 and not args.no_cpu_baseline:

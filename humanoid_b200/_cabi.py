@@ -208,6 +208,9 @@ class PhcHostStepArgs(C.Structure):
 
 
 BUILD_FILTER_RADIUS = 8
+PEER_MAX_WORLD = 16
+PEER_HANDLE_BYTES = 64
+PEER_TIMEOUT = -7
 
 
 class PhcBuildArgs(C.Structure):
@@ -293,6 +296,16 @@ SIGNATURES = {
         [C.c_void_p, C.POINTER(PhcAmpEnvArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p],
     ),
     "phc_motion_build": (C.c_int, [C.POINTER(PhcBuildArgs), C.c_void_p]),
+    "phc_peer_reduce_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
+    "phc_peer_reduce_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phc_peer_reduce_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phc_peer_reduce_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "phc_running_norm_update_peers": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "phc_peer_reduce_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "phc_peer_reduce_destroy": (None, [C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -7,5 +7,5 @@ here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="${here}/../libphc_b200.so"
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
   -Xcompiler -fPIC,-fvisibility=hidden -shared ${PHC_NVCC_EXTRA:-} \
-  -o "${out}" "${here}/phc_kernels.cu" "${here}/phc_host.cu" "${here}/phc_build.cu"
+  -o "${out}" "${here}/phc_kernels.cu" "${here}/phc_host.cu" "${here}/phc_build.cu" "${here}/phc_peer.cu"
 echo "built ${out}"

@@ -2019,6 +2019,7 @@ const char* phc_strerror(int code) {
     case PHC_ERR_UNSUPPORTED: return "not supported by this build";
     case PHC_ERR_CUDA: return "CUDA runtime error";
     case PHC_ERR_ALLOC: return "allocation failed";
+    case PHC_PEER_TIMEOUT: return "a peer rank did not publish its partials in time";
     default: return "unknown error";
   }
 }

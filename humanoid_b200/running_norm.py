@@ -64,9 +64,21 @@ class RunningNorm(nn.Module):
         )
         return sums
 
+    def enable_peer_reduce(self, group=None, timeout_ms: int = 0):
+        """Multi-GPU: do the all-reduce and the blend in ONE kernel over NVLink peer memory instead of
+        NCCL all-reduce + update kernel (``parallel.PeerReduce``).  Collective: every rank of ``group`` calls it."""
+        from .parallel import PeerReduce
+
+        self._peers = PeerReduce.from_process_group(self.shape, self.running_mean.device, group, timeout_ms)
+        return self._peers
+
     @torch.no_grad()
     def update_from_moments(self, sums: torch.Tensor, rows: int, group=None):
-        """Blend statistics given local partials; all-reduces them first when distributed."""
+        """Blend statistics given local partials; all-reduces them first when distributed.  With
+        ``enable_peer_reduce`` the reduction and the blend are one launch and ``sums`` is zeroed by it."""
+        if getattr(self, "_peers", None) is not None:
+            self._peers.update(self.running_mean, self.running_var, self.count, sums, rows)
+            return
         payload = reduce_moments(sums, rows, group)
         n = 2 * self.shape
         _cabi.check(

@@ -50,7 +50,8 @@ enum {
   PHC_ERR_ALIGN = -3,       /* pointer or stride not aligned as required */
   PHC_ERR_UNSUPPORTED = -4, /* valid in the reference, not implemented here */
   PHC_ERR_CUDA = -5,        /* CUDA runtime error (phc_last_cuda_error() has the code) */
-  PHC_ERR_ALLOC = -6
+  PHC_ERR_ALLOC = -6,
+  PHC_PEER_TIMEOUT = -7     /* a peer rank did not publish its partials within the timeout */
 };
 
 PHC_API const char* phc_strerror(int code);
@@ -374,6 +375,36 @@ PHC_API int phc_obs_moments(const float* x, int64_t rows, int64_t cols, int64_t 
 PHC_API int phc_running_norm_update(float* running_mean, float* running_var, float* count, const double* sums,
                             const double* total_rows /* device scalar */, int64_t cols,
                             phc_stream_t stream);
+/* ------------------------------------------------------------------------------------
+ * RunningNorm.update across the GPUs of one node in ONE launch per rank: the all-reduce of the
+ * [2*cols + 1] fp64 partials over NVLink peer memory fused with the blend (running_norm.py:23-34
+ * over the concatenated batch of all ranks).  Replaces ncclAllReduce + phc_running_norm_update.
+ *   create            -> allocates this rank's mailbox (device memory, two slots + flags)
+ *   handle / connect  -> CUDA IPC: every rank exports PHC_PEER_HANDLE_BYTES, the caller all-gathers
+ *                        them (any host channel) and hands connect() the world * 64 bytes in rank order
+ *   connect_local     -> same for "ranks" that live in one process (tests, one-process-many-GPUs)
+ *   update_peers      -> one kernel: publish sums[2*cols] + rows, wait for every rank's epoch flag,
+ *                        add the payloads in rank order (bit-identical statistics on every rank),
+ *                        blend into running_mean / running_var, count += 1, zero sums.
+ *                        rows: device scalar if rows_dev != NULL, else the value `rows`.
+ *                        Never synchronises; CUDA-graph capturable (the epoch lives on the device).
+ *   status            -> synchronises; PHC_PEER_TIMEOUT if a launch gave up waiting (its update was
+ *                        skipped), and the number of completed reductions.
+ * ---------------------------------------------------------------------------------- */
+#define PHC_PEER_MAX_WORLD 16
+#define PHC_PEER_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
+typedef struct PhcPeerReduce PhcPeerReduce;
+PHC_API int phc_peer_reduce_create(int32_t rank, int32_t world, int64_t cols, int64_t timeout_ms /* <= 0: 5000 */,
+                                   PhcPeerReduce** out);
+PHC_API int phc_peer_reduce_handle(const PhcPeerReduce* ctx, void* handle_out /* 64 bytes */);
+PHC_API int phc_peer_reduce_connect(PhcPeerReduce* ctx, const void* handles /* world * 64 bytes, rank order */);
+PHC_API int phc_peer_reduce_connect_local(PhcPeerReduce* ctx, PhcPeerReduce* const* all /* [world] */);
+PHC_API int phc_running_norm_update_peers(PhcPeerReduce* ctx, double* sums, const double* rows_dev, double rows,
+                                          float* running_mean, float* running_var, float* count,
+                                          phc_stream_t stream);
+PHC_API int phc_peer_reduce_status(PhcPeerReduce* ctx, int64_t* completed_out /* may be NULL */);
+PHC_API void phc_peer_reduce_destroy(PhcPeerReduce* ctx);
+
 /* RunningNorm.forward                                      policies/running_norm.py:15-20 */
 PHC_API int phc_running_norm_forward(const float* x, int64_t rows, int64_t cols, int64_t row_stride,
                              const float* running_mean, const float* running_var, float epsilon,

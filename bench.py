@@ -384,8 +384,18 @@ def run_gpu(args):
     # the NCCL all-reduce + update-kernel path is timed beside it.
     rn = RunningNorm(obs_dim, device=dev)
     rn_nccl = RunningNorm(obs_dim, device=dev)
+    peer_note = None
     if world > 1:
-        rn.enable_peer_reduce(timeout_ms=20000)
+        try:
+            rn.enable_peer_reduce(timeout_ms=20000)
+            ok = torch.ones(1, device=dev)
+        except Exception as exc:  # e.g. no P2P between two of the devices: keep the NCCL path, say so in the line
+            peer_note = f"peer path unavailable on rank {rank}: {exc}"
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks or none
+        if float(ok.item()) == 0.0:
+            rn._peers = None
+            peer_note = peer_note or "peer path unavailable on another rank"
     sums = torch.zeros(2 * obs_dim, dtype=torch.float64, device=dev)
     roll = min(32, R)
 
@@ -412,8 +422,12 @@ def run_gpu(args):
     rms_ms = timed_ms(rms_once)
     exch_fused_us = timed_ms(lambda: rn.update_from_moments(sums, roll * N), reps=50) * 1e3
     exch_nccl_us = timed_ms(lambda: rn_nccl.update_from_moments(sums, roll * N), reps=50) * 1e3
-    if world > 1:
-        rn._peers.status()  # raises if any launch timed out waiting for a peer
+    if world > 1 and rn._peers is not None:
+        try:
+            rn._peers.status()  # raises if any launch timed out waiting for a peer
+        except Exception as exc:
+            peer_note = f"peer launch failed: {exc}"
+    fused_on = world > 1 and getattr(rn, "_peers", None) is not None
 
     if rank != 0:
         if world > 1:
@@ -447,10 +461,12 @@ def run_gpu(args):
                      "kernel": "phc::step_fast_kernel<4,8>" if T == 1 else "phc::step_multi_kernel", "launch_ms": ms_per_step},
         "rms": {"what": f"RunningNorm.update over a {roll}-step rollout: fp64 column moments + "
                         + (f"one fused launch per rank (all-reduce of {(2 * obs_dim + 1) * 8} B over NVLink peer memory + blend)"
-                           if world > 1 else "blend (1 GPU: no exchange)"),
+                           if fused_on else f"NCCL all-reduce of {(2 * obs_dim + 1) * 8} B + blend" if world > 1
+                           else "blend (1 GPU: no exchange)"),
                 "ms_per_rollout": rms_ms,
-                "exchange_and_blend_us": {"fused_peer_kernel" if world > 1 else "update_kernel": exch_fused_us,
-                                          "nccl_all_reduce_plus_update_kernel" if world > 1 else "update_kernel_again": exch_nccl_us}},
+                "exchange_and_blend_us": {"fused_peer_kernel" if fused_on else "update_path": exch_fused_us,
+                                          "nccl_all_reduce_plus_update_kernel" if world > 1 else "update_path_again": exch_nccl_us},
+                **({"note": peer_note} if peer_note else {})},
     }  # fmt: skip
 
     if world == 1 and not args.no_cpu_baseline:

@@ -30,6 +30,7 @@ class RunningNorm(nn.Module):
         self.epsilon = epsilon
         self.clip = clip
         self.shape = shape
+        self._peers = None  # parallel.PeerReduce once enable_peer_reduce() was called
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # :15-20
         _cabi.require_cuda(x, "x", torch.float32)

@@ -1329,3 +1329,51 @@ def test_eval_sweep_swaps_libraries_and_walks_the_clips(golden):
     assert env._motion_lib is train and not env.flag_test
     assert hist.tolist() == [0, 1, 0, 0, 1, 0] and train._sampling_prob.tolist() == [0, 0.5, 0, 0, 0.5, 0]
     assert float(env._termination_distances[0]) == 0.25
+
+
+def test_motion_build_large_ragged_library_properties():
+    """Size-independent properties at ~0.5 M frames (3000 ragged clips, mixed fps), where the oracle would take minutes:
+    rigid translation at constant velocity with constant joint rotations must give exact kinematics."""
+    import numpy as np
+    from scipy.spatial.transform import Rotation as R
+
+    from humanoid_b200.motion_build import build_motion_tensors
+
+    rng = np.random.default_rng(11)
+    parents = [-1, 0, 1, 2, 3, 0, 5, 6, 7, 0, 9, 10, 11, 12, 11, 14, 15, 16, 17, 11, 19, 20, 21, 22]
+    M = 3000
+    nf = rng.integers(2, 340, size=M)
+    nf[:3] = (2, 3, 7000)  # shortest clips and one AMASS-length clip
+    fps = rng.choice([30, 60, 120], size=M)
+    F = int(nf.sum())
+    starts = np.concatenate([[0], np.cumsum(nf)])
+    clip = np.repeat(np.arange(M), nf)
+    k = np.arange(F) - starts[clip]  # frame index inside the clip
+    vel = rng.normal(size=(M, 3)) * 0.01  # positions stay within a few metres even over the 7000-frame clip
+    x0 = rng.normal(size=(M, 3))
+    trans = x0[clip] + vel[clip] * (k / fps[clip])[:, None]
+    pose = R.random(M * 24, random_state=2).as_quat().reshape(M, 24, 4)  # one constant pose per clip
+    pose *= np.where(pose[..., 3:] < 0, -1.0, 1.0)  # w >= 0, the loader's canonical sign (quat_pos)
+    quat = pose[clip]
+    lt = (rng.normal(size=(M, 24, 3)) * 0.2).astype(np.float32)
+    out = build_motion_tensors(quat, trans, None, nf, fps, parents, lt, device=DEV)
+    torch.cuda.synchronize()
+    assert out["gts"].shape == (F, 24, 3) and torch.equal(out["length_starts"].cpu(), torch.from_numpy(starts[:-1]))
+    assert torch.equal(out["grs"].cpu(), torch.from_numpy(quat).float()), "global rotations are the inputs, rounded"
+    assert torch.equal(out["gts"][:, 0].cpu(), torch.from_numpy(trans).float()), "root = root translation, rounded"
+    # constant pose: no angular or dof velocity anywhere, bodies ride along with the root
+    assert float(out["gavs"].abs().max()) == 0.0 and float(out["dvs"].abs().max()) < 1e-3
+    rel = (out["gts"] - out["gts"][:, :1]).cpu()
+    first = torch.from_numpy(starts[:-1])
+    assert float((rel - rel[first][clip]).abs().max()) < 2e-5, "body offsets from the root are constant inside a clip"
+    # constant root velocity survives np.gradient and the 17-tap filter with 'nearest' edges (taps sum to 1)
+    want = torch.from_numpy(vel[clip]).float()[:, None, :].expand(-1, 24, -1)
+    err = (out["gvs"].cpu() - want).abs()
+    tol = 2e-5 + fps[clip][:, None, None] * float(np.spacing(np.float32(np.abs(trans).max() + 1.0)))  # one fp32 position ulp times fps
+    assert bool((err <= torch.from_numpy(tol)).all()), float(err.max())
+    # local rotations compose back to the global ones through the tree
+    lrs, grs = out["lrs"].cpu().double(), out["grs"].cpu().double()
+    j = 7
+    comp = O.quat_mul(grs[:, parents[j]], lrs[:, j])
+    sign = torch.sign((comp * grs[:, j]).sum(-1, keepdim=True))
+    assert float((comp * sign - grs[:, j]).abs().max()) < 1e-6

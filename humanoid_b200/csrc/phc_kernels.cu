@@ -1193,7 +1193,8 @@ __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, 
   return r;
 }
 
-template <int EPB, int MINB>
+// NORM: compiled with the RunningNorm.forward epilogue (obs_norm set); the plain instantiation carries none of it
+template <int EPB, int MINB, bool NORM = false>
 __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem<EPB>& S = *reinterpret_cast<FastSmem<EPB>*>(smem_raw);
@@ -1482,6 +1483,61 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       atomicAdd(p.moments + STAGE_FLOATS + c, s2);
     }
   }
+  // RunningNorm.forward, fp32 rows, full blocks: once the raw store has READ the stage, normalise it in place and
+  // send it out with a second bulk store instead of 20 scattered 8-byte stores per thread
+  const bool norm_inplace = NORM && p.obs_norm && bulk_ok && !p.norm_bf16;
+  if (norm_inplace) {
+    if (tid == NT - 1) bulk_wait_read();
+    __syncthreads();
+    float2* st = reinterpret_cast<float2*>(S.frames);
+    for (int c2 = tid; c2 < STAGE_FLOATS / 2; c2 += NT) {
+      float m0, sd0, r0, m1, sd1, r1;
+      norm_column(p, 2 * c2, m0, sd0, r0);
+      norm_column(p, 2 * c2 + 1, m1, sd1, r1);
+      for (int ee = 0; ee < nvalid; ++ee) {
+        const float2 x = st[ee * (STAGE_FLOATS / 2) + c2];
+        st[ee * (STAGE_FLOATS / 2) + c2] =
+            make_float2(norm_value(x.x, m0, sd0, r0, p.norm_clip), norm_value(x.y, m1, sd1, r1, p.norm_clip));
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == NT - 1) bulk_s2g(p.obs_norm + env0 * STAGE_FLOATS, S.frames, out_bytes);
+  }
+  // bf16 rows, full blocks: the four rows (7472 B) are packed into shared memory that is dead by now — the sim tile
+  // and the tail of the frame buffer behind the stage — so nothing waits for the raw store; the split falls on
+  // bf16 element 1864 so that both pieces are multiples of 16 B, and they leave with two bulk stores
+  constexpr int NORM16_SPLIT = 932;  // pairs in the first piece: 3728 B, the second holds 936 pairs = 3744 B
+  static_assert(EPB != 4 || (NORM16_SPLIT * 4 <= (int)sizeof(S.sim) && (EPB * STAGE_FLOATS / 2 - NORM16_SPLIT) * 4 <=
+                                 (int)sizeof(S.frames) - EPB * STAGE_FLOATS * 4), "bf16 staging fits the dead regions");
+  const bool norm16_staged =
+      NORM && p.obs_norm && bulk_ok && p.norm_bf16 && nvalid == EPB && EPB == 4 && ((uintptr_t)p.obs_norm & 15) == 0;
+  if (norm16_staged) {
+    __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(S.sim);
+    __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(S.frames + EPB * STAGE_FLOATS);
+    const float2* src = reinterpret_cast<const float2*>(S.frames);
+    for (int c2 = tid; c2 < STAGE_FLOATS / 2; c2 += NT) {
+      float m0, sd0, r0, m1, sd1, r1;
+      norm_column(p, 2 * c2, m0, sd0, r0);
+      norm_column(p, 2 * c2 + 1, m1, sd1, r1);
+#pragma unroll
+      for (int ee = 0; ee < EPB; ++ee) {
+        const int i = ee * (STAGE_FLOATS / 2) + c2;
+        const float2 x = src[i];
+        const __nv_bfloat162 y = __floats2bfloat162_rn(norm_value(x.x, m0, sd0, r0, p.norm_clip),
+                                                       norm_value(x.y, m1, sd1, r1, p.norm_clip));
+        if (i < NORM16_SPLIT) pa[i] = y;
+        else pb[i - NORM16_SPLIT] = y;
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == NT - 1) {
+      __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(p.obs_norm) + env0 * (STAGE_FLOATS / 2);
+      bulk_s2g(dst, pa, NORM16_SPLIT * 4);
+      bulk_s2g(dst + NORM16_SPLIT, pb, (EPB * STAGE_FLOATS / 2 - NORM16_SPLIT) * 4);
+    }
+  }
   // ---- reductions and scalar outputs (warp 0), off the critical path: nothing waits for them -------------------------------------------------
   if (tid < 32) {
     const int le = tid >> 2, k = tid & 3;
@@ -1526,7 +1582,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     if (act && k == 2 && p.mpjpe) p.mpjpe[env0 + le] = row_sum24(&S.part[4][le][0]) / 24.0f;  // humanoid_phc.py:167
   }
 
-  if (p.obs_norm) {
+  if (NORM && p.obs_norm && !norm_inplace && !norm16_staged) {
     // RunningNorm.forward fused into the epilogue: the staged rows are read a second time (while the
     // bulk store drains them) and leave normalised with coalesced 8-byte stores; mean / var are 7.5 KB
     // that every block reads from L2
@@ -2449,6 +2505,9 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
       first_wave[dev] = sms * (per_sm > 0 ? per_sm : 1);
     }
     p.first_wave_blocks = (g_pdl && !(args->flags & PHC_STEP_MAPPED_HOST_IO)) ? first_wave[dev] : 0;
+    static bool attr_fast4_norm[64] = {};
+    if (p.obs_norm)
+      return launch_step(step_fast_kernel<4, 8, true>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4_norm[dev], g_pdl != 0);
     return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev], g_pdl != 0);
   }
   // T > 1 on the AoS tensor + packed table: the pipelined TMA kernel

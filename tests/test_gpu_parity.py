@@ -1377,3 +1377,102 @@ def test_motion_build_large_ragged_library_properties():
     comp = O.quat_mul(grs[:, parents[j]], lrs[:, j])
     sign = torch.sign((comp * grs[:, j]).sum(-1, keepdim=True))
     assert float((comp * sign - grs[:, j]).abs().max()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------
+# no kernel writes outside its outputs (compute-sanitizer is not available on the pool): every output buffer of
+# the env is re-seated in the middle of a canary-filled allocation
+# ---------------------------------------------------------------------------------------
+def _guarded(t, pad=4096):
+    """A tensor like ``t`` carved out of a larger allocation whose bytes before and after it hold a canary."""
+    nbytes = t.numel() * t.element_size()
+    lead = pad + (-pad) % 256
+    raw = torch.full((lead + nbytes + pad,), 0xA5, dtype=torch.uint8, device=t.device)
+    view = raw[lead : lead + nbytes].view(t.dtype).view(t.shape)
+    view.copy_(t)
+    return raw, view, lead, nbytes
+
+
+@pytest.mark.parametrize("N,T,mode", [(4099, 1, "fast"), (4096, 1, "fast_norm16"), (4099, 1, "fast_norm32"), (1001, 1, "generic"),
+                                      (515, 3, "multi"), (515, 3, "generic_norm")])  # fmt: skip
+def test_step_kernels_stay_inside_their_output_buffers(N, T, mode):
+    from humanoid_b200 import HumanoidPHC, RunningNorm, _cabi
+
+    lib_data, clock, state = _gpu_case(N, 48, 321, max_progress=30)
+    env = HumanoidPHC(MotionLib(lib_data, device=DEV), N, device=DEV, time_steps=T, obs_moments=True)
+    env.set_sim_state(state)
+    env.set_clock(clock)
+    if "norm" in mode:
+        env.set_obs_normalizer(RunningNorm(env.num_obs, device=DEV), dtype=torch.bfloat16 if "16" in mode else torch.float32)
+    guards = {}
+    for name in ("obs_buf", "rew_buf", "reward_raw", "reset_buf", "_terminate_buf", "progress_buf", "obs_norm_buf", "obs_moments"):
+        t = getattr(env, name)
+        if t is None:
+            continue
+        raw, view, lead, nbytes = _guarded(t)
+        setattr(env, name, view)
+        guards[name] = (raw, lead, nbytes)
+    env._step_args = None
+    capi = _cabi.load()
+    try:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if mode.startswith("generic") else 0)
+        for _ in range(3):
+            env.step()
+    finally:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+    torch.cuda.synchronize()
+    assert float(env.obs_buf.abs().sum()) > 0 and int(env.progress_buf.max()) >= 3
+    for name, (raw, lead, nbytes) in guards.items():
+        assert bool((raw[:lead] == 0xA5).all()), f"{name}: bytes before the buffer were written"
+        assert bool((raw[lead + nbytes :] == 0xA5).all()), f"{name}: bytes after the buffer were written"
+
+
+def test_build_and_reset_kernels_stay_inside_their_output_buffers(golden):
+    """Same for the per-function outputs that have ragged shapes: the motion-library build (dvs rows are 23 joints,
+    motion_aa 72) and the device-side reset of a few envs."""
+    import ctypes as C
+
+    import numpy as np
+
+    from humanoid_b200 import HumanoidPHC, _cabi
+    from humanoid_b200.motion_build import gaussian_taps
+
+    g = golden("motion_build")
+    F, M = int(g.inp("num_frames").sum()), len(g.inp("num_frames"))
+    starts = np.concatenate([[0], np.cumsum(g.inp("num_frames").tolist())[:-1]]).astype(np.int64)
+    dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(DEV)  # noqa: E731
+    ins = [dev(g.inp("pose_quat_global").numpy(), torch.float64), dev(g.inp("root_trans_offset").numpy(), torch.float64),
+           dev(g.inp("pose_aa").numpy(), torch.float64), dev(g.inp("local_translation").numpy(), torch.float32),
+           dev(g.inp("num_frames").numpy(), torch.int64), dev(starts, torch.int64), dev(g.inp("fps").numpy(), torch.float64)]  # fmt: skip
+    shapes = {"gts": (F, 24, 3), "grs": (F, 24, 4), "lrs": (F, 24, 4), "gvs": (F, 24, 3), "gavs": (F, 24, 3), "dvs": (F, 23, 3),
+              "motion_aa": (F, 72)}  # fmt: skip
+    outs = {k: _guarded(torch.zeros(v, device=DEV)) for k, v in shapes.items()}
+    scratch = _guarded(torch.zeros(F * 108, dtype=torch.float64, device=DEV))
+    parents = (C.c_int32 * 24)(*g.inp("parent_indices").tolist())
+    taps = (C.c_double * 17)(*gaussian_taps().tolist())
+    args = _cabi.PhcBuildArgs(*[t.data_ptr() for t in ins], None, parents, taps, F, M,
+                              *[outs[k][1].data_ptr() for k in ("gts", "grs", "lrs", "gvs", "gavs", "dvs", "motion_aa")],
+                              scratch[1].data_ptr())  # fmt: skip
+    _cabi.check(_cabi.load().phc_motion_build(C.byref(args), torch.cuda.current_stream().cuda_stream), "phc_motion_build")
+    torch.cuda.synchronize()
+    assert_close(outs["gts"][1].cpu(), g.out("deterministic.gts"), rtol=0, atol=0, what="gts")
+    for name, (raw, _, lead, nbytes) in list(outs.items()) + [("scratch", scratch)]:
+        assert bool((raw[:lead] == 0xA5).all()) and bool((raw[lead + nbytes :] == 0xA5).all()), name
+
+    lib_data, clock, state = _gpu_case(37, 5, 77, max_progress=10)
+    env = HumanoidPHC(MotionLib(lib_data, device=DEV), 37, device=DEV, use_amp_obs=True)
+    env.set_clock(clock)
+    guards = {}
+    for name in ("obs_buf", "progress_buf", "reset_buf", "_terminate_buf", "_motion_start_times", "_global_offset",
+                 "_humanoid_root_states", "_rigid_body_state_reshaped", "_amp_obs_buf", "_amp_obs_demo_buf"):  # fmt: skip
+        raw, view, lead, nbytes = _guarded(getattr(env, name))
+        setattr(env, name, view)
+        guards[name] = (raw, lead, nbytes)
+    env._bind_body_views()
+    env._curr_amp_obs_buf, env._hist_amp_obs_buf = env._amp_obs_buf[:, 0], env._amp_obs_buf[:, 1:]
+    env._step_args = None
+    env.reset(torch.tensor([0, 5, 36], device=DEV), torch.tensor([0.1, 0.5, 0.9], device=DEV))
+    env.step()
+    torch.cuda.synchronize()
+    for name, (raw, lead, nbytes) in guards.items():
+        assert bool((raw[:lead] == 0xA5).all()) and bool((raw[lead + nbytes :] == 0xA5).all()), name

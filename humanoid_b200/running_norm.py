@@ -32,6 +32,13 @@ class RunningNorm(nn.Module):
         self.shape = shape
         self._peers = None  # parallel.PeerReduce once enable_peer_reduce() was called
 
+    def __getstate__(self):
+        """``torch.save(model)`` (running_norm.py:36-53): buffers and scalars travel, the peer mailbox (device memory
+        mapped into other processes) does not — call ``enable_peer_reduce`` again after loading."""
+        state = self.__dict__.copy()
+        state["_peers"] = None
+        return state
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # :15-20
         _cabi.require_cuda(x, "x", torch.float32)
         x2 = x.reshape(-1, self.shape)

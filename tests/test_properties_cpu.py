@@ -119,3 +119,28 @@ def test_clip_sampler_host_logic():
     assert not s.update_sampling_prob(torch.zeros(5)) and not s.update_sampling_prob(torch.ones(4))
     s.update_hard_sampling_weight([])
     assert torch.allclose(s._sampling_prob, torch.full((5,), 0.2))
+
+
+def test_running_norm_checkpoint_compatibility():
+    """the accumulators stay plain fp32 buffers under the reference's names, so a reference checkpoint
+    loads; pickling the module drops the peer mailbox handle instead of failing."""
+    import io
+    import pickle
+
+    from humanoid_b200 import RunningNorm
+
+    rn = RunningNorm(934, device="cpu")
+    sd = rn.state_dict()
+    assert list(sd) == ["running_mean", "running_var", "count"]
+    assert sd["running_mean"].shape == (1, 934) and sd["running_var"].shape == (1, 934) and sd["count"].shape == (1,)
+    assert all(v.dtype == torch.float32 for v in sd.values())
+    ref_like = {"running_mean": torch.full((1, 934), 0.5), "running_var": torch.full((1, 934), 2.0), "count": torch.tensor([7.0])}
+    rn.load_state_dict(ref_like)
+    assert float(rn.count) == 7.0 and float(rn.running_var[0, 3]) == 2.0
+    rn._peers = object()  # stands in for a live PeerReduce (holds a ctypes pointer)
+    buf = io.BytesIO()
+    torch.save(rn, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert back._peers is None and torch.equal(back.running_mean, rn.running_mean) and back.clip == rn.clip
+    assert pickle.loads(pickle.dumps(rn))._peers is None

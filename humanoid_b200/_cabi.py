@@ -126,6 +126,7 @@ class PhcStepArgs(C.Structure):
         ("norm_epsilon", C.c_float),
         ("norm_clip", C.c_float),
         ("mpjpe", C.c_void_p),
+        ("obs_moments_buckets", C.c_int32),
     ]
 
 
@@ -296,6 +297,7 @@ SIGNATURES = {
         [C.c_void_p, C.POINTER(PhcAmpEnvArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p],
     ),
     "phc_motion_build": (C.c_int, [C.POINTER(PhcBuildArgs), C.c_void_p]),
+    "phc_obs_moments_fold": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "phc_peer_reduce_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
     "phc_peer_reduce_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "phc_peer_reduce_connect": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -795,6 +795,7 @@ struct StepParams {
   uint8_t* reset;
   uint8_t* term;
   double* moments;
+  int moment_buckets;  // >= 1: moments is [buckets][2W]; block b adds into bucket b % buckets
   float* mpjpe;     // NULL, or [n]: mean over the 24 bodies of |body_pos - ref_body_pos| (extras["mpjpe"])
   float* obs_norm;  // NULL, or the normalised copy of the obs rows (RunningNorm.forward)
   int64_t obs_norm_stride;
@@ -1125,8 +1126,9 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
           s1 += x;
           s2 += x * x;
         }
-        atomicAdd(p.moments + c_off + c, s1);
-        atomicAdd(p.moments + W + c_off + c, s2);
+        double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * W;
+        atomicAdd(mom + c_off + c, s1);
+        atomicAdd(mom + W + c_off + c, s2);
       }
     }
     if (p.obs_norm) {  // RunningNorm.forward of the same staged columns
@@ -1479,8 +1481,9 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
         s1 += x;
         s2 += x * x;
       }
-      atomicAdd(p.moments + c, s1);
-      atomicAdd(p.moments + STAGE_FLOATS + c, s2);
+      double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * STAGE_FLOATS;
+      atomicAdd(mom + c, s1);
+      atomicAdd(mom + STAGE_FLOATS + c, s2);
     }
   }
   // RunningNorm.forward, fp32 rows, full blocks: once the raw store has READ the stage, normalise it in place and
@@ -1801,8 +1804,9 @@ __global__ void __launch_bounds__(MULTI_EPB* J24, 5) step_multi_kernel(const Ste
             s1 += x;
             s2 += x * x;
           }
-          atomicAdd(p.moments + c_off + c, s1);
-          atomicAdd(p.moments + W + c_off + c, s2);
+          double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * W;
+          atomicAdd(mom + c_off + c, s1);
+          atomicAdd(mom + W + c_off + c, s2);
         }
       }
       if (valid && b == 0) bulk_wait_read();
@@ -1859,17 +1863,19 @@ __global__ void __launch_bounds__(MULTI_EPB* J24, 5) step_multi_kernel(const Ste
 // RunningNorm kernels (policies/running_norm.py:15-34)
 // ---------------------------------------------------------------------------------------
 constexpr int MOM_ROWS_PER_BLOCK = 32;
+constexpr int MOM_MAX_ROW_BLOCKS = 256;
 
-// grid (ceil(cols / (128*VEC)), ceil(rows / 32)); a thread owns VEC adjacent columns (coalesced
-// across the warp) and walks 32 rows with 8 independent loads in flight; fp64 partials are merged
-// with one atomicAdd per column per block.
+// grid (ceil(cols / (128*VEC)), ceil(rows / rows_per_block)); a thread owns VEC adjacent columns (coalesced
+// across the warp) and walks its rows with 8 independent loads in flight; fp64 partials are merged
+// with one atomicAdd per column per block.  fp64 atomics on one address serialise (~30 ns each), so the
+// host caps the number of row blocks at MOM_MAX_ROW_BLOCKS by giving each block more rows.
 template <int VEC>
 __global__ void obs_moments_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t stride,
-                                   double* __restrict__ sums) {
+                                   int64_t rows_per_block, double* __restrict__ sums) {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-  const int64_t r0 = (int64_t)blockIdx.y * MOM_ROWS_PER_BLOCK;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   if (c >= cols) return;
-  const int64_t r1 = r0 + MOM_ROWS_PER_BLOCK < rows ? r0 + MOM_ROWS_PER_BLOCK : rows;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   double s1[VEC], s2[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) s1[v] = s2[v] = 0.0;
@@ -1906,6 +1912,18 @@ __global__ void obs_moments_kernel(const float* __restrict__ x, int64_t rows, in
       atomicAdd(sums + c + v, s1[v]);
       atomicAdd(sums + cols + c + v, s2[v]);
     }
+}
+
+// sums[i] += sum_b buckets[b][i] in bucket order; buckets are left zero
+__global__ void moments_fold_kernel(double* __restrict__ buckets, int nb, int64_t cols2, double* __restrict__ sums) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cols2) return;
+  double acc = sums[i];
+  for (int b = 0; b < nb; ++b) {
+    acc += buckets[(int64_t)b * cols2 + i];
+    buckets[(int64_t)b * cols2 + i] = 0.0;
+  }
+  sums[i] = acc;
 }
 
 __global__ void running_norm_update_kernel(float* __restrict__ mean, float* __restrict__ var,
@@ -2290,6 +2308,8 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.reset = a->reset_buf;
   p.term = a->terminate_buf;
   p.moments = a->obs_moments;
+  p.moment_buckets = a->obs_moments_buckets > 1 ? a->obs_moments_buckets : 1;
+  if (a->obs_moments_buckets < 0 || a->obs_moments_buckets > 4096) return PHC_ERR_SHAPE;
   p.mpjpe = a->mpjpe;
   p.obs_norm = a->obs_norm;
   p.obs_norm_stride = a->obs_norm_stride;
@@ -2525,16 +2545,25 @@ int phc_obs_moments(const float* x, int64_t rows, int64_t cols, int64_t row_stri
   if (rows == 0 || cols == 0) return PHC_OK;
   if (rows < 0 || cols < 0 || row_stride < cols) return PHC_ERR_SHAPE;
   if (!x || !sums) return PHC_ERR_NULL;
-  const unsigned gy = (unsigned)((rows + MOM_ROWS_PER_BLOCK - 1) / MOM_ROWS_PER_BLOCK);
-  if (gy > 65535u) return PHC_ERR_SHAPE;
+  int64_t rpb = MOM_ROWS_PER_BLOCK;
+  if ((rows + rpb - 1) / rpb > MOM_MAX_ROW_BLOCKS) rpb = ((rows + MOM_MAX_ROW_BLOCKS - 1) / MOM_MAX_ROW_BLOCKS + 7) / 8 * 8;
+  const unsigned gy = (unsigned)((rows + rpb - 1) / rpb);
   const bool vec2 = (cols % 2 == 0) && (row_stride % 2 == 0) && (((uintptr_t)x & 7) == 0);
   if (vec2) {
     dim3 grid((unsigned)((cols / 2 + 127) / 128), gy);
-    obs_moments_kernel<2><<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, sums);
+    obs_moments_kernel<2><<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, rpb, sums);
   } else {
     dim3 grid((unsigned)((cols + 127) / 128), gy);
-    obs_moments_kernel<1><<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, sums);
+    obs_moments_kernel<1><<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, rpb, sums);
   }
+  return launch_status();
+}
+
+int phc_obs_moments_fold(double* buckets, int32_t num_buckets, int64_t cols2, double* sums, phc_stream_t stream) {
+  if (cols2 == 0 || num_buckets == 0) return PHC_OK;
+  if (cols2 < 0 || num_buckets < 0) return PHC_ERR_SHAPE;
+  if (!buckets || !sums) return PHC_ERR_NULL;
+  moments_fold_kernel<<<(unsigned)((cols2 + 127) / 128), 128, 0, stream>>>(buckets, num_buckets, cols2, sums);
   return launch_status();
 }
 

@@ -260,6 +260,11 @@ typedef struct PhcStepArgs {
   float* mpjpe;                          /* NULL or [n]: extras["mpjpe"] of eval mode, the mean over all
                                             24 bodies of |rigid_body_pos - ref rg_pos| at the reward
                                             time                              humanoid_phc.py:159-167 */
+  int32_t obs_moments_buckets;           /* 0 / 1: obs_moments is one [2*(358+576*T)] accumulator.  B > 1: obs_moments is
+                                            [B][2*(358+576*T)] and block b adds into bucket b % B — fp64 atomics on ONE
+                                            address serialise (~30 ns each), so 1024 blocks on a single accumulator cost
+                                            35 us per 4096-env step; 32 buckets make the epilogue free.  The consumer
+                                            sums the buckets (phc_obs_moments_fold).                                  */
 } PhcStepArgs;
 
 PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream);
@@ -372,6 +377,8 @@ PHC_API int64_t phc_host_step_d2h_bytes(const PhcHostStep* ctx, int64_t n);
  * ---------------------------------------------------------------------------------- */
 PHC_API int phc_obs_moments(const float* x, int64_t rows, int64_t cols, int64_t row_stride, double* sums,
                     phc_stream_t stream);
+/* sums[cols2] += sum over b of buckets[b][cols2] (fixed order), then buckets are zeroed for the next rollout */
+PHC_API int phc_obs_moments_fold(double* buckets, int32_t num_buckets, int64_t cols2, double* sums, phc_stream_t stream);
 PHC_API int phc_running_norm_update(float* running_mean, float* running_var, float* count, const double* sums,
                             const double* total_rows /* device scalar */, int64_t cols,
                             phc_stream_t stream);

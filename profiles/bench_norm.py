@@ -19,11 +19,13 @@ rn = RunningNorm(934, device=dev)
 R, K = 17, 256
 
 
-def make(fused):
+def make(fused, moments=False):
     envs = []
     for r in range(R):
         ref = lib.get_motion_state(clock.sampled_motion_ids, synth.reward_time(clock, extra_steps=r + 1), clock.global_offset)
-        env = HumanoidPHC(lib, N, device=dev)
+        env = HumanoidPHC(lib, N, device=dev, obs_moments=moments)
+        if moments and r:
+            env._obs_moment_buckets = envs[0]._obs_moment_buckets  # one accumulator for the rollout
         env.set_sim_state(synth.make_sim_state(ref, seed=1236 + r), copy=False)
         env.set_clock(clock)
         if r:
@@ -69,12 +71,17 @@ def timed(envs, after):
 
 outs = [torch.empty(N, 934, device=dev) for _ in range(R)]
 plain = timed(make(False), lambda e: None)
+mom = timed(make(False, moments=True), lambda e: None)
+sums = torch.zeros(2 * 934, dtype=torch.float64, device=dev)
+mom_sep = timed(make(False), lambda e: rn.moments(e.obs_buf, sums))
 sep = timed(make(False), lambda e: rn(e.obs_buf))
 fused = timed(make(torch.float32), lambda e: None)
 fused16 = timed(make(torch.bfloat16), lambda e: None)
 print(f"# RunningNorm.forward at N = {N} (us per step, {K}-step CUDA graph, best of 5)\n")
 print("| variant | us / step |\n|---|---|")
 print(f"| step only (raw obs) | {plain:.2f} |")
+print(f"| step with the RunningNorm moments epilogue (obs_moments: fp64 column sums accumulated in the step, 32 buckets) | {mom:.2f} |")
+print(f"| step + standalone phc_obs_moments over the same rows | {mom_sep:.2f} |")
 print(f"| step + standalone phc_running_norm_forward (allocates its output) | {sep:.2f} |")
 print(f"| step with the fused epilogue (raw + normalised fp32 rows) | {fused:.2f} |")
 print(f"| step with the fused epilogue, normalised rows as bf16 (PHC_STEP_OBS_NORM_BF16) | {fused16:.2f} |")

@@ -480,6 +480,21 @@ def test_fused_moments_epilogue_matches_column_moments():
     torch.testing.assert_close(env.obs_moments, sums, rtol=1e-12, atol=1e-9)
     x = env.obs_buf.double()
     torch.testing.assert_close(sums[:934], x.sum(0), rtol=1e-12, atol=1e-9)
+    # the step's blocks spread over buckets (one accumulator would serialise the fp64 atomics); a rollout folds them
+    assert env._obs_moment_buckets.shape == (32, 2 * 934) and int((env._obs_moment_buckets[:, 0] != 0).sum()) == 32
+    env.step()
+    both = torch.cat([x, env.obs_buf.double()])
+    got, rows = env.take_obs_moments()
+    assert rows == 2 * 3000 and float(env._obs_moment_buckets.abs().max()) == 0.0 and env.obs_moment_rows == 0
+    torch.testing.assert_close(got[:934], both.sum(0), rtol=1e-12, atol=1e-9)
+    torch.testing.assert_close(got[934:], (both * both).sum(0), rtol=1e-12, atol=1e-9)
+    got2, _ = env.take_obs_moments(got)  # += into the caller's accumulator; nothing new since the last take
+    assert got2 is got and torch.equal(got2[:934], got[:934])
+    # the standalone kernel on a rollout-sized buffer (more rows per block, still one atomic per column per block)
+    big = torch.randn(70001, 934, device=DEV) * 3 + 1
+    s_big = rn.moments(big)
+    torch.testing.assert_close(s_big[:934], big.double().sum(0), rtol=1e-12, atol=1e-8)
+    torch.testing.assert_close(s_big[934:], (big.double() ** 2).sum(0), rtol=1e-12, atol=1e-7)
     torch.testing.assert_close(sums[934:], (x * x).sum(0), rtol=1e-12, atol=1e-9)
 
 
@@ -1405,7 +1420,8 @@ def test_step_kernels_stay_inside_their_output_buffers(N, T, mode):
     if "norm" in mode:
         env.set_obs_normalizer(RunningNorm(env.num_obs, device=DEV), dtype=torch.bfloat16 if "16" in mode else torch.float32)
     guards = {}
-    for name in ("obs_buf", "rew_buf", "reward_raw", "reset_buf", "_terminate_buf", "progress_buf", "obs_norm_buf", "obs_moments"):
+    for name in ("obs_buf", "rew_buf", "reward_raw", "reset_buf", "_terminate_buf", "progress_buf", "obs_norm_buf",
+                 "_obs_moment_buckets"):  # fmt: skip
         t = getattr(env, name)
         if t is None:
             continue

@@ -483,6 +483,33 @@ def run_gpu(args):
             "sample": f"{cs} steps of the same {N}-env workload (same tensors copied to host), "
                       f"oracle/phc_oracle.py torch CPU fp32, {threads} threads",
         }  # fmt: skip
+    if world == 1 and args.torch_cuda_baseline:
+        # the reference's own deployment: the same torch ops, eager, on this GPU (about 1100 launches per step)
+        from oracle import phc_oracle as O
+
+        lib_o = O.OracleMotionLib(lib_data)
+        term = torch.full((24,), 0.25, device=dev)
+        st = envs[0]._rigid_body_state_reshaped
+
+        def torch_step():
+            prog = progress0.clone()
+            O.step(lib_o, st, prog, clock.motion_start_times, clock.motion_start_times_offset, clock.global_offset,
+                   clock.sampled_motion_ids, term, synth.SIM_DT)  # fmt: skip
+
+        with torch.no_grad():
+            for _ in range(5):
+                torch_step()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 30
+            t0.record()
+            for _ in range(reps):
+                torch_step()
+            t1.record()
+            torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / reps
+        line["torch_cuda_baseline"] = {"value": N / ms * 1e3, "unit": UNIT, "ms_per_step": ms,
+                                       "what": "oracle/phc_oracle.py (the reference's torch ops, fp32) eager on this GPU"}  # fmt: skip
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -505,6 +532,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=64)
     ap.add_argument("--e2e-chunks", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-cuda-baseline", action="store_true",
+                    help="also time the reference's torch ops (oracle port) eager on this GPU; reported, not the target")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -98,7 +98,7 @@ def heading_angle(q: Tensor) -> Tensor:
 def quat_from_z_angle(angle: Tensor) -> Tensor:
     """quat_from_angle_axis with axis (0,0,1), torch_utils.py:354-358 (+ normalize :45,
     quat_unit :174-179)."""
-    axis = torch.zeros(angle.shape + (3,), dtype=angle.dtype)
+    axis = torch.zeros(angle.shape + (3,), dtype=angle.dtype, device=angle.device)
     axis[..., 2] = 1
     half = (angle / 2).unsqueeze(-1)
     unit_axis = axis / axis.norm(p=2, dim=-1).clamp(min=1e-9, max=None).unsqueeze(-1)
@@ -159,7 +159,7 @@ _BASE_ROT_CONJ = (-0.5, -0.5, -0.5, 0.5)
 
 def remove_base_rot(q: Tensor) -> Tensor:
     """envs/common.py:15-19."""
-    base = torch.tensor(_BASE_ROT_CONJ, dtype=q.dtype).expand_as(q)
+    base = torch.tensor(_BASE_ROT_CONJ, dtype=q.dtype, device=q.device).expand_as(q)
     return quat_mul(q, base)
 
 
@@ -505,9 +505,9 @@ def step(
     vel = state[:, :J, 7:10]
     ang = state[:, :J, 10:13]
     if reset_buf is None:
-        reset_buf = torch.ones(N, dtype=torch.bool)
+        reset_buf = torch.ones(N, dtype=torch.bool, device=state.device)
     if reset_body_ids is None:
-        reset_body_ids = torch.arange(J)
+        reset_body_ids = torch.arange(J, device=state.device)
 
     progress_buf += 1
 

@@ -135,3 +135,46 @@ def test_two_processes_over_cuda_ipc():
     )  # fmt: skip
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "PEER_REDUCE_OK" in out.stdout
+
+
+def test_rollout_cycle_step_epilogue_to_fused_update():
+    """The whole statistics path of a rollout on two 'ranks': the step's moments epilogue accumulates while stepping,
+    take_obs_moments() folds the buckets, ONE fused launch per rank exchanges and blends — against
+    RunningNorm.update(experience.obs) of the reference (policies/running_norm.py:23-34, scripts/phc_train.py:331-332)
+    on the concatenated rows of both ranks."""
+    from humanoid_b200 import HumanoidPHC, MotionLib, synth
+    from oracle import phc_oracle as O
+
+    world, steps = 2, 5
+    peers, rns, streams = _ranks(world)
+    envs, rows = [], []
+    for r in range(world):
+        N = 1000 + 37 * r
+        lib_data = synth.make_motion_lib(32, 60, 120, (30,), seed=40 + r, device="cuda")
+        lib = MotionLib(lib_data, device="cuda")
+        clock = synth.make_clock(lib_data, N, seed=50 + r, max_progress=20)
+        ref = lib.get_motion_state(clock.sampled_motion_ids, synth.reward_time(clock, extra_steps=1), clock.global_offset)
+        env = HumanoidPHC(lib, N, device="cuda", obs_moments=True)
+        env.set_sim_state(synth.make_sim_state(ref, seed=60 + r))
+        env.set_clock(clock)
+        envs.append(env)
+    m, v, c = torch.zeros(1, C), torch.ones(1, C), torch.ones(1)
+    for rollout in range(2):
+        experience = []
+        for _ in range(steps):
+            for env in envs:
+                env.step()
+                experience.append(env.obs_buf.cpu().clone())
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                streams[r].wait_stream(torch.cuda.current_stream())
+                sums, n = envs[r].take_obs_moments()
+                assert n == steps * envs[r].num_envs
+                peers[r].update(rns[r].running_mean, rns[r].running_var, rns[r].count, sums, n)
+        torch.cuda.synchronize()
+        m, v, c = O.running_norm_update(m, v, c, torch.cat(experience))
+        for r in range(world):
+            assert_close(rns[r].running_mean.cpu(), m, rtol=1e-5, atol=1e-6, what=f"mean, rollout {rollout}, rank {r}")
+            assert_close(rns[r].running_var.cpu(), v, rtol=1e-5, atol=1e-6, what=f"var, rollout {rollout}, rank {r}")
+        assert torch.equal(rns[0].running_mean, rns[1].running_mean)

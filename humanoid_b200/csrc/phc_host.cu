@@ -26,6 +26,9 @@
 
 #include "../../include/phc_b200.h"
 
+// phc_kernels.cu: phc_step_fused that also writes the advanced progress to a second address
+int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream, int16_t* progress_mirror);
+
 namespace {
 
 constexpr int kStreams = 3;
@@ -219,7 +222,7 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
       // per 4096-env step when the kernel read the clock in place) — while each chunk's kernel
       // WRITES obs rows, rewards and flags straight into the mapped host buffers.  The copy
       // engine pulling chunk c+1 and the kernel pushing chunk c's rows use opposite directions of
-      // the link.  The advanced progress returns with one 2-byte-per-env copy per chunk.
+      // the link.  The advanced progress is written to the caller's buffer by the kernel as well.
       // equal chunks here: measured, a small first chunk does not help this path (the step is
       // bound by the kernels' posted writes, ~300 us per 4096 envs, plus the first copy)
       const int C = c->chunks < 1 ? 1 : c->chunks;
@@ -271,9 +274,9 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
         k.terminate_buf = a->terminate_buf + lo;
         k.flags = PHC_STEP_MAPPED_HOST_IO;
         k.obs_moments = nullptr;
-        int rc = phc_step_fused(c->lib, &k, m, s);
+        // the advanced progress goes straight into the caller's buffer too (no device->host copy at the tail)
+        int rc = step_fused_mirrored(c->lib, &k, m, s, a->progress_buf + lo);
         if (rc) return rc;
-        HOST_CUDA(c, cudaMemcpyAsync(a->progress_buf + lo, dc + L.prog, (size_t)m * 2, cudaMemcpyDeviceToHost, s));
         coff += L.clock_bytes;
       }
       for (int i = 0; i < kStreams; ++i) HOST_CUDA(c, cudaStreamSynchronize(c->streams[i]));

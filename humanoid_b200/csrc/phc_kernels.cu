@@ -778,6 +778,7 @@ struct StepParams {
   LibDev L;
   PhcBodyState body;
   int16_t* progress;
+  int16_t* progress_mirror;  // NULL, or a second place (mapped host memory) that receives the advanced progress
   const float* start;
   const float* start_off;
   const float* goff;
@@ -974,7 +975,10 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
   }
   __syncthreads();  // frame indices visible
   // progress is written only after every query lane of the env (possibly in another warp) read it
-  if (valid && b == 0 && p.advance && !p.obs_only) p.progress[env] = (int16_t)S.prog[e];
+  if (valid && b == 0 && p.advance && !p.obs_only) {
+    p.progress[env] = (int16_t)S.prog[e];
+    if (p.progress_mirror) p.progress_mirror[env] = (int16_t)S.prog[e];
+  }
 
   // ---- phase 1: reference state at t; reward; reset -------------------------------------
   load_frames<EPB>(p.L, S, 0, e, b, valid);
@@ -1340,7 +1344,10 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       S.prog[le] = prog;
       S.pass[le] = a_t >= len;  // _compute_reset, humanoid_phc.py:1317
       S.fallen[le] = 0;
-      if (p.advance) p.progress[env] = (int16_t)prog;
+      if (p.advance) {
+        p.progress[env] = (int16_t)prog;
+        if (p.progress_mirror) p.progress_mirror[env] = (int16_t)prog;
+      }
       S.goff[le][0] = g0;
       S.goff[le][1] = g1;
       S.goff[le][2] = g2;
@@ -2288,6 +2295,7 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.L = lib->d;
   p.body = a->body;
   p.progress = a->progress_buf;
+  p.progress_mirror = nullptr;
   p.start = a->motion_start_times;
   p.start_off = a->motion_start_times_offset;
   p.goff = a->global_offset;
@@ -2498,12 +2506,16 @@ int phc_set_option(int key, int value) {
   }
 }
 
-int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream) {
+}  // extern "C"
+
+// phc_step_fused plus a mirror for the advanced progress (the host pipeline points it at the caller's pinned buffer)
+int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream, int16_t* progress_mirror) {
   if (n == 0) return PHC_OK;
   if (n < 0) return PHC_ERR_SHAPE;
   StepParams p;
   int rc = step_fill_params(lib, args, n, p);
   if (rc) return rc;
+  p.progress_mirror = progress_mirror;
   int dev = 0;
   PHC_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return PHC_ERR_UNSUPPORTED;
@@ -2537,6 +2549,12 @@ int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_st
   if (multi)
     return launch_step(step_multi_kernel, sizeof(MultiSmem), MULTI_EPB, p, stream, &attr_multi[dev], false);
   return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev], false);
+}
+
+extern "C" {
+
+int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream) {
+  return step_fused_mirrored(lib, args, n, stream, nullptr);
 }
 
 // ---- RunningNorm ---------------------------------------------------------------------------

@@ -22,7 +22,7 @@ from __future__ import annotations
 import ctypes as C
 import random
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import numpy as np
 import torch

@@ -29,6 +29,7 @@ OPT_FORCE_GENERIC_STEP = 1
 OPT_STEP_EPB = 2
 OPT_STEP_PDL = 3
 OPT_TEST_SPEC_FAULT = 4
+OPT_MULTI_GROUPS = 5
 
 STATE_INIT_START = 0
 STATE_INIT_RANDOM = 1

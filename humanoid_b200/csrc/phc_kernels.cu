@@ -1867,6 +1867,264 @@ __global__ void __launch_bounds__(MULTI_EPB* J24, 5) step_multi_kernel(const Ste
 }
 
 // ---------------------------------------------------------------------------------------
+// K6-multi2: K6-multi with TWO thread groups per block.  Group g (96 threads = 4 envs x 24 bodies)
+// owns the queries q = g, g+2, g+4, .. and the frame half g, so consecutive queries of an env are
+// worked on at the same time: at small N (config 5 on 8 GPUs: 2048 envs per GPU) a block of K6-multi is
+// one warp-serial chain of ~450 dependent instructions per query with 10 warps per SM; here the chain
+// per query pair is the same length and the SM holds twice the warps.  Each group synchronises on its
+// own named barrier; the groups only meet at the start (sim rows, heading) and never wait for each
+// other.  A half is refilled (query q+2) right after its group consumed it, while the group's staged
+// rows leave with their bulk stores.
+// ---------------------------------------------------------------------------------------
+constexpr int STAGE0_STRIDE = 580;  // group 0 stages task blocks only: 576 + 2 shift, rounded to 16 B
+
+struct Multi2Smem {
+  float sim[MULTI_EPB * ROW13];
+  float frames[MULTI_EPB][4][FRAME_FLOATS];  // [env][group*2 + row][312]
+  float stage1[MULTI_EPB][STAGE_STRIDE];     // group 1: q = 1 stages self obs + first task block
+  float stage0[MULTI_EPB][STAGE0_STRIDE];    // group 0: q >= 2
+  float part[6][MULTI_EPB][J24];
+  unsigned long long bar[2];  // frames of group g
+  unsigned long long bar_sim;
+  int64_t row0[PHC_MAX_TIME_STEPS + 1][MULTI_EPB];
+  int two[PHC_MAX_TIME_STEPS + 1][MULTI_EPB];
+  float bl[PHC_MAX_TIME_STEPS + 1][MULTI_EPB];
+  float goff[MULTI_EPB][4];
+  float hz[MULTI_EPB], hw[MULTI_EPB];
+  int prog[MULTI_EPB], pass[MULTI_EPB], fallen[MULTI_EPB];
+};
+
+__device__ __forceinline__ void group_sync(int g) {  // named barrier 1 + g over the group's 96 threads
+  if (g) asm volatile("bar.sync 2, %0;" ::"r"(MULTI_EPB * J24) : "memory");
+  else asm volatile("bar.sync 1, %0;" ::"r"(MULTI_EPB * J24) : "memory");
+}
+
+__global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(const StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Multi2Smem& S = *reinterpret_cast<Multi2Smem*>(smem_raw);
+  constexpr int EPB = MULTI_EPB, GT = EPB * J24;
+  const int tid = threadIdx.x;
+  const int g = tid / GT, lt = tid - g * GT;  // group, thread within the group
+  const int64_t env0 = (int64_t)blockIdx.x * EPB;
+  const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
+  const int T = p.T;
+  const int W = SELF_DIM + TASK_DIM * T;
+
+  // frames of query q for env le -> the half of group q & 1
+  auto issue_frames = [&](int le, int q) {
+    const uint32_t bytes = (uint32_t)(1 + S.two[q][le]) * (uint32_t)(FRAME_FLOATS * 4);
+    mbar_expect_tx(&S.bar[q & 1], bytes);
+    bulk_g2s(&S.frames[le][(q & 1) * 2][0], p.L.packed + S.row0[q][le] * FRAME_FLOATS, bytes, &S.bar[q & 1]);
+  };
+
+  // ---- phase 0 (whole block) ----------------------------------------------------------------
+  if (tid < 32) {
+    if (tid == 0) {
+      mbar_init(&S.bar[0], 1);
+      mbar_init(&S.bar[1], 1);
+      mbar_init(&S.bar_sim, 1);
+    }
+    __syncwarp();
+    for (int pair = tid; pair < nvalid * (T + 1); pair += 32) {
+      const int le = pair / (T + 1), q = pair - le * (T + 1);
+      const int64_t env = env0 + le;
+      int prog = (int)p.progress[env];
+      if (p.advance) prog = (int)(int16_t)(prog + 1);
+      const float t = (float)(int16_t)(prog + q) * p.dt + p.start[env] + p.start_off[env];
+      const int64_t id = p.ids[env];
+      const float len = p.L.len[id];
+      int i0, i1;
+      float bl;
+      calc_frame_blend32(t, len, (int)p.L.nf[id], p.L.mdt[id], i0, i1, bl);
+      S.row0[q][le] = p.L.starts[id] + i0;
+      S.two[q][le] = i1 - i0;
+      S.bl[q][le] = bl;
+      if (q == 0) {
+        S.prog[le] = prog;
+        S.pass[le] = t >= len;  // _compute_reset, humanoid_phc.py:1317
+        S.fallen[le] = 0;
+        S.goff[le][0] = p.goff ? p.goff[env * 3 + 0] : 0.0f;
+        S.goff[le][1] = p.goff ? p.goff[env * 3 + 1] : 0.0f;
+        S.goff[le][2] = p.goff ? p.goff[env * 3 + 2] : 0.0f;
+      }
+    }
+    __syncwarp();
+    // progress is written only now: a lane's later (env, q) pair must still read the old value
+    if (tid < nvalid && p.advance) p.progress[env0 + tid] = (int16_t)S.prog[tid];
+    if (tid < nvalid) {
+      mbar_expect_tx(&S.bar_sim, ROW13 * 4);
+      bulk_g2s(S.sim + tid * ROW13, p.body.pos.ptr + (env0 + tid) * p.body.pos.stride_env, ROW13 * 4, &S.bar_sim);
+      issue_frames(tid, 0);
+      issue_frames(tid, 1);
+    }
+    __syncwarp();
+    if (tid == 0) {
+      mbar_arrive(&S.bar_sim);
+      mbar_arrive(&S.bar[0]);
+      mbar_arrive(&S.bar[1]);
+    }
+  } else if (tid >= 32 && tid < 32 + nvalid) {  // warp 1: heading quaternions from global memory
+    const int le = tid - 32;
+    const float* rq = p.body.pos.ptr + (env0 + le) * p.body.pos.stride_env + 3;
+    const Heading h0 = heading_quat_inv(Quat{rq[0], rq[1], rq[2], rq[3]});  // upright (common.py:42-44)
+    S.hz[le] = h0.z;
+    S.hw[le] = h0.w;
+  }
+  __syncthreads();  // the only block-wide barrier
+
+  const int e = lt / J24, b = lt % J24;
+  const bool valid = e < nvalid;
+  const int64_t env = env0 + e;
+  const Heading hi = {S.hz[valid ? e : 0], S.hw[valid ? e : 0]};
+  const HeadingRot hr = heading_rot(hi);
+  mbar_wait(&S.bar_sim, 0u);  // single phase: both groups read the sim rows
+  Vec3 pos = {}, vel = {}, ang = {}, root_pos = {};
+  Quat rot = {};
+  if (valid) {
+    const float* d = S.sim + e * ROW13 + b * 13;
+    pos = {d[0], d[1], d[2]};
+    rot = {d[3], d[4], d[5], d[6]};
+    vel = {d[7], d[8], d[9]};
+    ang = {d[10], d[11], d[12]};
+    root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
+  }
+  float* const stage_base = g ? &S.stage1[0][0] : &S.stage0[0][0];
+  const int stage_stride = g ? STAGE_STRIDE : STAGE0_STRIDE;
+
+  for (int q = g, it = 0; q <= T; q += 2, ++it) {
+    mbar_wait(&S.bar[g], (uint32_t)(it & 1));
+    float* dst = nullptr;  // this env's segment of obs_buf for query q
+    int seg = 0, shift = 0;
+    float* row = nullptr;
+    if (valid) {
+      const float* f0 = &S.frames[e][g * 2][0];
+      const RefBody r = blend_ref2(f0, f0 + S.two[q][e] * FRAME_FLOATS, S.bl[q][e], S.goff[e], b);
+      if (q == 0) {
+        float sp, sr, sv, sa;
+        reward_partials(pos, rot, vel, ang, r, sp, sr, sv, sa);
+        S.part[0][e][b] = sp;
+        S.part[1][e][b] = sr;
+        S.part[2][e][b] = sv;
+        S.part[3][e][b] = sa;
+        const float dist = norm3(pos - r.pos);  // common.py:343/348
+        S.part[4][e][b] = dist;
+        if (!p.use_mean && (p.reset_mask >> b & 1u) && dist > p.term_dist[b]) S.fallen[e] = 1;
+        if (p.dof_force) S.part[5][e][b] = power_partial(p, env, b);
+      } else {
+        const int64_t c_off = q == 1 ? 0 : SELF_DIM + (int64_t)TASK_DIM * (q - 1);
+        seg = q == 1 ? STAGE_FLOATS : TASK_DIM;
+        dst = p.obs + env * p.obs_stride + c_off;
+        shift = ((uintptr_t)dst & 15) ? 2 : 0;  // 8-B aligned rows: stage shifted so the bulk part is 16-B aligned
+        row = stage_base + e * stage_stride + shift;
+        float* tk = row;
+        if (q == 1) {  // self obs, common.py:23-103 (default flags)
+          if (b == 0)
+            row[0] = root_pos.z;
+          else
+            st3(row + 1 + (b - 1) * 3, heading_rotate(hr, pos - root_pos));
+          float t6[6];
+          quat_tan_norm(heading_mul_left(hi, rot), t6);
+          st6_shared(row + 70 + b * 6, t6);
+          st3(row + 214 + b * 3, heading_rotate(hr, vel));
+          st3(row + 286 + b * 3, heading_rotate(hr, ang));
+          tk = row + SELF_DIM;
+        }
+        TaskObs o;  // task obs v6 block of future step q, common.py:106-176
+        task_obs_body(hi, hr, root_pos, pos, rot, vel, ang, r, true, o);
+        st3(tk + b * 3, o.d_pos);
+        st6_shared(tk + 72 + b * 6, o.d_rot);
+        st3(tk + 216 + b * 3, o.d_vel);
+        st3(tk + 288 + b * 3, o.d_ang);
+        st3(tk + 360 + b * 3, o.l_pos);
+        st6_shared(tk + 432 + b * 6, o.l_rot);
+      }
+    }
+    fence_proxy_async();  // stage writes -> bulk store; frame reads -> the copy that refills the half
+    group_sync(g);        // A: the group's half consumed, its stage complete
+
+    if (q + 2 <= T && lt < 32) {  // refill the half with query q + 2
+      if (lt < nvalid) issue_frames(lt, q + 2);
+      __syncwarp();
+      if (lt == 0) mbar_arrive(&S.bar[g]);
+    }
+    if (q >= 1) {
+      float* srow = stage_base + e * stage_stride;
+      if (valid && b == 0) {  // one bulk store per env: the 16-B aligned middle of the segment
+        const int body4 = (seg - shift) & ~3;  // floats
+        bulk_s2g(dst + shift, srow + 2 * shift, (uint32_t)body4 * 4);
+      }
+      if (valid && shift && b < 2) dst[b] = srow[shift + b];  // leading pair
+      if (valid && b >= 2 && b < 2 + ((seg - shift) & 3)) {   // trailing pair
+        const int c = shift + ((seg - shift) & ~3) + (b - 2);
+        dst[c] = srow[shift + c];
+      }
+      if (p.moments) {
+        const int64_t c_off = q == 1 ? 0 : SELF_DIM + (int64_t)TASK_DIM * (q - 1);
+        const int sl = q == 1 ? STAGE_FLOATS : TASK_DIM;
+        for (int c = lt; c < sl; c += GT) {
+          double s1 = 0.0, s2 = 0.0;
+          for (int ee = 0; ee < nvalid; ++ee) {
+            const float* d2 = p.obs + (env0 + ee) * p.obs_stride + c_off;
+            const double x = (double)stage_base[ee * stage_stride + (((uintptr_t)d2 & 15) ? 2 : 0) + c];
+            s1 += x;
+            s2 += x * x;
+          }
+          double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * W;
+          atomicAdd(mom + c_off + c, s1);
+          atomicAdd(mom + W + c_off + c, s2);
+        }
+      }
+      if (valid && b == 0) bulk_wait_read();
+      group_sync(g);  // B: stage free
+    }
+  }
+
+  // ---- reductions and scalar outputs (first warp of group 0, which owned q = 0) ------------------
+  if (tid < 32) {
+    const int le = tid >> 2, k = tid & 3;
+    const bool act = le < nvalid && tid < 4 * EPB;
+    float term_k = 0.0f;
+    if (act) {
+      const float kk = k == 0 ? p.rwd.k_pos : k == 1 ? p.rwd.k_rot : k == 2 ? p.rwd.k_vel : p.rwd.k_ang_vel;
+      term_k = expf((-kk) * (row_sum24(&S.part[k][le][0]) / 24.0f));  // common.py:298-320
+      p.raw[(env0 + le) * p.raw_stride + k] = term_k;
+    }
+    const int base = tid & ~3;
+    const float t0 = __shfl_sync(0xffffffffu, term_k, base), t1 = __shfl_sync(0xffffffffu, term_k, base + 1);
+    const float t2 = __shfl_sync(0xffffffffu, term_k, base + 2), t3 = __shfl_sync(0xffffffffu, term_k, base + 3);
+    if (act && k == 0) {
+      float r = p.rwd.w_pos * t0 + p.rwd.w_rot * t1 + p.rwd.w_vel * t2 + p.rwd.w_ang_vel * t3;
+      if (p.dof_force) {
+        const float pr = power_reward(p, &S.part[5][le][0], S.prog[le]);
+        r += pr;
+        p.raw[(env0 + le) * p.raw_stride + p.power_col] = pr;
+      }
+      p.rew[env0 + le] = r;
+    }
+    if (act && k == 1) {
+      bool fallen = false;
+      if (p.early) {
+        if (p.use_mean) {
+          float sel[J24];
+          int m = 0;
+#pragma unroll
+          for (int j = 0; j < J24; ++j)
+            if (p.reset_mask >> j & 1u) sel[m++] = S.part[4][le][j];
+          const int first = __ffs(p.reset_mask) - 1;
+          fallen = m > 0 && (row_sum8(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+        } else {
+          fallen = S.fallen[le] != 0;
+        }
+        fallen = fallen && (S.prog[le] > 1);  // common.py:353
+      }
+      p.term[env0 + le] = fallen ? 1 : 0;
+      p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
+    }
+    if (act && k == 2 && p.mpjpe) p.mpjpe[env0 + le] = row_sum24(&S.part[4][le][0]) / 24.0f;  // humanoid_phc.py:167
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // RunningNorm kernels (policies/running_norm.py:15-34)
 // ---------------------------------------------------------------------------------------
 constexpr int MOM_ROWS_PER_BLOCK = 32;
@@ -2306,6 +2564,7 @@ int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_pos, int
 constexpr int STEP_EPB = 8;
 
 static int g_spec_fault = 0;  // PHC_OPT_TEST_SPEC_FAULT
+static int g_multi_groups = 0;  // PHC_OPT_MULTI_GROUPS: 0 = by batch size
 static unsigned long long* g_trace = nullptr;  // phc_set_trace_buffer (profiling only)
 static int64_t g_trace_capacity = 0;
 static int64_t g_trace_launch = 0;
@@ -2530,6 +2789,10 @@ int phc_set_option(int key, int value) {
     case PHC_OPT_TEST_SPEC_FAULT:
       g_spec_fault = value;
       return PHC_OK;
+    case PHC_OPT_MULTI_GROUPS:
+      if (value < 0 || value > 2) return PHC_ERR_SHAPE;
+      g_multi_groups = value;
+      return PHC_OK;
     default:
       return PHC_ERR_UNSUPPORTED;
   }
@@ -2574,7 +2837,17 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
   // T > 1 on the AoS tensor + packed table: the pipelined TMA kernel
   const bool multi = !g_force_generic && p.T > 1 && p.aos && p.L.packed && p.obs_vec2 && !p.obs_norm &&
                      !(args->flags & PHC_STEP_MAPPED_HOST_IO);
-  static bool attr_multi[64] = {};
+  static bool attr_multi[64] = {}, attr_multi2[64] = {};
+  // two query groups per block pay off while a step is latency-bound (measured: 2048 / 4096 envs +8 %, 16384 envs -7 %)
+  const int multi_groups = g_multi_groups ? g_multi_groups : (p.n <= 6144 ? 2 : 1);
+  if (multi && multi_groups == 2) {
+    if (!attr_multi2[dev]) {
+      PHC_CUDA(cudaFuncSetAttribute(step_multi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Multi2Smem)));
+      attr_multi2[dev] = true;
+    }
+    step_multi2_kernel<<<(unsigned)((p.n + MULTI_EPB - 1) / MULTI_EPB), 2 * MULTI_EPB * J24, sizeof(Multi2Smem), stream>>>(p);
+    return launch_status();
+  }
   if (multi)
     return launch_step(step_multi_kernel, sizeof(MultiSmem), MULTI_EPB, p, stream, &attr_multi[dev], false);
   return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev], false);

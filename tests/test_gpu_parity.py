@@ -816,10 +816,12 @@ def test_rollout_with_device_side_resets_vs_oracle():
         s["state"] = env._rigid_body_state_reshaped.cpu().clone()  # keep both sides on identical inputs
 
 
-@pytest.mark.parametrize("N,T", [(1027, 10), (64, 16), (515, 2)])
-def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T):
-    """T > 1 dispatches to the pipelined TMA kernel; the generic kernel is the same math.  Also a
-    regression test: the clock must be advanced only after every query lane has read it."""
+@pytest.mark.parametrize("groups", [2, 1], ids=["two_groups", "one_group"])
+@pytest.mark.parametrize("N,T", [(1027, 10), (64, 16), (515, 2), (2050, 3), (9, 5)])
+def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T, groups):
+    """T > 1 dispatches to the pipelined TMA kernels (two query groups per block by default, one as the cross-check);
+    the generic kernel is the same math.  Also a regression test: the clock must be advanced only after every query
+    lane has read it."""
     from humanoid_b200 import HumanoidPHC, _cabi
 
     lib_data, clock, state = _gpu_case(N, 64, 210, max_frames=60, max_progress=40)
@@ -827,6 +829,7 @@ def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T):
     capi = _cabi.load()
     outs = []
     try:
+        assert capi.phc_set_option(_cabi.OPT_MULTI_GROUPS, groups) == 0
         for generic in (1, 0):
             assert capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, generic) == 0
             env = HumanoidPHC(lib, N, device=DEV, time_steps=T, obs_moments=True, use_power_reward=True)
@@ -840,6 +843,7 @@ def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T):
             outs.append(env)
     finally:
         capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+        capi.phc_set_option(_cabi.OPT_MULTI_GROUPS, 0)
     g, f = outs
     assert torch.equal(f.obs_buf, g.obs_buf)
     assert torch.equal(f.rew_buf, g.rew_buf) and torch.equal(f.reward_raw, g.reward_raw)

@@ -459,7 +459,7 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(T), "peak_source": peak_src, "bytes_per_env_step": bytes_step,
                      "kernel": "phc::step_fast_kernel<4,8,false>" if T == 1
-                     else ("phc::step_multi2_kernel" if N <= 6144 else "phc::step_multi_kernel"), "launch_ms": ms_per_step},
+                     else "phc::step_multi2_kernel", "launch_ms": ms_per_step},
         "rms": {"what": f"RunningNorm.update over a {roll}-step rollout: fp64 column moments + "
                         + (f"one fused launch per rank (all-reduce of {(2 * obs_dim + 1) * 8} B over NVLink peer memory + blend)"
                            if fused_on else f"NCCL all-reduce of {(2 * obs_dim + 1) * 8} B + blend" if world > 1

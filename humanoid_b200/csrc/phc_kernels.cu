@@ -1873,8 +1873,8 @@ __global__ void __launch_bounds__(MULTI_EPB* J24, 5) step_multi_kernel(const Ste
 // one warp-serial chain of ~450 dependent instructions per query with 10 warps per SM; here the chain
 // per query pair is the same length and the SM holds twice the warps.  Each group synchronises on its
 // own named barrier; the groups only meet at the start (sim rows, heading) and never wait for each
-// other.  A half is refilled (query q+2) right after its group consumed it, while the group's staged
-// rows leave with their bulk stores.
+// other.  A half is refilled (query q+2) as soon as every thread of its group holds the blended reference
+// body, so the copy flies while the observation block is computed, staged and stored.
 // ---------------------------------------------------------------------------------------
 constexpr int STAGE0_STRIDE = 580;  // group 0 stages task blocks only: 576 + 2 shift, rounded to 16 B
 
@@ -1918,14 +1918,13 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
   };
 
   // ---- phase 0 (whole block) ----------------------------------------------------------------
-  if (tid < 32) {
+  if (tid < 64) {  // two warps share the (env, query) pairs: one round of dependent clip-metadata loads for T <= 15
     if (tid == 0) {
       mbar_init(&S.bar[0], 1);
       mbar_init(&S.bar[1], 1);
       mbar_init(&S.bar_sim, 1);
     }
-    __syncwarp();
-    for (int pair = tid; pair < nvalid * (T + 1); pair += 32) {
+    for (int pair = tid; pair < nvalid * (T + 1); pair += 64) {
       const int le = pair / (T + 1), q = pair - le * (T + 1);
       const int64_t env = env0 + le;
       int prog = (int)p.progress[env];
@@ -1948,7 +1947,7 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
         S.goff[le][2] = p.goff ? p.goff[env * 3 + 2] : 0.0f;
       }
     }
-    __syncwarp();
+    asm volatile("bar.sync 3, 64;" ::: "memory");  // both warps have read the clock and filled the tables
     // progress is written only now: a lane's later (env, q) pair must still read the old value
     if (tid < nvalid && p.advance) p.progress[env0 + tid] = (int16_t)S.prog[tid];
     if (tid < nvalid) {
@@ -1957,14 +1956,14 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
       issue_frames(tid, 0);
       issue_frames(tid, 1);
     }
-    __syncwarp();
+    if (tid < 32) __syncwarp();
     if (tid == 0) {
       mbar_arrive(&S.bar_sim);
       mbar_arrive(&S.bar[0]);
       mbar_arrive(&S.bar[1]);
     }
-  } else if (tid >= 32 && tid < 32 + nvalid) {  // warp 1: heading quaternions from global memory
-    const int le = tid - 32;
+  } else if (tid >= 64 && tid < 64 + nvalid) {  // warp 2: heading quaternions from global memory
+    const int le = tid - 64;
     const float* rq = p.body.pos.ptr + (env0 + le) * p.body.pos.stride_env + 3;
     const Heading h0 = heading_quat_inv(Quat{rq[0], rq[1], rq[2], rq[3]});  // upright (common.py:42-44)
     S.hz[le] = h0.z;
@@ -1996,9 +1995,22 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
     float* dst = nullptr;  // this env's segment of obs_buf for query q
     int seg = 0, shift = 0;
     float* row = nullptr;
+    RefBody r = {};
     if (valid) {
       const float* f0 = &S.frames[e][g * 2][0];
-      const RefBody r = blend_ref2(f0, f0 + S.two[q][e] * FRAME_FLOATS, S.bl[q][e], S.goff[e], b);
+      r = blend_ref2(f0, f0 + S.two[q][e] * FRAME_FLOATS, S.bl[q][e], S.goff[e], b);
+    }
+    // the half is dead once every thread of the group holds its reference body: refill it with query q + 2 now, so
+    // the copy flies while the observation block is computed, staged and stored
+    if (valid && b == 0) bulk_wait_read();  // the previous query's bulk store has read the stage: it may be rewritten
+    fence_proxy_async();                    // frame reads -> the copy that refills the half
+    group_sync(g);                          // R
+    if (q + 2 <= T && lt < 32) {
+      if (lt < nvalid) issue_frames(lt, q + 2);
+      __syncwarp();
+      if (lt == 0) mbar_arrive(&S.bar[g]);
+    }
+    if (valid) {
       if (q == 0) {
         float sp, sr, sv, sa;
         reward_partials(pos, rot, vel, ang, r, sp, sr, sv, sa);
@@ -2039,15 +2051,9 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
         st6_shared(tk + 432 + b * 6, o.l_rot);
       }
     }
-    fence_proxy_async();  // stage writes -> bulk store; frame reads -> the copy that refills the half
-    group_sync(g);        // A: the group's half consumed, its stage complete
-
-    if (q + 2 <= T && lt < 32) {  // refill the half with query q + 2
-      if (lt < nvalid) issue_frames(lt, q + 2);
-      __syncwarp();
-      if (lt == 0) mbar_arrive(&S.bar[g]);
-    }
     if (q >= 1) {
+      fence_proxy_async();  // stage writes -> bulk store
+      group_sync(g);        // A: the group's stage complete
       float* srow = stage_base + e * stage_stride;
       if (valid && b == 0) {  // one bulk store per env: the 16-B aligned middle of the segment
         const int body4 = (seg - shift) & ~3;  // floats
@@ -2074,10 +2080,9 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
           atomicAdd(mom + W + c_off + c, s2);
         }
       }
-      if (valid && b == 0) bulk_wait_read();
-      group_sync(g);  // B: stage free
     }
   }
+  if (valid && b == 0) bulk_wait_read();  // shared memory must outlive the last store's reads
 
   // ---- reductions and scalar outputs (first warp of group 0, which owned q = 0) ------------------
   if (tid < 32) {
@@ -2564,7 +2569,7 @@ int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_pos, int
 constexpr int STEP_EPB = 8;
 
 static int g_spec_fault = 0;  // PHC_OPT_TEST_SPEC_FAULT
-static int g_multi_groups = 0;  // PHC_OPT_MULTI_GROUPS: 0 = by batch size
+static int g_multi_groups = 0;  // PHC_OPT_MULTI_GROUPS: 0 = default (2)
 static unsigned long long* g_trace = nullptr;  // phc_set_trace_buffer (profiling only)
 static int64_t g_trace_capacity = 0;
 static int64_t g_trace_launch = 0;
@@ -2838,8 +2843,8 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
   const bool multi = !g_force_generic && p.T > 1 && p.aos && p.L.packed && p.obs_vec2 && !p.obs_norm &&
                      !(args->flags & PHC_STEP_MAPPED_HOST_IO);
   static bool attr_multi[64] = {}, attr_multi2[64] = {};
-  // two query groups per block pay off while a step is latency-bound (measured: 2048 / 4096 envs +8 %, 16384 envs -7 %)
-  const int multi_groups = g_multi_groups ? g_multi_groups : (p.n <= 6144 ? 2 : 1);
+  // two query groups per block (measured: 2048 envs 21.6 -> 18.3 us, 4096 envs 43.7 -> 37.2, 16384 envs 128.2 -> 127.5)
+  const int multi_groups = g_multi_groups ? g_multi_groups : 2;
   if (multi && multi_groups == 2) {
     if (!attr_multi2[dev]) {
       PHC_CUDA(cudaFuncSetAttribute(step_multi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Multi2Smem)));

@@ -319,9 +319,8 @@ PHC_API int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* args, int64_t 
 #define PHC_OPT_TEST_SPEC_FAULT 4     /* test hook, bit mask: perturb the clock the fast kernel speculated on
                                         (1 progress-1, 2 start time, 4 progress-2, 8 motion id) so the
                                         validation / redo paths run; results must not change */
-#define PHC_OPT_MULTI_GROUPS 5        /* thread groups per block of the T > 1 kernel: 2 (queries of an env are worked on in pairs:
-                                        faster while the step is latency-bound), 1 (the single-group pipeline: faster at
-                                        16384 envs), 0 (default) = 2 up to 6144 envs per launch, else 1 */
+#define PHC_OPT_MULTI_GROUPS 5        /* thread groups per block of the T > 1 kernel: 2 (default; also value 0): the queries of an
+                                        env are worked on in pairs; 1: the single-group pipeline, kept as the cross-check */
 PHC_API int phc_set_option(int key, int value);
 /* Profiling aid: when a device buffer of capacity_warps x 8 uint64 is set, every warp of the
  * fast step kernel (EPB 4: 3 warps per block) stamps %globaltimer (ns) at its phase boundaries:

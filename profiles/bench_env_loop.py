@@ -1,0 +1,64 @@
+"""Everything the env does around the physics step, through the shim's public API, in a CUDA graph:
+PHCPufferEnv.step = clamp actions -> HumanoidPHC.step (fused step + power reward [+ AMP buffers]) -> reward clone ->
+episode bookkeeping -> device-side reset of the flagged envs (sample start time, pose, clock, masked obs pass).
+
+    python profiles/bench_env_loop.py [num_envs]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from humanoid_b200 import HumanoidPHC, MotionLib, PHCPufferEnv, synth  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+dev = torch.device("cuda", 0)
+lib_data = synth.make_motion_lib(N, 60, 300, (30,), seed=1234, device=dev)
+lib = MotionLib(lib_data, device=dev)
+clock = synth.make_clock(lib_data, N, seed=1235, max_progress=30)
+K = 128
+print(f"# Whole env step through the shim at N = {N} (us per step, {K}-step CUDA graph, best of 5)\n")
+print("| variant | us / step | env-steps/s |\n|---|---|---|")
+for name, kw in (("fused step only (HumanoidPHC.post_physics_step)", None),
+                 ("PHCPufferEnv.step: power reward, episode bookkeeping, device-side resets", dict(use_power_reward=True)),
+                 ("the same + AMP observation buffers (10-step history)", dict(use_power_reward=True, use_amp_obs=True))):
+    env = HumanoidPHC(lib, N, device=dev, **(kw or {}))
+    ref = lib.get_motion_state(clock.sampled_motion_ids, synth.reward_time(clock, extra_steps=1), clock.global_offset)
+    env.set_sim_state(synth.make_sim_state(ref, seed=1236))
+    env.set_clock(clock)
+    penv = PHCPufferEnv(env, log_interval=1 << 30, use_amp_obs=bool(kw and kw.get("use_amp_obs")))
+    actions = torch.rand(N, 69, device=dev) * 2.4 - 1.2
+    phase = torch.rand(N, device=dev)
+    state0 = env._rigid_body_state_reshaped.clone()
+
+    def one():
+        if kw is None:
+            env.post_physics_step(True)
+        else:
+            env._rigid_body_state_reshaped.copy_(state0)  # stands in for the physics write-back
+            penv.step(actions, phase)
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(K):
+                one()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(s):
+            e0.record(s)
+            g.replay()
+            e1.record(s)
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / K * 1e3)
+    print(f"| {name} | {best:.2f} | {N / best * 1e6:.3g} |", flush=True)

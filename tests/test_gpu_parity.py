@@ -924,7 +924,7 @@ def test_episode_bookkeeping_vs_reference_recording(golden):
     replay_episode_golden(golden("episode"), lambda n, c: _episode_state(n, c, DEV), _episode_update_cabi, read=lambda t: t.cpu())
 
 
-@pytest.mark.parametrize("N", [1, 257, 70001, 300000])
+@pytest.mark.parametrize("N", [1, 257, 4096, 8192, 8193, 70001, 300000])  # one-block path up to 8192 envs, tickets beyond
 def test_episode_bookkeeping_vs_oracle_many_blocks(N):
     g = torch.Generator().manual_seed(N)
     want = _episode_state(N, 5, "cpu")

@@ -1,5 +1,9 @@
+"""Each piece of PHCPufferEnv.step alone in a 64-launch CUDA graph (N = 4096): where the env-side loop spends its time.
+
+    python profiles/bench_env_breakdown.py
+"""
 import os, sys
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from humanoid_b200 import HumanoidPHC, MotionLib, PHCPufferEnv, synth
 N=4096; dev=torch.device("cuda",0)

@@ -1496,3 +1496,47 @@ def test_build_and_reset_kernels_stay_inside_their_output_buffers(golden):
     torch.cuda.synchronize()
     for name, (raw, lead, nbytes) in guards.items():
         assert bool((raw[:lead] == 0xA5).all()) and bool((raw[lead + nbytes :] == 0xA5).all()), name
+
+
+# ---------------------------------------------------------------------------------------
+# randomised differential test: many small seeded workloads with adversarial clocks against the oracle
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(16))
+def test_fused_step_randomised_differential(seed):
+    """Random batch size / clip count / fps mix / id regime / time alignment / rotation regime per seed, clocks that run
+    past the end of short clips (pass_time) and start before 0, T in {1, 2, 5}, every step kernel (TMA kernels by
+    default, the generic kernel for odd seeds): flags and progress exact, floats within the 1e-5 bar, two steps deep."""
+    from humanoid_b200 import _cabi
+
+    rng = torch.Generator().manual_seed(1000 + seed)
+    r = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=rng))  # noqa: E731
+    N, M = r(1, 333), r(1, 24)
+    T = (1, 1, 2, 5)[seed % 4]
+    kw = dict(num_envs=N, num_motions=M, seed=2000 + seed, min_frames=r(2, 12), max_frames=r(13, 80),
+              fps_choices=((30,), (30, 60), (30, 60, 120))[seed % 3], ids=("mod", "random")[seed % 2],
+              aligned=bool(seed % 3), rot_regime=("mocap", "random")[(seed // 2) % 2], max_progress=r(0, 60))  # fmt: skip
+    lib_data, clock, state = make_case_cpu(**kw)
+    # adversarial clocks: some envs start before the clip (negative time), some far past its end
+    n_adv = max(1, N // 7)
+    idx = torch.randperm(N, generator=rng)[:n_adv]
+    clock.motion_start_times_offset[idx[: n_adv // 2 + 1]] = -1.5
+    clock.motion_start_times[idx[n_adv // 2 :]] += 40.0
+    capi = _cabi.load()
+    env = env_from(lib_data, clock, state, time_steps=T)
+    prog = clock.progress_buf.clone()
+    lib_o = O.OracleMotionLib(lib_data)
+    try:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, seed % 2)
+        for step in range(2):
+            want = O.step(lib_o, state, prog, clock.motion_start_times, clock.motion_start_times_offset, clock.global_offset,
+                          clock.sampled_motion_ids, torch.full((24,), 0.25), synth.SIM_DT, time_steps=T)  # fmt: skip
+            env.step()
+            what = f"seed {seed} step {step} {kw} T={T}"
+            assert_equal_exact(env.progress_buf, prog, what + ": progress")
+            assert_equal_exact(env.reset_buf, want[3], what + ": reset")
+            assert_equal_exact(env._terminate_buf, want[4], what + ": terminated")
+            assert_close(env.obs_buf, want[0], what=what + ": obs", **OBS_TOL)
+            assert_close(env.rew_buf, want[1], what=what + ": reward", **OBS_TOL)
+            assert_close(env.reward_raw[:, :4], want[2], what=what + ": reward_raw", **OBS_TOL)
+    finally:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)

@@ -128,6 +128,14 @@ class PhcStepArgs(C.Structure):
         ("norm_clip", C.c_float),
         ("mpjpe", C.c_void_p),
         ("obs_moments_buckets", C.c_int32),
+        ("ep_terminals", C.c_void_p),
+        ("ep_truncations", C.c_void_p),
+        ("ep_masks", C.c_void_p),
+        ("ep_returns", C.c_void_p),
+        ("ep_lengths", C.c_void_p),
+        ("ep_sums", C.c_void_p),
+        ("ep_buckets", C.c_int32),
+        ("ep_raw_cols", C.c_int32),
     ]
 
 
@@ -210,6 +218,7 @@ class PhcHostStepArgs(C.Structure):
 
 
 BUILD_FILTER_RADIUS = 8
+EPISODE_SUM_COLS = 12
 PEER_MAX_WORLD = 16
 PEER_HANDLE_BYTES = 64
 PEER_TIMEOUT = -7
@@ -298,6 +307,7 @@ SIGNATURES = {
         [C.c_void_p, C.POINTER(PhcAmpEnvArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p],
     ),
     "phc_motion_build": (C.c_int, [C.POINTER(PhcBuildArgs), C.c_void_p]),
+    "phc_episode_fold": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "phc_obs_moments_fold": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "phc_peer_reduce_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
     "phc_peer_reduce_handle": (C.c_int, [C.c_void_p, C.c_void_p]),

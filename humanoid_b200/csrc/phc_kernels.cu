@@ -788,6 +788,8 @@ constexpr int FRAME_FLOATS = J24 * 13;       // pos 72 | rot 96 | vel 72 | ang 7
 constexpr int FRAME_F4 = FRAME_FLOATS / 4;   // 78
 constexpr int STAGE_FLOATS = SELF_DIM + TASK_DIM;  // 934
 
+constexpr int EP_SUM_COLS = 12;  // 4 episode sums + up to 8 reward_raw column sums (PHC_EPISODE_SUM_COLS)
+
 struct StepParams {
   LibDev L;
   PhcBodyState body;
@@ -811,6 +813,12 @@ struct StepParams {
   uint8_t* term;
   double* moments;
   int moment_buckets;  // >= 1: moments is [buckets][2W]; block b adds into bucket b % buckets
+  // episode bookkeeping of the pufferlib wrapper fused into the step (clean_pufferl/env.py:121-159), off when ep_returns is NULL
+  uint8_t *ep_terminals, *ep_truncations, *ep_masks;
+  float* ep_returns;
+  int32_t* ep_lengths;
+  double* ep_sums;  // [ep_buckets][EP_SUM_COLS]: {episodes, sum of returns, sum of lengths, truncations, sum of reward_raw[:, c]}
+  int ep_buckets, ep_raw_cols;
   float* mpjpe;     // NULL, or [n]: mean over the 24 bodies of |body_pos - ref_body_pos| (extras["mpjpe"])
   float* obs_norm;  // NULL, or the normalised copy of the obs rows (RunningNorm.forward)
   int64_t obs_norm_stride;
@@ -1214,7 +1222,8 @@ __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, 
 }
 
 // NORM: compiled with the RunningNorm.forward epilogue (obs_norm set); the plain instantiation carries none of it
-template <int EPB, int MINB, bool NORM = false>
+// EP: compiled with the wrapper's episode bookkeeping in the reduction warp (ep_returns set)
+template <int EPB, int MINB, bool NORM = false, bool EP = false>
 __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem<EPB>& S = *reinterpret_cast<FastSmem<EPB>*>(smem_raw);
@@ -1575,10 +1584,12 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     const int base = tid & ~3;
     const float t0 = __shfl_sync(0xffffffffu, term_k, base), t1 = __shfl_sync(0xffffffffu, term_k, base + 1);
     const float t2 = __shfl_sync(0xffffffffu, term_k, base + 2), t3 = __shfl_sync(0xffffffffu, term_k, base + 3);
+    float r = 0.0f, pr = 0.0f;  // lanes k == 0: the env's reward and its power term
+    int flags = 0;              // lanes k == 1: bit 0 = reset, bit 1 = terminated
     if (act && k == 0) {
-      float r = p.rwd.w_pos * t0 + p.rwd.w_rot * t1 + p.rwd.w_vel * t2 + p.rwd.w_ang_vel * t3;
+      r = p.rwd.w_pos * t0 + p.rwd.w_rot * t1 + p.rwd.w_vel * t2 + p.rwd.w_ang_vel * t3;
       if (p.dof_force) {
-        const float pr = power_reward(p, &S.part[5][le][0], S.prog[le]);
+        pr = power_reward(p, &S.part[5][le][0], S.prog[le]);
         r += pr;  // rew_buf[:] += power_reward (humanoid_phc.py:1304)
         p.raw[(env0 + le) * p.raw_stride + p.power_col] = pr;
       }
@@ -1602,8 +1613,53 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       }
       p.term[env0 + le] = fallen ? 1 : 0;
       p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
+      flags = (S.pass[le] || fallen ? 1 : 0) | (fallen ? 2 : 0);
     }
     if (act && k == 2 && p.mpjpe) p.mpjpe[env0 + le] = row_sum24(&S.part[4][le][0]) / 24.0f;  // humanoid_phc.py:167
+    if constexpr (EP) {
+      // PHCPufferEnv.step's bookkeeping (clean_pufferl/env.py:121-159) for the block's envs, on the lanes that hold the
+      // reward; the block's sums go to one of ep_buckets accumulators (fp64 atomics on one address serialise)
+      flags = __shfl_sync(0xffffffffu, flags, base + 1);
+      double v[EP_SUM_COLS];
+#pragma unroll
+      for (int i = 0; i < EP_SUM_COLS; ++i) v[i] = 0.0;
+      if (act && k == 0) {
+        const int64_t e = env0 + le;
+        const bool rs = flags & 1, tm = (flags & 2) != 0, tr = rs && !tm;
+        p.ep_terminals[e] = tm ? 1 : 0;
+        p.ep_truncations[e] = tr ? 1 : 0;
+        p.ep_masks[e] = tr ? 0 : 1;
+        float ret = p.ep_returns[e];
+        int32_t len = p.ep_lengths[e];
+        if (rs) {
+          v[0] = 1.0;
+          v[1] = (double)ret;
+          v[2] = (double)len;
+          v[3] = tr ? 1.0 : 0.0;
+          ret = 0.0f;
+          len = 0;
+        }
+        p.ep_returns[e] = ret + r;
+        p.ep_lengths[e] = len + 1;
+        v[4] = (double)t0, v[5] = (double)t1, v[6] = (double)t2, v[7] = (double)t3;
+        if (p.dof_force) {
+#pragma unroll
+          for (int i = 8; i < EP_SUM_COLS; ++i)
+            if (i == 4 + p.power_col) v[i] = (double)pr;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < EP_SUM_COLS; ++i) {  // the four k == 0 lanes (0, 4, 8, 12) -> lane 0
+        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 4);
+        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 8);
+      }
+      if (tid == 0) {
+        double* acc = p.ep_sums + (int64_t)(blockIdx.x % p.ep_buckets) * EP_SUM_COLS;
+#pragma unroll
+        for (int i = 0; i < EP_SUM_COLS; ++i)
+          if (i < 4 + p.ep_raw_cols && v[i] != 0.0) atomicAdd(acc + i, v[i]);
+      }
+    }
   }
 
   if (NORM && p.obs_norm && !norm_inplace && !norm16_staged) {
@@ -2362,6 +2418,65 @@ __global__ void __launch_bounds__(256) episode_update_kernel(EpisodeParams p) {
   if (threadIdx.x == 32) *reinterpret_cast<unsigned long long*>(&p.ws[12]) = 0ull;
 }
 
+// The same bookkeeping for the step kernels that do not carry it (generic, T > 1): one thread per env after the step,
+// block sums into the bucket of the block.
+__global__ void __launch_bounds__(256) episode_bucket_kernel(StepParams p) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v[EP_SUM_COLS];
+#pragma unroll
+  for (int i = 0; i < EP_SUM_COLS; ++i) v[i] = 0.0;
+  if (e < p.n) {
+    const bool rs = p.reset[e] != 0, tm = p.term[e] != 0, tr = rs && !tm;
+    p.ep_terminals[e] = tm ? 1 : 0;
+    p.ep_truncations[e] = tr ? 1 : 0;
+    p.ep_masks[e] = tr ? 0 : 1;
+    float ret = p.ep_returns[e];
+    int32_t len = p.ep_lengths[e];
+    if (rs) {
+      v[0] = 1.0;
+      v[1] = (double)ret;
+      v[2] = (double)len;
+      v[3] = tr ? 1.0 : 0.0;
+      ret = 0.0f;
+      len = 0;
+    }
+    p.ep_returns[e] = ret + p.rew[e];
+    p.ep_lengths[e] = len + 1;
+#pragma unroll
+    for (int c = 0; c < EP_SUM_COLS - 4; ++c)
+      if (c < p.ep_raw_cols) v[4 + c] = (double)p.raw[e * p.raw_stride + c];
+  }
+  __shared__ double part[8][EP_SUM_COLS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < EP_SUM_COLS; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) part[warp][i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 + p.ep_raw_cols) {
+    double x = 0.0;
+    for (int w = 0; w < 8; ++w) x += part[w][threadIdx.x];
+    if (x != 0.0) atomicAdd(p.ep_sums + (int64_t)(blockIdx.x % p.ep_buckets) * EP_SUM_COLS + threadIdx.x, x);
+  }
+}
+
+// stats[i] += sum_b sums[b][i] (i < 4), raw_rewards[c] += sum_b sums[b][4 + c] / n; the buckets are left zero
+__global__ void episode_fold_kernel(double* __restrict__ sums, int nb, int raw_cols, double n, double* __restrict__ stats,
+                                    float* __restrict__ raw_rewards) {
+  const int i = threadIdx.x;
+  if (i >= 4 + raw_cols) return;
+  double acc = 0.0;
+  for (int b = 0; b < nb; ++b) {
+    acc += sums[b * EP_SUM_COLS + i];
+    sums[b * EP_SUM_COLS + i] = 0.0;
+  }
+  if (i < 4) stats[i] += acc;
+  else raw_rewards[i - 4] += (float)(acc / n);
+}
+
 }  // namespace phc
 
 // =========================================================================================
@@ -2624,6 +2739,18 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.term = a->terminate_buf;
   p.moments = a->obs_moments;
   p.moment_buckets = a->obs_moments_buckets > 1 ? a->obs_moments_buckets : 1;
+  p.ep_terminals = a->ep_terminals;
+  p.ep_truncations = a->ep_truncations;
+  p.ep_masks = a->ep_masks;
+  p.ep_returns = a->ep_returns;
+  p.ep_lengths = a->ep_lengths;
+  p.ep_sums = a->ep_sums;
+  p.ep_buckets = a->ep_buckets;
+  p.ep_raw_cols = a->ep_raw_cols;
+  if (a->ep_returns) {
+    if (!a->ep_terminals || !a->ep_truncations || !a->ep_masks || !a->ep_lengths || !a->ep_sums) return PHC_ERR_NULL;
+    if (a->ep_buckets < 1 || a->ep_buckets > 4096 || a->ep_raw_cols < 0 || a->ep_raw_cols > EP_SUM_COLS - 4) return PHC_ERR_SHAPE;
+  }
   if (a->obs_moments_buckets < 0 || a->obs_moments_buckets > 4096) return PHC_ERR_SHAPE;
   p.mpjpe = a->mpjpe;
   p.obs_norm = a->obs_norm;
@@ -2848,7 +2975,11 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
       first_wave[dev] = sms * (per_sm > 0 ? per_sm : 1);
     }
     p.first_wave_blocks = (g_pdl && !(args->flags & PHC_STEP_MAPPED_HOST_IO)) ? first_wave[dev] : 0;
-    static bool attr_fast4_norm[64] = {};
+    static bool attr_fast4_norm[64] = {}, attr_fast4_ep[64] = {}, attr_fast4_norm_ep[64] = {};
+    if (p.obs_norm && p.ep_returns)
+      return launch_step(step_fast_kernel<4, 8, true, true>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4_norm_ep[dev], g_pdl != 0);
+    if (p.ep_returns)
+      return launch_step(step_fast_kernel<4, 8, false, true>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4_ep[dev], g_pdl != 0);
     if (p.obs_norm)
       return launch_step(step_fast_kernel<4, 8, true>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4_norm[dev], g_pdl != 0);
     return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev], g_pdl != 0);
@@ -2865,11 +2996,17 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
       attr_multi2[dev] = true;
     }
     step_multi2_kernel<<<(unsigned)((p.n + MULTI_EPB - 1) / MULTI_EPB), 2 * MULTI_EPB * J24, sizeof(Multi2Smem), stream>>>(p);
-    return launch_status();
+    rc = launch_status();
+  } else if (multi) {
+    rc = launch_step(step_multi_kernel, sizeof(MultiSmem), MULTI_EPB, p, stream, &attr_multi[dev], false);
+  } else {
+    rc = launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev], false);
   }
-  if (multi)
-    return launch_step(step_multi_kernel, sizeof(MultiSmem), MULTI_EPB, p, stream, &attr_multi[dev], false);
-  return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen[dev], false);
+  if (rc == PHC_OK && p.ep_returns) {  // these kernels do not carry the episode bookkeeping: a second, small launch
+    episode_bucket_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(p);
+    rc = launch_status();
+  }
+  return rc;
 }
 
 extern "C" {
@@ -2934,6 +3071,14 @@ int phc_running_norm_forward(const float* x, int64_t rows, int64_t cols, int64_t
     running_norm_forward_kernel<1><<<grid, 128, 0, stream>>>(x, rows, cols, row_stride, running_mean, running_var, epsilon,
                                                              clip, out, out_stride);
   }
+  return launch_status();
+}
+
+int phc_episode_fold(double* sums, int32_t num_buckets, int32_t raw_cols, int64_t n, double* stats, float* raw_rewards,
+                     phc_stream_t stream) {
+  if (!sums || !stats || (raw_cols > 0 && !raw_rewards)) return PHC_ERR_NULL;
+  if (num_buckets < 1 || raw_cols < 0 || raw_cols > EP_SUM_COLS - 4 || n < 1) return PHC_ERR_SHAPE;
+  episode_fold_kernel<<<1, 32, 0, stream>>>(sums, num_buckets, raw_cols, (double)n, stats, raw_rewards);
   return launch_status();
 }
 

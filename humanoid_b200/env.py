@@ -281,6 +281,12 @@ class HumanoidPHC:
         if self._obs_moment_buckets is not None:
             a.obs_moments = self._obs_moment_buckets.data_ptr()
             a.obs_moments_buckets = self._obs_moment_buckets.shape[0]
+        ep = getattr(self, "_episode_buffers", None)
+        if ep is not None:  # PHCPufferEnv(fused=True): the wrapper's bookkeeping rides in the step (clean_pufferl/env.py:121-159)
+            a.ep_terminals, a.ep_truncations, a.ep_masks = (ep[k].data_ptr() for k in ("terminals", "truncations", "masks"))
+            a.ep_returns, a.ep_lengths = ep["episode_returns"].data_ptr(), ep["episode_lengths"].data_ptr()
+            a.ep_sums, a.ep_buckets = ep["sums"].data_ptr(), ep["sums"].shape[0]
+            a.ep_raw_cols = self.reward_raw.shape[1]
         if self.flag_im_eval:  # extras["mpjpe"] (:159-167), from the distances the reset test computes anyway
             if self._mpjpe is None:
                 self._mpjpe = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
@@ -325,6 +331,12 @@ class HumanoidPHC:
         )  # fmt: skip
         rows, self.obs_moment_rows = self.obs_moment_rows, 0
         return sums, rows
+
+    def set_episode_buffers(self, buffers: Optional[Dict[str, torch.Tensor]]):
+        """Let the step do ``PHCPufferEnv.step``'s per-env episode bookkeeping: ``terminals / truncations / masks`` (bool
+        [N]), ``episode_returns`` (f32 [N]), ``episode_lengths`` (i32 [N]) and ``sums`` (f64 [B, 12] accumulators)."""
+        self._episode_buffers = buffers
+        self._step_args = None
 
     def set_obs_normalizer(self, normalizer, dtype=torch.float32):
         """Fuse ``RunningNorm.forward`` (PHC/policies/running_norm.py:15-20) into the step: every step also

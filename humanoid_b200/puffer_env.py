@@ -24,7 +24,7 @@ from .env import HumanoidPHC
 
 class PHCPufferEnv:
     def __init__(self, env: HumanoidPHC, num_actions: int = 69, clip_actions: bool = True, log_interval: int = 32,
-                 use_amp_obs: bool = False):  # fmt: skip
+                 use_amp_obs: bool = False, fused: bool = False):  # fmt: skip
         self.env = env
         self.clip_actions = clip_actions
         self.log_interval = log_interval
@@ -46,6 +46,24 @@ class PHCPufferEnv:
         self._workspace = torch.zeros(16, dtype=torch.float64, device=dev)
         self.amp_obs = None
         self.tick = 0
+        # fused=True: the bookkeeping below is done by the env's step kernel (PhcStepArgs.ep_*), one launch fewer per
+        # step; the sums collect in 32 accumulators that mean_and_log folds
+        self.fused = bool(fused)
+        self._ep_sums = torch.zeros((32, _cabi.EPISODE_SUM_COLS), dtype=torch.float64, device=dev) if fused else None
+        if fused:
+            env.set_episode_buffers(dict(terminals=self.terminals, truncations=self.truncations, masks=self.masks,
+                                         episode_returns=self.episode_returns, episode_lengths=self.episode_lengths,
+                                         sums=self._ep_sums))  # fmt: skip
+
+    def _fold(self):
+        if self.fused:
+            _cabi.check(
+                _cabi.load().phc_episode_fold(
+                    self._ep_sums.data_ptr(), self._ep_sums.shape[0], self.raw_rewards.shape[0], self.terminals.shape[0],
+                    self._stats.data_ptr(), self.raw_rewards.data_ptr(), _cabi.stream_ptr(self.device),
+                ),
+                "phc_episode_fold",
+            )  # fmt: skip
 
     @property
     def num_agents(self):
@@ -61,6 +79,8 @@ class PHCPufferEnv:
         self.actions[:] = 0
         self.raw_rewards[:] = 0
         self._stats.zero_()
+        if self.fused:
+            self._ep_sums.zero_()
         return self.observations, []
 
     def update_episodes(self, reset: Optional[torch.Tensor] = None, terminate: Optional[torch.Tensor] = None,
@@ -98,7 +118,8 @@ class PHCPufferEnv:
         self.env.step(self.actions)
         self.amp_obs = getattr(self.env, "amp_obs", None) if self.use_amp_obs else None
         rew = self.rewards.clone()
-        self.update_episodes()
+        if not self.fused:
+            self.update_episodes()
         self.env.reset_done(phase_by_env)  # :133-135 without the nonzero() sync
         info = []
         self.tick += 1
@@ -108,6 +129,7 @@ class PHCPufferEnv:
 
     def mean_and_log(self):
         """:191-204 plus the reward terms of :164-176 — the one host read per ``log_interval`` steps."""
+        self._fold()
         stats = self._stats.tolist()
         raw = (self.raw_rewards / self.log_interval).tolist()
         self._stats.zero_()

@@ -212,6 +212,7 @@ PHC_API int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_
                                       device address space: no L2 prefetch, no pre-dependency speculation */
 #define PHC_STEP_OBS_NORM_BF16 2u  /* obs_norm points to bfloat16 rows (the policy's input dtype under autocast): each
                                       normalised fp32 value is rounded to nearest-even; obs_norm_stride counts bf16 elements */
+#define PHC_EPISODE_SUM_COLS 12
 typedef struct PhcStepArgs {
   PhcBodyState body;                     /* sim state views, J must be 24               */
   int16_t* progress_buf;                 /* [n] in/out                  humanoid_phc.py:571 */
@@ -265,6 +266,19 @@ typedef struct PhcStepArgs {
                                             address serialise (~30 ns each), so 1024 blocks on a single accumulator cost
                                             35 us per 4096-env step; 32 buckets make the epilogue free.  The consumer
                                             sums the buckets (phc_obs_moments_fold).                                  */
+  /* PHCPufferEnv.step's per-env episode bookkeeping (clean_pufferl/env.py:121-159; phc_episode_update is the standalone
+   * form and documents the semantics) done by the step itself, off when ep_returns is NULL.  The T = 1 kernel does it in
+   * its reduction warp; the other kernels are followed by one small launch.  The sums go to ep_buckets accumulators
+   * of PHC_EPISODE_SUM_COLS doubles {episodes finished, sum of returns, sum of lengths, truncations, sum over envs of
+   * reward_raw[:, c]}, folded by phc_episode_fold when the caller logs.                                            */
+  uint8_t* ep_terminals;                 /* [n] out */
+  uint8_t* ep_truncations;               /* [n] out */
+  uint8_t* ep_masks;                     /* [n] out */
+  float* ep_returns;                     /* [n] in/out */
+  int32_t* ep_lengths;                   /* [n] in/out */
+  double* ep_sums;                       /* [ep_buckets][PHC_EPISODE_SUM_COLS], zeroed by the caller once */
+  int32_t ep_buckets;                    /* >= 1 (32 is plenty: see obs_moments_buckets) */
+  int32_t ep_raw_cols;                   /* columns of reward_raw that are logged, <= 8 */
 } PhcStepArgs;
 
 PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream);
@@ -449,6 +463,9 @@ typedef struct PhcEpisodeArgs {
   double* workspace;          /* [PHC_EPISODE_WORKSPACE_DOUBLES] */
 } PhcEpisodeArgs;
 PHC_API int phc_episode_update(const PhcEpisodeArgs* args, int64_t n, phc_stream_t stream);
+/* stats[0..3] += sum over buckets; raw_rewards[c] += (sum over buckets of column 4 + c) / n; the buckets are zeroed */
+PHC_API int phc_episode_fold(double* ep_sums, int32_t num_buckets, int32_t raw_cols, int64_t n, double* stats,
+                             float* raw_rewards, phc_stream_t stream);
 
 /* The env's AMP observation buffers                          envs/humanoid_phc.py:596-611
  *   _amp_obs_buf [n, S, P]: slot 0 = _curr_amp_obs_buf, slots 1.. = _hist_amp_obs_buf; P as phc_amp_obs

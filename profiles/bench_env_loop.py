@@ -20,14 +20,15 @@ clock = synth.make_clock(lib_data, N, seed=1235, max_progress=30)
 K = 128
 print(f"# Whole env step through the shim at N = {N} (us per step, {K}-step CUDA graph, best of 5)\n")
 print("| variant | us / step | env-steps/s |\n|---|---|---|")
-for name, kw in (("fused step only (HumanoidPHC.post_physics_step)", None),
-                 ("PHCPufferEnv.step: power reward, episode bookkeeping, device-side resets", dict(use_power_reward=True)),
-                 ("the same + AMP observation buffers (10-step history)", dict(use_power_reward=True, use_amp_obs=True))):
+for name, kw, fused in (("fused step only (HumanoidPHC.post_physics_step)", None, False),
+                        ("PHCPufferEnv.step: power reward, episode bookkeeping, device-side resets", dict(use_power_reward=True), False),
+                        ("the same with the bookkeeping done by the step kernel (PHCPufferEnv(fused=True))", dict(use_power_reward=True), True),
+                        ("the same + AMP observation buffers (10-step history)", dict(use_power_reward=True, use_amp_obs=True), True)):
     env = HumanoidPHC(lib, N, device=dev, **(kw or {}))
     ref = lib.get_motion_state(clock.sampled_motion_ids, synth.reward_time(clock, extra_steps=1), clock.global_offset)
     env.set_sim_state(synth.make_sim_state(ref, seed=1236))
     env.set_clock(clock)
-    penv = PHCPufferEnv(env, log_interval=1 << 30, use_amp_obs=bool(kw and kw.get("use_amp_obs")))
+    penv = PHCPufferEnv(env, log_interval=1 << 30, use_amp_obs=bool(kw and kw.get("use_amp_obs")), fused=fused)
     actions = torch.rand(N, 69, device=dev) * 2.4 - 1.2
     phase = torch.rand(N, device=dev)
     state0 = env._rigid_body_state_reshaped.clone()

@@ -974,6 +974,50 @@ def test_puffer_env_step_matches_oracle():
     assert abs(info[0]["rew_body_pos"] - float(want["raw_rewards"][0]) / 3) < 1e-6
 
 
+@pytest.mark.parametrize("N,T,mode", [(1503, 1, "fast"), (4096, 1, "fast_power_norm"), (700, 1, "generic"), (515, 3, "multi")])
+def test_episode_bookkeeping_fused_into_the_step_equals_the_standalone_kernel(N, T, mode):
+    """PHCPufferEnv(fused=True): the step kernel (T = 1) or one small launch after it (other kernels) does the wrapper's
+    bookkeeping; buffers must equal the standalone phc_episode_update path bit for bit, the logged means to 1e-12."""
+    from humanoid_b200 import HumanoidPHC, PHCPufferEnv, RunningNorm, _cabi
+
+    lib_data, clock, state = _gpu_case(N, 40, 555, max_progress=30)
+    lib = MotionLib(lib_data, device=DEV)
+    capi = _cabi.load()
+    gen = torch.Generator().manual_seed(8)
+    steps = [(torch.rand(N, 69, generator=gen) * 4 - 2, torch.rand(N, generator=gen)) for _ in range(4)]
+    outs = []
+    try:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if mode == "generic" else 0)
+        for fused in (False, True):
+            env = HumanoidPHC(lib, N, device=DEV, time_steps=T, use_power_reward="power" in mode)
+            env.set_sim_state(state)
+            env.set_clock(clock)
+            if "power" in mode:
+                env.dof_force_tensor.normal_(generator=torch.Generator(device=DEV).manual_seed(1))
+                env._dof_vel.copy_(torch.randn(N, 69, generator=torch.Generator(device=DEV).manual_seed(2), device=DEV))
+            if "norm" in mode:
+                env.set_obs_normalizer(RunningNorm(env.num_obs, device=DEV))
+            pe = PHCPufferEnv(env, log_interval=4, fused=fused)
+            pe.episode_returns.fill_(0.25)  # as if episodes were under way
+            pe.episode_lengths.fill_(7)
+            infos = []
+            for actions, phase in steps:
+                obs, rew, term, trunc, info = pe.step(cuda(actions), phase_by_env=cuda(phase))
+                infos += info
+            torch.cuda.synchronize()
+            outs.append((pe, env, infos))
+    finally:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+    (a, ea, ia), (b, eb, ib) = outs
+    assert torch.equal(ea.obs_buf, eb.obs_buf) and torch.equal(ea.rew_buf, eb.rew_buf)
+    for k in ("terminals", "truncations", "masks", "episode_returns", "episode_lengths"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert len(ia) == len(ib) == 1 and a.episode_count == b.episode_count > 0
+    for k, v in ia[0].items():
+        assert abs(v - ib[0][k]) <= 1e-12 + 1e-6 * abs(v), (k, v, ib[0][k])  # raw_rewards accumulate in fp32 per step vs per log
+    assert float(b._ep_sums.abs().max()) == 0.0  # folded and cleared
+
+
 # ---------------------------------------------------------------------------------------
 # RunningNorm.forward fused into the step's obs epilogue (policies/running_norm.py:15-20)
 # ---------------------------------------------------------------------------------------

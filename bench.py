@@ -458,7 +458,7 @@ def run_gpu(args):
         "gpu_launches": K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(T), "peak_source": peak_src, "bytes_per_env_step": bytes_step,
-                     "kernel": "phc::step_fast_kernel<4,8,false>" if T == 1
+                     "kernel": "phc::step_fast_kernel<4,8,false,false>" if T == 1
                      else "phc::step_multi2_kernel", "launch_ms": ms_per_step},
         "rms": {"what": f"RunningNorm.update over a {roll}-step rollout: fp64 column moments + "
                         + (f"one fused launch per rank (all-reduce of {(2 * obs_dim + 1) * 8} B over NVLink peer memory + blend)"

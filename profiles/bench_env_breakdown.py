@@ -46,3 +46,14 @@ env.use_amp_obs=True
 m = env.reset_buf.clone()
 timed(lambda: env._init_amp_obs_masked(m), "amp init for flagged envs")
 print("flagged fraction", float(env.reset_buf.float().mean()))
+# with a realistic share of flagged envs (the synthetic state terminates ~24 % per step)
+env.set_clock(clock)
+env._rigid_body_state_reshaped.copy_(state0)
+env.post_physics_step(True)
+m = env.reset_buf.clone()
+print("flagged fraction", float(m.float().mean()))
+timed(lambda: env._init_amp_obs_masked(m), "amp init, 24 % flagged")
+env.use_amp_obs = False
+timed(lambda: env._reset_masked(m, phase), "reset kernel + masked obs pass, 24 % flagged")
+env.use_amp_obs = True
+timed(lambda: env._reset_masked(m, phase), "reset incl. amp init, 24 % flagged")

@@ -363,18 +363,21 @@ def run_gpu(args):
     envs[0].post_physics_step(True)
     torch.cuda.synchronize()
     e2e_ok = bool(torch.equal(envs[0].obs_buf.cpu(), h_obs) and torch.equal(envs[0].rew_buf.cpu(), h_rew))
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        if i % R == 0:
-            h_prog.copy_(h_prog0)
-        _cabi.check(capi.phc_host_step(ctx, C.byref(hargs), N), "phc_host_step")
-    t1 = time.perf_counter()
-    barrier()
-    e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = N * world * Ke / float(e2e_s.item())
+    e2e_runs = []
+    for _ in range(3):  # median of three timed loops of Ke calls (each call returns with the outputs in host memory)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            if i % R == 0:
+                h_prog.copy_(h_prog0)
+            _cabi.check(capi.phc_host_step(ctx, C.byref(hargs), N), "phc_host_step")
+        t1 = time.perf_counter()
+        barrier()
+        e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_runs.append(float(e2e_s.item()))
+    e2e_value = N * world * Ke / statistics.median(e2e_runs)
     h2d = int(capi.phc_host_step_h2d_bytes(ctx, N))
     d2h = int(capi.phc_host_step_d2h_bytes(ctx, N))
     capi.phc_host_step_destroy(ctx)
@@ -454,7 +457,7 @@ def run_gpu(args):
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                "steps": Ke, "chunks": args.e2e_chunks, "matches_device_path": e2e_ok},
+                "steps": Ke, "timing_repeats": 3, "chunks": args.e2e_chunks, "matches_device_path": e2e_ok},
         "gpu_launches": K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(T), "peak_source": peak_src, "bytes_per_env_step": bytes_step,

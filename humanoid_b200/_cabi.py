@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphc_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NUM_BODIES = 24
 SELF_OBS_DIM = 358
 TASK_OBS_DIM = 576

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PHC_ABI_VERSION 1
+#define PHC_ABI_VERSION 2 /* 2: PhcStepArgs grew (obs_moments_buckets, ep_*), phc_motion_build / phc_peer_reduce_* / phc_episode_fold added */
 #define PHC_NUM_BODIES 24      /* SMPL humanoid, body_sets.py:11-36 */
 #define PHC_SELF_OBS_DIM 358   /* envs/humanoid_phc.py:461 */
 #define PHC_TASK_OBS_DIM 576   /* per future step, envs/humanoid_phc.py:464 */

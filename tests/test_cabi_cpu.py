@@ -61,6 +61,35 @@ def test_struct_layouts_match_the_header():
     assert fields == in_header, (fields, in_header)
 
 
+def test_every_struct_matches_the_header_as_a_c_compiler_lays_it_out(tmp_path):
+    """gcc compiles a C99 consumer of include/phc_b200.h (so the header has no C++ / torch types in it) that
+    prints sizeof and offsetof for every field the ctypes mirror declares; both sides must agree, field by
+    field — the check that catches an argument struct growing on one side only."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = [v for v in vars(_cabi).values() if isinstance(v, type) and issubclass(v, C.Structure) and v is not C.Structure]
+    assert len(structs) >= 12
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "phc_b200.h"', "int main(void) {"]
+    for st in structs:
+        lines.append(f'  printf("{st.__name__} %zu\\n", sizeof({st.__name__}));')
+        for name, *_ in st._fields_:
+            lines.append(f'  printf("{st.__name__}.{name} %zu\\n", offsetof({st.__name__}, {name}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.dirname(HEADER),
+                    str(src), "-o", str(exe)], check=True)  # fmt: skip
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for st in structs:
+        assert int(out[st.__name__]) == C.sizeof(st), st.__name__
+        for name, *_ in st._fields_:
+            assert int(out[f"{st.__name__}.{name}"]) == getattr(st, name).offset, f"{st.__name__}.{name}"
+
+
 def test_argument_validation_returns_codes(lib):
     h = C.c_void_p()
     assert lib.phc_lib_create(None, C.byref(h)) == -1

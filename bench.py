@@ -180,7 +180,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------
@@ -514,12 +514,35 @@ def run_gpu(args):
         ms = t0.elapsed_time(t1) / reps
         line["torch_cuda_baseline"] = {"value": N / ms * 1e3, "unit": UNIT, "ms_per_step": ms,
                                        "what": "oracle/phc_oracle.py (the reference's torch ops, fp32) eager on this GPU"}  # fmt: skip
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def keep_stdout_for_the_json_line():
+    """The contract is ONE line on stdout.  Libraries write there too (NCCL prints its version banner from C when
+    NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+    the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=512)

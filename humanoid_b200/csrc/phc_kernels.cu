@@ -700,11 +700,12 @@ struct ResetParams {
 
 constexpr int K7_EPB = 8;
 
-__global__ void __launch_bounds__(K7_EPB* J24) reset_scatter_kernel(const ResetParams p) {
+// `act`: this thread's env is in range and selected by the mask (read by the caller, once, before anything is
+// written: the mask may be reset_buf itself, which the last lines clear)
+__device__ __forceinline__ void reset_scatter_body(const ResetParams& p, const bool act) {
   __shared__ float s_goff[K7_EPB][3];
   const int e = threadIdx.x / J24, b = threadIdx.x % J24;
   const int64_t env = (int64_t)blockIdx.x * K7_EPB + e;
-  const bool act = env < p.n && p.mask[env];
   if (act && b < 3) s_goff[e][b] = p.goff ? p.goff[env * 3 + b] : 0.0f;  // the OLD offset poses the env (:860)
   __syncthreads();
   if (!act) return;
@@ -932,8 +933,9 @@ __device__ __forceinline__ RefBody blend_ref(const StepSmem<EPB>& S, int q, int 
   return r;
 }
 
+// `sel`: -1 = select envs by p.env_mask (NULL = all); 0 / 1 = the caller has already read this thread's mask byte
 template <int EPB>
-__global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
+__device__ __forceinline__ void step_body(const StepParams& p, const int sel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<EPB>& S = *reinterpret_cast<StepSmem<EPB>*>(smem_raw);
   constexpr int NT = EPB * J24;
@@ -941,7 +943,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
   const int e = tid / J24, b = tid % J24;
   const int64_t env0 = (int64_t)blockIdx.x * EPB;
   const int64_t env = env0 + e;
-  const bool valid = env < p.n && (!p.env_mask || p.env_mask[env]);
+  const bool valid = env < p.n && (sel >= 0 ? sel != 0 : (!p.env_mask || p.env_mask[env]));
   const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
   const int T = p.T;
   if (b == 0) S.act[e] = valid;  // read after the first barrier
@@ -1177,6 +1179,24 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
     }
   }
   cp_async_wait_all();
+}
+
+template <int EPB>
+__global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
+  step_body<EPB>(p, -1);
+}
+
+// Reset of the flagged envs and their observations in ONE launch (phc_reset_envs): a block scatters the new state
+// of its 8 envs, then runs the obs-only pass of the generic step on what it has just written (block-local: no env
+// reads another env's state).  The mask byte is read once, first, so it may be reset_buf itself; blocks without a
+// flagged env leave at once — with nothing flagged the launch reads n mask bytes and nothing else.
+__global__ void __launch_bounds__(K7_EPB* J24) reset_obs_kernel(const ResetParams r, const StepParams p) {
+  const int64_t env = (int64_t)blockIdx.x * K7_EPB + threadIdx.x / J24;
+  const bool act = env < r.n && r.mask[env] != 0;
+  if (!__syncthreads_or(act)) return;
+  reset_scatter_body(r, act);
+  __syncthreads();  // sim rows and clock of the block's envs are written and visible to the block
+  step_body<K7_EPB>(p, act ? 1 : 0);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2849,7 +2869,6 @@ int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* a, int64_t n, phc_stre
   if (a->state_init == PHC_STATE_INIT_RANDOM && !a->flag_test && !a->phase) return PHC_ERR_NULL;
   if (a->state_init != PHC_STATE_INIT_RANDOM && a->state_init != PHC_STATE_INIT_START) return PHC_ERR_UNSUPPORTED;
   if ((a->dof_pos && !lib->d.lrs) || (a->dof_vel && !lib->d.dvs)) return PHC_ERR_NULL;
-  if ((const void*)a->env_mask == (const void*)a->reset_buf) return PHC_ERR_UNSUPPORTED;
   if (a->time_steps < 1 || a->time_steps > PHC_MAX_TIME_STEPS) return PHC_ERR_SHAPE;
   const int64_t W = SELF_DIM + (int64_t)TASK_DIM * a->time_steps;
   if (a->obs_stride < W || ((a->dof_pos || a->dof_vel) && a->dof_elem_stride < 1)) return PHC_ERR_SHAPE;
@@ -2875,11 +2894,7 @@ int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* a, int64_t n, phc_stre
   r.state_init = a->state_init;
   r.flag_test = a->flag_test;
   r.n = n;
-  reset_scatter_kernel<<<(unsigned)((n + K7_EPB - 1) / K7_EPB), K7_EPB * J24, 0, stream>>>(r);
-  rc = launch_status();
-  if (rc) return rc;
-
-  // _compute_observations(env_ids): masked obs-only pass of the generic step kernel on the new state
+  // _compute_observations(env_ids): masked obs-only pass of the generic step on the new state, same launch
   PhcStepArgs s{};
   s.body = a->body;
   s.progress_buf = a->progress_buf;
@@ -2908,8 +2923,15 @@ int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* a, int64_t n, phc_stre
   int dev = 0;
   PHC_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return PHC_ERR_UNSUPPORTED;
-  static bool attr_gen_reset[64] = {};
-  return launch_step(step_kernel<STEP_EPB>, sizeof(StepSmem<STEP_EPB>), STEP_EPB, p, stream, &attr_gen_reset[dev], false);
+  static_assert(K7_EPB == STEP_EPB, "reset_obs_kernel runs both bodies on one block shape");
+  static bool attr_reset_obs[64] = {};
+  if (!attr_reset_obs[dev]) {
+    PHC_CUDA(cudaFuncSetAttribute(reset_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(StepSmem<STEP_EPB>)));
+    attr_reset_obs[dev] = true;
+  }
+  reset_obs_kernel<<<(unsigned)((n + K7_EPB - 1) / K7_EPB), K7_EPB * J24, sizeof(StepSmem<STEP_EPB>), stream>>>(r, p);
+  return launch_status();
 }
 
 int phc_set_trace_buffer(uint64_t* device_buf, int64_t capacity_warps) {

@@ -535,7 +535,10 @@ class HumanoidPHC:
         host sync.  ``phase_by_env [N]`` supplies one uniform number per env (used where flagged)."""
         if phase_by_env is None:
             phase_by_env = torch.rand(self.num_envs, device=self.device)
-        self._reset_masked(self.reset_buf.clone(), phase_by_env.to(self.device, torch.float32).contiguous())
+        # the reset kernel reads each mask byte once before it clears reset_buf, so reset_buf can be its own mask;
+        # the AMP initialisation that follows needs the flags after they are cleared, hence the copy there
+        mask = self.reset_buf.clone() if self.use_amp_obs else self.reset_buf
+        self._reset_masked(mask, phase_by_env.to(self.device, torch.float32).contiguous())
         return self.obs_buf
 
     def set_humanoid_assets(self, skeleton_trees, humanoid_shapes, humanoid_limb_and_weights):

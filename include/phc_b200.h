@@ -290,9 +290,11 @@ PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n
  *     -> get_motion_state -> _set_env_state (:901-931) -> clock updates of
  *     _reset_ref_state_init (:724-731) -> buffer zeroing of _reset_env_tensors (:775-778)
  *     -> _compute_observations(env_ids) (:937-961).
- * The PhysX setters (:748-765) are out of scope.  Envs are selected by a byte mask (e.g. a copy
- * of reset_buf), so the `nonzero()` of clean_pufferl/env.py:133 is not needed.  Random numbers
+ * The PhysX setters (:748-765) are out of scope.  Envs are selected by a byte mask (reset_buf
+ * itself, or a copy), so the `nonzero()` of clean_pufferl/env.py:133 is not needed.  Random numbers
  * come from the caller (`phase`, what torch.rand gives in sample_time_interval), indexed by env.
+ * ONE launch: a block scatters the new state of its 8 envs and then computes their observation
+ * rows from what it has just written; a block without a selected env reads 8 mask bytes and leaves.
  * ---------------------------------------------------------------------------------- */
 #define PHC_STATE_INIT_START 0  /* motion time 0                       state_init.py */
 #define PHC_STATE_INIT_RANDOM 1 /* sample_time_interval(phase)                       */
@@ -311,7 +313,7 @@ typedef struct PhcResetArgs {
   float* motion_start_times_offset;       /* [n] -> 0                                         */
   float* global_offset;                   /* [n,3] read (old value offsets the pose), then -> 0 */
   const int64_t* sampled_motion_ids;      /* [n]                                              */
-  const uint8_t* env_mask;                /* [n] 1 = reset this env; must not alias reset_buf  */
+  const uint8_t* env_mask;                /* [n] 1 = reset this env; may be reset_buf itself   */
   const float* phase;                     /* [n] uniform [0,1), used when state_init == RANDOM */
   int32_t state_init;                     /* PHC_STATE_INIT_*                                 */
   int32_t flag_test;                      /* motion_times[:] = 0         humanoid_phc.py:856  */

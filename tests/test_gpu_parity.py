@@ -816,6 +816,37 @@ def test_rollout_with_device_side_resets_vs_oracle():
         s["state"] = env._rigid_body_state_reshaped.cpu().clone()  # keep both sides on identical inputs
 
 
+@pytest.mark.parametrize("N,flag", [(1029, "some"), (515, "none"), (64, "all"), (7, "some")])
+def test_reset_with_reset_buf_as_its_own_mask_equals_the_copied_mask_bitwise(N, flag):
+    """phc_reset_envs reads each mask byte once before it clears reset_buf, so the flags can select the envs
+    directly (reset_done without AMP); same buffers, bit for bit, as with a copy of the flags, and with nothing
+    flagged nothing is written at all."""
+    lib_data, clock, state = make_case_cpu(num_envs=N, num_motions=max(4, N // 3), seed=131, max_progress=30,
+                                           fps_choices=(30, 60), min_frames=40, max_frames=200)  # fmt: skip
+    a, b = env_from(lib_data, clock, state), env_from(lib_data, clock, state)
+    gen = torch.Generator().manual_seed(11)
+    flags = torch.rand(N, generator=gen) < 0.3 if flag == "some" else torch.full((N,), flag == "all")
+    phase = cuda(torch.rand(N, generator=gen))
+    for env in (a, b):
+        env.step()
+        env.reset_buf.copy_(cuda(flags))
+        env._terminate_buf.copy_(cuda(flags))
+    before = {k: getattr(a, k).clone() for k in ("obs_buf", "_rigid_body_state_reshaped", "progress_buf")}
+    a._reset_masked(a.reset_buf.clone(), phase)  # a copy of the flags selects the envs
+    b.reset_done(phase)  # reset_buf itself does
+    assert b.use_amp_obs is False
+    for k in ("obs_buf", "_rigid_body_state_reshaped", "_humanoid_root_states", "_dof_state", "progress_buf", "reset_buf",
+              "_terminate_buf", "_motion_start_times", "_motion_start_times_offset", "_global_offset"):  # fmt: skip
+        if hasattr(a, k):
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert not bool(b.reset_buf.any()) and not bool(b._terminate_buf[cuda(flags)].any())
+    if flag == "none":
+        for k, v in before.items():
+            assert torch.equal(getattr(b, k), v), k
+    else:
+        assert not torch.equal(b.obs_buf, before["obs_buf"])
+
+
 @pytest.mark.parametrize("groups", [2, 1], ids=["two_groups", "one_group"])
 @pytest.mark.parametrize("N,T", [(1027, 10), (64, 16), (515, 2), (2050, 3), (9, 5)])
 def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T, groups):

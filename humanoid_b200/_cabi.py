@@ -200,7 +200,7 @@ class PhcAmpEnvArgs(C.Structure):
         ("flags", C.c_uint32),
         ("num_steps", C.c_int32),
         ("obs_per_step", C.c_int32),
-        ("_pad0", C.c_int32),
+        ("init_slot0", C.c_int32),
         ("amp_obs_buf", C.c_void_p),
         ("amp_obs_demo_buf", C.c_void_p),
         ("env_mask", C.c_void_p),

@@ -368,7 +368,13 @@ __global__ void imitation_obs_kernel(const float* __restrict__ root_pos, int64_t
 // dof3(d, pos, vel) = position / velocity of three dof indices, key_pos(i) = position of key body i.
 template <class Src>
 __device__ __forceinline__ void amp_obs_row(const Src& src, int K, const int64_t* __restrict__ dof_subset, int num_sel,
-                                            uint32_t flags, int lane, float* __restrict__ row) {
+                                            uint32_t flags, int lane, float* __restrict__ row,
+                                            float* __restrict__ row2 = nullptr) {  // row2: NULL, or a second copy of the row
+  const auto put = [&](int i, float v) {
+    row[i] = v;
+    if (row2) row2[i] = v;
+  };
+  const auto put3 = [&](int i, Vec3 v) { put(i, v.x), put(i + 1, v.y), put(i + 2, v.z); };
   const int nj = num_sel / 3;
   const Vec3 root_pos = src.root_pos();
   Quat root_rot = src.root_rot();
@@ -377,16 +383,16 @@ __device__ __forceinline__ void amp_obs_row(const Src& src, int K, const int64_t
   const HeadingRot hr = heading_rot(hi);
   int col = 0;
   if (flags & PHC_OBS_ROOT_HEIGHT) {
-    if (lane == 0) row[0] = root_pos.z;
+    if (lane == 0) put(0, root_pos.z);
     col = 1;
   }
   if (lane == 0) {
     float t6[6];
     quat_tan_norm((flags & PHC_OBS_LOCAL_ROOT) ? heading_mul_left(hi, root_rot) : root_rot, t6);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) row[col + k] = t6[k];
-    st3(row + col + 6, heading_rotate(hr, src.root_vel()));
-    st3(row + col + 9, heading_rotate(hr, src.root_ang_vel()));
+    for (int k = 0; k < 6; ++k) put(col + k, t6[k]);
+    put3(col + 6, heading_rotate(hr, src.root_vel()));
+    put3(col + 9, heading_rotate(hr, src.root_ang_vel()));
   }
   col += 12;
   for (int j = lane; j < nj; j += 32) {  // dof_to_obs_smpl (:179-189) + the selected dof velocities
@@ -398,12 +404,12 @@ __device__ __forceinline__ void amp_obs_row(const Src& src, int K, const int64_t
     float t6[6];
     quat_tan_norm(exp_map_to_quat(Vec3{e3[0], e3[1], e3[2]}), t6);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) row[col + 6 * j + k] = t6[k];
+    for (int k = 0; k < 6; ++k) put(col + 6 * j + k, t6[k]);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) row[col + 6 * nj + 3 * j + k] = v3[k];
+    for (int k = 0; k < 3; ++k) put(col + 6 * nj + 3 * j + k, v3[k]);
   }
   col += 9 * nj;
-  if (lane < K) st3(row + col + 3 * lane, heading_rotate(hr, src.key_pos(lane) - root_pos));
+  if (lane < K) put3(col + 3 * lane, heading_rotate(hr, src.key_pos(lane) - root_pos));
 }
 
 struct AmpSrcArrays {  // build_amp_observations_smpl's argument list, row `env`
@@ -433,8 +439,9 @@ __global__ void amp_obs_kernel(PhcAmpArgs a, int64_t n, float* __restrict__ out,
 // ---------------------------------------------------------------------------------------
 // K11 / K12: the env's AMP observation buffers (envs/humanoid_phc.py:791-843, 1125-1176, 1341-1350).
 //   amp_step_kernel      one warp per env: history roll (slot k+1 <- slot k) + slot 0 from the sim state
-//   amp_init_ref_kernel  one warp per (env, slot) of the selected envs: slot k >= 1 from the motion library
-//                        at motion_time - k*dt, then the env's row copied to the demo buffer
+//   amp_init_ref_kernel  a block per 8 envs, its warps over the (selected env, slot) pairs: slot 0 from the sim
+//                        state (optional), slot k >= 1 from the motion library at motion_time - k*dt, each row
+//                        written to the demo buffer as well
 // ---------------------------------------------------------------------------------------
 constexpr int AMP_MAX_STEPS = 16;
 struct AmpEnvParams {
@@ -538,28 +545,46 @@ __global__ void amp_step_kernel(AmpEnvParams p) {
   amp_obs_row(AmpSrcSim{p, env}, p.K, p.dof_subset, p.num_sel, p.flags, lane, rows);
 }
 
-__global__ void amp_init_ref_kernel(AmpEnvParams p, LibDev L, const int64_t* __restrict__ motion_ids,
-                                    const float* __restrict__ motion_times, float dt) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t env = w / p.S;
-  const int k = (int)(w % p.S);
-  if (env >= p.n || (p.mask && !p.mask[env])) return;
-  float* row = p.buf + (env * p.S + k) * (int64_t)p.P;
-  if (k > 0) {
-    const int64_t id = motion_ids[env];
-    // motion_times + (-dt * (arange(S-1) + 1)), both fp32 (:809-810)
-    const float t = motion_times[env] + (-dt) * (float)k;
-    int64_t i0, i1;
-    float bl;
-    calc_frame_blend(t, L.len[id], L.nf[id], L.mdt[id], i0, i1, bl);
-    const int64_t st = L.starts[id];
-    amp_obs_row(AmpSrcLib{L, p.key_ids, i0 + st, i1 + st, bl}, p.K, p.dof_subset, p.num_sel, p.flags, lane, row);
-    __syncwarp();
+// One block = 8 envs.  Warp 0 lists the block's selected envs (ballot); a block without one leaves after
+// reading 8 mask bytes.  The block's warps then walk the (selected env, slot) pairs: slot 0 from the sim state when
+// `slot0` (_compute_amp_observations(env_ids), :792), slots >= 1 from the motion library, then the demo copy.
+constexpr int AMPI_EPB = 8;
+
+__global__ void __launch_bounds__(1024)
+    amp_init_ref_kernel(AmpEnvParams p, LibDev L, const int64_t* __restrict__ motion_ids,
+                        const float* __restrict__ motion_times, float dt, int slot0, int epb) {
+  __shared__ int s_list[AMPI_EPB];
+  __shared__ int s_count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t env0 = (int64_t)blockIdx.x * epb;
+  if (warp == 0) {
+    const bool f = lane < epb && env0 + lane < p.n && (!p.mask || p.mask[env0 + lane]);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (f) s_list[__popc(m & ((1u << lane) - 1u))] = lane;
+    if (lane == 0) s_count = __popc(m);
   }
-  if (p.demo) {  // _amp_obs_demo_buf[env_ids] = _amp_obs_buf[env_ids] (:819)
-    float* drow = p.demo + (env * p.S + k) * (int64_t)p.P;
-    for (int i = lane; i < p.P; i += 32) drow[i] = row[i];
+  __syncthreads();
+  const int pairs = s_count * p.S;
+  for (int w = warp; w < pairs; w += (int)(blockDim.x >> 5)) {
+    const int64_t env = env0 + s_list[w / p.S];
+    const int k = w % p.S;
+    float* row = p.buf + (env * p.S + k) * (int64_t)p.P;
+    // the demo row, _amp_obs_demo_buf[env_ids] = _amp_obs_buf[env_ids] (:819), is written with the row itself
+    float* drow = p.demo ? p.demo + (env * p.S + k) * (int64_t)p.P : nullptr;
+    if (k > 0) {
+      const int64_t id = motion_ids[env];
+      // motion_times + (-dt * (arange(S-1) + 1)), both fp32 (:809-810)
+      const float t = motion_times[env] + (-dt) * (float)k;
+      int64_t i0, i1;
+      float bl;
+      calc_frame_blend(t, L.len[id], L.nf[id], L.mdt[id], i0, i1, bl);
+      const int64_t st = L.starts[id];
+      amp_obs_row(AmpSrcLib{L, p.key_ids, i0 + st, i1 + st, bl}, p.K, p.dof_subset, p.num_sel, p.flags, lane, row, drow);
+    } else if (slot0) {
+      amp_obs_row(AmpSrcSim{p, env}, p.K, p.dof_subset, p.num_sel, p.flags, lane, row, drow);
+    } else if (drow) {  // slot 0 was written by an earlier launch
+      for (int i = lane; i < p.P; i += 32) drow[i] = row[i];
+    }
   }
 }
 
@@ -3189,9 +3214,22 @@ int phc_amp_init_ref(const PhcLib* lib, const PhcAmpEnvArgs* a, const int64_t* m
   if (!lib->d.lrs || !lib->d.dvs) return PHC_ERR_NULL;  // dof_pos / dof_vel need the local rotations and dof velocities
   for (int i = 0; i < a->num_key_bodies; ++i)
     if (a->key_body_ids[i] >= J24) return PHC_ERR_SHAPE;
-  const int wpb = 4;
-  const int64_t warps = n * p.S;
-  amp_init_ref_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p, lib->d, motion_ids, motion_times, dt);
+  if (a->init_slot0 && (!a->dof_pos || !a->dof_vel)) return PHC_ERR_NULL;
+  if (a->init_slot0 && a->dof_elem_stride < 1) return PHC_ERR_SHAPE;
+  // measured at 4096 envs x 10 slots (profiles/r1_env_loop.md): 8 envs x 16 warps per block is 2.0 us with nothing
+  // flagged and 40 us with 31 % flagged; 2 x 10 is 3.7 / 36 us, 1 x 10 is 6.4 / 35 us — the rows themselves are
+  // issue-bound (slerp + exp-map + tan-norm per joint in precise libdevice math), so the default favours the empty case
+  static int wpb = 0, epb = 0;
+  if (!wpb) {
+    const char* v = getenv("PHC_AMPI_WARPS");
+    const char* e = getenv("PHC_AMPI_EPB");
+    epb = e ? atoi(e) : AMPI_EPB;
+    if (epb < 1 || epb > AMPI_EPB) epb = AMPI_EPB;
+    wpb = v ? atoi(v) : 16;
+    if (wpb < 1 || wpb > 32) wpb = 16;
+  }
+  amp_init_ref_kernel<<<(unsigned)((n + epb - 1) / epb), wpb * 32, 0, stream>>>(
+      p, lib->d, motion_ids, motion_times, dt, a->init_slot0 ? 1 : 0, epb);
   return launch_status();
 }
 

@@ -434,8 +434,8 @@ class HumanoidPHC:
     def _init_amp_obs_masked(self, mask: torch.Tensor):
         """``_init_amp_obs(env_ids)`` (:791-799) for the envs of a byte mask, right after their reset:
         slot 0 from the freshly set sim state, the history from the motion library, the demo rows."""
-        self._amp_step(roll=False, mask=mask)
         a, keep = self._amp_args(mask)
+        a.init_slot0 = 1  # _compute_amp_observations(env_ids) rides in the same launch
         _cabi.check(
             _cabi.load().phc_amp_init_ref(
                 self._motion_lib.handle, C.byref(a), self._sampled_motion_ids.data_ptr(),

@@ -481,7 +481,10 @@ PHC_API int phc_episode_fold(double* ep_sums, int32_t num_buckets, int32_t raw_c
  * phc_amp_init_ref: _init_amp_obs_ref (:805-819) for the selected envs — slot k >= 1 is the AMP
  *   observation of clip motion_ids[env] at motion_times[env] - k*dt (_get_amp_obs :821-838, no global
  *   offset), then the env's whole row is copied to amp_obs_demo_buf (may be NULL).  motion_ids /
- *   motion_times are indexed by env (after a reset: _sampled_motion_ids / _motion_start_times). */
+ *   motion_times are indexed by env (after a reset: _sampled_motion_ids / _motion_start_times).
+ *   With init_slot0 it is the whole _init_amp_obs(env_ids) (:791-799): slot 0 is written from the sim
+ *   state first, as phc_amp_step(roll_history = 0) under the same mask would.  A block of 8 envs
+ *   without a selected env reads 8 mask bytes and leaves. */
 typedef struct PhcAmpEnvArgs {
   PhcBodyState body;           /* sim state views (phc_amp_step); num_bodies also bounds key_body_ids */
   const float* dof_pos;        /* [n,69] view (phc_amp_step)       humanoid_phc.py:535 */
@@ -495,7 +498,7 @@ typedef struct PhcAmpEnvArgs {
   uint32_t flags;              /* PHC_OBS_LOCAL_ROOT | PHC_OBS_ROOT_HEIGHT | PHC_OBS_UPRIGHT */
   int32_t num_steps;           /* S = num_amp_obs_steps <= 16      config.py:141 */
   int32_t obs_per_step;        /* P */
-  int32_t _pad0;
+  int32_t init_slot0;          /* phc_amp_init_ref only: 1 = also write slot 0 from the sim state (:792), same launch */
   float* amp_obs_buf;          /* [n, S, P] */
   float* amp_obs_demo_buf;     /* [n, S, P] or NULL (phc_amp_init_ref) */
   const uint8_t* env_mask;     /* NULL or [n] */

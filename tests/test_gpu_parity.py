@@ -847,6 +847,39 @@ def test_reset_with_reset_buf_as_its_own_mask_equals_the_copied_mask_bitwise(N, 
         assert not torch.equal(b.obs_buf, before["obs_buf"])
 
 
+@pytest.mark.parametrize("N,flag", [(1029, "some"), (515, "none"), (37, "all"), (5, "some")])
+def test_amp_init_with_slot0_in_the_same_launch_equals_the_two_launches_bitwise(N, flag):
+    """_init_amp_obs(env_ids) (:791-799) as one launch (PhcAmpEnvArgs.init_slot0) against
+    _compute_amp_observations(env_ids) + _init_amp_obs_ref(env_ids) as two; untouched envs keep their rows."""
+    import ctypes as C
+
+    from humanoid_b200 import _cabi
+
+    lib_data, clock, state = make_case_cpu(num_envs=N, num_motions=max(4, N // 3), seed=137, max_progress=30,
+                                           fps_choices=(30, 60), min_frames=40, max_frames=200)  # fmt: skip
+    a, b = env_from(lib_data, clock, state, use_amp_obs=True), env_from(lib_data, clock, state, use_amp_obs=True)
+    gen = torch.Generator().manual_seed(12)
+    flags = cuda(torch.rand(N, generator=gen) < 0.3 if flag == "some" else torch.full((N,), flag == "all"))
+    for env in (a, b):
+        env.step()
+        env._amp_obs_buf.copy_(cuda(torch.rand(env._amp_obs_buf.shape, generator=torch.Generator().manual_seed(13))))
+        env._amp_obs_demo_buf.fill_(7.0)
+    before = b._amp_obs_buf.clone()
+    a._amp_step(roll=False, mask=flags)
+    args, keep = a._amp_args(flags)
+    _cabi.check(_cabi.load().phc_amp_init_ref(a._motion_lib.handle, C.byref(args), a._sampled_motion_ids.data_ptr(),
+                                              a._motion_start_times.data_ptr(), a.dt, N, _cabi.stream_ptr(a.device)),
+                "phc_amp_init_ref")  # fmt: skip
+    b._init_amp_obs_masked(flags)
+    assert torch.equal(a._amp_obs_buf, b._amp_obs_buf)
+    assert torch.equal(a._amp_obs_demo_buf, b._amp_obs_demo_buf)
+    assert torch.equal(b._amp_obs_buf[~flags], before[~flags])
+    assert bool((b._amp_obs_demo_buf[~flags] == 7.0).all())
+    if flag != "none":
+        assert not torch.equal(b._amp_obs_buf[flags], before[flags])
+        assert torch.equal(b._amp_obs_demo_buf[flags], b._amp_obs_buf[flags])
+
+
 @pytest.mark.parametrize("groups", [2, 1], ids=["two_groups", "one_group"])
 @pytest.mark.parametrize("N,T", [(1027, 10), (64, 16), (515, 2), (2050, 3), (9, 5)])
 def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T, groups):

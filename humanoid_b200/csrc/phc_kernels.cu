@@ -721,13 +721,43 @@ struct ResetParams {
   const float* phase;
   int state_init, flag_test;
   int64_t n;
+  float* obs;  // [n, 358 + 576 T]: rows of the reset envs rewritten
+  int64_t obs_stride;
+  int T;
+  float dt;
+};
+
+struct ResetEnvOut {  // what the scatter leaves in registers for the observation of the same (env, body)
+  Vec3 pos, vel, ang;
+  Quat rot;
+  float t, len, mdt;
+  int64_t nf, st;
 };
 
 constexpr int K7_EPB = 8;
 
+// the reference body b of a just-reset env at (progress + q) dt + start + offset with progress = 0, offset = 0
+// (humanoid_phc.py:1063-1067), blended like blend_ref; the global offset is the zero the reset leaves
+__device__ __forceinline__ RefBody reset_ref_body(const LibDev& L, int q, float dt, float t, float len, int64_t nf, float mdt,
+                                                  int64_t st, int b) {
+  const float tq = (float)(int16_t)q * dt + t + 0.0f;
+  int64_t i0, i1;
+  float bl;
+  calc_frame_blend(tq, len, nf, mdt, i0, i1, bl);
+  const int64_t f0 = i0 + st, f1 = i1 + st;
+  const float om = 1.0f - bl;
+  RefBody r;
+  r.pos = lerp3(om, bl, ld3(L.gts + (f0 * J24 + b) * 3), ld3(L.gts + (f1 * J24 + b) * 3));
+  r.pos.x += 0.0f, r.pos.y += 0.0f, r.pos.z += 0.0f;
+  r.rot = quat_slerp(ld4v(L.grs + (f0 * J24 + b) * 4), ld4v(L.grs + (f1 * J24 + b) * 4), bl);
+  r.vel = lerp3(om, bl, ld3(L.gvs + (f0 * J24 + b) * 3), ld3(L.gvs + (f1 * J24 + b) * 3));
+  r.ang = lerp3(om, bl, ld3(L.gavs + (f0 * J24 + b) * 3), ld3(L.gavs + (f1 * J24 + b) * 3));
+  return r;
+}
+
 // `act`: this thread's env is in range and selected by the mask (read by the caller, once, before anything is
 // written: the mask may be reset_buf itself, which the last lines clear)
-__device__ __forceinline__ void reset_scatter_body(const ResetParams& p, const bool act) {
+__device__ __forceinline__ void reset_scatter_body(const ResetParams& p, const bool act, ResetEnvOut& o) {
   __shared__ float s_goff[K7_EPB][3];
   const int e = threadIdx.x / J24, b = threadIdx.x % J24;
   const int64_t env = (int64_t)blockIdx.x * K7_EPB + e;
@@ -746,7 +776,9 @@ __device__ __forceinline__ void reset_scatter_body(const ResetParams& p, const b
   }
   int64_t i0, i1;
   float bl;
-  calc_frame_blend(t, len, p.L.nf[id], p.L.mdt[id], i0, i1, bl);
+  const int64_t nf = p.L.nf[id];
+  const float mdt = p.L.mdt[id];
+  calc_frame_blend(t, len, nf, mdt, i0, i1, bl);
   const int64_t st = p.L.starts[id];
   const int64_t f0 = i0 + st, f1 = i1 + st;
   const float om = 1.0f - bl;
@@ -797,6 +829,8 @@ __device__ __forceinline__ void reset_scatter_body(const ResetParams& p, const b
     p.reset[env] = 0;
     p.term[env] = 0;
   }
+  o.pos = pos, o.rot = rot, o.vel = vel, o.ang = ang;
+  o.t = t, o.len = len, o.mdt = mdt, o.nf = nf, o.st = st;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1211,17 +1245,57 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
   step_body<EPB>(p, -1);
 }
 
-// Reset of the flagged envs and their observations in ONE launch (phc_reset_envs): a block scatters the new state
-// of its 8 envs, then runs the obs-only pass of the generic step on what it has just written (block-local: no env
-// reads another env's state).  The mask byte is read once, first, so it may be reset_buf itself; blocks without a
-// flagged env leave at once — with nothing flagged the launch reads n mask bytes and nothing else.
-__global__ void __launch_bounds__(K7_EPB* J24) reset_obs_kernel(const ResetParams r, const StepParams p) {
-  const int64_t env = (int64_t)blockIdx.x * K7_EPB + threadIdx.x / J24;
-  const bool act = env < r.n && r.mask[env] != 0;
+// Reset of the flagged envs and their observations in ONE launch (phc_reset_envs).  A thread scatters the new state
+// of its (env, body) and, with that state still in registers, writes the body's columns of the env's obs row
+// (_compute_observations(env_ids), :937-961): the root position and heading come from body 0 through shared memory,
+// the reference bodies at t + q dt straight from the motion library.  The arithmetic is the generic step kernel's,
+// operand for operand (the clock of a just-reset env: progress 0, offsets 0), so the rows are bit-identical to an
+// obs-only pass of step_kernel over the new state; the chain of dependent memory round trips is less than half as
+// long.  The mask byte is read once, first, so it may be reset_buf itself; blocks without a flagged env leave at once —
+// with nothing flagged the launch reads n mask bytes and nothing else.
+__global__ void __launch_bounds__(K7_EPB* J24) reset_obs_kernel(const ResetParams p) {
+  __shared__ float s_root[K7_EPB][5];  // root pos xyz | inverse heading z, w
+  const int e = threadIdx.x / J24, b = threadIdx.x % J24;
+  const int64_t env = (int64_t)blockIdx.x * K7_EPB + e;
+  const bool act = env < p.n && p.mask[env] != 0;
   if (!__syncthreads_or(act)) return;
-  reset_scatter_body(r, act);
-  __syncthreads();  // sim rows and clock of the block's envs are written and visible to the block
-  step_body<K7_EPB>(p, act ? 1 : 0);
+  ResetEnvOut o;
+  reset_scatter_body(p, act, o);
+  if (act && b == 0) {
+    const Heading h0 = heading_quat_inv(o.rot);  // upright: root_rot used as is (common.py:42-44)
+    s_root[e][0] = o.pos.x, s_root[e][1] = o.pos.y, s_root[e][2] = o.pos.z;
+    s_root[e][3] = h0.z, s_root[e][4] = h0.w;
+  }
+  __syncthreads();
+  if (!act) return;
+  const Vec3 root_pos = {s_root[e][0], s_root[e][1], s_root[e][2]};
+  const Heading hi = {s_root[e][3], s_root[e][4]};
+  const HeadingRot hr = heading_rot(hi);
+  float* row = p.obs + env * p.obs_stride;
+  // self obs, common.py:23-103 (default flags: local root, height, upright)
+  if (b == 0)
+    row[0] = root_pos.z;
+  else
+    st3(row + 1 + (b - 1) * 3, heading_rotate(hr, o.pos - root_pos));
+  quat_tan_norm(heading_mul_left(hi, o.rot), row + 70 + b * 6);
+  st3(row + 214 + b * 3, heading_rotate(hr, o.vel));
+  st3(row + 286 + b * 3, heading_rotate(hr, o.ang));
+  for (int q = 1; q <= p.T; ++q) {
+    // loading the t + dt frames together with the scatter's (before its stores) was measured: 10 more registers,
+    // 3 instead of 4 blocks per SM — 0.6 us faster per loop step at 4 % flagged, 2.5 us slower at 31 %; not kept
+    const RefBody r = reset_ref_body(p.L, q, p.dt, o.t, o.len, o.nf, o.mdt, o.st, b);
+    TaskObs t;
+    task_obs_body(hi, hr, root_pos, o.pos, o.rot, o.vel, o.ang, r, true, t);
+    float* tk = row + SELF_DIM + (int64_t)TASK_DIM * (q - 1);
+    st3(tk + b * 3, t.d_pos);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tk[72 + b * 6 + k] = t.d_rot[k];
+    st3(tk + 216 + b * 3, t.d_vel);
+    st3(tk + 288 + b * 3, t.d_ang);
+    st3(tk + 360 + b * 3, t.l_pos);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tk[432 + b * 6 + k] = t.l_rot[k];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1621,6 +1695,14 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     const int le = tid >> 2, k = tid & 3;
     const bool act = le < nvalid && tid < 4 * EPB;
     float term_k = 0.0f;
+    float ep_ret = 0.0f;  // EP: the env's running return / length, fetched before the reductions below need them
+    int32_t ep_len = 0;
+    if constexpr (EP) {
+      if (act && k == 0) {
+        ep_ret = p.ep_returns[env0 + le];
+        ep_len = p.ep_lengths[env0 + le];
+      }
+    }
     if (act) {
       const float kk = k == 0 ? p.rwd.k_pos : k == 1 ? p.rwd.k_rot : k == 2 ? p.rwd.k_vel : p.rwd.k_ang_vel;
       term_k = expf((-kk) * (row_sum24(&S.part[k][le][0]) / 24.0f));  // common.py:298-320
@@ -1674,8 +1756,8 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
         p.ep_terminals[e] = tm ? 1 : 0;
         p.ep_truncations[e] = tr ? 1 : 0;
         p.ep_masks[e] = tr ? 0 : 1;
-        float ret = p.ep_returns[e];
-        int32_t len = p.ep_lengths[e];
+        float ret = ep_ret;
+        int32_t len = ep_len;
         if (rs) {
           v[0] = 1.0;
           v[1] = (double)ret;
@@ -2919,43 +3001,11 @@ int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* a, int64_t n, phc_stre
   r.state_init = a->state_init;
   r.flag_test = a->flag_test;
   r.n = n;
-  // _compute_observations(env_ids): masked obs-only pass of the generic step on the new state, same launch
-  PhcStepArgs s{};
-  s.body = a->body;
-  s.progress_buf = a->progress_buf;
-  s.motion_start_times = a->motion_start_times;
-  s.motion_start_times_offset = a->motion_start_times_offset;
-  s.global_offset = a->global_offset;
-  s.sampled_motion_ids = a->sampled_motion_ids;
-  s.time_steps = a->time_steps;
-  s.dt = a->dt;
-  s.obs_buf = a->obs_buf;
-  s.obs_stride = a->obs_stride;
-  StepParams p;
-  // reward / flag outputs are not written in obs-only mode; give the validator harmless non-NULLs
-  s.termination_distances = a->motion_start_times;
-  s.rew_buf = a->motion_start_times;
-  s.reward_raw = a->motion_start_times;
-  s.reward_raw_stride = 4;
-  s.reset_buf = a->reset_buf;
-  s.terminate_buf = a->terminate_buf;
-  rc = step_fill_params(lib, &s, n, p);
-  if (rc) return rc;
-  p.env_mask = a->env_mask;
-  p.obs_only = 1;
-  p.advance = 0;
-  p.trace = nullptr;
-  int dev = 0;
-  PHC_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return PHC_ERR_UNSUPPORTED;
-  static_assert(K7_EPB == STEP_EPB, "reset_obs_kernel runs both bodies on one block shape");
-  static bool attr_reset_obs[64] = {};
-  if (!attr_reset_obs[dev]) {
-    PHC_CUDA(cudaFuncSetAttribute(reset_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(StepSmem<STEP_EPB>)));
-    attr_reset_obs[dev] = true;
-  }
-  reset_obs_kernel<<<(unsigned)((n + K7_EPB - 1) / K7_EPB), K7_EPB * J24, sizeof(StepSmem<STEP_EPB>), stream>>>(r, p);
+  r.obs = a->obs_buf;  // _compute_observations(env_ids), same launch
+  r.obs_stride = a->obs_stride;
+  r.T = a->time_steps;
+  r.dt = a->dt;
+  reset_obs_kernel<<<(unsigned)((n + K7_EPB - 1) / K7_EPB), K7_EPB * J24, 0, stream>>>(r);
   return launch_status();
 }
 

@@ -816,14 +816,14 @@ def test_rollout_with_device_side_resets_vs_oracle():
         s["state"] = env._rigid_body_state_reshaped.cpu().clone()  # keep both sides on identical inputs
 
 
-@pytest.mark.parametrize("N,flag", [(1029, "some"), (515, "none"), (64, "all"), (7, "some")])
-def test_reset_with_reset_buf_as_its_own_mask_equals_the_copied_mask_bitwise(N, flag):
+@pytest.mark.parametrize("N,flag,T", [(1029, "some", 1), (515, "none", 1), (64, "all", 3), (7, "some", 10), (300, "some", 2)])
+def test_reset_with_reset_buf_as_its_own_mask_equals_the_copied_mask_bitwise(N, flag, T):
     """phc_reset_envs reads each mask byte once before it clears reset_buf, so the flags can select the envs
     directly (reset_done without AMP); same buffers, bit for bit, as with a copy of the flags, and with nothing
     flagged nothing is written at all."""
     lib_data, clock, state = make_case_cpu(num_envs=N, num_motions=max(4, N // 3), seed=131, max_progress=30,
                                            fps_choices=(30, 60), min_frames=40, max_frames=200)  # fmt: skip
-    a, b = env_from(lib_data, clock, state), env_from(lib_data, clock, state)
+    a, b = env_from(lib_data, clock, state, time_steps=T), env_from(lib_data, clock, state, time_steps=T)
     gen = torch.Generator().manual_seed(11)
     flags = torch.rand(N, generator=gen) < 0.3 if flag == "some" else torch.full((N,), flag == "all")
     phase = cuda(torch.rand(N, generator=gen))
@@ -845,6 +845,10 @@ def test_reset_with_reset_buf_as_its_own_mask_equals_the_copied_mask_bitwise(N, 
             assert torch.equal(getattr(b, k), v), k
     else:
         assert not torch.equal(b.obs_buf, before["obs_buf"])
+        # the rows the reset kernel wrote are, bit for bit, what the step kernel computes from the new state and clock
+        rows = b.obs_buf[cuda(flags)].clone()
+        b.post_physics_step(advance_progress=False)
+        assert torch.equal(b.obs_buf[cuda(flags)], rows)
 
 
 @pytest.mark.parametrize("N,flag", [(1029, "some"), (515, "none"), (37, "all"), (5, "some")])

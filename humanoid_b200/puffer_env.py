@@ -47,9 +47,12 @@ class PHCPufferEnv:
         self.amp_obs = None
         self.tick = 0
         # fused=True: the bookkeeping below is done by the env's step kernel (PhcStepArgs.ep_*), one launch fewer per
-        # step; the sums collect in 32 accumulators that mean_and_log folds
+        # step; the sums collect in per-block accumulators that mean_and_log folds
         self.fused = bool(fused)
-        self._ep_sums = torch.zeros((32, _cabi.EPISODE_SUM_COLS), dtype=torch.float64, device=dev) if fused else None
+        # one accumulator row per block of the step kernel (4 envs): fp64 atomics on one 128-byte line serialise in L2,
+        # and with 32 rows the 9 sums of 32 blocks each queued on one line at the tail of every step
+        buckets = max(32, min(4096, (N + 3) // 4))
+        self._ep_sums = torch.zeros((buckets, _cabi.EPISODE_SUM_COLS), dtype=torch.float64, device=dev) if fused else None
         if fused:
             env.set_episode_buffers(dict(terminals=self.terminals, truncations=self.truncations, masks=self.masks,
                                          episode_returns=self.episode_returns, episode_lengths=self.episode_lengths,

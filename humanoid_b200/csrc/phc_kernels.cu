@@ -1778,17 +1778,17 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
             if (i == 4 + p.power_col) v[i] = pr;
         }
       }
+      // the four k == 0 lanes (0, 4, 8, 12) -> lane i keeps the sum of column i, then ONE atomic instruction for the row
+      float mine = 0.0f;
 #pragma unroll
-      for (int i = 0; i < EP_SUM_COLS; ++i) {  // the four k == 0 lanes (0, 4, 8, 12) -> lane 0
+      for (int i = 0; i < EP_SUM_COLS; ++i) {
         v[i] += __shfl_xor_sync(0xffffffffu, v[i], 4);
         v[i] += __shfl_xor_sync(0xffffffffu, v[i], 8);
+        const float tot = __shfl_sync(0xffffffffu, v[i], 0);
+        if (tid == i) mine = tot;
       }
-      if (tid == 0) {
-        double* acc = p.ep_sums + (int64_t)(blockIdx.x % p.ep_buckets) * EP_SUM_COLS;
-#pragma unroll
-        for (int i = 0; i < EP_SUM_COLS; ++i)
-          if (i < 4 + p.ep_raw_cols && v[i] != 0.0f) atomicAdd(acc + i, (double)v[i]);
-      }
+      if (tid < 4 + p.ep_raw_cols && mine != 0.0f)
+        atomicAdd(p.ep_sums + (int64_t)(blockIdx.x % p.ep_buckets) * EP_SUM_COLS + tid, (double)mine);
     }
   }
 

@@ -992,9 +992,8 @@ __device__ __forceinline__ RefBody blend_ref(const StepSmem<EPB>& S, int q, int 
   return r;
 }
 
-// `sel`: -1 = select envs by p.env_mask (NULL = all); 0 / 1 = the caller has already read this thread's mask byte
 template <int EPB>
-__device__ __forceinline__ void step_body(const StepParams& p, const int sel) {
+__global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<EPB>& S = *reinterpret_cast<StepSmem<EPB>*>(smem_raw);
   constexpr int NT = EPB * J24;
@@ -1002,7 +1001,7 @@ __device__ __forceinline__ void step_body(const StepParams& p, const int sel) {
   const int e = tid / J24, b = tid % J24;
   const int64_t env0 = (int64_t)blockIdx.x * EPB;
   const int64_t env = env0 + e;
-  const bool valid = env < p.n && (sel >= 0 ? sel != 0 : (!p.env_mask || p.env_mask[env]));
+  const bool valid = env < p.n && (!p.env_mask || p.env_mask[env]);
   const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
   const int T = p.T;
   if (b == 0) S.act[e] = valid;  // read after the first barrier
@@ -1238,11 +1237,6 @@ __device__ __forceinline__ void step_body(const StepParams& p, const int sel) {
     }
   }
   cp_async_wait_all();
-}
-
-template <int EPB>
-__global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
-  step_body<EPB>(p, -1);
 }
 
 // Reset of the flagged envs and their observations in ONE launch (phc_reset_envs).  A thread scatters the new state

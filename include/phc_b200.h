@@ -270,14 +270,16 @@ typedef struct PhcStepArgs {
    * form and documents the semantics) done by the step itself, off when ep_returns is NULL.  The T = 1 kernel does it in
    * its reduction warp; the other kernels are followed by one small launch.  The sums go to ep_buckets accumulators
    * of PHC_EPISODE_SUM_COLS doubles {episodes finished, sum of returns, sum of lengths, truncations, sum over envs of
-   * reward_raw[:, c]}, folded by phc_episode_fold when the caller logs.                                            */
+   * reward_raw[:, c]}, folded by phc_episode_fold when the caller logs.  A block of the T = 1 kernel sums its four
+   * envs in fp32 (counts and lengths exact) and adds the row of bucket blockIdx % ep_buckets with one atomic
+   * instruction; ceil(n / 4) buckets give every block its own row.                                                */
   uint8_t* ep_terminals;                 /* [n] out */
   uint8_t* ep_truncations;               /* [n] out */
   uint8_t* ep_masks;                     /* [n] out */
   float* ep_returns;                     /* [n] in/out */
   int32_t* ep_lengths;                   /* [n] in/out */
   double* ep_sums;                       /* [ep_buckets][PHC_EPISODE_SUM_COLS], zeroed by the caller once */
-  int32_t ep_buckets;                    /* >= 1 (32 is plenty: see obs_moments_buckets) */
+  int32_t ep_buckets;                    /* 1 .. 4096; ceil(n / 4) = one row per block    */
   int32_t ep_raw_cols;                   /* columns of reward_raw that are logged, <= 8 */
 } PhcStepArgs;
 

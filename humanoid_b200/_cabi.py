@@ -318,6 +318,7 @@ SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     ),
     "phc_peer_reduce_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "phc_peer_reduce_resync": (C.c_int, [C.c_void_p]),
     "phc_peer_reduce_destroy": (None, [C.c_void_p]),
 }
 

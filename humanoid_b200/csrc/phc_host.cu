@@ -5,7 +5,7 @@
 // kernel writes obs rows, rewards and flags straight into the caller's host buffers with its
 // bulk stores (no device->host DMA descriptors, no device staging of outputs), so the two
 // directions of the link overlap.  Used whenever cudaPointerGetAttributes says every buffer is
-// device-accessible.
+// pinned / managed host memory mapped at its own address (device pointers are rejected: PHC_ERR_UNSUPPORTED).
 //
 // Staged path (any pageable buffer): chunked copy pipeline, below.
 //
@@ -67,14 +67,24 @@ struct PhcHostStep {
   int seen_direct = -1;
 };
 
-#define HOST_CUDA(ctx, call)            \
-  do {                                  \
-    cudaError_t e__ = (call);           \
-    if (e__ != cudaSuccess) {           \
-      if (ctx) (ctx)->last_cuda = e__;  \
-      return PHC_ERR_CUDA;              \
-    }                                   \
+// After the first enqueue an early return must not leave kernels writing into the caller's (mapped) buffers or
+// into the staging buffers the next call reuses: every error path drains the three streams first.
+static int host_fail(PhcHostStep* c, int rc, cudaError_t e);
+#define HOST_CUDA(ctx, call)                                        \
+  do {                                                              \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess) return host_fail((ctx), PHC_ERR_CUDA, e__); \
   } while (0)
+
+static int host_fail(PhcHostStep* c, int rc, cudaError_t e) {
+  if (c) {
+    if (e != cudaSuccess) c->last_cuda = e;
+    for (auto& s : c->streams)
+      if (s) (void)cudaStreamSynchronize(s);
+    (void)cudaGetLastError();
+  }
+  return rc;
+}
 
 extern "C" {
 
@@ -208,7 +218,9 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
         if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess) {
           (void)cudaGetLastError();
           direct = 0;
-        } else if (at.type == cudaMemoryTypeUnregistered || at.devicePointer != ptrs[i]) {
+        } else if (at.type == cudaMemoryTypeDevice) {
+          return PHC_ERR_UNSUPPORTED;  // this entry point takes HOST buffers (the clock arrays are memcpy'd by the CPU)
+        } else if ((at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged) || at.devicePointer != ptrs[i]) {
           direct = 0;  // pageable, or mapped at a different device address
         }
       }
@@ -233,7 +245,7 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
       for (int64_t lo = 0; lo < n; lo += per, ++ci) {
         const int64_t m = (n - lo) < per ? (n - lo) : per;
         const Layout L = layout(m);
-        if (coff + L.clock_bytes > c->pack_capacity) return PHC_ERR_SHAPE;
+        if (coff + L.clock_bytes > c->pack_capacity) return host_fail(c, PHC_ERR_SHAPE, cudaSuccess);
         cudaStream_t s = c->streams[ci % kStreams];
         float* st = c->d_state + lo * kStateFloats;
         unsigned char* hc = c->h_clock + coff;
@@ -276,7 +288,7 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
         k.obs_moments = nullptr;
         // the advanced progress goes straight into the caller's buffer too (no device->host copy at the tail)
         int rc = step_fused_mirrored(c->lib, &k, m, s, a->progress_buf + lo);
-        if (rc) return rc;
+        if (rc) return host_fail(c, rc, cudaSuccess);
         coff += L.clock_bytes;
       }
       for (int i = 0; i < kStreams; ++i) HOST_CUDA(c, cudaStreamSynchronize(c->streams[i]));
@@ -291,7 +303,8 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
     const int64_t lo = bounds[ci], m = bounds[ci + 1] - bounds[ci];
     if (m <= 0) continue;
     const Layout L = layout(m);
-    if (coff + L.clock_bytes > c->pack_capacity || ooff + L.out_bytes > c->pack_capacity) return PHC_ERR_SHAPE;
+    if (coff + L.clock_bytes > c->pack_capacity || ooff + L.out_bytes > c->pack_capacity)
+      return host_fail(c, PHC_ERR_SHAPE, cudaSuccess);
     cudaStream_t s = c->streams[ci % kStreams];
     // pack the chunk's clock on the host (tens of KB), then ONE transfer
     unsigned char* hc = c->h_clock + coff;
@@ -335,7 +348,7 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
     k.terminate_buf = dout + L.term;
     k.obs_moments = nullptr;
     int rc = phc_step_fused(c->lib, &k, m, s);
-    if (rc) return rc;
+    if (rc) return host_fail(c, rc, cudaSuccess);
     // the advanced progress rides back with the scalar outputs
     HOST_CUDA(c, cudaMemcpyAsync(dout + L.oprog, dc + L.prog, (size_t)m * 2, cudaMemcpyDeviceToDevice, s));
     HOST_CUDA(c, cudaMemcpyAsync(a->obs_buf + lo * c->obs_dim, c->d_obs + lo * c->obs_dim,

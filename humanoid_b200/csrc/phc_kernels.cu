@@ -602,7 +602,7 @@ __device__ __forceinline__ void reward_partials(Vec3 pos, Quat rot, Vec3 vel, Ve
 
 // one env's reward from the four per-body rows (ATen row-sum order), common.py:298-320
 __device__ __forceinline__ float reward_term(const float* row, int J, float k) {
-  float d = row_sum8(row, J) / (float)J;
+  float d = aten_row_sum(row, J) / (float)J;
   return expf((-k) * d);
 }
 
@@ -660,7 +660,7 @@ __global__ void reset_kernel(PhcView pos, PhcView ref, int R, const int16_t* __r
     if (early) {
       const float* d = sm + e * R;
       if (use_mean) {
-        fallen = (row_sum8(d, R) / (float)R) > term_dist[0];
+        fallen = (aten_row_sum(d, R) / (float)R) > term_dist[0];
       } else {
         for (int j = 0; j < R; ++j) fallen = fallen || (d[j] > term_dist[j]);
       }
@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
           if (p.reset_mask >> j & 1u) sel[m++] = d[j];
         // threshold of the first selected body: termination_distance[reset_ids][0] (common.py:343)
         int first = __ffs(p.reset_mask) - 1;
-        fallen = m > 0 && (row_sum8(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+        fallen = m > 0 && (aten_row_sum(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
       } else {
 #pragma unroll
         for (int j = 0; j < J24; ++j)
@@ -1359,7 +1359,10 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   // frames and precomputed blends are simply selected, otherwise the env's leader lane redoes
   // its blends and copies.  No caller contract is needed: every dependent read (sim state,
   // progress) and every write happens after the wait.
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  // A launch that may not speculate at all (first_wave_blocks == 0: the library was just (re)written on this stream,
+  // or the I/O is mapped host memory) releases its dependents only AFTER its own wait: the next step's pre-wait
+  // reads of the library are then ordered behind everything this launch was ordered behind.
+  if (p.first_wave_blocks > 0) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   // blocks beyond the first wave start after the dependency is long resolved: nothing to overlap
   const bool speculate = blockIdx.x < (unsigned)p.first_wave_blocks;
   if (tid < 32) {
@@ -1421,6 +1424,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
                    : "memory");
     }
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    if (p.first_wave_blocks <= 0) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     PHC_STAMP(2);
     // -- dependent data: one round of clock loads, the sim rows' copy issued under them
     int prog_in = 0;
@@ -1726,7 +1730,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
           for (int j = 0; j < J24; ++j)
             if (p.reset_mask >> j & 1u) sel[m++] = S.part[4][le][j];
           const int first = __ffs(p.reset_mask) - 1;
-          fallen = m > 0 && (row_sum8(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+          fallen = m > 0 && (aten_row_sum(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
         } else {
           fallen = S.fallen[le] != 0;
         }
@@ -2047,7 +2051,7 @@ __global__ void __launch_bounds__(MULTI_EPB* J24, 5) step_multi_kernel(const Ste
           for (int j = 0; j < J24; ++j)
             if (p.reset_mask >> j & 1u) sel[m++] = S.part[4][le][j];
           const int first = __ffs(p.reset_mask) - 1;
-          fallen = m > 0 && (row_sum8(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+          fallen = m > 0 && (aten_row_sum(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
         } else {
           fallen = S.fallen[le] != 0;
         }
@@ -2310,7 +2314,7 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
           for (int j = 0; j < J24; ++j)
             if (p.reset_mask >> j & 1u) sel[m++] = S.part[4][le][j];
           const int first = __ffs(p.reset_mask) - 1;
-          fallen = m > 0 && (row_sum8(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+          fallen = m > 0 && (aten_row_sum(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
         } else {
           fallen = S.fallen[le] != 0;
         }
@@ -2632,6 +2636,11 @@ static int launch_step(Kern kern, size_t smem, int epb, const StepParams& p, cud
 struct PhcLib {
   LibDev d;
   float* packed_owned = nullptr;
+  // The fast step kernel reads clip metadata and frame rows BEFORE griddepcontrol.wait (it treats the library as
+  // immutable).  A launch that (re)writes the library on the same stream — phc_lib_pack, phc_motion_build followed
+  // by phc_lib_pack, or the caller's own kernels before phc_lib_create — is only ordered before the step's
+  // post-wait reads, so the first fused step after phc_lib_create / phc_lib_pack runs without the speculation.
+  mutable int unspeculated_steps = 1;
 };
 
 extern "C" {
@@ -2689,6 +2698,7 @@ int phc_lib_pack(PhcLib* lib, phc_stream_t stream) {
   int rc = launch_status();
   if (rc) return rc;
   lib->d.packed = lib->packed_owned;
+  lib->unspeculated_steps = 1;  // the next fused step must not read the table before its dependency wait
   return PHC_OK;
 }
 
@@ -3069,6 +3079,10 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
       first_wave[dev] = sms * (per_sm > 0 ? per_sm : 1);
     }
     p.first_wave_blocks = (g_pdl && !(args->flags & PHC_STEP_MAPPED_HOST_IO)) ? first_wave[dev] : 0;
+    if (lib->unspeculated_steps > 0) {  // library (re)written since the last step: nothing may be read before the wait
+      p.first_wave_blocks = 0;
+      --lib->unspeculated_steps;
+    }
     static bool attr_fast4_norm[64] = {}, attr_fast4_ep[64] = {}, attr_fast4_norm_ep[64] = {};
     if (p.obs_norm && p.ep_returns)
       return launch_step(step_fast_kernel<4, 8, true, true>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4_norm_ep[dev], g_pdl != 0);

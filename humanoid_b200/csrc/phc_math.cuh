@@ -264,22 +264,36 @@ __device__ __forceinline__ float mean_sq3(Vec3 d) {
   return __fmaf_rn(d.z, d.z, __fmaf_rn(d.y, d.y, d.x * d.x)) * 0.333333343267440796f;
 }
 
-// ATen CPU sum over a contiguous row of floats (vectorised inner reduction, measured on torch
-// 2.11): 8 lane accumulators filled round-robin (lane l gets v[l], v[l+8], ..), then combined
-// left to right.  Exact for n = 24; for n <= 7 it degenerates to the sequential sum ATen uses.
-// The lane loop is fully unrolled so the accumulators stay in registers.
-__device__ __forceinline__ float row_sum8(const float* v, int n) {
+// ATen CPU sum over a contiguous row of n floats (aten/src/ATen/native/cpu/SumKernel.cpp, the AVX2 build that torch
+// dispatches to on AVX2 and AVX-512 hosts alike; checked against torch 2.11 for every n in 1..48, tests/test_oracle_c.py):
+//   n >= 8  vectorized_inner_sum: the n / 8 full vectors are added lane-wise in order (lane l = v[l] + v[l+8] + ..),
+//           then the scalar accumulator takes the n % 8 tail elements FIRST, in order, and the 8 lanes after them;
+//   n <  8  scalar_inner_sum -> row_sum with four partials: p[k] = v[k] (k < 4), the elements from 4 on go to p[0],
+//           then ((p0 + p1) + p2) + p3.
+// Valid for n <= 39 (from 5 vectors on ATen's four-way unrolling reorders the lane sums).
+__device__ __forceinline__ float aten_row_sum(const float* v, int n) {
+  if (n < 8) {
+    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;  // 0 + x is exact
+    if (n >= 4) {
+      p0 = v[0], p1 = v[1], p2 = v[2], p3 = v[3];
+      for (int i = 4; i < n; ++i) p0 += v[i];
+    } else {
+      for (int i = 0; i < n; ++i) p0 += v[i];
+    }
+    return ((p0 + p1) + p2) + p3;
+  }
+  const int nv = n >> 3;
   float acc[8];
 #pragma unroll
-  for (int l = 0; l < 8; ++l) acc[l] = 0.0f;
-  for (int base = 0; base < n; base += 8) {
+  for (int l = 0; l < 8; ++l) acc[l] = v[l];
+  for (int i = 1; i < nv; ++i) {
 #pragma unroll
-    for (int l = 0; l < 8; ++l)
-      if (base + l < n) acc[l] += v[base + l];  // 0 + x is exact
+    for (int l = 0; l < 8; ++l) acc[l] += v[i * 8 + l];
   }
-  float s = acc[0];
+  float s = 0.0f;
+  for (int k = nv * 8; k < n; ++k) s += v[k];
 #pragma unroll
-  for (int l = 1; l < 8; ++l) s = s + acc[l];
+  for (int l = 0; l < 8; ++l) s = s + acc[l];
   return s;
 }
 

@@ -16,8 +16,11 @@
 // Two slots alternate by epoch parity: a rank can only reach epoch e+2 (and overwrite slot e&1) after
 // every peer has published e+1, which each does (stream order) after its epoch-e kernel finished
 // reading.  The epoch lives in device memory, so the launch is CUDA-graph capturable.  A peer that
-// never shows up makes the wait time out: the kernel records PHC_PEER_TIMEOUT in the context's
-// status word and leaves the running buffers untouched instead of hanging the GPU.
+// never shows up makes the wait time out: ONE block decides for the whole launch, so on a timeout the kernel
+// records PHC_PEER_TIMEOUT in the context's status word and touches nothing — not the running buffers, not the
+// caller's partials, not count / epoch — instead of hanging the GPU.  A timed-out rank has published its flag for
+// an epoch its peers may or may not complete, so the group is out of step afterwards: every rank calls
+// phc_peer_reduce_resync (between two host barriers) before the next update.
 #include <cstdint>
 #include <cstring>
 #include <new>
@@ -47,6 +50,8 @@ struct PeerParams {
   unsigned long long* epoch;  // device: number of completed reductions
   unsigned int* ticket;       // device: [0] publish ticket, [1] finish ticket
   int* status;                // device: 0 ok, PHC_PEER_TIMEOUT
+  unsigned long long* decision;  // device: (launch sequence number << 1) | ok, written by block 0
+  unsigned long long* seq;       // device: launches completed (timed-out ones included)
   unsigned long long timeout_ns;
 };
 
@@ -72,10 +77,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) { st_release_sys(p, v); }
+
 __global__ void __launch_bounds__(kThreads) peer_reduce_update_kernel(const PeerParams p) {
   __shared__ int s_ok;
   const int64_t C = p.cols, L = 2 * C + 1;
-  const unsigned long long e = *p.epoch + 1;  // *p.epoch is only advanced by the last block, at the very end
+  // *p.epoch and *p.seq are only advanced by the last block of a launch, at its very end: every block reads the same
+  const unsigned long long e = *p.epoch + 1;
+  const unsigned long long seq = *p.seq + 1;  // launches so far + 1, timed-out ones included
   const int slot = (int)(e & 1);
   double* mine = p.peers[p.rank] + slot * p.slot_stride;
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
@@ -90,25 +99,35 @@ __global__ void __launch_bounds__(kThreads) peer_reduce_update_kernel(const Peer
       __threadfence_system();
       st_release_sys(flag_ptr(p.peers[p.rank], p.slot_stride, slot), e);
     }
-    // 2. wait for every rank's flag of this epoch (own included: other blocks of this grid wrote part of it)
+    // 2. ONE decision per launch: block 0 waits for every rank's flag of this epoch (own included: other blocks of
+    // this grid wrote part of it) and publishes ok / timed out; the other blocks take its verdict, so either every
+    // block blends and clears its columns or none does.  All blocks are co-resident (<= 32 blocks).
     int ok = 1;
-    const unsigned long long t0 = global_ns();
-    for (int r = 0; r < p.world && ok; ++r) {
-      const unsigned long long* f = flag_ptr(p.peers[r], p.slot_stride, slot);
-      while (ld_acquire_sys(f) != e) {
-        if (global_ns() - t0 > p.timeout_ns) {
-          ok = 0;
-          break;
+    if (blockIdx.x == 0) {
+      const unsigned long long t0 = global_ns();
+      for (int r = 0; r < p.world && ok; ++r) {
+        const unsigned long long* f = flag_ptr(p.peers[r], p.slot_stride, slot);
+        while (ld_acquire_sys(f) != e) {
+          if (global_ns() - t0 > p.timeout_ns) {
+            ok = 0;
+            break;
+          }
+          __nanosleep(200);
         }
-        __nanosleep(200);
       }
+      st_release_sys_u64(p.decision, seq * 2 + (unsigned long long)ok);
+    } else {
+      unsigned long long d;
+      while (((d = ld_acquire_sys(p.decision)) >> 1) != seq) __nanosleep(100);
+      ok = (int)(d & 1ull);
     }
     s_ok = ok;
   }
   __syncthreads();
   const bool ok = s_ok != 0;
 
-  // 3 + 4. sum in rank order, blend (policies/running_norm.py:23-34)
+  // 3 + 4. sum in rank order, blend (policies/running_norm.py:23-34).  On a timeout nothing is touched: not the
+  // running buffers, not the caller's partials, not count / epoch.
   if (ok) {
     double n = 0.0;
     for (int r = 0; r < p.world; ++r) n += ld_sys(p.peers[r] + slot * p.slot_stride + 2 * C);
@@ -134,8 +153,9 @@ __global__ void __launch_bounds__(kThreads) peer_reduce_update_kernel(const Peer
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(&p.ticket[1], 1u) == gridDim.x - 1) {  // every block has read count and the epoch
+    if (atomicAdd(&p.ticket[1], 1u) == gridDim.x - 1) {  // every block has read count, the epoch and the sequence number
       p.ticket[1] = 0;
+      *p.seq = seq;
       if (ok) {
         *p.count = *p.count + 1.0f;
         *p.epoch = e;
@@ -246,6 +266,8 @@ int phc_running_norm_update_peers(PhcPeerReduce* c, double* sums, const double* 
   p.epoch = c->epoch;
   p.ticket = reinterpret_cast<unsigned int*>(c->epoch + 1);
   p.status = reinterpret_cast<int*>(c->epoch + 3);
+  p.decision = c->epoch + 4;
+  p.seq = c->epoch + 5;
   p.timeout_ns = c->timeout_ns;
   const int64_t L = 2 * c->cols + 1;
   int blocks = (int)((L + kThreads - 1) / kThreads);
@@ -268,6 +290,15 @@ int phc_peer_reduce_status(PhcPeerReduce* c, int64_t* epoch_out) {
     return status;
   }
   return PHC_OK;
+}
+
+int phc_peer_reduce_resync(PhcPeerReduce* c) {
+  if (!c) return PHC_ERR_NULL;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemset(c->mailbox, 0, c->mailbox_bytes);  // both slots and both epoch flags
+  if (e == cudaSuccess) e = cudaMemset(c->epoch, 0, 64);                  // epoch, tickets, status, decision, sequence
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  return e == cudaSuccess ? PHC_OK : phc::record_cuda_error((int)e);
 }
 
 void phc_peer_reduce_destroy(PhcPeerReduce* c) {

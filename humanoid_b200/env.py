@@ -309,7 +309,7 @@ class HumanoidPHC:
             a.dof_vel_elem_stride = self._dof_vel.stride(1)
             a.rew_power_coef = self.rew_power_coef
             a.power_col = self.reward_raw.shape[1] - 1
-        self._step_args = (a, advance, keep)
+        self._step_args = (a, advance, keep, (self.flag_im_eval, self.use_power_reward, self.time_steps))
         return a
 
     @property
@@ -356,11 +356,27 @@ class HumanoidPHC:
         self.obs_normalizer = normalizer
         self._step_args = None
 
+    def _refresh_step_scalars(self, a):
+        """The cached ``PhcStepArgs`` keeps pointers and strides; everything a reference-style script may change by
+        plain attribute assignment between steps (``env.flag_im_eval = True``, ``env.rwd_specs[...] = ...``,
+        ``env.enable_early_termination``, ``env.dt``, the power-reward switches) is re-read on every step, as the
+        unfused ``_compute_*`` path does."""
+        a.use_mean = 1 if self.flag_im_eval else 0
+        a.enable_early_termination = 1 if self.enable_early_termination else 0
+        a.dt = self.dt
+        r = self._rwd_specs
+        a.rwd.k_pos, a.rwd.k_rot, a.rwd.k_vel, a.rwd.k_ang_vel = r["k_pos"], r["k_rot"], r["k_vel"], r["k_ang_vel"]
+        a.rwd.w_pos, a.rwd.w_rot, a.rwd.w_vel, a.rwd.w_ang_vel = r["w_pos"], r["w_rot"], r["w_vel"], r["w_ang_vel"]
+        a.rew_power_coef = self.rew_power_coef
+
     def post_physics_step(self, advance_progress: bool = True):
         """progress += 1; reward; reset; observations (humanoid_phc.py:138-149) — one launch."""
-        if self._step_args is None or self._step_args[1] != advance_progress:
-            self._build_step_args(advance_progress)
+        cached = self._step_args
+        if (cached is None or cached[1] != advance_progress or cached[3] != (self.flag_im_eval, self.use_power_reward,
+                                                                             self.time_steps)):  # fmt: skip
+            self._build_step_args(advance_progress)  # these three change which pointers the struct carries
         a = self._step_args[0]
+        self._refresh_step_scalars(a)
         _cabi.check(
             _cabi.load().phc_step_fused(
                 self._motion_lib.handle, C.byref(a), self.num_envs, _cabi.stream_ptr(self.device)

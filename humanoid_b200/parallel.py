@@ -104,6 +104,23 @@ class PeerReduce:
         _cabi.check(_cabi.load().phc_peer_reduce_status(self._handle, C.byref(done)), "phc_peer_reduce_status")
         return done.value
 
+    def resync(self, group=None, local: Optional[List["PeerReduce"]] = None) -> None:
+        """Collective recovery after a timeout (``phc_peer_reduce_resync``): host barrier, every rank clears its
+        mailbox / flags / epoch / status, host barrier.  ``local``: the ranks of one process (tests) instead of a
+        process group.  Partials that a timed-out launch did not consume stay with the caller."""
+        if local is not None:
+            for r in local:
+                with torch.cuda.device(r.device):
+                    _cabi.check(_cabi.load().phc_peer_reduce_resync(r._handle), "phc_peer_reduce_resync")
+            return
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if distributed:
+            dist.barrier(group=group)
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.load().phc_peer_reduce_resync(self._handle), "phc_peer_reduce_resync")
+        if distributed:
+            dist.barrier(group=group)
+
     def close(self):
         if getattr(self, "_handle", None):
             _cabi.load().phc_peer_reduce_destroy(self._handle)

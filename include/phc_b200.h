@@ -86,8 +86,11 @@ PHC_API void phc_lib_destroy(PhcLib* lib);
 /* (Re)build the library's packed frame table on `stream`: one 1248-B row per frame,
  * [gts 72 | grs 96 | gvs 72 | gavs 72] floats, owned by the handle (1248 B x F of HBM).  The
  * fused step's TMA fast path reads it; without it phc_step_fused uses the generic kernel on
- * the four reference tensors.  Call once after phc_lib_create and again if the caller rewrites
- * the frame tensors in place. */
+ * the four reference tensors.  Call once after phc_lib_create and again whenever the caller rewrites
+ * ANY library tensor in place (frames or per-clip metadata): the fast step kernel overlaps its prologue
+ * with the previous kernel on the stream and reads the library before that kernel has finished, so it
+ * must know when the library changed.  The first phc_step_fused after phc_lib_create / phc_lib_pack
+ * launches without that overlap and therefore sees every write ordered before it on the stream. */
 PHC_API int phc_lib_pack(PhcLib* lib, phc_stream_t stream);
 
 /* [n, J, C] fp32 view, innermost C contiguous; strides in elements. */
@@ -361,7 +364,8 @@ PHC_API int phc_action_to_pd_targets(const float* action, const float* pd_action
 /* ------------------------------------------------------------------------------------
  * Host-buffer pipeline around the fused step (the end-to-end call): chunked
  * H2D(sim state, clock) -> phc_step_fused -> D2H(obs, reward, flags) on internal streams.
- * All pointers in PhcHostStepArgs are HOST pointers (pinned for full speed).
+ * All pointers in PhcHostStepArgs are HOST pointers (pinned for full speed); a device pointer is refused with
+ * PHC_ERR_UNSUPPORTED.  On any error the internal streams are drained before the call returns.
  * ---------------------------------------------------------------------------------- */
 typedef struct PhcHostStep PhcHostStep;
 
@@ -415,8 +419,14 @@ PHC_API int phc_running_norm_update(float* running_mean, float* running_var, flo
  *                        blend into running_mean / running_var, count += 1, zero sums.
  *                        rows: device scalar if rows_dev != NULL, else the value `rows`.
  *                        Never synchronises; CUDA-graph capturable (the epoch lives on the device).
- *   status            -> synchronises; PHC_PEER_TIMEOUT if a launch gave up waiting (its update was
- *                        skipped), and the number of completed reductions.
+ *   status            -> synchronises; PHC_PEER_TIMEOUT if a launch gave up waiting, and the number of completed
+ *                        reductions.  The wait is decided ONCE per launch: a timed-out launch touches neither
+ *                        running_mean / running_var nor sums, count or the epoch.
+ *   resync            -> after a timeout the ranks are out of step (this rank published an epoch its peers may or
+ *                        may not have completed).  Collective recovery: host barrier, every rank calls resync
+ *                        (synchronises its device; clears its mailbox, flags, epoch and status), host barrier.
+ *                        The caller re-broadcasts running_mean / running_var / count if a peer did complete the
+ *                        epoch this rank gave up on, and keeps its own partials (they were not consumed).
  * ---------------------------------------------------------------------------------- */
 #define PHC_PEER_MAX_WORLD 16
 #define PHC_PEER_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
@@ -430,6 +440,7 @@ PHC_API int phc_running_norm_update_peers(PhcPeerReduce* ctx, double* sums, cons
                                           float* running_mean, float* running_var, float* count,
                                           phc_stream_t stream);
 PHC_API int phc_peer_reduce_status(PhcPeerReduce* ctx, int64_t* completed_out /* may be NULL */);
+PHC_API int phc_peer_reduce_resync(PhcPeerReduce* ctx);
 PHC_API void phc_peer_reduce_destroy(PhcPeerReduce* ctx);
 
 /* RunningNorm.forward                                      policies/running_norm.py:15-20 */

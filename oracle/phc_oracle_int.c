@@ -41,11 +41,49 @@ void phc_oracle_sample_time(int64_t n, const float* phase, const float* motion_l
   }
 }
 
-/* compute_humanoid_im_reset, envs/common.py:325-364 (use_mean = False branch and the use_mean
- * branch's distances).  pos / ref are dense [n, R, 3]; pass_time, reset, terminated are bytes. */
+/* torch.sum(x, dim=-1) of a contiguous row of n floats on ATen CPU (aten/src/ATen/native/cpu/SumKernel.cpp, the
+ * AVX2 build torch dispatches to on AVX2 and AVX-512 hosts):
+ *   n >= 8: vectorized_inner_sum — the n / 8 full 8-lane vectors are added lane-wise (row_sum: four interleaved
+ *           vector partials, combined 0+1+2+3), the scalar accumulator then takes the n % 8 tail elements in order
+ *           and the 8 lanes after them;
+ *   n <  8: scalar_inner_sum — row_sum with four scalar partials. */
+float phc_oracle_row_sum(const float* v, int32_t n) {
+  if (n < 8) {
+    float p[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const int32_t si = n / 4;
+    for (int32_t i = 0; i < si; ++i)
+      for (int k = 0; k < 4; ++k) p[k] += v[i * 4 + k];
+    for (int32_t i = si * 4; i < n; ++i) p[0] += v[i];
+    for (int k = 1; k < 4; ++k) p[0] += p[k];
+    return p[0];
+  }
+  const int32_t nv = n / 8, si = nv / 4;
+  float part[4][8] = {{0}};
+  for (int32_t i = 0; i < si; ++i)
+    for (int k = 0; k < 4; ++k)
+      for (int l = 0; l < 8; ++l) part[k][l] += v[(i * 4 + k) * 8 + l];
+  for (int32_t i = si * 4; i < nv; ++i)
+    for (int l = 0; l < 8; ++l) part[0][l] += v[i * 8 + l];
+  for (int k = 1; k < 4; ++k)
+    for (int l = 0; l < 8; ++l) part[0][l] += part[k][l];
+  float acc = 0.0f;
+  for (int32_t k = nv * 8; k < n; ++k) acc += v[k];
+  for (int l = 0; l < 8; ++l) acc += part[0][l];
+  return acc;
+}
+
+void phc_oracle_row_sums(int64_t rows, int32_t n, const float* x, float* out) {
+  for (int64_t i = 0; i < rows; ++i) out[i] = phc_oracle_row_sum(x + i * n, n);
+}
+
+/* compute_humanoid_im_reset, envs/common.py:325-364.  pos / ref are dense [n, R, 3] (the caller's gather of the
+ * reset bodies, humanoid_phc.py:1321-1322); pass_time, reset, terminated are bytes.
+ *   use_mean == 0: any_b(|p_b - r_b| > term_dist[b])                       (:348-350)
+ *   use_mean != 0: mean_b |p_b - r_b| > term_dist[0], mean = row sum / R   (:343-346) */
 void phc_oracle_im_reset(int64_t n, int32_t R, const float* pos, const float* ref, const int16_t* progress,
-                         const uint8_t* pass_time, const float* term_dist, int32_t early, uint8_t* reset,
-                         uint8_t* terminated, float* dist_out /* [n,R] or NULL */) {
+                         const uint8_t* pass_time, const float* term_dist, int32_t early, int32_t use_mean,
+                         uint8_t* reset, uint8_t* terminated, float* dist_out /* [n,R] or NULL */) {
+  float d[64];
   for (int64_t i = 0; i < n; ++i) {
     int fallen = 0;
     for (int32_t b = 0; b < R; ++b) {
@@ -53,10 +91,11 @@ void phc_oracle_im_reset(int64_t n, int32_t R, const float* pos, const float* re
       const float* r = ref + (i * R + b) * 3;
       const float x = p[0] - r[0], y = p[1] - r[1], z = p[2] - r[2];
       /* torch.norm(dim=-1) over 3 on ATen CPU: sqrt(fma(z,z,fma(y,y,x*x))) */
-      const float d = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
-      if (dist_out) dist_out[i * R + b] = d;
-      if (d > term_dist[b]) fallen = 1;
+      d[b] = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+      if (dist_out) dist_out[i * R + b] = d[b];
+      if (!use_mean && d[b] > term_dist[b]) fallen = 1;
     }
+    if (use_mean) fallen = (phc_oracle_row_sum(d, R) / (float)R) > term_dist[0];
     if (!early) fallen = 0;
     if (!(progress[i] > 1)) fallen = 0; /* has_fallen *= progress_buf > 1 (:353) */
     terminated[i] = (uint8_t)fallen;

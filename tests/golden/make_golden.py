@@ -122,6 +122,41 @@ def reference_step(lib, state, clock, term_dist, time_steps=1, reset_body_ids=No
     return out
 
 
+def case_reset_mean():
+    """compute_humanoid_im_reset(use_mean=True) (PHC/envs/common.py:343-346) on rows whose mean distance sits within
+    a few ulps of the threshold: the flag then depends on the ASSOCIATION of ATen's row sum, which is what the CUDA
+    kernels and oracle/phc_oracle_int.c have to reproduce.  One block of rows per reset-body count R."""
+    g = torch.Generator().manual_seed(21)
+    thr = 0.15
+    arrays = {"in.threshold": np.float32(thr), "in.rs": np.asarray([1, 3, 4, 5, 6, 7, 8, 9, 12, 15, 16, 17, 20, 23, 24])}
+    for R in arrays["in.rs"].tolist():
+        n = 192
+        ref = torch.randn(n, R, 3, generator=g)
+        delta = torch.randn(n, R, 3, generator=g) * 0.1
+        for _ in range(3):  # rescale so that the mean distance lands on the threshold to within rounding
+            m = torch.norm((ref + delta) - ref, dim=-1).mean(dim=-1)
+            delta = delta * (thr / m)[:, None, None]
+        # spread the rows over the few floats either side of the threshold
+        delta = delta * (1.0 + torch.randint(-2, 4, (n,), generator=g).float() * 6e-8)[:, None, None]
+        pos = ref + delta
+        progress = torch.full((n,), 5, dtype=torch.int16)
+        progress[::17] = 1  # has_fallen *= progress_buf > 1
+        pass_time = torch.zeros(n, dtype=torch.bool)
+        pass_time[::13] = True
+        term_dist = torch.full((R,), thr, dtype=torch.float32)
+        reset, term = ref_common.compute_humanoid_im_reset(
+            torch.ones(n, dtype=torch.bool), progress, torch.zeros(n, R, 3), torch.zeros(4, dtype=torch.long),
+            pos.clone(), ref.clone(), pass_time, True, term_dist, True,
+        )  # fmt: skip
+        mean = torch.norm(pos - ref, dim=-1).mean(dim=-1)
+        frac_on = float(((mean - thr).abs() <= 3e-8).float().mean())
+        print(f"  R={R}: terminated {float(term.float().mean()):.2f}, within 2 ulp of the threshold {frac_on:.2f}")
+        arrays.update({f"in.pos{R}": pos.numpy(), f"in.ref{R}": ref.numpy(), f"in.progress{R}": progress.numpy(),
+                       f"in.pass_time{R}": pass_time.numpy(), f"out.reset{R}": reset.numpy(),
+                       f"out.terminated{R}": term.numpy(), f"out.mean{R}": mean.numpy()})  # fmt: skip
+    save("reset_mean", arrays)
+
+
 def save(name, arrays):
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **arrays)
@@ -746,6 +781,7 @@ if __name__ == "__main__":
     case_flags()
     case_running_norm()
     case_sample_time()
+    case_reset_mean()
     case_amp_obs()
     case_episode()
     case_motion_build()

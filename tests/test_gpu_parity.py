@@ -252,16 +252,65 @@ def test_eval_mode_reset_vs_oracle():
     env.toggle_eval_mode()
     env.set_termination_distances(0.12)
     env.step()
-    mism = (env._terminate_buf.cpu() != o[4]).sum().item()
-    # the mean over 20 bodies is summed in a different association than ATen's: a flag
-    # may differ only when the mean is within 1 ulp of the threshold
-    assert mism <= 1, f"{mism} eval-mode termination flags differ"
+    # the mean over the 20 eval bodies is summed in ATen's association (phc_math.cuh aten_row_sum): flags are exact
+    assert_equal_exact(env._terminate_buf, o[4], "eval-mode terminated")
+    assert_equal_exact(env.reset_buf, o[3], "eval-mode reset")
     assert 0.05 < o[4].float().mean() < 0.95
     # extras["mpjpe"] (humanoid_phc.py:159-167): mean over all 24 bodies at the reward time
     t = synth.reward_time(clock, extra_steps=1)
     ref = O.OracleMotionLib(lib_data).get_motion_state(clock.sampled_motion_ids, t, clock.global_offset)
     want = (state[:, :, 0:3] - ref["rg_pos"]).norm(dim=-1).mean(dim=-1)
     assert_close(env.extras["mpjpe"], want, what="mpjpe", **OBS_TOL)
+
+
+def test_eval_mode_termination_on_threshold_rows_bit_exact(golden):
+    """compute_humanoid_im_reset(use_mean=True) through K5 on rows whose mean distance sits within a few ulps of the
+    threshold, for every reset-body count: the fixture is the reference's own output, every flag must be equal."""
+    g = golden("reset_mean")
+    thr = float(g.inp("threshold"))
+    for R in g.inp("rs").tolist():
+        pos, ref = cuda(g.inp(f"pos{R}")), cuda(g.inp(f"ref{R}"))
+        n = pos.shape[0]
+        got = compute_humanoid_im_reset(
+            torch.ones(n, dtype=torch.bool, device=DEV), cuda(g.inp(f"progress{R}")), None, None, pos, ref,
+            cuda(g.inp(f"pass_time{R}")), True, torch.full((R,), thr, device=DEV), True)  # fmt: skip
+        assert_equal_exact(got[1], g.out(f"terminated{R}"), f"terminated, R = {R}")
+        assert_equal_exact(got[0], g.out(f"reset{R}"), f"reset, R = {R}")
+
+
+@pytest.mark.parametrize("T,generic", [(1, False), (1, True), (3, False)], ids=["fast", "generic", "multi"])
+def test_eval_mode_fused_step_flags_on_threshold_rows_bit_exact(T, generic):
+    """The fused kernels' eval-mode test on envs posed so that the mean distance of the 20 eval bodies hugs the
+    threshold (to within a few floats either side, in the oracle's arithmetic): flags equal to the oracle's."""
+    from humanoid_b200 import _cabi
+
+    N, thr = 2048, 0.2
+    lib_data, clock, state = make_case_cpu(num_envs=N, num_motions=64, seed=131, max_progress=40)
+    eval_ids = torch.tensor([i for i in range(24) if i not in (4, 8, 18, 23)])
+    t = synth.reward_time(clock, extra_steps=1)
+    ref = O.OracleMotionLib(lib_data).get_motion_state(clock.sampled_motion_ids, t, clock.global_offset)["rg_pos"]
+    gen = torch.Generator().manual_seed(7)
+    delta = torch.randn(N, 24, 3, generator=gen) * 0.1
+    for _ in range(4):
+        m = torch.norm(((ref + delta) - ref)[:, eval_ids], dim=-1).mean(dim=-1)
+        delta = delta * (thr / m)[:, None, None]
+    delta = delta * (1.0 + torch.randint(-2, 4, (N,), generator=gen).float() * 6e-8)[:, None, None]
+    state = state.clone()
+    state[:, :, 0:3] = ref + delta
+    o = oracle_step(lib_data, clock, state, term=thr, reset_body_ids=eval_ids, use_mean=True, time_steps=T)
+    mean = torch.norm((state[:, :, 0:3] - ref)[:, eval_ids], dim=-1).mean(dim=-1)
+    assert ((mean - thr).abs() < 1e-7).float().mean() > 0.8, "rows should sit on the threshold"
+    assert 0.2 < o[4].float().mean() < 0.8
+    env = env_from(lib_data, clock, state, time_steps=T)
+    env.toggle_eval_mode()
+    env.set_termination_distances(thr)
+    _cabi.load().phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if generic else 0)
+    try:
+        env.step()
+    finally:
+        _cabi.load().phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+    assert_equal_exact(env._terminate_buf, o[4], "terminated")
+    assert_equal_exact(env.reset_buf, o[3], "reset")
 
 
 # ---------------------------------------------------------------------------------------
@@ -586,6 +635,66 @@ def test_speculation_miss_paths_do_not_change_results(regime):
         assert torch.equal(f.rew_buf, g.rew_buf) and torch.equal(f.reward_raw, g.reward_raw)
         assert torch.equal(f.reset_buf, g.reset_buf) and torch.equal(f._terminate_buf, g._terminate_buf)
         assert torch.equal(f.progress_buf, g.progress_buf)
+
+
+def test_library_rewritten_in_place_is_seen_by_the_next_step():
+    """The fast kernel reads clip metadata and frame rows before its dependency wait.  Rewriting the library in
+    place + repack() right before a step, on the same stream and without a sync, must still be seen: the first step
+    after phc_lib_pack launches without the speculation (and releases its dependents only after its own wait)."""
+    N = 4096
+    lib_data, clock, state = _gpu_case(N, N, seed=77, max_progress=30)
+    env = env_from(lib_data, clock, state)
+    for _ in range(3):  # steady state: speculating launches
+        env.progress_buf.copy_(clock.progress_buf)
+        env.step()
+    lib = env._motion_lib
+    env.progress_buf.copy_(clock.progress_buf)
+    # a long kernel in front, so that the rewrite is still in flight when the step's blocks become resident
+    big = torch.empty(1 << 26, dtype=torch.float32, device=DEV)
+    big.fill_(1.0)
+    lib.gts.add_(0.125)
+    lib.gvs.mul_(2.0)
+    lib.repack()
+    env.step()
+    env.step()  # the second step after the rewrite speculates again
+    got = [t.clone() for t in (env.obs_buf, env.rew_buf, env.reset_buf, env._terminate_buf)]
+    torch.cuda.synchronize()
+    # the same two steps on a fresh env over a fresh library built from the rewritten tensors
+    d2 = lib_data.as_dict()
+    d2["gts"], d2["gvs"] = lib.gts.clone(), lib.gvs.clone()
+    env2 = env_from(synth.MotionData(**d2), clock, state)
+    torch.cuda.synchronize()
+    env2.step()
+    env2.step()
+    for a, b, nm in zip(got, (env2.obs_buf, env2.rew_buf, env2.reset_buf, env2._terminate_buf), ("obs", "rew", "reset", "term")):
+        assert torch.equal(a, b), f"{nm}: the step after an in-place library rewrite used stale frames"
+
+
+def test_plain_attribute_assignment_is_honoured_by_the_fused_step():
+    """Reference-style scripts flip ``env.flag_im_eval`` / edit ``env.rwd_specs`` / ``enable_early_termination`` by
+    plain assignment; the cached step arguments must not hide that (the unfused path reads them every call)."""
+    lib_data, clock, state = _gpu_case(1024, 64, seed=91, max_progress=30)
+    env, ref = env_from(lib_data, clock, state), env_from(lib_data, clock, state)
+    env.step()  # builds and caches the step arguments
+    for e in (env, ref):
+        e.progress_buf.copy_(clock.progress_buf)
+        e.flag_im_eval = True
+        e.rwd_specs["k_pos"] = 50.0
+        e.rwd_specs["w_rot"] = 0.2
+        e.set_termination_distances(0.2)
+    env.step()
+    ref.post_physics_step_unfused()
+    assert torch.equal(env._terminate_buf, ref._terminate_buf) and torch.equal(env.reset_buf, ref.reset_buf)
+    assert torch.equal(env.rew_buf, ref.rew_buf) and torch.equal(env.obs_buf, ref.obs_buf)
+    assert env.extras["mpjpe"] is not None
+    for e in (env, ref):
+        e.progress_buf.copy_(clock.progress_buf)
+        e.flag_im_eval = False
+        e.enable_early_termination = False
+    env.step()
+    ref.post_physics_step_unfused()
+    assert torch.equal(env._terminate_buf, ref._terminate_buf) and not bool(env._terminate_buf.any())
+    assert torch.equal(env.reset_buf, ref.reset_buf)
 
 
 def test_env_reset_between_steps_is_seen_by_the_next_step():

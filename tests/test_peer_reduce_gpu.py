@@ -107,6 +107,43 @@ def test_missing_peer_times_out_instead_of_hanging():
     assert peers[0].status() == 0  # the status word is cleared once reported; nothing completed
 
 
+def test_timeout_then_resync_then_retry_gives_the_right_statistics():
+    """A timed-out launch decides once for all its blocks (nothing is half-updated), leaves the ranks out of step,
+    and phc_peer_reduce_resync puts the group back: the retried update equals the oracle on both ranks."""
+    from humanoid_b200 import _cabi
+    from oracle import phc_oracle as O
+
+    peers, rns, streams = _ranks(2, timeout_ms=50)
+    gen = torch.Generator().manual_seed(3)
+    xs = [torch.randn(100 + 57 * r, C, generator=gen) * 2 + 0.5 for r in range(2)]
+    sums = [rns[r].moments(xs[r].cuda()) for r in range(2)]
+    keep0 = sums[0].clone()
+    # one good epoch first, so that the failure happens at a non-zero epoch with both slots' history in place
+    for r in range(2):
+        with torch.cuda.stream(streams[r]):
+            peers[r].update(rns[r].running_mean, rns[r].running_var, rns[r].count, sums[r].clone(), xs[r].shape[0])
+    torch.cuda.synchronize()
+    m, v, c = O.running_norm_update(torch.zeros(1, C), torch.ones(1, C), torch.ones(1), torch.cat(xs))
+    before = (rns[0].running_mean.clone(), rns[0].running_var.clone(), float(rns[0].count))
+    peers[0].update(rns[0].running_mean, rns[0].running_var, rns[0].count, sums[0], xs[0].shape[0])  # rank 1 absent
+    with pytest.raises(_cabi.PhcError, match="peer"):
+        peers[0].status()
+    assert torch.equal(rns[0].running_mean, before[0]) and torch.equal(rns[0].running_var, before[1])
+    assert float(rns[0].count) == before[2] and torch.equal(sums[0], keep0), "a timed-out launch must touch nothing"
+    peers[0].resync(local=peers)
+    for r in reversed(range(2)):
+        with torch.cuda.stream(streams[r]):
+            peers[r].update(rns[r].running_mean, rns[r].running_var, rns[r].count, sums[r], xs[r].shape[0])
+    torch.cuda.synchronize()
+    m, v, c = O.running_norm_update(m, v, c, torch.cat(xs))
+    for r in range(2):
+        assert peers[r].status() == 1  # epochs restart after a resync
+        assert_close(rns[r].running_mean.cpu(), m, rtol=1e-5, atol=1e-6, what=f"mean after retry, rank {r}")
+        assert_close(rns[r].running_var.cpu(), v, rtol=1e-5, atol=1e-6, what=f"var after retry, rank {r}")
+        assert float(rns[r].count) == float(c) and float(sums[r].abs().max()) == 0.0
+    assert torch.equal(rns[0].running_mean, rns[1].running_mean) and torch.equal(rns[0].running_var, rns[1].running_var)
+
+
 def test_bad_arguments():
     from humanoid_b200 import _cabi
     from humanoid_b200.parallel import PeerReduce

@@ -17,6 +17,7 @@
 // transfer each through pinned staging buffers owned by the context (a DMA descriptor costs a
 // few microseconds regardless of size; 22 of them per chunk were half of the step time).  The
 // call returns when every output is in the caller's host memory.
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -65,6 +66,13 @@ struct PhcHostStep {
   // direct path: verdict cached per set of caller pointers
   const void* seen[11] = {};
   int seen_direct = -1;
+  // which output path pinned callers take: 0 = auto (time both over the first calls, keep the faster), 1 = direct
+  // (kernels post into the mapped host buffers), 2 = staged (copy-engine D2H).  PHC_HOST_PATH=auto|direct|staged.
+  int mode = 0;
+  int chosen = 0;  // auto: 0 while undecided
+  int calls = 0;
+  double t_path[3] = {0, 0, 0};
+  int n_path[3] = {0, 0, 0};
 };
 
 // After the first enqueue an early return must not leave kernels writing into the caller's (mapped) buffers or
@@ -120,6 +128,8 @@ int phc_host_step_create(const PhcLib* lib, int64_t max_envs, int32_t time_steps
   c->early = enable_early_termination;
   c->dt = dt;
   c->rwd = *rwd;
+  if (const char* m = getenv("PHC_HOST_PATH")) c->mode = !strcmp(m, "direct") ? 1 : !strcmp(m, "staged") ? 2 : 0;
+  if (getenv("PHC_HOST_STAGED")) c->mode = 2;
   const size_t n = (size_t)max_envs;
   // every chunk's packed region is padded so each sub-array starts 16-B aligned
   c->pack_capacity = n * 32 + (size_t)num_chunks * 6 * 64 + 4096;
@@ -207,12 +217,12 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
     return L;
   };
 
-  {  // ---- direct path: every buffer is mapped host (or device) memory ----------------------
+  {  // ---- can the direct path be used: every buffer is pinned / managed host memory mapped at its own address ----------------------
     const void* ptrs[11] = {a->state, a->progress_buf, a->motion_start_times, a->motion_start_times_offset,
                             a->global_offset, a->sampled_motion_ids, a->obs_buf, a->rew_buf, a->reward_raw,
                             a->reset_buf, a->terminate_buf};
     if (c->seen_direct < 0 || memcmp(ptrs, c->seen, sizeof(ptrs)) != 0) {
-      int direct = getenv("PHC_HOST_STAGED") ? 0 : 1;
+      int direct = 1;
       for (int i = 0; i < 11 && direct; ++i) {
         cudaPointerAttributes at{};
         if (cudaPointerGetAttributes(&at, ptrs[i]) != cudaSuccess) {
@@ -227,7 +237,8 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
       memcpy(c->seen, ptrs, sizeof(ptrs));
       c->seen_direct = direct;
     }
-    if (c->seen_direct == 1) {
+  }
+  auto direct_path = [&]() -> int {
       // Hybrid: everything INBOUND rides the host->device copy engine in a few chunks — the sim
       // rows directly from the caller's buffer, the five small clock arrays packed into one
       // transfer (SM-issued reads of system memory are 32-B PCIe round trips: 6 per block, ~70 us
@@ -293,9 +304,8 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
       }
       for (int i = 0; i < kStreams; ++i) HOST_CUDA(c, cudaStreamSynchronize(c->streams[i]));
       return PHC_OK;
-    }
-  }
-  // ---- staged path ---------------------------------------------------------------------------
+  };
+  auto staged_path = [&]() -> int {
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
 
   size_t coff = 0, ooff = 0;
@@ -373,6 +383,34 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
     ooff += L.out_bytes;
   }
   return PHC_OK;
+  };
+
+  // ---- which path ----------------------------------------------------------------------------
+  if (c->seen_direct != 1 || c->mode == 2) return staged_path();
+  if (c->mode == 1) return direct_path();
+  if (c->chosen) return c->chosen == 1 ? direct_path() : staged_path();
+  // auto: calls 0-2 warm both paths up, calls 3-8 alternate and are timed; the faster mean stays.  What decides is
+  // the machine: one GPU posts its obs rows into host memory faster than a copy engine drains a staging buffer;
+  // eight GPUs posting at once into one root complex may not (profiles/r2_e2e_floor.md).
+  const int k = c->calls++;
+  const int which = k < 2 ? 1 : k == 2 ? 2 : ((k & 1) ? 1 : 2);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = which == 1 ? direct_path() : staged_path();
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (rc == PHC_OK && k >= 3) {
+    c->t_path[which] += dt;
+    c->n_path[which] += 1;
+    if (c->n_path[1] >= 3 && c->n_path[2] >= 3)
+      c->chosen = (c->t_path[1] / c->n_path[1] <= c->t_path[2] / c->n_path[2]) ? 1 : 2;
+  }
+  return rc;
+}
+
+int phc_host_step_path(const PhcHostStep* c) {
+  if (!c) return 0;
+  if (c->seen_direct == 0 || c->mode == 2) return 2;
+  if (c->mode == 1) return 1;
+  return c->chosen;
 }
 
 }  // extern "C"

@@ -37,6 +37,7 @@ class RunningNorm(nn.Module):
         mapped into other processes) does not — call ``enable_peer_reduce`` again after loading."""
         state = self.__dict__.copy()
         state["_peers"] = None
+        state.pop("_payload", None)
         return state
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # :15-20
@@ -87,8 +88,22 @@ class RunningNorm(nn.Module):
         if getattr(self, "_peers", None) is not None:
             self._peers.update(self.running_mean, self.running_var, self.count, sums, rows)
             return
-        payload = reduce_moments(sums, rows, group)
         n = 2 * self.shape
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            payload = reduce_moments(sums, rows, group)
+        else:
+            # one process: no exchange.  The payload lives in a persistent buffer filled by device-side copies, so the
+            # whole update can be captured in a CUDA graph together with the steps that produced the partials.
+            payload = getattr(self, "_payload", None)
+            if payload is None or payload.device != sums.device:
+                payload = self._payload = torch.empty(n + 1, dtype=torch.float64, device=sums.device)
+            payload[:n].copy_(sums)
+            if isinstance(rows, torch.Tensor):
+                payload[n:].copy_(rows.reshape(1))
+            else:
+                payload[n:].fill_(float(rows))
         _cabi.check(
             _cabi.load().phc_running_norm_update(
                 self.running_mean.data_ptr(), self.running_var.data_ptr(), self.count.data_ptr(),

@@ -389,6 +389,11 @@ PHC_API int phc_host_step_create(const PhcLib* lib, int64_t max_envs, int32_t ti
                          const PhcRewardSpec* rwd, PhcHostStep** out);
 PHC_API int phc_host_step(PhcHostStep* ctx, const PhcHostStepArgs* args, int64_t n);
 PHC_API void phc_host_step_destroy(PhcHostStep* ctx);
+/* Which output path pinned callers are on: 1 = direct (each chunk's kernel posts obs rows / rewards / flags into the
+ * mapped host buffers), 2 = staged (device buffers + copy-engine D2H; always the case for pageable callers), 0 = not
+ * decided yet.  By default the context times both over its first calls (3 each, alternating, under whatever load
+ * the other GPUs of the box put on the host at that moment) and keeps the faster; PHC_HOST_PATH=direct|staged pins it. */
+PHC_API int phc_host_step_path(const PhcHostStep* ctx);
 PHC_API int64_t phc_host_step_h2d_bytes(const PhcHostStep* ctx, int64_t n);
 PHC_API int64_t phc_host_step_d2h_bytes(const PhcHostStep* ctx, int64_t n);
 

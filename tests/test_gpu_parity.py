@@ -562,14 +562,20 @@ def test_running_norm_vs_reference_fixture(golden):
     assert_close(rn(cuda(g.inp("x2")[:32])), g.out("fwd"), what="forward", rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("pinned", [True, False], ids=["pinned_direct", "pageable_staged"])
-def test_host_pipeline_matches_device_path(pinned):
-    """phc_host_step on host buffers == the device path, bit for bit.  Pinned buffers take the
-    direct path (the kernel works on the mapped host memory), pageable ones the staged copies."""
+@pytest.mark.parametrize("mode", ["pinned_direct", "pinned_staged", "pinned_auto", "pageable_staged"])
+def test_host_pipeline_matches_device_path(mode, monkeypatch):
+    """phc_host_step on host buffers == the device path, bit for bit, on every path: pinned buffers with the kernels
+    posting into the mapped host memory (direct), pinned buffers with copy-engine D2H (staged), the automatic choice
+    between the two (timed over the first calls), and pageable buffers (always staged)."""
     import ctypes as C
 
     from humanoid_b200 import HumanoidPHC, _cabi
 
+    pinned = mode != "pageable_staged"
+    if mode in ("pinned_direct", "pinned_staged"):
+        monkeypatch.setenv("PHC_HOST_PATH", mode.split("_")[1])
+    else:
+        monkeypatch.delenv("PHC_HOST_PATH", raising=False)
     N = 5000
     lib_data, clock, state = _gpu_case(N, 64, 208, max_progress=40)
     lib = MotionLib(lib_data, device=DEV)
@@ -593,13 +599,29 @@ def test_host_pipeline_matches_device_path(pinned):
     )  # fmt: skip
     args = _cabi.PhcHostStepArgs(*[h[k].data_ptr() for k in ("state", "prog", "start", "off", "goff", "ids", "obs",
                                                              "rew", "raw", "reset", "term")])  # fmt: skip
-    _cabi.check(capi.phc_host_step(ctx, C.byref(args), N), "host step")
+    calls = 12 if mode == "pinned_auto" else 1  # auto: both paths are timed over calls 3..8, then one is kept
+    for i in range(calls):
+        h["prog"].copy_(clock.progress_buf.cpu())
+        h["obs"].fill_(float("nan"))
+        _cabi.check(capi.phc_host_step(ctx, C.byref(args), N), "host step")
+        assert torch.equal(h["obs"], env.obs_buf.cpu()), f"call {i}"
     assert capi.phc_host_step_h2d_bytes(ctx, N) == N * (1248 + 2 + 4 + 4 + 12 + 8)
+    path = capi.phc_host_step_path(ctx)
+    assert path == {"pinned_direct": 1, "pinned_staged": 2, "pageable_staged": 2}.get(mode, path) and path in (1, 2)
     capi.phc_host_step_destroy(ctx)
     assert torch.equal(h["obs"], env.obs_buf.cpu()) and torch.equal(h["rew"], env.rew_buf.cpu())
     assert torch.equal(h["raw"], env.reward_raw[:, :4].cpu())
     assert torch.equal(h["reset"].bool(), env.reset_buf.cpu()) and torch.equal(h["term"].bool(), env._terminate_buf.cpu())
     assert torch.equal(h["prog"], env.progress_buf.cpu())
+    if pinned:  # device pointers are refused, not dereferenced by the CPU
+        bad = _cabi.PhcHostStepArgs(*[h[k].data_ptr() for k in ("state", "prog", "start", "off", "goff", "ids", "obs",
+                                                                "rew", "raw", "reset", "term")])  # fmt: skip
+        bad.state = env._rigid_body_state_reshaped.data_ptr()
+        ctx2 = C.c_void_p()
+        _cabi.check(capi.phc_host_step_create(lib.handle, N, 1, 3, term, 0xFFFFFF, 0, 1, synth.SIM_DT, C.byref(spec),
+                                              C.byref(ctx2)), "create")  # fmt: skip
+        assert capi.phc_host_step(ctx2, C.byref(bad), N) == -4  # PHC_ERR_UNSUPPORTED
+        capi.phc_host_step_destroy(ctx2)
 
 
 @pytest.mark.parametrize("regime", ["aligned30", "mixed_fps_unaligned"])

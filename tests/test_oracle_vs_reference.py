@@ -141,3 +141,20 @@ def test_clip_sampler_matches_reference_sampling_state(golden):
         assert torch.equal(mine.pick_clips(N, False, 4, None, is_deterministic=False), ref._curr_motion_ids)
         ref.update_soft_sampling_weight([]), mine.update_soft_sampling_weight([])
         assert torch.equal(mine._sampling_prob, ref._sampling_prob)
+
+
+def test_reference_step_orchestration_equals_the_oracle_step_bit_for_bit():
+    """``ref_loader.reference_step`` — what ``bench.py --impl reference`` times (the reference's own functions in the
+    env's order) — against ``oracle.step`` on the same inputs, T = 1 and T = 3."""
+    for T in (1, 3):
+        lib_data, clock, state = synth.make_case(query=_ref_query, num_envs=300, num_motions=24, seed=5 + T, max_progress=20)
+        term = torch.full((24,), 0.25)
+        p1, p2 = clock.progress_buf.clone(), clock.progress_buf.clone()
+        want = O.step(O.OracleMotionLib(lib_data), state, p1, clock.motion_start_times, clock.motion_start_times_offset,
+                      clock.global_offset, clock.sampled_motion_ids, term, synth.SIM_DT, time_steps=T)  # fmt: skip
+        got = ref_loader.reference_step(ref_loader.make_reference_lib(lib_data), state, p2, clock.motion_start_times,
+                                        clock.motion_start_times_offset, clock.global_offset, clock.sampled_motion_ids,
+                                        term, synth.SIM_DT, time_steps=T)  # fmt: skip
+        assert torch.equal(p1, p2)
+        for a, b, nm in zip(got, want, ("obs", "reward", "reward_raw", "reset", "terminated")):
+            assert_equal_exact(a, b, f"T={T}: {nm}")

@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphc_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NUM_BODIES = 24
 SELF_OBS_DIM = 358
 TASK_OBS_DIM = 576
@@ -37,6 +37,7 @@ STATE_INIT_RANDOM = 1
 OBS_LOCAL_ROOT = 1
 OBS_ROOT_HEIGHT = 2
 OBS_UPRIGHT = 4
+STEP_OBS_FLAGS_SET = 0x80000000
 
 
 class PhcLibDesc(C.Structure):
@@ -88,6 +89,46 @@ class PhcRewardSpec(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("k_pos", "k_rot", "k_vel", "k_ang_vel", "w_pos", "w_rot", "w_vel", "w_ang_vel")]
 
 
+class PhcResetArgs(C.Structure):
+    _fields_ = [
+        ("body", PhcBodyState),
+        ("humanoid_root_states", C.c_void_p),
+        ("root_stride", C.c_int64),
+        ("dof_pos", C.c_void_p),
+        ("dof_vel", C.c_void_p),
+        ("dof_stride", C.c_int64),
+        ("dof_elem_stride", C.c_int64),
+        ("progress_buf", C.c_void_p),
+        ("reset_buf", C.c_void_p),
+        ("terminate_buf", C.c_void_p),
+        ("motion_start_times", C.c_void_p),
+        ("motion_start_times_offset", C.c_void_p),
+        ("global_offset", C.c_void_p),
+        ("sampled_motion_ids", C.c_void_p),
+        ("env_mask", C.c_void_p),
+        ("phase", C.c_void_p),
+        ("state_init", C.c_int32),
+        ("flag_test", C.c_int32),
+        ("time_steps", C.c_int32),
+        ("dt", C.c_float),
+        ("obs_buf", C.c_void_p),
+        ("obs_stride", C.c_int64),
+        ("obs_norm", C.c_void_p),
+        ("obs_norm_stride", C.c_int64),
+        ("norm_mean", C.c_void_p),
+        ("norm_var", C.c_void_p),
+        ("norm_epsilon", C.c_float),
+        ("norm_clip", C.c_float),
+        ("obs_norm_bf16", C.c_int32),
+        ("obs_moments_mode", C.c_int32),
+        ("obs_moments", C.c_void_p),
+        ("obs_moments_buckets", C.c_int32),
+        ("obs_flags", C.c_uint32),
+        ("ref_dof_pos", C.c_void_p),
+        ("ref_dof_pos_stride", C.c_int64),
+    ]
+
+
 class PhcStepArgs(C.Structure):
     _fields_ = [
         ("body", PhcBodyState),
@@ -136,33 +177,13 @@ class PhcStepArgs(C.Structure):
         ("ep_sums", C.c_void_p),
         ("ep_buckets", C.c_int32),
         ("ep_raw_cols", C.c_int32),
-    ]
-
-
-class PhcResetArgs(C.Structure):
-    _fields_ = [
-        ("body", PhcBodyState),
-        ("humanoid_root_states", C.c_void_p),
-        ("root_stride", C.c_int64),
-        ("dof_pos", C.c_void_p),
-        ("dof_vel", C.c_void_p),
-        ("dof_stride", C.c_int64),
-        ("dof_elem_stride", C.c_int64),
-        ("progress_buf", C.c_void_p),
-        ("reset_buf", C.c_void_p),
-        ("terminate_buf", C.c_void_p),
-        ("motion_start_times", C.c_void_p),
-        ("motion_start_times_offset", C.c_void_p),
-        ("global_offset", C.c_void_p),
-        ("sampled_motion_ids", C.c_void_p),
-        ("env_mask", C.c_void_p),
-        ("phase", C.c_void_p),
-        ("state_init", C.c_int32),
-        ("flag_test", C.c_int32),
-        ("time_steps", C.c_int32),
-        ("dt", C.c_float),
-        ("obs_buf", C.c_void_p),
-        ("obs_stride", C.c_int64),
+        ("rew_out", C.c_void_p),
+        ("reset_out", C.c_void_p),
+        ("terminate_out", C.c_void_p),
+        ("auto_reset", C.POINTER(PhcResetArgs)),
+        ("ref_dof_pos", C.c_void_p),
+        ("ref_dof_pos_stride", C.c_int64),
+        ("obs_flags", C.c_uint32),
     ]
 
 
@@ -275,7 +296,7 @@ SIGNATURES = {
     "phc_action_to_pd_targets": (
         C.c_int,
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32,
-         C.c_int64, C.c_int32, C.c_void_p, C.c_void_p],
+         C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
     ),  # fmt: skip
     "phc_step_fused": (C.c_int, [C.c_void_p, C.POINTER(PhcStepArgs), C.c_int64, C.c_void_p]),
     "phc_reset_envs": (C.c_int, [C.c_void_p, C.POINTER(PhcResetArgs), C.c_int64, C.c_void_p]),

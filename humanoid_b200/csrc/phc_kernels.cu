@@ -678,19 +678,24 @@ __global__ void reset_kernel(PhcView pos, PhcView ref, int R, const int16_t* __r
 __global__ void pd_targets_kernel(const float* __restrict__ action, const float* __restrict__ offset,
                                   const float* __restrict__ scale, int res_action, const float* __restrict__ ref_dof_pos,
                                   const float* __restrict__ dof_pos, int64_t dp_stride, int64_t dp_estride,
-                                  uint32_t zero_mask, int64_t n, int D, float* __restrict__ out) {
+                                  uint32_t zero_mask, int64_t n, int D, float clip, float* __restrict__ actions_out,
+                                  float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * D) return;
   const int64_t env = i / D;
   const int d = (int)(i - env * D);
+  float a = action[i];
+  // np.clip(actions, -1, 1) of the wrapper (clean_pufferl/env.py:110-112); NaN stays NaN as in numpy
+  if (clip > 0.0f) a = a < -clip ? -clip : (a > clip ? clip : a);
+  if (actions_out) actions_out[i] = a;  // self.actions[:] = ...
   float pd;
   if (res_action) {
-    pd = ref_dof_pos[i] + scale[d] * action[i];
+    pd = ref_dof_pos[i] + scale[d] * a;
     const float q = dof_pos[env * dp_stride + d * dp_estride];
     const float half_pi = 1.57079637050628662f;  // f32(np.pi / 2)
     pd = fmaxf(fminf(pd, q + half_pi), q - half_pi);  // maximum(minimum(pd, upper), lower)
   } else {
-    pd = offset[d] + scale[d] * action[i];
+    pd = offset[d] + scale[d] * a;
   }
   if (zero_mask >> (d / 3) & 1u) pd = 0.0f;
   out[i] = pd;
@@ -702,8 +707,8 @@ __global__ void pd_targets_kernel(const float* __restrict__ action, const float*
 // dof_pos, dof velocities) -> _set_env_state scatter -> clock / buffer resets.  The observation
 // of the reset envs is a masked obs-only pass of the step kernel, launched right after.
 // ---------------------------------------------------------------------------------------
-struct ResetParams {
-  LibDev L;
+// what a reset writes besides the observation row (shared by phc_reset_envs and the reset inside the fused step)
+struct ResetTargets {
   PhcBodyState body;  // written
   float* root;
   int64_t root_stride;
@@ -716,15 +721,43 @@ struct ResetParams {
   float* start;
   float* start_off;
   float* goff;
-  const int64_t* ids;
-  const uint8_t* mask;
   const float* phase;
   int state_init, flag_test;
+};
+
+// self-observation variant (compute_humanoid_observations_smpl_max flags, humanoid_phc.py:963-998)
+struct ObsFlags {
+  int hcol;        // 1: root height column present (root_height_obs)
+  int local_root;  // local_root_obs
+  int upright;     // upright (False: remove_base_rot before the heading)
+};
+
+// RunningNorm.forward of the rows a kernel writes (policies/running_norm.py:15-20)
+struct NormOut {
+  float* out;  // NULL = off
+  int64_t stride;
+  const float* mean;
+  const float* var;
+  float eps, clip;
+  int bf16;
+};
+
+struct ResetParams {
+  LibDev L;
+  ResetTargets w;
+  const int64_t* ids;
+  const uint8_t* mask;
   int64_t n;
-  float* obs;  // [n, 358 + 576 T]: rows of the reset envs rewritten
+  float* obs;  // [n, selfw + 576 T]: rows of the reset envs rewritten
   int64_t obs_stride;
   int T;
   float dt;
+  ObsFlags of;
+  NormOut norm;
+  double* moments;  // NULL, or [buckets][2 W]
+  int moment_buckets, moments_mode;  // mode 1: add the new rows; 2: replace (subtract the old row first)
+  float* ref_dof_pos;  // NULL, or [n, 69]
+  int64_t ref_dof_pos_stride;
 };
 
 struct ResetEnvOut {  // what the scatter leaves in registers for the observation of the same (env, body)
@@ -738,13 +771,18 @@ constexpr int K7_EPB = 8;
 
 // the reference body b of a just-reset env at (progress + q) dt + start + offset with progress = 0, offset = 0
 // (humanoid_phc.py:1063-1067), blended like blend_ref; the global offset is the zero the reset leaves
-__device__ __forceinline__ RefBody reset_ref_body(const LibDev& L, int q, float dt, float t, float len, int64_t nf, float mdt,
-                                                  int64_t st, int b) {
+__device__ __forceinline__ void reset_query_frames(int q, float dt, float t, float len, int64_t nf, float mdt, int64_t st,
+                                                   int64_t& f0, int64_t& f1, float& bl) {
   const float tq = (float)(int16_t)q * dt + t + 0.0f;
   int64_t i0, i1;
-  float bl;
   calc_frame_blend(tq, len, nf, mdt, i0, i1, bl);
-  const int64_t f0 = i0 + st, f1 = i1 + st;
+  f0 = i0 + st, f1 = i1 + st;
+}
+__device__ __forceinline__ RefBody reset_ref_body(const LibDev& L, int q, float dt, float t, float len, int64_t nf, float mdt,
+                                                  int64_t st, int b) {
+  int64_t f0, f1;
+  float bl;
+  reset_query_frames(q, dt, t, len, nf, mdt, st, f0, f1, bl);
   const float om = 1.0f - bl;
   RefBody r;
   r.pos = lerp3(om, bl, ld3(L.gts + (f0 * J24 + b) * 3), ld3(L.gts + (f1 * J24 + b) * 3));
@@ -755,82 +793,143 @@ __device__ __forceinline__ RefBody reset_ref_body(const LibDev& L, int q, float 
   return r;
 }
 
+// MotionLibBase.sample_time_interval (motion_lib.py:526-535) with the caller's uniform number:
+//   ((phase * motion_len) / curr_fps).long() * curr_fps with curr_fps = 1/30; 0 for StateInit.Start / flag_test (:856)
+__device__ __forceinline__ float reset_start_time(const ResetTargets& w, int64_t env, float len) {
+  if (w.state_init == PHC_STATE_INIT_RANDOM && !w.flag_test) {
+    const float c30 = (float)(1.0 / 30.0);
+    const long long k = (long long)((w.phase[env] * len) / c30);
+    return (float)k * c30;
+  }
+  return 0.0f;
+}
+
+// One (env, body) of a reference-state-init reset: get_motion_state at the new start time (motion_lib.py:549-626)
+// posed with the OLD global offset (:860), the _set_env_state scatter (humanoid_phc.py:901-931) and, on body 0, the
+// clock updates of _reset_ref_state_init (:724-731) and the buffer resets of _reset_env_tensors (:775-778).
+// `write_flags`: also clear reset_buf / terminate_buf (the fused step leaves that to the lane that owns the flags).
+__device__ __forceinline__ void reset_scatter_thread(const LibDev& L, const ResetTargets& w, int64_t env, int b, float t,
+                                                     float len, int64_t nf, float mdt, int64_t st, float g0, float g1,
+                                                     float g2, bool write_flags, ResetEnvOut& o) {
+  int64_t i0, i1;
+  float bl;
+  calc_frame_blend(t, len, nf, mdt, i0, i1, bl);
+  const int64_t f0 = i0 + st, f1 = i1 + st;
+  const float om = 1.0f - bl;
+  Vec3 pos = lerp3(om, bl, ld3(L.gts + (f0 * J24 + b) * 3), ld3(L.gts + (f1 * J24 + b) * 3));
+  pos.x += g0;
+  pos.y += g1;
+  pos.z += g2;
+  const Quat rot = quat_slerp(ld4v(L.grs + (f0 * J24 + b) * 4), ld4v(L.grs + (f1 * J24 + b) * 4), bl);
+  const Vec3 vel = lerp3(om, bl, ld3(L.gvs + (f0 * J24 + b) * 3), ld3(L.gvs + (f1 * J24 + b) * 3));
+  const Vec3 ang = lerp3(om, bl, ld3(L.gavs + (f0 * J24 + b) * 3), ld3(L.gavs + (f1 * J24 + b) * 3));
+  st3(const_cast<float*>(view_at(w.body.pos, env, b)), pos);
+  st4(const_cast<float*>(view_at(w.body.rot, env, b)), rot);
+  st3(const_cast<float*>(view_at(w.body.vel, env, b)), vel);
+  st3(const_cast<float*>(view_at(w.body.ang_vel, env, b)), ang);
+  if (b == 0 && w.root) {
+    float* r = w.root + env * w.root_stride;
+    st3(r, pos);
+    st4(r + 3, rot);
+    st3(r + 7, vel);
+    st3(r + 10, ang);
+  }
+  if (w.dof_pos && b >= 1) {  // _local_rotation_to_dof_smpl (motion_lib.py:670-673)
+    const Quat lr = quat_slerp(ld4v(L.lrs + (f0 * J24 + b) * 4), ld4v(L.lrs + (f1 * J24 + b) * 4), bl);
+    const Vec3 em = quat_exp_map(lr);
+    float* d = w.dof_pos + env * w.dof_stride + (int64_t)(b - 1) * 3 * w.dof_estride;
+    d[0] = em.x;
+    d[w.dof_estride] = em.y;
+    d[2 * w.dof_estride] = em.z;
+  }
+  if (w.dof_vel && b < 23) {
+    const Vec3 dv = lerp3(om, bl, ld3(L.dvs + (f0 * 23 + b) * 3), ld3(L.dvs + (f1 * 23 + b) * 3));
+    float* d = w.dof_vel + env * w.dof_stride + (int64_t)b * 3 * w.dof_estride;
+    d[0] = dv.x;
+    d[w.dof_estride] = dv.y;
+    d[2 * w.dof_estride] = dv.z;
+  }
+  if (b == 0) {
+    if (w.goff) {
+      w.goff[env * 3 + 0] = 0.0f;
+      w.goff[env * 3 + 1] = 0.0f;
+      w.goff[env * 3 + 2] = 0.0f;
+    }
+    w.start[env] = t;
+    w.start_off[env] = 0.0f;
+    w.progress[env] = 0;
+    if (write_flags) {
+      w.reset[env] = 0;
+      w.term[env] = 0;
+    }
+  }
+  o.pos = pos, o.rot = rot, o.vel = vel, o.ang = ang;
+  o.t = t, o.len = len, o.mdt = mdt, o.nf = nf, o.st = st;
+}
+
 // `act`: this thread's env is in range and selected by the mask (read by the caller, once, before anything is
 // written: the mask may be reset_buf itself, which the last lines clear)
 __device__ __forceinline__ void reset_scatter_body(const ResetParams& p, const bool act, ResetEnvOut& o) {
   __shared__ float s_goff[K7_EPB][3];
   const int e = threadIdx.x / J24, b = threadIdx.x % J24;
   const int64_t env = (int64_t)blockIdx.x * K7_EPB + e;
-  if (act && b < 3) s_goff[e][b] = p.goff ? p.goff[env * 3 + b] : 0.0f;  // the OLD offset poses the env (:860)
+  if (act && b < 3) s_goff[e][b] = p.w.goff ? p.w.goff[env * 3 + b] : 0.0f;  // the OLD offset poses the env (:860)
   __syncthreads();
   if (!act) return;
   const int64_t id = p.ids[env];
   const float len = p.L.len[id];
-  // MotionLibBase.sample_time_interval (motion_lib.py:526-535):
-  //   ((phase * motion_len) / curr_fps).long() * curr_fps with curr_fps = 1/30
-  float t = 0.0f;
-  if (p.state_init == PHC_STATE_INIT_RANDOM && !p.flag_test) {
-    const float c30 = (float)(1.0 / 30.0);
-    const long long k = (long long)((p.phase[env] * len) / c30);
-    t = (float)k * c30;
+  const float t = reset_start_time(p.w, env, len);
+  reset_scatter_thread(p.L, p.w, env, b, t, len, p.L.nf[id], p.L.mdt[id], p.L.starts[id], s_goff[e][0], s_goff[e][1],
+                       s_goff[e][2], true, o);
+}
+
+// ---- the observation row of one (env, body): shared by every step kernel and the reset kernel -----------------
+// DEF: the env's default flags (height column, local root, upright) with the 8-byte aligned shared-memory stage of the
+// TMA kernels: constant column offsets and float2 stores.  !DEF: any flag combination, any alignment.
+template <bool DEF>
+__device__ __forceinline__ void put6(float* p, const float* v) {
+  if (DEF) {
+    st6_shared(p, v);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p[k] = v[k];
   }
-  int64_t i0, i1;
-  float bl;
-  const int64_t nf = p.L.nf[id];
-  const float mdt = p.L.mdt[id];
-  calc_frame_blend(t, len, nf, mdt, i0, i1, bl);
-  const int64_t st = p.L.starts[id];
-  const int64_t f0 = i0 + st, f1 = i1 + st;
-  const float om = 1.0f - bl;
-  // get_motion_state (motion_lib.py:549-626)
-  Vec3 pos = lerp3(om, bl, ld3(p.L.gts + (f0 * J24 + b) * 3), ld3(p.L.gts + (f1 * J24 + b) * 3));
-  pos.x += s_goff[e][0];
-  pos.y += s_goff[e][1];
-  pos.z += s_goff[e][2];
-  const Quat rot = quat_slerp(ld4v(p.L.grs + (f0 * J24 + b) * 4), ld4v(p.L.grs + (f1 * J24 + b) * 4), bl);
-  const Vec3 vel = lerp3(om, bl, ld3(p.L.gvs + (f0 * J24 + b) * 3), ld3(p.L.gvs + (f1 * J24 + b) * 3));
-  const Vec3 ang = lerp3(om, bl, ld3(p.L.gavs + (f0 * J24 + b) * 3), ld3(p.L.gavs + (f1 * J24 + b) * 3));
-  // _set_env_state (humanoid_phc.py:901-931)
-  st3(const_cast<float*>(view_at(p.body.pos, env, b)), pos);
-  st4(const_cast<float*>(view_at(p.body.rot, env, b)), rot);
-  st3(const_cast<float*>(view_at(p.body.vel, env, b)), vel);
-  st3(const_cast<float*>(view_at(p.body.ang_vel, env, b)), ang);
-  if (b == 0 && p.root) {
-    float* r = p.root + env * p.root_stride;
-    st3(r, pos);
-    st4(r + 3, rot);
-    st3(r + 7, vel);
-    st3(r + 10, ang);
+}
+// the root rotation the heading is taken from: as is when upright, remove_base_rot first otherwise (common.py:42-47)
+__device__ __forceinline__ Quat heading_source(Quat root_rot, int upright) { return upright ? root_rot : remove_base_rot(root_rot); }
+
+// self obs, common.py:23-103: [root_h? | rot(h^-1, p_b - p_root) b >= 1 | tan_norm(h^-1 (x) q_b) | rot(h^-1, v_b) | rot(h^-1, w_b)]
+template <bool DEF>
+__device__ __forceinline__ void emit_self_obs(float* row, const ObsFlags& of, int b, Vec3 root_pos, Heading hi,
+                                              const HeadingRot& hr, Vec3 pos, Quat rot, Vec3 vel, Vec3 ang) {
+  const int h = DEF ? 1 : of.hcol;
+  if (b == 0) {
+    if (h) row[0] = root_pos.z;
+  } else {
+    st3(row + h + (b - 1) * 3, heading_rotate(hr, pos - root_pos));
   }
-  if (p.dof_pos && b >= 1) {  // _local_rotation_to_dof_smpl (motion_lib.py:670-673)
-    const Quat lr = quat_slerp(ld4v(p.L.lrs + (f0 * J24 + b) * 4), ld4v(p.L.lrs + (f1 * J24 + b) * 4), bl);
-    const Vec3 em = quat_exp_map(lr);
-    float* d = p.dof_pos + env * p.dof_stride + (int64_t)(b - 1) * 3 * p.dof_estride;
-    d[0] = em.x;
-    d[p.dof_estride] = em.y;
-    d[2 * p.dof_estride] = em.z;
-  }
-  if (p.dof_vel && b < 23) {
-    const Vec3 dv = lerp3(om, bl, ld3(p.L.dvs + (f0 * 23 + b) * 3), ld3(p.L.dvs + (f1 * 23 + b) * 3));
-    float* d = p.dof_vel + env * p.dof_stride + (int64_t)b * 3 * p.dof_estride;
-    d[0] = dv.x;
-    d[p.dof_estride] = dv.y;
-    d[2 * p.dof_estride] = dv.z;
-  }
-  if (b == 0) {  // _reset_ref_state_init (:724-731) and _reset_env_tensors (:775-778)
-    if (p.goff) {
-      p.goff[env * 3 + 0] = 0.0f;
-      p.goff[env * 3 + 1] = 0.0f;
-      p.goff[env * 3 + 2] = 0.0f;
-    }
-    p.start[env] = t;
-    p.start_off[env] = 0.0f;
-    p.progress[env] = 0;
-    p.reset[env] = 0;
-    p.term[env] = 0;
-  }
-  o.pos = pos, o.rot = rot, o.vel = vel, o.ang = ang;
-  o.t = t, o.len = len, o.mdt = mdt, o.nf = nf, o.st = st;
+  float t6[6];
+  if (!DEF && b == 0 && !of.local_root)
+    quat_tan_norm(heading_source(rot, of.upright), t6);  // "if not local_root_obs: root_rot_obs = quat_to_tan_norm(root_rot)" (:76-78)
+  else
+    quat_tan_norm(heading_mul_left(hi, rot), t6);
+  put6<DEF>(row + h + 69 + b * 6, t6);
+  st3(row + h + 213 + b * 3, heading_rotate(hr, vel));
+  st3(row + h + 285 + b * 3, heading_rotate(hr, ang));
+}
+
+// one v6 block of 576 floats, common.py:106-176
+template <bool DEF>
+__device__ __forceinline__ void emit_task_obs(float* tk, int b, Heading hi, const HeadingRot& hr, Vec3 root_pos, Vec3 pos,
+                                              Quat rot, Vec3 vel, Vec3 ang, const RefBody& r) {
+  TaskObs o;
+  task_obs_body(hi, hr, root_pos, pos, rot, vel, ang, r, true, o);
+  st3(tk + b * 3, o.d_pos);
+  put6<DEF>(tk + 72 + b * 6, o.d_rot);
+  st3(tk + 216 + b * 3, o.d_vel);
+  st3(tk + 288 + b * 3, o.d_ang);
+  st3(tk + 360 + b * 3, o.l_pos);
+  put6<DEF>(tk + 432 + b * 6, o.l_rot);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -900,7 +999,25 @@ struct StepParams {
   int obs_only;             // 1: observations only — no reward / reset outputs, clock untouched
   int aos;        // sim state is one AoS-13 tensor, 16-B aligned rows
   int obs_vec2;   // obs rows can be written with 8-byte stores
+  float* rew_out;      // NULL, or a second copy of rew_buf (the wrapper's rewards.clone())
+  uint8_t* reset_out;  // NULL, or the step's reset flags (kept when the in-step reset clears reset_buf)
+  uint8_t* term_out;   // NULL, or extras["terminate"]
+  float* ref_dof_pos;  // NULL, or [n, 69]: dof_pos of the query at t + dt (res_action, humanoid_phc.py:1115-1120)
+  int64_t ref_dof_pos_stride;
+  ObsFlags of;         // self-obs flags; of.hcol && of.local_root && of.upright = the env's defaults
+  int selfw;           // 357 + of.hcol
+  int reset_on;        // the flagged envs are reset inside the step (PhcStepArgs.auto_reset)
+  ResetTargets rw;
 };
+
+__host__ __device__ __forceinline__ bool default_obs_flags(const ObsFlags& f) { return f.hcol && f.local_root && f.upright; }
+
+// dof_pos of the motion query whose frames are rows f0 / f1 of the library (motion_lib.py:608-610, 670-673): body b >= 1
+__device__ __forceinline__ void write_ref_dof_pos(const StepParams& p, int64_t env, int b, int64_t f0, int64_t f1, float bl) {
+  if (b < 1) return;
+  const Quat lr = quat_slerp(ld4v(p.L.lrs + (f0 * J24 + b) * 4), ld4v(p.L.lrs + (f1 * J24 + b) * 4), bl);
+  st3(p.ref_dof_pos + env * p.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
+}
 
 // RunningNorm.forward of one value (policies/running_norm.py:15-20): clamp((x - mean) / sqrt(var + eps)).
 // `sd` = sqrt(var + eps) and `r` ~ 1/sd are per column; the quotient is within 1 ulp of IEEE division.
@@ -1087,7 +1204,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
     S.part[4][e][b] = norm3(pos - r.pos);  // torch.norm(rigid_body_pos - ref_body_pos), common.py:343/348
     if (p.dof_force) S.part[5][e][b] = power_partial(p, env, b);
     if (b == 0) {
-      const Heading hi = heading_quat_inv(rot);  // upright: root_rot used as is (common.py:42-44)
+      const Heading hi = heading_quat_inv(heading_source(rot, p.of.upright));  // common.py:42-47
       S.hz[e] = hi.z;
       S.hw[e] = hi.w;
     }
@@ -1095,6 +1212,7 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
   __syncthreads();  // partials written; frames(t) no longer needed
 
   if (T >= 1) load_frames<EPB>(p.L, S, 1, e, b, valid);  // overlap with the reductions below
+  if (valid && p.ref_dof_pos && !p.obs_only) write_ref_dof_pos(p, env, b, S.f0[1][e], S.f1[1][e], S.bl[1][e]);
 
   const bool outs = valid && !p.obs_only;  // obs-only passes leave reward / flags untouched
   if (outs && b < 4) {
@@ -1122,8 +1240,11 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
       }
       fallen = fallen && (S.prog[e] > 1);  // common.py:353
     }
+    const bool rs = S.pass[e] || fallen;  // common.py:362
     p.term[env] = fallen ? 1 : 0;
-    p.reset[env] = S.pass[e] ? 1 : (fallen ? 1 : 0);  // common.py:362
+    p.reset[env] = rs ? 1 : 0;
+    if (p.term_out) p.term_out[env] = fallen ? 1 : 0;
+    if (p.reset_out) p.reset_out[env] = rs ? 1 : 0;
   } else if (outs && b == 5 && p.mpjpe) {
     p.mpjpe[env] = row_sum24(&S.part[4][e][0]) / 24.0f;  // humanoid_phc.py:167
   }
@@ -1137,13 +1258,16 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
       p.raw[env * p.raw_stride + p.power_col] = pr;
     }
     p.rew[env] = r;
+    if (p.rew_out) p.rew_out[env] = r;
   }
 
   // ---- phase 2: observations -------------------------------------------------------------
   const Vec3 root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
   const Heading hi = {S.hz[e], S.hw[e]};
   const HeadingRot hr = heading_rot(hi);
-  const int W = SELF_DIM + TASK_DIM * T;
+  const int SW = p.selfw;           // 358 with the root height column, 357 without
+  const int RW = SW + TASK_DIM;     // floats of a staged row (self obs + one task block)
+  const int W = SW + TASK_DIM * T;
 
   for (int q = 1; q <= T; ++q) {
     cp_async_wait_all();
@@ -1152,36 +1276,18 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
     if (valid) r = blend_ref<EPB>(S, q, e, b);
     __syncthreads();  // frame buffer dead -> becomes the obs stage
 
-    float* row = S.buf + e * STAGE_FLOATS;
+    float* row = S.buf + e * STAGE_FLOATS;  // staged rows keep the 934-float pitch whatever the flags
     if (valid) {
-      if (q == 1) {  // self obs, common.py:23-103 (default flags: local root, height, upright)
-        if (b == 0)
-          row[0] = root_pos.z;
-        else
-          st3(row + 1 + (b - 1) * 3, heading_rotate(hr, pos - root_pos));
-        quat_tan_norm(heading_mul_left(hi, rot), row + 70 + b * 6);
-        st3(row + 214 + b * 3, heading_rotate(hr, vel));
-        st3(row + 286 + b * 3, heading_rotate(hr, ang));
-      }
-      TaskObs o;
-      task_obs_body(hi, hr, root_pos, pos, rot, vel, ang, r, true, o);
-      float* tk = row + SELF_DIM;
-      st3(tk + b * 3, o.d_pos);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) tk[72 + b * 6 + k] = o.d_rot[k];
-      st3(tk + 216 + b * 3, o.d_vel);
-      st3(tk + 288 + b * 3, o.d_ang);
-      st3(tk + 360 + b * 3, o.l_pos);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) tk[432 + b * 6 + k] = o.l_rot[k];
+      if (q == 1) emit_self_obs<false>(row, p.of, b, root_pos, hi, hr, pos, rot, vel, ang);
+      emit_task_obs<false>(row + SW, b, hi, hr, root_pos, pos, rot, vel, ang, r);
     }
     __syncthreads();  // stage complete
 
-    // stream the staged columns out: q == 1 -> cols [0, 934), else [358 + 576(q-1), +576)
-    const int s_off = q == 1 ? 0 : SELF_DIM;
-    const int s_len = q == 1 ? STAGE_FLOATS : TASK_DIM;
-    const int64_t c_off = q == 1 ? 0 : SELF_DIM + (int64_t)TASK_DIM * (q - 1);
-    if (p.obs_vec2) {
+    // stream the staged columns out: q == 1 -> cols [0, RW), else [SW + 576(q-1), +576)
+    const int s_off = q == 1 ? 0 : SW;
+    const int s_len = q == 1 ? RW : TASK_DIM;
+    const int64_t c_off = q == 1 ? 0 : SW + (int64_t)TASK_DIM * (q - 1);
+    if (p.obs_vec2 && (SW & 1) == 0) {
       if (T == 1 && p.obs_stride == STAGE_FLOATS && !p.env_mask) {  // rows of the block are one contiguous span
         float2* dst = reinterpret_cast<float2*>(p.obs + env0 * STAGE_FLOATS);
         const float2* src = reinterpret_cast<const float2*>(S.buf);
@@ -1239,6 +1345,28 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
   cp_async_wait_all();
 }
 
+// the columns of an observation row that thread `b` of an env writes: f(first column, count)
+template <class F>
+__device__ __forceinline__ void for_owned_columns(int b, int hcol, int SW, int T, F f) {
+  if (b == 0) {
+    if (hcol) f(0, 1);
+  } else {
+    f(hcol + (b - 1) * 3, 3);
+  }
+  f(hcol + 69 + b * 6, 6);
+  f(hcol + 213 + b * 3, 3);
+  f(hcol + 285 + b * 3, 3);
+  for (int q = 1; q <= T; ++q) {
+    const int base = SW + TASK_DIM * (q - 1);
+    f(base + b * 3, 3);
+    f(base + 72 + b * 6, 6);
+    f(base + 216 + b * 3, 3);
+    f(base + 288 + b * 3, 3);
+    f(base + 360 + b * 3, 3);
+    f(base + 432 + b * 6, 6);
+  }
+}
+
 // Reset of the flagged envs and their observations in ONE launch (phc_reset_envs).  A thread scatters the new state
 // of its (env, body) and, with that state still in registers, writes the body's columns of the env's obs row
 // (_compute_observations(env_ids), :937-961): the root position and heading come from body 0 through shared memory,
@@ -1247,6 +1375,9 @@ __global__ void __launch_bounds__(EPB* J24) step_kernel(const StepParams p) {
 // obs-only pass of step_kernel over the new state; the chain of dependent memory round trips is less than half as
 // long.  The mask byte is read once, first, so it may be reset_buf itself; blocks without a flagged env leave at once —
 // with nothing flagged the launch reads n mask bytes and nothing else.
+// The step's fused epilogues stay consistent with the rewritten rows: the normalised copy of the row is rewritten
+// too (norm.out), and the RunningNorm partials either gain the new row (moments_mode 1: rows that were never
+// counted) or have the row the step had counted replaced by it (mode 2).
 __global__ void __launch_bounds__(K7_EPB* J24) reset_obs_kernel(const ResetParams p) {
   __shared__ float s_root[K7_EPB][5];  // root pos xyz | inverse heading z, w
   const int e = threadIdx.x / J24, b = threadIdx.x % J24;
@@ -1256,7 +1387,7 @@ __global__ void __launch_bounds__(K7_EPB* J24) reset_obs_kernel(const ResetParam
   ResetEnvOut o;
   reset_scatter_body(p, act, o);
   if (act && b == 0) {
-    const Heading h0 = heading_quat_inv(o.rot);  // upright: root_rot used as is (common.py:42-44)
+    const Heading h0 = heading_quat_inv(heading_source(o.rot, p.of.upright));  // common.py:42-47
     s_root[e][0] = o.pos.x, s_root[e][1] = o.pos.y, s_root[e][2] = o.pos.z;
     s_root[e][3] = h0.z, s_root[e][4] = h0.w;
   }
@@ -1266,29 +1397,49 @@ __global__ void __launch_bounds__(K7_EPB* J24) reset_obs_kernel(const ResetParam
   const Heading hi = {s_root[e][3], s_root[e][4]};
   const HeadingRot hr = heading_rot(hi);
   float* row = p.obs + env * p.obs_stride;
-  // self obs, common.py:23-103 (default flags: local root, height, upright)
-  if (b == 0)
-    row[0] = root_pos.z;
-  else
-    st3(row + 1 + (b - 1) * 3, heading_rotate(hr, o.pos - root_pos));
-  quat_tan_norm(heading_mul_left(hi, o.rot), row + 70 + b * 6);
-  st3(row + 214 + b * 3, heading_rotate(hr, o.vel));
-  st3(row + 286 + b * 3, heading_rotate(hr, o.ang));
+  const int SW = 357 + p.of.hcol, W = SW + TASK_DIM * p.T;
+  double* mom = p.moments ? p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * W : nullptr;
+  if (mom && p.moments_mode == 2) {  // the step that flagged this env counted the row it wrote: take it out again
+    for_owned_columns(b, p.of.hcol, SW, p.T, [&](int c0, int n) {
+      for (int c = c0; c < c0 + n; ++c) {
+        const double x = (double)__ldcg(row + c);
+        atomicAdd(mom + c, -x);
+        atomicAdd(mom + W + c, -(x * x));
+      }
+    });
+  }
+  emit_self_obs<false>(row, p.of, b, root_pos, hi, hr, o.pos, o.rot, o.vel, o.ang);
+  if (p.ref_dof_pos && b >= 1) {  // self.ref_dof_pos[env_ids] = dof_pos of the query at t + dt (humanoid_phc.py:1115-1120)
+    int64_t f0, f1;
+    float bl;
+    reset_query_frames(1, p.dt, o.t, o.len, o.nf, o.mdt, o.st, f0, f1, bl);
+    const Quat lr = quat_slerp(ld4v(p.L.lrs + (f0 * J24 + b) * 4), ld4v(p.L.lrs + (f1 * J24 + b) * 4), bl);
+    st3(p.ref_dof_pos + env * p.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
+  }
   for (int q = 1; q <= p.T; ++q) {
     // loading the t + dt frames together with the scatter's (before its stores) was measured: 10 more registers,
     // 3 instead of 4 blocks per SM — 0.6 us faster per loop step at 4 % flagged, 2.5 us slower at 31 %; not kept
     const RefBody r = reset_ref_body(p.L, q, p.dt, o.t, o.len, o.nf, o.mdt, o.st, b);
-    TaskObs t;
-    task_obs_body(hi, hr, root_pos, o.pos, o.rot, o.vel, o.ang, r, true, t);
-    float* tk = row + SELF_DIM + (int64_t)TASK_DIM * (q - 1);
-    st3(tk + b * 3, t.d_pos);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) tk[72 + b * 6 + k] = t.d_rot[k];
-    st3(tk + 216 + b * 3, t.d_vel);
-    st3(tk + 288 + b * 3, t.d_ang);
-    st3(tk + 360 + b * 3, t.l_pos);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) tk[432 + b * 6 + k] = t.l_rot[k];
+    emit_task_obs<false>(row + SW + (int64_t)TASK_DIM * (q - 1), b, hi, hr, root_pos, o.pos, o.rot, o.vel, o.ang, r);
+  }
+  if (mom || p.norm.out) {  // the thread's own stores above are visible to it
+    for_owned_columns(b, p.of.hcol, SW, p.T, [&](int c0, int n) {
+      for (int c = c0; c < c0 + n; ++c) {
+        const float v = row[c];
+        if (mom) {
+          const double x = (double)v;
+          atomicAdd(mom + c, x);
+          atomicAdd(mom + W + c, x * x);
+        }
+        if (p.norm.out) {  // policies/running_norm.py:15-20, the step kernels' arithmetic
+          const float sd = sqrt_faithful(p.norm.var[c] + p.norm.eps);
+          const float y = fminf(fmaxf(div_faithful(v - p.norm.mean[c], sd, rcp_approx(sd)), -p.norm.clip), p.norm.clip);
+          const int64_t at = env * p.norm.stride + c;
+          if (p.norm.bf16) reinterpret_cast<__nv_bfloat16*>(p.norm.out)[at] = __float2bfloat16_rn(y);
+          else p.norm.out[at] = y;
+        }
+      }
+    });
   }
 }
 
@@ -1319,6 +1470,14 @@ struct FastSmem {
   float hz[EPB], hw[EPB];
   int prog[EPB], pass[EPB], fallen[EPB];
   int parity;  // phase of `bar` the consumers wait for
+  // clip metadata of the block's envs (the in-step reset samples a new start time from it) and the library rows of
+  // the query at t + dt (ref_dof_pos reads the local rotations of the same two frames)
+  float meta_len[EPB], meta_mdt[EPB];
+  int meta_nf[EPB];
+  int64_t meta_st[EPB];
+  int64_t row1[2][EPB];
+  int rst[EPB];          // env is reset inside this launch
+  float nroot[EPB][5];   // root position and inverse heading of a just-reset env
 };
 
 __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, float bl, const float* goff, int b) {
@@ -1334,14 +1493,53 @@ __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, 
   return r;
 }
 
+// The reset of the envs a step flags, inside the step (PhcStepArgs.auto_reset; clean_pufferl/env.py:133-135 ->
+// humanoid_phc.py:665-676).  Called by EVERY thread of a block that has a flagged env, after phase 1: a thread of a
+// flagged env re-poses its body from the motion library (reset_scatter_thread, the arithmetic of phc_reset_envs),
+// body 0 publishes the new root position and heading, and after the block barrier the thread holds what the
+// observation of the new state needs — its body's new state and the reference body at the new t + dt.  Kept out
+// of line: the common path (no env flagged) pays a handful of instructions for the test and nothing else.
+template <int EPB>
+__device__ __noinline__ void reset_in_step(const StepParams& p, FastSmem<EPB>& S, bool mine, int e, int b, int64_t env,
+                                           Vec3& pos, Quat& rot, Vec3& vel, Vec3& ang, RefBody& r1) {
+  ResetEnvOut o;
+  if (mine) {
+    const float len = S.meta_len[e];
+    const float t = reset_start_time(p.rw, env, len);
+    reset_scatter_thread(p.L, p.rw, env, b, t, len, (int64_t)S.meta_nf[e], S.meta_mdt[e], S.meta_st[e], S.goff[e][0],
+                         S.goff[e][1], S.goff[e][2], false, o);
+    if (b == 0) {
+      if (p.progress_mirror) p.progress_mirror[env] = 0;
+      const Heading h0 = heading_quat_inv(heading_source(o.rot, p.of.upright));
+      S.nroot[e][0] = o.pos.x, S.nroot[e][1] = o.pos.y, S.nroot[e][2] = o.pos.z;
+      S.nroot[e][3] = h0.z, S.nroot[e][4] = h0.w;
+    }
+  }
+  __syncthreads();
+  if (mine) {
+    pos = o.pos, rot = o.rot, vel = o.vel, ang = o.ang;
+    r1 = reset_ref_body(p.L, 1, p.dt, o.t, o.len, o.nf, o.mdt, o.st, b);
+    if (p.ref_dof_pos && b >= 1) {  // humanoid_phc.py:1115-1120 on the reset's _compute_task_obs(env_ids)
+      int64_t f0, f1;
+      float bl;
+      reset_query_frames(1, p.dt, o.t, o.len, o.nf, o.mdt, o.st, f0, f1, bl);
+      const Quat lr = quat_slerp(ld4v(p.L.lrs + (f0 * J24 + b) * 4), ld4v(p.L.lrs + (f1 * J24 + b) * 4), bl);
+      st3(p.ref_dof_pos + env * p.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
+    }
+  }
+}
+
 // NORM: compiled with the RunningNorm.forward epilogue (obs_norm set); the plain instantiation carries none of it
-// EP: compiled with the wrapper's episode bookkeeping in the reduction warp (ep_returns set)
-template <int EPB, int MINB, bool NORM = false, bool EP = false>
+// EP: compiled with the wrapper's episode bookkeeping in the reduction warp (used when ep_returns is set)
+// RESET: compiled with the in-step reset of the flagged envs (used when reset_on is set)
+// DEF: the env's default self-obs flags (height column, local root, upright): constant columns, 934-float rows
+template <int EPB, int MINB, bool NORM = false, bool EP = false, bool RESET = false, bool DEF = true>
 __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem<EPB>& S = *reinterpret_cast<FastSmem<EPB>*>(smem_raw);
   constexpr int NT = EPB * J24;
   static_assert(4 * EPB <= 32, "reductions run on one warp");
+  static_assert(!NORM || DEF, "the normaliser epilogue is laid out for the default 934-float rows");
   const int tid = threadIdx.x;
   const int64_t env0 = (int64_t)blockIdx.x * EPB;
   const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
@@ -1491,6 +1689,10 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
       S.goff[le][0] = g0;
       S.goff[le][1] = g1;
       S.goff[le][2] = g2;
+      if (RESET) {
+        S.meta_len[le] = len, S.meta_mdt[le] = mdt, S.meta_nf[le] = nf, S.meta_st[le] = st;
+      }
+      if (p.ref_dof_pos) S.row1[0][le] = st + b_f0, S.row1[1][le] = st + b_f1;
       if (ok && spec) {  // frames are already (arriving) in the slots
         S.slot[0][0][le] = a_f0 - s_lo;
         S.slot[0][1][le] = a_f1 - s_lo;
@@ -1538,8 +1740,9 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     if (tid >= 32 && tid < 32 + nvalid) {
       const int le = tid - 32;
       const float* rq = p.body.pos.ptr + (env0 + le) * p.body.pos.stride_env + 3;
-      const Heading h0 = heading_quat_inv(Quat{__ldcg(rq), __ldcg(rq + 1), __ldcg(rq + 2), __ldcg(rq + 3)});
-      S.hz[le] = h0.z;  // upright: root_rot used as is (common.py:42-44)
+      const Quat rq4 = Quat{__ldcg(rq), __ldcg(rq + 1), __ldcg(rq + 2), __ldcg(rq + 3)};
+      const Heading h0 = heading_quat_inv(DEF ? rq4 : heading_source(rq4, p.of.upright));  // common.py:42-47
+      S.hz[le] = h0.z;
       S.hw[le] = h0.w;
     }
   }
@@ -1579,60 +1782,86 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   PHC_STAMP(4);
   __syncthreads();  // #2: partials / heading visible; frame buffer dead -> becomes the obs stage
 
+  // ---- in-step reset of the flagged envs (RESET) -------------------------------------------------
+  // Every thread works out which of the block's envs this step flags (the test of the reduction warp below, from
+  // the same shared-memory values); a block without one goes straight on.
+  bool my_rst = false;
+  if constexpr (RESET) {
+    if (p.reset_on) {
+      if (p.use_mean) {  // eval mode: the mean needs ATen's row sum — one lane per env, then a block barrier
+        if (tid < nvalid) {
+          float sel[J24];
+          int m = 0;
+#pragma unroll
+          for (int j = 0; j < J24; ++j)
+            if (p.reset_mask >> j & 1u) sel[m++] = S.part[4][tid][j];
+          const int first = __ffs(p.reset_mask) - 1;
+          bool fallen = p.early && m > 0 && (aten_row_sum(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+          fallen = fallen && (S.prog[tid] > 1);
+          S.rst[tid] = (S.pass[tid] || fallen) ? 1 : 0;
+        }
+        __syncthreads();
+      }
+      int any = 0;
+#pragma unroll
+      for (int i = 0; i < EPB; ++i) {
+        int r = 0;
+        if (i < nvalid) r = p.use_mean ? S.rst[i] : ((S.pass[i] || (p.early && S.fallen[i] && S.prog[i] > 1)) ? 1 : 0);
+        any |= r;
+        if (i == e) my_rst = valid && r;
+      }
+      if (any) reset_in_step<EPB>(p, S, my_rst, e, b, env0 + e, pos, rot, vel, ang, r1);
+    }
+  }
+
   // ---- phase 2: observations into the stage ---------------------------------------------------
+  const int SW = DEF ? SELF_DIM : p.selfw;  // 358 with the root height column, 357 without
+  const int RW = SW + TASK_DIM;             // floats of a staged row
   if (valid) {
-    const Vec3 root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
-    const Heading hi = {S.hz[e], S.hw[e]};
+    Vec3 root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
+    Heading hi = {S.hz[e], S.hw[e]};
+    if (RESET && my_rst) {
+      root_pos = {S.nroot[e][0], S.nroot[e][1], S.nroot[e][2]};
+      hi = {S.nroot[e][3], S.nroot[e][4]};
+    }
     const HeadingRot hr = heading_rot(hi);
-    float* row = S.frames + e * STAGE_FLOATS;
-    // self obs, common.py:23-103 (default flags: local root, height, upright)
-    if (b == 0)
-      row[0] = root_pos.z;
-    else
-      st3(row + 1 + (b - 1) * 3, heading_rotate(hr, pos - root_pos));
-    float t6[6];
-    quat_tan_norm(heading_mul_left(hi, rot), t6);
-    st6_shared(row + 70 + b * 6, t6);
-    st3(row + 214 + b * 3, heading_rotate(hr, vel));
-    st3(row + 286 + b * 3, heading_rotate(hr, ang));
-    // task obs v6, common.py:106-176
-    TaskObs o;
-    task_obs_body(hi, hr, root_pos, pos, rot, vel, ang, r1, true, o);
-    float* tk = row + SELF_DIM;
-    st3(tk + b * 3, o.d_pos);
-    st6_shared(tk + 72 + b * 6, o.d_rot);
-    st3(tk + 216 + b * 3, o.d_vel);
-    st3(tk + 288 + b * 3, o.d_ang);
-    st3(tk + 360 + b * 3, o.l_pos);
-    st6_shared(tk + 432 + b * 6, o.l_rot);
+    float* row = S.frames + e * RW;
+    emit_self_obs<DEF>(row, p.of, b, root_pos, hi, hr, pos, rot, vel, ang);           // common.py:23-103
+    emit_task_obs<DEF>(row + SW, b, hi, hr, root_pos, pos, rot, vel, ang, r1);        // common.py:106-176
   }
   fence_proxy_async();  // stage writes -> visible to the bulk-store engine
   PHC_STAMP(5);
   __syncthreads();      // #3: stage complete
   PHC_STAMP(6);
 
-  const uint32_t out_bytes = (uint32_t)nvalid * (STAGE_FLOATS * 4);
+  const uint32_t out_bytes = (uint32_t)nvalid * (uint32_t)(RW * 4);
   const bool bulk_ok = (out_bytes & 15u) == 0;
   if (bulk_ok) {
-    if (tid == NT - 1) bulk_s2g(p.obs + env0 * STAGE_FLOATS, S.frames, out_bytes);
-  } else {  // odd tail block: 8-byte stores
-    float2* dst = reinterpret_cast<float2*>(p.obs + env0 * STAGE_FLOATS);
+    if (tid == NT - 1) bulk_s2g(p.obs + env0 * RW, S.frames, out_bytes);
+  } else if (DEF || ((nvalid * RW) & 1) == 0) {  // odd tail block: 8-byte stores
+    float2* dst = reinterpret_cast<float2*>(p.obs + env0 * RW);
     const float2* src = reinterpret_cast<const float2*>(S.frames);
-    for (int i = tid; i < nvalid * (STAGE_FLOATS / 2); i += NT) dst[i] = src[i];
+    for (int i = tid; i < nvalid * RW / 2; i += NT) dst[i] = src[i];
+  } else {
+    for (int i = tid; i < nvalid * RW; i += NT) p.obs[env0 * RW + i] = S.frames[i];
   }
   if (p.moments) {  // RunningNorm partials: per-column fp64 sum / sum of squares over the block's envs
-    for (int c = tid; c < STAGE_FLOATS; c += NT) {
+    for (int c = tid; c < RW; c += NT) {
       double s1 = 0.0, s2 = 0.0;
       for (int ee = 0; ee < nvalid; ++ee) {
-        const double x = (double)S.frames[ee * STAGE_FLOATS + c];
+        const double x = (double)S.frames[ee * RW + c];
         s1 += x;
         s2 += x * x;
       }
-      double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * STAGE_FLOATS;
+      double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * RW;
       atomicAdd(mom + c, s1);
-      atomicAdd(mom + STAGE_FLOATS + c, s2);
+      atomicAdd(mom + RW + c, s2);
     }
   }
+  // res_action: dof_pos of the query at t + dt (humanoid_phc.py:1115-1120), off the critical path; a just-reset env
+  // got its row from the reset above
+  if (p.ref_dof_pos && valid && !(RESET && my_rst))
+    write_ref_dof_pos(p, env0 + e, b, S.row1[0][e], S.row1[1][e], S.bl[1][e]);
   // RunningNorm.forward, fp32 rows, full blocks: once the raw store has READ the stage, normalise it in place and
   // send it out with a second bulk store instead of 20 scattered 8-byte stores per thread
   const bool norm_inplace = NORM && p.obs_norm && bulk_ok && !p.norm_bf16;
@@ -1696,7 +1925,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     float ep_ret = 0.0f;  // EP: the env's running return / length, fetched before the reductions below need them
     int32_t ep_len = 0;
     if constexpr (EP) {
-      if (act && k == 0) {
+      if (p.ep_returns && act && k == 0) {
         ep_ret = p.ep_returns[env0 + le];
         ep_len = p.ep_lengths[env0 + le];
       }
@@ -1719,6 +1948,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
         p.raw[(env0 + le) * p.raw_stride + p.power_col] = pr;
       }
       p.rew[env0 + le] = r;
+      if (p.rew_out) p.rew_out[env0 + le] = r;
     }
     if (act && k == 1) {
       bool fallen = false;
@@ -1736,12 +1966,18 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
         }
         fallen = fallen && (S.prog[le] > 1);  // common.py:353
       }
-      p.term[env0 + le] = fallen ? 1 : 0;
-      p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
-      flags = (S.pass[le] || fallen ? 1 : 0) | (fallen ? 2 : 0);
+      const bool rs = S.pass[le] || fallen;  // common.py:362
+      // with the in-step reset the flagged envs have been reset by now: reset_buf / terminate_buf read 0 afterwards
+      // (_reset_env_tensors, humanoid_phc.py:775-778) and the step's flags live on in reset_out / terminate_out
+      const bool cleared = RESET && p.reset_on;
+      p.term[env0 + le] = (fallen && !cleared) ? 1 : 0;
+      p.reset[env0 + le] = (rs && !cleared) ? 1 : 0;
+      if (p.term_out) p.term_out[env0 + le] = fallen ? 1 : 0;
+      if (p.reset_out) p.reset_out[env0 + le] = rs ? 1 : 0;
+      flags = (rs ? 1 : 0) | (fallen ? 2 : 0);
     }
     if (act && k == 2 && p.mpjpe) p.mpjpe[env0 + le] = row_sum24(&S.part[4][le][0]) / 24.0f;  // humanoid_phc.py:167
-    if constexpr (EP) {
+    if constexpr (EP) if (p.ep_returns) {
       // PHCPufferEnv.step's bookkeeping (clean_pufferl/env.py:121-159) for the block's envs, on the lanes that hold the
       // reward; the block's sums go to one of ep_buckets fp64 accumulators (atomics on one address serialise).  The sums
       // over the block's four envs are taken in fp32 — counts and lengths are exact there, a four-term sum of returns or
@@ -2040,6 +2276,7 @@ __global__ void __launch_bounds__(MULTI_EPB* J24, 5) step_multi_kernel(const Ste
         p.raw[(env0 + le) * p.raw_stride + p.power_col] = pr;
       }
       p.rew[env0 + le] = r;
+      if (p.rew_out) p.rew_out[env0 + le] = r;
     }
     if (act && k == 1) {
       bool fallen = false;
@@ -2057,10 +2294,17 @@ __global__ void __launch_bounds__(MULTI_EPB* J24, 5) step_multi_kernel(const Ste
         }
         fallen = fallen && (S.prog[le] > 1);  // common.py:353
       }
+      const bool rs = S.pass[le] || fallen;  // common.py:362
       p.term[env0 + le] = fallen ? 1 : 0;
-      p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
+      p.reset[env0 + le] = rs ? 1 : 0;
+      if (p.term_out) p.term_out[env0 + le] = fallen ? 1 : 0;
+      if (p.reset_out) p.reset_out[env0 + le] = rs ? 1 : 0;
     }
     if (act && k == 2 && p.mpjpe) p.mpjpe[env0 + le] = row_sum24(&S.part[4][le][0]) / 24.0f;  // humanoid_phc.py:167
+  }
+  if (p.ref_dof_pos && tid < EPB * J24 && tid / J24 < nvalid) {  // res_action: dof_pos of the query at t + dt
+    const int le = tid / J24;
+    write_ref_dof_pos(p, env0 + le, tid % J24, S.row0[1][le], S.row0[1][le] + S.two[1][le], S.bl[1][le]);
   }
 }
 
@@ -2303,6 +2547,7 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
         p.raw[(env0 + le) * p.raw_stride + p.power_col] = pr;
       }
       p.rew[env0 + le] = r;
+      if (p.rew_out) p.rew_out[env0 + le] = r;
     }
     if (act && k == 1) {
       bool fallen = false;
@@ -2320,10 +2565,17 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
         }
         fallen = fallen && (S.prog[le] > 1);  // common.py:353
       }
+      const bool rs = S.pass[le] || fallen;  // common.py:362
       p.term[env0 + le] = fallen ? 1 : 0;
-      p.reset[env0 + le] = S.pass[le] ? 1 : (fallen ? 1 : 0);  // common.py:362
+      p.reset[env0 + le] = rs ? 1 : 0;
+      if (p.term_out) p.term_out[env0 + le] = fallen ? 1 : 0;
+      if (p.reset_out) p.reset_out[env0 + le] = rs ? 1 : 0;
     }
     if (act && k == 2 && p.mpjpe) p.mpjpe[env0 + le] = row_sum24(&S.part[4][le][0]) / 24.0f;  // humanoid_phc.py:167
+  }
+  if (p.ref_dof_pos && tid < EPB * J24 && tid / J24 < nvalid) {  // res_action: dof_pos of the query at t + dt
+    const int le = tid / J24;
+    write_ref_dof_pos(p, env0 + le, tid % J24, S.row0[1][le], S.row0[1][le] + S.two[1][le], S.bl[1][le]);
   }
 }
 
@@ -2837,6 +3089,78 @@ static unsigned long long* g_trace = nullptr;  // phc_set_trace_buffer (profilin
 static int64_t g_trace_capacity = 0;
 static int64_t g_trace_launch = 0;
 
+static ObsFlags obs_flags_from(uint32_t f) {
+  ObsFlags of;
+  if (!(f & PHC_STEP_OBS_FLAGS_SET) && (f & 7u) == 0) f = PHC_OBS_LOCAL_ROOT | PHC_OBS_ROOT_HEIGHT | PHC_OBS_UPRIGHT;
+  of.hcol = (f & PHC_OBS_ROOT_HEIGHT) ? 1 : 0;
+  of.local_root = (f & PHC_OBS_LOCAL_ROOT) ? 1 : 0;
+  of.upright = (f & PHC_OBS_UPRIGHT) ? 1 : 0;
+  return of;
+}
+
+static int reset_fill(const PhcLib* lib, const PhcResetArgs* a, int64_t n, ResetParams& r) {
+  if (n < 0) return PHC_ERR_SHAPE;
+  if (!lib || !a) return PHC_ERR_NULL;
+  int rc = check_body(&a->body);
+  if (rc) return rc;
+  if (a->body.num_bodies != J24) return PHC_ERR_UNSUPPORTED;
+  if (!a->progress_buf || !a->reset_buf || !a->terminate_buf || !a->motion_start_times ||
+      !a->motion_start_times_offset || !a->sampled_motion_ids || !a->obs_buf)
+    return PHC_ERR_NULL;
+  if (a->state_init == PHC_STATE_INIT_RANDOM && !a->flag_test && !a->phase) return PHC_ERR_NULL;
+  if (a->state_init != PHC_STATE_INIT_RANDOM && a->state_init != PHC_STATE_INIT_START) return PHC_ERR_UNSUPPORTED;
+  if ((a->dof_pos && !lib->d.lrs) || (a->dof_vel && !lib->d.dvs) || (a->ref_dof_pos && !lib->d.lrs)) return PHC_ERR_NULL;
+  if (a->time_steps < 1 || a->time_steps > PHC_MAX_TIME_STEPS) return PHC_ERR_SHAPE;
+  const ObsFlags of = obs_flags_from(a->obs_flags);
+  const int64_t W = 357 + of.hcol + (int64_t)TASK_DIM * a->time_steps;
+  if (a->obs_stride < W || ((a->dof_pos || a->dof_vel) && a->dof_elem_stride < 1)) return PHC_ERR_SHAPE;
+  if (a->obs_norm && (!a->norm_mean || !a->norm_var)) return PHC_ERR_NULL;
+  if (a->obs_norm && (a->obs_norm_stride < W || !(a->norm_clip > 0.0f))) return PHC_ERR_SHAPE;
+  if (a->obs_moments_mode < 0 || a->obs_moments_mode > 2 || a->obs_moments_buckets < 0 || a->obs_moments_buckets > 4096)
+    return PHC_ERR_SHAPE;
+  if (a->obs_moments_mode && !a->obs_moments) return PHC_ERR_NULL;
+  if (a->ref_dof_pos && a->ref_dof_pos_stride < 69) return PHC_ERR_SHAPE;
+  r = ResetParams{};
+  r.L = lib->d;
+  r.w.body = a->body;
+  r.w.root = a->humanoid_root_states;
+  r.w.root_stride = a->root_stride;
+  r.w.dof_pos = a->dof_pos;
+  r.w.dof_vel = a->dof_vel;
+  r.w.dof_stride = a->dof_stride;
+  r.w.dof_estride = a->dof_elem_stride;
+  r.w.progress = a->progress_buf;
+  r.w.reset = a->reset_buf;
+  r.w.term = a->terminate_buf;
+  r.w.start = a->motion_start_times;
+  r.w.start_off = a->motion_start_times_offset;
+  r.w.goff = a->global_offset;
+  r.w.phase = a->phase;
+  r.w.state_init = a->state_init;
+  r.w.flag_test = a->flag_test;
+  r.ids = a->sampled_motion_ids;
+  r.mask = a->env_mask;
+  r.n = n;
+  r.obs = a->obs_buf;  // _compute_observations(env_ids), same launch
+  r.obs_stride = a->obs_stride;
+  r.T = a->time_steps;
+  r.dt = a->dt;
+  r.of = of;
+  r.norm = NormOut{a->obs_norm, a->obs_norm_stride, a->norm_mean, a->norm_var, a->norm_epsilon, a->norm_clip,
+                   a->obs_norm_bf16 ? 1 : 0};
+  r.moments = a->obs_moments_mode ? a->obs_moments : nullptr;
+  r.moment_buckets = a->obs_moments_buckets > 1 ? a->obs_moments_buckets : 1;
+  r.moments_mode = a->obs_moments_mode;
+  r.ref_dof_pos = a->ref_dof_pos;
+  r.ref_dof_pos_stride = a->ref_dof_pos_stride;
+  return PHC_OK;
+}
+
+static int reset_launch(const ResetParams& r, cudaStream_t stream) {
+  reset_obs_kernel<<<(unsigned)((r.n + K7_EPB - 1) / K7_EPB), K7_EPB * J24, 0, stream>>>(r);
+  return launch_status();
+}
+
 static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, StepParams& p) {
   if (!lib || !a) return PHC_ERR_NULL;
   int rc = check_body(&a->body);
@@ -2846,8 +3170,38 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
       !a->termination_distances || !a->obs_buf || !a->rew_buf || !a->reward_raw || !a->reset_buf || !a->terminate_buf)
     return PHC_ERR_NULL;
   if (a->time_steps < 1 || a->time_steps > PHC_MAX_TIME_STEPS) return PHC_ERR_SHAPE;
-  const int64_t W = SELF_DIM + (int64_t)TASK_DIM * a->time_steps;
+  p.of = obs_flags_from(a->obs_flags);
+  p.selfw = 357 + p.of.hcol;
+  const int64_t W = p.selfw + (int64_t)TASK_DIM * a->time_steps;
   if (a->obs_stride < W || a->reward_raw_stride < 4) return PHC_ERR_SHAPE;
+  p.rew_out = a->rew_out;
+  p.reset_out = a->reset_out;
+  p.term_out = a->terminate_out;
+  p.ref_dof_pos = a->ref_dof_pos;
+  p.ref_dof_pos_stride = a->ref_dof_pos_stride;
+  if (a->ref_dof_pos && (!lib->d.lrs || a->ref_dof_pos_stride < 69)) return lib->d.lrs ? PHC_ERR_SHAPE : PHC_ERR_NULL;
+  p.reset_on = 0;
+  p.rw = ResetTargets{};
+  if (a->auto_reset) {
+    // the reset rides on the step's own buffers: anything else would not be "the envs this step flags"
+    const PhcResetArgs* r = a->auto_reset;
+    if (r->body.pos.ptr != a->body.pos.ptr || r->body.rot.ptr != a->body.rot.ptr || r->body.vel.ptr != a->body.vel.ptr ||
+        r->body.ang_vel.ptr != a->body.ang_vel.ptr || r->body.pos.stride_env != a->body.pos.stride_env ||
+        r->body.pos.stride_body != a->body.pos.stride_body || r->progress_buf != a->progress_buf ||
+        r->reset_buf != a->reset_buf || r->terminate_buf != a->terminate_buf || r->obs_buf != a->obs_buf ||
+        r->obs_stride != a->obs_stride || r->sampled_motion_ids != a->sampled_motion_ids ||
+        r->motion_start_times != a->motion_start_times || r->motion_start_times_offset != a->motion_start_times_offset ||
+        r->global_offset != a->global_offset || r->time_steps != a->time_steps || r->dt != a->dt)
+      return PHC_ERR_SHAPE;
+    const ObsFlags rf = obs_flags_from(r->obs_flags);
+    if (rf.hcol != p.of.hcol || rf.local_root != p.of.local_root || rf.upright != p.of.upright) return PHC_ERR_SHAPE;
+    ResetParams rp;
+    rc = reset_fill(lib, r, n, rp);
+    if (rc) return rc;
+    if (r->ref_dof_pos != a->ref_dof_pos) return PHC_ERR_SHAPE;
+    p.rw = rp.w;
+    p.reset_on = 1;
+  }
   p.L = lib->d;
   p.body = a->body;
   p.progress = a->progress_buf;
@@ -2896,7 +3250,7 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.norm_bf16 = (a->flags & PHC_STEP_OBS_NORM_BF16) ? 1 : 0;
   if (a->obs_norm) {
     if (!a->norm_mean || !a->norm_var) return PHC_ERR_NULL;
-    if (a->obs_norm_stride < SELF_DIM + (int64_t)TASK_DIM * a->time_steps || !(a->norm_clip > 0.0f)) return PHC_ERR_SHAPE;
+    if (a->obs_norm_stride < W || !(a->norm_clip > 0.0f)) return PHC_ERR_SHAPE;
   }
   p.dof_force = a->dof_force;
   p.dof_force_stride = a->dof_force_stride;
@@ -2958,62 +3312,26 @@ static void init_options() {
 int phc_action_to_pd_targets(const float* action, const float* pd_action_offset, const float* pd_action_scale,
                              int32_t res_action, const float* ref_dof_pos, const float* dof_pos,
                              int64_t dof_pos_stride, int64_t dof_pos_elem_stride, uint32_t zero_mask, int64_t n,
-                             int32_t num_dof, float* out, phc_stream_t stream) {
+                             int32_t num_dof, float action_clip, float* actions_out, float* out, phc_stream_t stream) {
   if (n == 0) return PHC_OK;
-  if (n < 0 || num_dof < 1 || num_dof > 96) return PHC_ERR_SHAPE;
+  if (n < 0 || num_dof < 1 || num_dof > 96 || !(action_clip >= 0.0f)) return PHC_ERR_SHAPE;
   if (!action || !pd_action_scale || !out) return PHC_ERR_NULL;
   if (res_action ? (!ref_dof_pos || !dof_pos) : !pd_action_offset) return PHC_ERR_NULL;
   const int64_t total = n * num_dof;
   pd_targets_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(action, pd_action_offset, pd_action_scale,
                                                                          res_action, ref_dof_pos, dof_pos, dof_pos_stride,
-                                                                         dof_pos_elem_stride, zero_mask, n, num_dof, out);
+                                                                         dof_pos_elem_stride, zero_mask, n, num_dof,
+                                                                         action_clip, actions_out, out);
   return launch_status();
 }
 
 int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* a, int64_t n, phc_stream_t stream) {
   if (n == 0) return PHC_OK;
-  if (n < 0) return PHC_ERR_SHAPE;
-  if (!lib || !a) return PHC_ERR_NULL;
-  int rc = check_body(&a->body);
+  ResetParams r;
+  const int rc = reset_fill(lib, a, n, r);
   if (rc) return rc;
-  if (a->body.num_bodies != J24) return PHC_ERR_UNSUPPORTED;
-  if (!a->progress_buf || !a->reset_buf || !a->terminate_buf || !a->motion_start_times ||
-      !a->motion_start_times_offset || !a->sampled_motion_ids || !a->env_mask || !a->obs_buf)
-    return PHC_ERR_NULL;
-  if (a->state_init == PHC_STATE_INIT_RANDOM && !a->flag_test && !a->phase) return PHC_ERR_NULL;
-  if (a->state_init != PHC_STATE_INIT_RANDOM && a->state_init != PHC_STATE_INIT_START) return PHC_ERR_UNSUPPORTED;
-  if ((a->dof_pos && !lib->d.lrs) || (a->dof_vel && !lib->d.dvs)) return PHC_ERR_NULL;
-  if (a->time_steps < 1 || a->time_steps > PHC_MAX_TIME_STEPS) return PHC_ERR_SHAPE;
-  const int64_t W = SELF_DIM + (int64_t)TASK_DIM * a->time_steps;
-  if (a->obs_stride < W || ((a->dof_pos || a->dof_vel) && a->dof_elem_stride < 1)) return PHC_ERR_SHAPE;
-
-  ResetParams r{};
-  r.L = lib->d;
-  r.body = a->body;
-  r.root = a->humanoid_root_states;
-  r.root_stride = a->root_stride;
-  r.dof_pos = a->dof_pos;
-  r.dof_vel = a->dof_vel;
-  r.dof_stride = a->dof_stride;
-  r.dof_estride = a->dof_elem_stride;
-  r.progress = a->progress_buf;
-  r.reset = a->reset_buf;
-  r.term = a->terminate_buf;
-  r.start = a->motion_start_times;
-  r.start_off = a->motion_start_times_offset;
-  r.goff = a->global_offset;
-  r.ids = a->sampled_motion_ids;
-  r.mask = a->env_mask;
-  r.phase = a->phase;
-  r.state_init = a->state_init;
-  r.flag_test = a->flag_test;
-  r.n = n;
-  r.obs = a->obs_buf;  // _compute_observations(env_ids), same launch
-  r.obs_stride = a->obs_stride;
-  r.T = a->time_steps;
-  r.dt = a->dt;
-  reset_obs_kernel<<<(unsigned)((n + K7_EPB - 1) / K7_EPB), K7_EPB * J24, 0, stream>>>(r);
-  return launch_status();
+  if (!a->env_mask) return PHC_ERR_NULL;
+  return reset_launch(r, stream);
 }
 
 int phc_set_trace_buffer(uint64_t* device_buf, int64_t capacity_warps) {
@@ -3062,11 +3380,16 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
   PHC_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return PHC_ERR_UNSUPPORTED;
   init_options();
-  // fast path: T == 1, AoS sim tensor (16-B aligned rows), dense 16-B aligned obs_buf
-  const bool fast = !g_force_generic && p.T == 1 && p.aos && p.L.packed && p.obs_stride == STAGE_FLOATS &&
+  // fast path: T == 1, AoS sim tensor (16-B aligned rows), dense 16-B aligned obs_buf.  Any self-obs flag combination
+  // runs on it (rows of 933 floats without the height column: four of them are still a multiple of 16 B); the fused
+  // normaliser epilogue is laid out for the default 934-float rows only.
+  const bool def = default_obs_flags(p.of);
+  const int RW = p.selfw + TASK_DIM;
+  const bool fast = !g_force_generic && p.T == 1 && p.aos && p.L.packed && p.obs_stride == RW &&
                     ((uintptr_t)p.obs & 15) == 0 &&
-                    (!p.obs_norm || (p.obs_norm_stride == STAGE_FLOATS && ((uintptr_t)p.obs_norm & (p.norm_bf16 ? 3 : 15)) == 0));
-  static bool attr_fast4[64] = {}, attr_gen[64] = {};
+                    (!p.obs_norm || (def && p.obs_norm_stride == STAGE_FLOATS &&
+                                     ((uintptr_t)p.obs_norm & (p.norm_bf16 ? 3 : 15)) == 0));
+  static bool attr_gen[64] = {};
   static int first_wave[64] = {};
   if (fast) {
     if (!first_wave[dev]) {
@@ -3083,17 +3406,24 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
       p.first_wave_blocks = 0;
       --lib->unspeculated_steps;
     }
-    static bool attr_fast4_norm[64] = {}, attr_fast4_ep[64] = {}, attr_fast4_norm_ep[64] = {};
-    if (p.obs_norm && p.ep_returns)
-      return launch_step(step_fast_kernel<4, 8, true, true>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4_norm_ep[dev], g_pdl != 0);
-    if (p.ep_returns)
-      return launch_step(step_fast_kernel<4, 8, false, true>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4_ep[dev], g_pdl != 0);
-    if (p.obs_norm)
-      return launch_step(step_fast_kernel<4, 8, true>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4_norm[dev], g_pdl != 0);
-    return launch_step(step_fast_kernel<4, 8>, sizeof(FastSmem<4>), 4, p, stream, &attr_fast4[dev], g_pdl != 0);
+    // instantiations <EPB, blocks/SM, NORM, EP, RESET, DEF>: the plain one carries none of the optional epilogues; the
+    // RESET ones are compiled with the bookkeeping too (both are switched at run time inside); one catch-all for
+    // non-default self-obs flags
+    static bool attr[7][64] = {};
+    const bool pdl = g_pdl != 0;
+    constexpr size_t SM = sizeof(FastSmem<4>);
+    if (!def) return launch_step(step_fast_kernel<4, 8, false, true, true, false>, SM, 4, p, stream, &attr[6][dev], pdl);
+    if (p.reset_on) {
+      if (p.obs_norm) return launch_step(step_fast_kernel<4, 8, true, true, true>, SM, 4, p, stream, &attr[5][dev], pdl);
+      return launch_step(step_fast_kernel<4, 8, false, true, true>, SM, 4, p, stream, &attr[4][dev], pdl);
+    }
+    if (p.obs_norm && p.ep_returns) return launch_step(step_fast_kernel<4, 8, true, true>, SM, 4, p, stream, &attr[3][dev], pdl);
+    if (p.ep_returns) return launch_step(step_fast_kernel<4, 8, false, true>, SM, 4, p, stream, &attr[2][dev], pdl);
+    if (p.obs_norm) return launch_step(step_fast_kernel<4, 8, true>, SM, 4, p, stream, &attr[1][dev], pdl);
+    return launch_step(step_fast_kernel<4, 8>, SM, 4, p, stream, &attr[0][dev], pdl);
   }
   // T > 1 on the AoS tensor + packed table: the pipelined TMA kernel
-  const bool multi = !g_force_generic && p.T > 1 && p.aos && p.L.packed && p.obs_vec2 && !p.obs_norm &&
+  const bool multi = !g_force_generic && p.T > 1 && p.aos && p.L.packed && p.obs_vec2 && !p.obs_norm && def &&
                      !(args->flags & PHC_STEP_MAPPED_HOST_IO);
   static bool attr_multi[64] = {}, attr_multi2[64] = {};
   // two query groups per block (measured: 2048 envs 21.6 -> 18.3 us, 4096 envs 43.7 -> 37.2, 16384 envs 128.2 -> 127.5)
@@ -3113,6 +3443,19 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
   if (rc == PHC_OK && p.ep_returns) {  // these kernels do not carry the episode bookkeeping: a second, small launch
     episode_bucket_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(p);
     rc = launch_status();
+  }
+  if (rc == PHC_OK && p.reset_on) {
+    // ... nor the in-step reset: phc_reset_envs behind them, reset_buf as its own mask (the step's flags are already
+    // in reset_out / terminate_out), the normalised rows and the moments kept consistent with the rewritten rows
+    ResetParams r;
+    rc = reset_fill(lib, args->auto_reset, n, r);
+    if (rc) return rc;
+    r.mask = p.reset;
+    r.norm = NormOut{p.obs_norm, p.obs_norm_stride, p.norm_mean, p.norm_var, p.norm_eps, p.norm_clip, p.norm_bf16};
+    r.moments = p.moments;
+    r.moment_buckets = p.moment_buckets;
+    r.moments_mode = p.moments ? 2 : 0;
+    rc = reset_launch(r, stream);
   }
   return rc;
 }

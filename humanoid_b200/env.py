@@ -72,6 +72,10 @@ class HumanoidPHC:
         rew_power_coef: float = 0.0005,  # config.py:112
         use_amp_obs: bool = False,  # config.py:98
         num_amp_obs_steps: int = 10,  # config.py:141
+        local_root_obs: bool = True,  # config.py:121
+        root_height_obs: bool = True,  # config.py:122
+        has_upright_start: bool = True,  # config.py:61
+        res_action: bool = False,  # config.py (False by default, humanoid_phc.py:1219)
     ):
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -90,6 +94,13 @@ class HumanoidPHC:
         self.use_power_reward = bool(use_power_reward)
         self.rew_power_coef = float(rew_power_coef)
         self.num_dof = 69
+        # self-observation flags (humanoid_phc.py:963-998); the defaults are the env's constants
+        self.local_root_obs, self.root_height_obs, self.has_upright_start = bool(local_root_obs), bool(root_height_obs), bool(has_upright_start)
+        self._obs_flags = (
+            (_cabi.OBS_LOCAL_ROOT if self.local_root_obs else 0) | (_cabi.OBS_ROOT_HEIGHT if self.root_height_obs else 0)
+            | (_cabi.OBS_UPRIGHT if self.has_upright_start else 0) | _cabi.STEP_OBS_FLAGS_SET
+        )  # fmt: skip
+        self.res_action = bool(res_action)
 
         N = num_envs
         # sim tensors (stand-in for the gymtorch-wrapped PhysX buffer, humanoid_phc.py:542-549)
@@ -105,7 +116,7 @@ class HumanoidPHC:
         self._pd_action_scale = torch.ones(self.num_dof, dtype=torch.float32, device=dev)
 
         # env buffers (humanoid_phc.py:556-597)
-        self.num_obs = _cabi.SELF_OBS_DIM + _cabi.TASK_OBS_DIM * self.time_steps  # :461-467
+        self.num_obs = (_cabi.SELF_OBS_DIM - (0 if self.root_height_obs else 1)) + _cabi.TASK_OBS_DIM * self.time_steps  # :461-467
         self.obs_buf = torch.zeros((N, self.num_obs), dtype=torch.float32, device=dev)
         self.rew_buf = torch.zeros(N, dtype=torch.float32, device=dev)  # (:560 calls the torch module; fixed)
         self.reward_raw = torch.zeros((N, 5), dtype=torch.float32, device=dev)  # 4 + power slot (:562-569)
@@ -113,6 +124,17 @@ class HumanoidPHC:
         self.reset_buf = torch.ones(N, dtype=torch.bool, device=dev)
         self._terminate_buf = torch.ones(N, dtype=torch.bool, device=dev)
         self.extras = {}
+        # what the reference keeps as separate tensors: extras["terminate"] = _terminate_buf.clone() (:151) and the
+        # step's reset flags (the in-step reset clears reset_buf / _terminate_buf as _reset_env_tensors does, :775-778)
+        self._terminate_out = torch.zeros(N, dtype=torch.bool, device=dev)
+        self._reset_out = torch.zeros(N, dtype=torch.bool, device=dev)
+        self.ref_dof_pos = torch.zeros((N, self.num_dof), dtype=torch.float32, device=dev) if self.res_action else None  # :1119
+        self._pd_target = torch.zeros((N, self.num_dof), dtype=torch.float32, device=dev)
+        self._rew_out = None  # set_reward_copy(): the wrapper's rewards.clone() written by the step itself
+        self.auto_reset = False  # enable_auto_reset(): the flagged envs are reset inside the step's launch
+        self._phase_pool = None
+        self._phase_cursor = 0
+        self._reset_args = None
         self._global_offset = torch.zeros((N, 3), dtype=torch.float32, device=dev)
         self._motion_start_times = torch.zeros(N, dtype=torch.float32, device=dev)
         self._motion_start_times_offset = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -278,6 +300,17 @@ class HumanoidPHC:
         # torch.bool is one byte holding 0/1 — the kernel writes uint8 0/1 straight into it
         a.reset_buf = self.reset_buf.data_ptr()
         a.terminate_buf = self._terminate_buf.data_ptr()
+        a.terminate_out = self._terminate_out.data_ptr()
+        a.reset_out = self._reset_out.data_ptr()
+        a.obs_flags = self._obs_flags
+        if self._rew_out is not None:
+            a.rew_out = self._rew_out.data_ptr()
+        if self.res_action:
+            a.ref_dof_pos = self.ref_dof_pos.data_ptr()
+            a.ref_dof_pos_stride = self.ref_dof_pos.stride(0)
+        if self.auto_reset:  # humanoid_phc.py:665-676 for the envs this step flags, inside the step's launch
+            self._reset_args = self._fill_reset_args(None, None)
+            a.auto_reset = C.pointer(self._reset_args)
         if self._obs_moment_buckets is not None:
             a.obs_moments = self._obs_moment_buckets.data_ptr()
             a.obs_moments_buckets = self._obs_moment_buckets.shape[0]
@@ -338,6 +371,41 @@ class HumanoidPHC:
         self._episode_buffers = buffers
         self._step_args = None
 
+    def set_reward_copy(self, rew_out: Optional[torch.Tensor]):
+        """``rew = self.rewards.clone()`` of ``PHCPufferEnv.step`` (clean_pufferl/env.py:121) as a second output of the
+        step kernel: ``rew_out [N]`` receives what ``rew_buf`` receives."""
+        if rew_out is not None:
+            _cabi.require_cuda(rew_out, "rew_out", torch.float32)
+        self._rew_out = rew_out
+        self._step_args = None
+
+    def enable_auto_reset(self, on: bool = True, phase_pool_steps: int = 32):
+        """Reset the envs a step flags INSIDE that step's launch (``PhcStepArgs.auto_reset``): what
+        ``PHCPufferEnv.step`` does with ``nonzero(reset_buf)`` + ``env.reset(indices)`` (clean_pufferl/env.py:133-135)
+        with no second launch and no host sync.  After such a step ``reset_buf`` / ``_terminate_buf`` read 0 (as
+        after the reference's reset, humanoid_phc.py:775-778); the step's own flags are ``extras["reset"]`` /
+        ``extras["terminate"]``.  The uniform numbers of ``sample_time_interval`` come from a pool drawn
+        ``phase_pool_steps`` steps at a time (one ``torch.rand`` launch per that many steps) unless ``step(phase_by_env=...)``
+        supplies them.  Buffers are bit-identical to ``step()`` followed by ``reset_done(phase)``."""
+        self.auto_reset = bool(on)
+        self._phase_pool_steps = int(phase_pool_steps)
+        self._step_args = None
+
+    def _next_phase(self, phase_by_env: Optional[torch.Tensor]) -> torch.Tensor:
+        if phase_by_env is not None:
+            ph = phase_by_env.to(self.device, torch.float32).contiguous()
+            self._phase_keep = ph
+            return ph
+        P = self._phase_pool_steps
+        if self._phase_pool is None or self._phase_cursor >= P:
+            if self._phase_pool is None:
+                self._phase_pool = torch.empty((P, self.num_envs), dtype=torch.float32, device=self.device)
+            self._phase_pool.uniform_()
+            self._phase_cursor = 0
+        ph = self._phase_pool[self._phase_cursor]
+        self._phase_cursor += 1
+        return ph
+
     def set_obs_normalizer(self, normalizer, dtype=torch.float32):
         """Fuse ``RunningNorm.forward`` (PHC/policies/running_norm.py:15-20) into the step: every step also
         writes ``obs_norm_buf = clamp((obs_buf - running_mean) / sqrt(running_var + eps), -clip, clip)`` —
@@ -369,14 +437,21 @@ class HumanoidPHC:
         a.rwd.w_pos, a.rwd.w_rot, a.rwd.w_vel, a.rwd.w_ang_vel = r["w_pos"], r["w_rot"], r["w_vel"], r["w_ang_vel"]
         a.rew_power_coef = self.rew_power_coef
 
-    def post_physics_step(self, advance_progress: bool = True):
-        """progress += 1; reward; reset; observations (humanoid_phc.py:138-149) — one launch."""
+    def post_physics_step(self, advance_progress: bool = True, phase_by_env: Optional[torch.Tensor] = None):
+        """progress += 1; reward; reset; observations (humanoid_phc.py:138-149) — one launch (with ``auto_reset`` the
+        reset of the flagged envs and their new observation rows too)."""
         cached = self._step_args
         if (cached is None or cached[1] != advance_progress or cached[3] != (self.flag_im_eval, self.use_power_reward,
                                                                              self.time_steps)):  # fmt: skip
             self._build_step_args(advance_progress)  # these three change which pointers the struct carries
         a = self._step_args[0]
         self._refresh_step_scalars(a)
+        if self.auto_reset:
+            r = self._reset_args
+            r.phase = self._next_phase(phase_by_env).data_ptr()
+            r.state_init = _cabi.STATE_INIT_RANDOM if self.state_init_random else _cabi.STATE_INIT_START
+            r.flag_test = 1 if self.flag_test else 0
+            r.dt = self.dt
         _cabi.check(
             _cabi.load().phc_step_fused(
                 self._motion_lib.handle, C.byref(a), self.num_envs, _cabi.stream_ptr(self.device)
@@ -386,15 +461,28 @@ class HumanoidPHC:
         if self._obs_moment_buckets is not None:
             self.obs_moment_rows += self.num_envs
 
-    def step(self, actions=None):
-        """The reference's ``step`` minus PD targets and PhysX (both out of scope): the caller
-        has already written the post-physics rigid-body state."""
-        self.post_physics_step(True)
-        self.extras["terminate"] = self._terminate_buf
+    def pre_physics_step(self, actions: torch.Tensor, clip: float = 0.0, actions_out: Optional[torch.Tensor] = None):
+        """The pre-physics half of ``step`` (:105-128): actions -> PD targets in ``self._pd_target`` (what the
+        reference hands to ``gym.set_dof_position_target_tensor``), one launch.  With ``clip`` the wrapper's
+        ``np.clip(actions, -clip, clip)`` (clean_pufferl/env.py:110-112) rides in the same launch and the clipped
+        actions are stored in ``actions_out``."""
+        return self._action_to_pd_targets(actions, res_action=self.res_action, ref_dof_pos=self.ref_dof_pos,
+                                          clip=clip, actions_out=actions_out, out=self._pd_target)  # fmt: skip
+
+    def step(self, actions=None, phase_by_env: Optional[torch.Tensor] = None):
+        """The reference's ``step`` minus PhysX (out of scope): the caller has already written the post-physics
+        rigid-body state.  ``actions`` (optional) are turned into PD targets first, as :105-128 does."""
+        if actions is not None:
+            self.pre_physics_step(actions)
+        self.post_physics_step(True, phase_by_env)
+        self.extras["terminate"] = self._terminate_out  # = _terminate_buf.clone() (:151)
+        self.extras["reset"] = self._reset_out
         self.extras["reward_raw"] = self.reward_raw
         if self.use_amp_obs:  # :153-157
             self._amp_step(roll=True)
             self.extras["amp_obs"] = self.amp_obs
+            if self.auto_reset:  # _reset_envs (:675-676) for the envs the step has just reset
+                self._init_amp_obs_masked(self._reset_out)
         if self.flag_im_eval:  # :159-167 (body_pos / body_pos_gt are host copies the caller can take itself)
             self.extras["mpjpe"] = self._mpjpe
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
@@ -464,7 +552,8 @@ class HumanoidPHC:
     # pre-physics: actions -> PD targets (humanoid_phc.py:105-128, 1218-1228)
     # ------------------------------------------------------------------------------------
     def _action_to_pd_targets(self, action: torch.Tensor, res_action: bool = False, ref_dof_pos=None,
-                              freeze_hand: bool = False, freeze_toe: bool = False) -> torch.Tensor:  # fmt: skip
+                              freeze_hand: bool = False, freeze_toe: bool = False, clip: float = 0.0,
+                              actions_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:  # fmt: skip
         """``pd_action_offset + pd_action_scale * action`` (or the clamped residual form), with the
         hand / toe joints zeroed as ``step()`` does when ``freeze_hand`` / ``freeze_toe`` are set.
         ``self._pd_action_offset`` / ``_pd_action_scale`` are [69] tensors the owner fills
@@ -472,7 +561,12 @@ class HumanoidPHC:
         _cabi.require_cuda(action, "action", torch.float32)
         action = action.contiguous()
         n, D = action.shape
-        out = torch.empty_like(action)
+        if out is None:
+            out = torch.empty_like(action)
+        if actions_out is not None:
+            _cabi.require_cuda(actions_out, "actions_out", torch.float32)
+            if actions_out.shape != action.shape or not actions_out.is_contiguous():
+                raise ValueError("actions_out must be a contiguous tensor of the actions' shape")
         dof_names = BODY_NAMES[1:]
         mask = 0
         if freeze_hand:
@@ -484,7 +578,8 @@ class HumanoidPHC:
             _cabi.load().phc_action_to_pd_targets(
                 action.data_ptr(), self._pd_action_offset.data_ptr(), self._pd_action_scale.data_ptr(),
                 1 if res_action else 0, _cabi.ptr(ref), self._dof_pos.data_ptr(), self._dof_pos.stride(0),
-                self._dof_pos.stride(1), mask, n, D, out.data_ptr(), _cabi.stream_ptr(self.device),
+                self._dof_pos.stride(1), mask, n, D, float(clip), _cabi.ptr(actions_out), out.data_ptr(),
+                _cabi.stream_ptr(self.device),
             ),
             "phc_action_to_pd_targets",
         )  # fmt: skip
@@ -493,7 +588,7 @@ class HumanoidPHC:
     # ------------------------------------------------------------------------------------
     # reset (humanoid_phc.py:90-103, 665-778) — on the device, no host sync
     # ------------------------------------------------------------------------------------
-    def _reset_masked(self, mask: torch.Tensor, phase_by_env: torch.Tensor):
+    def _fill_reset_args(self, mask: Optional[torch.Tensor], phase_by_env: Optional[torch.Tensor], moments_mode: int = 0):
         body, keep = _cabi.body_state(
             self._rigid_body_pos, self._rigid_body_rot, self._rigid_body_vel, self._rigid_body_ang_vel
         )
@@ -512,14 +607,38 @@ class HumanoidPHC:
         a.motion_start_times_offset = self._motion_start_times_offset.data_ptr()
         a.global_offset = self._global_offset.data_ptr()
         a.sampled_motion_ids = self._sampled_motion_ids.data_ptr()
-        a.env_mask = mask.data_ptr()
-        a.phase = phase_by_env.data_ptr()
+        a.env_mask = _cabi.ptr(mask)
+        a.phase = _cabi.ptr(phase_by_env)
         a.state_init = _cabi.STATE_INIT_RANDOM if self.state_init_random else _cabi.STATE_INIT_START
         a.flag_test = 1 if self.flag_test else 0
         a.time_steps = self.time_steps
         a.dt = self.dt
         a.obs_buf = self.obs_buf.data_ptr()
         a.obs_stride = self.obs_buf.stride(0)
+        a.obs_flags = self._obs_flags
+        if self.res_action:
+            a.ref_dof_pos = self.ref_dof_pos.data_ptr()
+            a.ref_dof_pos_stride = self.ref_dof_pos.stride(0)
+        # keep the step's fused epilogues consistent with the rows a reset rewrites: the policy reads obs_norm_buf,
+        # and RunningNorm.update must see the rows the policy saw (experience.obs holds the post-reset rows)
+        if self.obs_normalizer is not None:
+            rn = self.obs_normalizer
+            a.obs_norm = self.obs_norm_buf.data_ptr()
+            a.obs_norm_stride = self.obs_norm_buf.stride(0)
+            a.norm_mean, a.norm_var = rn.running_mean.data_ptr(), rn.running_var.data_ptr()
+            a.norm_epsilon, a.norm_clip = rn.epsilon, rn.clip
+            a.obs_norm_bf16 = 1 if self.obs_norm_buf.dtype == torch.bfloat16 else 0
+        if self._obs_moment_buckets is not None and moments_mode:
+            a.obs_moments_mode = moments_mode
+            a.obs_moments = self._obs_moment_buckets.data_ptr()
+            a.obs_moments_buckets = self._obs_moment_buckets.shape[0]
+        a._keep = (keep, mask, phase_by_env)
+        return a
+
+    def _reset_masked(self, mask: torch.Tensor, phase_by_env: torch.Tensor, moments_mode: int = 0):
+        """``moments_mode``: 1 = the new rows are added to the step's RunningNorm partials (rows never counted: a
+        ``reset()``), 2 = they replace the rows the flagging step had counted (``reset_done()``)."""
+        a = self._fill_reset_args(mask, phase_by_env, moments_mode)
         _cabi.check(
             _cabi.load().phc_reset_envs(self._motion_lib.handle, C.byref(a), self.num_envs, _cabi.stream_ptr(self.device)),
             "phc_reset_envs",
@@ -542,7 +661,9 @@ class HumanoidPHC:
         mask[env_ids] = True
         by_env = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
         by_env[env_ids] = phase.to(self.device, torch.float32)
-        self._reset_masked(mask, by_env)
+        self._reset_masked(mask, by_env, moments_mode=1)
+        if self._obs_moment_buckets is not None:
+            self.obs_moment_rows += int(env_ids.numel())  # rows the policy will see and no step has counted
         return self.obs_buf
 
     def reset_done(self, phase_by_env: Optional[torch.Tensor] = None):
@@ -554,7 +675,7 @@ class HumanoidPHC:
         # the reset kernel reads each mask byte once before it clears reset_buf, so reset_buf can be its own mask;
         # the AMP initialisation that follows needs the flags after they are cleared, hence the copy there
         mask = self.reset_buf.clone() if self.use_amp_obs else self.reset_buf
-        self._reset_masked(mask, phase_by_env.to(self.device, torch.float32).contiguous())
+        self._reset_masked(mask, phase_by_env.to(self.device, torch.float32).contiguous(), moments_mode=2)
         return self.obs_buf
 
     def set_humanoid_assets(self, skeleton_trees, humanoid_shapes, humanoid_limb_and_weights):
@@ -657,7 +778,8 @@ class HumanoidPHC:
         sel = (lambda x: x) if env_ids is None else (lambda x: x[env_ids])
         return compute_humanoid_observations_smpl_max(
             sel(self._rigid_body_pos), sel(self._rigid_body_rot), sel(self._rigid_body_vel),
-            sel(self._rigid_body_ang_vel), None, None, True, True, True, False, False,
+            sel(self._rigid_body_ang_vel), None, None, self.local_root_obs, self.root_height_obs,
+            self.has_upright_start, False, False,
         )  # fmt: skip
 
     def _compute_task_obs(self, env_ids=None):  # :1050-1123
@@ -673,9 +795,15 @@ class HumanoidPHC:
                 return refs[0][key]
             return torch.stack([r[key] for r in refs], dim=1).flatten(0, 1)
 
+        if self.res_action:  # :1115-1120
+            if env_ids is None:
+                self.ref_dof_pos[:] = refs[0]["dof_pos"]
+            else:
+                self.ref_dof_pos[env_ids] = refs[0]["dof_pos"]
         return compute_imitation_observations_v6(
             pos[..., 0, :], rot[..., 0, :], pos, rot, vel, ang,
-            stack("rg_pos"), stack("rb_rot"), stack("body_vel"), stack("body_ang_vel"), self.time_steps, True,
+            stack("rg_pos"), stack("rb_rot"), stack("body_vel"), stack("body_ang_vel"), self.time_steps,
+            self.has_upright_start,
         )  # fmt: skip
 
     def _compute_observations(self, env_ids=None):  # :937-961

@@ -2,6 +2,10 @@
 over the B200 ``HumanoidPHC`` shim, with the per-step episode bookkeeping (:121-159) as one
 kernel (``phc_episode_update``) and the reset of flagged envs on the device (``reset_done``).
 
+``fused=True`` is the whole wrapper step in TWO launches around the physics: (1) the action clip (:110-112) with
+the PD targets of ``env.step`` (humanoid_phc.py:105-128) — ``phc_action_to_pd_targets`` — and (2) the fused step
+with the episode bookkeeping, the ``rewards.clone()`` (:121) and the reset of the flagged envs (:133-135) inside it.
+
 What changes against the reference, and why: the reference finds the flagged envs with
 ``torch.nonzero(reset_buf)`` and appends their returns / lengths to Python lists — two host
 syncs and a device-to-host copy every step.  Here the lists are replaced by four running sums
@@ -53,10 +57,13 @@ class PHCPufferEnv:
         # and with 32 rows the 9 sums of 32 blocks each queued on one line at the tail of every step
         buckets = max(32, min(4096, (N + 3) // 4))
         self._ep_sums = torch.zeros((buckets, _cabi.EPISODE_SUM_COLS), dtype=torch.float64, device=dev) if fused else None
+        self._rew = torch.zeros(N, dtype=torch.float32, device=dev)  # `rew = self.rewards.clone()` lives here when fused
         if fused:
             env.set_episode_buffers(dict(terminals=self.terminals, truncations=self.truncations, masks=self.masks,
                                          episode_returns=self.episode_returns, episode_lengths=self.episode_lengths,
                                          sums=self._ep_sums))  # fmt: skip
+            env.set_reward_copy(self._rew)
+            env.enable_auto_reset(True)
 
     def _fold(self):
         if self.fused:
@@ -114,16 +121,24 @@ class PHCPufferEnv:
         """:109-183.  ``actions`` may be a numpy array (as pufferlib passes it) or a device tensor."""
         if isinstance(actions, np.ndarray):
             actions = torch.from_numpy(actions).to(self.device, non_blocking=True)
-        if self.clip_actions:
-            torch.clamp(actions, -1, 1, out=self.actions)
+        if self.fused:
+            # launch 1, before the physics: clip into self.actions + PD targets (env._pd_target)
+            self.env.pre_physics_step(actions.to(torch.float32), clip=1.0 if self.clip_actions else 0.0, actions_out=self.actions)
+            # (PhysX steps here in the reference; the owner of the shim writes the post-physics state)
+            # launch 2: progress, reward, flags, bookkeeping, reward copy, reset of the flagged envs, observations
+            self.env.step(None, phase_by_env)
+            self.amp_obs = getattr(self.env, "amp_obs", None) if self.use_amp_obs else None
+            rew = self._rew  # rewritten by the next step (the reference returns a fresh clone every step)
         else:
-            self.actions.copy_(actions)
-        self.env.step(self.actions)
-        self.amp_obs = getattr(self.env, "amp_obs", None) if self.use_amp_obs else None
-        rew = self.rewards.clone()
-        if not self.fused:
+            if self.clip_actions:
+                torch.clamp(actions, -1, 1, out=self.actions)
+            else:
+                self.actions.copy_(actions)
+            self.env.step(self.actions)
+            self.amp_obs = getattr(self.env, "amp_obs", None) if self.use_amp_obs else None
+            rew = self.rewards.clone()
             self.update_episodes()
-        self.env.reset_done(phase_by_env)  # :133-135 without the nonzero() sync
+            self.env.reset_done(phase_by_env)  # :133-135 without the nonzero() sync
         info = []
         self.tick += 1
         if self.tick % self.log_interval == 0:

@@ -29,7 +29,8 @@
 extern "C" {
 #endif
 
-#define PHC_ABI_VERSION 2 /* 2: PhcStepArgs grew (obs_moments_buckets, ep_*), phc_motion_build / phc_peer_reduce_* / phc_episode_fold added */
+#define PHC_ABI_VERSION 3 /* 3: PhcStepArgs grew (rew_out, reset_out, terminate_out, auto_reset, ref_dof_pos, obs_flags), PhcResetArgs grew (obs_norm*, obs_moments*),
+                              phc_action_to_pd_targets takes the action clip; 2: obs_moments_buckets, ep_*, phc_motion_build / phc_peer_reduce_* / phc_episode_fold */
 #define PHC_NUM_BODIES 24      /* SMPL humanoid, body_sets.py:11-36 */
 #define PHC_SELF_OBS_DIM 358   /* envs/humanoid_phc.py:461 */
 #define PHC_TASK_OBS_DIM 576   /* per future step, envs/humanoid_phc.py:464 */
@@ -216,6 +217,7 @@ PHC_API int phc_im_reset(const PhcView* rigid_body_pos, const PhcView* ref_body_
 #define PHC_STEP_OBS_NORM_BF16 2u  /* obs_norm points to bfloat16 rows (the policy's input dtype under autocast): each
                                       normalised fp32 value is rounded to nearest-even; obs_norm_stride counts bf16 elements */
 #define PHC_EPISODE_SUM_COLS 12
+struct PhcResetArgs;
 typedef struct PhcStepArgs {
   PhcBodyState body;                     /* sim state views, J must be 24               */
   int16_t* progress_buf;                 /* [n] in/out                  humanoid_phc.py:571 */
@@ -284,7 +286,33 @@ typedef struct PhcStepArgs {
   double* ep_sums;                       /* [ep_buckets][PHC_EPISODE_SUM_COLS], zeroed by the caller once */
   int32_t ep_buckets;                    /* 1 .. 4096; ceil(n / 4) = one row per block    */
   int32_t ep_raw_cols;                   /* columns of reward_raw that are logged, <= 8 */
+  /* ---- ABI 3 ------------------------------------------------------------------------------------------------- */
+  float* rew_out;                        /* NULL or [n]: a second copy of rew_buf — `rew = self.rewards.clone()` of
+                                            PHCPufferEnv.step (clean_pufferl/env.py:121), written with it            */
+  uint8_t* reset_out;                    /* NULL or [n]: the step's reset flags, kept when auto_reset clears reset_buf */
+  uint8_t* terminate_out;                /* NULL or [n]: extras["terminate"] = _terminate_buf.clone()  humanoid_phc.py:151 */
+  /* The reset of the envs this step flags, INSIDE the step (clean_pufferl/env.py:133-135 -> HumanoidPHC.reset(indices),
+   * humanoid_phc.py:665-676), off when NULL.  A block that has flagged envs re-poses them from the motion library
+   * (exactly phc_reset_envs: sample_time_interval, full get_motion_state, _set_env_state scatter, clock and buffer
+   * resets), recomputes their observation rows from the new state before the rows leave shared memory, and clears
+   * reset_buf / terminate_buf / progress_buf of those envs; the step's own flags survive in reset_out /
+   * terminate_out, and the moments / normaliser epilogues and the episode bookkeeping see what the reference's
+   * wrapper would see (final rows, the step's flags).  Every buffer is bit-identical to phc_step_fused followed by
+   * phc_reset_envs(env_mask = reset_buf).  The struct's body / progress_buf / reset_buf / terminate_buf / obs_buf /
+   * sampled_motion_ids / clock pointers / time_steps / dt must be the step's own (PHC_ERR_SHAPE otherwise); env_mask
+   * is ignored.  Kernels without the in-kernel path (T > 1, strided inputs) are followed by phc_reset_envs.         */
+  const struct PhcResetArgs* auto_reset;
+  /* res_action (humanoid_phc.py:1115-1120, 1218-1228): the reference keeps ref_dof_pos = dof_pos of the motion query
+   * at the observation time t + dt for the next _action_to_pd_targets.  NULL, or [n, 69] (needs the library's lrs).  */
+  float* ref_dof_pos;
+  int64_t ref_dof_pos_stride;
+  /* self-observation flags of compute_humanoid_observations_smpl_max (humanoid_phc.py:963-998, config.py:61-69):
+   * PHC_OBS_LOCAL_ROOT | PHC_OBS_ROOT_HEIGHT | PHC_OBS_UPRIGHT.  0 means the env's defaults (all three); any other
+   * combination changes the self-obs columns (no height column: 357 + 576 T floats per row) and, for !upright, the
+   * heading both observations are expressed in.  PHC_STEP_OBS_FLAGS_SET marks the field as given.                   */
+  uint32_t obs_flags;
 } PhcStepArgs;
+#define PHC_STEP_OBS_FLAGS_SET 0x80000000u
 
 PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream);
 
@@ -326,6 +354,23 @@ typedef struct PhcResetArgs {
   float dt;
   float* obs_buf;                         /* [n, 358+576*T]: rows of the selected envs rewritten */
   int64_t obs_stride;
+  /* ---- ABI 3: keep the step's fused epilogues consistent with the rows a reset rewrites ------------------------- */
+  float* obs_norm;                        /* NULL, or the normalised copy of obs_buf (PhcStepArgs.obs_norm): the rows of
+                                             the selected envs are rewritten too          policies/running_norm.py:15-20 */
+  int64_t obs_norm_stride;
+  const float* norm_mean;                 /* [358+576*T] */
+  const float* norm_var;                  /* [358+576*T] */
+  float norm_epsilon, norm_clip;
+  int32_t obs_norm_bf16;                  /* obs_norm holds bfloat16 rows */
+  int32_t obs_moments_mode;               /* 0: moments untouched; 1: the new rows are ADDED (an initial reset: the rows
+                                             were never counted); 2: the old rows are REPLACED (subtract old, add new:
+                                             the step that flagged the envs had counted the rows it wrote)             */
+  double* obs_moments;                    /* NULL, or [buckets][2*(358+576*T)] fp64 accumulators as in PhcStepArgs      */
+  int32_t obs_moments_buckets;
+  uint32_t obs_flags;                     /* as PhcStepArgs.obs_flags (0 = the env's defaults)                          */
+  float* ref_dof_pos;                     /* NULL or [n, 69]: _compute_task_obs(env_ids) of the reset keeps the dof_pos of
+                                             the query at t + dt for res_action            humanoid_phc.py:1115-1120 */
+  int64_t ref_dof_pos_stride;
 } PhcResetArgs;
 PHC_API int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* args, int64_t n, phc_stream_t stream);
 
@@ -355,11 +400,15 @@ PHC_API int phc_set_trace_buffer(uint64_t* device_buf, int64_t capacity_warps);
  *   res_action != 0:  pd = clamp(ref_dof_pos + pd_action_scale * action, dof_pos -+ pi/2)
  * offset / scale are [D]; action, ref_dof_pos, out are dense [n, D]; dof_pos is the strided view
  * of the dof state.  The freeze_hand / freeze_toe zeroing of step() (:118-127) is `zero_mask`:
- * bit j set = the 3 dofs of joint j are written as 0. */
+ * bit j set = the 3 dofs of joint j are written as 0.
+ * The wrapper's action clip rides in the same launch (clean_pufferl/env.py:110-112: np.clip(actions, -1, 1) into
+ * self.actions, which env.step then turns into PD targets): with action_clip > 0 the action is clamped to
+ * [-action_clip, action_clip] first; when actions_out is not NULL the (clamped) action is stored there. */
 PHC_API int phc_action_to_pd_targets(const float* action, const float* pd_action_offset, const float* pd_action_scale,
                                      int32_t res_action, const float* ref_dof_pos, const float* dof_pos,
                                      int64_t dof_pos_stride, int64_t dof_pos_elem_stride, uint32_t zero_mask,
-                                     int64_t n, int32_t num_dof, float* out, phc_stream_t stream);
+                                     int64_t n, int32_t num_dof, float action_clip, float* actions_out, float* out,
+                                     phc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Host-buffer pipeline around the fused step (the end-to-end call): chunked

@@ -1209,12 +1209,200 @@ def test_episode_bookkeeping_fused_into_the_step_equals_the_standalone_kernel(N,
         capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
     (a, ea, ia), (b, eb, ib) = outs
     assert torch.equal(ea.obs_buf, eb.obs_buf) and torch.equal(ea.rew_buf, eb.rew_buf)
-    for k in ("terminals", "truncations", "masks", "episode_returns", "episode_lengths"):
+    for k in ("terminals", "truncations", "masks", "episode_returns", "episode_lengths", "actions"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
+    # fused=True also resets the flagged envs inside the step's launch: every buffer the two-launch path (step, then
+    # reset_done) leaves must be there bit for bit, and the normalised rows must be those of the FINAL obs rows
+    for k in ("_rigid_body_state_reshaped", "_humanoid_root_states", "_dof_state", "progress_buf", "reset_buf",
+              "_terminate_buf", "_motion_start_times", "_motion_start_times_offset", "_global_offset", "reward_raw"):
+        assert torch.equal(getattr(ea, k), getattr(eb, k)), k
+    assert not bool(eb.reset_buf.any()) and not bool(eb._terminate_buf.any())
+    assert torch.equal(eb.extras["terminate"], b.terminals) and torch.equal(eb.extras["reset"], b.terminals | b.truncations)
+    if "norm" in mode:
+        assert torch.equal(ea.obs_norm_buf, eb.obs_norm_buf)
+        assert_close(eb.obs_norm_buf, eb.obs_normalizer(eb.obs_buf), what="obs_norm_buf after resets", rtol=1e-6, atol=1e-6)
     assert len(ia) == len(ib) == 1 and a.episode_count == b.episode_count > 0
     for k, v in ia[0].items():
         assert abs(v - ib[0][k]) <= 1e-12 + 1e-6 * abs(v), (k, v, ib[0][k])  # raw_rewards accumulate in fp32 per step vs per log
     assert float(b._ep_sums.abs().max()) == 0.0  # folded and cleared
+
+
+def _reset_case(N, T=1, seed=777, **env_kw):
+    lib_data, clock, state = _gpu_case(N, 48, seed, max_progress=30, max_frames=90)
+    lib = MotionLib(lib_data, device=DEV)
+    from humanoid_b200 import HumanoidPHC
+
+    def make():
+        env = HumanoidPHC(lib, N, device=DEV, time_steps=T, **env_kw)
+        env.set_sim_state(state)
+        env.set_clock(clock)
+        # a dof state / root state that the reset must overwrite for the flagged envs only
+        env._dof_state.copy_(torch.randn(env._dof_state.shape, generator=torch.Generator().manual_seed(3)).to(DEV))
+        env._humanoid_root_states.fill_(0.5)
+        return env
+
+    return make
+
+
+ENV_BUFFERS = ("obs_buf", "rew_buf", "reward_raw", "_rigid_body_state_reshaped", "_humanoid_root_states", "_dof_state",
+               "progress_buf", "reset_buf", "_terminate_buf", "_motion_start_times", "_motion_start_times_offset",
+               "_global_offset")  # fmt: skip
+
+
+@pytest.mark.parametrize("N,T,mode", [(4096, 1, "fast"), (1029, 1, "fast"), (3, 1, "fast"), (1029, 1, "fast_eval"),
+                                      (1000, 1, "generic"), (515, 3, "multi"), (700, 1, "fast_start"),
+                                      (1029, 1, "fast_res_action"), (515, 2, "multi_res_action")])  # fmt: skip
+def test_reset_inside_the_step_equals_step_then_reset_bitwise(N, T, mode):
+    """PhcStepArgs.auto_reset: the envs a step flags are re-posed, their clocks restarted and their observation rows
+    recomputed inside the step's own launch.  Every buffer equals step() followed by reset_done(phase) — three steps
+    deep, so that the steps after a reset (progress 0, new start time, zeroed offsets) are covered as well."""
+    from humanoid_b200 import _cabi
+
+    kw = dict(res_action=True) if "res_action" in mode else {}
+    make = _reset_case(N, T, **kw)
+    a, b = make(), make()
+    b.enable_auto_reset(True)
+    for e in (a, b):
+        if "eval" in mode:
+            e.flag_im_eval = True
+            e.set_termination_distances(0.1)
+        if "start" in mode:
+            e.state_init_random = False
+    gen = torch.Generator().manual_seed(4)
+    capi = _cabi.load()
+    capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if mode == "generic" else 0)
+    try:
+        for k in range(3):
+            phase = cuda(torch.rand(N, generator=gen))
+            a.step()
+            flags = (a.reset_buf.clone(), a._terminate_buf.clone())
+            a.reset_done(phase)
+            b.step(phase_by_env=phase)
+            torch.cuda.synchronize()
+            assert 0 < int(flags[0].sum()) < N or N < 8, "the case should flag some envs and spare others"
+            for name in ENV_BUFFERS:
+                assert torch.equal(getattr(a, name), getattr(b, name)), f"step {k}: {name}"
+            assert torch.equal(b.extras["reset"], flags[0]) and torch.equal(b.extras["terminate"], flags[1])
+            assert not bool(b.reset_buf.any()) and not bool(b._terminate_buf.any())
+            if "res_action" in mode:
+                assert torch.equal(a.ref_dof_pos, b.ref_dof_pos), f"step {k}: ref_dof_pos"
+    finally:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("auto", [True, False], ids=["reset_in_step", "reset_done"])
+def test_normalised_rows_and_moments_follow_the_rows_a_reset_rewrites(auto, dtype):
+    """The policy reads obs_norm_buf and RunningNorm.update must see what the policy saw: after a step whose flagged
+    envs were reset (inside the step, or by reset_done()), obs_norm_buf == rn(obs_buf) for the FINAL rows and the
+    fp64 partials are the column moments of the final rows — the initial reset()'s rows included."""
+    from humanoid_b200 import HumanoidPHC, RunningNorm
+
+    N = 2052
+    lib_data, clock, state = _gpu_case(N, 48, 991, max_progress=30, max_frames=90)
+    lib = MotionLib(lib_data, device=DEV)
+    env = HumanoidPHC(lib, N, device=DEV, obs_moments=True)
+    rn = RunningNorm(env.num_obs, device=DEV)
+    rn.running_mean.normal_(generator=torch.Generator(device=DEV).manual_seed(1))
+    rn.running_var.uniform_(0.5, 2.0, generator=torch.Generator(device=DEV).manual_seed(2))
+    env.set_obs_normalizer(rn, dtype=dtype)
+    env.enable_auto_reset(auto)
+    gen = torch.Generator().manual_seed(6)
+    env.reset(phase=cuda(torch.rand(N, generator=gen)))  # the rows the policy sees first
+    want = torch.zeros(2 * env.num_obs, dtype=torch.float64, device=DEV)
+    rows = 0
+
+    def check(tag):
+        nonlocal rows
+        x = env.obs_buf.double()
+        want[: env.num_obs] += x.sum(0)
+        want[env.num_obs :] += (x * x).sum(0)
+        rows += N
+        ref = rn(env.obs_buf)
+        if dtype == torch.bfloat16:
+            assert torch.equal(env.obs_norm_buf, ref.to(torch.bfloat16)) or (
+                (env.obs_norm_buf.float() - ref).abs().max() <= 0.0626), tag  # 1 bf16 ulp at |x| <= 10 (the quotient is within 1 fp32 ulp of IEEE division)
+        else:
+            assert_close(env.obs_norm_buf, ref, what=f"obs_norm_buf {tag}", rtol=1e-6, atol=1e-6)
+
+    check("after reset()")
+    for k in range(3):
+        env.set_sim_state(state)  # the "physics": every step sees the noisy state again, so envs keep getting flagged
+        phase = cuda(torch.rand(N, generator=gen))
+        if auto:
+            env.step(phase_by_env=phase)
+        else:
+            env.step()
+            assert 0 < int(env.reset_buf.sum()) < N
+            env.reset_done(phase)
+        check(f"after step {k}")
+    sums, got_rows = env.take_obs_moments()
+    assert got_rows == rows
+    scale = want.abs().clamp_min(1.0)
+    assert float(((sums - want).abs() / scale).max()) < 1e-11, "moments must be those of the rows the policy saw"
+
+
+FLAG_SETS = [(True, True, True), (False, True, True), (True, False, True), (True, True, False), (False, False, False)]
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS, ids=lambda f: "local%d_height%d_upright%d" % tuple(map(int, f)))
+@pytest.mark.parametrize("kernel", ["fast", "generic", "reset_in_step"])
+def test_self_obs_flag_variants_on_the_fused_path(flags, kernel):
+    """local_root_obs / root_height_obs / has_upright_start (humanoid_phc.py:963-998, config.py:61-69) on the fused
+    kernels: rows equal the per-function kernels bit for bit (those are pinned by the reference's `flags` fixture)
+    and the oracle within the float tolerance; without the height column a row has 933 floats."""
+    from humanoid_b200 import _cabi
+
+    local, height, upright = flags
+    N = 1030
+    make = _reset_case(N, 1, seed=313, local_root_obs=local, root_height_obs=height, has_upright_start=upright)
+    env, ref = make(), make()
+    assert env.num_obs == 934 - (0 if height else 1)
+    capi = _cabi.load()
+    capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if kernel == "generic" else 0)
+    try:
+        if kernel == "reset_in_step":
+            env.enable_auto_reset(True)
+            phase = cuda(torch.rand(N, generator=torch.Generator().manual_seed(1)))
+            env.step(phase_by_env=phase)
+            ref.step()
+            ref.reset_done(phase)
+        else:
+            env.step()
+            ref.post_physics_step_unfused()
+    finally:
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+    assert torch.equal(env.obs_buf, ref.obs_buf), "fused rows differ from the per-function / two-launch rows"
+    assert torch.equal(env.rew_buf, ref.rew_buf) and torch.equal(env.progress_buf, ref.progress_buf)
+    if kernel != "reset_in_step":
+        st = env._rigid_body_state_reshaped.cpu()
+        pos, rot, vel, ang = synth.body_views(st)
+        want = O.self_obs_smpl_max(pos, rot, vel, ang, None, None, local, height, upright, False, False)
+        assert_close(env.obs_buf[:, : want.shape[1]], want, what="self obs vs oracle", **OBS_TOL)
+
+
+def test_ref_dof_pos_of_the_fused_step_equals_the_motion_query():
+    """res_action (humanoid_phc.py:1115-1120): the step keeps dof_pos of the query at t + dt; equal to K1's dof_pos."""
+    N = 2050
+    for T, generic in ((1, False), (1, True), (3, False)):
+        from humanoid_b200 import _cabi
+
+        make = _reset_case(N, T, seed=99, res_action=True)
+        env = make()
+        _cabi.load().phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if generic else 0)
+        try:
+            env.step()
+        finally:
+            _cabi.load().phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+        t1 = env._motion_times(plus=1)
+        want = env._motion_lib.get_motion_state(env._sampled_motion_ids, t1, env._global_offset)["dof_pos"]
+        assert torch.equal(env.ref_dof_pos, want), f"T={T} generic={generic}"
+        # and the PD targets of the next pre-physics step use it (clamped residual form)
+        act = cuda(torch.rand(N, 69, generator=torch.Generator().manual_seed(2)) * 4 - 2)
+        pd = env.pre_physics_step(act, clip=1.0, actions_out=torch.empty_like(act))
+        want_pd = O.action_to_pd_targets(act.clamp(-1, 1).cpu(), env._pd_action_offset.cpu(), env._pd_action_scale.cpu(),
+                                         res_action=True, ref_dof_pos=want.cpu(), dof_pos=env._dof_pos.cpu())
+        assert_equal_exact(pd, want_pd, "pd targets (res_action, clipped actions)")
 
 
 # ---------------------------------------------------------------------------------------

@@ -30,6 +30,8 @@ OPT_STEP_EPB = 2
 OPT_STEP_PDL = 3
 OPT_TEST_SPEC_FAULT = 4
 OPT_MULTI_GROUPS = 5
+OPT_MOMENTS_BULK = 6
+OPT_STEP_PERSIST = 7
 
 STATE_INIT_START = 0
 STATE_INIT_RANDOM = 1

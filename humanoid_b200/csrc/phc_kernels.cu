@@ -134,6 +134,15 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+// shared -> global with an fp64 add at the destination (TMA bulk reduction, SASS UBLKRED): the L2 does the adds
+__device__ __forceinline__ void bulk_reduce_add_f64(double* gmem_dst, const double* smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;\n" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -972,6 +981,7 @@ struct StepParams {
   uint8_t* term;
   double* moments;
   int moment_buckets;  // >= 1: moments is [buckets][2W]; block b adds into bucket b % buckets
+  int moments_bulk;    // the T = 1 kernel hands its partials to TMA bulk reductions instead of issuing atomics
   // episode bookkeeping of the pufferlib wrapper fused into the step (clean_pufferl/env.py:121-159), off when ep_returns is NULL
   uint8_t *ep_terminals, *ep_truncations, *ep_masks;
   float* ep_returns;
@@ -1008,6 +1018,7 @@ struct StepParams {
   int selfw;           // 357 + of.hcol
   int reset_on;        // the flagged envs are reset inside the step (PhcStepArgs.auto_reset)
   ResetTargets rw;
+  unsigned* tile_counter;  // persistent kernel: [0] next tile to draw, [1] blocks that have left (both 0 between launches)
 };
 
 __host__ __device__ __forceinline__ bool default_obs_flags(const ObsFlags& f) { return f.hcol && f.local_root && f.upright; }
@@ -1494,38 +1505,58 @@ __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, 
 }
 
 // The reset of the envs a step flags, inside the step (PhcStepArgs.auto_reset; clean_pufferl/env.py:133-135 ->
-// humanoid_phc.py:665-676).  Called by EVERY thread of a block that has a flagged env, after phase 1: a thread of a
-// flagged env re-poses its body from the motion library (reset_scatter_thread, the arithmetic of phc_reset_envs),
-// body 0 publishes the new root position and heading, and after the block barrier the thread holds what the
-// observation of the new state needs — its body's new state and the reference body at the new t + dt.  Kept out
-// of line: the common path (no env flagged) pays a handful of instructions for the test and nothing else.
-template <int EPB>
-__device__ __noinline__ void reset_in_step(const StepParams& p, FastSmem<EPB>& S, bool mine, int e, int b, int64_t env,
-                                           Vec3& pos, Quat& rot, Vec3& vel, Vec3& ang, RefBody& r1) {
+// humanoid_phc.py:665-676).  Called by EVERY thread of a block that has a flagged env, after phase 1 (the frame
+// buffer is dead, the stage may be written): a thread of a flagged env re-poses its body from the motion library
+// (reset_scatter_thread, the arithmetic of phc_reset_envs), body 0 publishes the new root position and heading, and
+// after the block barrier the thread writes its columns of the env's observation row — computed from the new state
+// and the reference body at the new t + dt — into the stage; the caller skips its own phase 2 for these threads.
+// Kept out of line and self-contained (everything it needs travels by value or through shared memory): the common
+// path, a block without a flagged env, pays the test and nothing else, the caller's per-body state stays in
+// registers and its kernel parameters stay constant-bank operands (a first version took `p` by reference: every
+// p.x of the kernel became a load, 7.8 -> 19.3 us per 4096-env step).
+struct ResetInStep {  // what the out-of-line reset needs, by value
+  LibDev L;
+  ResetTargets rw;
+  ObsFlags of;
+  float dt;
+  int selfw;
+  float* ref_dof_pos;
+  int64_t ref_dof_pos_stride;
+  int16_t* progress_mirror;
+};
+
+template <int EPB, bool DEF>
+__device__ __noinline__ void reset_in_step(const ResetInStep a, FastSmem<EPB>* Sp, bool mine, int e, int b, int64_t env) {
+  FastSmem<EPB>& S = *Sp;
   ResetEnvOut o;
   if (mine) {
     const float len = S.meta_len[e];
-    const float t = reset_start_time(p.rw, env, len);
-    reset_scatter_thread(p.L, p.rw, env, b, t, len, (int64_t)S.meta_nf[e], S.meta_mdt[e], S.meta_st[e], S.goff[e][0],
+    const float t = reset_start_time(a.rw, env, len);
+    reset_scatter_thread(a.L, a.rw, env, b, t, len, (int64_t)S.meta_nf[e], S.meta_mdt[e], S.meta_st[e], S.goff[e][0],
                          S.goff[e][1], S.goff[e][2], false, o);
     if (b == 0) {
-      if (p.progress_mirror) p.progress_mirror[env] = 0;
-      const Heading h0 = heading_quat_inv(heading_source(o.rot, p.of.upright));
+      if (a.progress_mirror) a.progress_mirror[env] = 0;
+      const Heading h0 = heading_quat_inv(heading_source(o.rot, a.of.upright));
       S.nroot[e][0] = o.pos.x, S.nroot[e][1] = o.pos.y, S.nroot[e][2] = o.pos.z;
       S.nroot[e][3] = h0.z, S.nroot[e][4] = h0.w;
     }
   }
   __syncthreads();
-  if (mine) {
-    pos = o.pos, rot = o.rot, vel = o.vel, ang = o.ang;
-    r1 = reset_ref_body(p.L, 1, p.dt, o.t, o.len, o.nf, o.mdt, o.st, b);
-    if (p.ref_dof_pos && b >= 1) {  // humanoid_phc.py:1115-1120 on the reset's _compute_task_obs(env_ids)
-      int64_t f0, f1;
-      float bl;
-      reset_query_frames(1, p.dt, o.t, o.len, o.nf, o.mdt, o.st, f0, f1, bl);
-      const Quat lr = quat_slerp(ld4v(p.L.lrs + (f0 * J24 + b) * 4), ld4v(p.L.lrs + (f1 * J24 + b) * 4), bl);
-      st3(p.ref_dof_pos + env * p.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
-    }
+  if (!mine) return;
+  const int SW = DEF ? SELF_DIM : a.selfw;
+  const Vec3 root_pos = {S.nroot[e][0], S.nroot[e][1], S.nroot[e][2]};
+  const Heading hi = {S.nroot[e][3], S.nroot[e][4]};
+  const HeadingRot hr = heading_rot(hi);
+  float* row = S.frames + e * (SW + TASK_DIM);
+  emit_self_obs<DEF>(row, a.of, b, root_pos, hi, hr, o.pos, o.rot, o.vel, o.ang);
+  const RefBody r1 = reset_ref_body(a.L, 1, a.dt, o.t, o.len, o.nf, o.mdt, o.st, b);
+  emit_task_obs<DEF>(row + SW, b, hi, hr, root_pos, o.pos, o.rot, o.vel, o.ang, r1);
+  if (a.ref_dof_pos && b >= 1) {  // humanoid_phc.py:1115-1120 on the reset's _compute_task_obs(env_ids)
+    int64_t f0, f1;
+    float bl;
+    reset_query_frames(1, a.dt, o.t, o.len, o.nf, o.mdt, o.st, f0, f1, bl);
+    const Quat lr = quat_slerp(ld4v(a.L.lrs + (f0 * J24 + b) * 4), ld4v(a.L.lrs + (f1 * J24 + b) * 4), bl);
+    st3(a.ref_dof_pos + env * a.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
   }
 }
 
@@ -1534,7 +1565,7 @@ __device__ __noinline__ void reset_in_step(const StepParams& p, FastSmem<EPB>& S
 // RESET: compiled with the in-step reset of the flagged envs (used when reset_on is set)
 // DEF: the env's default self-obs flags (height column, local root, upright): constant columns, 934-float rows
 template <int EPB, int MINB, bool NORM = false, bool EP = false, bool RESET = false, bool DEF = true>
-__global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepParams p) {
+__global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastSmem<EPB>& S = *reinterpret_cast<FastSmem<EPB>*>(smem_raw);
   constexpr int NT = EPB * J24;
@@ -1542,7 +1573,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   static_assert(!NORM || DEF, "the normaliser epilogue is laid out for the default 934-float rows");
   const int tid = threadIdx.x;
   const int64_t env0 = (int64_t)blockIdx.x * EPB;
-  const int nvalid = (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
+  const int nvalid = p.n <= env0 ? 0 : (int)((p.n - env0) < EPB ? (p.n - env0) : EPB);
   PHC_STAMP(0);
 
   // ---- phase 0: clock, frame-blend, TMA loads ---------------------------------------------------
@@ -1810,20 +1841,19 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
         any |= r;
         if (i == e) my_rst = valid && r;
       }
-      if (any) reset_in_step<EPB>(p, S, my_rst, e, b, env0 + e, pos, rot, vel, ang, r1);
+      if (any)  // writes the stage rows of the flagged envs; the arguments travel by value: taking the address of the
+                // kernel parameters would turn every p.x of this kernel from a constant-bank operand into a load
+        reset_in_step<EPB, DEF>(ResetInStep{p.L, p.rw, p.of, p.dt, p.selfw, p.ref_dof_pos, p.ref_dof_pos_stride,
+                                            p.progress_mirror}, &S, my_rst, e, b, env0 + e);
     }
   }
 
   // ---- phase 2: observations into the stage ---------------------------------------------------
   const int SW = DEF ? SELF_DIM : p.selfw;  // 358 with the root height column, 357 without
   const int RW = SW + TASK_DIM;             // floats of a staged row
-  if (valid) {
-    Vec3 root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
-    Heading hi = {S.hz[e], S.hw[e]};
-    if (RESET && my_rst) {
-      root_pos = {S.nroot[e][0], S.nroot[e][1], S.nroot[e][2]};
-      hi = {S.nroot[e][3], S.nroot[e][4]};
-    }
+  if (valid && !(RESET && my_rst)) {
+    const Vec3 root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
+    const Heading hi = {S.hz[e], S.hw[e]};
     const HeadingRot hr = heading_rot(hi);
     float* row = S.frames + e * RW;
     emit_self_obs<DEF>(row, p.of, b, root_pos, hi, hr, pos, rot, vel, ang);           // common.py:23-103
@@ -1837,7 +1867,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   const uint32_t out_bytes = (uint32_t)nvalid * (uint32_t)(RW * 4);
   const bool bulk_ok = (out_bytes & 15u) == 0;
   if (bulk_ok) {
-    if (tid == NT - 1) bulk_s2g(p.obs + env0 * RW, S.frames, out_bytes);
+    if (tid == NT - 1 && out_bytes) bulk_s2g(p.obs + env0 * RW, S.frames, out_bytes);
   } else if (DEF || ((nvalid * RW) & 1) == 0) {  // odd tail block: 8-byte stores
     float2* dst = reinterpret_cast<float2*>(p.obs + env0 * RW);
     const float2* src = reinterpret_cast<const float2*>(S.frames);
@@ -1845,17 +1875,57 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
   } else {
     for (int i = tid; i < nvalid * RW; i += NT) p.obs[env0 * RW + i] = S.frames[i];
   }
-  if (p.moments) {  // RunningNorm partials: per-column fp64 sum / sum of squares over the block's envs
-    for (int c = tid; c < RW; c += NT) {
-      double s1 = 0.0, s2 = 0.0;
-      for (int ee = 0; ee < nvalid; ++ee) {
-        const double x = (double)S.frames[ee * RW + c];
-        s1 += x;
-        s2 += x * x;
+  if (p.moments) {
+    // RunningNorm partials: per-column fp64 sum / sum of squares of the block's staged rows, added to one of the
+    // accumulator buckets.  As 1868 atomic instructions per block this saturates the L2 atomic units (1.9 M fp64 atomics
+    // per 4096-env step: +3.9 us on a 7 us step).  Instead the block writes its 1868 partial sums into shared memory
+    // that is dead by now — the sim tile and the tail of the frame buffer behind the stage, 624 doubles each — and
+    // hands them to the TMA engine as THREE bulk reductions (cp.reduce.async.bulk .add.f64): no atomic instruction
+    // is issued by an SM, the adds happen in L2 a 16-byte chunk at a time.
+    double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * RW;
+    if (p.moments_bulk) {
+      constexpr int CH = 624;  // doubles per region: min(sizeof sim, sizeof frames - stage) / 8, even
+      static_assert(CH * 8 <= (int)sizeof(S.sim) && CH * 8 <= (int)sizeof(S.frames) - EPB * STAGE_FLOATS * 4, "regions");
+      double* regA = reinterpret_cast<double*>(S.sim);
+      double* regB = reinterpret_cast<double*>(S.frames + EPB * RW);
+      const int total = 2 * RW;
+      for (int c0 = 0, r = 0; c0 < total; c0 += CH, ++r) {
+        double* reg = (r & 1) ? regB : regA;
+        const int cnt = total - c0 < CH ? total - c0 : CH;
+        if (r >= 2) {  // the region is being read by the reduction issued two rounds ago
+          if (tid == 0) bulk_wait_read_all_but_one();
+          __syncthreads();
+        }
+        for (int i = tid; i < cnt; i += NT) {
+          const int g = c0 + i;
+          const bool sq = g >= RW;
+          const int col = sq ? g - RW : g;
+          double acc = 0.0;
+          for (int ee = 0; ee < nvalid; ++ee) {
+            const double x = (double)S.frames[ee * RW + col];
+            acc += sq ? x * x : x;
+          }
+          reg[i] = acc;
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) bulk_reduce_add_f64(mom + c0, reg, (uint32_t)cnt * 8u);
       }
-      double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * RW;
-      atomicAdd(mom + c, s1);
-      atomicAdd(mom + RW + c, s2);
+      if (NORM && p.obs_norm) {  // the bf16 staging below reuses both regions
+        if (tid == 0) bulk_wait_read();
+        __syncthreads();
+      }
+    } else {
+      for (int c = tid; c < RW; c += NT) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int ee = 0; ee < nvalid; ++ee) {
+          const double x = (double)S.frames[ee * RW + c];
+          s1 += x;
+          s2 += x * x;
+        }
+        atomicAdd(mom + c, s1);
+        atomicAdd(mom + RW + c, s2);
+      }
     }
   }
   // res_action: dof_pos of the query at t + dt (humanoid_phc.py:1115-1120), off the critical path; a just-reset env
@@ -2046,7 +2116,310 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const StepPar
     }
   }
   if (bulk_ok && tid == NT - 1) bulk_wait_read();  // shared memory must outlive the store's reads
+  if (p.moments && p.moments_bulk && tid == 0) bulk_wait_read();  // ... and the reductions'
   PHC_STAMP(7);
+}
+
+// ---------------------------------------------------------------------------------------
+// K6-persist: the T = 1 fused step for grids of more than one wave (BASELINE config 3: 8192 .. 65536 envs per GPU).
+//
+// K6-fast runs one block per four envs: load -> compute -> store, serially, behind three block barriers, and relies
+// on eight co-resident blocks per SM to overlap one block's loads with another's math.  With several waves of blocks
+// that leaves the SM's issue slots idle 55-70 % of the time (ncu, round 1): every block spends about half of its life
+// in the chain clock -> clip metadata -> frame copy, and the tail of each wave runs under-occupied.  Here a block is
+// PERSISTENT and WARP-SPECIALISED:
+//
+//   * grid = 4 blocks per SM, each 3 consumer warps (4 envs x 24 bodies) + 1 producer warp, looping over env tiles it
+//     draws from a device-side counter (the first tile is blockIdx.x), so the SMs finish together whatever the tile
+//     count;
+//   * the producer warp runs the whole dependent chain of tile k+1 — clock loads, clip metadata gathers, the frame
+//     blend in the reference's fp32 order, the TMA copies of the sim rows and the frame span, the heading
+//     quaternions — into the second shared-memory stage while the consumers compute tile k; stages are handed over
+//     with mbarrier full / empty pairs (the full barrier counts the TMA bytes and the producer's arrival, the empty
+//     one is released when the tile's bulk store has read the stage and its reductions are done);
+//   * the consumers never touch global memory for input and never wait for a block barrier: two named barriers over
+//     the 96 consumer threads per tile (frame buffer -> obs stage hand-over, stage complete), the obs rows leave with
+//     one bulk store per tile, reductions and scalar outputs run on consumer warp 0 while warps 1-2 start the next
+//     tile.
+// Same per-body arithmetic as K6-fast, operand for operand: results are bit-identical (tested against the generic kernel).
+// ---------------------------------------------------------------------------------------
+constexpr int PS_STAGES = 2;
+constexpr int PS_EPB = 4;
+constexpr int PS_CONSUMERS = PS_EPB * J24;  // 96
+constexpr int PS_THREADS = PS_CONSUMERS + 32;
+constexpr int PS_BLOCKS_PER_SM = 4;
+
+struct PersistStage {
+  float sim[PS_EPB * ROW13];
+  float frames[PS_EPB * 4 * FRAME_FLOATS];  // [env][slot 0..3][312]; later the obs stage [env][934]
+  float part[6][PS_EPB][J24];
+  float bl[2][PS_EPB];
+  int slot[2][2][PS_EPB];
+  float goff[PS_EPB][4];
+  float hz[PS_EPB], hw[PS_EPB];
+  int prog[PS_EPB], pass[PS_EPB], fallen[PS_EPB];
+  int tile;  // env tile held by the stage, -1: no more tiles
+  int pad_[3];
+};
+static_assert(sizeof(PersistStage) % 16 == 0, "stages keep the 16-byte alignment of the TMA destinations");
+struct PersistSmem {
+  PersistStage st[PS_STAGES];
+  unsigned long long full[PS_STAGES], empty[PS_STAGES];
+};
+
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"r"(PS_CONSUMERS) : "memory"); }
+
+__global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PersistSmem& M = *reinterpret_cast<PersistSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int num_tiles = (int)((p.n + PS_EPB - 1) / PS_EPB);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < PS_STAGES; ++s) {
+      mbar_init(&M.full[s], 1);
+      mbar_init(&M.empty[s], 1);
+    }
+  }
+  __syncthreads();
+
+  if (tid >= PS_CONSUMERS) {
+    // =========================== producer warp ===========================
+    const int lane = tid - PS_CONSUMERS;
+    const int le = lane >> 3, j = lane & 7;  // 8 lanes per env of the tile: lane 0 leads, lane 1 does the heading
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    const bool block_sim = p.body.pos.stride_env == ROW13;  // a tile's sim rows are one span
+    int tile = (int)blockIdx.x;
+    for (int it = 0;; ++it) {
+      const int s = it % PS_STAGES;
+      PersistStage& S = M.st[s];
+      if (it >= PS_STAGES) mbar_wait(&M.empty[s], (uint32_t)(((it / PS_STAGES) - 1) & 1));
+      if (tile >= num_tiles) {  // tell the consumers and leave
+        if (lane == 0) {
+          S.tile = -1;
+          mbar_arrive(&M.full[s]);
+        }
+        break;
+      }
+      // the tile after this one: the atomic's round trip hides behind this tile's loads
+      int grab = 0;
+      if (lane == 0) grab = (int)gridDim.x + (int)atomicAdd(p.tile_counter, 1u);
+      const int64_t env0 = (int64_t)tile * PS_EPB;
+      const int nvalid = (int)((p.n - env0) < PS_EPB ? (p.n - env0) : PS_EPB);
+      const bool act = le < nvalid;
+      const int64_t env = env0 + (act ? le : 0);
+      float* fr = S.frames + le * (4 * FRAME_FLOATS);
+      if (act && j == 0) {
+        // clock: one round of loads (.cg: the previous step's kernel wrote some of these)
+        const int prog_in = (int)__ldcg(p.progress + env);
+        const int64_t id = __ldcg(p.ids + env);
+        const float start = __ldcg(p.start + env), soff = __ldcg(p.start_off + env);
+        float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+        if (p.goff) {
+          g0 = __ldcg(p.goff + env * 3 + 0);
+          g1 = __ldcg(p.goff + env * 3 + 1);
+          g2 = __ldcg(p.goff + env * 3 + 2);
+        }
+        if (block_sim ? le == 0 : true) {  // sim rows: issued while the clock loads are in flight
+          const uint32_t bytes = (block_sim ? (uint32_t)nvalid : 1u) * (uint32_t)(ROW13 * 4);
+          mbar_expect_tx(&M.full[s], bytes);
+          bulk_g2s(S.sim + le * ROW13, p.body.pos.ptr + env * p.body.pos.stride_env, bytes, &M.full[s]);
+        }
+        const float len = p.L.len[id];
+        const int nf = (int)p.L.nf[id];
+        const float mdt = p.L.mdt[id];
+        const int64_t st = p.L.starts[id];
+        int prog = prog_in;
+        if (p.advance) prog = (int)(int16_t)(prog + 1);
+        // q = 0: t = progress*dt + start + offset (humanoid_phc.py:1236); q = 1: (progress+1)*dt + ..
+        // (humanoid_phc.py:1063-1067), progress already advanced (humanoid_phc.py:138)
+        int a_f0, a_f1, b_f0, b_f1;
+        float a_bl, b_bl;
+        const float a_t = (float)(int16_t)prog * p.dt + start + soff;
+        calc_frame_blend32(a_t, len, nf, mdt, a_f0, a_f1, a_bl);
+        const float t1 = (float)(int16_t)(prog + 1) * p.dt + start + soff;
+        calc_frame_blend32(t1, len, nf, mdt, b_f0, b_f1, b_bl);
+        S.bl[0][le] = a_bl;
+        S.bl[1][le] = b_bl;
+        S.prog[le] = prog;
+        S.pass[le] = a_t >= len;  // _compute_reset, humanoid_phc.py:1317
+        S.fallen[le] = 0;
+        if (p.advance) {
+          p.progress[env] = (int16_t)prog;
+          if (p.progress_mirror) p.progress_mirror[env] = (int16_t)prog;
+        }
+        S.goff[le][0] = g0;
+        S.goff[le][1] = g1;
+        S.goff[le][2] = g2;
+        // frames of one clip are consecutive rows of the packed table: when the (up to four) frames span <= 4 rows
+        // they arrive with ONE copy and slot = frame - first
+        const float* tab = p.L.packed + st * FRAME_FLOATS;
+        const int lo = a_f0 < b_f0 ? a_f0 : b_f0;
+        int hi = a_f1 > b_f1 ? a_f1 : b_f1;
+        hi = hi > a_f0 ? hi : a_f0;
+        hi = hi > b_f0 ? hi : b_f0;
+        if (hi - lo <= 3) {
+          S.slot[0][0][le] = a_f0 - lo;
+          S.slot[0][1][le] = a_f1 - lo;
+          S.slot[1][0][le] = b_f0 - lo;
+          S.slot[1][1][le] = b_f1 - lo;
+          const uint32_t bytes = (uint32_t)(hi - lo + 1) * (uint32_t)(FRAME_FLOATS * 4);
+          mbar_expect_tx(&M.full[s], bytes);
+          bulk_g2s(fr, tab + (int64_t)lo * FRAME_FLOATS, bytes, &M.full[s]);
+        } else {  // two spans of one or two rows each (idx1 is idx0 or idx0 + 1)
+          S.slot[0][0][le] = 0;
+          S.slot[0][1][le] = a_f1 - a_f0;
+          S.slot[1][0][le] = 2;
+          S.slot[1][1][le] = 2 + (b_f1 - b_f0);
+          const uint32_t ba = (uint32_t)(a_f1 - a_f0 + 1) * (uint32_t)(FRAME_FLOATS * 4);
+          const uint32_t bb = (uint32_t)(b_f1 - b_f0 + 1) * (uint32_t)(FRAME_FLOATS * 4);
+          mbar_expect_tx(&M.full[s], ba + bb);
+          bulk_g2s(fr, tab + (int64_t)a_f0 * FRAME_FLOATS, ba, &M.full[s]);
+          bulk_g2s(fr + 2 * FRAME_FLOATS, tab + (int64_t)b_f0 * FRAME_FLOATS, bb, &M.full[s]);
+        }
+      } else if (act && j == 1) {
+        // the heading quaternion straight from the root rotation in global memory (floats 3..6 of the env's sim row)
+        const float* rq = p.body.pos.ptr + env * p.body.pos.stride_env + 3;
+        const Heading h0 = heading_quat_inv(Quat{__ldcg(rq), __ldcg(rq + 1), __ldcg(rq + 2), __ldcg(rq + 3)});
+        S.hz[le] = h0.z;  // upright: root_rot used as is (common.py:42-44)
+        S.hw[le] = h0.w;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        S.tile = tile;
+        mbar_arrive(&M.full[s]);  // release: the stage's scalars are visible to whoever sees the phase complete
+      }
+      tile = __shfl_sync(0xffffffffu, grab, 0);
+    }
+    // the last block out rewinds the tile counter for the next launch that draws this slot
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(p.tile_counter + 1, 1u) == gridDim.x - 1) {
+        p.tile_counter[0] = 0;
+        p.tile_counter[1] = 0;
+        __threadfence();
+      }
+    }
+    return;
+  }
+
+  // =========================== consumer warps ===========================
+  const int e = tid / J24, b = tid % J24;
+  for (int it = 0;; ++it) {
+    const int s = it % PS_STAGES;
+    PersistStage& S = M.st[s];
+    mbar_wait(&M.full[s], (uint32_t)((it / PS_STAGES) & 1));
+    const int tile = S.tile;
+    if (tile < 0) break;
+    const int64_t env0 = (int64_t)tile * PS_EPB;
+    const int nvalid = (int)((p.n - env0) < PS_EPB ? (p.n - env0) : PS_EPB);
+    const bool valid = e < nvalid;
+
+    // ---- phase 1: per-body reference states, reward partials, distance ------------------------
+    Vec3 pos, vel, ang, root_pos;
+    Quat rot;
+    RefBody r1;
+    if (valid) {
+      const float* d = S.sim + e * ROW13 + b * 13;
+      pos = {d[0], d[1], d[2]};
+      rot = {d[3], d[4], d[5], d[6]};
+      vel = {d[7], d[8], d[9]};
+      ang = {d[10], d[11], d[12]};
+      root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
+      const float* fr = S.frames + e * (4 * FRAME_FLOATS);
+      {
+        const RefBody r0 = blend_ref2(fr + S.slot[0][0][e] * FRAME_FLOATS, fr + S.slot[0][1][e] * FRAME_FLOATS,
+                                      S.bl[0][e], S.goff[e], b);
+        float sp, sr, sv, sa;
+        reward_partials(pos, rot, vel, ang, r0, sp, sr, sv, sa);
+        S.part[0][e][b] = sp;
+        S.part[1][e][b] = sr;
+        S.part[2][e][b] = sv;
+        S.part[3][e][b] = sa;
+        const float dist = norm3(pos - r0.pos);  // torch.norm(rigid_body_pos - ref_body_pos), common.py:343/348
+        S.part[4][e][b] = dist;
+        if (!p.use_mean && (p.reset_mask >> b & 1u) && dist > p.term_dist[b]) S.fallen[e] = 1;  // any(), benign race
+        if (p.dof_force) S.part[5][e][b] = power_partial(p, env0 + e, b);
+      }
+      r1 = blend_ref2(fr + S.slot[1][0][e] * FRAME_FLOATS, fr + S.slot[1][1][e] * FRAME_FLOATS, S.bl[1][e], S.goff[e], b);
+    }
+    consumer_sync();  // partials visible; frame buffer dead -> becomes the obs stage
+
+    // ---- phase 2: observations into the stage ---------------------------------------------------
+    if (valid) {
+      const Heading hi = {S.hz[e], S.hw[e]};
+      const HeadingRot hr = heading_rot(hi);
+      float* row = S.frames + e * STAGE_FLOATS;
+      emit_self_obs<true>(row, p.of, b, root_pos, hi, hr, pos, rot, vel, ang);       // common.py:23-103
+      emit_task_obs<true>(row + SELF_DIM, b, hi, hr, root_pos, pos, rot, vel, ang, r1);  // common.py:106-176
+    }
+    fence_proxy_async();  // stage writes -> visible to the bulk-store engine
+    consumer_sync();      // stage complete
+
+    const uint32_t out_bytes = (uint32_t)nvalid * (STAGE_FLOATS * 4);
+    const bool bulk_ok = (out_bytes & 15u) == 0;
+    if (bulk_ok) {
+      if (tid == 0) bulk_s2g(p.obs + env0 * STAGE_FLOATS, S.frames, out_bytes);
+    } else {  // odd tail tile: 8-byte stores by everyone, and everyone has to be done before the stage is released
+      float2* dst = reinterpret_cast<float2*>(p.obs + env0 * STAGE_FLOATS);
+      const float2* src = reinterpret_cast<const float2*>(S.frames);
+      for (int i = tid; i < nvalid * (STAGE_FLOATS / 2); i += PS_CONSUMERS) dst[i] = src[i];
+      consumer_sync();
+    }
+    // ---- reductions and scalar outputs (consumer warp 0) while warps 1-2 start the next tile ----------
+    if (tid < 32) {
+      const int le = tid >> 2, k = tid & 3;
+      const bool act = le < nvalid && tid < 4 * PS_EPB;
+      float term_k = 0.0f;
+      if (act) {
+        const float kk = k == 0 ? p.rwd.k_pos : k == 1 ? p.rwd.k_rot : k == 2 ? p.rwd.k_vel : p.rwd.k_ang_vel;
+        term_k = expf((-kk) * (row_sum24(&S.part[k][le][0]) / 24.0f));  // common.py:298-320
+        p.raw[(env0 + le) * p.raw_stride + k] = term_k;
+      }
+      const int base = tid & ~3;
+      const float t0 = __shfl_sync(0xffffffffu, term_k, base), t1 = __shfl_sync(0xffffffffu, term_k, base + 1);
+      const float t2 = __shfl_sync(0xffffffffu, term_k, base + 2), t3 = __shfl_sync(0xffffffffu, term_k, base + 3);
+      if (act && k == 0) {
+        float r = p.rwd.w_pos * t0 + p.rwd.w_rot * t1 + p.rwd.w_vel * t2 + p.rwd.w_ang_vel * t3;
+        if (p.dof_force) {
+          const float pr = power_reward(p, &S.part[5][le][0], S.prog[le]);
+          r += pr;  // rew_buf[:] += power_reward (humanoid_phc.py:1304)
+          p.raw[(env0 + le) * p.raw_stride + p.power_col] = pr;
+        }
+        p.rew[env0 + le] = r;
+        if (p.rew_out) p.rew_out[env0 + le] = r;
+      }
+      if (act && k == 1) {
+        bool fallen = false;
+        if (p.early) {
+          if (p.use_mean) {  // eval mode: mean distance of the selected bodies vs the first one's threshold
+            float sel[J24];
+            int m = 0;
+#pragma unroll
+            for (int jj = 0; jj < J24; ++jj)
+              if (p.reset_mask >> jj & 1u) sel[m++] = S.part[4][le][jj];
+            const int first = __ffs(p.reset_mask) - 1;
+            fallen = m > 0 && (aten_row_sum(sel, m) / (float)m) > p.term_dist[first < 0 ? 0 : first];
+          } else {
+            fallen = S.fallen[le] != 0;
+          }
+          fallen = fallen && (S.prog[le] > 1);  // common.py:353
+        }
+        const bool rs = S.pass[le] || fallen;  // common.py:362
+        p.term[env0 + le] = fallen ? 1 : 0;
+        p.reset[env0 + le] = rs ? 1 : 0;
+        if (p.term_out) p.term_out[env0 + le] = fallen ? 1 : 0;
+        if (p.reset_out) p.reset_out[env0 + le] = rs ? 1 : 0;
+      }
+      if (act && k == 2 && p.mpjpe) p.mpjpe[env0 + le] = row_sum24(&S.part[4][le][0]) / 24.0f;  // humanoid_phc.py:167
+      __syncwarp();
+      if (tid == 0) {  // the stage goes back to the producer once the store has read it and the partials are consumed
+        if (bulk_ok) bulk_wait_read();
+        mbar_arrive(&M.empty[s]);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2864,6 +3237,10 @@ __global__ void episode_fold_kernel(double* __restrict__ sums, int nb, int raw_c
 // =========================================================================================
 using namespace phc;
 
+static int g_moments_bulk = -1;  // PHC_OPT_MOMENTS_BULK / env PHC_MOMENTS_BULK=0|1 (default 1)
+static int g_persist = -1;       // PHC_OPT_STEP_PERSIST / env PHC_STEP_PERSIST: 0 never, 1 from g_persist_min envs on (default), 2 always
+static int64_t g_persist_min = 6144;
+
 template <typename Kern>
 static int launch_step(Kern kern, size_t smem, int epb, const StepParams& p, cudaStream_t stream, bool* attr_set,
                        bool pdl) {
@@ -2893,7 +3270,12 @@ struct PhcLib {
   // by phc_lib_pack, or the caller's own kernels before phc_lib_create — is only ordered before the step's
   // post-wait reads, so the first fused step after phc_lib_create / phc_lib_pack runs without the speculation.
   mutable int unspeculated_steps = 1;
+  // tile counters of the persistent step kernel: every launch draws the next of TILE_SLOTS slots (two words that the
+  // launch leaves zero), so launches that overlap on different streams do not share one
+  unsigned* tile_counters = nullptr;
+  mutable unsigned tile_seq = 0;
 };
+constexpr unsigned TILE_SLOTS = 256;
 
 extern "C" {
 
@@ -2944,6 +3326,16 @@ int phc_lib_pack(PhcLib* lib, phc_stream_t stream) {
       return PHC_ERR_ALLOC;
     }
   }
+  if (!lib->tile_counters) {
+    cudaError_t e = cudaMalloc((void**)&lib->tile_counters, TILE_SLOTS * 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemsetAsync(lib->tile_counters, 0, TILE_SLOTS * 2 * sizeof(unsigned), stream);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      g_last_cuda_error = (int)e;
+      lib->tile_counters = nullptr;
+      return PHC_ERR_ALLOC;
+    }
+  }
   const int64_t total4 = lib->d.F * 78;
   const unsigned grid = (unsigned)((total4 + 255) / 256 < 148 * 16 ? (total4 + 255) / 256 : 148 * 16);
   pack_frames_kernel<<<grid, 256, 0, stream>>>(lib->d, lib->packed_owned);
@@ -2957,6 +3349,7 @@ int phc_lib_pack(PhcLib* lib, phc_stream_t stream) {
 void phc_lib_destroy(PhcLib* lib) {
   if (!lib) return;
   if (lib->packed_owned) cudaFree(lib->packed_owned);
+  if (lib->tile_counters) cudaFree(lib->tile_counters);
   delete lib;
 }
 
@@ -3182,6 +3575,7 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   if (a->ref_dof_pos && (!lib->d.lrs || a->ref_dof_pos_stride < 69)) return lib->d.lrs ? PHC_ERR_SHAPE : PHC_ERR_NULL;
   p.reset_on = 0;
   p.rw = ResetTargets{};
+  p.tile_counter = nullptr;
   if (a->auto_reset) {
     // the reset rides on the step's own buffers: anything else would not be "the envs this step flags"
     const PhcResetArgs* r = a->auto_reset;
@@ -3227,6 +3621,7 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.term = a->terminate_buf;
   p.moments = a->obs_moments;
   p.moment_buckets = a->obs_moments_buckets > 1 ? a->obs_moments_buckets : 1;
+  p.moments_bulk = 0;
   p.ep_terminals = a->ep_terminals;
   p.ep_truncations = a->ep_truncations;
   p.ep_masks = a->ep_masks;
@@ -3307,6 +3702,16 @@ static void init_options() {
     const char* w = getenv("PHC_STEP_PDL");
     g_pdl = (w && w[0] == '0') ? 0 : 1;
   }
+  if (g_moments_bulk < 0) {
+    const char* w = getenv("PHC_MOMENTS_BULK");
+    g_moments_bulk = (w && w[0] == '0') ? 0 : 1;
+  }
+  if (g_persist < 0) {
+    const char* w = getenv("PHC_STEP_PERSIST");
+    g_persist = (w && w[0] >= '0' && w[0] <= '2') ? w[0] - '0' : 1;
+    const char* m = getenv("PHC_STEP_PERSIST_MIN");
+    if (m && atoll(m) > 0) g_persist_min = atoll(m);
+  }
 }
 
 int phc_action_to_pd_targets(const float* action, const float* pd_action_offset, const float* pd_action_scale,
@@ -3361,6 +3766,13 @@ int phc_set_option(int key, int value) {
       if (value < 0 || value > 2) return PHC_ERR_SHAPE;
       g_multi_groups = value;
       return PHC_OK;
+    case PHC_OPT_MOMENTS_BULK:
+      g_moments_bulk = value ? 1 : 0;
+      return PHC_OK;
+    case PHC_OPT_STEP_PERSIST:
+      if (value < 0 || value > 2) return PHC_ERR_SHAPE;
+      g_persist = value;
+      return PHC_OK;
     default:
       return PHC_ERR_UNSUPPORTED;
   }
@@ -3391,6 +3803,36 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
                                      ((uintptr_t)p.obs_norm & (p.norm_bf16 ? 3 : 15)) == 0));
   static bool attr_gen[64] = {};
   static int first_wave[64] = {};
+  // several waves of blocks (BASELINE config 3): the persistent warp-specialised kernel.  It carries the plain step
+  // (+ power reward, flag / reward copies); the optional epilogues stay with K6-fast.
+  static bool attr_persist[64] = {};
+  static int sm_count[64] = {};
+  const bool persist = fast && def && g_persist != 0 && (g_persist == 2 || p.n >= g_persist_min) && !p.obs_norm &&
+                       !p.ep_returns && !p.reset_on && !p.moments && !p.ref_dof_pos && !p.trace && lib->tile_counters &&
+                       !(args->flags & PHC_STEP_MAPPED_HOST_IO);
+  if (persist) {
+    if (!sm_count[dev]) PHC_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    if (!attr_persist[dev]) {
+      PHC_CUDA(cudaFuncSetAttribute(step_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
+      attr_persist[dev] = true;
+    }
+    if (lib->unspeculated_steps > 0) --lib->unspeculated_steps;  // nothing is read before the dependency wait here
+    p.tile_counter = lib->tile_counters + 2 * (lib->tile_seq++ % TILE_SLOTS);
+    const int64_t tiles = (p.n + PS_EPB - 1) / PS_EPB;
+    const int64_t resident = (int64_t)sm_count[dev] * PS_BLOCKS_PER_SM;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(tiles < resident ? tiles : resident));
+    cfg.blockDim = dim3(PS_THREADS);
+    cfg.dynamicSmemBytes = sizeof(PersistSmem);
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    PHC_CUDA(cudaLaunchKernelEx(&cfg, step_persist_kernel, p));
+    return launch_status();
+  }
   if (fast) {
     if (!first_wave[dev]) {
       int sms = 0, per_sm = 0;
@@ -3412,6 +3854,8 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
     static bool attr[7][64] = {};
     const bool pdl = g_pdl != 0;
     constexpr size_t SM = sizeof(FastSmem<4>);
+    // the moments epilogue leaves as TMA bulk reductions when the accumulators are 16-B aligned
+    p.moments_bulk = (p.moments && g_moments_bulk && ((uintptr_t)p.moments & 15) == 0) ? 1 : 0;
     if (!def) return launch_step(step_fast_kernel<4, 8, false, true, true, false>, SM, 4, p, stream, &attr[6][dev], pdl);
     if (p.reset_on) {
       if (p.obs_norm) return launch_step(step_fast_kernel<4, 8, true, true, true>, SM, 4, p, stream, &attr[5][dev], pdl);

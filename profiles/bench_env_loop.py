@@ -1,6 +1,8 @@
-"""Everything the env does around the physics step, through the shim's public API, in a CUDA graph:
-PHCPufferEnv.step = clamp actions -> HumanoidPHC.step (fused step + power reward [+ AMP buffers]) -> reward clone ->
-episode bookkeeping -> device-side reset of the flagged envs (sample start time, pose, clock, masked obs pass).
+"""Everything the env does around the physics step, through the shim's public API, in a CUDA graph.
+fused=False: PHCPufferEnv.step = clamp actions -> PD targets -> HumanoidPHC.step (fused step + power reward [+ AMP
+buffers]) -> reward clone -> episode bookkeeping -> device-side reset of the flagged envs (one launch each).
+fused=True (round 2): TWO launches — action clip + PD targets; fused step with power reward, bookkeeping, reward copy
+and the reset of the flagged envs inside it.
 
     python profiles/bench_env_loop.py [num_envs]
 """
@@ -25,8 +27,9 @@ print("| variant | us / step | env-steps/s |\n|---|---|---|")
 # the rate of the real task (episodes of up to 300 steps)
 for name, kw, fused, far in (("fused step only (HumanoidPHC.post_physics_step)", None, False, False),
                              ("PHCPufferEnv.step: power reward, episode bookkeeping, device-side resets", dict(use_power_reward=True), False, False),
-                             ("the same with the bookkeeping done by the step kernel (PHCPufferEnv(fused=True))", dict(use_power_reward=True), True, False),
+                             ("PHCPufferEnv(fused=True): two launches (clip + PD targets; step with bookkeeping, reward copy, reset inside)", dict(use_power_reward=True), True, False),
                              ("the same + AMP observation buffers (10-step history)", dict(use_power_reward=True, use_amp_obs=True), True, False),
+                             ("PHCPufferEnv(fused=False), resets at clip ends only", dict(use_power_reward=True), False, True),
                              ("PHCPufferEnv(fused=True), resets at clip ends only", dict(use_power_reward=True), True, True),
                              ("the same + AMP observation buffers", dict(use_power_reward=True, use_amp_obs=True), True, True)):
     env = HumanoidPHC(lib, N, device=dev, **(kw or {}))

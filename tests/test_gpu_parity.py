@@ -516,6 +516,85 @@ def test_fast_kernel_equals_generic_kernel_bitwise(N):
         torch.testing.assert_close(f.obs_moments, g.obs_moments, rtol=1e-12, atol=1e-9)
 
 
+@pytest.mark.parametrize("N,regime", [(8192, "aligned30"), (16387, "aligned30"), (6150, "mixed_fps_unaligned"), (7, "aligned30"),
+                                      (2401, "power")])  # fmt: skip
+def test_persistent_kernel_equals_generic_kernel_bitwise(N, regime):
+    """K6-persist (persistent blocks, producer warp + consumer warps, tiles drawn from a device counter) against the
+    generic kernel: every output bit for bit, three steps deep (the counter must rewind itself between launches),
+    ragged N, the two-span frame case of unaligned clips, and the power reward."""
+    from humanoid_b200 import HumanoidPHC, _cabi
+
+    kw = dict(max_progress=40)
+    if regime == "mixed_fps_unaligned":
+        kw.update(ids="random", aligned=False, fps_choices=(30, 60, 120), min_frames=60, max_frames=400)
+    lib_data, clock, state = _gpu_case(N, 300, 77, **kw)
+    lib = MotionLib(lib_data, device=DEV)
+    capi = _cabi.load()
+    outs = []
+    try:
+        for which in ("persist", "generic"):
+            capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 2 if which == "persist" else 0)
+            capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if which == "generic" else 0)
+            env = HumanoidPHC(lib, N, device=DEV, use_power_reward=regime == "power")
+            env.set_sim_state(state)
+            env.set_clock(clock)
+            if regime == "power":
+                env.dof_force_tensor.normal_(generator=torch.Generator(device=DEV).manual_seed(1))
+                env._dof_vel.copy_(torch.randn(N, 69, generator=torch.Generator(device=DEV).manual_seed(2), device=DEV))
+            snaps = []
+            for _ in range(3):
+                env.step()
+                snaps.append([getattr(env, k).clone() for k in ("obs_buf", "rew_buf", "reward_raw", "reset_buf",
+                                                                "_terminate_buf", "progress_buf", "_reset_out", "_terminate_out")])
+            torch.cuda.synchronize()
+            outs.append(snaps)
+    finally:
+        capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 1)
+        capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
+    for k, (a, b) in enumerate(zip(*outs)):
+        for x, y, nm in zip(a, b, ("obs", "rew", "reward_raw", "reset", "terminate", "progress", "reset_out", "terminate_out")):
+            assert torch.equal(x, y), f"step {k}: {nm}"
+
+
+def test_persistent_kernel_in_a_cuda_graph_with_many_launches():
+    """300 consecutive launches in one graph (more than the 256 tile-counter slots), replayed twice, against the
+    single-wave kernel: the counters rewind themselves and a slot that comes round again is clean."""
+    from humanoid_b200 import HumanoidPHC, _cabi
+
+    N = 6200
+    lib_data, clock, state = _gpu_case(N, 200, 78, max_progress=10, min_frames=400, max_frames=500)
+    lib = MotionLib(lib_data, device=DEV)
+    capi = _cabi.load()
+    res = []
+    try:
+        for mode in (2, 0):
+            capi.phc_set_option(_cabi.OPT_STEP_PERSIST, mode)
+            env = HumanoidPHC(lib, N, device=DEV)
+            env.set_sim_state(state)
+            env.set_clock(clock)
+            env.step()
+            env.set_clock(clock)
+            torch.cuda.synchronize()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(g, stream=s):
+                    for _ in range(300):
+                        env.post_physics_step(True)
+            for _ in range(2):
+                env.set_clock(clock)
+                torch.cuda.synchronize()
+                g.replay()
+            torch.cuda.synchronize()
+            res.append([env.obs_buf.clone(), env.rew_buf.clone(), env.progress_buf.clone(), env.reset_buf.clone()])
+    finally:
+        capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 1)
+    for x, y in zip(*res):
+        assert torch.equal(x, y)
+    assert int(res[0][2][0]) == int(clock.progress_buf[0]) + 300
+
+
 def test_fused_moments_epilogue_matches_column_moments():
     from humanoid_b200 import HumanoidPHC, RunningNorm
 
@@ -545,6 +624,46 @@ def test_fused_moments_epilogue_matches_column_moments():
     torch.testing.assert_close(s_big[:934], big.double().sum(0), rtol=1e-12, atol=1e-8)
     torch.testing.assert_close(s_big[934:], (big.double() ** 2).sum(0), rtol=1e-12, atol=1e-7)
     torch.testing.assert_close(sums[934:], (x * x).sum(0), rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("bulk", [1, 0], ids=["bulk_reduce", "atomics"])
+@pytest.mark.parametrize("N", [4096, 4099, 33, 5])
+def test_moments_epilogue_bulk_reductions_equal_column_moments(N, bulk):
+    """The T = 1 step's moments epilogue stages each block's 1868 fp64 partial sums in dead shared memory and hands
+    them to the TMA engine as three bulk reductions (cp.reduce.async.bulk .add.f64) instead of issuing 1868 atomics.
+    Both ways, ragged N included: partials equal phc_obs_moments to 1e-12 relative, every other output is untouched."""
+    from humanoid_b200 import HumanoidPHC, RunningNorm, _cabi
+
+    lib_data, clock, state = _gpu_case(N, 64, 41, max_progress=40)
+    lib = MotionLib(lib_data, device=DEV)
+    plain = HumanoidPHC(lib, N, device=DEV)
+    env = HumanoidPHC(lib, N, device=DEV, obs_moments=True)
+    for e in (plain, env):
+        e.set_sim_state(state)
+        e.set_clock(clock)
+    capi = _cabi.load()
+    assert capi.phc_set_option(_cabi.OPT_MOMENTS_BULK, bulk) == 0
+    try:
+        for _ in range(2):
+            plain.step()
+            env.step()
+        torch.cuda.synchronize()
+    finally:
+        capi.phc_set_option(_cabi.OPT_MOMENTS_BULK, 1)
+    for k in ("obs_buf", "rew_buf", "reward_raw", "reset_buf", "_terminate_buf", "progress_buf"):
+        assert torch.equal(getattr(env, k), getattr(plain, k)), k
+    rn = RunningNorm(934, device=DEV)
+    # two steps were accumulated; the second step's rows are in obs_buf, the first step's are recomputed
+    redo = HumanoidPHC(lib, N, device=DEV)
+    redo.set_sim_state(state)
+    redo.set_clock(clock)
+    redo.step()
+    want = rn.moments(redo.obs_buf)
+    rn.moments(env.obs_buf, want)
+    got, rows = env.take_obs_moments()
+    assert rows == 2 * N
+    scale = want.abs().clamp_min(1.0)
+    assert float(((got - want).abs() / scale).max()) < 1e-12
 
 
 def test_running_norm_vs_reference_fixture(golden):
@@ -1378,7 +1497,14 @@ def test_self_obs_flag_variants_on_the_fused_path(flags, kernel):
         st = env._rigid_body_state_reshaped.cpu()
         pos, rot, vel, ang = synth.body_views(st)
         want = O.self_obs_smpl_max(pos, rot, vel, ang, None, None, local, height, upright, False, False)
-        assert_close(env.obs_buf[:, : want.shape[1]], want, what="self obs vs oracle", **OBS_TOL)
+        # the heading is atan2(ry, rx) of the rotated x axis: where that axis is nearly vertical (rx^2 + ry^2 small, which
+        # remove_base_rot of a random root rotation produces) the reference's own heading is ill-conditioned and a 1-ulp
+        # difference in atan2f shows at 1e-4; those envs are compared against the per-function kernels only (above)
+        rr = rot[:, 0] if upright else O.remove_base_rot(rot[:, 0])
+        x_axis = O.rotate(rr, torch.tensor([1.0, 0.0, 0.0]).expand(N, 3))
+        ok = (x_axis[:, 0] ** 2 + x_axis[:, 1] ** 2) > 0.05
+        assert ok.float().mean() > 0.9
+        assert_close(env.obs_buf[:, : want.shape[1]].cpu()[ok], want[ok], what="self obs vs oracle", **OBS_TOL)
 
 
 def test_ref_dof_pos_of_the_fused_step_equals_the_motion_query():

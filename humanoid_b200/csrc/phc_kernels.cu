@@ -1510,53 +1510,44 @@ __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, 
 // (reset_scatter_thread, the arithmetic of phc_reset_envs), body 0 publishes the new root position and heading, and
 // after the block barrier the thread writes its columns of the env's observation row — computed from the new state
 // and the reference body at the new t + dt — into the stage; the caller skips its own phase 2 for these threads.
-// Kept out of line and self-contained (everything it needs travels by value or through shared memory): the common
-// path, a block without a flagged env, pays the test and nothing else, the caller's per-body state stays in
-// registers and its kernel parameters stay constant-bank operands (a first version took `p` by reference: every
-// p.x of the kernel became a load, 7.8 -> 19.3 us per 4096-env step).
-struct ResetInStep {  // what the out-of-line reset needs, by value
-  LibDev L;
-  ResetTargets rw;
-  ObsFlags of;
-  float dt;
-  int selfw;
-  float* ref_dof_pos;
-  int64_t ref_dof_pos_stride;
-  int16_t* progress_mirror;
-};
-
+// Self-contained and inlined: nothing of it is live outside the branch, so the common path (no env flagged) pays the
+// test only.  (Out of line it was a disaster twice over: with the caller's per-body state passed by reference that
+// state lived in local memory for the whole kernel, 7.8 -> 46 us per 4096-env step; with the kernel parameters
+// passed by reference, 19 us.)
 template <int EPB, bool DEF>
-__device__ __noinline__ void reset_in_step(const ResetInStep a, FastSmem<EPB>* Sp, bool mine, int e, int b, int64_t env) {
-  FastSmem<EPB>& S = *Sp;
+__device__ __forceinline__ void reset_in_step(const StepParams& p, FastSmem<EPB>& S, bool mine, int e, int b, int64_t env) {
   ResetEnvOut o;
+  RefBody r1;
   if (mine) {
     const float len = S.meta_len[e];
-    const float t = reset_start_time(a.rw, env, len);
-    reset_scatter_thread(a.L, a.rw, env, b, t, len, (int64_t)S.meta_nf[e], S.meta_mdt[e], S.meta_st[e], S.goff[e][0],
+    const float t = reset_start_time(p.rw, env, len);
+    // the reference body at the new t + dt depends on the new start time only: its gathers go out together with the
+    // scatter's (one round trip to the library instead of two on the slow path that decides a single-wave step)
+    r1 = reset_ref_body(p.L, 1, p.dt, t, len, (int64_t)S.meta_nf[e], S.meta_mdt[e], S.meta_st[e], b);
+    reset_scatter_thread(p.L, p.rw, env, b, t, len, (int64_t)S.meta_nf[e], S.meta_mdt[e], S.meta_st[e], S.goff[e][0],
                          S.goff[e][1], S.goff[e][2], false, o);
     if (b == 0) {
-      if (a.progress_mirror) a.progress_mirror[env] = 0;
-      const Heading h0 = heading_quat_inv(heading_source(o.rot, a.of.upright));
+      if (p.progress_mirror) p.progress_mirror[env] = 0;
+      const Heading h0 = heading_quat_inv(heading_source(o.rot, p.of.upright));
       S.nroot[e][0] = o.pos.x, S.nroot[e][1] = o.pos.y, S.nroot[e][2] = o.pos.z;
       S.nroot[e][3] = h0.z, S.nroot[e][4] = h0.w;
     }
   }
   __syncthreads();
   if (!mine) return;
-  const int SW = DEF ? SELF_DIM : a.selfw;
+  const int SW = DEF ? SELF_DIM : p.selfw;
   const Vec3 root_pos = {S.nroot[e][0], S.nroot[e][1], S.nroot[e][2]};
   const Heading hi = {S.nroot[e][3], S.nroot[e][4]};
   const HeadingRot hr = heading_rot(hi);
   float* row = S.frames + e * (SW + TASK_DIM);
-  emit_self_obs<DEF>(row, a.of, b, root_pos, hi, hr, o.pos, o.rot, o.vel, o.ang);
-  const RefBody r1 = reset_ref_body(a.L, 1, a.dt, o.t, o.len, o.nf, o.mdt, o.st, b);
+  emit_self_obs<DEF>(row, p.of, b, root_pos, hi, hr, o.pos, o.rot, o.vel, o.ang);
   emit_task_obs<DEF>(row + SW, b, hi, hr, root_pos, o.pos, o.rot, o.vel, o.ang, r1);
-  if (a.ref_dof_pos && b >= 1) {  // humanoid_phc.py:1115-1120 on the reset's _compute_task_obs(env_ids)
+  if (p.ref_dof_pos && b >= 1) {  // humanoid_phc.py:1115-1120 on the reset's _compute_task_obs(env_ids)
     int64_t f0, f1;
     float bl;
-    reset_query_frames(1, a.dt, o.t, o.len, o.nf, o.mdt, o.st, f0, f1, bl);
-    const Quat lr = quat_slerp(ld4v(a.L.lrs + (f0 * J24 + b) * 4), ld4v(a.L.lrs + (f1 * J24 + b) * 4), bl);
-    st3(a.ref_dof_pos + env * a.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
+    reset_query_frames(1, p.dt, o.t, o.len, o.nf, o.mdt, o.st, f0, f1, bl);
+    const Quat lr = quat_slerp(ld4v(p.L.lrs + (f0 * J24 + b) * 4), ld4v(p.L.lrs + (f1 * J24 + b) * 4), bl);
+    st3(p.ref_dof_pos + env * p.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
   }
 }
 
@@ -1841,10 +1832,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const __grid_
         any |= r;
         if (i == e) my_rst = valid && r;
       }
-      if (any)  // writes the stage rows of the flagged envs; the arguments travel by value: taking the address of the
-                // kernel parameters would turn every p.x of this kernel from a constant-bank operand into a load
-        reset_in_step<EPB, DEF>(ResetInStep{p.L, p.rw, p.of, p.dt, p.selfw, p.ref_dof_pos, p.ref_dof_pos_stride,
-                                            p.progress_mirror}, &S, my_rst, e, b, env0 + e);
+      if (any) reset_in_step<EPB, DEF>(p, S, my_rst, e, b, env0 + e);  // writes the stage rows of the flagged envs
     }
   }
 
@@ -1877,11 +1865,16 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const __grid_
   }
   if (p.moments) {
     // RunningNorm partials: per-column fp64 sum / sum of squares of the block's staged rows, added to one of the
-    // accumulator buckets.  As 1868 atomic instructions per block this saturates the L2 atomic units (1.9 M fp64 atomics
-    // per 4096-env step: +3.9 us on a 7 us step).  Instead the block writes its 1868 partial sums into shared memory
-    // that is dead by now — the sim tile and the tail of the frame buffer behind the stage, 624 doubles each — and
-    // hands them to the TMA engine as THREE bulk reductions (cp.reduce.async.bulk .add.f64): no atomic instruction
-    // is issued by an SM, the adds happen in L2 a 16-byte chunk at a time.
+    // accumulator buckets: 1868 fp64 adds in L2 per block of four envs (1.9 M per 4096-env step: +3.8 us on a 6.7 us
+    // step).  Two ways to cut that were built and measured in round 2 (profiles/r2_step_variants.md):
+    //   * p.moments_bulk (PHC_OPT_MOMENTS_BULK, kept as an option): the block writes its 1868 partial sums into shared
+    //     memory that is dead by now — the sim tile and the tail of the frame buffer behind the stage, 624 doubles
+    //     each — and hands them to the TMA engine as THREE bulk reductions (cp.reduce.async.bulk .add.f64), so no SM
+    //     issues an atomic.  10.95 us against 10.47 us for the atomics: the adds themselves, in L2, are the cost, not
+    //     their issue.
+    //   * a cluster of 8 CTAs pre-reducing over each other's staged rows through distributed shared memory (8x fewer
+    //     L2 adds): 16.8 us (cluster of 4: 14.0, of 2: 12.7) — a cluster launch gang-schedules its CTAs and two cluster
+    //     barriers sit at the tail of every block of a single-wave grid.  Removed.
     double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * RW;
     if (p.moments_bulk) {
       constexpr int CH = 624;  // doubles per region: min(sizeof sim, sizeof frames - stage) / 8, even
@@ -2185,76 +2178,114 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
 
   if (tid >= PS_CONSUMERS) {
     // =========================== producer warp ===========================
+    // A tile's inputs sit behind a chain of three dependent memory round trips: clock -> clip metadata -> frame rows.
+    // Run one tile at a time that chain is what a block waits for (measured: 4.5 us per tile under load, the whole
+    // kernel slower than K6-fast).  The producer is therefore a software pipeline over THREE tiles: in one iteration
+    // it issues the clock loads of tile i+2, the metadata gathers of tile i+1 (whose clock it loaded an iteration ago)
+    // and — from registers only — blends and copies tile i.  Every load has a whole iteration to land.
     const int lane = tid - PS_CONSUMERS;
     const int le = lane >> 3, j = lane & 7;  // 8 lanes per env of the tile: lane 0 leads, lane 1 does the heading
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     const bool block_sim = p.body.pos.stride_env == ROW13;  // a tile's sim rows are one span
-    int tile = (int)blockIdx.x;
+    struct Clock {
+      int prog_in;
+      int64_t id;
+      float start, soff, g0, g1, g2;
+    };
+    struct Meta {
+      float len, mdt;
+      int nf;
+      int64_t st;
+    };
+    const auto env_of = [&](int tile) { return (int64_t)tile * PS_EPB + le; };
+    const auto live = [&](int tile) { return tile < num_tiles && env_of(tile) < p.n; };
+    const auto load_clock = [&](int tile) {  // .cg: the previous step's kernel wrote some of these
+      Clock c{0, 0, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+      if (j == 0 && live(tile)) {
+        const int64_t env = env_of(tile);
+        c.prog_in = (int)__ldcg(p.progress + env);
+        c.id = __ldcg(p.ids + env);
+        c.start = __ldcg(p.start + env);
+        c.soff = __ldcg(p.start_off + env);
+        if (p.goff) {
+          c.g0 = __ldcg(p.goff + env * 3 + 0);
+          c.g1 = __ldcg(p.goff + env * 3 + 1);
+          c.g2 = __ldcg(p.goff + env * 3 + 2);
+        }
+      }
+      return c;
+    };
+    const auto load_rootq = [&](int tile) {  // floats 3..6 of the env's sim row: the root rotation
+      Quat q{0.0f, 0.0f, 0.0f, 1.0f};
+      if (j == 1 && live(tile)) {
+        const float* rq = p.body.pos.ptr + env_of(tile) * p.body.pos.stride_env + 3;
+        q = Quat{__ldcg(rq), __ldcg(rq + 1), __ldcg(rq + 2), __ldcg(rq + 3)};
+      }
+      return q;
+    };
+    const auto load_meta = [&](int tile, const Clock& c) {
+      Meta m{1.0f, 1.0f, 2, 0};
+      if (j == 0 && live(tile)) {
+        m.len = p.L.len[c.id];
+        m.nf = (int)p.L.nf[c.id];
+        m.mdt = p.L.mdt[c.id];
+        m.st = p.L.starts[c.id];
+      }
+      return m;
+    };
+    // a block's first three tiles are static (blockIdx.x, + grid, + 2 grid): nothing to wait for at the start; from the
+    // fourth on they are drawn from the counter, which evens out the tail
+    const int G = 3 * (int)gridDim.x;
+    int tA = (int)blockIdx.x, tB = tA + (int)gridDim.x, tC = tB + (int)gridDim.x;
+    Clock cA = load_clock(tA), cB = load_clock(tB);
+    Quat qA = load_rootq(tA), qB = load_rootq(tB);
+    Meta mA = load_meta(tA, cA);
     for (int it = 0;; ++it) {
       const int s = it % PS_STAGES;
       PersistStage& S = M.st[s];
-      if (it >= PS_STAGES) mbar_wait(&M.empty[s], (uint32_t)(((it / PS_STAGES) - 1) & 1));
-      if (tile >= num_tiles) {  // tell the consumers and leave
+      if (tA >= num_tiles) {  // tell the consumers and leave
+        if (it >= PS_STAGES) mbar_wait(&M.empty[s], (uint32_t)(((it / PS_STAGES) - 1) & 1));
         if (lane == 0) {
           S.tile = -1;
           mbar_arrive(&M.full[s]);
         }
         break;
       }
-      // the tile after this one: the atomic's round trip hides behind this tile's loads
+      // loads for the tiles behind this one, consumed an iteration from now
       int grab = 0;
-      if (lane == 0) grab = (int)gridDim.x + (int)atomicAdd(p.tile_counter, 1u);
-      const int64_t env0 = (int64_t)tile * PS_EPB;
+      if (lane == 0) grab = G + (int)atomicAdd(p.tile_counter, 1u);
+      const Clock cC = load_clock(tC);
+      const Quat qC = load_rootq(tC);
+      const Meta mB = load_meta(tB, cB);
+      // this tile: the stage has to be free
+      if (it >= PS_STAGES) mbar_wait(&M.empty[s], (uint32_t)(((it / PS_STAGES) - 1) & 1));
+      const int64_t env0 = (int64_t)tA * PS_EPB;
       const int nvalid = (int)((p.n - env0) < PS_EPB ? (p.n - env0) : PS_EPB);
       const bool act = le < nvalid;
       const int64_t env = env0 + (act ? le : 0);
       float* fr = S.frames + le * (4 * FRAME_FLOATS);
       if (act && j == 0) {
-        // clock: one round of loads (.cg: the previous step's kernel wrote some of these)
-        const int prog_in = (int)__ldcg(p.progress + env);
-        const int64_t id = __ldcg(p.ids + env);
-        const float start = __ldcg(p.start + env), soff = __ldcg(p.start_off + env);
-        float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
-        if (p.goff) {
-          g0 = __ldcg(p.goff + env * 3 + 0);
-          g1 = __ldcg(p.goff + env * 3 + 1);
-          g2 = __ldcg(p.goff + env * 3 + 2);
-        }
-        if (block_sim ? le == 0 : true) {  // sim rows: issued while the clock loads are in flight
+        if (block_sim ? le == 0 : true) {  // sim rows
           const uint32_t bytes = (block_sim ? (uint32_t)nvalid : 1u) * (uint32_t)(ROW13 * 4);
           mbar_expect_tx(&M.full[s], bytes);
           bulk_g2s(S.sim + le * ROW13, p.body.pos.ptr + env * p.body.pos.stride_env, bytes, &M.full[s]);
         }
-        const float len = p.L.len[id];
-        const int nf = (int)p.L.nf[id];
-        const float mdt = p.L.mdt[id];
-        const int64_t st = p.L.starts[id];
-        int prog = prog_in;
+        const float len = mA.len, mdt = mA.mdt;
+        const int nf = mA.nf;
+        int prog = cA.prog_in;
         if (p.advance) prog = (int)(int16_t)(prog + 1);
         // q = 0: t = progress*dt + start + offset (humanoid_phc.py:1236); q = 1: (progress+1)*dt + ..
         // (humanoid_phc.py:1063-1067), progress already advanced (humanoid_phc.py:138)
         int a_f0, a_f1, b_f0, b_f1;
         float a_bl, b_bl;
-        const float a_t = (float)(int16_t)prog * p.dt + start + soff;
+        const float a_t = (float)(int16_t)prog * p.dt + cA.start + cA.soff;
         calc_frame_blend32(a_t, len, nf, mdt, a_f0, a_f1, a_bl);
-        const float t1 = (float)(int16_t)(prog + 1) * p.dt + start + soff;
+        const float t1 = (float)(int16_t)(prog + 1) * p.dt + cA.start + cA.soff;
         calc_frame_blend32(t1, len, nf, mdt, b_f0, b_f1, b_bl);
-        S.bl[0][le] = a_bl;
-        S.bl[1][le] = b_bl;
-        S.prog[le] = prog;
-        S.pass[le] = a_t >= len;  // _compute_reset, humanoid_phc.py:1317
-        S.fallen[le] = 0;
-        if (p.advance) {
-          p.progress[env] = (int16_t)prog;
-          if (p.progress_mirror) p.progress_mirror[env] = (int16_t)prog;
-        }
-        S.goff[le][0] = g0;
-        S.goff[le][1] = g1;
-        S.goff[le][2] = g2;
         // frames of one clip are consecutive rows of the packed table: when the (up to four) frames span <= 4 rows
         // they arrive with ONE copy and slot = frame - first
-        const float* tab = p.L.packed + st * FRAME_FLOATS;
+        const float* tab = p.L.packed + mA.st * FRAME_FLOATS;
         const int lo = a_f0 < b_f0 ? a_f0 : b_f0;
         int hi = a_f1 > b_f1 ? a_f1 : b_f1;
         hi = hi > a_f0 ? hi : a_f0;
@@ -2278,19 +2309,30 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
           bulk_g2s(fr, tab + (int64_t)a_f0 * FRAME_FLOATS, ba, &M.full[s]);
           bulk_g2s(fr + 2 * FRAME_FLOATS, tab + (int64_t)b_f0 * FRAME_FLOATS, bb, &M.full[s]);
         }
+        S.bl[0][le] = a_bl;
+        S.bl[1][le] = b_bl;
+        S.prog[le] = prog;
+        S.pass[le] = a_t >= len;  // _compute_reset, humanoid_phc.py:1317
+        S.fallen[le] = 0;
+        if (p.advance) {
+          p.progress[env] = (int16_t)prog;
+          if (p.progress_mirror) p.progress_mirror[env] = (int16_t)prog;
+        }
+        S.goff[le][0] = cA.g0;
+        S.goff[le][1] = cA.g1;
+        S.goff[le][2] = cA.g2;
       } else if (act && j == 1) {
-        // the heading quaternion straight from the root rotation in global memory (floats 3..6 of the env's sim row)
-        const float* rq = p.body.pos.ptr + env * p.body.pos.stride_env + 3;
-        const Heading h0 = heading_quat_inv(Quat{__ldcg(rq), __ldcg(rq + 1), __ldcg(rq + 2), __ldcg(rq + 3)});
-        S.hz[le] = h0.z;  // upright: root_rot used as is (common.py:42-44)
+        const Heading h0 = heading_quat_inv(qA);  // upright: root_rot used as is (common.py:42-44)
+        S.hz[le] = h0.z;
         S.hw[le] = h0.w;
       }
       __syncwarp();
       if (lane == 0) {
-        S.tile = tile;
+        S.tile = tA;
         mbar_arrive(&M.full[s]);  // release: the stage's scalars are visible to whoever sees the phase complete
       }
-      tile = __shfl_sync(0xffffffffu, grab, 0);
+      tA = tB, tB = tC, tC = __shfl_sync(0xffffffffu, grab, 0);
+      cA = cB, cB = cC, mA = mB, qA = qB, qB = qC;
     }
     // the last block out rewinds the tile counter for the next launch that draws this slot
     if (lane == 0) {
@@ -3237,9 +3279,9 @@ __global__ void episode_fold_kernel(double* __restrict__ sums, int nb, int raw_c
 // =========================================================================================
 using namespace phc;
 
-static int g_moments_bulk = -1;  // PHC_OPT_MOMENTS_BULK / env PHC_MOMENTS_BULK=0|1 (default 1)
+static int g_moments_bulk = -1;  // PHC_OPT_MOMENTS_BULK / env PHC_MOMENTS_BULK=0|1 (default 0: measured no faster than the atomics)
 static int g_persist = -1;       // PHC_OPT_STEP_PERSIST / env PHC_STEP_PERSIST: 0 never, 1 from g_persist_min envs on (default), 2 always
-static int64_t g_persist_min = 6144;
+static int64_t g_persist_min = 16384;
 
 template <typename Kern>
 static int launch_step(Kern kern, size_t smem, int epb, const StepParams& p, cudaStream_t stream, bool* attr_set,
@@ -3704,7 +3746,7 @@ static void init_options() {
   }
   if (g_moments_bulk < 0) {
     const char* w = getenv("PHC_MOMENTS_BULK");
-    g_moments_bulk = (w && w[0] == '0') ? 0 : 1;
+    g_moments_bulk = (w && w[0] == '1') ? 1 : 0;
   }
   if (g_persist < 0) {
     const char* w = getenv("PHC_STEP_PERSIST");

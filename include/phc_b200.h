@@ -387,9 +387,9 @@ PHC_API int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* args, int64_t 
                                         validation / redo paths run; results must not change */
 #define PHC_OPT_MULTI_GROUPS 5        /* thread groups per block of the T > 1 kernel: 2 (default; also value 0): the queries of an
                                         env are worked on in pairs; 1: the single-group pipeline, kept as the cross-check */
-#define PHC_OPT_MOMENTS_BULK 6        /* 1 (default): the T = 1 kernel's moments epilogue (obs_moments) hands each block's 1868 partial sums
-                                        to the TMA engine as three bulk fp64 reductions; 0: one atomic instruction per sum (cross-check) */
-#define PHC_OPT_STEP_PERSIST 7        /* the persistent warp-specialised T = 1 kernel for multi-wave grids: 1 (default) from 6144 envs on
+#define PHC_OPT_MOMENTS_BULK 6        /* 1: the T = 1 kernel's moments epilogue (obs_moments) hands each block's 1868 partial sums to the TMA
+                                        engine as three bulk fp64 reductions; 0 (default, measured a little faster): one atomic per sum */
+#define PHC_OPT_STEP_PERSIST 7        /* the persistent warp-specialised T = 1 kernel for multi-wave grids: 1 (default) from 16384 envs on
                                         (env PHC_STEP_PERSIST_MIN), 0 never, 2 always (tests) */
 PHC_API int phc_set_option(int key, int value);
 /* Profiling aid: when a device buffer of capacity_warps x 8 uint64 is set, every warp of the

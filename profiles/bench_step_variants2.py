@@ -24,17 +24,17 @@ print(f"# step kernel variants at N = {N} (us per launch, {K}-launch CUDA graph,
 print("| variant | us |\n|---|---|")
 VARIANTS = [
     ("plain", {}),
-    ("+ moments, TMA bulk reductions (default)", dict(moments=1)),
-    ("+ moments, one atomic per sum (round 1)", dict(moments=2)),
+    ("+ moments, one atomic per sum (default)", dict(moments=2)),
+    ("+ moments, TMA bulk reductions (PHC_OPT_MOMENTS_BULK)", dict(moments=1)),
     ("+ normaliser fp32", dict(norm=torch.float32)),
     ("+ normaliser bf16", dict(norm=torch.bfloat16)),
     ("+ episode bookkeeping", dict(ep=True)),
     ("+ bookkeeping + reset in the step (synthetic state: ~25 % flagged per step)", dict(ep=True, reset=True)),
     ("+ bookkeeping + reset in the step, termination out of reach (clip ends only)", dict(ep=True, reset=True, far=True)),
-    ("+ bookkeeping + reset + moments + normaliser bf16 (everything)", dict(ep=True, reset=True, far=True, moments=1, norm=torch.bfloat16)),
+    ("+ bookkeeping + reset + moments + normaliser bf16 (everything)", dict(ep=True, reset=True, far=True, moments=2, norm=torch.bfloat16)),
 ]
 for name, v in VARIANTS:
-    capi.phc_set_option(_cabi.OPT_MOMENTS_BULK, 0 if v.get("moments") == 2 else 1)
+    capi.phc_set_option(_cabi.OPT_MOMENTS_BULK, 1 if v.get("moments") == 1 else 0)
     envs, states = [], []
     first = None
     for r in range(R):
@@ -99,4 +99,4 @@ for name, v in VARIANTS:
     print(f"| {name}{extra} | {best:.2f} |", flush=True)
     del envs, g
     torch.cuda.empty_cache()
-capi.phc_set_option(_cabi.OPT_MOMENTS_BULK, 1)
+capi.phc_set_option(_cabi.OPT_MOMENTS_BULK, 0)

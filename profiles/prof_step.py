@@ -30,7 +30,7 @@ else:
     lib_data = synth.make_motion_lib(N, 60, 300, (30,), seed=1234, device=dev)
 lib = MotionLib(lib_data, device=dev)
 clock = synth.make_clock(lib_data, N, seed=1235, max_progress=30)
-R = 17
+R = max(4, -(-320 * (1 << 20) // (N * (312 + 358 + 576 * T) * 4)))  # ring of buffer sets larger than the 126 MB L2
 envs = []
 for r in range(R):
     if C4:

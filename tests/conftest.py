@@ -64,8 +64,59 @@ def golden():
 STEP_CASES = ["step_aligned", "step_random", "step_T10", "step_eval_reset", "step_no_early_term"]
 
 
-def assert_close(actual, expected, rtol=1e-5, atol=1e-6, what=""):
-    """|a-e| <= atol + rtol*|e| elementwise, with a readable report of the worst entry."""
+def _obs_groups(width):
+    """(offset, vectors, floats per vector) of every column group of an obs row [self obs | T x v6 block]
+    (SURVEY Appendix B); None if `width` is not an obs row."""
+    for h in (1, 0):
+        rest = width - (357 + h)
+        if rest >= 0 and rest % 576 == 0:
+            g = [(0, 1, 1)] if h else []
+            g += [(h, 23, 3), (h + 69, 24, 6), (h + 213, 24, 3), (h + 285, 24, 3)]
+            for t in range(rest // 576):
+                o = 357 + h + 576 * t
+                g += [(o, 24, 3), (o + 72, 24, 6), (o + 216, 24, 3), (o + 288, 24, 3), (o + 360, 24, 3), (o + 432, 24, 6)]
+            return g
+    if width % 576 == 0:  # v6 blocks only (compute_imitation_observations_v6's own output)
+        g = []
+        for o in range(0, width, 576):
+            g += [(o, 24, 3), (o + 72, 24, 6), (o + 216, 24, 3), (o + 288, 24, 3), (o + 360, 24, 3), (o + 432, 24, 6)]
+        return g
+    if width % 216 == 0:  # v7 column subset [d_pos | d_vel | l_pos] per step
+        return [(o, 72, 3) for o in range(0, width, 216)]
+    if width in (357, 358):  # self obs only
+        h = width - 357
+        return ([(0, 1, 1)] if h else []) + [(h, 23, 3), (h + 69, 24, 6), (h + 213, 24, 3), (h + 285, 24, 3)]
+    return None
+
+
+def natural_scale(e: torch.Tensor) -> torch.Tensor:
+    """Per element, the magnitude an error is to be judged against: the norm of the vector the element is a
+    component of — a body's position / velocity 3-vector, a quaternion, a tangent-normal 6-vector, a joint's exp-map
+    3-vector — instead of the element itself.  A rotation by a heading that is off by one ulp of atan2f moves every
+    component by ~1e-7 |v|, whatever the component's own size; |v| is the scale such an error is relative to."""
+    sc = e.abs().clone()
+    if e.dim() >= 3 and e.shape[-1] in (3, 4):  # [.., J, 3|4]
+        return e.norm(dim=-1, keepdim=True).expand_as(e).clone()
+    if e.dim() == 2:
+        groups = _obs_groups(e.shape[1])
+        if groups is None and e.shape[1] in (69, 72):  # dof_pos / dof_vel / motion_aa: 3 per joint
+            groups = [(0, e.shape[1] // 3, 3)]
+        if groups is None and e.shape[1] % 196 == 0:  # AMP rows (humanoid_phc.py:469-478): [h | root rot 6 | root vel 3 |
+            groups = []                               # root ang vel 3 | 19 x dof obs 6 | 19 x dof vel 3 | 4 x key pos 3] per step
+            for o in range(0, e.shape[1], 196):
+                groups += [(o, 1, 1), (o + 1, 1, 6), (o + 7, 2, 3), (o + 13, 19, 6), (o + 127, 19, 3), (o + 184, 4, 3)]
+        if groups is not None:
+            for off, n, k in groups:
+                v = e[:, off : off + n * k].reshape(e.shape[0], n, k)
+                sc[:, off : off + n * k] = v.norm(dim=-1, keepdim=True).expand_as(v).reshape(e.shape[0], n * k)
+    return sc
+
+
+def assert_close(actual, expected, rtol=1e-5, atol=1e-6, what="", scale=None, small_angle=None):
+    """|a-e| <= atol + rtol*s, with a readable report of the worst entry.  s = |e| elementwise by default;
+    ``scale="vec"``: s = the norm of the vector the element belongs to (``natural_scale``).  ``small_angle`` =
+    dict(below, rtol, atol): for [n, 3k] exp-map rows, joints whose rotation angle |e_joint| is below ``below`` get
+    their own tolerance (the reference's axis = xyz / sqrt(1 - w*w) amplifies a 1-ulp difference in w there)."""
     a = torch.as_tensor(actual).detach().cpu().double()
     e = torch.as_tensor(expected).detach().cpu().double()
     assert a.shape == e.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(e.shape)}"
@@ -74,15 +125,19 @@ def assert_close(actual, expected, rtol=1e-5, atol=1e-6, what=""):
     a = torch.where(nan_a, torch.zeros_like(a), a)
     e = torch.where(nan_e, torch.zeros_like(e), e)
     err = (a - e).abs()
-    tol = atol + rtol * e.abs()
+    s = natural_scale(e) if scale == "vec" else e.abs()
+    tol = atol + rtol * s
+    if small_angle is not None and e.dim() == 2 and e.shape[1] % 3 == 0:
+        ang = e.reshape(e.shape[0], -1, 3).norm(dim=-1, keepdim=True).expand(-1, -1, 3).reshape(e.shape)
+        tol = torch.where(ang < small_angle["below"], small_angle["atol"] + small_angle["rtol"] * s, tol)
     bad = err > tol
     if bad.any():
         worst = torch.argmax(err - tol)
         idx = np.unravel_index(int(worst), a.shape) if a.dim() else ()
         raise AssertionError(
-            f"{what}: {int(bad.sum())}/{a.numel()} outside rtol={rtol} atol={atol}; worst at {idx}: "
-            f"got {a.flatten()[worst].item():.9g} want {e.flatten()[worst].item():.9g} "
-            f"(abs err {err.flatten()[worst].item():.3g})"
+            f"{what}: {int(bad.sum())}/{a.numel()} outside rtol={rtol} atol={atol}{' (vector-relative)' if scale else ''}; "
+            f"worst at {idx}: got {a.flatten()[worst].item():.9g} want {e.flatten()[worst].item():.9g} "
+            f"(abs err {err.flatten()[worst].item():.3g}, scale {s.flatten()[worst].item():.3g})"
         )
 
 

@@ -2140,31 +2140,42 @@ constexpr int PS_STAGES = 2;
 constexpr int PS_EPB = 4;
 constexpr int PS_CONSUMERS = PS_EPB * J24;  // 96
 constexpr int PS_THREADS = PS_CONSUMERS + 32;
-constexpr int PS_BLOCKS_PER_SM = 4;
 
+// SLOTS: frame rows per env held in a stage.  A step needs the rows of two queries, t and t + dt: three consecutive
+// rows when the clip's frame time equals the env's dt (the reference's regime: 30 fps clips, dt = 1/30 s), up to
+// four otherwise (60 / 120 fps clips, unaligned times).  With SLOTS = 3 a stage is 22.5 KB and FIVE blocks fit an SM
+// (15 consumer warps instead of 12: +5 % at 32768 / 65536 envs, 0.93 / 0.98 of the measured HBM peak); an env that
+// needs a fourth row reads that one row ("far" row) straight from the packed table, L2-prefetched by the producer.
+template <int SLOTS>
 struct PersistStage {
   float sim[PS_EPB * ROW13];
-  float frames[PS_EPB * 4 * FRAME_FLOATS];  // [env][slot 0..3][312]; later the obs stage [env][934]
+  float frames[PS_EPB * SLOTS * FRAME_FLOATS];  // [env][slot][312]; later the obs stage [env][934]
   float part[6][PS_EPB][J24];
   float bl[2][PS_EPB];
-  int slot[2][2][PS_EPB];
+  int slot[2][2][PS_EPB];   // slot of (query, frame 0 / 1); == SLOTS: the far row
+  int64_t far[PS_EPB];      // packed-table row of the env's far row
   float goff[PS_EPB][4];
   float hz[PS_EPB], hw[PS_EPB];
   int prog[PS_EPB], pass[PS_EPB], fallen[PS_EPB];
   int tile;  // env tile held by the stage, -1: no more tiles
   int pad_[3];
+  static_assert(SLOTS * FRAME_FLOATS >= STAGE_FLOATS, "the obs stage aliases the frame buffer");
 };
-static_assert(sizeof(PersistStage) % 16 == 0, "stages keep the 16-byte alignment of the TMA destinations");
+template <int SLOTS>
 struct PersistSmem {
-  PersistStage st[PS_STAGES];
+  PersistStage<SLOTS> st[PS_STAGES];
   unsigned long long full[PS_STAGES], empty[PS_STAGES];
 };
+static_assert(sizeof(PersistStage<3>) % 16 == 0 && sizeof(PersistStage<4>) % 16 == 0,
+              "stages keep the 16-byte alignment of the TMA destinations");
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"r"(PS_CONSUMERS) : "memory"); }
 
-__global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_kernel(const __grid_constant__ StepParams p) {
+template <int SLOTS, int BLOCKS_PER_SM>
+__global__ void __launch_bounds__(PS_THREADS, BLOCKS_PER_SM) step_persist_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PersistSmem& M = *reinterpret_cast<PersistSmem*>(smem_raw);
+  PersistSmem<SLOTS>& M = *reinterpret_cast<PersistSmem<SLOTS>*>(smem_raw);
+  using Stage = PersistStage<SLOTS>;
   const int tid = threadIdx.x;
   const int num_tiles = (int)((p.n + PS_EPB - 1) / PS_EPB);
   if (tid == 0) {
@@ -2185,6 +2196,10 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
     // and — from registers only — blends and copies tile i.  Every load has a whole iteration to land.
     const int lane = tid - PS_CONSUMERS;
     const int le = lane >> 3, j = lane & 7;  // 8 lanes per env of the tile: lane 0 leads, lane 1 does the heading
+    // Nothing is read before the dependency wait.  (Copying the frame rows of a block's first two tiles before the wait
+    // and validating the clock after it — K6-fast's scheme — was built and measured: 27.59 against 27.59 us at 16384
+    // envs, 15.48 against 14.85 at 8192.  What a multi-wave launch loses at its boundaries is the under-filled last
+    // tile period and the first tile period in which every block loads at once, not the first tile's round trips.)
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     const bool block_sim = p.body.pos.stride_env == ROW13;  // a tile's sim rows are one span
@@ -2243,7 +2258,7 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
     Meta mA = load_meta(tA, cA);
     for (int it = 0;; ++it) {
       const int s = it % PS_STAGES;
-      PersistStage& S = M.st[s];
+      Stage& S = M.st[s];
       if (tA >= num_tiles) {  // tell the consumers and leave
         if (it >= PS_STAGES) mbar_wait(&M.empty[s], (uint32_t)(((it / PS_STAGES) - 1) & 1));
         if (lane == 0) {
@@ -2264,7 +2279,7 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
       const int nvalid = (int)((p.n - env0) < PS_EPB ? (p.n - env0) : PS_EPB);
       const bool act = le < nvalid;
       const int64_t env = env0 + (act ? le : 0);
-      float* fr = S.frames + le * (4 * FRAME_FLOATS);
+      float* fr = S.frames + le * (SLOTS * FRAME_FLOATS);
       if (act && j == 0) {
         if (block_sim ? le == 0 : true) {  // sim rows
           const uint32_t bytes = (block_sim ? (uint32_t)nvalid : 1u) * (uint32_t)(ROW13 * 4);
@@ -2283,14 +2298,16 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
         calc_frame_blend32(a_t, len, nf, mdt, a_f0, a_f1, a_bl);
         const float t1 = (float)(int16_t)(prog + 1) * p.dt + cA.start + cA.soff;
         calc_frame_blend32(t1, len, nf, mdt, b_f0, b_f1, b_bl);
-        // frames of one clip are consecutive rows of the packed table: when the (up to four) frames span <= 4 rows
-        // they arrive with ONE copy and slot = frame - first
+        // frames of one clip are consecutive rows of the packed table: when the (up to four) frames span <= SLOTS rows
+        // they arrive with ONE copy and slot = frame - first; otherwise the two queries' spans (one or two rows each)
+        // are copied one after the other, and a row that does not fit (the fourth of a 3-slot stage) stays in the
+        // table as the env's far row
         const float* tab = p.L.packed + mA.st * FRAME_FLOATS;
         const int lo = a_f0 < b_f0 ? a_f0 : b_f0;
         int hi = a_f1 > b_f1 ? a_f1 : b_f1;
         hi = hi > a_f0 ? hi : a_f0;
         hi = hi > b_f0 ? hi : b_f0;
-        if (hi - lo <= 3) {
+        if (hi - lo <= SLOTS - 1) {
           S.slot[0][0][le] = a_f0 - lo;
           S.slot[0][1][le] = a_f1 - lo;
           S.slot[1][0][le] = b_f0 - lo;
@@ -2298,16 +2315,26 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
           const uint32_t bytes = (uint32_t)(hi - lo + 1) * (uint32_t)(FRAME_FLOATS * 4);
           mbar_expect_tx(&M.full[s], bytes);
           bulk_g2s(fr, tab + (int64_t)lo * FRAME_FLOATS, bytes, &M.full[s]);
-        } else {  // two spans of one or two rows each (idx1 is idx0 or idx0 + 1)
+        } else {  // spans (a_f0 .. a_f1) and (b_f0 .. b_f1), idx1 is idx0 or idx0 + 1
+          const int na = a_f1 - a_f0 + 1;
+          int nb = b_f1 - b_f0 + 1;
           S.slot[0][0][le] = 0;
           S.slot[0][1][le] = a_f1 - a_f0;
-          S.slot[1][0][le] = 2;
-          S.slot[1][1][le] = 2 + (b_f1 - b_f0);
-          const uint32_t ba = (uint32_t)(a_f1 - a_f0 + 1) * (uint32_t)(FRAME_FLOATS * 4);
-          const uint32_t bb = (uint32_t)(b_f1 - b_f0 + 1) * (uint32_t)(FRAME_FLOATS * 4);
+          S.slot[1][0][le] = na;
+          S.slot[1][1][le] = na + (b_f1 - b_f0);
+          if (na + nb > SLOTS) {  // SLOTS == 3 and four distinct rows: the last one stays in the table
+            nb -= 1;
+            S.slot[1][1][le] = SLOTS;
+            S.far[le] = mA.st + b_f1;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(tab + (int64_t)b_f1 * FRAME_FLOATS),
+                         "r"((uint32_t)(FRAME_FLOATS * 4))
+                         : "memory");
+          }
+          const uint32_t ba = (uint32_t)na * (uint32_t)(FRAME_FLOATS * 4);
+          const uint32_t bb = (uint32_t)nb * (uint32_t)(FRAME_FLOATS * 4);
           mbar_expect_tx(&M.full[s], ba + bb);
           bulk_g2s(fr, tab + (int64_t)a_f0 * FRAME_FLOATS, ba, &M.full[s]);
-          bulk_g2s(fr + 2 * FRAME_FLOATS, tab + (int64_t)b_f0 * FRAME_FLOATS, bb, &M.full[s]);
+          bulk_g2s(fr + na * FRAME_FLOATS, tab + (int64_t)b_f0 * FRAME_FLOATS, bb, &M.full[s]);
         }
         S.bl[0][le] = a_bl;
         S.bl[1][le] = b_bl;
@@ -2350,7 +2377,7 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
   const int e = tid / J24, b = tid % J24;
   for (int it = 0;; ++it) {
     const int s = it % PS_STAGES;
-    PersistStage& S = M.st[s];
+    Stage& S = M.st[s];
     mbar_wait(&M.full[s], (uint32_t)((it / PS_STAGES) & 1));
     const int tile = S.tile;
     if (tile < 0) break;
@@ -2369,10 +2396,10 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
       vel = {d[7], d[8], d[9]};
       ang = {d[10], d[11], d[12]};
       root_pos = {S.sim[e * ROW13 + 0], S.sim[e * ROW13 + 1], S.sim[e * ROW13 + 2]};
-      const float* fr = S.frames + e * (4 * FRAME_FLOATS);
+      const float* fr = S.frames + e * (SLOTS * FRAME_FLOATS);
       {
         const RefBody r0 = blend_ref2(fr + S.slot[0][0][e] * FRAME_FLOATS, fr + S.slot[0][1][e] * FRAME_FLOATS,
-                                      S.bl[0][e], S.goff[e], b);
+                                      S.bl[0][e], S.goff[e], b);  // the far row, if any, is the second query's
         float sp, sr, sv, sa;
         reward_partials(pos, rot, vel, ang, r0, sp, sr, sv, sa);
         S.part[0][e][b] = sp;
@@ -2384,7 +2411,11 @@ __global__ void __launch_bounds__(PS_THREADS, PS_BLOCKS_PER_SM) step_persist_ker
         if (!p.use_mean && (p.reset_mask >> b & 1u) && dist > p.term_dist[b]) S.fallen[e] = 1;  // any(), benign race
         if (p.dof_force) S.part[5][e][b] = power_partial(p, env0 + e, b);
       }
-      r1 = blend_ref2(fr + S.slot[1][0][e] * FRAME_FLOATS, fr + S.slot[1][1][e] * FRAME_FLOATS, S.bl[1][e], S.goff[e], b);
+      const int s11 = S.slot[1][1][e];
+      if (SLOTS >= 4 || s11 < SLOTS)
+        r1 = blend_ref2(fr + S.slot[1][0][e] * FRAME_FLOATS, fr + s11 * FRAME_FLOATS, S.bl[1][e], S.goff[e], b);
+      else  // the fourth row of a 3-slot stage: read from the packed table (L2: the producer prefetched it)
+        r1 = blend_ref2(fr + S.slot[1][0][e] * FRAME_FLOATS, p.L.packed + S.far[e] * FRAME_FLOATS, S.bl[1][e], S.goff[e], b);
     }
     consumer_sync();  // partials visible; frame buffer dead -> becomes the obs stage
 
@@ -3280,7 +3311,9 @@ __global__ void episode_fold_kernel(double* __restrict__ sums, int nb, int raw_c
 using namespace phc;
 
 static int g_moments_bulk = -1;  // PHC_OPT_MOMENTS_BULK / env PHC_MOMENTS_BULK=0|1 (default 0: measured no faster than the atomics)
-static int g_persist = -1;       // PHC_OPT_STEP_PERSIST / env PHC_STEP_PERSIST: 0 never, 1 from g_persist_min envs on (default), 2 always
+static int g_persist = -1;       // PHC_OPT_STEP_PERSIST / env PHC_STEP_PERSIST: 0 never, 1 from g_persist_min envs on (default), 2 always,
+                                 // 3 always and the 4-slot / 4-blocks-per-SM instantiation
+static int g_persist_pdl = 1;
 static int64_t g_persist_min = 16384;
 
 template <typename Kern>
@@ -3750,7 +3783,8 @@ static void init_options() {
   }
   if (g_persist < 0) {
     const char* w = getenv("PHC_STEP_PERSIST");
-    g_persist = (w && w[0] >= '0' && w[0] <= '2') ? w[0] - '0' : 1;
+    g_persist = (w && w[0] >= '0' && w[0] <= '3') ? w[0] - '0' : 1;
+    g_persist_pdl = g_pdl;
     const char* m = getenv("PHC_STEP_PERSIST_MIN");
     if (m && atoll(m) > 0) g_persist_min = atoll(m);
   }
@@ -3800,6 +3834,7 @@ int phc_set_option(int key, int value) {
       return PHC_OK;
     case PHC_OPT_STEP_PDL:
       g_pdl = value ? 1 : 0;
+      g_persist_pdl = g_pdl;
       return PHC_OK;
     case PHC_OPT_TEST_SPEC_FAULT:
       g_spec_fault = value;
@@ -3812,7 +3847,7 @@ int phc_set_option(int key, int value) {
       g_moments_bulk = value ? 1 : 0;
       return PHC_OK;
     case PHC_OPT_STEP_PERSIST:
-      if (value < 0 || value > 2) return PHC_ERR_SHAPE;
+      if (value < 0 || value > 3) return PHC_ERR_SHAPE;
       g_persist = value;
       return PHC_OK;
     default:
@@ -3847,32 +3882,35 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
   static int first_wave[64] = {};
   // several waves of blocks (BASELINE config 3): the persistent warp-specialised kernel.  It carries the plain step
   // (+ power reward, flag / reward copies); the optional epilogues stay with K6-fast.
-  static bool attr_persist[64] = {};
+  static bool attr_persist[2][64] = {};
   static int sm_count[64] = {};
-  const bool persist = fast && def && g_persist != 0 && (g_persist == 2 || p.n >= g_persist_min) && !p.obs_norm &&
+  const bool persist = fast && def && g_persist != 0 && (g_persist >= 2 || p.n >= g_persist_min) && !p.obs_norm &&
                        !p.ep_returns && !p.reset_on && !p.moments && !p.ref_dof_pos && !p.trace && lib->tile_counters &&
                        !(args->flags & PHC_STEP_MAPPED_HOST_IO);
   if (persist) {
     if (!sm_count[dev]) PHC_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-    if (!attr_persist[dev]) {
-      PHC_CUDA(cudaFuncSetAttribute(step_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PersistSmem)));
-      attr_persist[dev] = true;
+    const bool four = g_persist == 3;  // the 4-slot / 4-blocks-per-SM instantiation (tests, comparisons)
+    auto kern = four ? step_persist_kernel<4, 4> : step_persist_kernel<3, 5>;
+    const size_t smem = four ? sizeof(PersistSmem<4>) : sizeof(PersistSmem<3>);
+    if (!attr_persist[four][dev]) {
+      PHC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_persist[four][dev] = true;
     }
     if (lib->unspeculated_steps > 0) --lib->unspeculated_steps;  // nothing is read before the dependency wait here
     p.tile_counter = lib->tile_counters + 2 * (lib->tile_seq++ % TILE_SLOTS);
     const int64_t tiles = (p.n + PS_EPB - 1) / PS_EPB;
-    const int64_t resident = (int64_t)sm_count[dev] * PS_BLOCKS_PER_SM;
+    const int64_t resident = (int64_t)sm_count[dev] * (four ? 4 : 5);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(tiles < resident ? tiles : resident));
     cfg.blockDim = dim3(PS_THREADS);
-    cfg.dynamicSmemBytes = sizeof(PersistSmem);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = g_pdl ? 1 : 0;
-    PHC_CUDA(cudaLaunchKernelEx(&cfg, step_persist_kernel, p));
+    cfg.numAttrs = g_persist_pdl ? 1 : 0;
+    PHC_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     return launch_status();
   }
   if (fast) {

@@ -390,7 +390,8 @@ PHC_API int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* args, int64_t 
 #define PHC_OPT_MOMENTS_BULK 6        /* 1: the T = 1 kernel's moments epilogue (obs_moments) hands each block's 1868 partial sums to the TMA
                                         engine as three bulk fp64 reductions; 0 (default, measured a little faster): one atomic per sum */
 #define PHC_OPT_STEP_PERSIST 7        /* the persistent warp-specialised T = 1 kernel for multi-wave grids: 1 (default) from 16384 envs on
-                                        (env PHC_STEP_PERSIST_MIN), 0 never, 2 always (tests) */
+                                        (env PHC_STEP_PERSIST_MIN), 0 never, 2 always (tests), 3 always with four
+                                        frame slots per env and four blocks per SM instead of three and five (comparison) */
 PHC_API int phc_set_option(int key, int value);
 /* Profiling aid: when a device buffer of capacity_warps x 8 uint64 is set, every warp of the
  * fast step kernel (EPB 4: 3 warps per block) stamps %globaltimer (ns) at its phase boundaries:

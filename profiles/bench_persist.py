@@ -22,7 +22,7 @@ except Exception:
     peak = 6456.2
 K = 64
 print(f"# K6-persist vs K6-fast (us per step, {K}-step graph, best of 5; frac of {peak} GB/s at 8804 B/env-step)\n")
-print("| envs | K6-fast us | frac | K6-persist us | frac |\n|---|---|---|---|---|")
+print("| envs | K6-fast us | frac | K6-persist (3 slots, 5 blocks/SM) us | frac | K6-persist (4 slots, 4 blocks/SM) us | frac |\n|---|---|---|---|---|---|---|")
 for N in sizes:
     lib_data = synth.make_motion_lib(N, 60, 300, (30,), seed=1234, device=dev)
     lib = MotionLib(lib_data, device=dev)
@@ -50,7 +50,7 @@ for N in sizes:
             envs[i % R].post_physics_step(True)
 
     row = []
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         capi.phc_set_option(_cabi.OPT_STEP_PERSIST, mode)
         run(R)
         torch.cuda.synchronize()
@@ -76,6 +76,6 @@ for N in sizes:
         del g
     capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 1)
     f = lambda us: 8804 * N / (us * 1e-6) / 1e9 / peak  # noqa: E731
-    print(f"| {N} | {row[0]:.2f} | {f(row[0]):.3f} | {row[1]:.2f} | {f(row[1]):.3f} |", flush=True)
+    print(f"| {N} | {row[0]:.2f} | {f(row[0]):.3f} | {row[1]:.2f} | {f(row[1]):.3f} | {row[2]:.2f} | {f(row[2]):.3f} |", flush=True)
     del envs, first, lib, lib_data
     torch.cuda.empty_cache()

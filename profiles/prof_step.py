@@ -42,9 +42,20 @@ for r in range(R):
     envs.append(env)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+prog0 = [e.progress_buf.clone() for e in envs] if C4 else envs[0].progress_buf.clone()
+if not C4:  # all ring slots share one motion clock, re-seeded at every lap like bench.py does
+    for e in envs[1:]:
+        for k in ("progress_buf", "_motion_start_times", "_motion_start_times_offset", "_global_offset", "_sampled_motion_ids"):
+            setattr(e, k, getattr(envs[0], k))
 for i in range(L):
     if i == L // 2:
         e0.record()
+    if i % R == 0:
+        if C4:
+            for e, p0 in zip(envs, prog0):
+                e.progress_buf.copy_(p0)
+        else:
+            envs[0].progress_buf.copy_(prog0)
     envs[i % R].post_physics_step(True)
 e1.record()
 torch.cuda.synchronize()

@@ -13,11 +13,8 @@ run() { # tag regex args...
     --log-file "gpurun_out/traffic_${tag}.csv" python profiles/prof_step.py "$@" > "gpurun_out/traffic_${tag}.ncu.log" 2>&1
   echo "$tag: $(cat gpurun_out/traffic_${tag}.plain.log | tail -1)"
 }
-run step_kernel_T1_N4096 step_ 4096 1 60
-run step_kernel_T1_N8192 step_ 8192 1 60
-run step_kernel_T1_N16384 step_ 16384 1 60
-run step_kernel_T1_N65536 step_ 65536 1 60
-run config4_T1_N4096 step_ 4096 1 60 config4
-run step_kernel_T10_N2048 step_ 2048 10 60
-run step_kernel_T10_N16384 step_ 16384 10 60
+# launches 40..47 of an 80-launch run; every config bench.py reports at 1 / 2 / 4 / 8 GPUs
+for n in 4096 8192 16384 32768 65536; do run step_kernel_T1_N$n step_ $n 1 80; done
+run config4_T1_N4096 step_ 4096 1 80 config4
+for n in 2048 4096 8192 16384; do run step_kernel_T10_N$n step_ $n 10 80; done
 python profiles/traffic_from_ncu.py gpurun_out > gpurun_out/traffic_summary.md; cat gpurun_out/traffic_summary.md

@@ -521,7 +521,8 @@ def test_fast_kernel_equals_generic_kernel_bitwise(N):
 def test_persistent_kernel_equals_generic_kernel_bitwise(N, regime):
     """K6-persist (persistent blocks, producer warp + consumer warps, tiles drawn from a device counter) against the
     generic kernel: every output bit for bit, three steps deep (the counter must rewind itself between launches),
-    ragged N, the two-span frame case of unaligned clips, and the power reward."""
+    ragged N, the two-span frame case of unaligned clips (with three frame slots per env: the far row read from the
+    packed table), and the power reward; both instantiations (3 slots / 5 blocks per SM, 4 slots / 4 blocks)."""
     from humanoid_b200 import HumanoidPHC, _cabi
 
     kw = dict(max_progress=40)
@@ -532,8 +533,8 @@ def test_persistent_kernel_equals_generic_kernel_bitwise(N, regime):
     capi = _cabi.load()
     outs = []
     try:
-        for which in ("persist", "generic"):
-            capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 2 if which == "persist" else 0)
+        for which in ("persist_3slots_5blocks", "persist_4slots_4blocks", "generic"):
+            capi.phc_set_option(_cabi.OPT_STEP_PERSIST, {"persist_3slots_5blocks": 2, "persist_4slots_4blocks": 3}.get(which, 0))
             capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 1 if which == "generic" else 0)
             env = HumanoidPHC(lib, N, device=DEV, use_power_reward=regime == "power")
             env.set_sim_state(state)
@@ -551,9 +552,52 @@ def test_persistent_kernel_equals_generic_kernel_bitwise(N, regime):
     finally:
         capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 1)
         capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
-    for k, (a, b) in enumerate(zip(*outs)):
-        for x, y, nm in zip(a, b, ("obs", "rew", "reward_raw", "reset", "terminate", "progress", "reset_out", "terminate_out")):
-            assert torch.equal(x, y), f"step {k}: {nm}"
+    for variant in (0, 1):
+        for k, (a, b) in enumerate(zip(outs[variant], outs[2])):
+            for x, y, nm in zip(a, b, ("obs", "rew", "reward_raw", "reset", "terminate", "progress", "reset_out", "terminate_out")):
+                assert torch.equal(x, y), f"variant {variant}, step {k}: {nm}"
+
+
+@pytest.mark.parametrize("variant", [2, 3], ids=["3slots_5blocks", "4slots_4blocks"])
+def test_persistent_kernel_with_resets_between_steps_equals_single_wave_kernel(variant):
+    """Four steps with a device-side reset of the flagged envs in between (their clocks restart under the producers'
+    three-tile pipeline), mixed 30 / 60 fps clips and unaligned times (far rows): every output bit-identical to the
+    single-wave kernel's."""
+    from humanoid_b200 import HumanoidPHC, _cabi
+
+    N = 16390
+    lib_data, clock, state = _gpu_case(N, 300, 79, max_progress=30, ids="random", aligned=False, fps_choices=(30, 60),
+                                       min_frames=80, max_frames=300)  # fmt: skip
+    lib = MotionLib(lib_data, device=DEV)
+    capi = _cabi.load()
+    outs = []
+    gen = torch.Generator().manual_seed(3)
+    phases = [torch.rand(N, generator=gen).to(DEV) for _ in range(4)]
+    try:
+        capi.phc_set_option(_cabi.OPT_STEP_PERSIST, variant)
+        for _ in range(2):
+            env = HumanoidPHC(lib, N, device=DEV)
+            env.set_sim_state(state)
+            env.set_clock(clock)
+            for k in range(4):
+                env.step()
+                if k == 1:
+                    env.reset_done(phases[k])  # clocks of the flagged envs change under the next step's speculation
+            torch.cuda.synchronize()
+            outs.append(env)
+    finally:
+        capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 0)
+    ref = HumanoidPHC(lib, N, device=DEV)  # the single-wave kernel as the reference
+    ref.set_sim_state(state)
+    ref.set_clock(clock)
+    for k in range(4):
+        ref.step()
+        if k == 1:
+            ref.reset_done(phases[k])
+    capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 1)
+    for f in outs:
+        for nm in ("obs_buf", "rew_buf", "reward_raw", "reset_buf", "_terminate_buf", "progress_buf"):
+            assert torch.equal(getattr(f, nm), getattr(ref, nm)), nm
 
 
 def test_persistent_kernel_in_a_cuda_graph_with_many_launches():

@@ -314,6 +314,12 @@ typedef struct PhcStepArgs {
 } PhcStepArgs;
 #define PHC_STEP_OBS_FLAGS_SET 0x80000000u
 
+/* Kernel selection (all bit-identical): T == 1 on one AoS-13 sim tensor with a dense 16-B aligned obs_buf runs the
+ * single-wave TMA kernel, or — from 16384 envs on, when none of the optional epilogues is asked for — the persistent
+ * warp-specialised kernel, whose blocks draw env tiles from a device-side counter owned by `lib` (256 counter slots used
+ * round robin, each left zero by the launch that used it: launches of one PhcLib may overlap on different streams as
+ * long as fewer than 256 of them are in flight or captured in concurrently replayed graphs); T > 1 runs the pipelined
+ * multi-query kernel; anything else (strided views, non-default flags with T > 1) the generic kernel. */
 PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n, phc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 //
 // Compiled with -fmad=false (see phc_math.cuh).
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -3344,11 +3345,11 @@ struct PhcLib {
   // immutable).  A launch that (re)writes the library on the same stream — phc_lib_pack, phc_motion_build followed
   // by phc_lib_pack, or the caller's own kernels before phc_lib_create — is only ordered before the step's
   // post-wait reads, so the first fused step after phc_lib_create / phc_lib_pack runs without the speculation.
-  mutable int unspeculated_steps = 1;
+  mutable std::atomic<int> unspeculated_steps{1};
   // tile counters of the persistent step kernel: every launch draws the next of TILE_SLOTS slots (two words that the
   // launch leaves zero), so launches that overlap on different streams do not share one
   unsigned* tile_counters = nullptr;
-  mutable unsigned tile_seq = 0;
+  mutable std::atomic<unsigned> tile_seq{0};  // host threads may launch steps of one library concurrently
 };
 constexpr unsigned TILE_SLOTS = 256;
 
@@ -3897,7 +3898,7 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
       attr_persist[four][dev] = true;
     }
     if (lib->unspeculated_steps > 0) --lib->unspeculated_steps;  // nothing is read before the dependency wait here
-    p.tile_counter = lib->tile_counters + 2 * (lib->tile_seq++ % TILE_SLOTS);
+    p.tile_counter = lib->tile_counters + 2 * (lib->tile_seq.fetch_add(1u, std::memory_order_relaxed) % TILE_SLOTS);
     const int64_t tiles = (p.n + PS_EPB - 1) / PS_EPB;
     const int64_t resident = (int64_t)sm_count[dev] * (four ? 4 : 5);
     cudaLaunchConfig_t cfg{};

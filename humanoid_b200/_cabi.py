@@ -312,6 +312,8 @@ SIGNATURES = {
     "phc_host_step": (C.c_int, [C.c_void_p, C.POINTER(PhcHostStepArgs), C.c_int64]),
     "phc_host_step_destroy": (None, [C.c_void_p]),
     "phc_host_step_path": (C.c_int, [C.c_void_p]),
+    "phc_host_step_chunks": (C.c_int, [C.c_void_p]),
+    "phc_host_step_tuning_calls": (C.c_int, [C.c_void_p]),
     "phc_host_step_h2d_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
     "phc_host_step_d2h_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
     "phc_obs_moments": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),

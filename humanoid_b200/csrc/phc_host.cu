@@ -19,6 +19,7 @@
 // call returns when every output is in the caller's host memory.
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -69,11 +70,16 @@ struct PhcHostStep {
   // which output path pinned callers take: 0 = auto (time both over the first calls, keep the faster), 1 = direct
   // (kernels post into the mapped host buffers), 2 = staged (copy-engine D2H).  PHC_HOST_PATH=auto|direct|staged.
   int mode = 0;
-  int chosen = 0;  // auto: 0 while undecided
+  // the schedule (output path, chunk count) of pinned callers is tuned over the first calls: every candidate is timed
+  // kTuneReps times, interleaved, and the fastest mean stays.  num_chunks > 0 at create and PHC_HOST_PATH narrow the
+  // candidates (down to one: nothing to tune).
+  struct Cand { int path, chunks; double t; int n; };
+  Cand cand[8] = {};
+  int ncand = 0;
+  int chosen = -1;  // index into cand once decided
   int calls = 0;
-  double t_path[3] = {0, 0, 0};
-  int n_path[3] = {0, 0, 0};
 };
+constexpr int kTuneWarm = 2, kTuneReps = 3;
 
 // After the first enqueue an early return must not leave kernels writing into the caller's (mapped) buffers or
 // into the staging buffers the next call reuses: every error path drains the three streams first.
@@ -114,7 +120,7 @@ int phc_host_step_create(const PhcLib* lib, int64_t max_envs, int32_t time_steps
                          const float* termination_distances_host, uint32_t reset_body_mask, int32_t use_mean,
                          int32_t enable_early_termination, float dt, const PhcRewardSpec* rwd, PhcHostStep** out) {
   if (!lib || !termination_distances_host || !rwd || !out) return PHC_ERR_NULL;
-  if (max_envs <= 0 || time_steps < 1 || time_steps > PHC_MAX_TIME_STEPS || num_chunks < 1 || num_chunks > 1024)
+  if (max_envs <= 0 || time_steps < 1 || time_steps > PHC_MAX_TIME_STEPS || num_chunks < 0 || num_chunks > 1024)
     return PHC_ERR_SHAPE;
   PhcHostStep* c = new (std::nothrow) PhcHostStep;
   if (!c) return PHC_ERR_ALLOC;
@@ -132,7 +138,23 @@ int phc_host_step_create(const PhcLib* lib, int64_t max_envs, int32_t time_steps
   if (getenv("PHC_HOST_STAGED")) c->mode = 2;
   const size_t n = (size_t)max_envs;
   // every chunk's packed region is padded so each sub-array starts 16-B aligned
-  c->pack_capacity = n * 32 + (size_t)num_chunks * 6 * 64 + 4096;
+  c->pack_capacity = n * 32 + (size_t)(num_chunks > 8 ? num_chunks : 8) * 6 * 64 + 4096;
+  {  // candidates: direct with 2 / 3 / 4 / 6 equal chunks, staged with 3 / 4 doubling chunks
+    static const int direct_chunks[] = {3, 4, 2, 6}, staged_chunks[] = {3, 4};
+    auto add = [&](int path, int chunks) {
+      if (c->mode && c->mode != path) return;
+      if (num_chunks > 0 && chunks != num_chunks) return;
+      c->cand[c->ncand++] = {path, chunks, 0.0, 0};
+    };
+    if (num_chunks > 0) {
+      add(1, num_chunks);
+      add(2, num_chunks);
+    } else {
+      for (int ch : direct_chunks) add(1, ch);
+      for (int ch : staged_chunks) add(2, ch);
+    }
+    if (c->ncand == 1) c->chosen = 0;
+  }
   cudaError_t e = cudaSuccess;
   auto dmalloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
@@ -178,8 +200,8 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
   // multiples of 8 envs so every chunk's obs rows start 16-B aligned.
   int64_t bounds[1026];
   int nchunks = 0;
-  {
-    const int C = c->chunks;
+  auto make_bounds = [&](const int C) {
+    nchunks = 0;
     int64_t lo = 0;
     bounds[0] = 0;
     for (int i = 0; i < C && lo < n; ++i) {
@@ -192,7 +214,7 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
       lo = hi;
     }
     bounds[nchunks] = n;
-  }
+  };
   // sub-array offsets inside a chunk's packed regions (each 16-B aligned)
   struct Layout {
     size_t ids, goff, start, soff, prog, clock_bytes;
@@ -238,7 +260,7 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
       c->seen_direct = direct;
     }
   }
-  auto direct_path = [&]() -> int {
+  auto direct_path = [&](const int chunks) -> int {
       // Hybrid: everything INBOUND rides the host->device copy engine in a few chunks — the sim
       // rows directly from the caller's buffer, the five small clock arrays packed into one
       // transfer (SM-issued reads of system memory are 32-B PCIe round trips: 6 per block, ~70 us
@@ -248,11 +270,21 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
       // the link.  The advanced progress is written to the caller's buffer by the kernel as well.
       // equal chunks here: measured, a small first chunk does not help this path (the step is
       // bound by the kernels' posted writes, ~300 us per 4096 envs, plus the first copy)
-      const int C = c->chunks < 1 ? 1 : c->chunks;
+      const int C = chunks < 1 ? 1 : chunks;
       int64_t per = (n + C - 1) / C;
       per = (per + 7) / 8 * 8;
       size_t coff = 0;
       int ci = 0;
+      static const bool trace_on = getenv("PHC_HOST_TRACE") != nullptr;
+      static int trace_calls = 0;
+      const bool trace = trace_on && ++trace_calls == 20;
+      cudaEvent_t ev0 = nullptr, evh[64], evk[64];
+      double host_us[64];
+      const auto th0 = std::chrono::steady_clock::now();
+      if (trace) {
+        cudaEventCreate(&ev0);
+        cudaEventRecord(ev0, c->streams[0]);
+      }
       for (int64_t lo = 0; lo < n; lo += per, ++ci) {
         const int64_t m = (n - lo) < per ? (n - lo) : per;
         const Layout L = layout(m);
@@ -270,6 +302,10 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
         HOST_CUDA(c, cudaMemcpyAsync(st, a->state + lo * kStateFloats, (size_t)m * kStateFloats * sizeof(float),
                                      cudaMemcpyHostToDevice, s));
         PhcStepArgs k{};
+        if (trace && ci < 64) {
+          cudaEventCreate(&evh[ci]);
+          cudaEventRecord(evh[ci], s);
+        }
         k.body.pos = PhcView{st, kStateFloats, 13};
         k.body.rot = PhcView{st + 3, kStateFloats, 13};
         k.body.vel = PhcView{st + 7, kStateFloats, 13};
@@ -300,13 +336,30 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
         // the advanced progress goes straight into the caller's buffer too (no device->host copy at the tail)
         int rc = step_fused_mirrored(c->lib, &k, m, s, a->progress_buf + lo);
         if (rc) return host_fail(c, rc, cudaSuccess);
+        if (trace && ci < 64) {
+          cudaEventCreate(&evk[ci]);
+          cudaEventRecord(evk[ci], s);
+          host_us[ci] = std::chrono::duration<double>(std::chrono::steady_clock::now() - th0).count() * 1e6;
+        }
         coff += L.clock_bytes;
       }
       for (int i = 0; i < kStreams; ++i) HOST_CUDA(c, cudaStreamSynchronize(c->streams[i]));
+      if (trace) {
+        const double tot = std::chrono::duration<double>(std::chrono::steady_clock::now() - th0).count() * 1e6;
+        fprintf(stderr, "[phc_host trace] %d chunks of %lld envs, host total %.1f us\n", ci, (long long)per, tot);
+        for (int i = 0; i < ci && i < 64; ++i) {
+          float a_ms = 0, b_ms = 0;
+          cudaEventElapsedTime(&a_ms, ev0, evh[i]);
+          cudaEventElapsedTime(&b_ms, ev0, evk[i]);
+          fprintf(stderr, "  chunk %d: submitted at %.1f us (host), H2D done %.1f us, kernel done %.1f us\n", i, host_us[i],
+                  a_ms * 1e3, b_ms * 1e3);
+        }
+      }
       return PHC_OK;
   };
-  auto staged_path = [&]() -> int {
+  auto staged_path = [&](const int chunks) -> int {
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+  make_bounds(chunks < 1 ? 1 : chunks);
 
   size_t coff = 0, ooff = 0;
   for (int ci = 0; ci < nchunks; ++ci) {
@@ -385,32 +438,59 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
   return PHC_OK;
   };
 
-  // ---- which path ----------------------------------------------------------------------------
-  if (c->seen_direct != 1 || c->mode == 2) return staged_path();
-  if (c->mode == 1) return direct_path();
-  if (c->chosen) return c->chosen == 1 ? direct_path() : staged_path();
-  // auto: calls 0-2 warm both paths up, calls 3-8 alternate and are timed; the faster mean stays.  What decides is
-  // the machine: one GPU posts its obs rows into host memory faster than a copy engine drains a staging buffer;
-  // eight GPUs posting at once into one root complex may not (profiles/r2_e2e_floor.md).
+  // ---- which schedule ------------------------------------------------------------------------
+  const int fallback_chunks = c->chunks > 0 ? c->chunks : 3;
+  if (c->seen_direct != 1) return staged_path(fallback_chunks);  // pageable caller: copy-engine path only
+  auto run = [&](const PhcHostStep::Cand& k) { return k.path == 1 ? direct_path(k.chunks) : staged_path(k.chunks); };
+  if (c->chosen >= 0) return run(c->cand[c->chosen]);
+  // Tuning: calls 0-1 warm up, then the candidates take turns (kTuneReps timed calls each) and the fastest mean
+  // stays.  What decides is the machine, under whatever load the other GPUs of the box put on the host at that moment:
+  // one GPU posts its obs rows into host memory faster than a copy engine drains a staging buffer, eight GPUs posting
+  // into one root complex may not (profiles/r2_e2e_floor.md); and on some hosts the inbound copy of the next chunk
+  // crawls while a kernel is posting (its read requests queue behind the posted writes), which moves the best chunk
+  // count (profiles/r2_host_timeline.md).
   const int k = c->calls++;
-  const int which = k < 2 ? 1 : k == 2 ? 2 : ((k & 1) ? 1 : 2);
+  const int which = k < kTuneWarm ? k % c->ncand : (k - kTuneWarm) % c->ncand;
   const auto t0 = std::chrono::steady_clock::now();
-  const int rc = which == 1 ? direct_path() : staged_path();
+  const int rc = run(c->cand[which]);
   const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  if (rc == PHC_OK && k >= 3) {
-    c->t_path[which] += dt;
-    c->n_path[which] += 1;
-    if (c->n_path[1] >= 3 && c->n_path[2] >= 3)
-      c->chosen = (c->t_path[1] / c->n_path[1] <= c->t_path[2] / c->n_path[2]) ? 1 : 2;
+  if (rc == PHC_OK && k >= kTuneWarm) {
+    // the first timed call of a candidate warms its own launch configuration: not counted
+    if (k - kTuneWarm >= c->ncand) {
+      c->cand[which].t += dt;
+      c->cand[which].n += 1;
+    }
+    bool done = true;
+    for (int i = 0; i < c->ncand; ++i) done = done && c->cand[i].n >= kTuneReps;
+    if (done) {
+      int best = 0;
+      for (int i = 1; i < c->ncand; ++i)
+        if (c->cand[i].t / c->cand[i].n < c->cand[best].t / c->cand[best].n) best = i;
+      c->chosen = best;
+      if (getenv("PHC_HOST_TRACE"))
+        for (int i = 0; i < c->ncand; ++i)
+          fprintf(stderr, "[phc_host tune] %s, %d chunks: %.1f us%s\n", c->cand[i].path == 1 ? "direct" : "staged",
+                  c->cand[i].chunks, c->cand[i].t / c->cand[i].n * 1e6, i == best ? "  <- kept" : "");
+    }
   }
   return rc;
 }
 
 int phc_host_step_path(const PhcHostStep* c) {
   if (!c) return 0;
-  if (c->seen_direct == 0 || c->mode == 2) return 2;
-  if (c->mode == 1) return 1;
-  return c->chosen;
+  if (c->seen_direct == 0) return 2;
+  return c->chosen >= 0 ? c->cand[c->chosen].path : 0;
+}
+
+int phc_host_step_chunks(const PhcHostStep* c) {
+  if (!c) return 0;
+  if (c->seen_direct == 0) return c->chunks > 0 ? c->chunks : 3;
+  return c->chosen >= 0 ? c->cand[c->chosen].chunks : 0;
+}
+
+int phc_host_step_tuning_calls(const PhcHostStep* c) {
+  if (!c || c->ncand <= 1) return 0;
+  return kTuneWarm + c->ncand * (kTuneReps + 1);
 }
 
 }  // extern "C"

@@ -449,11 +449,15 @@ PHC_API int phc_host_step_create(const PhcLib* lib, int64_t max_envs, int32_t ti
                          const PhcRewardSpec* rwd, PhcHostStep** out);
 PHC_API int phc_host_step(PhcHostStep* ctx, const PhcHostStepArgs* args, int64_t n);
 PHC_API void phc_host_step_destroy(PhcHostStep* ctx);
-/* Which output path pinned callers are on: 1 = direct (each chunk's kernel posts obs rows / rewards / flags into the
- * mapped host buffers), 2 = staged (device buffers + copy-engine D2H; always the case for pageable callers), 0 = not
- * decided yet.  By default the context times both over its first calls (3 each, alternating, under whatever load
- * the other GPUs of the box put on the host at that moment) and keeps the faster; PHC_HOST_PATH=direct|staged pins it. */
+/* The schedule pinned callers are on.  phc_host_step_path: 1 = direct (each chunk's kernel posts obs rows / rewards /
+ * flags into the mapped host buffers), 2 = staged (device buffers + copy-engine D2H; always the case for pageable
+ * callers), 0 = not decided yet.  phc_host_step_chunks: the chunk count in use (0 = not decided yet).  With
+ * num_chunks = 0 at create the context tunes (path, chunk count) over its first phc_host_step_tuning_calls() calls —
+ * every candidate timed three times, interleaved, under whatever load the other GPUs of the box put on the host at
+ * that moment — and keeps the fastest; num_chunks > 0 fixes the chunk count and PHC_HOST_PATH=direct|staged the path. */
 PHC_API int phc_host_step_path(const PhcHostStep* ctx);
+PHC_API int phc_host_step_chunks(const PhcHostStep* ctx);
+PHC_API int phc_host_step_tuning_calls(const PhcHostStep* ctx);
 PHC_API int64_t phc_host_step_h2d_bytes(const PhcHostStep* ctx, int64_t n);
 PHC_API int64_t phc_host_step_d2h_bytes(const PhcHostStep* ctx, int64_t n);
 

@@ -725,11 +725,12 @@ def test_running_norm_vs_reference_fixture(golden):
     assert_close(rn(cuda(g.inp("x2")[:32])), g.out("fwd"), what="forward", rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("mode", ["pinned_direct", "pinned_staged", "pinned_auto", "pageable_staged"])
+@pytest.mark.parametrize("mode", ["pinned_direct", "pinned_staged", "pinned_auto", "pinned_tuned", "pageable_staged"])
 def test_host_pipeline_matches_device_path(mode, monkeypatch):
-    """phc_host_step on host buffers == the device path, bit for bit, on every path: pinned buffers with the kernels
+    """phc_host_step on host buffers == the device path, bit for bit, on every schedule: pinned buffers with the kernels
     posting into the mapped host memory (direct), pinned buffers with copy-engine D2H (staged), the automatic choice
-    between the two (timed over the first calls), and pageable buffers (always staged)."""
+    between the two with a fixed chunk count (timed over the first calls), the full tuning of path and chunk count
+    (num_chunks = 0: every candidate runs, every call is checked), and pageable buffers (always staged)."""
     import ctypes as C
 
     from humanoid_b200 import HumanoidPHC, _cabi
@@ -750,7 +751,8 @@ def test_host_pipeline_matches_device_path(mode, monkeypatch):
     ctx = C.c_void_p()
     term = (C.c_float * 24)(*([0.25] * 24))
     spec = _cabi.reward_spec(env.rwd_specs)
-    _cabi.check(capi.phc_host_step_create(lib.handle, N, 1, 3, term, 0xFFFFFF, 0, 1, synth.SIM_DT, C.byref(spec),
+    want_chunks = 0 if mode == "pinned_tuned" else 3
+    _cabi.check(capi.phc_host_step_create(lib.handle, N, 1, want_chunks, term, 0xFFFFFF, 0, 1, synth.SIM_DT, C.byref(spec),
                                           C.byref(ctx)), "create")  # fmt: skip
     mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
     h = dict(
@@ -762,7 +764,9 @@ def test_host_pipeline_matches_device_path(mode, monkeypatch):
     )  # fmt: skip
     args = _cabi.PhcHostStepArgs(*[h[k].data_ptr() for k in ("state", "prog", "start", "off", "goff", "ids", "obs",
                                                              "rew", "raw", "reset", "term")])  # fmt: skip
-    calls = 12 if mode == "pinned_auto" else 1  # auto: both paths are timed over calls 3..8, then one is kept
+    # auto / tuned: every candidate schedule is timed over the first calls, then one is kept
+    calls = capi.phc_host_step_tuning_calls(ctx) + 2 if mode in ("pinned_auto", "pinned_tuned") else 1
+    assert calls == {"pinned_auto": 2 + 2 * 4 + 2, "pinned_tuned": 2 + 6 * 4 + 2}.get(mode, 1)
     for i in range(calls):
         h["prog"].copy_(clock.progress_buf.cpu())
         h["obs"].fill_(float("nan"))
@@ -771,6 +775,7 @@ def test_host_pipeline_matches_device_path(mode, monkeypatch):
     assert capi.phc_host_step_h2d_bytes(ctx, N) == N * (1248 + 2 + 4 + 4 + 12 + 8)
     path = capi.phc_host_step_path(ctx)
     assert path == {"pinned_direct": 1, "pinned_staged": 2, "pageable_staged": 2}.get(mode, path) and path in (1, 2)
+    assert capi.phc_host_step_chunks(ctx) in ((2, 3, 4, 6) if mode == "pinned_tuned" else (3,))
     capi.phc_host_step_destroy(ctx)
     assert torch.equal(h["obs"], env.obs_buf.cpu()) and torch.equal(h["rew"], env.rew_buf.cpu())
     assert torch.equal(h["raw"], env.reward_raw[:, :4].cpu())

@@ -788,6 +788,14 @@ __device__ __forceinline__ void reset_query_frames(int q, float dt, float t, flo
   calc_frame_blend(tq, len, nf, mdt, i0, i1, bl);
   f0 = i0 + st, f1 = i1 + st;
 }
+// the same with a 32-bit frame count (identical results, see calc_frame_blend32): the in-step reset's dependent chain
+__device__ __forceinline__ void reset_query_frames32(int q, float dt, float t, float len, int nf, float mdt, int64_t st,
+                                                     int64_t& f0, int64_t& f1, float& bl) {
+  const float tq = (float)(int16_t)q * dt + t + 0.0f;
+  int i0, i1;
+  calc_frame_blend32(tq, len, nf, mdt, i0, i1, bl);
+  f0 = st + i0, f1 = st + i1;
+}
 __device__ __forceinline__ RefBody reset_ref_body(const LibDev& L, int q, float dt, float t, float len, int64_t nf, float mdt,
                                                   int64_t st, int b) {
   int64_t f0, f1;
@@ -818,6 +826,62 @@ __device__ __forceinline__ float reset_start_time(const ResetTargets& w, int64_t
 // posed with the OLD global offset (:860), the _set_env_state scatter (humanoid_phc.py:901-931) and, on body 0, the
 // clock updates of _reset_ref_state_init (:724-731) and the buffer resets of _reset_env_tensors (:775-778).
 // `write_flags`: also clear reset_buf / terminate_buf (the fused step leaves that to the lane that owns the flags).
+// the _set_env_state scatter of one (env, body) (humanoid_phc.py:901-931) and, on body 0, the clock updates of
+// _reset_ref_state_init (:724-731) and the buffer resets of _reset_env_tensors (:775-778)
+__device__ __forceinline__ void reset_store_body(const ResetTargets& w, int64_t env, int b, float t, Vec3 pos, Quat rot,
+                                                 Vec3 vel, Vec3 ang, bool write_flags) {
+  st3(const_cast<float*>(view_at(w.body.pos, env, b)), pos);
+  st4(const_cast<float*>(view_at(w.body.rot, env, b)), rot);
+  st3(const_cast<float*>(view_at(w.body.vel, env, b)), vel);
+  st3(const_cast<float*>(view_at(w.body.ang_vel, env, b)), ang);
+  if (b == 0) {
+    if (w.root) {
+      float* r = w.root + env * w.root_stride;
+      st3(r, pos);
+      st4(r + 3, rot);
+      st3(r + 7, vel);
+      st3(r + 10, ang);
+    }
+    if (w.goff) {
+      w.goff[env * 3 + 0] = 0.0f;
+      w.goff[env * 3 + 1] = 0.0f;
+      w.goff[env * 3 + 2] = 0.0f;
+    }
+    w.start[env] = t;
+    w.start_off[env] = 0.0f;
+    w.progress[env] = 0;
+    if (write_flags) {
+      w.reset[env] = 0;
+      w.term[env] = 0;
+    }
+  }
+}
+
+// dof_pos / dof_vel of one (env, body) from library rows f0, f1: _local_rotation_to_dof_smpl (motion_lib.py:670-673)
+// and the dof_vel lerp (:604)
+__device__ __forceinline__ void reset_store_dof(const LibDev& L, const ResetTargets& w, int64_t env, int b, int64_t f0,
+                                                int64_t f1, float bl) {
+  const float om = 1.0f - bl;
+  if (w.dof_pos && b >= 1) {
+    const Quat lr = quat_slerp(ld4v(L.lrs + (f0 * J24 + b) * 4), ld4v(L.lrs + (f1 * J24 + b) * 4), bl);
+    const Vec3 em = quat_exp_map(lr);
+    float* d = w.dof_pos + env * w.dof_stride + (int64_t)(b - 1) * 3 * w.dof_estride;
+    d[0] = em.x;
+    d[w.dof_estride] = em.y;
+    d[2 * w.dof_estride] = em.z;
+  }
+  if (w.dof_vel && b < 23) {
+    const Vec3 dv = lerp3(om, bl, ld3(L.dvs + (f0 * 23 + b) * 3), ld3(L.dvs + (f1 * 23 + b) * 3));
+    float* d = w.dof_vel + env * w.dof_stride + (int64_t)b * 3 * w.dof_estride;
+    d[0] = dv.x;
+    d[w.dof_estride] = dv.y;
+    d[2 * w.dof_estride] = dv.z;
+  }
+}
+
+// One (env, body) of a reference-state-init reset: get_motion_state at the new start time (motion_lib.py:549-626)
+// posed with the OLD global offset (:860), then the two scatters above.
+// `write_flags`: also clear reset_buf / terminate_buf (the fused step leaves that to the lane that owns the flags).
 __device__ __forceinline__ void reset_scatter_thread(const LibDev& L, const ResetTargets& w, int64_t env, int b, float t,
                                                      float len, int64_t nf, float mdt, int64_t st, float g0, float g1,
                                                      float g2, bool write_flags, ResetEnvOut& o) {
@@ -833,46 +897,8 @@ __device__ __forceinline__ void reset_scatter_thread(const LibDev& L, const Rese
   const Quat rot = quat_slerp(ld4v(L.grs + (f0 * J24 + b) * 4), ld4v(L.grs + (f1 * J24 + b) * 4), bl);
   const Vec3 vel = lerp3(om, bl, ld3(L.gvs + (f0 * J24 + b) * 3), ld3(L.gvs + (f1 * J24 + b) * 3));
   const Vec3 ang = lerp3(om, bl, ld3(L.gavs + (f0 * J24 + b) * 3), ld3(L.gavs + (f1 * J24 + b) * 3));
-  st3(const_cast<float*>(view_at(w.body.pos, env, b)), pos);
-  st4(const_cast<float*>(view_at(w.body.rot, env, b)), rot);
-  st3(const_cast<float*>(view_at(w.body.vel, env, b)), vel);
-  st3(const_cast<float*>(view_at(w.body.ang_vel, env, b)), ang);
-  if (b == 0 && w.root) {
-    float* r = w.root + env * w.root_stride;
-    st3(r, pos);
-    st4(r + 3, rot);
-    st3(r + 7, vel);
-    st3(r + 10, ang);
-  }
-  if (w.dof_pos && b >= 1) {  // _local_rotation_to_dof_smpl (motion_lib.py:670-673)
-    const Quat lr = quat_slerp(ld4v(L.lrs + (f0 * J24 + b) * 4), ld4v(L.lrs + (f1 * J24 + b) * 4), bl);
-    const Vec3 em = quat_exp_map(lr);
-    float* d = w.dof_pos + env * w.dof_stride + (int64_t)(b - 1) * 3 * w.dof_estride;
-    d[0] = em.x;
-    d[w.dof_estride] = em.y;
-    d[2 * w.dof_estride] = em.z;
-  }
-  if (w.dof_vel && b < 23) {
-    const Vec3 dv = lerp3(om, bl, ld3(L.dvs + (f0 * 23 + b) * 3), ld3(L.dvs + (f1 * 23 + b) * 3));
-    float* d = w.dof_vel + env * w.dof_stride + (int64_t)b * 3 * w.dof_estride;
-    d[0] = dv.x;
-    d[w.dof_estride] = dv.y;
-    d[2 * w.dof_estride] = dv.z;
-  }
-  if (b == 0) {
-    if (w.goff) {
-      w.goff[env * 3 + 0] = 0.0f;
-      w.goff[env * 3 + 1] = 0.0f;
-      w.goff[env * 3 + 2] = 0.0f;
-    }
-    w.start[env] = t;
-    w.start_off[env] = 0.0f;
-    w.progress[env] = 0;
-    if (write_flags) {
-      w.reset[env] = 0;
-      w.term[env] = 0;
-    }
-  }
+  reset_store_body(w, env, b, t, pos, rot, vel, ang, write_flags);
+  reset_store_dof(L, w, env, b, f0, f1, bl);
   o.pos = pos, o.rot = rot, o.vel = vel, o.ang = ang;
   o.t = t, o.len = len, o.mdt = mdt, o.nf = nf, o.st = st;
 }
@@ -1492,13 +1518,17 @@ struct FastSmem {
   float nroot[EPB][5];   // root position and inverse heading of a just-reset env
 };
 
+__device__ __forceinline__ RefBody blend_ref3(const float* f0, const float* f1, float bl, float g0, float g1, float g2, int b);
 __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, float bl, const float* goff, int b) {
+  return blend_ref3(f0, f1, bl, goff[0], goff[1], goff[2], b);
+}
+__device__ __forceinline__ RefBody blend_ref3(const float* f0, const float* f1, float bl, float g0, float g1, float g2, int b) {
   const float om = 1.0f - bl;
   RefBody r;
   r.pos = lerp3(om, bl, ld3(f0 + b * 3), ld3(f1 + b * 3));
-  r.pos.x += goff[0];
-  r.pos.y += goff[1];
-  r.pos.z += goff[2];
+  r.pos.x += g0;
+  r.pos.y += g1;
+  r.pos.z += g2;
   r.rot = quat_slerp(ld4v(f0 + 72 + b * 4), ld4v(f1 + 72 + b * 4), bl);
   r.vel = lerp3(om, bl, ld3(f0 + 168 + b * 3), ld3(f1 + 168 + b * 3));
   r.ang = lerp3(om, bl, ld3(f0 + 240 + b * 3), ld3(f1 + 240 + b * 3));
@@ -1506,49 +1536,108 @@ __device__ __forceinline__ RefBody blend_ref2(const float* f0, const float* f1, 
 }
 
 // The reset of the envs a step flags, inside the step (PhcStepArgs.auto_reset; clean_pufferl/env.py:133-135 ->
-// humanoid_phc.py:665-676).  Called by EVERY thread of a block that has a flagged env, after phase 1 (the frame
-// buffer is dead, the stage may be written): a thread of a flagged env re-poses its body from the motion library
-// (reset_scatter_thread, the arithmetic of phc_reset_envs), body 0 publishes the new root position and heading, and
-// after the block barrier the thread writes its columns of the env's observation row — computed from the new state
-// and the reference body at the new t + dt — into the stage; the caller skips its own phase 2 for these threads.
-// Self-contained and inlined: nothing of it is live outside the branch, so the common path (no env flagged) pays the
-// test only.  (Out of line it was a disaster twice over: with the caller's per-body state passed by reference that
-// state lived in local memory for the whole kernel, 7.8 -> 46 us per 4096-env step; with the kernel parameters
-// passed by reference, 19 us.)
+// humanoid_phc.py:665-676).  Called by EVERY thread of a block that has a flagged env, once per flagged env, after
+// phase 2 (the frame buffer is the stage by now, the threads' own per-body state is dead).  A block with a flagged
+// env is what a single-wave step waits for, and its length is a dependent instruction chain, not bandwidth — so the
+// work of ONE flagged env is spread over the block's three warps by ROLE, lane = body:
+//   warp 0  the env's new state at the start time (get_motion_state, posed with the OLD global offset), the
+//           _set_env_state scatter, the clock; publishes the state in the env's (dead) row of the sim tile and the
+//           root position / inverse heading; after the block barrier: the self-observation columns of the new row
+//   warp 1  the reference body at the new t + dt; after the barrier: the imitation columns (state from the sim tile)
+//   warp 2  dof_pos (slerp of the local rotations + exp-map) and dof_vel of the new state; ref_dof_pos if asked for
+// Every value is computed by the same functions on the same operands as phc_reset_envs computes it: bit-identical.
+// Measured (profiles/r2_step_variants.md, 4096 envs, step with bookkeeping 7.9 us): the env's own 24 threads doing
+// all of it one after the other (first version) 16.3 us whatever the fraction flagged; by role 11.7 us at 1 %
+// flagged, 18.0 us at 46 % (blocks with several flagged envs take them one after the other; first version 17.1).
+// Sharing the tasks of ALL flagged envs of a block out over the warps (state handed over through shared memory
+// instead of registers, one barrier per block): 12.4 / 18.7 us, not kept.  The library rows are L2-prefetched
+// (reset_prefetch) before phase 2, which covers their latency.
+// (Out of line it was a disaster twice over: with the caller's per-body state passed by reference that state lived in
+// local memory for the whole kernel, 7.8 -> 46 us per 4096-env step; with the kernel parameters passed by reference,
+// 19 us.)
+template <int EPB>
+__device__ __forceinline__ void reset_prefetch(const StepParams& p, const FastSmem<EPB>& S, int f, int64_t env) {
+  // warps 0 / 1, one lane each: both library rows of the state at t / of the reference at t + dt as one L2 prefetch
+  // of the packed table; warp 2: the local rotations / dof velocities lane by lane
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float len = S.meta_len[f];
+  const float t = reset_start_time(p.rw, env, len);
+  int64_t f0, f1;
+  float bl;
+  reset_query_frames32(w == 1 ? 1 : 0, p.dt, t, len, S.meta_nf[f], S.meta_mdt[f], S.meta_st[f], f0, f1, bl);
+  if (w < 2) {
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(f1 - f0 + 1) * (uint32_t)(FRAME_FLOATS * 4);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p.L.packed + f0 * FRAME_FLOATS), "r"(bytes) : "memory");
+    }
+  } else if (lane < J24) {
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.L.lrs + (f0 * J24 + lane) * 4) : "memory");
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.L.lrs + (f1 * J24 + lane) * 4) : "memory");
+    if (lane < 23) {
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.L.dvs + (f0 * 23 + lane) * 3) : "memory");
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.L.dvs + (f1 * 23 + lane) * 3) : "memory");
+    }
+  }
+}
+
+__device__ __forceinline__ void put13(float* d, Vec3 pos, Quat rot, Vec3 vel, Vec3 ang) {
+  d[0] = pos.x, d[1] = pos.y, d[2] = pos.z;
+  d[3] = rot.x, d[4] = rot.y, d[5] = rot.z, d[6] = rot.w;
+  d[7] = vel.x, d[8] = vel.y, d[9] = vel.z;
+  d[10] = ang.x, d[11] = ang.y, d[12] = ang.z;
+}
+
 template <int EPB, bool DEF>
-__device__ __forceinline__ void reset_in_step(const StepParams& p, FastSmem<EPB>& S, bool mine, int e, int b, int64_t env) {
-  ResetEnvOut o;
-  RefBody r1;
-  if (mine) {
-    const float len = S.meta_len[e];
-    const float t = reset_start_time(p.rw, env, len);
-    // the reference body at the new t + dt depends on the new start time only: its gathers go out together with the
-    // scatter's (one round trip to the library instead of two on the slow path that decides a single-wave step)
-    r1 = reset_ref_body(p.L, 1, p.dt, t, len, (int64_t)S.meta_nf[e], S.meta_mdt[e], S.meta_st[e], b);
-    reset_scatter_thread(p.L, p.rw, env, b, t, len, (int64_t)S.meta_nf[e], S.meta_mdt[e], S.meta_st[e], S.goff[e][0],
-                         S.goff[e][1], S.goff[e][2], false, o);
-    if (b == 0) {
-      if (p.progress_mirror) p.progress_mirror[env] = 0;
-      const Heading h0 = heading_quat_inv(heading_source(o.rot, p.of.upright));
-      S.nroot[e][0] = o.pos.x, S.nroot[e][1] = o.pos.y, S.nroot[e][2] = o.pos.z;
-      S.nroot[e][3] = h0.z, S.nroot[e][4] = h0.w;
+__device__ __forceinline__ void reset_in_step(const StepParams& p, FastSmem<EPB>& S, int f, int64_t env) {
+  const int w = threadIdx.x >> 5, b = threadIdx.x & 31;
+  const bool act = b < J24;
+  const float len = S.meta_len[f], mdt = S.meta_mdt[f];
+  const int nf = S.meta_nf[f];
+  const int64_t st = S.meta_st[f];
+  const float t = reset_start_time(p.rw, env, len);
+  RefBody own;  // warp 0: the new state; warp 1: the reference at t + dt
+  if (act) {
+    int64_t f0, f1;
+    float bl;
+    reset_query_frames32(w == 1 ? 1 : 0, p.dt, t, len, nf, mdt, st, f0, f1, bl);
+    if (w < 2) {  // warp 0: posed with the old global offset; warp 1: with the zero the reset leaves
+      const bool A = w == 0;
+      own = blend_ref3(p.L.packed + f0 * FRAME_FLOATS, p.L.packed + f1 * FRAME_FLOATS, bl, A ? S.goff[f][0] : 0.0f,
+                       A ? S.goff[f][1] : 0.0f, A ? S.goff[f][2] : 0.0f, b);
+      if (A) {
+        reset_store_body(p.rw, env, b, t, own.pos, own.rot, own.vel, own.ang, false);
+        put13(S.sim + f * ROW13 + b * 13, own.pos, own.rot, own.vel, own.ang);
+        if (b == 0) {
+          if (p.progress_mirror) p.progress_mirror[env] = 0;
+          const Heading h0 = heading_quat_inv(heading_source(own.rot, p.of.upright));
+          S.nroot[f][0] = own.pos.x, S.nroot[f][1] = own.pos.y, S.nroot[f][2] = own.pos.z;
+          S.nroot[f][3] = h0.z, S.nroot[f][4] = h0.w;
+        }
+      }
+    } else {
+      reset_store_dof(p.L, p.rw, env, b, f0, f1, bl);
+      if (p.ref_dof_pos && b >= 1) {  // humanoid_phc.py:1115-1120 on the reset's _compute_task_obs(env_ids)
+        int64_t g0, g1;
+        float gl;
+        reset_query_frames32(1, p.dt, t, len, nf, mdt, st, g0, g1, gl);
+        const Quat lr = quat_slerp(ld4v(p.L.lrs + (g0 * J24 + b) * 4), ld4v(p.L.lrs + (g1 * J24 + b) * 4), gl);
+        st3(p.ref_dof_pos + env * p.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
+      }
     }
   }
   __syncthreads();
-  if (!mine) return;
+  if (!act || w == 2) return;
   const int SW = DEF ? SELF_DIM : p.selfw;
-  const Vec3 root_pos = {S.nroot[e][0], S.nroot[e][1], S.nroot[e][2]};
-  const Heading hi = {S.nroot[e][3], S.nroot[e][4]};
+  const Vec3 root_pos = {S.nroot[f][0], S.nroot[f][1], S.nroot[f][2]};
+  const Heading hi = {S.nroot[f][3], S.nroot[f][4]};
   const HeadingRot hr = heading_rot(hi);
-  float* row = S.frames + e * (SW + TASK_DIM);
-  emit_self_obs<DEF>(row, p.of, b, root_pos, hi, hr, o.pos, o.rot, o.vel, o.ang);
-  emit_task_obs<DEF>(row + SW, b, hi, hr, root_pos, o.pos, o.rot, o.vel, o.ang, r1);
-  if (p.ref_dof_pos && b >= 1) {  // humanoid_phc.py:1115-1120 on the reset's _compute_task_obs(env_ids)
-    int64_t f0, f1;
-    float bl;
-    reset_query_frames(1, p.dt, o.t, o.len, o.nf, o.mdt, o.st, f0, f1, bl);
-    const Quat lr = quat_slerp(ld4v(p.L.lrs + (f0 * J24 + b) * 4), ld4v(p.L.lrs + (f1 * J24 + b) * 4), bl);
-    st3(p.ref_dof_pos + env * p.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
+  float* row = S.frames + f * (SW + TASK_DIM);
+  if (w == 0) {
+    emit_self_obs<DEF>(row, p.of, b, root_pos, hi, hr, own.pos, own.rot, own.vel, own.ang);
+  } else {
+    const float* d = S.sim + f * ROW13 + b * 13;
+    emit_task_obs<DEF>(row + SW, b, hi, hr, root_pos, Vec3{d[0], d[1], d[2]}, Quat{d[3], d[4], d[5], d[6]},
+                       Vec3{d[7], d[8], d[9]}, Vec3{d[10], d[11], d[12]}, own);
   }
 }
 
@@ -1809,6 +1898,7 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const __grid_
   // Every thread works out which of the block's envs this step flags (the test of the reduction warp below, from
   // the same shared-memory values); a block without one goes straight on.
   bool my_rst = false;
+  int rst_mask = 0;  // bit i: env i of the block is reset inside this launch
   if constexpr (RESET) {
     if (p.reset_on) {
       if (p.use_mean) {  // eval mode: the mean needs ATen's row sum — one lane per env, then a block barrier
@@ -1825,15 +1915,17 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const __grid_
         }
         __syncthreads();
       }
-      int any = 0;
 #pragma unroll
       for (int i = 0; i < EPB; ++i) {
         int r = 0;
         if (i < nvalid) r = p.use_mean ? S.rst[i] : ((S.pass[i] || (p.early && S.fallen[i] && S.prog[i] > 1)) ? 1 : 0);
-        any |= r;
+        rst_mask |= r << i;
         if (i == e) my_rst = valid && r;
       }
-      if (any) reset_in_step<EPB, DEF>(p, S, my_rst, e, b, env0 + e);  // writes the stage rows of the flagged envs
+      // the library rows the reset below will read: into L2 now, phase 2 covers their latency
+#pragma unroll
+      for (int i = 0; i < EPB; ++i)
+        if (rst_mask >> i & 1) reset_prefetch<EPB>(p, S, i, env0 + i);
     }
   }
 
@@ -1847,6 +1939,13 @@ __global__ void __launch_bounds__(EPB* J24, MINB) step_fast_kernel(const __grid_
     float* row = S.frames + e * RW;
     emit_self_obs<DEF>(row, p.of, b, root_pos, hi, hr, pos, rot, vel, ang);           // common.py:23-103
     emit_task_obs<DEF>(row + SW, b, hi, hr, root_pos, pos, rot, vel, ang, r1);        // common.py:106-176
+  }
+  if constexpr (RESET) {
+    if (rst_mask) {  // the rows of the flagged envs, from their new state (one env at a time, the whole block on it)
+#pragma unroll 1
+      for (int i = 0; i < EPB; ++i)
+        if (rst_mask >> i & 1) reset_in_step<EPB, DEF>(p, S, i, env0 + i);
+    }
   }
   fence_proxy_async();  // stage writes -> visible to the bulk-store engine
   PHC_STAMP(5);

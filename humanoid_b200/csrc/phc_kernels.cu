@@ -2271,7 +2271,12 @@ static_assert(sizeof(PersistStage<3>) % 16 == 0 && sizeof(PersistStage<4>) % 16 
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"r"(PS_CONSUMERS) : "memory"); }
 
-template <int SLOTS, int BLOCKS_PER_SM>
+// MOM: the RunningNorm partials of the rows a block writes (obs_moments) stay in REGISTERS across the block's tiles —
+// consumer thread i owns columns i, i + 96, ..: ten fp64 sums and ten sums of squares — and reach the accumulator
+// buckets once, when the block runs out of tiles: 1868 adds in L2 per BLOCK (592 blocks) instead of per TILE.  In
+// K6-fast the same partials cost 1868 adds per four envs, and those adds — 0.6 per ns for the whole chip whatever their
+// width or issuer (profiles/r2_moments_modes_experiment.md) — are what its moments epilogue costs.
+template <int SLOTS, int BLOCKS_PER_SM, bool MOM = false>
 __global__ void __launch_bounds__(PS_THREADS, BLOCKS_PER_SM) step_persist_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PersistSmem<SLOTS>& M = *reinterpret_cast<PersistSmem<SLOTS>*>(smem_raw);
@@ -2282,7 +2287,7 @@ __global__ void __launch_bounds__(PS_THREADS, BLOCKS_PER_SM) step_persist_kernel
 #pragma unroll
     for (int s = 0; s < PS_STAGES; ++s) {
       mbar_init(&M.full[s], 1);
-      mbar_init(&M.empty[s], 1);
+      mbar_init(&M.empty[s], MOM ? PS_CONSUMERS / 32 : 1);  // MOM: every consumer warp reads the finished stage
     }
   }
   __syncthreads();
@@ -2475,6 +2480,12 @@ __global__ void __launch_bounds__(PS_THREADS, BLOCKS_PER_SM) step_persist_kernel
 
   // =========================== consumer warps ===========================
   const int e = tid / J24, b = tid % J24;
+  constexpr int MOM_COLS = (STAGE_FLOATS + PS_CONSUMERS - 1) / PS_CONSUMERS;  // 10 columns per consumer thread
+  double ms1[MOM ? MOM_COLS : 1], ms2[MOM ? MOM_COLS : 1];
+  if constexpr (MOM) {
+#pragma unroll
+    for (int k = 0; k < MOM_COLS; ++k) ms1[k] = 0.0, ms2[k] = 0.0;
+  }
   for (int it = 0;; ++it) {
     const int s = it % PS_STAGES;
     Stage& S = M.st[s];
@@ -2540,6 +2551,24 @@ __global__ void __launch_bounds__(PS_THREADS, BLOCKS_PER_SM) step_persist_kernel
       for (int i = tid; i < nvalid * (STAGE_FLOATS / 2); i += PS_CONSUMERS) dst[i] = src[i];
       consumer_sync();
     }
+    if constexpr (MOM) {  // x * x is exact in fp64 for an fp32 x: the fused form equals mul + add bit for bit
+#pragma unroll
+      for (int k = 0; k < MOM_COLS; ++k) {
+        const int c = tid + k * PS_CONSUMERS;
+        if (c < STAGE_FLOATS) {
+#pragma unroll
+          for (int ee = 0; ee < PS_EPB; ++ee) {
+            if (ee < nvalid) {
+              const double x = (double)S.frames[ee * STAGE_FLOATS + c];
+              ms1[k] += x;
+              ms2[k] = __fma_rn(x, x, ms2[k]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (tid >= 32 && (tid & 31) == 0) mbar_arrive(&M.empty[s]);  // warps 1-2 are done with the stage; warp 0 below
+    }
     // ---- reductions and scalar outputs (consumer warp 0) while warps 1-2 start the next tile ----------
     if (tid < 32) {
       const int le = tid >> 2, k = tid & 3;
@@ -2590,6 +2619,17 @@ __global__ void __launch_bounds__(PS_THREADS, BLOCKS_PER_SM) step_persist_kernel
       if (tid == 0) {  // the stage goes back to the producer once the store has read it and the partials are consumed
         if (bulk_ok) bulk_wait_read();
         mbar_arrive(&M.empty[s]);
+      }
+    }
+  }
+  if constexpr (MOM) {
+    double* mom = p.moments + (int64_t)(blockIdx.x % p.moment_buckets) * 2 * STAGE_FLOATS;
+#pragma unroll
+    for (int k = 0; k < MOM_COLS; ++k) {
+      const int c = tid + k * PS_CONSUMERS;
+      if (c < STAGE_FLOATS) {
+        atomicAdd(mom + c, ms1[k]);
+        atomicAdd(mom + STAGE_FLOATS + c, ms2[k]);
       }
     }
   }
@@ -3415,6 +3455,7 @@ static int g_persist = -1;       // PHC_OPT_STEP_PERSIST / env PHC_STEP_PERSIST:
                                  // 3 always and the 4-slot / 4-blocks-per-SM instantiation
 static int g_persist_pdl = 1;
 static int64_t g_persist_min = 16384;
+static int64_t g_persist_min_moments = 8192;  // with obs_moments: K6-fast pays 1868 L2 adds per four envs
 
 template <typename Kern>
 static int launch_step(Kern kern, size_t smem, int epb, const StepParams& p, cudaStream_t stream, bool* attr_set,
@@ -3982,24 +4023,29 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
   static int first_wave[64] = {};
   // several waves of blocks (BASELINE config 3): the persistent warp-specialised kernel.  It carries the plain step
   // (+ power reward, flag / reward copies); the optional epilogues stay with K6-fast.
-  static bool attr_persist[2][64] = {};
+  static bool attr_persist[3][64] = {};
   static int sm_count[64] = {};
-  const bool persist = fast && def && g_persist != 0 && (g_persist >= 2 || p.n >= g_persist_min) && !p.obs_norm &&
-                       !p.ep_returns && !p.reset_on && !p.moments && !p.ref_dof_pos && !p.trace && lib->tile_counters &&
+  const bool persist = fast && def && g_persist != 0 &&
+                       (g_persist >= 2 || p.n >= (p.moments ? g_persist_min_moments : g_persist_min)) && !p.obs_norm &&
+                       !p.ep_returns && !p.reset_on && !p.ref_dof_pos && !p.trace && lib->tile_counters &&
                        !(args->flags & PHC_STEP_MAPPED_HOST_IO);
   if (persist) {
     if (!sm_count[dev]) PHC_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-    const bool four = g_persist == 3;  // the 4-slot / 4-blocks-per-SM instantiation (tests, comparisons)
-    auto kern = four ? step_persist_kernel<4, 4> : step_persist_kernel<3, 5>;
+    // instantiations: 3 frame slots / 5 blocks per SM (default), 4 slots / 4 blocks (tests, comparisons), and with the
+    // moments in registers 3 slots / 4 blocks (twenty fp64 accumulators per consumer thread: 128 registers)
+    const bool mom = p.moments != nullptr;
+    const bool four = !mom && g_persist == 3;
+    const int which = mom ? 2 : four ? 1 : 0;
+    auto kern = mom ? step_persist_kernel<3, 4, true> : four ? step_persist_kernel<4, 4> : step_persist_kernel<3, 5>;
     const size_t smem = four ? sizeof(PersistSmem<4>) : sizeof(PersistSmem<3>);
-    if (!attr_persist[four][dev]) {
+    if (!attr_persist[which][dev]) {
       PHC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_persist[four][dev] = true;
+      attr_persist[which][dev] = true;
     }
     if (lib->unspeculated_steps > 0) --lib->unspeculated_steps;  // nothing is read before the dependency wait here
     p.tile_counter = lib->tile_counters + 2 * (lib->tile_seq.fetch_add(1u, std::memory_order_relaxed) % TILE_SLOTS);
     const int64_t tiles = (p.n + PS_EPB - 1) / PS_EPB;
-    const int64_t resident = (int64_t)sm_count[dev] * (four ? 4 : 5);
+    const int64_t resident = (int64_t)sm_count[dev] * (four || mom ? 4 : 5);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(tiles < resident ? tiles : resident));
     cfg.blockDim = dim3(PS_THREADS);

@@ -710,6 +710,46 @@ def test_moments_epilogue_bulk_reductions_equal_column_moments(N, bulk):
     assert float(((got - want).abs() / scale).max()) < 1e-12
 
 
+@pytest.mark.parametrize("N,regime", [(8192, "aligned30"), (16387, "aligned30"), (9001, "mixed_fps_unaligned"), (5, "aligned30"),
+                                      (2371, "aligned30")])  # fmt: skip
+def test_persistent_kernel_keeps_the_moments_in_registers(N, regime):
+    """With obs_moments the persistent kernel keeps each block's RunningNorm partials in registers across its tiles
+    (ten fp64 column sums + ten sums of squares per consumer thread) and adds them to the accumulator buckets once at
+    the end.  Every other output bit-identical to the plain step; partials equal phc_obs_moments of the rows to 1e-12
+    relative; three steps deep (the partials of consecutive launches add up), ragged N, far rows."""
+    from humanoid_b200 import HumanoidPHC, RunningNorm, _cabi
+
+    kw = dict(max_progress=40)
+    if regime == "mixed_fps_unaligned":
+        kw.update(ids="random", aligned=False, fps_choices=(30, 60, 120), min_frames=60, max_frames=400)
+    lib_data, clock, state = _gpu_case(N, 300, 91, **kw)
+    lib = MotionLib(lib_data, device=DEV)
+    capi = _cabi.load()
+    rn = RunningNorm(934, device=DEV)
+    plain = HumanoidPHC(lib, N, device=DEV)
+    env = HumanoidPHC(lib, N, device=DEV, obs_moments=True)
+    for e in (plain, env):
+        e.set_sim_state(state)
+        e.set_clock(clock)
+    want = torch.zeros(2 * 934, dtype=torch.float64, device=DEV)
+    try:
+        for _ in range(3):
+            capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 0)
+            plain.step()
+            capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 2)  # the persistent kernel whatever N
+            env.step()
+            rn.moments(plain.obs_buf, want)
+            for k in ("obs_buf", "rew_buf", "reward_raw", "reset_buf", "_terminate_buf", "progress_buf"):
+                assert torch.equal(getattr(env, k), getattr(plain, k)), k
+    finally:
+        capi.phc_set_option(_cabi.OPT_STEP_PERSIST, 1)
+    got, rows = env.take_obs_moments()
+    assert rows == 3 * N
+    scale = want.abs().clamp_min(1.0)
+    assert float(((got - want).abs() / scale).max()) < 1e-12
+    assert float(env._obs_moment_buckets.abs().max()) == 0.0
+
+
 def test_running_norm_vs_reference_fixture(golden):
     from humanoid_b200 import RunningNorm
 

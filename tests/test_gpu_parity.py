@@ -1224,11 +1224,11 @@ def test_amp_init_with_slot0_in_the_same_launch_equals_the_two_launches_bitwise(
 
 
 @pytest.mark.parametrize("groups", [2, 1], ids=["two_groups", "one_group"])
-@pytest.mark.parametrize("N,T", [(1027, 10), (64, 16), (515, 2), (2050, 3), (9, 5)])
+@pytest.mark.parametrize("N,T", [(1027, 10), (64, 16), (515, 2), (2050, 3), (9, 5), (9473, 10), (12001, 3)])
 def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T, groups):
     """T > 1 dispatches to the pipelined TMA kernels (two query groups per block by default, one as the cross-check);
-    the generic kernel is the same math.  Also a regression test: the clock must be advanced only after every query
-    lane has read it."""
+    the generic kernel is the same math, three steps deep, single-wave and multi-wave grids.  Also a regression test:
+    the clock must be advanced only after every query lane has read it."""
     from humanoid_b200 import HumanoidPHC, _cabi
 
     lib_data, clock, state = _gpu_case(N, 64, 210, max_frames=60, max_progress=40)
@@ -1244,18 +1244,20 @@ def test_multi_T_kernel_equals_generic_kernel_bitwise(N, T, groups):
             env.set_clock(clock)
             env.dof_force_tensor.normal_(generator=torch.Generator(device=DEV).manual_seed(1))
             env._dof_vel.copy_(torch.randn(N, 69, generator=torch.Generator(device=DEV).manual_seed(2), device=DEV))
-            for _ in range(2):
+            snaps = []
+            for _ in range(3):
                 env.step()
+                snaps.append([getattr(env, k).clone() for k in ("obs_buf", "rew_buf", "reward_raw", "reset_buf",
+                                                                "_terminate_buf", "progress_buf")])
             torch.cuda.synchronize()
-            outs.append(env)
+            outs.append((env, snaps))
     finally:
         capi.phc_set_option(_cabi.OPT_FORCE_GENERIC_STEP, 0)
         capi.phc_set_option(_cabi.OPT_MULTI_GROUPS, 0)
-    g, f = outs
-    assert torch.equal(f.obs_buf, g.obs_buf)
-    assert torch.equal(f.rew_buf, g.rew_buf) and torch.equal(f.reward_raw, g.reward_raw)
-    assert torch.equal(f.reset_buf, g.reset_buf) and torch.equal(f._terminate_buf, g._terminate_buf)
-    assert torch.equal(f.progress_buf, g.progress_buf)
+    (g, gs), (f, fs) = outs
+    for k, (a, b) in enumerate(zip(fs, gs)):
+        for x, y, nm in zip(a, b, ("obs", "rew", "reward_raw", "reset", "terminate", "progress")):
+            assert torch.equal(x, y), f"step {k}: {nm}"
     torch.testing.assert_close(f.obs_moments, g.obs_moments, rtol=1e-12, atol=1e-9)
 
 

@@ -73,13 +73,13 @@ struct PhcHostStep {
   // the schedule (output path, chunk count) of pinned callers is tuned over the first calls: every candidate is timed
   // kTuneReps times, interleaved, and the fastest mean stays.  num_chunks > 0 at create and PHC_HOST_PATH narrow the
   // candidates (down to one: nothing to tune).
-  struct Cand { int path, chunks; double t; int n; };
+  struct Cand { int path, chunks; double t; int n; };  // t: fastest timed call so far
   Cand cand[8] = {};
   int ncand = 0;
   int chosen = -1;  // index into cand once decided
   int calls = 0;
 };
-constexpr int kTuneWarm = 2, kTuneReps = 3;
+constexpr int kTuneWarm = 2, kTuneReps = 4;
 
 // After the first enqueue an early return must not leave kernels writing into the caller's (mapped) buffers or
 // into the staging buffers the next call reuses: every error path drains the three streams first.
@@ -455,22 +455,25 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
   const int rc = run(c->cand[which]);
   const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (rc == PHC_OK && k >= kTuneWarm) {
-    // the first timed call of a candidate warms its own launch configuration: not counted
+    // the first timed call of a candidate warms its own launch configuration: not counted.  A candidate's figure is
+    // its FASTEST call (what the schedule can do; a mean over three calls carries the host's jitter), and the first
+    // candidate — three chunks, direct: the best schedule on most hosts — is only given up for one that is 2 % faster.
     if (k - kTuneWarm >= c->ncand) {
-      c->cand[which].t += dt;
+      c->cand[which].t = c->cand[which].n == 0 || dt < c->cand[which].t ? dt : c->cand[which].t;
       c->cand[which].n += 1;
     }
     bool done = true;
     for (int i = 0; i < c->ncand; ++i) done = done && c->cand[i].n >= kTuneReps;
     if (done) {
       int best = 0;
+      double best_t = c->cand[0].t * 0.98;
       for (int i = 1; i < c->ncand; ++i)
-        if (c->cand[i].t / c->cand[i].n < c->cand[best].t / c->cand[best].n) best = i;
+        if (c->cand[i].t < best_t) best = i, best_t = c->cand[i].t;
       c->chosen = best;
       if (getenv("PHC_HOST_TRACE"))
         for (int i = 0; i < c->ncand; ++i)
           fprintf(stderr, "[phc_host tune] %s, %d chunks: %.1f us%s\n", c->cand[i].path == 1 ? "direct" : "staged",
-                  c->cand[i].chunks, c->cand[i].t / c->cand[i].n * 1e6, i == best ? "  <- kept" : "");
+                  c->cand[i].chunks, c->cand[i].t * 1e6, i == best ? "  <- kept" : "");
     }
   }
   return rc;

@@ -453,8 +453,8 @@ PHC_API void phc_host_step_destroy(PhcHostStep* ctx);
  * flags into the mapped host buffers), 2 = staged (device buffers + copy-engine D2H; always the case for pageable
  * callers), 0 = not decided yet.  phc_host_step_chunks: the chunk count in use (0 = not decided yet).  With
  * num_chunks = 0 at create the context tunes (path, chunk count) over its first phc_host_step_tuning_calls() calls —
- * every candidate timed three times, interleaved, under whatever load the other GPUs of the box put on the host at
- * that moment — and keeps the fastest; num_chunks > 0 fixes the chunk count and PHC_HOST_PATH=direct|staged the path. */
+ * every candidate timed four times, interleaved, under whatever load the other GPUs of the box put on the host at
+ * that moment — and keeps the fastest (three chunks on the direct path unless another schedule is 2 % faster); num_chunks > 0 fixes the chunk count and PHC_HOST_PATH=direct|staged the path. */
 PHC_API int phc_host_step_path(const PhcHostStep* ctx);
 PHC_API int phc_host_step_chunks(const PhcHostStep* ctx);
 PHC_API int phc_host_step_tuning_calls(const PhcHostStep* ctx);

@@ -806,7 +806,7 @@ def test_host_pipeline_matches_device_path(mode, monkeypatch):
                                                              "rew", "raw", "reset", "term")])  # fmt: skip
     # auto / tuned: every candidate schedule is timed over the first calls, then one is kept
     calls = capi.phc_host_step_tuning_calls(ctx) + 2 if mode in ("pinned_auto", "pinned_tuned") else 1
-    assert calls == {"pinned_auto": 2 + 2 * 4 + 2, "pinned_tuned": 2 + 6 * 4 + 2}.get(mode, 1)
+    assert calls == {"pinned_auto": 2 + 2 * 5 + 2, "pinned_tuned": 2 + 6 * 5 + 2}.get(mode, 1)
     for i in range(calls):
         h["prog"].copy_(clock.progress_buf.cpu())
         h["obs"].fill_(float("nan"))

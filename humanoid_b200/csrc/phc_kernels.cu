@@ -1589,6 +1589,7 @@ __device__ __forceinline__ void put13(float* d, Vec3 pos, Quat rot, Vec3 vel, Ve
 
 template <int EPB, bool DEF>
 __device__ __forceinline__ void reset_in_step(const StepParams& p, FastSmem<EPB>& S, int f, int64_t env) {
+  static_assert(EPB * J24 == 96, "three warps, one role each");
   const int w = threadIdx.x >> 5, b = threadIdx.x & 31;
   const bool act = b < J24;
   const float len = S.meta_len[f], mdt = S.meta_mdt[f];

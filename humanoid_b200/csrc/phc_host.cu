@@ -362,6 +362,14 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
   make_bounds(chunks < 1 ? 1 : chunks);
 
   size_t coff = 0, ooff = 0;
+  static const bool strace_on = getenv("PHC_HOST_TRACE") != nullptr;
+  static int strace_calls = 0;
+  const bool strace = strace_on && ++strace_calls == 20;
+  cudaEvent_t sev0 = nullptr, sevh[16], sevk[16], sevd[16];
+  if (strace) {
+    cudaEventCreate(&sev0);
+    cudaEventRecord(sev0, c->streams[0]);
+  }
   for (int ci = 0; ci < nchunks; ++ci) {
     const int64_t lo = bounds[ci], m = bounds[ci + 1] - bounds[ci];
     if (m <= 0) continue;
@@ -410,17 +418,40 @@ int phc_host_step(PhcHostStep* c, const PhcHostStepArgs* a, int64_t n) {
     k.reset_buf = dout + L.reset;
     k.terminate_buf = dout + L.term;
     k.obs_moments = nullptr;
+    if (strace && ci < 16) {
+      cudaEventCreate(&sevh[ci]);
+      cudaEventRecord(sevh[ci], s);
+    }
     int rc = phc_step_fused(c->lib, &k, m, s);
     if (rc) return host_fail(c, rc, cudaSuccess);
+    if (strace && ci < 16) {
+      cudaEventCreate(&sevk[ci]);
+      cudaEventRecord(sevk[ci], s);
+    }
     // the advanced progress rides back with the scalar outputs
     HOST_CUDA(c, cudaMemcpyAsync(dout + L.oprog, dc + L.prog, (size_t)m * 2, cudaMemcpyDeviceToDevice, s));
     HOST_CUDA(c, cudaMemcpyAsync(a->obs_buf + lo * c->obs_dim, c->d_obs + lo * c->obs_dim,
                                  (size_t)m * c->obs_dim * sizeof(float), D2H, s));
     HOST_CUDA(c, cudaMemcpyAsync(c->h_out + ooff, dout, L.out_bytes, D2H, s));
+    if (strace && ci < 16) {
+      cudaEventCreate(&sevd[ci]);
+      cudaEventRecord(sevd[ci], s);
+    }
     coff += L.clock_bytes;
     ooff += L.out_bytes;
   }
   for (int i = 0; i < kStreams; ++i) HOST_CUDA(c, cudaStreamSynchronize(c->streams[i]));
+  if (strace) {
+    fprintf(stderr, "[phc_host trace] staged, %d chunks\n", nchunks);
+    for (int i = 0; i < nchunks && i < 16; ++i) {
+      float a_ms = 0, b_ms = 0, d_ms = 0;
+      cudaEventElapsedTime(&a_ms, sev0, sevh[i]);
+      cudaEventElapsedTime(&b_ms, sev0, sevk[i]);
+      cudaEventElapsedTime(&d_ms, sev0, sevd[i]);
+      fprintf(stderr, "  chunk %d (%lld envs): H2D done %.1f us, kernel done %.1f us, D2H done %.1f us\n", i,
+              (long long)(bounds[i + 1] - bounds[i]), a_ms * 1e3, b_ms * 1e3, d_ms * 1e3);
+    }
+  }
   // unpack the scalar outputs
   ooff = 0;
   for (int ci = 0; ci < nchunks; ++ci) {

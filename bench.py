@@ -574,7 +574,7 @@ def measure_e2e(ctx, ring, K):
     torch.cuda.synchronize()
     e2e_ok = bool(torch.equal(e0.obs_buf.cpu(), h_obs) and torch.equal(e0.rew_buf.cpu(), h_rew))
     runs = []
-    for _ in range(3):  # median of three timed loops of Ke calls (each call returns with the outputs in host memory)
+    for _ in range(5):  # median of five timed loops of Ke calls (each call returns with the outputs in host memory)
         ctx.barrier()
         t0 = time.perf_counter()
         for i in range(Ke):
@@ -627,7 +627,7 @@ def measure_e2e(ctx, ring, K):
     world = ctx.world
     return {
         "value": N * world * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-        "steps": Ke, "timing_repeats": 3, "chunks": chunks, "chunks_requested": args.e2e_chunks or "auto", "matches_device_path": e2e_ok,
+        "steps": Ke, "timing_repeats": 5, "chunks": chunks, "chunks_requested": args.e2e_chunks or "auto", "matches_device_path": e2e_ok,
         "us_per_step": e2e_us, "output_path": path,
         "floor": {
             "what": f"all {world} rank(s) at once: pinned H2D of {h2d} B and D2H of {d2h} B per rank on the copy engines, "

@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphc_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NUM_BODIES = 24
 SELF_OBS_DIM = 358
 TASK_OBS_DIM = 576
@@ -35,6 +35,8 @@ OPT_STEP_PERSIST = 7
 
 STATE_INIT_START = 0
 STATE_INIT_RANDOM = 1
+STATE_INIT_DEFAULT = 2
+STATE_INIT_HYBRID = 3
 
 OBS_LOCAL_ROOT = 1
 OBS_ROOT_HEIGHT = 2
@@ -128,6 +130,12 @@ class PhcResetArgs(C.Structure):
         ("obs_flags", C.c_uint32),
         ("ref_dof_pos", C.c_void_p),
         ("ref_dof_pos_stride", C.c_int64),
+        ("initial_root_states", C.c_void_p),
+        ("initial_root_stride", C.c_int64),
+        ("initial_dof_pos", C.c_void_p),
+        ("initial_dof_vel", C.c_void_p),
+        ("initial_dof_stride", C.c_int64),
+        ("default_mask", C.c_void_p),
     ]
 
 

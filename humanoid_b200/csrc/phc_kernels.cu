@@ -733,6 +733,13 @@ struct ResetTargets {
   float* goff;
   const float* phase;
   int state_init, flag_test;
+  // StateInit.Default / Hybrid (humanoid_phc.py:688-692, :733-745)
+  const float* init_root;
+  int64_t init_root_stride;
+  const float* init_dof_pos;
+  const float* init_dof_vel;
+  int64_t init_dof_stride;
+  const uint8_t* default_mask;
 };
 
 // self-observation variant (compute_humanoid_observations_smpl_max flags, humanoid_phc.py:963-998)
@@ -775,6 +782,9 @@ struct ResetEnvOut {  // what the scatter leaves in registers for the observatio
   Quat rot;
   float t, len, mdt;
   int64_t nf, st;
+  // the clock the env's reference bodies are queried with afterwards: (progress + q) dt + t + soff, posed with g.
+  // Reference-state init leaves soff = 0 and g = 0; a default-init env keeps its start time, offset and global offset.
+  float soff, g0, g1, g2;
 };
 
 constexpr int K7_EPB = 8;
@@ -782,8 +792,8 @@ constexpr int K7_EPB = 8;
 // the reference body b of a just-reset env at (progress + q) dt + start + offset with progress = 0, offset = 0
 // (humanoid_phc.py:1063-1067), blended like blend_ref; the global offset is the zero the reset leaves
 __device__ __forceinline__ void reset_query_frames(int q, float dt, float t, float len, int64_t nf, float mdt, int64_t st,
-                                                   int64_t& f0, int64_t& f1, float& bl) {
-  const float tq = (float)(int16_t)q * dt + t + 0.0f;
+                                                   int64_t& f0, int64_t& f1, float& bl, float soff = 0.0f) {
+  const float tq = (float)(int16_t)q * dt + t + soff;
   int64_t i0, i1;
   calc_frame_blend(tq, len, nf, mdt, i0, i1, bl);
   f0 = i0 + st, f1 = i1 + st;
@@ -797,14 +807,15 @@ __device__ __forceinline__ void reset_query_frames32(int q, float dt, float t, f
   f0 = st + i0, f1 = st + i1;
 }
 __device__ __forceinline__ RefBody reset_ref_body(const LibDev& L, int q, float dt, float t, float len, int64_t nf, float mdt,
-                                                  int64_t st, int b) {
+                                                  int64_t st, int b, float soff = 0.0f, float g0 = 0.0f, float g1 = 0.0f,
+                                                  float g2 = 0.0f) {
   int64_t f0, f1;
   float bl;
-  reset_query_frames(q, dt, t, len, nf, mdt, st, f0, f1, bl);
+  reset_query_frames(q, dt, t, len, nf, mdt, st, f0, f1, bl, soff);
   const float om = 1.0f - bl;
   RefBody r;
   r.pos = lerp3(om, bl, ld3(L.gts + (f0 * J24 + b) * 3), ld3(L.gts + (f1 * J24 + b) * 3));
-  r.pos.x += 0.0f, r.pos.y += 0.0f, r.pos.z += 0.0f;
+  r.pos.x += g0, r.pos.y += g1, r.pos.z += g2;
   r.rot = quat_slerp(ld4v(L.grs + (f0 * J24 + b) * 4), ld4v(L.grs + (f1 * J24 + b) * 4), bl);
   r.vel = lerp3(om, bl, ld3(L.gvs + (f0 * J24 + b) * 3), ld3(L.gvs + (f1 * J24 + b) * 3));
   r.ang = lerp3(om, bl, ld3(L.gavs + (f0 * J24 + b) * 3), ld3(L.gavs + (f1 * J24 + b) * 3));
@@ -814,7 +825,7 @@ __device__ __forceinline__ RefBody reset_ref_body(const LibDev& L, int q, float 
 // MotionLibBase.sample_time_interval (motion_lib.py:526-535) with the caller's uniform number:
 //   ((phase * motion_len) / curr_fps).long() * curr_fps with curr_fps = 1/30; 0 for StateInit.Start / flag_test (:856)
 __device__ __forceinline__ float reset_start_time(const ResetTargets& w, int64_t env, float len) {
-  if (w.state_init == PHC_STATE_INIT_RANDOM && !w.flag_test) {
+  if ((w.state_init == PHC_STATE_INIT_RANDOM || w.state_init == PHC_STATE_INIT_HYBRID) && !w.flag_test) {
     const float c30 = (float)(1.0 / 30.0);
     const long long k = (long long)((w.phase[env] * len) / c30);
     return (float)k * c30;
@@ -901,6 +912,42 @@ __device__ __forceinline__ void reset_scatter_thread(const LibDev& L, const Rese
   reset_store_dof(L, w, env, b, f0, f1, bl);
   o.pos = pos, o.rot = rot, o.vel = vel, o.ang = ang;
   o.t = t, o.len = len, o.mdt = mdt, o.nf = nf, o.st = st;
+  o.soff = 0.0f, o.g0 = 0.0f, o.g1 = 0.0f, o.g2 = 0.0f;
+}
+
+// One (env, body) of a default-init reset (_reset_default, humanoid_phc.py:688-692, then _reset_env_tensors :775-778):
+// root / dof state from the initial buffers; the rigid-body tensors, start time, offset and global offset stay; the
+// body's CURRENT state goes to the registers the observation of the same launch is computed from.
+__device__ __forceinline__ void reset_default_thread(const LibDev& L, const ResetTargets& w, int64_t env, int b, int64_t id,
+                                                     float g0, float g1, float g2, ResetEnvOut& o) {
+  o.pos = ld3(view_at(w.body.pos, env, b));
+  o.rot = ld4(view_at(w.body.rot, env, b));
+  o.vel = ld3(view_at(w.body.vel, env, b));
+  o.ang = ld3(view_at(w.body.ang_vel, env, b));
+  if (b == 0 && w.root) {
+    const float* src = w.init_root + env * w.init_root_stride;
+    float* r = w.root + env * w.root_stride;
+#pragma unroll
+    for (int k = 0; k < 13; ++k) r[k] = src[k];
+  }
+  if (w.dof_pos && b >= 1) {
+    const float* src = w.init_dof_pos + env * w.init_dof_stride + (b - 1) * 3;
+    float* d = w.dof_pos + env * w.dof_stride + (int64_t)(b - 1) * 3 * w.dof_estride;
+    d[0] = src[0], d[w.dof_estride] = src[1], d[2 * w.dof_estride] = src[2];
+  }
+  if (w.dof_vel && b < 23) {
+    const float* src = w.init_dof_vel + env * w.init_dof_stride + b * 3;
+    float* d = w.dof_vel + env * w.dof_stride + (int64_t)b * 3 * w.dof_estride;
+    d[0] = src[0], d[w.dof_estride] = src[1], d[2 * w.dof_estride] = src[2];
+  }
+  o.t = w.start[env], o.soff = w.start_off[env];  // the motion clock is not restarted
+  o.len = L.len[id], o.mdt = L.mdt[id], o.nf = L.nf[id], o.st = L.starts[id];
+  o.g0 = g0, o.g1 = g1, o.g2 = g2;
+  if (b == 0) {
+    w.progress[env] = 0;
+    w.reset[env] = 0;
+    w.term[env] = 0;
+  }
 }
 
 // `act`: this thread's env is in range and selected by the mask (read by the caller, once, before anything is
@@ -913,6 +960,10 @@ __device__ __forceinline__ void reset_scatter_body(const ResetParams& p, const b
   __syncthreads();
   if (!act) return;
   const int64_t id = p.ids[env];
+  if (p.w.state_init == PHC_STATE_INIT_DEFAULT || (p.w.state_init == PHC_STATE_INIT_HYBRID && p.w.default_mask[env])) {
+    reset_default_thread(p.L, p.w, env, b, id, s_goff[e][0], s_goff[e][1], s_goff[e][2], o);
+    return;
+  }
   const float len = p.L.len[id];
   const float t = reset_start_time(p.w, env, len);
   reset_scatter_thread(p.L, p.w, env, b, t, len, p.L.nf[id], p.L.mdt[id], p.L.starts[id], s_goff[e][0], s_goff[e][1],
@@ -1450,14 +1501,14 @@ __global__ void __launch_bounds__(K7_EPB* J24) reset_obs_kernel(const ResetParam
   if (p.ref_dof_pos && b >= 1) {  // self.ref_dof_pos[env_ids] = dof_pos of the query at t + dt (humanoid_phc.py:1115-1120)
     int64_t f0, f1;
     float bl;
-    reset_query_frames(1, p.dt, o.t, o.len, o.nf, o.mdt, o.st, f0, f1, bl);
+    reset_query_frames(1, p.dt, o.t, o.len, o.nf, o.mdt, o.st, f0, f1, bl, o.soff);
     const Quat lr = quat_slerp(ld4v(p.L.lrs + (f0 * J24 + b) * 4), ld4v(p.L.lrs + (f1 * J24 + b) * 4), bl);
     st3(p.ref_dof_pos + env * p.ref_dof_pos_stride + (b - 1) * 3, quat_exp_map(lr));
   }
   for (int q = 1; q <= p.T; ++q) {
     // loading the t + dt frames together with the scatter's (before its stores) was measured: 10 more registers,
     // 3 instead of 4 blocks per SM — 0.6 us faster per loop step at 4 % flagged, 2.5 us slower at 31 %; not kept
-    const RefBody r = reset_ref_body(p.L, q, p.dt, o.t, o.len, o.nf, o.mdt, o.st, b);
+    const RefBody r = reset_ref_body(p.L, q, p.dt, o.t, o.len, o.nf, o.mdt, o.st, b, o.soff, o.g0, o.g1, o.g2);
     emit_task_obs<false>(row + SW + (int64_t)TASK_DIM * (q - 1), b, hi, hr, root_pos, o.pos, o.rot, o.vel, o.ang, r);
   }
   if (mom || p.norm.out) {  // the thread's own stores above are visible to it
@@ -3717,8 +3768,17 @@ static int reset_fill(const PhcLib* lib, const PhcResetArgs* a, int64_t n, Reset
   if (!a->progress_buf || !a->reset_buf || !a->terminate_buf || !a->motion_start_times ||
       !a->motion_start_times_offset || !a->sampled_motion_ids || !a->obs_buf)
     return PHC_ERR_NULL;
-  if (a->state_init == PHC_STATE_INIT_RANDOM && !a->flag_test && !a->phase) return PHC_ERR_NULL;
-  if (a->state_init != PHC_STATE_INIT_RANDOM && a->state_init != PHC_STATE_INIT_START) return PHC_ERR_UNSUPPORTED;
+  if (a->state_init < PHC_STATE_INIT_START || a->state_init > PHC_STATE_INIT_HYBRID) return PHC_ERR_UNSUPPORTED;
+  const bool samples = a->state_init == PHC_STATE_INIT_RANDOM || a->state_init == PHC_STATE_INIT_HYBRID;
+  if (samples && !a->flag_test && !a->phase) return PHC_ERR_NULL;
+  if (a->state_init >= PHC_STATE_INIT_DEFAULT) {
+    if (a->state_init == PHC_STATE_INIT_HYBRID && !a->default_mask) return PHC_ERR_NULL;
+    if ((a->humanoid_root_states && !a->initial_root_states) || (a->dof_pos && !a->initial_dof_pos) ||
+        (a->dof_vel && !a->initial_dof_vel))
+      return PHC_ERR_NULL;
+    if ((a->humanoid_root_states && a->initial_root_stride < 13) || ((a->dof_pos || a->dof_vel) && a->initial_dof_stride < 69))
+      return PHC_ERR_SHAPE;
+  }
   if ((a->dof_pos && !lib->d.lrs) || (a->dof_vel && !lib->d.dvs) || (a->ref_dof_pos && !lib->d.lrs)) return PHC_ERR_NULL;
   if (a->time_steps < 1 || a->time_steps > PHC_MAX_TIME_STEPS) return PHC_ERR_SHAPE;
   const ObsFlags of = obs_flags_from(a->obs_flags);
@@ -3748,6 +3808,12 @@ static int reset_fill(const PhcLib* lib, const PhcResetArgs* a, int64_t n, Reset
   r.w.phase = a->phase;
   r.w.state_init = a->state_init;
   r.w.flag_test = a->flag_test;
+  r.w.init_root = a->initial_root_states;
+  r.w.init_root_stride = a->initial_root_stride;
+  r.w.init_dof_pos = a->initial_dof_pos;
+  r.w.init_dof_vel = a->initial_dof_vel;
+  r.w.init_dof_stride = a->initial_dof_stride;
+  r.w.default_mask = a->default_mask;
   r.ids = a->sampled_motion_ids;
   r.mask = a->env_mask;
   r.n = n;
@@ -4060,6 +4126,7 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
     PHC_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     return launch_status();
   }
+  bool reset_after = false;
   if (fast) {
     if (!first_wave[dev]) {
       int sms = 0, per_sm = 0;
@@ -4083,16 +4150,23 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
     constexpr size_t SM = sizeof(FastSmem<4>);
     // the moments epilogue leaves as TMA bulk reductions when the accumulators are 16-B aligned
     p.moments_bulk = (p.moments && g_moments_bulk && ((uintptr_t)p.moments & 15) == 0) ? 1 : 0;
-    if (!def) return launch_step(step_fast_kernel<4, 8, false, true, true, false>, SM, 4, p, stream, &attr[6][dev], pdl);
-    if (p.reset_on) {
-      if (p.obs_norm) return launch_step(step_fast_kernel<4, 8, true, true, true>, SM, 4, p, stream, &attr[5][dev], pdl);
-      return launch_step(step_fast_kernel<4, 8, false, true, true>, SM, 4, p, stream, &attr[4][dev], pdl);
-    }
-    if (p.obs_norm && p.ep_returns) return launch_step(step_fast_kernel<4, 8, true, true>, SM, 4, p, stream, &attr[3][dev], pdl);
-    if (p.ep_returns) return launch_step(step_fast_kernel<4, 8, false, true>, SM, 4, p, stream, &attr[2][dev], pdl);
-    if (p.obs_norm) return launch_step(step_fast_kernel<4, 8, true>, SM, 4, p, stream, &attr[1][dev], pdl);
-    return launch_step(step_fast_kernel<4, 8>, SM, 4, p, stream, &attr[0][dev], pdl);
-  }
+    // StateInit.Default / Hybrid resets are not built into the step kernel: the step runs without the in-kernel reset and
+    // phc_reset_envs follows it (reset_after below), with the same result
+    const bool in_kernel = p.reset_on && p.rw.state_init <= PHC_STATE_INIT_RANDOM;
+    reset_after = p.reset_on && !in_kernel;
+    StepParams pk = p;
+    if (reset_after) pk.reset_on = 0;
+    if (!def) rc = launch_step(step_fast_kernel<4, 8, false, true, true, false>, SM, 4, pk, stream, &attr[6][dev], pdl);
+    else if (in_kernel) {
+      if (p.obs_norm) rc = launch_step(step_fast_kernel<4, 8, true, true, true>, SM, 4, pk, stream, &attr[5][dev], pdl);
+      else rc = launch_step(step_fast_kernel<4, 8, false, true, true>, SM, 4, pk, stream, &attr[4][dev], pdl);
+    } else if (p.obs_norm && p.ep_returns)
+      rc = launch_step(step_fast_kernel<4, 8, true, true>, SM, 4, pk, stream, &attr[3][dev], pdl);
+    else if (p.ep_returns) rc = launch_step(step_fast_kernel<4, 8, false, true>, SM, 4, pk, stream, &attr[2][dev], pdl);
+    else if (p.obs_norm) rc = launch_step(step_fast_kernel<4, 8, true>, SM, 4, pk, stream, &attr[1][dev], pdl);
+    else rc = launch_step(step_fast_kernel<4, 8>, SM, 4, pk, stream, &attr[0][dev], pdl);
+    if (rc != PHC_OK || !reset_after) return rc;
+  } else {
   // T > 1 on the AoS tensor + packed table: the pipelined TMA kernel
   const bool multi = !g_force_generic && p.T > 1 && p.aos && p.L.packed && p.obs_vec2 && !p.obs_norm && def &&
                      !(args->flags & PHC_STEP_MAPPED_HOST_IO);
@@ -4115,8 +4189,10 @@ int step_fused_mirrored(const PhcLib* lib, const PhcStepArgs* args, int64_t n, p
     episode_bucket_kernel<<<(unsigned)((p.n + 255) / 256), 256, 0, stream>>>(p);
     rc = launch_status();
   }
-  if (rc == PHC_OK && p.reset_on) {
-    // ... nor the in-step reset: phc_reset_envs behind them, reset_buf as its own mask (the step's flags are already
+  reset_after = p.reset_on != 0;  // ... nor the in-step reset
+  }
+  if (rc == PHC_OK && reset_after) {
+    // phc_reset_envs behind the step, reset_buf as its own mask (the step's flags are already
     // in reset_out / terminate_out), the normalised rows and the moments kept consistent with the rewritten rows
     ResetParams r;
     rc = reset_fill(lib, args->auto_reset, n, r);

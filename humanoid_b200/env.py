@@ -151,7 +151,14 @@ class HumanoidPHC:
 
         # root state of the humanoid actor (humanoid_phc.py:518-523)
         self._humanoid_root_states = torch.zeros((N, 13), dtype=torch.float32, device=dev)
-        self.state_init_random = True  # StateInit.Random (config.py:110); False = StateInit.Start
+        # StateInit (envs/state_init.py, config.py:110,139): "random" (the default), "start", "default", "hybrid"
+        self.state_init = "random"
+        self.hybrid_init_prob = 0.5
+        # what _reset_default restores (:521, :543-544; the reference clones them from the simulator at start-up)
+        self._initial_humanoid_root_states = torch.zeros((N, 13), dtype=torch.float32, device=dev)
+        self._initial_dof_pos = torch.zeros((N, self.num_dof), dtype=torch.float32, device=dev)
+        self._initial_dof_vel = torch.zeros((N, self.num_dof), dtype=torch.float32, device=dev)
+        self._default_mask = None  # hybrid: [N] uint8, 1 = the env takes the default path at its next reset
         self.flag_test = False
 
         # AMP observation buffers (humanoid_phc.py:186-194, 245, 469-478, 596-611)
@@ -187,6 +194,42 @@ class HumanoidPHC:
         self.obs_norm_buf = None
         self._mpjpe = None
         self._step_args = None
+
+    # ------------------------------------------------------------------------------------
+    @property
+    def state_init_random(self) -> bool:
+        """Round-1 spelling: True = StateInit.Random, False = StateInit.Start."""
+        return self.state_init == "random"
+
+    @state_init_random.setter
+    def state_init_random(self, on: bool):
+        self.state_init = "random" if on else "start"
+
+    def _state_init_code(self) -> int:
+        try:
+            return {"start": _cabi.STATE_INIT_START, "random": _cabi.STATE_INIT_RANDOM,
+                    "default": _cabi.STATE_INIT_DEFAULT, "hybrid": _cabi.STATE_INIT_HYBRID}[self.state_init]  # fmt: skip
+        except KeyError:
+            raise ValueError(f"Unsupported state initialization strategy: {self.state_init}")  # humanoid_phc.py:686
+
+    def _fill_state_init(self, a, default_mask_by_env: Optional[torch.Tensor]):
+        """StateInit fields of a PhcResetArgs.  Hybrid: ``default_mask_by_env`` [N] marks the envs that take the default
+        path (the reference draws ``torch.bernoulli(hybrid_init_prob) == 1`` for reference-state init, :733-737); drawn
+        here when omitted."""
+        a.state_init = self._state_init_code()
+        if self.state_init in ("default", "hybrid"):
+            if self.use_amp_obs:
+                raise NotImplementedError("Not tested yet")  # the reference's own words, humanoid_phc.py:795-797
+            a.initial_root_states = self._initial_humanoid_root_states.data_ptr()
+            a.initial_root_stride = self._initial_humanoid_root_states.stride(0)
+            a.initial_dof_pos = self._initial_dof_pos.data_ptr()
+            a.initial_dof_vel = self._initial_dof_vel.data_ptr()
+            a.initial_dof_stride = self._initial_dof_pos.stride(0)
+        if self.state_init == "hybrid":
+            if default_mask_by_env is None:
+                default_mask_by_env = torch.rand(self.num_envs, device=self.device) >= self.hybrid_init_prob
+            self._default_mask = default_mask_by_env.to(self.device, torch.uint8).contiguous()
+            a.default_mask = self._default_mask.data_ptr()
 
     # ------------------------------------------------------------------------------------
     @property
@@ -437,7 +480,8 @@ class HumanoidPHC:
         a.rwd.w_pos, a.rwd.w_rot, a.rwd.w_vel, a.rwd.w_ang_vel = r["w_pos"], r["w_rot"], r["w_vel"], r["w_ang_vel"]
         a.rew_power_coef = self.rew_power_coef
 
-    def post_physics_step(self, advance_progress: bool = True, phase_by_env: Optional[torch.Tensor] = None):
+    def post_physics_step(self, advance_progress: bool = True, phase_by_env: Optional[torch.Tensor] = None,
+                          default_mask_by_env: Optional[torch.Tensor] = None):
         """progress += 1; reward; reset; observations (humanoid_phc.py:138-149) — one launch (with ``auto_reset`` the
         reset of the flagged envs and their new observation rows too)."""
         cached = self._step_args
@@ -449,7 +493,7 @@ class HumanoidPHC:
         if self.auto_reset:
             r = self._reset_args
             r.phase = self._next_phase(phase_by_env).data_ptr()
-            r.state_init = _cabi.STATE_INIT_RANDOM if self.state_init_random else _cabi.STATE_INIT_START
+            self._fill_state_init(r, default_mask_by_env)
             r.flag_test = 1 if self.flag_test else 0
             r.dt = self.dt
         _cabi.check(
@@ -469,12 +513,13 @@ class HumanoidPHC:
         return self._action_to_pd_targets(actions, res_action=self.res_action, ref_dof_pos=self.ref_dof_pos,
                                           clip=clip, actions_out=actions_out, out=self._pd_target)  # fmt: skip
 
-    def step(self, actions=None, phase_by_env: Optional[torch.Tensor] = None):
+    def step(self, actions=None, phase_by_env: Optional[torch.Tensor] = None,
+             default_mask_by_env: Optional[torch.Tensor] = None):
         """The reference's ``step`` minus PhysX (out of scope): the caller has already written the post-physics
         rigid-body state.  ``actions`` (optional) are turned into PD targets first, as :105-128 does."""
         if actions is not None:
             self.pre_physics_step(actions)
-        self.post_physics_step(True, phase_by_env)
+        self.post_physics_step(True, phase_by_env, default_mask_by_env)
         self.extras["terminate"] = self._terminate_out  # = _terminate_buf.clone() (:151)
         self.extras["reset"] = self._reset_out
         self.extras["reward_raw"] = self.reward_raw
@@ -588,7 +633,8 @@ class HumanoidPHC:
     # ------------------------------------------------------------------------------------
     # reset (humanoid_phc.py:90-103, 665-778) — on the device, no host sync
     # ------------------------------------------------------------------------------------
-    def _fill_reset_args(self, mask: Optional[torch.Tensor], phase_by_env: Optional[torch.Tensor], moments_mode: int = 0):
+    def _fill_reset_args(self, mask: Optional[torch.Tensor], phase_by_env: Optional[torch.Tensor], moments_mode: int = 0,
+                         default_mask_by_env: Optional[torch.Tensor] = None):
         body, keep = _cabi.body_state(
             self._rigid_body_pos, self._rigid_body_rot, self._rigid_body_vel, self._rigid_body_ang_vel
         )
@@ -609,7 +655,7 @@ class HumanoidPHC:
         a.sampled_motion_ids = self._sampled_motion_ids.data_ptr()
         a.env_mask = _cabi.ptr(mask)
         a.phase = _cabi.ptr(phase_by_env)
-        a.state_init = _cabi.STATE_INIT_RANDOM if self.state_init_random else _cabi.STATE_INIT_START
+        self._fill_state_init(a, default_mask_by_env)
         a.flag_test = 1 if self.flag_test else 0
         a.time_steps = self.time_steps
         a.dt = self.dt
@@ -635,10 +681,11 @@ class HumanoidPHC:
         a._keep = (keep, mask, phase_by_env)
         return a
 
-    def _reset_masked(self, mask: torch.Tensor, phase_by_env: torch.Tensor, moments_mode: int = 0):
+    def _reset_masked(self, mask: torch.Tensor, phase_by_env: torch.Tensor, moments_mode: int = 0,
+                      default_mask_by_env: Optional[torch.Tensor] = None):
         """``moments_mode``: 1 = the new rows are added to the step's RunningNorm partials (rows never counted: a
         ``reset()``), 2 = they replace the rows the flagging step had counted (``reset_done()``)."""
-        a = self._fill_reset_args(mask, phase_by_env, moments_mode)
+        a = self._fill_reset_args(mask, phase_by_env, moments_mode, default_mask_by_env)
         _cabi.check(
             _cabi.load().phc_reset_envs(self._motion_lib.handle, C.byref(a), self.num_envs, _cabi.stream_ptr(self.device)),
             "phc_reset_envs",
@@ -646,36 +693,52 @@ class HumanoidPHC:
         if self.use_amp_obs:  # _reset_envs (:675-676)
             self._init_amp_obs_masked(mask)
 
-    def reset(self, env_ids=None, phase: Optional[torch.Tensor] = None):
-        """``HumanoidPHC.reset(env_ids)`` (:90-103) with reference-state init: sample a start time
-        per env (``sample_time_interval``), pose the env from the motion library, reset its clock
-        and buffers, recompute its observation.  ``phase`` are the uniform numbers the reference
-        draws with ``torch.rand(len(env_ids))``; drawn here when omitted.  The second, PhysX-settling
-        pass of ``safe_reset`` (:97-101) is out of scope."""
+    def reset(self, env_ids=None, phase: Optional[torch.Tensor] = None, default_mask: Optional[torch.Tensor] = None):
+        """``HumanoidPHC.reset(env_ids)`` (:90-103).  Reference-state init (``state_init`` "random" / "start"): sample a
+        start time per env (``sample_time_interval``), pose the env from the motion library, reset its clock and
+        buffers, recompute its observation.  ``phase`` are the uniform numbers the reference draws with
+        ``torch.rand(len(env_ids))``; drawn here when omitted.  ``state_init`` "default": root / dof state from the
+        initial buffers, clock and rigid-body state untouched (:688-692).  "hybrid": ``default_mask``
+        [len(env_ids)] picks the envs that take the default path (the reference's ``torch.bernoulli(hybrid_init_prob)
+        != 1``; drawn here when omitted); ``phase`` then has one number per env_id, or — as the reference draws them —
+        one per reference-init env.  The second, PhysX-settling pass of ``safe_reset`` (:97-101) is out of scope."""
         if env_ids is None:
             env_ids = self.all_env_ids
         env_ids = env_ids.to(self.device)
+        dmask_by_env = None
+        ref_ids = env_ids
+        if self.state_init == "hybrid":
+            if default_mask is None:
+                default_mask = torch.rand(env_ids.shape, device=self.device) >= self.hybrid_init_prob
+            default_mask = default_mask.to(self.device, torch.bool)
+            dmask_by_env = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+            dmask_by_env[env_ids] = default_mask
+            ref_ids = env_ids[~default_mask]
+        elif self.state_init == "default":
+            ref_ids = env_ids[:0]
         if phase is None:
-            phase = torch.rand(env_ids.shape, device=self.device)
+            phase = torch.rand(ref_ids.shape, device=self.device)
         mask = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         mask[env_ids] = True
         by_env = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
-        by_env[env_ids] = phase.to(self.device, torch.float32)
-        self._reset_masked(mask, by_env, moments_mode=1)
+        by_env[ref_ids if phase.shape[0] == ref_ids.shape[0] else env_ids] = phase.to(self.device, torch.float32)
+        self._reset_masked(mask, by_env, moments_mode=1, default_mask_by_env=dmask_by_env)
         if self._obs_moment_buckets is not None:
             self.obs_moment_rows += int(env_ids.numel())  # rows the policy will see and no step has counted
         return self.obs_buf
 
-    def reset_done(self, phase_by_env: Optional[torch.Tensor] = None):
+    def reset_done(self, phase_by_env: Optional[torch.Tensor] = None, default_mask_by_env: Optional[torch.Tensor] = None):
         """Reset every env whose ``reset_buf`` is set, entirely on the device: replaces the
         ``nonzero(reset_buf)`` + ``env.reset(reset_indices)`` of clean_pufferl/env.py:133-135 and its
-        host sync.  ``phase_by_env [N]`` supplies one uniform number per env (used where flagged)."""
+        host sync.  ``phase_by_env [N]`` supplies one uniform number per env (used where flagged);
+        ``default_mask_by_env [N]`` the hybrid-init choice per env (drawn here when omitted)."""
         if phase_by_env is None:
             phase_by_env = torch.rand(self.num_envs, device=self.device)
         # the reset kernel reads each mask byte once before it clears reset_buf, so reset_buf can be its own mask;
         # the AMP initialisation that follows needs the flags after they are cleared, hence the copy there
         mask = self.reset_buf.clone() if self.use_amp_obs else self.reset_buf
-        self._reset_masked(mask, phase_by_env.to(self.device, torch.float32).contiguous(), moments_mode=2)
+        self._reset_masked(mask, phase_by_env.to(self.device, torch.float32).contiguous(), moments_mode=2,
+                           default_mask_by_env=default_mask_by_env)
         return self.obs_buf
 
     def set_humanoid_assets(self, skeleton_trees, humanoid_shapes, humanoid_limb_and_weights):

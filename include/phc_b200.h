@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PHC_ABI_VERSION 3 /* 3: PhcStepArgs grew (rew_out, reset_out, terminate_out, auto_reset, ref_dof_pos, obs_flags), PhcResetArgs grew (obs_norm*, obs_moments*),
+#define PHC_ABI_VERSION 4 /* 4: PhcResetArgs grew (initial_*, default_mask: StateInit.Default / Hybrid); 3: PhcStepArgs grew (rew_out, reset_out, terminate_out, auto_reset, ref_dof_pos, obs_flags), PhcResetArgs grew (obs_norm*, obs_moments*),
                               phc_action_to_pd_targets takes the action clip; 2: obs_moments_buckets, ep_*, phc_motion_build / phc_peer_reduce_* / phc_episode_fold */
 #define PHC_NUM_BODIES 24      /* SMPL humanoid, body_sets.py:11-36 */
 #define PHC_SELF_OBS_DIM 358   /* envs/humanoid_phc.py:461 */
@@ -337,6 +337,15 @@ PHC_API int phc_step_fused(const PhcLib* lib, const PhcStepArgs* args, int64_t n
  * ---------------------------------------------------------------------------------- */
 #define PHC_STATE_INIT_START 0  /* motion time 0                       state_init.py */
 #define PHC_STATE_INIT_RANDOM 1 /* sample_time_interval(phase)                       */
+/* ABI 4.  StateInit.Default (_reset_default, envs/humanoid_phc.py:688-692): root / dof state of the selected envs from
+ * the initial_* buffers; the rigid-body tensors and the motion clock (start times, global offset) stay as they are,
+ * progress / reset / terminate -> 0, the observation rows are those of the (unchanged) rigid-body state at the restarted
+ * clock.  StateInit.Hybrid (_reset_hybrid_state_init, :733-745): an env whose default_mask byte is set takes the
+ * default path, the others reference-state init at a sampled time; the reference draws the mask with
+ * torch.bernoulli(hybrid_init_prob) — the caller supplies it, like `phase`.  (AMP buffers: the reference raises
+ * NotImplementedError for default-reset envs, :795-797.) */
+#define PHC_STATE_INIT_DEFAULT 2
+#define PHC_STATE_INIT_HYBRID 3
 typedef struct PhcResetArgs {
   PhcBodyState body;                      /* sim state views, written for the selected envs (J = 24) */
   float* humanoid_root_states;            /* NULL or [n,13]: pos3|rot4|vel3|ang vel3  humanoid_phc.py:518 */
@@ -377,6 +386,14 @@ typedef struct PhcResetArgs {
   float* ref_dof_pos;                     /* NULL or [n, 69]: _compute_task_obs(env_ids) of the reset keeps the dof_pos of
                                              the query at t + dt for res_action            humanoid_phc.py:1115-1120 */
   int64_t ref_dof_pos_stride;
+  /* ---- ABI 4: StateInit.Default / Hybrid ------------------------------------------------------------------------- */
+  const float* initial_root_states;       /* [n,13] _initial_humanoid_root_states (:521); needed for DEFAULT / HYBRID
+                                             when humanoid_root_states is set */
+  int64_t initial_root_stride;
+  const float* initial_dof_pos;           /* [n,69] _initial_dof_pos (:543), dense rows of initial_dof_stride floats */
+  const float* initial_dof_vel;           /* [n,69] _initial_dof_vel (:544) */
+  int64_t initial_dof_stride;
+  const uint8_t* default_mask;            /* HYBRID: [n], 1 = this env takes the default path */
 } PhcResetArgs;
 PHC_API int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* args, int64_t n, phc_stream_t stream);
 

@@ -609,35 +609,53 @@ def reset_envs(
     flag_test: bool = False,
     time_steps: int = 1,
     num_bodies: int = 24,
+    default_mask: Tensor = None,  # [len(env_ids)] bool: these envs take _reset_default (StateInit.Default: all of them;
+    #                               StateInit.Hybrid: where torch.bernoulli(hybrid_init_prob) came up 0, :733-745)
+    initial_root_states: Tensor = None,  # [N, 13]
+    initial_dof_pos: Tensor = None,  # [N, 69]
+    initial_dof_vel: Tensor = None,  # [N, 69]
 ):
-    """HumanoidPHC._reset_envs(env_ids) for StateInit.Random / Start, minus the PhysX setters
-    (humanoid_phc.py:665-676): _sample_ref_state (:845-875) -> _set_env_state (:901-931) ->
-    clock updates (:724-731) -> buffer zeroing (:775-778) -> _compute_observations(env_ids)
-    (:937-961).  All tensors are updated in place; returns the obs rows of env_ids."""
+    """HumanoidPHC._reset_envs(env_ids), minus the PhysX setters (humanoid_phc.py:665-676).  Reference-state init
+    (StateInit.Random / Start, and the reference-init share of Hybrid): _sample_ref_state (:845-875) -> _set_env_state
+    (:901-931) -> clock updates (:724-731); ``phase`` has one number per such env.  Default init (:688-692): root and
+    dof state from the initial buffers — the rigid-body tensors and the motion clock stay as they are.  Then, for all
+    of env_ids: buffer zeroing (:775-778) -> _compute_observations(env_ids) (:937-961).  All tensors are updated in
+    place; returns the obs rows of env_ids."""
     J = num_bodies
+    all_ids = env_ids
+    if default_mask is not None:
+        def_ids = env_ids[default_mask]
+        env_ids = env_ids[~default_mask]
+        # _reset_default
+        root_states[def_ids] = initial_root_states[def_ids]
+        dof_pos[def_ids] = initial_dof_pos[def_ids]
+        dof_vel[def_ids] = initial_dof_vel[def_ids]
+    if env_ids.shape[0] > 0:
+        ids = sampled_motion_ids[env_ids]
+        if random_init:
+            motion_times = sample_time_interval(lib._motion_lengths, ids, phase)
+        else:
+            motion_times = torch.zeros(env_ids.shape[0])
+        if flag_test:
+            motion_times[:] = 0
+        res = lib.get_motion_state(ids, motion_times, global_offset[env_ids])  # the old offset (:860)
+        # _set_env_state
+        root_states[env_ids, 0:3] = res["root_pos"]
+        root_states[env_ids, 3:7] = res["root_rot"]
+        root_states[env_ids, 7:10] = res["root_vel"]
+        root_states[env_ids, 10:13] = res["root_ang_vel"]
+        dof_pos[env_ids] = res["dof_pos"]
+        dof_vel[env_ids] = res["dof_vel"]
+        state[env_ids, :J, 0:3] = res["rg_pos"]
+        state[env_ids, :J, 3:7] = res["rb_rot"]
+        state[env_ids, :J, 7:10] = res["body_vel"]
+        state[env_ids, :J, 10:13] = res["body_ang_vel"]
+        # _reset_ref_state_init
+        global_offset[env_ids] = 0
+        motion_start_times[env_ids] = motion_times
+        motion_start_times_offset[env_ids] = 0
+    env_ids = all_ids
     ids = sampled_motion_ids[env_ids]
-    if random_init:
-        motion_times = sample_time_interval(lib._motion_lengths, ids, phase)
-    else:
-        motion_times = torch.zeros(env_ids.shape[0])
-    if flag_test:
-        motion_times[:] = 0
-    res = lib.get_motion_state(ids, motion_times, global_offset[env_ids])  # the old offset (:860)
-    # _set_env_state
-    root_states[env_ids, 0:3] = res["root_pos"]
-    root_states[env_ids, 3:7] = res["root_rot"]
-    root_states[env_ids, 7:10] = res["root_vel"]
-    root_states[env_ids, 10:13] = res["root_ang_vel"]
-    dof_pos[env_ids] = res["dof_pos"]
-    dof_vel[env_ids] = res["dof_vel"]
-    state[env_ids, :J, 0:3] = res["rg_pos"]
-    state[env_ids, :J, 3:7] = res["rb_rot"]
-    state[env_ids, :J, 7:10] = res["body_vel"]
-    state[env_ids, :J, 10:13] = res["body_ang_vel"]
-    # _reset_ref_state_init
-    global_offset[env_ids] = 0
-    motion_start_times[env_ids] = motion_times
-    motion_start_times_offset[env_ids] = 0
     # _reset_env_tensors
     progress_buf[env_ids] = 0
     reset_buf[env_ids] = 0
@@ -814,14 +832,22 @@ class OracleEnv:
                                                          self._key_body_ids, self.dof_subset)  # fmt: skip
         return pd_target
 
-    def reset(self, env_ids: Tensor, phase: Tensor):
+    def reset(self, env_ids: Tensor, phase: Tensor, default_mask: Tensor = None):
+        """``default_mask`` [len(env_ids)]: the envs that take StateInit.Default's path (all of them in Default mode, the
+        Bernoulli losers in Hybrid mode); ``phase`` then has one number per remaining env.  Needs ``initial_root_states``,
+        ``initial_dof_pos``, ``initial_dof_vel`` set on the instance."""
         if len(env_ids) == 0:
             return
+        kw = {}
+        if default_mask is not None:
+            assert not self.use_amp_obs, "_init_amp_obs raises NotImplementedError for default-reset envs (:795-797)"
+            kw = dict(default_mask=default_mask, initial_root_states=self.initial_root_states,
+                      initial_dof_pos=self.initial_dof_pos, initial_dof_vel=self.initial_dof_vel)  # fmt: skip
         reset_envs(
             self.lib, env_ids, phase, self.state, self.root_states, self.dof_state[..., 0], self.dof_state[..., 1],
             self.progress_buf, self.reset_buf, self._terminate_buf, self._motion_start_times,
             self._motion_start_times_offset, self._global_offset, self._sampled_motion_ids, self.obs_buf, self.dt,
-            flag_test=self.flag_test,
+            flag_test=self.flag_test, **kw,
         )  # fmt: skip
         if self.use_amp_obs:  # _init_amp_obs (:791-799)
             self._amp_obs_buf[env_ids, 0] = amp_obs_from_state(

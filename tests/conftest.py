@@ -221,3 +221,42 @@ def replay_env_rollout(g, env, read=lambda t: t, tol=None, dof_tol=None):
         assert_close(read(env._amp_obs_demo_buf).flatten(1), o("amp_obs_demo"), what=f"amp_obs_demo after reset[{k}]",
                      **dof_tol)  # fmt: skip
     return K
+
+
+def replay_env_reset_modes(g, env, mode, read=lambda t: t, tol=None, dof_tol=None):
+    """Drive ``env`` through the ``mode`` ("Default" / "Hybrid") half of tests/golden/env_reset_modes.npz — a recording of
+    the reference's own HumanoidPHC.step / reset with StateInit.Default / StateInit.Hybrid — and compare every buffer
+    after every call.  ``env`` as for replay_env_rollout, with reset(env_ids, phase, default_mask)."""
+    tol = tol or dict(rtol=1e-6, atol=1e-6)
+    dof_tol = dof_tol or tol
+    K = len([k for k in g.keys() if k.startswith(f"in.{mode}.actions.")])
+    for k in range(K):
+        def physics(e, k=k):
+            e.write_sim(g.inp(f"{mode}.state.{k}"), g.inp(f"{mode}.dof_state.{k}"), g.inp(f"{mode}.dof_force.{k}"))
+
+        pd = env.step(g.inp(f"{mode}.actions.{k}"), physics)
+        assert_equal_exact(read(pd), g.out(f"{mode}.pd_target.{k}"), f"pd_target[{k}]")
+        o = lambda n, k=k: g.out(f"{mode}.step.{k}.{n}")  # noqa: E731
+        assert_equal_exact(read(env.progress_buf), o("progress"), f"progress[{k}]")
+        assert_equal_exact(read(env.reset_buf), o("reset"), f"reset[{k}]")
+        assert_equal_exact(read(env._terminate_buf), o("terminate"), f"terminate[{k}]")
+        assert_close(read(env.obs_buf), o("obs"), what=f"obs[{k}]", **tol)
+        assert_close(read(env.rew_buf), o("rew"), what=f"rew[{k}]", **tol)
+        assert_close(read(env.reward_raw), o("reward_raw"), what=f"reward_raw[{k}]", **tol)
+        rows = g.inp(f"{mode}.reset_indices.{k}")
+        if mode == "Default":
+            default_mask, phase = torch.ones(rows.shape[0], dtype=torch.bool), torch.zeros(0)
+        else:
+            default_mask, phase = ~g.inp(f"{mode}.ref_mask.{k}"), g.inp(f"{mode}.phase.{k}")
+        env.reset(rows, phase, default_mask)
+        o = lambda n, k=k: g.out(f"{mode}.reset.{k}.{n}")  # noqa: E731
+        for name, attr in (("progress", "progress_buf"), ("reset", "reset_buf"), ("terminate", "_terminate_buf"),
+                           ("motion_start_times", "_motion_start_times"), ("global_offset", "_global_offset"),
+                           ("motion_start_times_offset", "_motion_start_times_offset")):  # fmt: skip
+            assert_equal_exact(read(getattr(env, attr)), o(name), f"{name} after reset[{k}]")
+        sim, root, dof = env.read_sim()
+        assert_close(read(sim), o("rigid_body_state"), what=f"rigid_body_state after reset[{k}]", **tol)
+        assert_close(read(root)[rows], o("root_states")[rows], what=f"root_states after reset[{k}]", **tol)
+        assert_close(read(dof)[rows], o("dof_state")[rows], what=f"dof_state after reset[{k}]", **dof_tol)
+        assert_close(read(env.obs_buf), o("obs"), what=f"obs after reset[{k}]", **tol)
+    return K

@@ -484,24 +484,22 @@ def load_reference_env_module():
     return H
 
 
-def case_env_rollout():
-    """The unmodified reference ``HumanoidPHC.step(actions)`` and ``HumanoidPHC.reset(env_ids)``
-    (envs/humanoid_phc.py:90-172) driven for a few steps as clean_pufferl/env.py:109-140 drives them, on
-    an instance built without ``__init__`` (which needs Isaac Gym and asset files).  PhysX is a scripted
-    stand-in: ``fetch_results`` writes the next rigid-body / dof state (reference pose at the coming
-    reward time + noise) into the same AoS tensors the reference wraps.  Default EnvConfig except
-    use_amp_obs=True and num_amp_obs_steps=4 (10 in the config; smaller fixture)."""
+def make_reference_env(N, S, use_amp=True, state_init=None, seed=41):
+    """An instance of the reference's HumanoidPHC built without ``__init__`` (which needs Isaac Gym and asset files),
+    with PhysX scripted: ``fetch_results`` writes the next rigid-body / dof state (reference pose at the coming reward
+    time + noise) into the same AoS tensors the reference wraps.  Returns (H, env, lib, lib_data, clock, rec, cfg)."""
     import types
 
     H = load_reference_env_module()
     from puffer_phc.config import EnvConfig
 
-    N, K, S = 24, 5, 4
-    lib_data, clock, _ = synth.make_case(N, N, ref_query, seed=41, device="cpu", min_frames=16, max_frames=26,
+    lib_data, clock, _ = synth.make_case(N, N, ref_query, seed=seed, device="cpu", min_frames=16, max_frames=26,
                                          max_progress=6)  # fmt: skip
     lib = ref_loader.make_reference_lib(lib_data)
     cfg = EnvConfig()
-    cfg.num_envs, cfg.device_type, cfg.use_amp_obs, cfg.num_amp_obs_steps = N, "cpu", True, S
+    cfg.num_envs, cfg.device_type, cfg.use_amp_obs, cfg.num_amp_obs_steps = N, "cpu", use_amp, S
+    if state_init is not None:
+        cfg.state_init = getattr(H.StateInit, state_init)
     assert cfg.device == "cpu" and cfg.robot.freeze_hand and cfg.robot.freeze_toe and cfg.reward.use_power_reward
 
     env = object.__new__(H.HumanoidPHC)
@@ -605,6 +603,19 @@ def case_env_rollout():
 
     env.gym = ScriptedGym()
 
+    return H, env, lib, lib_data, clock, rec, cfg
+
+
+def case_env_rollout():
+    """The unmodified reference ``HumanoidPHC.step(actions)`` and ``HumanoidPHC.reset(env_ids)``
+    (envs/humanoid_phc.py:90-172) driven for a few steps as clean_pufferl/env.py:109-140 drives them, on
+    an instance built without ``__init__`` (which needs Isaac Gym and asset files).  PhysX is a scripted
+    stand-in: ``fetch_results`` writes the next rigid-body / dof state (reference pose at the coming
+    reward time + noise) into the same AoS tensors the reference wraps.  Default EnvConfig except
+    use_amp_obs=True and num_amp_obs_steps=4 (10 in the config; smaller fixture)."""
+    N, K, S = 24, 5, 4
+    H, env, lib, lib_data, clock, rec, cfg = make_reference_env(N, S)
+
     arrays = {}
     arrays.update(npify(lib_data.as_dict(), "in.lib"))
     arrays.update(npify(clock.__dict__, "in.clock"))
@@ -645,6 +656,67 @@ def case_env_rollout():
         for k in range(K):
             arrays[("out" if n == "pd_target" else "in") + f".{n}.{k}"] = rec[n][k].numpy()
     save("env_rollout", arrays)
+
+
+def case_env_reset_modes():
+    """``HumanoidPHC.reset(env_ids)`` with StateInit.Default and StateInit.Hybrid (envs/humanoid_phc.py:678-745):
+    the unmodified reference driven like case_env_rollout (AMP off: ``_init_amp_obs`` raises NotImplementedError
+    for default-reset envs, :795-797).  Default: root / dof state from the initial buffers, the rigid-body tensors
+    and the motion clock untouched, progress 0, observations of the (stale) rigid-body state.  Hybrid:
+    ``torch.bernoulli(hybrid_init_prob)`` per env picks reference-state init or default; the mask and the uniform
+    numbers ``sample_time_interval`` draws afterwards are recorded."""
+    N, K, S = 24, 3, 4
+    arrays = {}
+    for mode in ("Default", "Hybrid"):
+        H, env, lib, lib_data, clock, rec, cfg = make_reference_env(N, S, use_amp=False, state_init=mode, seed=47)
+        cfg.hybrid_init_prob = 0.5
+        g = torch.Generator().manual_seed(48)
+        env._initial_humanoid_root_states = torch.randn(N, 13, generator=g)
+        env._initial_dof_pos = torch.randn(N, 69, generator=g) * 0.3
+        env._initial_dof_vel = torch.randn(N, 69, generator=g)
+        if mode == "Default":  # shared inputs, once
+            arrays.update(npify(lib_data.as_dict(), "in.lib"))
+            arrays.update(npify(clock.__dict__, "in.clock"))
+            arrays["in.pd_action_offset"], arrays["in.pd_action_scale"] = env._pd_action_offset.numpy(), env._pd_action_scale.numpy()
+            arrays["in.rew_power_coef"] = np.float32(cfg.rew_power_coef)
+            arrays["in.termination_distance"] = np.float32(cfg.termination_distance)
+            arrays["in.hybrid_init_prob"] = np.float32(cfg.hybrid_init_prob)
+            arrays["in.initial_root_states"] = env._initial_humanoid_root_states.numpy()
+            arrays["in.initial_dof_pos"] = env._initial_dof_pos.numpy()
+            arrays["in.initial_dof_vel"] = env._initial_dof_vel.numpy()
+        ga = torch.Generator().manual_seed(49)
+        for k in range(K):
+            actions = torch.rand(N, 69, generator=ga) * 2 - 1
+            arrays[f"in.{mode}.actions.{k}"] = actions.numpy()
+            obs, rew, reset, extras = env.step(actions)
+            out = {"obs": env.obs_buf, "rew": env.rew_buf, "reward_raw": env.reward_raw, "reset": env.reset_buf,
+                   "terminate": extras["terminate"], "progress": env.progress_buf}  # fmt: skip
+            arrays.update({f"out.{mode}.step.{k}.{n}": v.detach().numpy().copy() for n, v in out.items()})
+            reset_indices = torch.nonzero(env.reset_buf).squeeze(-1)
+            assert 0 < len(reset_indices) < N
+            arrays[f"in.{mode}.reset_indices.{k}"] = reset_indices.numpy()
+            torch.manual_seed(800 + k)
+            if mode == "Hybrid":  # what _reset_hybrid_state_init (:733-745) and then sample_time_interval will draw
+                probs = H.to_torch(np.array([cfg.hybrid_init_prob] * len(reset_indices)), device="cpu")
+                ref_mask = torch.bernoulli(probs) == 1.0
+                arrays[f"in.{mode}.ref_mask.{k}"] = ref_mask.numpy()
+                arrays[f"in.{mode}.phase.{k}"] = torch.rand(int(ref_mask.sum())).numpy()
+                assert 0 < int(ref_mask.sum()) < len(reset_indices)
+            torch.manual_seed(800 + k)
+            env.reset(reset_indices)
+            out = {
+                "rigid_body_state": env._rigid_body_state.view(N, 24, 13), "root_states": env._humanoid_root_states,
+                "dof_state": env._dof_state.view(N, 69, 2), "obs": env.obs_buf, "progress": env.progress_buf,
+                "reset": env.reset_buf, "terminate": env._terminate_buf, "motion_start_times": env._motion_start_times,
+                "motion_start_times_offset": env._motion_start_times_offset, "global_offset": env._global_offset,
+            }  # fmt: skip
+            arrays.update({f"out.{mode}.reset.{k}.{n}": v.detach().numpy().copy() for n, v in out.items()})
+        for n in ("state", "dof_state", "dof_force"):
+            for k in range(K):
+                arrays[f"in.{mode}.{n}.{k}"] = rec[n][k].numpy()
+        for k in range(K):
+            arrays[f"out.{mode}.pd_target.{k}"] = rec["pd_target"][k].numpy()
+    save("env_reset_modes", arrays)
 
 
 def synth_build_clips(tree_parents, seed=5, shapes=((20, 30), (45, 30), (3, 30), (33, 60), (12, 30), (2, 30))):
@@ -786,3 +858,4 @@ if __name__ == "__main__":
     case_episode()
     case_motion_build()
     case_env_rollout()
+    case_env_reset_modes()

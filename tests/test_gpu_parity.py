@@ -1749,6 +1749,111 @@ def test_env_rollout_vs_reference_step_and_reset(golden):
     replay_env_rollout(g, _ShimUnderReplay(g), read=lambda t: t.cpu(), tol=OBS_TOL, dof_tol=DOF_DERIVED_TOL)
 
 
+class _ShimUnderResetModes(_ShimUnderReplay):
+    """The shim in StateInit.Default / Hybrid (AMP off), behind conftest.replay_env_reset_modes.  ``route``: the reset
+    of the recorded indices through ``reset(env_ids)``, through ``reset_done()`` (device-side mask = reset_buf), or
+    inside the step (``auto_reset``: the reset rides behind the step launch, the replay's reset() is a no-op)."""
+
+    def __init__(self, g, mode, route):
+        from humanoid_b200 import HumanoidPHC
+
+        clock = clock_from_golden(g)
+        N = clock.progress_buf.shape[0]
+        self.g, self.mode, self.route, self.k = g, mode, route, 0
+        self.env = env = HumanoidPHC(
+            MotionLib(lib_from_golden(g), device=DEV), N, device=DEV, use_power_reward=True,
+            rew_power_coef=float(g.inp("rew_power_coef")), termination_distance=float(g.inp("termination_distance")),
+        )  # fmt: skip
+        env.set_clock(clock.to(DEV))
+        env._pd_action_offset.copy_(g.inp("pd_action_offset"))
+        env._pd_action_scale.copy_(g.inp("pd_action_scale"))
+        env.state_init = mode.lower()
+        env.hybrid_init_prob = float(g.inp("hybrid_init_prob"))
+        env._initial_humanoid_root_states.copy_(g.inp("initial_root_states"))
+        env._initial_dof_pos.copy_(g.inp("initial_dof_pos"))
+        env._initial_dof_vel.copy_(g.inp("initial_dof_vel"))
+        if route == "auto_reset":
+            env.enable_auto_reset(True)
+
+    def _by_env(self, k):
+        """The recorded draws of reset k, scattered to [N] (what the device-side routes take)."""
+        g, mode, N = self.g, self.mode, self.env.num_envs
+        rows = g.inp(f"{mode}.reset_indices.{k}")
+        dmask, phase = torch.zeros(N, dtype=torch.bool), torch.zeros(N)
+        if mode == "Default":
+            dmask[rows] = True
+        else:
+            ref = g.inp(f"{mode}.ref_mask.{k}")
+            dmask[rows] = ~ref
+            phase[rows[ref]] = g.inp(f"{mode}.phase.{k}")
+        return cuda(phase), cuda(dmask)
+
+    def step(self, actions, physics):
+        pd = self.env._action_to_pd_targets(cuda(actions), freeze_hand=True, freeze_toe=True)
+        physics(self)
+        if self.route == "auto_reset":
+            phase, dmask = self._by_env(self.k)
+            self.env.step(cuda(actions), phase_by_env=phase, default_mask_by_env=dmask)
+            self.after = {n: getattr(self.env, n).clone() for n in ("obs_buf", "progress_buf", "reset_buf", "_terminate_buf")}
+            # the replay compares the step's own outputs first: the flags live in extras, obs / progress of the envs that
+            # were reset in the same launch are checked after the replay's reset()
+            rows = cuda(self.g.inp(f"{self.mode}.reset_indices.{self.k}"))
+            assert torch.equal(torch.nonzero(self.env.extras["reset"]).squeeze(-1), rows)
+        else:
+            self.env.step(cuda(actions))
+        return pd
+
+    def reset(self, env_ids, phase, default_mask):
+        if self.route == "reset":
+            self.env.reset(cuda(env_ids), cuda(phase), cuda(default_mask) if self.mode == "Hybrid" else None)
+        elif self.route == "reset_done":
+            ph, dm = self._by_env(self.k)
+            self.env.reset_done(ph, dm)
+        self.k += 1
+
+
+@pytest.mark.parametrize("route", ["reset", "reset_done", "auto_reset"])
+@pytest.mark.parametrize("mode", ["Default", "Hybrid"])
+def test_env_reset_modes_vs_reference(golden, mode, route):
+    """StateInit.Default / StateInit.Hybrid (envs/humanoid_phc.py:678-745) against a recording of the reference's own
+    HumanoidPHC.step / reset in those modes, through all three reset routes of the shim."""
+    from conftest import replay_env_reset_modes
+
+    g = golden("env_reset_modes")
+    shim = _ShimUnderResetModes(g, mode, route)
+    if route != "auto_reset":
+        assert replay_env_reset_modes(g, shim, mode, read=lambda t: t.cpu(), tol=OBS_TOL, dof_tol=DOF_DERIVED_TOL) == 3
+        return
+    # auto_reset: step + reset are one call, so the per-step checks of the replay cannot see the pre-reset rows of the
+    # envs that were reset; compare the untouched envs with the step record and everything with the reset record
+    K = 3
+    for k in range(K):
+        def physics(e, k=k):
+            e.write_sim(g.inp(f"{mode}.state.{k}"), g.inp(f"{mode}.dof_state.{k}"), g.inp(f"{mode}.dof_force.{k}"))
+
+        shim.step(g.inp(f"{mode}.actions.{k}"), physics)
+        env = shim.env
+        rows = g.inp(f"{mode}.reset_indices.{k}")
+        keep = torch.ones(env.num_envs, dtype=torch.bool)
+        keep[rows] = False
+        s = lambda n, k=k: g.out(f"{mode}.step.{k}.{n}")  # noqa: E731
+        r = lambda n, k=k: g.out(f"{mode}.reset.{k}.{n}")  # noqa: E731
+        assert_equal_exact(env.extras["reset"].cpu(), s("reset"), f"reset flags[{k}]")
+        assert_equal_exact(env.extras["terminate"].cpu(), s("terminate"), f"terminate flags[{k}]")
+        assert_close(env.rew_buf.cpu(), s("rew"), what=f"rew[{k}]", **OBS_TOL)
+        assert_close(env.obs_buf.cpu()[keep], s("obs")[keep], what=f"obs of the envs not reset[{k}]", **OBS_TOL)
+        for name, attr in (("progress", "progress_buf"), ("reset", "reset_buf"), ("terminate", "_terminate_buf"),
+                           ("motion_start_times", "_motion_start_times"), ("global_offset", "_global_offset"),
+                           ("motion_start_times_offset", "_motion_start_times_offset")):  # fmt: skip
+            assert_equal_exact(getattr(env, attr).cpu(), r(name), f"{name} after reset[{k}]")
+        sim, root, dof = shim.read_sim()
+        assert_close(sim.cpu(), r("rigid_body_state"), what=f"rigid_body_state after reset[{k}]", **OBS_TOL)
+        assert_close(root.cpu()[rows], r("root_states")[rows], what=f"root_states after reset[{k}]", **OBS_TOL)
+        assert_close(dof.cpu()[rows], r("dof_state")[rows], what=f"dof_state after reset[{k}]", **DOF_DERIVED_TOL)
+        assert_close(env.obs_buf.cpu(), r("obs"), what=f"obs after reset[{k}]", **OBS_TOL)
+        shim.k += 1
+
+
 # ---------------------------------------------------------------------------------------
 # motion-library build (phc_motion_build) against the reference's own load_motions
 # ---------------------------------------------------------------------------------------

@@ -146,6 +146,20 @@ def test_env_rollout_vs_reference_step_and_reset(golden):
     assert sum(int(g.out(f"step.{k}.terminate").sum()) for k in range(5)) > 0
 
 
+@pytest.mark.parametrize("mode", ["Default", "Hybrid"])
+def test_env_reset_modes_vs_reference(golden, mode):
+    """StateInit.Default / StateInit.Hybrid (envs/humanoid_phc.py:678-745): oracle.OracleEnv against a recording of the
+    reference's own HumanoidPHC.step / reset in those modes."""
+    from conftest import replay_env_reset_modes
+    from util_cpu import oracle_env_from_golden
+
+    g = golden("env_reset_modes")
+    env = oracle_env_from_golden(g, use_amp_obs=False)
+    env.initial_root_states, env.initial_dof_pos = g.inp("initial_root_states"), g.inp("initial_dof_pos")
+    env.initial_dof_vel = g.inp("initial_dof_vel")
+    assert replay_env_reset_modes(g, env, mode) == 3
+
+
 def test_fixtures_exercise_both_flag_values(golden):
     seen_reset, seen_term, seen_pass = set(), set(), set()
     for case in STEP_CASES:

@@ -33,6 +33,10 @@ VARIANTS = [
     ("+ bookkeeping + reset in the step, termination out of reach (clip ends only)", dict(ep=True, reset=True, far=True)),
     ("+ bookkeeping + reset + moments + normaliser bf16 (everything)", dict(ep=True, reset=True, far=True, moments=2, norm=torch.bfloat16)),
 ]
+if os.environ.get("TERM_DISTS"):  # the in-step reset at intermediate flag rates: termination distances in metres
+    VARIANTS = [("+ episode bookkeeping", dict(ep=True))] + [
+        (f"+ bookkeeping + reset in the step, termination distance {d} m", dict(ep=True, reset=True, term=float(d)))
+        for d in os.environ["TERM_DISTS"].split(",")]
 for name, v in VARIANTS:
     capi.phc_set_option(_cabi.OPT_MOMENTS_BULK, 1 if v.get("moments") == 1 else 0)
     envs, states = [], []
@@ -50,6 +54,8 @@ for name, v in VARIANTS:
                 setattr(env, k, getattr(first, k))
         if v.get("far"):
             env.set_termination_distances(torch.full((24,), 1e6, device=dev))
+        if v.get("term"):
+            env.set_termination_distances(torch.full((24,), v["term"], device=dev))
         if v.get("norm") is not None:
             env.set_obs_normalizer(RunningNorm(934, device=dev), dtype=v["norm"])
         if v.get("ep"):

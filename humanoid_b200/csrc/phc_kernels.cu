@@ -3506,7 +3506,7 @@ static int g_moments_bulk = -1;  // PHC_OPT_MOMENTS_BULK / env PHC_MOMENTS_BULK=
 static int g_persist = -1;       // PHC_OPT_STEP_PERSIST / env PHC_STEP_PERSIST: 0 never, 1 from g_persist_min envs on (default), 2 always,
                                  // 3 always and the 4-slot / 4-blocks-per-SM instantiation
 static int g_persist_pdl = 1;
-static int64_t g_persist_min = 16384;
+static int64_t g_persist_min = 10240;  // measured crossover between 8192 (K6-fast 13.9 us, persistent 15.5) and 10240 (19.95 / 18.49)
 static int64_t g_persist_min_moments = 8192;  // with obs_moments: K6-fast pays 1868 L2 adds per four envs
 
 template <typename Kern>

@@ -315,7 +315,7 @@ typedef struct PhcStepArgs {
 #define PHC_STEP_OBS_FLAGS_SET 0x80000000u
 
 /* Kernel selection (all bit-identical): T == 1 on one AoS-13 sim tensor with a dense 16-B aligned obs_buf runs the
- * single-wave TMA kernel, or — from 16384 envs on, when none of the optional epilogues is asked for — the persistent
+ * single-wave TMA kernel, or — from 10240 envs on, when none of the optional epilogues is asked for — the persistent
  * warp-specialised kernel, whose blocks draw env tiles from a device-side counter owned by `lib` (256 counter slots used
  * round robin, each left zero by the launch that used it: launches of one PhcLib may overlap on different streams as
  * long as fewer than 256 of them are in flight or captured in concurrently replayed graphs); T > 1 runs the pipelined
@@ -412,7 +412,7 @@ PHC_API int phc_reset_envs(const PhcLib* lib, const PhcResetArgs* args, int64_t 
                                         env are worked on in pairs; 1: the single-group pipeline, kept as the cross-check */
 #define PHC_OPT_MOMENTS_BULK 6        /* 1: the T = 1 kernel's moments epilogue (obs_moments) hands each block's 1868 partial sums to the TMA
                                         engine as three bulk fp64 reductions; 0 (default, measured a little faster): one atomic per sum */
-#define PHC_OPT_STEP_PERSIST 7        /* the persistent warp-specialised T = 1 kernel for multi-wave grids: 1 (default) from 16384 envs on
+#define PHC_OPT_STEP_PERSIST 7        /* the persistent warp-specialised T = 1 kernel for multi-wave grids: 1 (default) from 10240 envs on
                                         (env PHC_STEP_PERSIST_MIN), 0 never, 2 always (tests), 3 always with four
                                         frame slots per env and four blocks per SM instead of three and five (comparison) */
 PHC_API int phc_set_option(int key, int value);

@@ -114,6 +114,30 @@ def test_argument_validation_returns_codes(lib):
     assert lib.phc_calc_frame_blend(None, None, None, None, 5, None, None, None, None) == -1
     assert lib.phc_obs_moments(None, 4, 4, 2, None, None) == -2  # stride < cols
     assert lib.phc_imitation_obs(None, 0, None, 0, None, None, 3, 0, 1, 6, None, 0, None) == -2  # T < 1
+    # phc_reset_envs: the StateInit modes are validated before anything is launched
+    r = _cabi.PhcResetArgs()
+    V = _cabi.PhcView
+    r.body = _cabi.PhcBodyState(V(4096, 312, 13), V(4096 + 12, 312, 13), V(4096 + 28, 312, 13), V(4096 + 40, 312, 13), 24)
+    for k in ("progress_buf", "reset_buf", "terminate_buf", "motion_start_times", "motion_start_times_offset",
+              "sampled_motion_ids", "obs_buf", "humanoid_root_states", "dof_pos", "dof_vel", "env_mask"):
+        setattr(r, k, 4096)
+    r.root_stride, r.dof_stride, r.dof_elem_stride, r.obs_stride, r.time_steps, r.dt = 13, 138, 2, 934, 1, 1 / 30
+    r.state_init = 7
+    assert lib.phc_reset_envs(h, C.byref(r), 8, None) == -4  # no such StateInit
+    r.state_init = _cabi.STATE_INIT_RANDOM
+    assert lib.phc_reset_envs(h, C.byref(r), 8, None) == -1  # RANDOM needs the caller's uniform numbers
+    r.state_init = _cabi.STATE_INIT_HYBRID
+    r.phase = 4096
+    assert lib.phc_reset_envs(h, C.byref(r), 8, None) == -1  # HYBRID needs the Bernoulli mask ...
+    r.default_mask = 4096
+    assert lib.phc_reset_envs(h, C.byref(r), 8, None) == -1  # ... and the initial buffers
+    r.initial_root_states = r.initial_dof_pos = r.initial_dof_vel = 4096
+    r.initial_root_stride, r.initial_dof_stride = 13, 60
+    assert lib.phc_reset_envs(h, C.byref(r), 8, None) == -2  # 69 dofs per row
+    r.state_init = _cabi.STATE_INIT_DEFAULT
+    r.default_mask = None
+    assert lib.phc_reset_envs(h, C.byref(r), 8, None) == -2
+    assert lib.phc_reset_envs(h, C.byref(r), -1, None) == -2
     lib.phc_lib_destroy(h)
     lib.phc_lib_destroy(None)
 

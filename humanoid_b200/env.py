@@ -55,6 +55,41 @@ def build_body_ids_tensor(body_names: Sequence[str], subset: Sequence[str], devi
     return torch.tensor([body_names.index(n) for n in subset], dtype=torch.long, device=device)
 
 
+def build_pd_action_offset_scale(dof_limits_lower, dof_limits_upper, bias_offset: bool = False,
+                                 has_smpl_pd_offset: bool = False, has_upright_start: bool = True):
+    """``HumanoidPHC._build_pd_action_offset_scale`` (envs/humanoid_phc.py:385-457): the ``_pd_action_offset`` /
+    ``_pd_action_scale`` that ``_action_to_pd_targets`` applies, from the asset's joint limits — host logic in the
+    reference too (numpy over 23 three-dof joints), run once at start-up.  Per joint the range becomes
+    +-min(1.2 max|limit|, pi) (with ``bias_offset``: mid +- 0.7 (high - low)); the knees' y axis gets scale 5
+    (:443-446); ``has_smpl_pd_offset`` biases the shoulders.  Returns two CPU fp32 tensors [69]."""
+    import numpy as np
+
+    lim_low = torch.as_tensor(dof_limits_lower).detach().cpu().numpy().astype(np.float32).copy()
+    lim_high = torch.as_tensor(dof_limits_upper).detach().cpu().numpy().astype(np.float32).copy()
+    dof_names = BODY_NAMES[1:]
+    for j in range(len(dof_names)):
+        sl = slice(3 * j, 3 * j + 3)
+        if not bias_offset:
+            scale = min(1.2 * max(np.max(np.abs(lim_low[sl])), np.max(np.abs(lim_high[sl]))), np.pi)
+            lim_low[sl], lim_high[sl] = -scale, scale
+        else:
+            mid = 0.5 * (lim_high[sl] + lim_low[sl])
+            scale = 0.7 * (lim_high[sl] - lim_low[sl])
+            lim_low[sl], lim_high[sl] = mid - scale, mid + scale
+    offset = torch.from_numpy(0.5 * (lim_high + lim_low)).float()
+    scale = torch.from_numpy(0.5 * (lim_high - lim_low)).float()
+    scale[dof_names.index("L_Knee") * 3 + 1] = 5  # "Modified SMPL to give stronger knee"
+    scale[dof_names.index("R_Knee") * 3 + 1] = 5
+    if has_smpl_pd_offset:
+        ls, rs = dof_names.index("L_Shoulder") * 3, dof_names.index("R_Shoulder") * 3
+        if has_upright_start:
+            offset[ls], offset[rs] = -np.pi / 2, np.pi / 2
+        else:
+            offset[ls], offset[ls + 2] = -np.pi / 6, -np.pi / 2
+            offset[rs], offset[rs + 2] = -np.pi / 3, np.pi / 2
+    return offset, scale
+
+
 class HumanoidPHC:
     def __init__(
         self,
@@ -596,6 +631,14 @@ class HumanoidPHC:
     # ------------------------------------------------------------------------------------
     # pre-physics: actions -> PD targets (humanoid_phc.py:105-128, 1218-1228)
     # ------------------------------------------------------------------------------------
+    def build_pd_action_offset_scale(self, dof_limits_lower, dof_limits_upper, bias_offset: bool = False,
+                                     has_smpl_pd_offset: bool = False, has_upright_start: bool = True):
+        """``_build_pd_action_offset_scale`` (:385-457) into ``self._pd_action_offset`` / ``_pd_action_scale``."""
+        offset, scale = build_pd_action_offset_scale(dof_limits_lower, dof_limits_upper, bias_offset, has_smpl_pd_offset,
+                                                     has_upright_start)  # fmt: skip
+        self._pd_action_offset, self._pd_action_scale = offset.to(self.device), scale.to(self.device)
+        return self._pd_action_offset, self._pd_action_scale
+
     def _action_to_pd_targets(self, action: torch.Tensor, res_action: bool = False, ref_dof_pos=None,
                               freeze_hand: bool = False, freeze_toe: bool = False, clip: float = 0.0,
                               actions_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:  # fmt: skip

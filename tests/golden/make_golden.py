@@ -719,6 +719,32 @@ def case_env_reset_modes():
     save("env_reset_modes", arrays)
 
 
+def case_pd_offset_scale():
+    """``HumanoidPHC._build_pd_action_offset_scale`` (envs/humanoid_phc.py:385-457), the reference's own method run on
+    an instance built without ``__init__``: what ``_action_to_pd_targets`` scales the actions with, from the asset's
+    joint limits.  All four (bias_offset, has_smpl_pd_offset x has_upright_start) variants."""
+    import types
+
+    H = load_reference_env_module()
+    g = torch.Generator().manual_seed(61)
+    lo = -(torch.rand(69, generator=g) * 2.5 + 0.1)
+    hi = torch.rand(69, generator=g) * 2.5 + 0.1
+    arrays = {"in.dof_limits_lower": lo.numpy(), "in.dof_limits_upper": hi.numpy()}
+    for name, bias, smpl_off, upright in (("default", False, False, True), ("bias_offset", True, False, True),
+                                          ("smpl_pd_offset_upright", False, True, True),
+                                          ("smpl_pd_offset_not_upright", False, True, False)):  # fmt: skip
+        env = object.__new__(H.HumanoidPHC)
+        env.cfg = types.SimpleNamespace(device="cpu", robot=types.SimpleNamespace(
+            bias_offset=bias, has_smpl_pd_offset=smpl_off, has_upright_start=upright))
+        env.dof_limits_lower, env.dof_limits_upper = lo.clone(), hi.clone()
+        env._dof_offsets = np.linspace(0, 69, 24).astype(int)  # :220
+        env._build_pd_action_offset_scale()
+        arrays[f"out.{name}.offset"] = env._pd_action_offset.numpy()
+        arrays[f"out.{name}.scale"] = env._pd_action_scale.numpy()
+        arrays[f"in.{name}"] = np.asarray([bias, smpl_off, upright])
+    save("pd_offset_scale", arrays)
+
+
 def synth_build_clips(tree_parents, seed=5, shapes=((20, 30), (45, 30), (3, 30), (33, 60), (12, 30), (2, 30))):
     """Synthetic stand-ins for the AMASS pkl entries (scripts/phc_convert_amass_data.py:186-194):
     per clip ``root_trans_offset`` (torch f64), ``pose_aa`` (numpy f64 [B,72]), ``pose_quat_global``
@@ -859,3 +885,4 @@ if __name__ == "__main__":
     case_motion_build()
     case_env_rollout()
     case_env_reset_modes()
+    case_pd_offset_scale()

@@ -160,6 +160,21 @@ def test_env_reset_modes_vs_reference(golden, mode):
     assert replay_env_reset_modes(g, env, mode) == 3
 
 
+def test_pd_action_offset_scale_vs_reference(golden):
+    """The shim's host-side ``build_pd_action_offset_scale`` against the reference's own ``_build_pd_action_offset_scale``
+    (envs/humanoid_phc.py:385-457) on random joint limits, all config variants.  1e-6: the reference multiplies numpy
+    float32 scalars by Python floats, which NumPy 1 did in float64 and NumPy 2 does in float32."""
+    from humanoid_b200.env import build_pd_action_offset_scale
+
+    g = golden("pd_offset_scale")
+    for name in ("default", "bias_offset", "smpl_pd_offset_upright", "smpl_pd_offset_not_upright"):
+        bias, smpl_off, upright = (bool(x) for x in g.inp(name))
+        off, sc = build_pd_action_offset_scale(g.inp("dof_limits_lower"), g.inp("dof_limits_upper"), bias, smpl_off, upright)
+        assert_close(off, g.out(f"{name}.offset"), what=f"{name} offset", rtol=1e-6, atol=1e-6)
+        assert_close(sc, g.out(f"{name}.scale"), what=f"{name} scale", rtol=1e-6, atol=1e-6)
+        assert float(sc[1 * 3 + 1]) == 5.0 and float(sc[5 * 3 + 1]) == 5.0  # L_Knee, R_Knee: dofs 1 and 5, y axis
+
+
 def test_fixtures_exercise_both_flag_values(golden):
     seen_reset, seen_term, seen_pass = set(), set(), set()
     for case in STEP_CASES:

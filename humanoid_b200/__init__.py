@@ -16,7 +16,7 @@ from .common import (  # noqa: F401
     compute_imitation_observations_v7,
     compute_imitation_reward,
 )
-from .env import HumanoidPHC  # noqa: F401
+from .env import HumanoidPHC, build_pd_action_offset_scale  # noqa: F401
 from .motion_lib import MotionLib  # noqa: F401
 from .puffer_env import PHCPufferEnv  # noqa: F401
 from .running_norm import RunningNorm  # noqa: F401
@@ -33,4 +33,5 @@ __all__ = [
     "compute_humanoid_im_reset",
     "build_amp_observations_smpl",
     "dof_subset_smpl",
+    "build_pd_action_offset_scale",
 ]

@@ -1059,6 +1059,7 @@ struct StepParams {
   uint8_t* term;
   double* moments;
   int moment_buckets;  // >= 1: moments is [buckets][2W]; block b adds into bucket b % buckets
+  int multi_prefetch;  // K6-multi2: L2-prefetch the frame rows two query iterations ahead
   int moments_bulk;    // the T = 1 kernel hands its partials to TMA bulk reductions instead of issuing atomics
   // episode bookkeeping of the pufferlib wrapper fused into the step (clean_pufferl/env.py:121-159), off when ep_returns is NULL
   uint8_t *ep_terminals, *ep_truncations, *ep_masks;
@@ -2996,6 +2997,15 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
     mbar_expect_tx(&S.bar[q & 1], bytes);
     bulk_g2s(&S.frames[le][(q & 1) * 2][0], p.L.packed + S.row0[q][le] * FRAME_FLOATS, bytes, &S.bar[q & 1]);
   };
+  // ... and of a query two iterations ahead -> L2: under load a 2.5 KB copy from DRAM takes longer than one query
+  // iteration (a sixth of the stall samples sat on the frame mbarrier, profiles/r2s2_multi2_T10_n16384_ncu.md); the copy
+  // issued an iteration later then finds its rows in L2
+  auto prefetch_frames = [&](int le, int q) {
+    if (!p.multi_prefetch) return;
+    const uint32_t bytes = (uint32_t)(1 + S.two[q][le]) * (uint32_t)(FRAME_FLOATS * 4);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p.L.packed + S.row0[q][le] * FRAME_FLOATS), "r"(bytes)
+                 : "memory");
+  };
 
   // ---- phase 0 (whole block) ----------------------------------------------------------------
   if (tid < 64) {  // two warps share the (env, query) pairs: one round of dependent clip-metadata loads for T <= 15
@@ -3035,6 +3045,8 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
       bulk_g2s(S.sim + tid * ROW13, p.body.pos.ptr + (env0 + tid) * p.body.pos.stride_env, ROW13 * 4, &S.bar_sim);
       issue_frames(tid, 0);
       issue_frames(tid, 1);
+      if (T >= 2) prefetch_frames(tid, 2);
+      if (T >= 3) prefetch_frames(tid, 3);
     }
     if (tid < 32) __syncwarp();
     if (tid == 0) {
@@ -3086,7 +3098,10 @@ __global__ void __launch_bounds__(2 * MULTI_EPB* J24, 4) step_multi2_kernel(cons
     fence_proxy_async();                    // frame reads -> the copy that refills the half
     group_sync(g);                          // R
     if (q + 2 <= T && lt < 32) {
-      if (lt < nvalid) issue_frames(lt, q + 2);
+      if (lt < nvalid) {
+        issue_frames(lt, q + 2);
+        if (q + 4 <= T) prefetch_frames(lt, q + 4);
+      }
       __syncwarp();
       if (lt == 0) mbar_arrive(&S.bar[g]);
     }
@@ -3905,6 +3920,14 @@ static int step_fill_params(const PhcLib* lib, const PhcStepArgs* a, int64_t n, 
   p.moments = a->obs_moments;
   p.moment_buckets = a->obs_moments_buckets > 1 ? a->obs_moments_buckets : 1;
   p.moments_bulk = 0;
+  {
+    static int mp = -1;  // env PHC_MULTI_PREFETCH=0|1 (default 1)
+    if (mp < 0) {
+      const char* w = getenv("PHC_MULTI_PREFETCH");
+      mp = (w && w[0] == '0') ? 0 : 1;
+    }
+    p.multi_prefetch = mp;
+  }
   p.ep_terminals = a->ep_terminals;
   p.ep_truncations = a->ep_truncations;
   p.ep_masks = a->ep_masks;
